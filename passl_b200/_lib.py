@@ -1,0 +1,75 @@
+"""ctypes binding of the C-ABI library (include/passl_b200.h).
+
+The library is the product: there is no Python / CPU fallback.  Importing a kernel wrapper without the built
+``libpassl_b200.so`` raises immediately (run ``python __graft_entry__.py`` to build it).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpassl_b200.so")
+
+c_void_p, c_int, c_ll, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
+
+# name -> (restype, [argtypes]); mirrors include/passl_b200.h one to one
+SIGNATURES = {
+    "passl_b200_version": (c_int, []),
+    "passl_b200_gemm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll,
+                                     c_int, c_int, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p, c_void_p,
+                                     c_void_p]),
+    "passl_b200_conv2d_fwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 9 +
+                                   [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "passl_b200_conv2d_dgrad_workspace_bytes": (c_ll, [c_int] * 4),
+    "passl_b200_conv2d_dgrad_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 10 + [c_void_p]),
+    "passl_b200_conv2d_wgrad_bf16": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 10 + [c_void_p]),
+    "passl_b200_simce_workspace_bytes": (c_ll, [c_int, c_int]),
+    "passl_b200_simce_fwd_f32": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_float,
+                                         c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll,
+                                         c_void_p]),
+    "passl_b200_simce_bwd_f32": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_float,
+                                         c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll,
+                                         c_void_p]),
+    "passl_b200_l2norm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
+    "passl_b200_l2norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                                      c_void_p]),
+    "passl_b200_queue_enqueue": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "passl_b200_ema_update": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_ll, c_void_p]),
+    "passl_b200_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_ll, c_void_p]),
+    "passl_b200_cast_bf16_to_f32": (c_int, [c_void_p, c_void_p, c_ll, c_void_p]),
+}
+
+_ERRORS = {-1: "bad argument / contract violation", -2: "unsupported configuration", -3: "TMA tensor-map encode failed",
+           -4: "workspace too small"}
+
+
+class PasslB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libpassl_b200.so and attach prototypes.  Raises if the library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PasslB200Error(
+            "passl_b200: %s is missing — the CUDA extension is mandatory (no CPU fallback). "
+            "Build it with `python __graft_entry__.py`." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(code, what):
+    if code == 0:
+        return
+    if code < 0:
+        raise PasslB200Error("%s: %s (code %d)" % (what, _ERRORS.get(code, "error"), code))
+    raise PasslB200Error("%s: CUDA error %d" % (what, code))

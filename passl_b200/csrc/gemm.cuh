@@ -1,0 +1,374 @@
+// passl_b200 — persistent warp-specialised tcgen05 GEMM / implicit-GEMM kernel for sm_100a.
+//
+//   D[m, n] = epilogue( alpha * sum_k A[m, k] * B[n, k] )         bf16 inputs, fp32 accumulation in TMEM
+//
+// One kernel serves every dense contraction on the PASSL hot path:
+//   * Linear fwd / dgrad / wgrad (ViT qkv/proj/fc1/fc2, necks, patch-embed, 1x1 convs)      -> MAT operands
+//   * 3x3 / strided convolution fwd + dgrad as implicit GEMM over NHWC activations             -> PATCH_K  A operand
+//   * convolution wgrad (K = output pixels, both operands channel-contiguous)                  -> PATCH_MN operands
+//
+// Structure (one CTA per SM, 192 threads):
+//   warp 0 lane 0 : TMA producer  — cp.async.bulk.tensor into a STAGES-deep smem ring (SWIZZLE_128B)
+//   warp 1 lane 0 : MMA issuer    — tcgen05.mma cta_group::1, M=128, N=BN, K=16 per instruction
+//   warps 2..5    : epilogue      — tcgen05.ld TMEM->regs, bias/activation/residual, bf16/fp32 store
+// TMEM holds two BN-column accumulators so the epilogue of tile i overlaps the main loop of tile i+1.
+#pragma once
+#include "common.cuh"
+
+namespace pb {
+
+enum OperandMode : int {
+  OP_MAT_K = 0,     // 2D matrix [rows, K], K contiguous            (tensor map dims: K, rows)
+  OP_MAT_MN = 1,    // 2D matrix [K, rows], rows contiguous         (tensor map dims: rows, K)
+  OP_PATCH_K = 2,   // NHWC activation patch, channels = K slice    (tensor map dims: C, W, H, N)
+  OP_PATCH_MN = 3,  // NHWC activation patch, pixels = K, channels = rows
+};
+enum ActMode : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_QUICKGELU = 3 };
+
+constexpr int kMaxTaps = 12;
+
+struct PatchGeom {
+  int TN, TH, TW;    // patch box: images x rows x cols  (TN*TH*TW <= 128)
+  int nb, hb, wb;    // number of patches along each axis
+  int Nimg, Ho, Wo;  // bounds of the pixel grid the patches enumerate
+};
+
+struct GemmOperand {
+  CUtensorMap maps[4];  // [0] always valid; [1..3] parity maps for stride-2 sources
+  int mode;
+  int cchunks;          // PATCH_K: 64-channel chunks per tap
+  int tx_bytes;         // bytes one stage load of this operand deposits
+  int ntaps;
+  signed char dh[kMaxTaps], dw[kMaxTaps], map[kMaxTaps];  // per-tap coordinate shift + parity map
+};
+
+struct GemmParams {
+  GemmOperand a, b;
+  PatchGeom geom;       // used when an operand is PATCH_* or out_pixel != 0
+  int M, N;             // logical output extent (rows, cols)
+  int m_blocks, n_blocks, splits;
+  int k_iters;          // total pipeline iterations over K (all taps / chunks / pixel patches)
+  int k_steps;          // UMMA (K=16) steps per pipeline iteration
+  // N-tile decode for wgrad: n_blk -> (tap, channel block)
+  int n_blocks_per_tap; // 0 => plain
+  int n_per_tap;        // Cin (columns per tap) when n_blocks_per_tap > 0
+  // epilogue
+  void* out;
+  long long ldc;        // elements between consecutive output rows (pixels)
+  int out_fp32;         // 0: bf16, 1: fp32
+  int atomic_add;       // fp32 only: red.add instead of store (split-K / wgrad)
+  int out_pixel;        // 1: row -> NHWC pixel address through geom + (OH, OW, osh, osw, oh0, ow0)
+  int OH, OW, osh, osw, oh0, ow0;
+  const float* bias;            // [N] or null
+  const __nv_bfloat16* residual;  // same addressing as out (bf16) or null
+  int act;
+  float alpha;
+  // optional per-column statistics of the stored value (BatchNorm batch stats): sum and sum of squares
+  float* col_sum;
+  float* col_sqsum;
+};
+
+template <int BN, int BK, bool A_MN, bool B_MN>
+struct GemmSmem {
+  static constexpr int BM = 128;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BUDGET = 196 * 1024;
+  static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+};
+
+__device__ __forceinline__ void decode_patch(const PatchGeom& g, int idx, int& n0, int& h0, int& w0) {
+  int iw = idx % g.wb;
+  int t = idx / g.wb;
+  int ih = t % g.hb;
+  int in_ = t / g.hb;
+  n0 = in_ * g.TN;
+  h0 = ih * g.TH;
+  w0 = iw * g.TW;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == ACT_RELU) return fmaxf(v, 0.f);
+  if (act == ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+  if (act == ACT_QUICKGELU) return v / (1.f + __expf(-1.702f * v));
+  return v;
+}
+
+// Issue the TMA loads of one pipeline stage for one operand.
+//   row_blk : index of the 128-row (A) / BN-row (B) block, or patch index in PATCH_K mode
+//   kit     : pipeline iteration
+template <int ROWS, int BK>
+__device__ __forceinline__ void issue_operand_load(const GemmOperand& op, const PatchGeom& g, uint8_t* dst,
+                                                   uint64_t* bar, int row0, int patch_idx, int tap_fixed,
+                                                   int kit) {
+  if (op.mode == OP_MAT_K) {
+    tma_load_2d(dst, &op.maps[0], bar, kit * BK, row0);
+  } else if (op.mode == OP_MAT_MN) {
+#pragma unroll
+    for (int j = 0; j < ROWS / 64; ++j) tma_load_2d(dst + j * (BK * 128), &op.maps[0], bar, row0 + 64 * j, kit * BK);
+  } else if (op.mode == OP_PATCH_K) {
+    int tap = kit / op.cchunks;
+    int cc = kit - tap * op.cchunks;
+    int n0, h0, w0;
+    decode_patch(g, patch_idx, n0, h0, w0);
+    tma_load_4d(dst, &op.maps[op.map[tap]], bar, cc * 64, w0 + op.dw[tap], h0 + op.dh[tap], n0);
+  } else {  // OP_PATCH_MN: K = pixels of patch `kit`, rows = channels starting at row0
+    int n0, h0, w0;
+    decode_patch(g, kit, n0, h0, w0);
+    int tap = tap_fixed;
+#pragma unroll
+    for (int j = 0; j < ROWS / 64; ++j)
+      tma_load_4d(dst + j * (BK * 128), &op.maps[op.map[tap]], bar, row0 + 64 * j, w0 + op.dw[tap],
+                  h0 + op.dh[tap], n0);
+  }
+}
+
+template <int BN, int BK, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+  using S = GemmSmem<BN, BK, A_MN, B_MN>;
+  constexpr int STAGES = S::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const uint32_t warp = warp_id();
+  const uint32_t lane = lane_id();
+  const int total_tiles = p.m_blocks * p.n_blocks * p.splits;
+
+  // PATCH_MN stages contain rows no TMA box ever writes (K padding) -> must be zero, not garbage.
+  if (p.a.mode == OP_PATCH_MN || p.b.mode == OP_PATCH_MN) {
+    uint4 z = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < STAGES * S::STAGE_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = z;
+    fence_proxy_async_smem();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.a.maps[0]);
+    tma_prefetch_desc(&p.b.maps[0]);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, S::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================= TMA producer =================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int split = tile % p.splits;
+        int rest = tile / p.splits;
+        int n_blk = rest % p.n_blocks;
+        int m_blk = rest / p.n_blocks;
+        int k_begin = (int)(((long long)split * p.k_iters) / p.splits);
+        int k_end = (int)(((long long)(split + 1) * p.k_iters) / p.splits);
+        int b_row0 = n_blk * BN, b_tap = 0;
+        if (p.n_blocks_per_tap > 0) {
+          b_tap = n_blk / p.n_blocks_per_tap;
+          b_row0 = (n_blk - b_tap * p.n_blocks_per_tap) * BN;
+        }
+        for (int kit = k_begin; kit < k_end; ++kit) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * S::STAGE_BYTES;
+          uint8_t* sb = sa + S::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(p.a.tx_bytes + p.b.tx_bytes));
+          issue_operand_load<128, BK>(p.a, p.geom, sa, &full_bar[stage], m_blk * 128, m_blk, 0, kit);
+          issue_operand_load<BN, BK>(p.b, p.geom, sb, &full_bar[stage], b_row0, n_blk, b_tap, kit);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ================= MMA issuer =================
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        int split = tile % p.splits;
+        int k_begin = (int)(((long long)split * p.k_iters) / p.splits);
+        int k_end = (int)(((long long)(split + 1) * p.k_iters) / p.splits);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kit = k_begin; kit < k_end; ++kit) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint32_t sb = sa + S::A_BYTES;
+          for (int k = 0; k < p.k_steps; ++k) {
+            // K-major: +32 B per 16-element K step inside the 128 B swizzle row.
+            // MN-major: +2048 B per 16 k-rows (two 8-row atoms); LBO = chunk stride (BK rows x 128 B).
+            uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * 2048, BK * 128, 1024)
+                               : make_smem_desc_sw128(sa + k * 32, 16, 1024);
+            uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * 2048, BK * 128, 1024)
+                               : make_smem_desc_sw128(sb + k * 32, 16, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (kit > k_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ================= epilogue warps (2..5) =================
+    const uint32_t q = warp & 3;  // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      int rest = tile / p.splits;
+      int n_blk = rest % p.n_blocks;
+      int m_blk = rest / p.n_blocks;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+
+      // row handled by this thread
+      const int r = q * 32 + lane;
+      bool row_ok;
+      long long row_off;   // element offset of the row start in out / residual
+      if (p.out_pixel) {
+        int n0, h0, w0;
+        decode_patch(p.geom, m_blk, n0, h0, w0);
+        int tw = r % p.geom.TW;
+        int t = r / p.geom.TW;
+        int th = t % p.geom.TH;
+        int tn = t / p.geom.TH;
+        int n = n0 + tn, h = h0 + th, w = w0 + tw;
+        row_ok = (tn < p.geom.TN) && (n < p.geom.Nimg) && (h < p.geom.Ho) && (w < p.geom.Wo);
+        row_off = (((long long)n * p.OH + (h * p.osh + p.oh0)) * p.OW + (w * p.osw + p.ow0)) * p.ldc;
+      } else {
+        int m = m_blk * 128 + r;
+        row_ok = m < p.M;
+        row_off = (long long)m * p.ldc;
+      }
+      int col0 = n_blk * BN;
+      int col_lim = p.N;  // exclusive bound on the logical column index
+      long long col_base = col0;
+      if (p.n_blocks_per_tap > 0) {
+        int tap = n_blk / p.n_blocks_per_tap;
+        int c0 = (n_blk - tap * p.n_blocks_per_tap) * BN;
+        col0 = c0;
+        col_lim = p.n_per_tap;
+        col_base = (long long)tap * p.n_per_tap + c0;
+      }
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((q * 32u) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_addr + c * 32, v);
+        tmem_ld_wait();
+        const int cc0 = col0 + c * 32;           // logical column of v[0] (within tap)
+        const long long oc0 = col_base + c * 32; // output column of v[0]
+        if (cc0 >= col_lim) break;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (cc0 + j < col_lim) f[j] += __ldg(p.bias + oc0 + j);
+        }
+        if (p.act != ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+        }
+        if (p.residual && row_ok) {
+          const __nv_bfloat16* rp = p.residual + row_off + oc0;
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            if (cc0 + j8 * 8 < col_lim) {
+              uint4 u = *reinterpret_cast<const uint4*>(rp + j8 * 8);
+              float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+              f[j8 * 8 + 0] += a0.x; f[j8 * 8 + 1] += a0.y; f[j8 * 8 + 2] += a1.x; f[j8 * 8 + 3] += a1.y;
+              f[j8 * 8 + 4] += a2.x; f[j8 * 8 + 5] += a2.y; f[j8 * 8 + 6] += a3.x; f[j8 * 8 + 7] += a3.y;
+            }
+          }
+        }
+        if (p.col_sum) {
+          // per-column batch statistics of the value that will be stored (rounded to bf16 if bf16 out)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = row_ok ? f[j] : 0.f;
+            if (!p.out_fp32) x = __bfloat162float(__float2bfloat16_rn(x));
+            float s = warp_sum(x);
+            float s2 = warp_sum(x * x);
+            if (lane == j && cc0 + j < col_lim) {
+              red_add_f32(p.col_sum + oc0 + j, s);
+              red_add_f32(p.col_sqsum + oc0 + j, s2);
+            }
+          }
+        }
+        if (row_ok) {
+          if (p.out_fp32) {
+            float* op = reinterpret_cast<float*>(p.out) + row_off + oc0;
+            if (p.atomic_add) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (cc0 + j < col_lim) red_add_f32(op + j, f[j]);
+            } else {
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4)
+                if (cc0 + j4 * 4 < col_lim)
+                  *reinterpret_cast<float4*>(op + j4 * 4) = make_float4(f[j4 * 4], f[j4 * 4 + 1], f[j4 * 4 + 2], f[j4 * 4 + 3]);
+            }
+          } else {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + row_off + oc0;
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8)
+              if (cc0 + j8 * 8 < col_lim) {
+                uint4 u;
+                u.x = pack_bf16x2(f[j8 * 8 + 0], f[j8 * 8 + 1]);
+                u.y = pack_bf16x2(f[j8 * 8 + 2], f[j8 * 8 + 3]);
+                u.z = pack_bf16x2(f[j8 * 8 + 4], f[j8 * 8 + 5]);
+                u.w = pack_bf16x2(f[j8 * 8 + 6], f[j8 * 8 + 7]);
+                *reinterpret_cast<uint4*>(op + j8 * 8) = u;
+              }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, S::TMEM_COLS);
+  }
+}
+
+}  // namespace pb

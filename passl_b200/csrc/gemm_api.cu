@@ -1,0 +1,368 @@
+// C-ABI launchers for the tcgen05 GEMM / implicit-GEMM convolution kernel (see gemm.cuh).
+#include "gemm.cuh"
+#include "host_utils.h"
+#include "../../include/passl_b200.h"
+
+#include <string.h>
+
+namespace pb {
+
+template <int BN, int BK, bool A_MN, bool B_MN>
+static int launch_gemm_t(const GemmParams& p, cudaStream_t st) {
+  using S = GemmSmem<BN, BK, A_MN, B_MN>;
+  auto kern = gemm_tcgen05_kernel<BN, BK, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    attr_set = true;
+  }
+  int tiles = p.m_blocks * p.n_blocks * p.splits;
+  int grid = tiles < num_sms() ? tiles : num_sms();
+  if (grid <= 0) return PB_OK;
+  kern<<<grid, 192, S::TOTAL, st>>>(p);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+static int launch_gemm(const GemmParams& p, int BN, int BK, bool a_mn, bool b_mn, cudaStream_t st) {
+#define PB_DISPATCH(bn)                                                                 \
+  if (BN == bn) {                                                                       \
+    if (BK == 128) return launch_gemm_t<bn, 128, true, true>(p, st);                    \
+    if (!a_mn && !b_mn) return launch_gemm_t<bn, 64, false, false>(p, st);              \
+    if (!a_mn && b_mn) return launch_gemm_t<bn, 64, false, true>(p, st);                \
+    if (a_mn && !b_mn) return launch_gemm_t<bn, 64, true, false>(p, st);                \
+    return launch_gemm_t<bn, 64, true, true>(p, st);                                    \
+  }
+  PB_DISPATCH(64)
+  PB_DISPATCH(128)
+  PB_DISPATCH(256)
+#undef PB_DISPATCH
+  return PB_ERR_UNSUPPORTED;
+}
+
+static int pick_bn(int m_blocks, int N) {
+  if (N <= 64) return 64;
+  if (N <= 128) return 128;
+  long long t256 = (long long)m_blocks * ((N + 255) / 256);
+  if (N % 256 == 0 && t256 >= num_sms()) return 256;
+  if (N >= 256 && t256 >= 2 * num_sms()) return 256;
+  return 128;
+}
+
+static int fill_mat_operand(GemmOperand& op, const void* base, bool mn_major, long long rows, long long K,
+                            long long ld, int block_rows, int BK) {
+  memset(&op, 0, sizeof(op));
+  uint64_t dims[2], strides[1];
+  uint32_t box[2];
+  strides[0] = (uint64_t)ld * 2;
+  if (!mn_major) {
+    op.mode = OP_MAT_K;
+    dims[0] = (uint64_t)K; dims[1] = (uint64_t)rows;
+    box[0] = 64; box[1] = (uint32_t)block_rows;
+  } else {
+    op.mode = OP_MAT_MN;
+    dims[0] = (uint64_t)rows; dims[1] = (uint64_t)K;
+    box[0] = 64; box[1] = (uint32_t)BK;
+  }
+  op.tx_bytes = block_rows * BK * 2;
+  op.ntaps = 1;
+  return make_tmap_bf16(&op.maps[0], base, 2, dims, strides, box);
+}
+
+static void set_epilogue(GemmParams& p, void* out, long long ldc, int out_fp32, int atomic_add, const float* bias,
+                         const void* residual, int act, float alpha, float* col_sum, float* col_sqsum) {
+  p.out = out; p.ldc = ldc; p.out_fp32 = out_fp32; p.atomic_add = atomic_add;
+  p.bias = bias; p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  p.act = act; p.alpha = alpha; p.col_sum = col_sum; p.col_sqsum = col_sqsum;
+}
+
+// ---- patch geometry ------------------------------------------------------------------------
+static void pick_patch(PatchGeom& g, int Nimg, int Ho, int Wo) {
+  g.Nimg = Nimg; g.Ho = Ho; g.Wo = Wo;
+  g.TW = Wo < 128 ? Wo : 128;
+  g.TH = 128 / g.TW; if (g.TH > Ho) g.TH = Ho; if (g.TH < 1) g.TH = 1;
+  g.TN = 1;
+  if (g.TH == Ho && g.TW == Wo) { g.TN = 128 / (g.TW * g.TH); if (g.TN > Nimg) g.TN = Nimg; if (g.TN < 1) g.TN = 1; }
+  g.wb = (Wo + g.TW - 1) / g.TW;
+  g.hb = (Ho + g.TH - 1) / g.TH;
+  g.nb = (Nimg + g.TN - 1) / g.TN;
+}
+
+static inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+static inline int posmod(int a, int b) { int m = a % b; return m < 0 ? m + b : m; }
+
+// 4D tensor maps over an NHWC tensor [N, H, W, C] (bf16). stride 1 -> one map; stride 2 -> 4 parity maps
+// viewing x[:, hp::2, wp::2, :].  Box {64, TW, TH, TN}.
+static int fill_patch_maps(GemmOperand& op, const void* base, int N, int H, int W, int C, int src_stride,
+                           const PatchGeom& g) {
+  uint32_t box[4] = {64, (uint32_t)g.TW, (uint32_t)g.TH, (uint32_t)g.TN};
+  if (src_stride == 1) {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+    return make_tmap_bf16(&op.maps[0], base, 4, dims, str, box);
+  }
+  if (src_stride != 2 || (H & 1) || (W & 1)) return PB_ERR_UNSUPPORTED;
+  for (int hp = 0; hp < 2; ++hp)
+    for (int wp = 0; wp < 2; ++wp) {
+      const char* b = reinterpret_cast<const char*>(base) + ((long long)hp * W + wp) * C * 2;
+      uint64_t dims[4] = {(uint64_t)C, (uint64_t)(W / 2), (uint64_t)(H / 2), (uint64_t)N};
+      uint64_t str[3] = {(uint64_t)2 * C * 2, (uint64_t)2 * W * C * 2, (uint64_t)H * W * C * 2};
+      int r = make_tmap_bf16(&op.maps[hp * 2 + wp], b, 4, dims, str, box);
+      if (r) return r;
+    }
+  return PB_OK;
+}
+
+}  // namespace pb
+
+using namespace pb;
+
+// ==============================================================================================
+// Dense GEMM
+// ==============================================================================================
+extern "C" int passl_b200_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K, int a_mn_major,
+                                    int b_mn_major, long long lda, long long ldb, long long ldc, int out_fp32,
+                                    int atomic_add, const float* bias, const void* residual, int act, float alpha,
+                                    int splits, float* col_sum, float* col_sqsum, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return PB_ERR_BAD_ARG;
+  if ((lda % 8) || (ldb % 8) || (N % 8) || (ldc % (out_fp32 ? 4 : 8))) return PB_ERR_BAD_ARG;
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(out)) & 15) return PB_ERR_BAD_ARG;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N;
+  p.m_blocks = (M + 127) / 128;
+  int BN = pick_bn(p.m_blocks, N);
+  p.n_blocks = (N + BN - 1) / BN;
+  p.k_iters = (K + 63) / 64;
+  p.k_steps = 4;
+  if (splits < 1) splits = 1;
+  if (splits > p.k_iters) splits = p.k_iters;
+  if (splits > 1 && !(out_fp32 && atomic_add)) return PB_ERR_BAD_ARG;
+  p.splits = splits;
+  int r = fill_mat_operand(p.a, A, a_mn_major != 0, M, K, lda, 128, 64);
+  if (r) return r;
+  r = fill_mat_operand(p.b, B, b_mn_major != 0, N, K, ldb, BN, 64);
+  if (r) return r;
+  set_epilogue(p, out, ldc, out_fp32, atomic_add, bias, residual, act, alpha, col_sum, col_sqsum);
+  return launch_gemm(p, BN, 64, a_mn_major != 0, b_mn_major != 0, (cudaStream_t)stream);
+}
+
+// ==============================================================================================
+// Convolution forward (implicit GEMM), NHWC bf16, weights [Cout, R, S, Cin] bf16.
+//   out[n, p, q, co] = epilogue( sum_{r,s,ci} x[n, p*stride + r - pad, q*stride + s - pad, ci] * w[co, r, s, ci] )
+// ==============================================================================================
+extern "C" int passl_b200_conv2d_fwd_bf16(const void* x, const void* w, void* out, int N, int H, int W, int Cin,
+                                          int Cout, int R, int S, int stride, int pad, const float* bias,
+                                          const void* residual, int act, float* col_sum, float* col_sqsum,
+                                          void* stream) {
+  if (Cin % 64 || Cout % 8 || R * S > kMaxTaps) return PB_ERR_UNSUPPORTED;
+  const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  if (R == 1 && S == 1 && stride == 1 && pad == 0) {
+    return passl_b200_gemm_bf16(x, w, out, N * H * W, Cout, Cin, 0, 0, Cin, Cin, Cout, 0, 0, bias, residual, act,
+                                1.f, 1, col_sum, col_sqsum, stream);
+  }
+  pick_patch(p.geom, N, Ho, Wo);
+  p.M = N * Ho * Wo; p.N = Cout;
+  p.m_blocks = p.geom.nb * p.geom.hb * p.geom.wb;
+  int BN = pick_bn(p.m_blocks, Cout);
+  p.n_blocks = (Cout + BN - 1) / BN;
+  p.splits = 1;
+  p.a.mode = OP_PATCH_K;
+  p.a.cchunks = Cin / 64;
+  p.a.ntaps = R * S;
+  p.a.tx_bytes = p.geom.TN * p.geom.TH * p.geom.TW * 128;
+  for (int r = 0; r < R; ++r)
+    for (int s = 0; s < S; ++s) {
+      int t = r * S + s;
+      int th = r - pad, tw = s - pad;
+      p.a.dh[t] = (signed char)floordiv(th, stride);
+      p.a.dw[t] = (signed char)floordiv(tw, stride);
+      p.a.map[t] = (signed char)(stride == 1 ? 0 : posmod(th, 2) * 2 + posmod(tw, 2));
+    }
+  int rc = fill_patch_maps(p.a, x, N, H, W, Cin, stride, p.geom);
+  if (rc) return rc;
+  p.k_iters = R * S * p.a.cchunks;
+  p.k_steps = 4;
+  rc = fill_mat_operand(p.b, w, false, Cout, (long long)R * S * Cin, (long long)R * S * Cin, BN, 64);
+  if (rc) return rc;
+  set_epilogue(p, out, Cout, 0, 0, bias, residual, act, 1.f, col_sum, col_sqsum);
+  p.out_pixel = 1; p.OH = Ho; p.OW = Wo; p.osh = 1; p.osw = 1; p.oh0 = 0; p.ow0 = 0;
+  return launch_gemm(p, BN, 64, false, false, (cudaStream_t)stream);
+}
+
+// ==============================================================================================
+// Convolution data gradient.  dx[n,h,w,ci] = sum dy[n,p,q,co] * w[co,r,s,ci]  over (p,q,r,s) with
+// h = p*stride + r - pad.  Runs one implicit GEMM per output-parity class over dy with class weights
+// wt[class][ci][tap][co] gathered by passl_b200_conv2d_dgrad_prepare_weights (same call order).
+//   accumulate != 0 : dx += result (dx already holds another branch's gradient), else dx = result.
+// ==============================================================================================
+namespace pb {
+struct DgradClass {
+  int a, b, ntaps;
+  int r[kMaxTaps], s[kMaxTaps], dh[kMaxTaps], dw[kMaxTaps];
+};
+static int build_dgrad_classes(DgradClass* cls, int R, int S, int stride, int pad) {
+  int n = 0;
+  for (int a = 0; a < stride; ++a)
+    for (int b = 0; b < stride; ++b) {
+      DgradClass& c = cls[n++];
+      c.a = a; c.b = b; c.ntaps = 0;
+      for (int r = 0; r < R; ++r) {
+        if (posmod(a + pad - r, stride)) continue;
+        for (int s = 0; s < S; ++s) {
+          if (posmod(b + pad - s, stride)) continue;
+          int t = c.ntaps++;
+          c.r[t] = r; c.s[t] = s;
+          c.dh[t] = floordiv(a + pad - r, stride);
+          c.dw[t] = floordiv(b + pad - s, stride);
+        }
+      }
+    }
+  return n;
+}
+
+__global__ void weight_gather_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ wt, int Cout,
+                                     int Cin, int R, int S, int ntaps, const int4 taps_rs_lo, const int4 taps_rs_hi,
+                                     const int4 taps_rs_top) {
+  // wt[ci][t][co] = w[co][r_t][s_t][ci];  taps packed as r*16+s in 12 ints
+  int packed[12] = {taps_rs_lo.x, taps_rs_lo.y, taps_rs_lo.z, taps_rs_lo.w, taps_rs_hi.x, taps_rs_hi.y,
+                    taps_rs_hi.z, taps_rs_hi.w, taps_rs_top.x, taps_rs_top.y, taps_rs_top.z, taps_rs_top.w};
+  __shared__ __nv_bfloat16 tile[32][33];
+  int t = blockIdx.z;
+  int r = packed[t] >> 4, s = packed[t] & 15;
+  int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int co = co0 + i, ci = ci0 + threadIdx.x;
+    if (co < Cout && ci < Cin) tile[i][threadIdx.x] = w[(((long long)co * R + r) * S + s) * Cin + ci];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int ci = ci0 + i, co = co0 + threadIdx.x;
+    if (co < Cout && ci < Cin) wt[((long long)ci * ntaps + t) * Cout + co] = tile[threadIdx.x][i];
+  }
+}
+}  // namespace pb
+
+extern "C" long long passl_b200_conv2d_dgrad_workspace_bytes(int Cin, int Cout, int R, int S) {
+  return (long long)Cin * Cout * R * S * 2 + 1024;
+}
+
+extern "C" int passl_b200_conv2d_dgrad_bf16(const void* dy, const void* w, void* dx, void* workspace, int N, int H,
+                                            int W, int Cin, int Cout, int R, int S, int stride, int pad,
+                                            int accumulate, void* stream) {
+  if (Cout % 64 || Cin % 8 || R * S > kMaxTaps || (stride != 1 && stride != 2)) return PB_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
+  if (R == 1 && S == 1 && stride == 1 && pad == 0) {
+    // dx[P, Cin] = dy[P, Cout] * w[Cout, Cin]  (B is MN-major: no weight transform)
+    return passl_b200_gemm_bf16(dy, w, dx, N * H * W, Cin, Cout, 0, 1, Cout, Cin, Cin, 0, 0, nullptr,
+                                accumulate ? dx : nullptr, ACT_NONE, 1.f, 1, nullptr, nullptr, stream);
+  }
+  if (stride == 2 && ((H & 1) || (W & 1))) return PB_ERR_UNSUPPORTED;
+  DgradClass cls[4];
+  int ncls = build_dgrad_classes(cls, R, S, stride, pad);
+  bool any_empty = false;
+  for (int c = 0; c < ncls; ++c) any_empty |= (cls[c].ntaps == 0);
+  if (any_empty && !accumulate) PB_CUDA_CHECK(cudaMemsetAsync(dx, 0, (size_t)N * H * W * Cin * 2, st));
+  __nv_bfloat16* wt = reinterpret_cast<__nv_bfloat16*>(workspace);
+  for (int c = 0; c < ncls; ++c) {
+    const DgradClass& k = cls[c];
+    if (k.ntaps == 0) continue;
+    int packed[12] = {0};
+    for (int t = 0; t < k.ntaps; ++t) packed[t] = k.r[t] * 16 + k.s[t];
+    dim3 grid((Cin + 31) / 32, (Cout + 31) / 32, k.ntaps), block(32, 8);
+    weight_gather_kernel<<<grid, block, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(w), wt, Cout, Cin, R, S,
+                                                 k.ntaps, make_int4(packed[0], packed[1], packed[2], packed[3]),
+                                                 make_int4(packed[4], packed[5], packed[6], packed[7]),
+                                                 make_int4(packed[8], packed[9], packed[10], packed[11]));
+    PB_LAUNCH_CHECK();
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    const int Hc = H / stride, Wc = W / stride;  // class pixel grid
+    pick_patch(p.geom, N, Hc, Wc);
+    p.M = N * Hc * Wc; p.N = Cin;
+    p.m_blocks = p.geom.nb * p.geom.hb * p.geom.wb;
+    int BN = pick_bn(p.m_blocks, Cin);
+    p.n_blocks = (Cin + BN - 1) / BN;
+    p.splits = 1;
+    p.a.mode = OP_PATCH_K;
+    p.a.cchunks = Cout / 64;
+    p.a.ntaps = k.ntaps;
+    p.a.tx_bytes = p.geom.TN * p.geom.TH * p.geom.TW * 128;
+    for (int t = 0; t < k.ntaps; ++t) { p.a.dh[t] = (signed char)k.dh[t]; p.a.dw[t] = (signed char)k.dw[t]; p.a.map[t] = 0; }
+    int rc = fill_patch_maps(p.a, dy, N, Ho, Wo, Cout, 1, p.geom);
+    if (rc) return rc;
+    p.k_iters = k.ntaps * p.a.cchunks;
+    p.k_steps = 4;
+    rc = fill_mat_operand(p.b, wt, false, Cin, (long long)k.ntaps * Cout, (long long)k.ntaps * Cout, BN, 64);
+    if (rc) return rc;
+    set_epilogue(p, dx, Cin, 0, 0, nullptr, accumulate ? dx : nullptr, ACT_NONE, 1.f, nullptr, nullptr);
+    p.out_pixel = 1; p.OH = H; p.OW = W; p.osh = stride; p.osw = stride; p.oh0 = k.a; p.ow0 = k.b;
+    rc = launch_gemm(p, BN, 64, false, false, st);
+    if (rc) return rc;
+    wt += (size_t)Cin * k.ntaps * Cout;
+  }
+  return PB_OK;
+}
+
+// ==============================================================================================
+// Convolution weight gradient: dw[co, r, s, ci] (fp32, atomically accumulated) =
+//     sum_{n,p,q} dy[n,p,q,co] * x[n, p*stride + r - pad, q*stride + s - pad, ci]
+// K = output pixels (patch tiles), split across CTAs.
+// ==============================================================================================
+extern "C" int passl_b200_conv2d_wgrad_bf16(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin,
+                                            int Cout, int R, int S, int stride, int pad, int zero_first,
+                                            void* stream) {
+  if (Cin % 8 || Cout % 8 || R * S > kMaxTaps || (stride != 1 && stride != 2)) return PB_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
+  if (zero_first) PB_CUDA_CHECK(cudaMemsetAsync(dw, 0, (size_t)Cout * R * S * Cin * 4, st));
+  if (R == 1 && S == 1 && stride == 1 && pad == 0) {
+    int P = N * H * W;
+    int mb = (Cout + 127) / 128;
+    int BNg = pick_bn(mb, Cin);
+    int tiles = mb * ((Cin + BNg - 1) / BNg);
+    int splits = (2 * num_sms() + tiles - 1) / tiles;
+    int kit = (P + 63) / 64;
+    if (splits > kit / 4) splits = kit / 4 > 0 ? kit / 4 : 1;
+    return passl_b200_gemm_bf16(dy, x, dw, Cout, Cin, P, 1, 1, Cout, Cin, Cin, 1, 1, nullptr, nullptr, ACT_NONE, 1.f,
+                                splits, nullptr, nullptr, stream);
+  }
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  pick_patch(p.geom, N, Ho, Wo);
+  const int rows = p.geom.TN * p.geom.TH * p.geom.TW;
+  p.M = Cout; p.N = R * S * Cin;
+  p.m_blocks = (Cout + 127) / 128;
+  int BN = Cin <= 64 ? 64 : 128;
+  p.n_blocks_per_tap = (Cin + BN - 1) / BN;
+  p.n_per_tap = Cin;
+  p.n_blocks = R * S * p.n_blocks_per_tap;
+  p.k_iters = p.geom.nb * p.geom.hb * p.geom.wb;
+  p.k_steps = (rows + 15) / 16;
+  int tiles = p.m_blocks * p.n_blocks;
+  int splits = (2 * num_sms() + tiles - 1) / tiles;
+  if (splits > p.k_iters) splits = p.k_iters;
+  if (splits < 1) splits = 1;
+  p.splits = splits;
+  // A = dy patches (channels = M rows), B = x patches shifted by the tap (channels = N rows)
+  p.a.mode = OP_PATCH_MN; p.a.ntaps = 1; p.a.tx_bytes = 2 * rows * 128;
+  p.a.dh[0] = 0; p.a.dw[0] = 0; p.a.map[0] = 0;
+  int rc = fill_patch_maps(p.a, dy, N, Ho, Wo, Cout, 1, p.geom);
+  if (rc) return rc;
+  p.b.mode = OP_PATCH_MN; p.b.ntaps = R * S; p.b.tx_bytes = (BN / 64) * rows * 128;
+  for (int r = 0; r < R; ++r)
+    for (int s = 0; s < S; ++s) {
+      int t = r * S + s;
+      int th = r - pad, tw = s - pad;
+      p.b.dh[t] = (signed char)floordiv(th, stride);
+      p.b.dw[t] = (signed char)floordiv(tw, stride);
+      p.b.map[t] = (signed char)(stride == 1 ? 0 : posmod(th, 2) * 2 + posmod(tw, 2));
+    }
+  rc = fill_patch_maps(p.b, x, N, H, W, Cin, stride, p.geom);
+  if (rc) return rc;
+  set_epilogue(p, dw, (long long)R * S * Cin, 1, 1, nullptr, nullptr, ACT_NONE, 1.f, nullptr, nullptr);
+  return launch_gemm(p, BN, 128, true, true, st);
+}

@@ -1,0 +1,215 @@
+"""Thin tensor-level wrappers over the C ABI: torch is only the carrier of device pointers and the current stream."""
+import torch
+
+from . import _lib
+
+ACT = {None: 0, "none": 0, "relu": 1, "gelu": 2, "quick_gelu": 3}
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.PasslB200Error("passl_b200 kernels need CUDA tensors (there is no CPU fallback)")
+
+
+_ws_cache = {}
+
+
+def workspace(nbytes, device, tag="default"):
+    key = (tag, str(device))
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GEMM
+# ------------------------------------------------------------------------------------------------------------
+def gemm(a, b, *, a_t=False, b_t=False, out=None, out_dtype=torch.bfloat16, bias=None, residual=None, act=None,
+         alpha=1.0, splits=1, accumulate=False, col_stats=None):
+    """out[M,N] = act(alpha * A @ B^T + bias) + residual.
+
+    a: [M,K] (or [K,M] when a_t), b: [N,K] (or [K,N] when b_t), bf16, last dim contiguous.
+    """
+    _need_cuda(a, b)
+    lib = _lib.load()
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    assert a.stride(-1) == 1 and b.stride(-1) == 1
+    if a_t:
+        K, M = a.shape
+    else:
+        M, K = a.shape
+    if b_t:
+        Kb, N = b.shape
+    else:
+        N, Kb = b.shape
+    assert K == Kb, (a.shape, b.shape)
+    if out is None:
+        out = (torch.zeros if (accumulate or splits > 1) else torch.empty)((M, N), dtype=out_dtype, device=a.device)
+    out_fp32 = out.dtype == torch.float32
+    atomic = 1 if (accumulate or splits > 1) else 0
+    cs = cq = None
+    if col_stats is not None:
+        cs, cq = col_stats
+    code = lib.passl_b200_gemm_bf16(_ptr(a), _ptr(b), _ptr(out), M, N, K, int(a_t), int(b_t), a.stride(0), b.stride(0),
+                                    out.stride(0), int(out_fp32), atomic, _ptr(bias), _ptr(residual), ACT[act],
+                                    float(alpha), int(splits), _ptr(cs), _ptr(cq), _stream())
+    _lib.check(code, "gemm_bf16")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Convolution (NHWC bf16, weights [Cout,R,S,Cin])
+# ------------------------------------------------------------------------------------------------------------
+def conv2d_fwd(x, w, stride=1, pad=0, bias=None, residual=None, act=None, col_stats=None, out=None):
+    _need_cuda(x, w)
+    lib = _lib.load()
+    N, H, W, Cin = x.shape
+    Cout, R, S, Cin2 = w.shape
+    assert Cin == Cin2 and x.is_contiguous() and w.is_contiguous()
+    Ho = (H + 2 * pad - R) // stride + 1
+    Wo = (W + 2 * pad - S) // stride + 1
+    if out is None:
+        out = torch.empty((N, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.device)
+    cs = cq = None
+    if col_stats is not None:
+        cs, cq = col_stats
+    code = lib.passl_b200_conv2d_fwd_bf16(_ptr(x), _ptr(w), _ptr(out), N, H, W, Cin, Cout, R, S, stride, pad, _ptr(bias),
+                                          _ptr(residual), ACT[act], _ptr(cs), _ptr(cq), _stream())
+    _lib.check(code, "conv2d_fwd_bf16")
+    return out
+
+
+def conv2d_dgrad(dy, w, x_shape, stride=1, pad=0, out=None, accumulate=False):
+    _need_cuda(dy, w)
+    lib = _lib.load()
+    N, H, W, Cin = x_shape
+    Cout, R, S, _ = w.shape
+    assert dy.is_contiguous() and w.is_contiguous()
+    if out is None:
+        assert not accumulate
+        out = torch.empty((N, H, W, Cin), dtype=torch.bfloat16, device=dy.device)
+    ws = workspace(lib.passl_b200_conv2d_dgrad_workspace_bytes(Cin, Cout, R, S), dy.device, "dgrad")
+    code = lib.passl_b200_conv2d_dgrad_bf16(_ptr(dy), _ptr(w), _ptr(out), _ptr(ws), N, H, W, Cin, Cout, R, S, stride, pad,
+                                            int(accumulate), _stream())
+    _lib.check(code, "conv2d_dgrad_bf16")
+    return out
+
+
+def conv2d_wgrad(x, dy, w_shape, stride=1, pad=0, out=None, accumulate=False):
+    _need_cuda(x, dy)
+    lib = _lib.load()
+    N, H, W, Cin = x.shape
+    Cout, R, S, _ = w_shape
+    assert x.is_contiguous() and dy.is_contiguous()
+    if out is None:
+        out = torch.empty((Cout, R, S, Cin), dtype=torch.float32, device=x.device)
+        accumulate = False
+    code = lib.passl_b200_conv2d_wgrad_bf16(_ptr(x), _ptr(dy), _ptr(out), N, H, W, Cin, Cout, R, S, stride, pad,
+                                            int(not accumulate), _stream())
+    _lib.check(code, "conv2d_wgrad_bf16")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Fused similarity / softmax / CE (fp32 SIMT variant)
+# ------------------------------------------------------------------------------------------------------------
+def simce_fwd(a, b, *, pos=None, label=None, excl=None, scale=1.0, loss_scale=1.0, want_rows=False):
+    _need_cuda(a, b)
+    lib = _lib.load()
+    N, D = a.shape
+    K = b.shape[0]
+    assert a.dtype == torch.float32 and a.is_contiguous() and b.is_contiguous()
+    lse = torch.empty(N, dtype=torch.float32, device=a.device)
+    tgt = torch.empty(N, dtype=torch.float32, device=a.device)
+    rows = torch.empty(N, dtype=torch.float32, device=a.device) if want_rows else None
+    out = torch.empty(3, dtype=torch.float32, device=a.device)
+    nb = lib.passl_b200_simce_workspace_bytes(N, K)
+    ws = workspace(nb, a.device, "simce")
+    code = lib.passl_b200_simce_fwd_f32(_ptr(a), _ptr(b), int(b.dtype == torch.bfloat16), _ptr(pos), _ptr(label),
+                                        _ptr(excl), float(scale), float(loss_scale), N, K, D, _ptr(lse), _ptr(tgt),
+                                        _ptr(rows), _ptr(out), _ptr(ws), ws.numel(), _stream())
+    _lib.check(code, "simce_fwd_f32")
+    return out, lse, tgt, rows
+
+
+def simce_bwd(a, b, lse, tgt, *, pos=None, label=None, excl=None, scale=1.0, loss_scale=1.0, dloss=None):
+    lib = _lib.load()
+    N, D = a.shape
+    K = b.shape[0]
+    da = torch.empty_like(a)
+    ws = workspace(N * 4 + 256, a.device, "simce_bwd")
+    code = lib.passl_b200_simce_bwd_f32(_ptr(a), _ptr(b), int(b.dtype == torch.bfloat16), _ptr(pos), _ptr(label),
+                                        _ptr(excl), float(scale), float(loss_scale), N, K, D, _ptr(lse), _ptr(tgt),
+                                        _ptr(dloss), _ptr(da), _ptr(ws), ws.numel(), _stream())
+    _lib.check(code, "simce_bwd_f32")
+    return da
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Embedding utilities
+# ------------------------------------------------------------------------------------------------------------
+L2_MODE = {"normalize": 0, "l2_normalize": 1, "clip": 2}
+
+
+def l2norm_fwd(x, mode="normalize", eps=1e-12, want_bf16=False):
+    _need_cuda(x)
+    lib = _lib.load()
+    N, D = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    y = torch.empty_like(x)
+    yb = torch.empty((N, D), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    inv = torch.empty(N, dtype=torch.float32, device=x.device)
+    _lib.check(lib.passl_b200_l2norm_fwd(_ptr(x), _ptr(y), _ptr(yb), _ptr(inv), N, D, L2_MODE[mode], float(eps), _stream()),
+               "l2norm_fwd")
+    return y, yb, inv
+
+
+def l2norm_bwd(dy, y, inv, mode="normalize", eps=1e-12, want_bf16=False):
+    lib = _lib.load()
+    N, D = y.shape
+    dx = torch.empty_like(y)
+    dxb = torch.empty((N, D), dtype=torch.bfloat16, device=y.device) if want_bf16 else None
+    _lib.check(lib.passl_b200_l2norm_bwd(_ptr(dy.contiguous()), _ptr(y), _ptr(inv), _ptr(dx), _ptr(dxb), N, D,
+                                         L2_MODE[mode], float(eps), _stream()), "l2norm_bwd")
+    return dx, dxb
+
+
+def queue_enqueue(keys, queue_ptr, queue_f32=None, queue_bf16=None):
+    """queue[ptr:ptr+Bg] = keys; ptr = (ptr+Bg) % K — all on device (moco.py:92-105)."""
+    _need_cuda(keys, queue_ptr)
+    lib = _lib.load()
+    Bg, D = keys.shape
+    q = queue_f32 if queue_f32 is not None else queue_bf16
+    K = q.shape[0]
+    if K % Bg != 0:
+        raise AssertionError("K %% batch_size != 0 (moco.py:99): K=%d batch=%d" % (K, Bg))
+    assert queue_ptr.dtype == torch.int64 and keys.dtype == torch.float32 and keys.is_contiguous()
+    _lib.check(lib.passl_b200_queue_enqueue(_ptr(keys), _ptr(queue_f32), _ptr(queue_bf16), _ptr(queue_ptr), Bg, D, K,
+                                            _stream()), "queue_enqueue")
+
+
+def ema_update(k, q, m, k_bf16=None):
+    _need_cuda(k, q)
+    lib = _lib.load()
+    assert k.dtype == torch.float32 and q.dtype == torch.float32 and k.numel() == q.numel()
+    _lib.check(lib.passl_b200_ema_update(_ptr(k), _ptr(q), _ptr(k_bf16), float(m), k.numel(), _stream()), "ema_update")
+
+
+def cast_bf16(x, out=None):
+    _need_cuda(x)
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.passl_b200_cast_f32_to_bf16(_ptr(x), _ptr(out), x.numel(), _stream()), "cast_f32_to_bf16")
+    return out

@@ -1,0 +1,113 @@
+"""Implicit-GEMM convolution (fwd / dgrad / wgrad) through the C ABI vs torch fp32 conv2d autograd on the same
+bf16-rounded inputs.  Shapes are the ResNet-50 stage shapes of SURVEY.md App. A.1 at small batch."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+# (N, H, W, Cin, Cout, R, stride, pad)
+CASES = [
+    (4, 56, 56, 64, 64, 3, 1, 1),
+    (2, 28, 28, 128, 128, 3, 1, 1),
+    (3, 14, 14, 256, 256, 3, 1, 1),
+    (5, 7, 7, 512, 512, 3, 1, 1),
+    (2, 56, 56, 128, 128, 3, 2, 1),
+    (2, 28, 28, 256, 256, 3, 2, 1),
+    (3, 14, 14, 512, 512, 3, 2, 1),
+    (2, 56, 56, 256, 512, 1, 2, 0),
+    (2, 56, 56, 64, 256, 1, 1, 0),
+    (2, 14, 14, 1024, 256, 1, 1, 0),
+    (1, 112, 112, 64, 64, 3, 1, 1),
+]
+
+
+def _mk(case, seed=0):
+    N, H, W, Cin, Cout, R, stride, pad = case
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(N, H, W, Cin, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(Cout, R, R, Cin, device="cuda", generator=g) / (R * R * Cin) ** 0.5).bfloat16()
+    return x, w
+
+
+def _ref(x, w, stride, pad, dy=None):
+    xr = x.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    wr = w.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    y = F.conv2d(xr, wr, stride=stride, padding=pad)
+    if dy is None:
+        return y.permute(0, 2, 3, 1).contiguous()
+    y.backward(dy.float().permute(0, 3, 1, 2).contiguous())
+    return xr.grad.permute(0, 2, 3, 1).contiguous(), wr.grad.permute(0, 2, 3, 1).contiguous()
+
+
+def _check(got, ref, tag, rel=2e-2):
+    d = (got.float() - ref).abs()
+    tol = rel * ref.abs().max().item() + 1e-3
+    nbad = int((d > tol).sum())
+    info = ""
+    if nbad:
+        idx = (d > tol).nonzero()
+        info = " first bad idx %s .. last %s" % (idx[0].tolist(), idx[-1].tolist())
+    assert nbad == 0, "%s: max err %.4g tol %.4g bad %d/%d%s" % (tag, d.max().item(), tol, nbad, d.numel(), info)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_conv_fwd(case):
+    from passl_b200 import kernels as K_
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    x, w = _mk(case)
+    stride, pad = case[6], case[7]
+    out = K_.conv2d_fwd(x, w, stride=stride, pad=pad)
+    torch.cuda.synchronize()
+    _check(out, _ref(x, w, stride, pad), "conv fwd %s" % (case,))
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_conv_dgrad(case):
+    from passl_b200 import kernels as K_
+    torch.backends.cudnn.allow_tf32 = False
+    x, w = _mk(case, 1)
+    stride, pad = case[6], case[7]
+    y = _ref(x, w, stride, pad)
+    dy = torch.randn_like(y).bfloat16()
+    dx_ref, _ = _ref(x, w, stride, pad, dy)
+    dx = K_.conv2d_dgrad(dy, w, tuple(x.shape), stride=stride, pad=pad)
+    torch.cuda.synchronize()
+    _check(dx, dx_ref, "conv dgrad %s" % (case,))
+    # accumulate mode: dx += grad
+    base = torch.randn_like(dx)
+    acc = base.clone()
+    K_.conv2d_dgrad(dy, w, tuple(x.shape), stride=stride, pad=pad, out=acc, accumulate=True)
+    torch.cuda.synchronize()
+    _check(acc, dx_ref + base.float(), "conv dgrad acc %s" % (case,), rel=3e-2)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_conv_wgrad(case):
+    from passl_b200 import kernels as K_
+    torch.backends.cudnn.allow_tf32 = False
+    x, w = _mk(case, 2)
+    stride, pad = case[6], case[7]
+    y = _ref(x, w, stride, pad)
+    dy = torch.randn_like(y).bfloat16()
+    _, dw_ref = _ref(x, w, stride, pad, dy)
+    dw = K_.conv2d_wgrad(x, dy, tuple(w.shape), stride=stride, pad=pad)
+    torch.cuda.synchronize()
+    _check(dw, dw_ref, "conv wgrad %s" % (case,), rel=1e-2)
+
+
+def test_conv_fwd_fused_epilogue():
+    from passl_b200 import kernels as K_
+    case = (2, 28, 28, 128, 256, 3, 1, 1)
+    x, w = _mk(case, 3)
+    res = torch.randn(2, 28, 28, 256, device="cuda").bfloat16()
+    cs = torch.zeros(256, device="cuda")
+    cq = torch.zeros(256, device="cuda")
+    out = K_.conv2d_fwd(x, w, stride=1, pad=1, residual=res, act="relu", col_stats=(cs, cq))
+    torch.cuda.synchronize()
+    ref = torch.relu(_ref(x, w, 1, 1)) + res.float()
+    _check(out, ref, "conv fused")
+    o = out.float().reshape(-1, 256)
+    assert torch.allclose(cs, o.sum(0), rtol=1e-3, atol=0.5)
+    assert torch.allclose(cq, (o * o).sum(0), rtol=1e-3, atol=2.0)
