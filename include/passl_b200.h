@@ -79,6 +79,17 @@ int passl_b200_simce_bwd_f32(const float* A, const void* B, int b_is_bf16, const
                              void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Fused InfoNCE forward on tcgen05 (bf16 operands, fp32 accumulate in TMEM, online softmax out of TMEM).
+ * Same contract as passl_b200_simce_fwd_f32 with Q and Kmat in bf16; the key matrix is streamed from HBM exactly
+ * once.  D multiple of 64, <= 512.
+ * ------------------------------------------------------------------------------------------------------------- */
+long long passl_b200_infonce_tc_workspace_bytes(int N, int K, int D);
+int passl_b200_infonce_tc_fwd(const void* Q, const void* Kmat, const float* P, const long long* label, const int* excl,
+                              float scale, float loss_scale, int N, int K, int D, float* lse, float* tgt,
+                              float* loss_rows, float* out_scalars, void* workspace, long long workspace_bytes,
+                              void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Embedding utilities.
  *   l2norm mode 0: x/max(||x||,eps) (paddle F.normalize, moco.py:159,170; mocov3.py:189-190)
  *          mode 1: x/sqrt(sum x^2+eps) (passl/nn/norm.py:18-40; simclr.py:58)

@@ -29,6 +29,9 @@ SIGNATURES = {
     "passl_b200_simce_bwd_f32": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_float,
                                          c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll,
                                          c_void_p]),
+    "passl_b200_infonce_tc_workspace_bytes": (c_ll, [c_int, c_int, c_int]),
+    "passl_b200_infonce_tc_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_int,
+                                          c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
     "passl_b200_l2norm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     "passl_b200_l2norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
                                       c_void_p]),

@@ -1,0 +1,254 @@
+// BatchNorm (training mode) over channels-last activations [P, C] bf16 — statistics, fused apply (+ReLU, +residual)
+// and the two-pass backward.  HBM-bound: every pass reads/writes each activation exactly once with 16-byte accesses.
+//
+// Reference: paddle nn.BatchNorm2D / BatchNorm1D as used at passl_v110/modeling/backbones/resnetimagenet.py:112-131
+// (conv-bn-relu, bn3 + identity + relu) and necks/base_neck.py:221-227 (fc-BN1D-ReLU).  Paddle conventions:
+// eps 1e-5, momentum 0.9 (running = 0.9*running + 0.1*batch), biased batch variance for normalisation.
+#include "common.cuh"
+#include "host_utils.h"
+#include "../../include/passl_b200.h"
+
+namespace pb {
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]); u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+
+// blockDim = (GX, GY): x over 8-channel groups, y over rows.  gridDim = (row blocks, channel-group blocks).
+// Accumulates per-channel sum(a) and sum(a*b') into out0/out1 with atomics, where
+//   MODE 0 (stats)      : a = y,               second = y*y
+//   MODE 1 (bwd reduce) : a = dz*mask,         second = a * (y - mean) * invstd
+template <int MODE>
+__global__ void bn_reduce_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dz,
+                                 const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean,
+                                 const float* __restrict__ invstd, float* __restrict__ out0, float* __restrict__ out1,
+                                 long long P, int C, int rows_per_block, int relu) {
+  extern __shared__ float red[];  // [GY][GX*16]
+  const int cg = blockIdx.y * blockDim.x + threadIdx.x;  // channel group
+  const int c0 = cg * 8;
+  const bool cok = c0 < C;
+  float s0[8], s1[8], mu[8], is[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s0[i] = 0.f; s1[i] = 0.f; mu[i] = 0.f; is[i] = 1.f; }
+  if (MODE == 1 && cok) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { mu[i] = mean[c0 + i]; is[i] = invstd[c0 + i]; }
+  }
+  const long long r_begin = (long long)blockIdx.x * rows_per_block;
+  long long r_end = r_begin + rows_per_block;
+  if (r_end > P) r_end = P;
+  if (cok) {
+    for (long long r = r_begin + threadIdx.y; r < r_end; r += blockDim.y) {
+      float a[8];
+      uint4 uy = ld_nc_v4(y + r * C + c0);
+      unpack8(uy, a);
+      if (MODE == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s0[i] += a[i]; s1[i] = fmaf(a[i], a[i], s1[i]); }
+      } else {
+        float g[8];
+        uint4 ug = ld_nc_v4(dz + r * C + c0);
+        unpack8(ug, g);
+        if (relu) {
+          float zz[8];
+          uint4 uz = ld_nc_v4(z + r * C + c0);
+          unpack8(uz, zz);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g[i] = zz[i] > 0.f ? g[i] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s0[i] += g[i]; s1[i] = fmaf(g[i], (a[i] - mu[i]) * is[i], s1[i]); }
+      }
+    }
+  }
+  float* my = red + (threadIdx.y * blockDim.x + threadIdx.x) * 16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { my[i] = s0[i]; my[8 + i] = s1[i]; }
+  __syncthreads();
+  if (threadIdx.y == 0 && cok) {
+    for (int yy = 1; yy < blockDim.y; ++yy) {
+      const float* o = red + (yy * blockDim.x + threadIdx.x) * 16;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s0[i] += o[i]; s1[i] += o[8 + i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { red_add_f32(out0 + c0 + i, s0[i]); red_add_f32(out1 + c0 + i, s1[i]); }
+  }
+}
+
+// sums -> mean / invstd / fused scale+shift, running statistics update (Paddle momentum convention).
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sqsum,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float* mean,
+                                   float* invstd, float* scale, float* shift, float* running_mean, float* running_var,
+                                   float inv_count, float eps, float momentum, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float m = sum[c] * inv_count;
+  float v = fmaxf(sqsum[c] * inv_count - m * m, 0.f);
+  float is = rsqrtf(v + eps);
+  float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  mean[c] = m; invstd[c] = is;
+  scale[c] = g * is;
+  shift[c] = b - m * g * is;
+  if (running_mean) running_mean[c] = momentum * running_mean[c] + (1.f - momentum) * m;
+  if (running_var) running_var[c] = momentum * running_var[c] + (1.f - momentum) * v;
+}
+
+// z = act(y*scale + shift + residual)
+__global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ residual,
+                                const float* __restrict__ scale, const float* __restrict__ shift,
+                                __nv_bfloat16* __restrict__ z, float* __restrict__ z_f32, long long total8, int C8,
+                                int relu) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % C8) * 8;
+    float a[8];
+    unpack8(ld_nc_v4(y + i * 8), a);
+    float4 s0 = *reinterpret_cast<const float4*>(scale + c0), s1 = *reinterpret_cast<const float4*>(scale + c0 + 4);
+    float4 h0 = *reinterpret_cast<const float4*>(shift + c0), h1 = *reinterpret_cast<const float4*>(shift + c0 + 4);
+    a[0] = fmaf(a[0], s0.x, h0.x); a[1] = fmaf(a[1], s0.y, h0.y); a[2] = fmaf(a[2], s0.z, h0.z); a[3] = fmaf(a[3], s0.w, h0.w);
+    a[4] = fmaf(a[4], s1.x, h1.x); a[5] = fmaf(a[5], s1.y, h1.y); a[6] = fmaf(a[6], s1.z, h1.z); a[7] = fmaf(a[7], s1.w, h1.w);
+    if (residual) {
+      float r[8];
+      unpack8(ld_nc_v4(residual + i * 8), r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += r[j];
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j], 0.f);
+    }
+    if (z) *reinterpret_cast<uint4*>(z + i * 8) = pack8(a);
+    if (z_f32) {
+      *reinterpret_cast<float4*>(z_f32 + i * 8) = make_float4(a[0], a[1], a[2], a[3]);
+      *reinterpret_cast<float4*>(z_f32 + i * 8 + 4) = make_float4(a[4], a[5], a[6], a[7]);
+    }
+  }
+}
+
+// dy = scale * (g - sum_g/P - xhat * sum_gx/P),  g = dz * relu_mask;   d_res = g (optional)
+__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dz,
+                                    const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                    const float* __restrict__ sum_g, const float* __restrict__ sum_gx,
+                                    __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dres, long long total8,
+                                    int C8, float inv_count, int relu) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % C8) * 8;
+    float a[8], g[8];
+    unpack8(ld_nc_v4(y + i * 8), a);
+    unpack8(ld_nc_v4(dz + i * 8), g);
+    if (relu) {
+      float zz[8];
+      unpack8(ld_nc_v4(z + i * 8), zz);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = zz[j] > 0.f ? g[j] : 0.f;
+    }
+    if (dres) *reinterpret_cast<uint4*>(dres + i * 8) = pack8(g);
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      const float is = invstd[c];
+      const float xhat = (a[j] - mean[c]) * is;
+      const float ga = gamma ? gamma[c] : 1.f;
+      o[j] = ga * is * (g[j] - sum_g[c] * inv_count - xhat * sum_gx[c] * inv_count);
+    }
+    *reinterpret_cast<uint4*>(dy + i * 8) = pack8(o);
+  }
+}
+
+static void reduce_cfg(long long P, int C, dim3& grid, dim3& block, int& rows_per_block, int& smem) {
+  int cg = C / 8;
+  int gx = cg < 64 ? cg : 64;
+  // round gx down to a power of two divisor-friendly size
+  int gy = 256 / gx;
+  if (gy < 1) gy = 1;
+  block = dim3(gx, gy);
+  int cgb = (cg + gx - 1) / gx;
+  long long target_blocks = (long long)num_sms() * 8 / cgb;
+  if (target_blocks < 1) target_blocks = 1;
+  long long rpb = (P + target_blocks - 1) / target_blocks;
+  if (rpb < gy) rpb = gy;
+  rows_per_block = (int)rpb;
+  grid = dim3((unsigned)((P + rpb - 1) / rpb), cgb);
+  smem = gx * gy * 16 * 4;
+}
+
+static int ew_blocks(long long total8) {
+  long long g = (total8 + 255) / 256;
+  long long cap = (long long)num_sms() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace pb
+
+using namespace pb;
+
+// sum[c] += sum_p y[p,c];  sqsum[c] += sum_p y[p,c]^2      (accumulators must be zeroed by the caller)
+extern "C" int passl_b200_bn_stats(const void* y, float* sum, float* sqsum, long long P, int C, void* stream) {
+  if (P <= 0 || C <= 0 || C % 8) return PB_ERR_BAD_ARG;
+  dim3 grid, block; int rpb, smem;
+  reduce_cfg(P, C, grid, block, rpb, smem);
+  bn_reduce_kernel<0><<<grid, block, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(y), nullptr, nullptr,
+                                                                    nullptr, nullptr, sum, sqsum, P, C, rpb, 0);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+extern "C" int passl_b200_bn_finalize(const float* sum, const float* sqsum, const float* gamma, const float* beta,
+                                      float* mean, float* invstd, float* scale, float* shift, float* running_mean,
+                                      float* running_var, long long count, float eps, float momentum, int C, void* stream) {
+  if (C <= 0 || count <= 0) return PB_ERR_BAD_ARG;
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sum, sqsum, gamma, beta, mean, invstd, scale, shift,
+                                                                        running_mean, running_var, 1.f / (float)count, eps,
+                                                                        momentum, C);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+extern "C" int passl_b200_bn_apply(const void* y, const void* residual, const float* scale, const float* shift, void* z,
+                                   float* z_f32, long long P, int C, int relu, void* stream) {
+  if (P <= 0 || C <= 0 || C % 8) return PB_ERR_BAD_ARG;
+  long long total8 = P * (C / 8);
+  bn_apply_kernel<<<ew_blocks(total8), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<const __nv_bfloat16*>(residual), scale, shift,
+      reinterpret_cast<__nv_bfloat16*>(z), z_f32, total8, C / 8, relu);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+// sum_g[c] += sum_p g[p,c];  sum_gx[c] += sum_p g[p,c]*xhat[p,c]   with g = dz * (z > 0 if relu)
+extern "C" int passl_b200_bn_bwd_reduce(const void* y, const void* dz, const void* z, const float* mean, const float* invstd,
+                                        float* sum_g, float* sum_gx, long long P, int C, int relu, void* stream) {
+  if (P <= 0 || C <= 0 || C % 8) return PB_ERR_BAD_ARG;
+  if (relu && !z) return PB_ERR_BAD_ARG;
+  dim3 grid, block; int rpb, smem;
+  reduce_cfg(P, C, grid, block, rpb, smem);
+  bn_reduce_kernel<1><<<grid, block, smem, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<const __nv_bfloat16*>(dz),
+      reinterpret_cast<const __nv_bfloat16*>(z), mean, invstd, sum_g, sum_gx, P, C, rpb, relu);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+extern "C" int passl_b200_bn_bwd_apply(const void* y, const void* dz, const void* z, const float* mean, const float* invstd,
+                                       const float* gamma, const float* sum_g, const float* sum_gx, void* dy, void* dres,
+                                       long long P, int C, int relu, void* stream) {
+  if (P <= 0 || C <= 0 || C % 8) return PB_ERR_BAD_ARG;
+  if (relu && !z) return PB_ERR_BAD_ARG;
+  long long total8 = P * (C / 8);
+  bn_bwd_apply_kernel<<<ew_blocks(total8), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<const __nv_bfloat16*>(dz),
+      reinterpret_cast<const __nv_bfloat16*>(z), mean, invstd, gamma, sum_g, sum_gx, reinterpret_cast<__nv_bfloat16*>(dy),
+      reinterpret_cast<__nv_bfloat16*>(dres), total8, C / 8, 1.f / (float)P, relu);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}

@@ -1,0 +1,315 @@
+// Fused InfoNCE forward on tcgen05 — the headline kernel (BASELINE.json: "fused InfoNCE HBM GB/s vs roofline").
+//
+//   logits[i, j] = scale * <Q_i, K_j>  are produced tile by tile in TMEM and consumed in place by an online
+//   softmax (running row max / sum) — the [N, K] logit matrix never exists in HBM.  HBM traffic is the
+//   algorithmic minimum: the key matrix (MoCo queue) is streamed exactly once by TMA, Q is read once per CTA
+//   (L2 resident).   SURVEY.md §8(d):  bytes = (2*N*D + D*K)*2 + 4*N,  C3: 16.91 MB, 4.295 GFLOP.
+//
+// Replaces: paddle.matmul(q, queue) + concat + /T + CrossEntropyLoss + topk
+//           (passl_v110/modeling/architectures/moco.py:178-182, heads/contrastive_head.py:37-60),
+//           einsum('nc,mc->nm')/T + CE (passl/models/mocov3.py:187-198), CLIP logits + CE (clip.py:331-335).
+//
+// Work decomposition: CTA = (row group of MB*128 queries) x (contiguous slice of 64-key tiles).
+//   warp 0 lane 0 : TMA producer  (Q once, then key tiles through a STAGES ring, SWIZZLE_128B)
+//   warp 1 lane 0 : MMA issuer    (tcgen05.mma M=128 N=64 K=16; TMEM double-buffered per row block)
+//   warps 2..2+4*MB : softmax warps — tcgen05.ld 64 logits / thread / tile, online max+sum in the log2 domain,
+//                     rank counter for top-1 / top-5 accuracy.
+// Partials (m, l, cnt) per (row, slice) are merged by simce_finalize_kernel (shared with the fp32 variant).
+#include "common.cuh"
+#include "host_utils.h"
+#include "simce_common.cuh"
+#include "../../include/passl_b200.h"
+
+#include <string.h>
+
+namespace pb {
+
+constexpr int NCE_BK = 64;          // keys per tile (= MMA N)
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+struct InfoNceTcParams {
+  CUtensorMap q_map;  // [N, D] bf16, box {64, 128}
+  CUtensorMap k_map;  // [K, D] bf16, box {64, 64}
+  const __nv_bfloat16* Q;
+  const __nv_bfloat16* Kmat;
+  const float* P;           // [N, D] fp32 positive keys (extra column) or null
+  const long long* label;   // [N] or null
+  const int* excl;          // [N] or null
+  float scale;
+  int N, K, D;
+  int row_groups, slices, tiles;
+  float* part_m; float* part_l; int* part_cnt;  // [N, slices]
+  float* tgt;                                   // [N]
+};
+
+template <int MB>
+__global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const __grid_constant__ InfoNceTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int DC = p.D / 64;                       // 64-wide feature chunks
+  const int q_bytes = MB * 128 * p.D * 2;
+  const int stage_bytes = NCE_BK * p.D * 2;
+  // stage count chosen on the host so that q_bytes + STAGES*stage_bytes fits; recompute the same way here
+  int STAGES = (200 * 1024 - q_bytes) / stage_bytes;
+  if (STAGES > 8) STAGES = 8;
+  uint8_t* q_smem = smem;
+  uint8_t* k_smem = smem + q_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(k_smem + STAGES * stage_bytes);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* k_full = bars + 1;        // STAGES
+  uint64_t* k_empty = k_full + 8;     // STAGES
+  uint64_t* s_full = k_empty + 8;     // 2
+  uint64_t* s_empty = s_full + 2;     // 2
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(s_empty + 2);
+
+  const uint32_t warp = warp_id(), lane = lane_id();
+  const int group = blockIdx.x / p.slices;
+  const int slice = blockIdx.x - group * p.slices;
+  const int row_base = group * MB * 128;
+  const int t_begin = (int)((long long)slice * p.tiles / p.slices);
+  const int t_end = (int)((long long)(slice + 1) * p.tiles / p.slices);
+  constexpr uint32_t TMEM_COLS = 2 * MB * NCE_BK;  // 128 or 256
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.q_map);
+    tma_prefetch_desc(&p.k_map);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 4 * MB);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      mbar_arrive_expect_tx(q_full, (uint32_t)q_bytes);
+      for (int b = 0; b < MB; ++b)
+        for (int c = 0; c < DC; ++c)
+          tma_load_2d(q_smem + (b * DC + c) * (128 * 128), &p.q_map, q_full, c * 64, row_base + b * 128);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(&k_empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&k_full[stage], (uint32_t)stage_bytes);
+        for (int c = 0; c < DC; ++c)
+          tma_load_2d(k_smem + stage * stage_bytes + c * (NCE_BK * 128), &p.k_map, &k_full[stage], c * 64, t * NCE_BK);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      constexpr uint32_t idesc = make_idesc_bf16(128, NCE_BK, false, false);
+      mbar_wait(q_full, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = t_begin; t < t_end; ++t, ++it) {
+        const int buf = it & 1;
+        const uint32_t bphase = (it >> 1) & 1;
+        mbar_wait(&s_empty[buf], bphase ^ 1);
+        mbar_wait(&k_full[stage], phase);
+        tc_fence_after();
+        const uint32_t kb = smem_u32(k_smem + stage * stage_bytes);
+        for (int b = 0; b < MB; ++b) {
+          const uint32_t d_tmem = tmem_base + (buf * MB + b) * NCE_BK;
+          const uint32_t qb = smem_u32(q_smem + b * DC * (128 * 128));
+          for (int c = 0; c < DC; ++c) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              uint64_t da = make_smem_desc_sw128(qb + c * (128 * 128) + k * 32, 16, 1024);
+              uint64_t db = make_smem_desc_sw128(kb + c * (NCE_BK * 128) + k * 32, 16, 1024);
+              umma_bf16(d_tmem, da, db, idesc, (c > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+        }
+        umma_commit(&k_empty[stage]);
+        umma_commit(&s_full[buf]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ---------------- softmax warps ----------------
+    const int ew = warp - 2;            // 0 .. 4*MB-1
+    const int b = ew >> 2;              // row block
+    const uint32_t q4 = warp & 3;       // TMEM lane quarter
+    const int row = row_base + b * 128 + q4 * 32 + lane;
+    const bool row_ok = row < p.N;
+    const float c2 = p.scale * kLog2e;  // logits in the log2 domain: y = dot * c2
+
+    // target logit (positive pair or labelled column), fp32 accumulate over bf16 q
+    float tgt2 = 0.f;
+    long long lab = -1;
+    int ex = -1;
+    if (row_ok) {
+      const __nv_bfloat16* qr = p.Q + (size_t)row * p.D;
+      float s = 0.f;
+      if (p.P) {
+        const float* pr = p.P + (size_t)row * p.D;
+        for (int d = 0; d < p.D; d += 8) {
+          uint4 u = *reinterpret_cast<const uint4*>(qr + d);
+          float4 a = *reinterpret_cast<const float4*>(pr + d), c = *reinterpret_cast<const float4*>(pr + d + 4);
+          float2 q0 = unpack_bf16x2(u.x), q1 = unpack_bf16x2(u.y), q2 = unpack_bf16x2(u.z), q3 = unpack_bf16x2(u.w);
+          s += q0.x * a.x + q0.y * a.y + q1.x * a.z + q1.y * a.w + q2.x * c.x + q2.y * c.y + q3.x * c.z + q3.y * c.w;
+        }
+      } else {
+        lab = p.label[row];
+        const __nv_bfloat16* kr = p.Kmat + (size_t)lab * p.D;
+        for (int d = 0; d < p.D; d += 8) {
+          uint4 u = *reinterpret_cast<const uint4*>(qr + d), w = *reinterpret_cast<const uint4*>(kr + d);
+          float2 q0 = unpack_bf16x2(u.x), q1 = unpack_bf16x2(u.y), q2 = unpack_bf16x2(u.z), q3 = unpack_bf16x2(u.w);
+          float2 k0 = unpack_bf16x2(w.x), k1 = unpack_bf16x2(w.y), k2 = unpack_bf16x2(w.z), k3 = unpack_bf16x2(w.w);
+          s += q0.x * k0.x + q0.y * k0.y + q1.x * k1.x + q1.y * k1.y + q2.x * k2.x + q2.y * k2.y + q3.x * k3.x + q3.y * k3.y;
+        }
+      }
+      tgt2 = s * c2;
+      if (p.excl) ex = p.excl[row];
+    }
+
+    float m = -INFINITY, l = 0.f;
+    int cnt = 0;
+    int it = 0;
+    for (int t = t_begin; t < t_end; ++t, ++it) {
+      const int buf = it & 1;
+      const uint32_t bphase = (it >> 1) & 1;
+      mbar_wait(&s_full[buf], bphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((q4 * 32u) << 16) + (buf * MB + b) * NCE_BK;
+      uint32_t v[64];
+      tmem_ld_32x32(taddr, v);
+      tmem_ld_32x32(taddr + 32, v + 32);
+      tmem_ld_wait();
+      // TMEM buffer can be refilled as soon as the values are in registers
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[buf]);
+
+      const int key0 = t * NCE_BK;
+      const bool special = (key0 + NCE_BK > p.K) || (ex >= key0 && ex < key0 + NCE_BK) ||
+                           (lab >= key0 && lab < key0 + NCE_BK);
+      float y[64];
+      float mx = -INFINITY;
+      if (!special) {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+          y[j] = __uint_as_float(v[j]) * c2;
+          mx = fmaxf(mx, y[j]);
+          cnt += (y[j] > tgt2) ? 1 : 0;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+          const int key = key0 + j;
+          const bool ok = (key < p.K) && (key != ex);
+          y[j] = ok ? __uint_as_float(v[j]) * c2 : -INFINITY;
+          mx = fmaxf(mx, y[j]);
+          cnt += (ok && key != lab && y[j] > tgt2) ? 1 : 0;
+        }
+      }
+      if (mx > -INFINITY) {
+        const float mn = fmaxf(m, mx);
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) s += exp2f(y[j] - mn);
+        l = l * exp2f(m - mn) + s;
+        m = mn;
+      }
+    }
+    if (row_ok) {
+      // back to the natural-log domain used by simce_finalize_kernel
+      p.part_m[(size_t)row * p.slices + slice] = m * kLn2;
+      p.part_l[(size_t)row * p.slices + slice] = l;
+      p.part_cnt[(size_t)row * p.slices + slice] = cnt;
+      if (slice == 0) p.tgt[row] = tgt2 * kLn2;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+static void nce_plan(int N, int K, int D, int& MB, int& groups, int& slices, int& tiles, int& smem) {
+  MB = (D <= 128 && N > 128) ? 2 : 1;
+  if (D > 256) MB = 1;
+  groups = (N + MB * 128 - 1) / (MB * 128);
+  tiles = (K + NCE_BK - 1) / NCE_BK;
+  slices = num_sms() / groups;
+  if (slices < 1) slices = 1;
+  if (slices > tiles) slices = tiles;
+  int q_bytes = MB * 128 * D * 2, stage_bytes = NCE_BK * D * 2;
+  int stages = (200 * 1024 - q_bytes) / stage_bytes;
+  if (stages > 8) stages = 8;
+  smem = q_bytes + stages * stage_bytes + 512 + 1024;
+}
+
+}  // namespace pb
+
+using namespace pb;
+
+extern "C" long long passl_b200_infonce_tc_workspace_bytes(int N, int K, int D) {
+  int MB, groups, slices, tiles, smem;
+  nce_plan(N, K, D, MB, groups, slices, tiles, smem);
+  return (long long)N * slices * 12 + 256;
+}
+
+// Forward.  Q [N,D] bf16 (normalised queries), Kmat [K,D] bf16 keys, P [N,D] fp32 optional positive keys
+// (MoCo), label int64 [N] (when P == NULL), excl int32 [N] optional.  Outputs as passl_b200_simce_fwd_f32.
+extern "C" int passl_b200_infonce_tc_fwd(const void* Q, const void* Kmat, const float* P, const long long* label,
+                                         const int* excl, float scale, float loss_scale, int N, int K, int D, float* lse,
+                                         float* tgt, float* loss_rows, float* out_scalars, void* workspace,
+                                         long long workspace_bytes, void* stream) {
+  if (N <= 0 || K <= 0 || D < 64 || D % 64 || D > 512) return PB_ERR_BAD_ARG;
+  if (!P && !label) return PB_ERR_BAD_ARG;
+  if ((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(Kmat) | reinterpret_cast<uintptr_t>(P)) & 15) return PB_ERR_BAD_ARG;
+  if (workspace_bytes < passl_b200_infonce_tc_workspace_bytes(N, K, D)) return PB_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  InfoNceTcParams p;
+  memset(&p, 0, sizeof(p));
+  int MB, smem;
+  nce_plan(N, K, D, MB, p.row_groups, p.slices, p.tiles, smem);
+  p.Q = reinterpret_cast<const __nv_bfloat16*>(Q);
+  p.Kmat = reinterpret_cast<const __nv_bfloat16*>(Kmat);
+  p.P = P; p.label = label; p.excl = excl; p.scale = scale; p.N = N; p.K = K; p.D = D;
+  char* ws = reinterpret_cast<char*>(workspace);
+  p.part_m = reinterpret_cast<float*>(ws); ws += (size_t)N * p.slices * 4;
+  p.part_l = reinterpret_cast<float*>(ws); ws += (size_t)N * p.slices * 4;
+  p.part_cnt = reinterpret_cast<int*>(ws);
+  p.tgt = tgt;
+  uint64_t qd[2] = {(uint64_t)D, (uint64_t)N}, qs[1] = {(uint64_t)D * 2};
+  uint32_t qb[2] = {64, 128};
+  int rc = make_tmap_bf16(&p.q_map, Q, 2, qd, qs, qb);
+  if (rc) return rc;
+  uint64_t kd[2] = {(uint64_t)D, (uint64_t)K};
+  uint32_t kbx[2] = {64, NCE_BK};
+  rc = make_tmap_bf16(&p.k_map, Kmat, 2, kd, qs, kbx);
+  if (rc) return rc;
+  int grid = p.row_groups * p.slices;
+  if (MB == 2) {
+    PB_CUDA_CHECK(cudaFuncSetAttribute(infonce_tc_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    infonce_tc_fwd_kernel<2><<<grid, 64 + 256, smem, st>>>(p);
+  } else {
+    PB_CUDA_CHECK(cudaFuncSetAttribute(infonce_tc_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    infonce_tc_fwd_kernel<1><<<grid, 64 + 128, smem, st>>>(p);
+  }
+  PB_LAUNCH_CHECK();
+  simce_finalize_kernel<<<1, 1024, 0, st>>>(p.part_m, p.part_l, p.part_cnt, tgt, N, p.slices, P ? 1 : 0, loss_scale,
+                                             lse, loss_rows, out_scalars);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}

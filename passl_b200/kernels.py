@@ -156,6 +156,27 @@ def simce_bwd(a, b, lse, tgt, *, pos=None, label=None, excl=None, scale=1.0, los
     return da
 
 
+def infonce_tc_fwd(q_bf16, keys_bf16, *, pos=None, label=None, excl=None, scale=1.0, loss_scale=1.0, want_rows=False):
+    """tcgen05 fused InfoNCE forward: q [N,D] bf16, keys [K,D] bf16 (streamed once), pos [N,D] fp32 optional."""
+    _need_cuda(q_bf16, keys_bf16)
+    lib = _lib.load()
+    N, D = q_bf16.shape
+    K = keys_bf16.shape[0]
+    assert q_bf16.dtype == torch.bfloat16 and keys_bf16.dtype == torch.bfloat16
+    assert q_bf16.is_contiguous() and keys_bf16.is_contiguous()
+    dev = q_bf16.device
+    lse = torch.empty(N, dtype=torch.float32, device=dev)
+    tgt = torch.empty(N, dtype=torch.float32, device=dev)
+    rows = torch.empty(N, dtype=torch.float32, device=dev) if want_rows else None
+    out = torch.empty(3, dtype=torch.float32, device=dev)
+    ws = workspace(lib.passl_b200_infonce_tc_workspace_bytes(N, K, D), dev, "infonce_tc")
+    code = lib.passl_b200_infonce_tc_fwd(_ptr(q_bf16), _ptr(keys_bf16), _ptr(pos), _ptr(label), _ptr(excl), float(scale),
+                                         float(loss_scale), N, K, D, _ptr(lse), _ptr(tgt), _ptr(rows), _ptr(out), _ptr(ws),
+                                         ws.numel(), _stream())
+    _lib.check(code, "infonce_tc_fwd")
+    return out, lse, tgt, rows
+
+
 # ------------------------------------------------------------------------------------------------------------
 # Embedding utilities
 # ------------------------------------------------------------------------------------------------------------

@@ -5,7 +5,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gp
 rc=0
 for f in ${@:-tests/test_*_gpu.py}; do
   b=$(basename $f .py)
-  timeout 600 python -m pytest $f -q -m gpu -x --timeout 300 > gpurun_out/$b.log 2>&1
+  timeout 600 python -m pytest $f -q -m gpu --timeout 300 > gpurun_out/$b.log 2>&1
   r=$?
   echo "== $b rc=$r"; tail -n 25 gpurun_out/$b.log
   [ $r -ne 0 ] && rc=$r
