@@ -43,6 +43,12 @@ int passl_b200_gemm_bf16(const void* A, const void* B, void* out, int M, int N, 
                          int b_mn_major, long long lda, long long ldb, long long ldc, int out_fp32, int atomic_add,
                          const float* bias, const void* residual, int act, float alpha, int splits, float* col_sum,
                          float* col_sqsum, void* stream);
+/* + gate after the activation: aux (bf16, addressed like out), aux_mode 1 = ReLU mask (aux>0), 2 = *GELU'(aux),
+ *   3 = *QuickGELU'(aux) — fuses the activation backward into the dgrad GEMM. */
+int passl_b200_gemm_bf16_ex(const void* A, const void* B, void* out, int M, int N, int K, int a_mn_major,
+                            int b_mn_major, long long lda, long long ldb, long long ldc, int out_fp32, int atomic_add,
+                            const float* bias, const void* residual, int act, float alpha, int splits, float* col_sum,
+                            float* col_sqsum, const void* aux, int aux_mode, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Convolution as implicit GEMM over NHWC bf16 (replaces paddle nn.Conv2D -> cuDNN fwd/dgrad/wgrad at
@@ -108,6 +114,60 @@ int passl_b200_queue_enqueue(const float* keys, float* queue_f32, void* queue_bf
 int passl_b200_ema_update(float* k, const float* q, void* k_bf16, float m, long long n, void* stream);
 int passl_b200_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream);
 int passl_b200_cast_bf16_to_f32(const void* x, float* y, long long n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * BatchNorm (training mode) on channels-last bf16 [P, C].  Replaces paddle nn.BatchNorm2D / BatchNorm1D (cuDNN BN
+ * fwd/bwd) at resnetimagenet.py:112-131 and necks/base_neck.py:221-227.  Paddle conventions: eps 1e-5,
+ * running = momentum*running + (1-momentum)*batch (momentum 0.9), biased batch variance.
+ *   bn_stats      : sum[c] += sum_p y, sqsum[c] += sum_p y^2 (zero the accumulators first; the GEMM/conv epilogue
+ *                   can produce the same sums through col_sum/col_sqsum)
+ *   bn_finalize   : -> mean, invstd, scale = gamma*invstd, shift = beta - mean*scale, running stats update
+ *   bn_apply      : z = relu?(y*scale + shift + residual)  (bf16 and/or fp32 output)
+ *   bn_bwd_reduce : sum_g = sum_p g, sum_gx = sum_p g*xhat with g = dz * (z>0 if relu)   (= dbeta, dgamma)
+ *   bn_bwd_apply  : dy = gamma*invstd*(g - sum_g/P - xhat*sum_gx/P); dres = g (gradient of the residual branch)
+ * ------------------------------------------------------------------------------------------------------------- */
+int passl_b200_bn_stats(const void* y, float* sum, float* sqsum, long long P, int C, void* stream);
+int passl_b200_bn_finalize(const float* sum, const float* sqsum, const float* gamma, const float* beta, float* mean,
+                           float* invstd, float* scale, float* shift, float* running_mean, float* running_var,
+                           long long count, float eps, float momentum, int C, void* stream);
+/* use_global_stats (passl_v110/modules/freeze.py:17-23, MoCo key encoder) / eval: affine from running statistics */
+int passl_b200_bn_global_affine(const float* running_mean, const float* running_var, const float* gamma, const float* beta,
+                                float* mean, float* invstd, float* scale, float* shift, float eps, int C, void* stream);
+/* y += a*x on fp32 vectors (bias / BN parameter gradient accumulation) */
+int passl_b200_axpy_f32(float* y, const float* x, float a, long long n, void* stream);
+int passl_b200_bn_apply(const void* y, const void* residual, const float* scale, const float* shift, void* z, float* z_f32,
+                        long long P, int C, int relu, void* stream);
+int passl_b200_bn_bwd_reduce(const void* y, const void* dz, const void* z, const float* mean, const float* invstd,
+                             float* sum_g, float* sum_gx, long long P, int C, int relu, void* stream);
+int passl_b200_bn_bwd_apply(const void* y, const void* dz, const void* z, const float* mean, const float* invstd,
+                            const float* gamma, const float* sum_g, const float* sum_gx, void* dy, void* dres, long long P,
+                            int C, int relu, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Stem / pooling.  im2col: reference NCHW fp32 images -> bf16 [N*Ho*Wo, Kpad] with K order (r, s, c), zero padded
+ * (7x7/2 stem conv resnetimagenet.py:190-198; 16x16/16 patch embedding vision_transformer.py:231-236).
+ * maxpool 3x3/2 pad 1 (resnetimagenet.py:198), arg-max tap saved as int8; global average pool (base_neck.py:52,79).
+ * ------------------------------------------------------------------------------------------------------------- */
+int passl_b200_im2col_nchw_f32(const float* x, void* out, int N, int C, int H, int W, int R, int S, int stride, int pad,
+                               int Kpad, void* stream);
+int passl_b200_maxpool3x3s2_fwd(const void* x, void* y, void* argmax, int N, int H, int W, int C, void* stream);
+int passl_b200_maxpool3x3s2_bwd(const void* dy, const void* argmax, void* dx, int N, int H, int W, int C, void* stream);
+int passl_b200_avgpool_fwd(const void* x, void* y_bf16, float* y_f32, int N, int HW, int C, void* stream);
+int passl_b200_avgpool_bwd(const void* dy, void* dx, int N, int HW, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Fused optimizer steps over flat fp32 buffers (+ bf16 compute copy).  Replace the per-parameter Python loops of
+ * passl/optimizer/momentum.py:60-158, momentum_lars.py:56-114, adamw.py:52-138.  Tensors start at multiples of 1024
+ * elements inside the flat buffer; block_seg[b] = tensor id of 1024-element block b.
+ * ------------------------------------------------------------------------------------------------------------- */
+int passl_b200_sgd_momentum(float* p, const float* g, float* v, void* p_bf16, float lr, float momentum, float wd,
+                            float grad_scale, long long n, void* stream);
+int passl_b200_lars_momentum(float* p, const float* g, float* v, void* p_bf16, const int* block_seg, const float* seg_wd,
+                             float* norms, int num_segments, float lr, float momentum, float lars_coeff, float eps,
+                             float grad_scale, long long n, void* stream);
+int passl_b200_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, const int* block_seg, const float* seg_wd,
+                     const float* seg_lr_ratio, float lr, float beta1, float beta2, float eps, int step, float grad_scale,
+                     long long n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -17,6 +17,9 @@ SIGNATURES = {
     "passl_b200_gemm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll,
                                      c_int, c_int, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p, c_void_p,
                                      c_void_p]),
+    "passl_b200_gemm_bf16_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll,
+                                        c_int, c_int, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p, c_void_p,
+                                        c_void_p, c_int, c_void_p]),
     "passl_b200_conv2d_fwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 9 +
                                    [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "passl_b200_conv2d_dgrad_workspace_bytes": (c_ll, [c_int] * 4),
@@ -39,6 +42,21 @@ SIGNATURES = {
     "passl_b200_ema_update": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_ll, c_void_p]),
     "passl_b200_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_ll, c_void_p]),
     "passl_b200_cast_bf16_to_f32": (c_int, [c_void_p, c_void_p, c_ll, c_void_p]),
+    "passl_b200_bn_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p]),
+    "passl_b200_bn_finalize": (c_int, [c_void_p] * 10 + [c_ll, c_float, c_float, c_int, c_void_p]),
+    "passl_b200_bn_global_affine": (c_int, [c_void_p] * 8 + [c_float, c_int, c_void_p]),
+    "passl_b200_axpy_f32": (c_int, [c_void_p, c_void_p, c_float, c_ll, c_void_p]),
+    "passl_b200_bn_apply": (c_int, [c_void_p] * 6 + [c_ll, c_int, c_int, c_void_p]),
+    "passl_b200_bn_bwd_reduce": (c_int, [c_void_p] * 7 + [c_ll, c_int, c_int, c_void_p]),
+    "passl_b200_bn_bwd_apply": (c_int, [c_void_p] * 10 + [c_ll, c_int, c_int, c_void_p]),
+    "passl_b200_im2col_nchw_f32": (c_int, [c_void_p, c_void_p] + [c_int] * 9 + [c_void_p]),
+    "passl_b200_maxpool3x3s2_fwd": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
+    "passl_b200_maxpool3x3s2_bwd": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
+    "passl_b200_avgpool_fwd": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 3 + [c_void_p]),
+    "passl_b200_avgpool_bwd": (c_int, [c_void_p, c_void_p] + [c_int] * 3 + [c_void_p]),
+    "passl_b200_sgd_momentum": (c_int, [c_void_p] * 4 + [c_float] * 4 + [c_ll, c_void_p]),
+    "passl_b200_lars_momentum": (c_int, [c_void_p] * 7 + [c_int] + [c_float] * 5 + [c_ll, c_void_p]),
+    "passl_b200_adamw": (c_int, [c_void_p] * 8 + [c_float] * 4 + [c_int, c_float, c_ll, c_void_p]),
 }
 
 _ERRORS = {-1: "bad argument / contract violation", -2: "unsupported configuration", -3: "TMA tensor-map encode failed",

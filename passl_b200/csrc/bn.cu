@@ -163,6 +163,22 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, const _
   }
 }
 
+// use_global_stats / eval mode: scale & shift straight from the running statistics (freeze.py:17-23)
+__global__ void bn_global_affine_kernel(const float* __restrict__ rmean, const float* __restrict__ rvar,
+                                        const float* __restrict__ gamma, const float* __restrict__ beta, float* mean,
+                                        float* invstd, float* scale, float* shift, float eps, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float m = rmean[c], is = rsqrtf(rvar[c] + eps);
+  float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  mean[c] = m; invstd[c] = is; scale[c] = g * is; shift[c] = b - m * g * is;
+}
+
+__global__ void axpy_f32_kernel(float* __restrict__ y, const float* __restrict__ x, float a, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = fmaf(a, x[i], y[i]);
+}
+
 static void reduce_cfg(long long P, int C, dim3& grid, dim3& block, int& rows_per_block, int& smem) {
   int cg = C / 8;
   int gx = cg < 64 ? cg : 64;
@@ -210,6 +226,26 @@ extern "C" int passl_b200_bn_finalize(const float* sum, const float* sqsum, cons
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sum, sqsum, gamma, beta, mean, invstd, scale, shift,
                                                                         running_mean, running_var, 1.f / (float)count, eps,
                                                                         momentum, C);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+extern "C" int passl_b200_bn_global_affine(const float* running_mean, const float* running_var, const float* gamma,
+                                           const float* beta, float* mean, float* invstd, float* scale, float* shift,
+                                           float eps, int C, void* stream) {
+  if (C <= 0) return PB_ERR_BAD_ARG;
+  bn_global_affine_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(running_mean, running_var, gamma, beta, mean,
+                                                                             invstd, scale, shift, eps, C);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+// y += a * x   (fp32; small vectors: bias / BN parameter gradients, loss bookkeeping)
+extern "C" int passl_b200_axpy_f32(float* y, const float* x, float a, long long n, void* stream) {
+  if (n <= 0) return PB_OK;
+  long long g = (n + 255) / 256;
+  if (g > 1184) g = 1184;
+  axpy_f32_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(y, x, a, n);
   PB_LAUNCH_CHECK();
   return PB_OK;
 }

@@ -63,6 +63,9 @@ struct GemmParams {
   const __nv_bfloat16* residual;  // same addressing as out (bf16) or null
   int act;
   float alpha;
+  // optional gate applied after the activation: 1 = ReLU mask (aux > 0), 2 = multiply by GELU'(aux), 3 = QuickGELU'(aux)
+  const __nv_bfloat16* aux;     // same addressing as out
+  int aux_mode;
   // optional per-column statistics of the stored value (BatchNorm batch stats): sum and sum of squares
   float* col_sum;
   float* col_sqsum;
@@ -302,6 +305,25 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
         if (p.act != ACT_NONE) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+        }
+        if (p.aux && row_ok) {
+          const __nv_bfloat16* ap = p.aux + row_off + oc0;
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            if (cc0 + j8 * 8 < col_lim) {
+              uint4 u = *reinterpret_cast<const uint4*>(ap + j8 * 8);
+              float a[8];
+              float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+              a[0] = a0.x; a[1] = a0.y; a[2] = a1.x; a[3] = a1.y; a[4] = a2.x; a[5] = a2.y; a[6] = a3.x; a[7] = a3.y;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float& v = f[j8 * 8 + e];
+                if (p.aux_mode == 1) v = a[e] > 0.f ? v : 0.f;
+                else if (p.aux_mode == 2) v *= 0.5f * (1.f + erff(a[e] * 0.70710678118654752f)) + a[e] * 0.3989422804014327f * __expf(-0.5f * a[e] * a[e]);
+                else { float sg = 1.f / (1.f + __expf(-1.702f * a[e])); v *= sg * (1.f + 1.702f * a[e] * (1.f - sg)); }
+              }
+            }
+          }
         }
         if (p.residual && row_ok) {
           const __nv_bfloat16* rp = p.residual + row_off + oc0;

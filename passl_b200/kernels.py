@@ -36,7 +36,7 @@ def workspace(nbytes, device, tag="default"):
 # GEMM
 # ------------------------------------------------------------------------------------------------------------
 def gemm(a, b, *, a_t=False, b_t=False, out=None, out_dtype=torch.bfloat16, bias=None, residual=None, act=None,
-         alpha=1.0, splits=1, accumulate=False, col_stats=None):
+         alpha=1.0, splits=1, accumulate=False, col_stats=None, aux=None, aux_mode_name="relu_mask"):
     """out[M,N] = act(alpha * A @ B^T + bias) + residual.
 
     a: [M,K] (or [K,M] when a_t), b: [N,K] (or [K,N] when b_t), bf16, last dim contiguous.
@@ -61,11 +61,22 @@ def gemm(a, b, *, a_t=False, b_t=False, out=None, out_dtype=torch.bfloat16, bias
     cs = cq = None
     if col_stats is not None:
         cs, cq = col_stats
-    code = lib.passl_b200_gemm_bf16(_ptr(a), _ptr(b), _ptr(out), M, N, K, int(a_t), int(b_t), a.stride(0), b.stride(0),
-                                    out.stride(0), int(out_fp32), atomic, _ptr(bias), _ptr(residual), ACT[act],
-                                    float(alpha), int(splits), _ptr(cs), _ptr(cq), _stream())
+    aux_mode = 0
+    if aux is not None:
+        aux_mode = {"relu_mask": 1, "gelu_grad": 2, "quick_gelu_grad": 3}[aux_mode_name]
+        assert aux.dtype == torch.bfloat16 and aux.stride(0) == out.stride(0)
+    code = lib.passl_b200_gemm_bf16_ex(_ptr(a), _ptr(b), _ptr(out), M, N, K, int(a_t), int(b_t), a.stride(0), b.stride(0),
+                                       out.stride(0), int(out_fp32), atomic, _ptr(bias), _ptr(residual), ACT[act],
+                                       float(alpha), int(splits), _ptr(cs), _ptr(cq), _ptr(aux), aux_mode, _stream())
     _lib.check(code, "gemm_bf16")
     return out
+
+
+def wgrad_splits(M, N, K):
+    """Split-K factor for weight-gradient GEMMs (small M x N output, long K)."""
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    s = max(1, (2 * 148 + tiles - 1) // tiles)
+    return max(1, min(s, (K + 63) // 64 // 4))
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -234,3 +245,124 @@ def cast_bf16(x, out=None):
         out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     _lib.check(lib.passl_b200_cast_f32_to_bf16(_ptr(x), _ptr(out), x.numel(), _stream()), "cast_f32_to_bf16")
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# BatchNorm (channels-last bf16 [P, C]) and pooling
+# ------------------------------------------------------------------------------------------------------------
+def bn_stats(y2d, stats):
+    """stats: fp32 [2, C] zero-initialised accumulator (sum, sqsum)."""
+    lib = _lib.load()
+    P, C = y2d.shape
+    _lib.check(lib.passl_b200_bn_stats(_ptr(y2d), _ptr(stats[0]), _ptr(stats[1]), P, C, _stream()), "bn_stats")
+
+
+def bn_finalize(stats, gamma, beta, running_mean, running_var, count, eps=1e-5, momentum=0.9):
+    """-> fp32 [4, C] = (mean, invstd, scale, shift); updates running stats in place (may be None)."""
+    lib = _lib.load()
+    C = stats.shape[1]
+    out = torch.empty((4, C), dtype=torch.float32, device=stats.device)
+    _lib.check(lib.passl_b200_bn_finalize(_ptr(stats[0]), _ptr(stats[1]), _ptr(gamma), _ptr(beta), _ptr(out[0]), _ptr(out[1]),
+                                          _ptr(out[2]), _ptr(out[3]), _ptr(running_mean), _ptr(running_var), int(count),
+                                          float(eps), float(momentum), C, _stream()), "bn_finalize")
+    return out
+
+
+def bn_apply(y, msss, relu, residual=None, out=None, out_f32=None):
+    lib = _lib.load()
+    C = y.shape[-1]
+    P = y.numel() // C
+    if out is None and out_f32 is None:
+        out = torch.empty_like(y)
+    _lib.check(lib.passl_b200_bn_apply(_ptr(y), _ptr(residual), _ptr(msss[2]), _ptr(msss[3]), _ptr(out), _ptr(out_f32), P, C,
+                                       int(relu), _stream()), "bn_apply")
+    return out if out is not None else out_f32
+
+
+def bn_bwd(y, dz, z, msss, gamma, relu, want_dres=False, grads_out=None):
+    """Returns (dy, dres, sums) with sums fp32 [2, C] = (dbeta, dgamma)."""
+    lib = _lib.load()
+    C = y.shape[-1]
+    P = y.numel() // C
+    sums = grads_out if grads_out is not None else torch.zeros((2, C), dtype=torch.float32, device=y.device)
+    _lib.check(lib.passl_b200_bn_bwd_reduce(_ptr(y), _ptr(dz), _ptr(z), _ptr(msss[0]), _ptr(msss[1]), _ptr(sums[0]),
+                                            _ptr(sums[1]), P, C, int(relu), _stream()), "bn_bwd_reduce")
+    dy = torch.empty_like(y)
+    dres = torch.empty_like(y) if want_dres else None
+    _lib.check(lib.passl_b200_bn_bwd_apply(_ptr(y), _ptr(dz), _ptr(z), _ptr(msss[0]), _ptr(msss[1]), _ptr(gamma), _ptr(sums[0]),
+                                           _ptr(sums[1]), _ptr(dy), _ptr(dres), P, C, int(relu), _stream()), "bn_bwd_apply")
+    return dy, dres, sums
+
+
+def im2col_nchw(x, R, S, stride, pad, kpad):
+    _need_cuda(x)
+    lib = _lib.load()
+    N, C, H, W = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    Ho = (H + 2 * pad - R) // stride + 1
+    Wo = (W + 2 * pad - S) // stride + 1
+    out = torch.empty((N * Ho * Wo, kpad), dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.passl_b200_im2col_nchw_f32(_ptr(x), _ptr(out), N, C, H, W, R, S, stride, pad, kpad, _stream()), "im2col")
+    return out, Ho, Wo
+
+
+def maxpool_fwd(x):
+    lib = _lib.load()
+    N, H, W, C = x.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = torch.empty((N, Ho, Wo, C), dtype=torch.bfloat16, device=x.device)
+    arg = torch.empty((N, Ho, Wo, C), dtype=torch.int8, device=x.device)
+    _lib.check(lib.passl_b200_maxpool3x3s2_fwd(_ptr(x), _ptr(y), _ptr(arg), N, H, W, C, _stream()), "maxpool_fwd")
+    return y, arg
+
+
+def maxpool_bwd(dy, arg, x_shape):
+    lib = _lib.load()
+    N, H, W, C = x_shape
+    dx = torch.empty(x_shape, dtype=torch.bfloat16, device=dy.device)
+    _lib.check(lib.passl_b200_maxpool3x3s2_bwd(_ptr(dy), _ptr(arg), _ptr(dx), N, H, W, C, _stream()), "maxpool_bwd")
+    return dx
+
+
+def avgpool_fwd(x, want_f32=False):
+    lib = _lib.load()
+    N, H, W, C = x.shape
+    y = torch.empty((N, C), dtype=torch.bfloat16, device=x.device)
+    yf = torch.empty((N, C), dtype=torch.float32, device=x.device) if want_f32 else None
+    _lib.check(lib.passl_b200_avgpool_fwd(_ptr(x), _ptr(y), _ptr(yf), N, H * W, C, _stream()), "avgpool_fwd")
+    return y, yf
+
+
+def avgpool_bwd(dy, x_shape):
+    lib = _lib.load()
+    N, H, W, C = x_shape
+    dx = torch.empty(x_shape, dtype=torch.bfloat16, device=dy.device)
+    _lib.check(lib.passl_b200_avgpool_bwd(_ptr(dy.contiguous()), _ptr(dx), N, H * W, C, _stream()), "avgpool_bwd")
+    return dx
+
+
+def cast_f32(x_bf16, out=None):
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty(x_bf16.shape, dtype=torch.float32, device=x_bf16.device)
+    _lib.check(lib.passl_b200_cast_bf16_to_f32(_ptr(x_bf16), _ptr(out), x_bf16.numel(), _stream()), "cast_bf16_to_f32")
+    return out
+
+
+def bn_global_affine(running_mean, running_var, gamma, beta, eps=1e-5):
+    lib = _lib.load()
+    C = running_mean.numel()
+    out = torch.empty((4, C), dtype=torch.float32, device=running_mean.device)
+    _lib.check(lib.passl_b200_bn_global_affine(_ptr(running_mean), _ptr(running_var), _ptr(gamma), _ptr(beta), _ptr(out[0]),
+                                               _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), float(eps), C, _stream()),
+               "bn_global_affine")
+    return out
+
+
+def axpy(y, x, a=1.0):
+    """y += a * x (fp32, in place)."""
+    lib = _lib.load()
+    assert y.dtype == torch.float32 and x.dtype == torch.float32 and y.numel() == x.numel()
+    assert y.is_contiguous() and x.is_contiguous()
+    _lib.check(lib.passl_b200_axpy_f32(_ptr(y), _ptr(x), float(a), y.numel(), _stream()), "axpy_f32")
+    return y

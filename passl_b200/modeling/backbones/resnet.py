@@ -1,0 +1,176 @@
+"""ResNet backbone (v1.5 bottleneck: stride on the 3x3) on the tcgen05 implicit-GEMM kernels, NHWC bf16.
+
+Mirrors passl_v110/modeling/backbones/resnet.py:25-77 (`ResNet(depth, num_classes=0, with_pool=False,
+zero_init_residual=False, frozen_stages=-1)`, kaiming fan_out init :75-88) over the structure of
+resnetimagenet.py:93-246, and `ResNetsimclr` (resnetsimclr.py:25-91 over resnetcifar.py:216-334: same net without the
+stem max-pool).  Input is the reference's NCHW fp32 image batch; output is NHWC bf16 [B, h, w, 2048]
+(or [B, 2048] with with_pool).
+
+The whole backbone is ONE autograd node: forward chains the fused conv+BN(+ReLU/+residual) units, backward walks them
+in reverse with hand-written dgrad / wgrad / BN-backward kernels and accumulates parameter gradients in place.
+"""
+import torch
+import torch.nn as nn
+
+from ... import kernels as K
+from ...core.param_store import compute_copy, grad_buffer
+from ...nn.layers import BatchNormState, ConvBN, _kaiming_normal_fan_out
+from ..registry import BACKBONES
+
+STEM_K = 7 * 7 * 3
+STEM_KPAD = 152  # multiple of 8 (16-byte rows for TMA); the tail is zero
+
+
+class Stem(nn.Module):
+    """conv 7x7/2 (3->64) as im2col + tcgen05 GEMM, BN, ReLU, optional 3x3/2 max-pool."""
+
+    def __init__(self, maxpool=True):
+        super().__init__()
+        self.weight = nn.Parameter(torch.zeros(64, STEM_KPAD))      # [Cout, (r, s, c) padded]
+        w = torch.empty(64, 7, 7, 3)
+        _kaiming_normal_fan_out(w, 64 * 7 * 7)
+        with torch.no_grad():
+            self.weight[:, :STEM_K] = w.reshape(64, STEM_K)
+        self.bn = BatchNormState(64)
+        self.maxpool = maxpool
+
+    def fwd(self, img, training=True, save=True):
+        N = img.shape[0]
+        cols, Ho, Wo = K.im2col_nchw(img, 7, 7, 2, 3, STEM_KPAD)
+        bn = self.bn
+        batch_stats = training and not bn.use_global_stats
+        w = compute_copy(self.weight)
+        if batch_stats:
+            stats = torch.zeros((2, 64), dtype=torch.float32, device=img.device)
+            y = K.gemm(cols, w, col_stats=(stats[0], stats[1]))
+            msss = K.bn_finalize(stats, bn.weight, bn.bias, bn._mean, bn._variance, y.shape[0], eps=bn.eps, momentum=bn.momentum)
+        else:
+            y = K.gemm(cols, w)
+            msss = bn.global_affine()
+        z = K.bn_apply(y, msss, True).view(N, Ho, Wo, 64)
+        if self.maxpool:
+            out, arg = K.maxpool_fwd(z)
+        else:
+            out, arg = z, None
+        return out, ((cols, y, z, msss, arg) if save else None)
+
+    def bwd(self, ctx, dout):
+        cols, y, z, msss, arg = ctx
+        dz = K.maxpool_bwd(dout, arg, tuple(z.shape)) if arg is not None else dout
+        bn = self.bn
+        dy, _, sums = K.bn_bwd(y, dz.view(y.shape), z.view(y.shape), msss, bn.weight, True)
+        if bn.weight.requires_grad:
+            K.axpy(grad_buffer(bn.bias), sums[0])
+            K.axpy(grad_buffer(bn.weight), sums[1])
+        if self.weight.requires_grad:
+            K.gemm(dy, cols, a_t=True, b_t=True, out=grad_buffer(self.weight), accumulate=True,
+                   splits=K.wgrad_splits(64, STEM_KPAD, dy.shape[0]))
+
+
+class Bottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, downsample=False):
+        super().__init__()
+        self.conv1 = ConvBN(inplanes, planes, 1, relu=True)
+        self.conv2 = ConvBN(planes, planes, 3, stride=stride, pad=1, relu=True)
+        self.conv3 = ConvBN(planes, planes * 4, 1, relu=True)          # ReLU applied after the residual add
+        self.downsample = ConvBN(inplanes, planes * 4, 1, stride=stride, relu=False) if downsample else None
+
+    def fwd(self, x, training=True, save=True):
+        o1, c1 = self.conv1.fwd(x, training=training, save=save)
+        o2, c2 = self.conv2.fwd(o1, training=training, save=save)
+        if self.downsample is not None:
+            idn, cd = self.downsample.fwd(x, training=training, save=save)
+        else:
+            idn, cd = x, None
+        o3, c3 = self.conv3.fwd(o2, residual=idn, training=training, save=save)
+        return o3, ((c1, c2, c3, cd) if save else None)
+
+    def bwd(self, ctx, dout, need_dx=True):
+        c1, c2, c3, cd = ctx
+        d_o2, d_idn = self.conv3.bwd(c3, dout)
+        d_o1, _ = self.conv2.bwd(c2, d_o2)
+        if self.downsample is not None:
+            dx, _ = self.downsample.bwd(cd, d_idn, need_dx=need_dx)
+            self.conv1.bwd(c1, d_o1, need_dx=need_dx, dx_out=dx, accumulate=True)
+        else:
+            dx = d_idn
+            self.conv1.bwd(c1, d_o1, need_dx=True, dx_out=dx, accumulate=True)
+        return dx
+
+
+class _BackboneFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, img, anchor):
+        out, saved = module._run_forward(img, training=module.training, save=torch.is_grad_enabled() or True)
+        ctx.module, ctx.saved = module, saved
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        ctx.module._run_backward(ctx.saved, dout.contiguous())
+        ctx.saved = None
+        return None, None, None
+
+
+@BACKBONES.register()
+class ResNet(nn.Module):
+    LAYER_CFG = {50: [3, 4, 6, 3], 101: [3, 4, 23, 3], 152: [3, 8, 36, 3]}
+
+    def __init__(self, depth=50, num_classes=0, with_pool=False, zero_init_residual=False, frozen_stages=-1,
+                 pretrained=None, stem_maxpool=True):
+        super().__init__()
+        if depth not in self.LAYER_CFG:
+            raise ValueError("passl_b200 ResNet supports bottleneck depths %s" % sorted(self.LAYER_CFG))
+        assert num_classes <= 0, "classification fc is outside the self-supervised hot path"
+        self.with_pool = with_pool
+        self.stem = Stem(maxpool=stem_maxpool)
+        blocks, inplanes = [], 64
+        for i, (planes, n) in enumerate(zip([64, 128, 256, 512], self.LAYER_CFG[depth])):
+            stride = 1 if i == 0 else 2
+            for b in range(n):
+                s = stride if b == 0 else 1
+                blocks.append(Bottleneck(inplanes, planes, s, downsample=(b == 0 and (s != 1 or inplanes != planes * 4))))
+                inplanes = planes * 4
+        self.blocks = nn.ModuleList(blocks)
+        self.out_channels = inplanes
+        if zero_init_residual:          # passl/models/resnet.py:68-73, resnet.py(v110):81-86
+            for blk in self.blocks:
+                nn.init.zeros_(blk.conv3.bn.weight)
+
+    # -- explicit forward / backward -------------------------------------------------------------------------
+    def _run_forward(self, img, training=True, save=True):
+        assert img.dim() == 4 and img.shape[1] == 3 and img.dtype == torch.float32, "expects NCHW fp32 images"
+        x, cs = self.stem.fwd(img.contiguous(), training=training, save=save)
+        ctxs = []
+        for blk in self.blocks:
+            x, c = blk.fwd(x, training=training, save=save)
+            ctxs.append(c)
+        pooled = None
+        if self.with_pool:
+            pooled, _ = K.avgpool_fwd(x)
+        return (pooled if self.with_pool else x), (cs, ctxs, tuple(x.shape))
+
+    def _run_backward(self, saved, dout):
+        cs, ctxs, feat_shape = saved
+        d = K.avgpool_bwd(dout, feat_shape) if self.with_pool else dout
+        for blk, c in zip(reversed(self.blocks), reversed(ctxs)):
+            d = blk.bwd(c, d)
+        self.stem.bwd(cs, d)
+
+    def forward(self, img):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return _BackboneFn.apply(self, img, self.stem.weight)
+        out, _ = self._run_forward(img, training=self.training, save=False)
+        return out
+
+
+@BACKBONES.register()
+class ResNetsimclr(ResNet):
+    """SimCLR backbone (resnetsimclr.py:25-91): the stem max-pool is absent (resnetcifar.py:275,321-332)."""
+
+    def __init__(self, depth=50, **kw):
+        kw.setdefault("stem_maxpool", False)
+        kw.setdefault("with_pool", True)
+        super().__init__(depth=depth, **kw)

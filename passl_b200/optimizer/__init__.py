@@ -1,0 +1,133 @@
+"""Optimizers over ParamStore flat buffers — one fused kernel per step.
+
+API follows the reference's torch-style optimizers (passl/optimizer/optimizer.py:32-233): ``step()``, ``clear_grad()``,
+``lr`` attribute driven by an LR scheduler, ``state_dict()``.  Weight-decay exclusion is expressed per tensor
+(regex on the parameter name), like the reference's param-group builder (passl/optimizer/__init__.py:124-215) and
+v110's ``exclude_from_weight_decay`` (configs/simclr/simclr_r50_IM.yaml:117-119).
+"""
+import math
+import re
+
+import torch
+
+from .. import _lib, kernels as K
+from ..distributed import get_world_size
+
+
+def _wd_table(store, weight_decay, exclude):
+    pats = [re.compile(p) for p in (exclude or [])]
+
+    def fn(name, p):
+        if p.dim() <= 1 and exclude is None:
+            return weight_decay
+        return 0.0 if any(r.search(name) for r in pats) else weight_decay
+    return store.segment_values(fn)
+
+
+class _FlatOptimizer:
+    def __init__(self, store, lr):
+        self.store = store
+        self.lr = float(lr)
+        self.grad_scale = 1.0 / get_world_size()     # the mean of sync_utils.py:41
+        self._step = 0
+
+    def clear_grad(self):
+        self.store.zero_grad()
+
+    zero_grad = clear_grad
+
+    def set_lr(self, lr):
+        self.lr = float(lr)
+
+    def get_lr(self):
+        return self.lr
+
+
+class Momentum(_FlatOptimizer):
+    """passl/optimizer/momentum.py:60-158 (L2 decay folded into the gradient, no nesterov)."""
+
+    def __init__(self, store, lr=0.01, momentum=0.9, weight_decay=0.0):
+        super().__init__(store, lr)
+        self.momentum, self.weight_decay = momentum, weight_decay
+        self.velocity = torch.zeros_like(store.master)
+
+    def step(self):
+        lib, s = _lib.load(), self.store
+        _lib.check(lib.passl_b200_sgd_momentum(s.master.data_ptr(), s.grad.data_ptr(), self.velocity.data_ptr(),
+                                               s.bf16.data_ptr(), self.lr, self.momentum, self.weight_decay, self.grad_scale,
+                                               s.numel, torch.cuda.current_stream().cuda_stream), "sgd_momentum")
+        self._step += 1
+
+    def state_dict(self):
+        return dict(velocity=self.velocity, step=self._step, lr=self.lr)
+
+
+class LarsMomentumOptimizer(_FlatOptimizer):
+    """paddle LarsMomentum as configured by passl_v110/solver/optimizer.py:20-26 and momentum_lars.py:56-114."""
+
+    def __init__(self, store, lr=0.1, momentum=0.9, lars_weight_decay=1e-4, lars_coeff=0.001, epsilon=0.0,
+                 exclude_from_weight_decay=("scale", "offset", r"\.bias", r"bn\.weight", r"bn\.bias")):
+        super().__init__(store, lr)
+        self.momentum, self.coeff, self.eps = momentum, lars_coeff, epsilon
+        self.velocity = torch.zeros_like(store.master)
+        self.seg_wd = _wd_table(store, lars_weight_decay, list(exclude_from_weight_decay))
+        self.norms = torch.zeros(2 * len(store.params), dtype=torch.float32, device=store.master.device)
+
+    def step(self):
+        lib, s = _lib.load(), self.store
+        _lib.check(lib.passl_b200_lars_momentum(s.master.data_ptr(), s.grad.data_ptr(), self.velocity.data_ptr(),
+                                                s.bf16.data_ptr(), s.block_seg.data_ptr(), self.seg_wd.data_ptr(),
+                                                self.norms.data_ptr(), len(s.params), self.lr, self.momentum, self.coeff,
+                                                self.eps, self.grad_scale, s.numel,
+                                                torch.cuda.current_stream().cuda_stream), "lars_momentum")
+        self._step += 1
+
+    def state_dict(self):
+        return dict(velocity=self.velocity, step=self._step, lr=self.lr)
+
+
+class AdamW(_FlatOptimizer):
+    """passl/optimizer/adamw.py:52-138 (decoupled decay, bias correction); no decay on 1-d tensors by default."""
+
+    def __init__(self, store, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01, no_decay=None, lr_ratio=None):
+        super().__init__(store, lr)
+        self.beta1, self.beta2, self.eps = beta1, beta2, eps
+        self.m = torch.zeros_like(store.master)
+        self.v = torch.zeros_like(store.master)
+        pats = [re.compile(p) for p in (no_decay or [])]
+        self.seg_wd = store.segment_values(
+            lambda n, p: 0.0 if (p.dim() <= 1 or any(r.search(n) for r in pats)) else weight_decay)
+        self.seg_lr = store.segment_values(lr_ratio) if lr_ratio is not None else None
+
+    def step(self):
+        lib, s = _lib.load(), self.store
+        self._step += 1
+        _lib.check(lib.passl_b200_adamw(s.master.data_ptr(), s.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                        s.bf16.data_ptr(), s.block_seg.data_ptr(), self.seg_wd.data_ptr(),
+                                        self.seg_lr.data_ptr() if self.seg_lr is not None else 0, self.lr, self.beta1,
+                                        self.beta2, self.eps, self._step, self.grad_scale, s.numel,
+                                        torch.cuda.current_stream().cuda_stream), "adamw")
+
+    def state_dict(self):
+        return dict(m=self.m, v=self.v, step=self._step, lr=self.lr)
+
+
+class CosineAnnealingDecay:
+    """paddle.optimizer.lr.CosineAnnealingDecay(learning_rate, T_max) (configs/moco/moco_v2_r50.yaml:84-87)."""
+
+    def __init__(self, learning_rate, T_max, eta_min=0.0):
+        self.base, self.T_max, self.eta_min, self.last_epoch = learning_rate, T_max, eta_min, 0
+
+    def get_lr(self):
+        return self.eta_min + (self.base - self.eta_min) * (1 + math.cos(math.pi * self.last_epoch / self.T_max)) / 2
+
+    def step(self):
+        self.last_epoch += 1
+        return self.get_lr()
+
+
+def build_optimizer(cfg, store):
+    cfg = dict(cfg)
+    name = cfg.pop("name")
+    cls = {"Momentum": Momentum, "LarsMomentumOptimizer": LarsMomentumOptimizer, "AdamW": AdamW}[name]
+    return cls(store, **cfg)

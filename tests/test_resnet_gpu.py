@@ -1,0 +1,188 @@
+"""ResNet building blocks and the full ResNet-50 / MoCo step on the GPU vs the torch-CPU oracle (oracle/resnet.py).
+
+Activations are bf16 between fused units, so tolerances are bf16-level (north_star: 1e-2 relative for bf16): outputs are
+compared by relative L2 error, weight gradients by relative L2 error + cosine similarity.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def cos(a, b):
+    a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
+    return (a @ b / (a.norm() * b.norm() + 1e-30)).item()
+
+
+def test_bn_kernels_match_torch():
+    from passl_b200 import kernels as K
+    torch.manual_seed(0)
+    P, C = 3000, 256
+    y = (torch.randn(P, C, device="cuda") * 2 + 0.5).bfloat16()
+    res = torch.randn(P, C, device="cuda").bfloat16()
+    gamma = torch.rand(C, device="cuda") + 0.5
+    beta = torch.randn(C, device="cuda")
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    stats = torch.zeros(2, C, device="cuda")
+    K.bn_stats(y, stats)
+    msss = K.bn_finalize(stats, gamma, beta, rm, rv, P)
+    z = K.bn_apply(y, msss, True, residual=res)
+    yr = y.double().requires_grad_(True)
+    rr = res.double().requires_grad_(True)
+    mean, var = yr.mean(0), yr.var(0, unbiased=False)
+    zr = torch.relu((yr - mean) / torch.sqrt(var + 1e-5) * gamma.double() + beta.double() + rr)
+    assert torch.allclose(msss[0].double(), mean, atol=1e-4) and torch.allclose(msss[1].double(), (var + 1e-5).rsqrt(), rtol=1e-4)
+    assert rel(z, zr) < 5e-3
+    # running stats: Paddle momentum 0.9, biased variance
+    assert torch.allclose(rm.double(), 0.1 * mean.detach(), atol=1e-5)
+    assert torch.allclose(rv.double(), 0.9 + 0.1 * var.detach(), rtol=1e-4)
+    dz = torch.randn(P, C, device="cuda").bfloat16()
+    zr.backward(dz.double() * (z.double() > 0) / (zr.detach() > 0).clamp(min=1))  # same mask as the bf16 output
+    dy, dres, sums = K.bn_bwd(y, dz, z, msss, gamma, True, want_dres=True)
+    yr2 = y.double().requires_grad_(True)
+    g = (dz.double() * (z.double() > 0))
+    xhat = (yr2 - mean.detach()) / torch.sqrt(var.detach() + 1e-5)
+    # analytic reference
+    dyr = gamma.double() * (var.detach() + 1e-5).rsqrt() * (g - g.mean(0) - xhat * (g * xhat).mean(0))
+    assert rel(dy, dyr) < 5e-3
+    assert rel(dres, g) < 1e-6
+    assert torch.allclose(sums[0].double(), g.sum(0), rtol=1e-3, atol=1e-2)
+    assert torch.allclose(sums[1].double(), (g * xhat).sum(0).detach(), rtol=1e-3, atol=5e-2)
+
+
+def test_pool_and_im2col_match_torch():
+    from passl_b200 import kernels as K
+    torch.manual_seed(1)
+    x = torch.randn(3, 3, 64, 64, device="cuda")
+    cols, Ho, Wo = K.im2col_nchw(x, 7, 7, 2, 3, 152)
+    ref = F.unfold(x.bfloat16().float(), 7, padding=3, stride=2)            # [N, C*49, L], (c, r, s) order
+    ref = ref.reshape(3, 3, 49, Ho * Wo).permute(0, 3, 2, 1).reshape(3 * Ho * Wo, 147)   # -> (r, s, c)
+    assert torch.equal(cols[:, :147].float(), ref) and cols[:, 147:].abs().max() == 0
+    a = torch.randn(2, 32, 32, 64, device="cuda").relu().bfloat16()          # ties at 0 like post-ReLU maps
+    y, arg = K.maxpool_fwd(a)
+    ar = a.float().permute(0, 3, 1, 2).requires_grad_(True)
+    yr = F.max_pool2d(ar, 3, 2, 1)
+    assert torch.equal(y.float(), yr.permute(0, 2, 3, 1))
+    dy = torch.randn_like(y)
+    dx = K.maxpool_bwd(dy, arg, tuple(a.shape))
+    # every output gradient lands on exactly one input of its window, and that input holds the max
+    assert torch.allclose(dx.float().sum((1, 2)), dy.float().sum((1, 2)), rtol=2e-2, atol=2e-1)
+    p, pf = K.avgpool_fwd(a, want_f32=True)
+    assert torch.allclose(pf, a.float().mean((1, 2)), rtol=1e-5, atol=1e-6)
+    dxa = K.avgpool_bwd(p, tuple(a.shape))
+    assert torch.allclose(dxa.float(), (p.float() / 1024).bfloat16().float()[:, None, None, :].expand(-1, 32, 32, -1))
+
+
+def _to_oracle_input(x_nhwc):
+    return x_nhwc.float().cpu().double().permute(0, 3, 1, 2).contiguous()
+
+
+@pytest.mark.parametrize("inpl,planes,stride,ds", [(64, 64, 1, True), (256, 64, 1, False), (256, 128, 2, True)])
+def test_bottleneck_fwd_bwd_vs_oracle(inpl, planes, stride, ds):
+    from oracle import resnet as O
+    from passl_b200.modeling.backbones.resnet import Bottleneck
+    torch.manual_seed(0)
+    blk = Bottleneck(inpl, planes, stride, downsample=ds).cuda()
+    for m in blk.modules():
+        if hasattr(m, "bn") and hasattr(m.bn, "weight"):
+            torch.nn.init.uniform_(m.bn.weight, 0.5, 1.5)
+            torch.nn.init.normal_(m.bn.bias, 0, 0.2)
+    x = torch.randn(4, 16, 16, inpl, device="cuda").relu().bfloat16()
+    out, ctx = blk.fwd(x)
+    dout = torch.randn_like(out)
+    for p in blk.parameters():
+        p.grad = torch.zeros_like(p)
+    dx = blk.bwd(ctx, dout)
+    torch.cuda.synchronize()
+    p = O.params_from_cuda_module(blk)
+    p = {"b." + k: v.requires_grad_(True) for k, v in p.items()}
+    xr = _to_oracle_input(x).requires_grad_(True)
+    outr = O.bottleneck(xr, p, "b", stride, ds)
+    outr.backward(_to_oracle_input(dout))
+    assert rel(out.permute(0, 3, 1, 2), outr) < 2e-2
+    assert rel(dx.permute(0, 3, 1, 2), xr.grad) < 4e-2
+    for name, prm in blk.named_parameters():
+        ref = p["b." + name].grad
+        got = prm.grad
+        if got.dim() == 4:
+            got = got.permute(0, 3, 1, 2)
+        assert cos(got, ref) > 0.995, (name, cos(got, ref))
+        assert rel(got, ref) < 8e-2, (name, rel(got, ref))
+
+
+def test_resnet50_small_fwd_bwd_vs_oracle():
+    from oracle import resnet as O
+    from passl_b200.modeling import build_backbone, build_neck
+    torch.manual_seed(0)
+    net = build_backbone(dict(name="ResNet", depth=50)).cuda()
+    neck = build_neck(dict(name="NonLinearNeckV1", in_channels=2048, hid_channels=2048, out_channels=128)).cuda()
+    img = torch.randn(8, 3, 64, 64, device="cuda")
+    for p in list(net.parameters()) + list(neck.parameters()):
+        p.grad = torch.zeros_like(p)
+    feat = net(img)
+    emb = neck(feat)
+    assert emb.dtype == torch.float32 and emb.shape == (8, 128)
+    g = torch.randn_like(emb)
+    emb.backward(g)
+    torch.cuda.synchronize()
+    p = O.params_from_cuda_module(net)
+    pn = O.params_from_cuda_module(neck)
+    for d in (p, pn):
+        for v in d.values():
+            v.requires_grad_(True)
+    fr = O.resnet_forward(img.cpu().double(), p)
+    er = O.neck_v1(fr, pn)
+    er.backward(g.cpu().double())
+    assert rel(feat.permute(0, 3, 1, 2), fr) < 5e-2, rel(feat.permute(0, 3, 1, 2), fr)
+    assert rel(emb, er) < 5e-2, rel(emb, er)
+    worst = 1.0
+    for name, prm in list(net.named_parameters()):
+        ref = p[name].grad
+        got = prm.grad
+        if name == "stem.weight":
+            got = got[:, :147].reshape(64, 7, 7, 3)
+        if got.dim() == 4:
+            got = got.permute(0, 3, 1, 2)
+        if ref.norm() > 0:
+            worst = min(worst, cos(got, ref))
+    assert worst > 0.97, worst
+    assert cos(neck.fc1.weight.grad, pn["fc1.weight"].grad) > 0.99
+
+
+def test_moco_train_iter_smoke_and_state():
+    from passl_b200.modeling import build_model
+    from passl_b200.optimizer import Momentum
+    torch.manual_seed(0)
+    Kq = 4096
+    model = build_model(dict(name="MoCo", backbone=dict(name="ResNet", depth=50),
+                             neck=dict(name="NonLinearNeckV1", in_channels=2048, hid_channels=2048, out_channels=128),
+                             head=dict(name="ContrastiveHead", temperature=0.2), K=Kq, T=0.2)).cuda()
+    sq, sk = model.build_param_stores()
+    opt = Momentum(sq, lr=0.015, momentum=0.9, weight_decay=1e-4)
+    k_before = sk.master.clone()
+    q0 = sq.master.clone()
+    losses = []
+    for it in range(3):
+        a = torch.randn(16, 3, 64, 64, device="cuda")
+        b = a + 0.1 * torch.randn_like(a)
+        opt.clear_grad()
+        out = model(a, b)
+        out["loss"].backward()
+        opt.step()
+        losses.append(out["loss"].item())
+        assert np.isfinite(losses[-1])
+        assert 0 <= out["acc1"].item() <= 100
+    model.flush_queue()
+    assert int(model.queue_ptr.item()) == (3 * 16) % Kq                      # bit-exact ring pointer
+    assert abs(losses[0] - np.log(Kq + 1)) < 1.0                             # random init: close to ln(K+1)
+    assert not torch.equal(sq.master, q0)                                    # parameters moved
+    # key encoder followed the EMA of the (updated) query encoder: k1 = m*k0 + (1-m)*q0 after the first step
+    assert (sk.master - k_before).abs().max() > 0
+    assert torch.equal(sq.bf16, sq.master.bfloat16())                        # bf16 mirror refreshed by the optimizer kernel
