@@ -300,13 +300,14 @@ extern "C" int passl_b200_infonce_tc_fwd(const void* Q, const void* Kmat, const 
   rc = make_tmap_bf16(&p.k_map, Kmat, 2, kd, qs, kbx);
   if (rc) return rc;
   int grid = p.row_groups * p.slices;
-  if (MB == 2) {
-    PB_CUDA_CHECK(cudaFuncSetAttribute(infonce_tc_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    infonce_tc_fwd_kernel<2><<<grid, 64 + 256, smem, st>>>(p);
-  } else {
-    PB_CUDA_CHECK(cudaFuncSetAttribute(infonce_tc_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    infonce_tc_fwd_kernel<1><<<grid, 64 + 128, smem, st>>>(p);
+  static bool attr_done = false;
+  if (!attr_done) {  // once per process: allow up to the full 227 KB dynamic smem carve-out
+    PB_CUDA_CHECK(cudaFuncSetAttribute(infonce_tc_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PB_CUDA_CHECK(cudaFuncSetAttribute(infonce_tc_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
   }
+  if (MB == 2) infonce_tc_fwd_kernel<2><<<grid, 64 + 256, smem, st>>>(p);
+  else infonce_tc_fwd_kernel<1><<<grid, 64 + 128, smem, st>>>(p);
   PB_LAUNCH_CHECK();
   simce_finalize_kernel<<<1, 1024, 0, st>>>(p.part_m, p.part_l, p.part_cnt, tgt, N, p.slices, P ? 1 : 0, loss_scale,
                                              lse, loss_rows, out_scalars);

@@ -42,7 +42,8 @@ class Stem(nn.Module):
         w = compute_copy(self.weight)
         if batch_stats:
             stats = torch.zeros((2, 64), dtype=torch.float32, device=img.device)
-            y = K.gemm(cols, w, col_stats=(stats[0], stats[1]))
+            y = K.gemm(cols, w)
+            K.bn_stats(y, stats)
             msss = K.bn_finalize(stats, bn.weight, bn.bias, bn._mean, bn._variance, y.shape[0], eps=bn.eps, momentum=bn.momentum)
         else:
             y = K.gemm(cols, w)

@@ -59,8 +59,9 @@ class ConvBN(nn.Module):
         batch_stats = training and not bn.use_global_stats
         if batch_stats:
             stats = torch.zeros((2, self.cout), dtype=torch.float32, device=x.device)
-            y = K.conv2d_fwd(x, w, stride=self.stride, pad=self.pad, col_stats=(stats[0], stats[1]))
+            y = K.conv2d_fwd(x, w, stride=self.stride, pad=self.pad)
             count = y.numel() // self.cout
+            K.bn_stats(y.view(count, self.cout), stats)
             msss = K.bn_finalize(stats, bn.weight, bn.bias, bn._mean, bn._variance, count, eps=bn.eps, momentum=bn.momentum)
         else:
             y = K.conv2d_fwd(x, w, stride=self.stride, pad=self.pad)

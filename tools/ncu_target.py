@@ -1,0 +1,36 @@
+"""Small targets for ncu captures (one warm-up + one profiled iteration, marked by cudaProfilerStart/Stop)."""
+import os
+import sys
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from passl_b200 import kernels as K  # noqa: E402
+
+what = sys.argv[1]
+if what == "resnet":
+    import torch.nn as nn
+    from passl_b200.core import ParamStore
+    from passl_b200.modeling import build_backbone, build_neck
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+    net = nn.Sequential(build_backbone(dict(name="ResNet", depth=50)),
+                        build_neck(dict(name="NonLinearNeckV1", in_channels=2048, hid_channels=2048, out_channels=128))).cuda()
+    ParamStore(net)
+    img = torch.randn(B, 3, 224, 224, device="cuda")
+    for i in range(2):
+        if i == 1:
+            torch.cuda.synchronize()
+            torch.cuda.cudart().cudaProfilerStart()
+        net._param_store.zero_grad()
+        e = net(img)
+        e.backward(torch.ones_like(e))
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
+elif what == "infonce":
+    N, D, Kq, T = 256, 128, 65536, 0.2
+    q = torch.nn.functional.normalize(torch.randn(N, D, device="cuda"), dim=1)
+    k = torch.nn.functional.normalize(torch.randn(N, D, device="cuda"), dim=1)
+    queue = torch.nn.functional.normalize(torch.randn(Kq, D, device="cuda"), dim=1).bfloat16()
+    qb = q.bfloat16()
+    for i in range(4):
+        out, lse, tgt, _ = K.infonce_tc_fwd(qb, queue, pos=k, scale=1 / T)
+    torch.cuda.synchronize()
