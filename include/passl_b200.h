@@ -28,6 +28,9 @@ extern "C" {
 #define PASSL_B200_ACT_QUICKGELU 3 /* x*sigmoid(1.702x): passl_v110/modeling/backbones/base_transformer.py:25-28 */
 
 int passl_b200_version(void);
+/* number of kernels this library has launched so far in the process (bench.py's gpu_launches) */
+long long passl_b200_launch_count(void);
+long long passl_b200_launch_counter_add(long long n);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Dense contraction (tcgen05 + TMA).  Replaces paddle nn.Linear / paddle.matmul (cuBLAS) at
@@ -96,6 +99,17 @@ int passl_b200_infonce_tc_fwd(const void* Q, const void* Kmat, const float* P, c
                               void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * SimCLR NT-Xent + CO2 (passl_v110/modeling/heads/simclr_contrastive_head.py:42-102) on a similarity matrix
+ * S = [h1;h2] [h1_all;h2_all]^T / T  (fp32 [2n, 2m], produced by passl_b200_gemm_bf16; m = world*n gathered negatives,
+ * rank selects the diagonal block).  fwd: out = {loss, acc1 (fraction), contrast, co2}; bwd: dS (bf16 [2n, 2m]).
+ * ------------------------------------------------------------------------------------------------------------- */
+long long passl_b200_ntxent_workspace_bytes(int n);
+int passl_b200_ntxent_co2_fwd(const float* S, int n, int m, int rank, float co2_weight, float* out, void* workspace,
+                              long long workspace_bytes, void* stream);
+int passl_b200_ntxent_co2_bwd(const float* S, int n, int m, int rank, float co2_weight, const float* dloss, void* dS_bf16,
+                              const void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Embedding utilities.
  *   l2norm mode 0: x/max(||x||,eps) (paddle F.normalize, moco.py:159,170; mocov3.py:189-190)
  *          mode 1: x/sqrt(sum x^2+eps) (passl/nn/norm.py:18-40; simclr.py:58)
@@ -119,15 +133,18 @@ int passl_b200_cast_bf16_to_f32(const void* x, float* y, long long n, void* stre
  * BatchNorm (training mode) on channels-last bf16 [P, C].  Replaces paddle nn.BatchNorm2D / BatchNorm1D (cuDNN BN
  * fwd/bwd) at resnetimagenet.py:112-131 and necks/base_neck.py:221-227.  Paddle conventions: eps 1e-5,
  * running = momentum*running + (1-momentum)*batch (momentum 0.9), biased batch variance.
- *   bn_stats      : sum[c] += sum_p y, sqsum[c] += sum_p y^2 (zero the accumulators first; the GEMM/conv epilogue
- *                   can produce the same sums through col_sum/col_sqsum)
- *   bn_finalize   : -> mean, invstd, scale = gamma*invstd, shift = beta - mean*scale, running stats update
+ *   bn_reduce_blocks : nblk = number of per-CTA partials the two reduce kernels write for a [P, C] tensor
+ *   bn_stats      : part[b][0][c] = sum_p y, part[b][1][c] = sum_p y^2 over the rows of CTA b (fp32 [nblk,2,C]; no atomics,
+ *                   deterministic; a [1,2,C] buffer filled by the GEMM/conv col_sum/col_sqsum epilogue is also accepted)
+ *   bn_finalize   : sums the partials -> mean, invstd, scale = gamma*invstd, shift = beta - mean*scale, running stats
  *   bn_apply      : z = relu?(y*scale + shift + residual)  (bf16 and/or fp32 output)
- *   bn_bwd_reduce : sum_g = sum_p g, sum_gx = sum_p g*xhat with g = dz * (z>0 if relu)   (= dbeta, dgamma)
+ *   bn_bwd_reduce : partials of sum_g = sum_p g, sum_gx = sum_p g*xhat with g = dz * (z>0 if relu)
+ *   bn_bwd_finalize: sums [2,C] = totals (= dbeta, dgamma), accumulated into the gradient buffers when given
  *   bn_bwd_apply  : dy = gamma*invstd*(g - sum_g/P - xhat*sum_gx/P); dres = g (gradient of the residual branch)
  * ------------------------------------------------------------------------------------------------------------- */
-int passl_b200_bn_stats(const void* y, float* sum, float* sqsum, long long P, int C, void* stream);
-int passl_b200_bn_finalize(const float* sum, const float* sqsum, const float* gamma, const float* beta, float* mean,
+int passl_b200_bn_reduce_blocks(long long P, int C);
+int passl_b200_bn_stats(const void* y, float* part, long long P, int C, void* stream);
+int passl_b200_bn_finalize(const float* part, int nblk, const float* gamma, const float* beta, float* mean,
                            float* invstd, float* scale, float* shift, float* running_mean, float* running_var,
                            long long count, float eps, float momentum, int C, void* stream);
 /* use_global_stats (passl_v110/modules/freeze.py:17-23, MoCo key encoder) / eval: affine from running statistics */
@@ -138,7 +155,8 @@ int passl_b200_axpy_f32(float* y, const float* x, float a, long long n, void* st
 int passl_b200_bn_apply(const void* y, const void* residual, const float* scale, const float* shift, void* z, float* z_f32,
                         long long P, int C, int relu, void* stream);
 int passl_b200_bn_bwd_reduce(const void* y, const void* dz, const void* z, const float* mean, const float* invstd,
-                             float* sum_g, float* sum_gx, long long P, int C, int relu, void* stream);
+                             float* part, long long P, int C, int relu, void* stream);
+int passl_b200_bn_bwd_finalize(const float* part, int nblk, float* sums, float* dgamma, float* dbeta, int C, void* stream);
 int passl_b200_bn_bwd_apply(const void* y, const void* dz, const void* z, const float* mean, const float* invstd,
                             const float* gamma, const float* sum_g, const float* sum_gx, void* dy, void* dres, long long P,
                             int C, int relu, void* stream);

@@ -14,6 +14,8 @@ c_void_p, c_int, c_ll, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlon
 # name -> (restype, [argtypes]); mirrors include/passl_b200.h one to one
 SIGNATURES = {
     "passl_b200_version": (c_int, []),
+    "passl_b200_launch_count": (c_ll, []),
+    "passl_b200_launch_counter_add": (c_ll, [c_ll]),
     "passl_b200_gemm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll,
                                      c_int, c_int, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p, c_void_p,
                                      c_void_p]),
@@ -35,6 +37,9 @@ SIGNATURES = {
     "passl_b200_infonce_tc_workspace_bytes": (c_ll, [c_int, c_int, c_int]),
     "passl_b200_infonce_tc_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_int,
                                           c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
+    "passl_b200_ntxent_workspace_bytes": (c_ll, [c_int]),
+    "passl_b200_ntxent_co2_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_ll, c_void_p]),
+    "passl_b200_ntxent_co2_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "passl_b200_l2norm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     "passl_b200_l2norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
                                       c_void_p]),
@@ -42,12 +47,14 @@ SIGNATURES = {
     "passl_b200_ema_update": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_ll, c_void_p]),
     "passl_b200_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_ll, c_void_p]),
     "passl_b200_cast_bf16_to_f32": (c_int, [c_void_p, c_void_p, c_ll, c_void_p]),
-    "passl_b200_bn_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p]),
-    "passl_b200_bn_finalize": (c_int, [c_void_p] * 10 + [c_ll, c_float, c_float, c_int, c_void_p]),
+    "passl_b200_bn_reduce_blocks": (c_int, [c_ll, c_int]),
+    "passl_b200_bn_stats": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p]),
+    "passl_b200_bn_finalize": (c_int, [c_void_p, c_int] + [c_void_p] * 8 + [c_ll, c_float, c_float, c_int, c_void_p]),
+    "passl_b200_bn_bwd_finalize": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "passl_b200_bn_global_affine": (c_int, [c_void_p] * 8 + [c_float, c_int, c_void_p]),
     "passl_b200_axpy_f32": (c_int, [c_void_p, c_void_p, c_float, c_ll, c_void_p]),
     "passl_b200_bn_apply": (c_int, [c_void_p] * 6 + [c_ll, c_int, c_int, c_void_p]),
-    "passl_b200_bn_bwd_reduce": (c_int, [c_void_p] * 7 + [c_ll, c_int, c_int, c_void_p]),
+    "passl_b200_bn_bwd_reduce": (c_int, [c_void_p] * 6 + [c_ll, c_int, c_int, c_void_p]),
     "passl_b200_bn_bwd_apply": (c_int, [c_void_p] * 10 + [c_ll, c_int, c_int, c_void_p]),
     "passl_b200_im2col_nchw_f32": (c_int, [c_void_p, c_void_p] + [c_int] * 9 + [c_void_p]),
     "passl_b200_maxpool3x3s2_fwd": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),

@@ -21,13 +21,14 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 }
 
 // blockDim = (GX, GY): x over 8-channel groups, y over rows.  gridDim = (row blocks, channel-group blocks).
-// Accumulates per-channel sum(a) and sum(a*b') into out0/out1 with atomics, where
+// Each CTA writes ONE partial per channel to part[blockIdx.x][0|1][C] — no atomics (same-address L2 atomics from ~1000 CTAs
+// serialise at ~50 ns each and made this kernel 40x slower than its HBM roofline), deterministic summation order.
 //   MODE 0 (stats)      : a = y,               second = y*y
 //   MODE 1 (bwd reduce) : a = dz*mask,         second = a * (y - mean) * invstd
 template <int MODE>
-__global__ void bn_reduce_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dz,
+__global__ void __launch_bounds__(256) bn_reduce_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dz,
                                  const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean,
-                                 const float* __restrict__ invstd, float* __restrict__ out0, float* __restrict__ out1,
+                                 const float* __restrict__ invstd, float* __restrict__ part,
                                  long long P, int C, int rows_per_block, int relu) {
   extern __shared__ float red[];  // [GY][GX*16]
   const int cg = blockIdx.y * blockDim.x + threadIdx.x;  // channel group
@@ -44,21 +45,52 @@ __global__ void bn_reduce_kernel(const __nv_bfloat16* __restrict__ y, const __nv
   long long r_end = r_begin + rows_per_block;
   if (r_end > P) r_end = P;
   if (cok) {
-    for (long long r = r_begin + threadIdx.y; r < r_end; r += blockDim.y) {
+    constexpr int U = 4;  // independent 16-byte loads in flight per thread
+    long long r = r_begin + threadIdx.y;
+    const long long step = blockDim.y;
+    for (; r + (U - 1) * step < r_end; r += U * step) {
+      uint4 uy[U], ug[U], uz[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        uy[u] = ld_nc_v4(y + (r + u * step) * C + c0);
+        if (MODE == 1) {
+          ug[u] = ld_nc_v4(dz + (r + u * step) * C + c0);
+          if (relu) uz[u] = ld_nc_v4(z + (r + u * step) * C + c0);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float a[8];
+        unpack8(uy[u], a);
+        if (MODE == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { s0[i] += a[i]; s1[i] = fmaf(a[i], a[i], s1[i]); }
+        } else {
+          float g[8];
+          unpack8(ug[u], g);
+          if (relu) {
+            float zz[8];
+            unpack8(uz[u], zz);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g[i] = zz[i] > 0.f ? g[i] : 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { s0[i] += g[i]; s1[i] = fmaf(g[i], (a[i] - mu[i]) * is[i], s1[i]); }
+        }
+      }
+    }
+    for (; r < r_end; r += step) {
       float a[8];
-      uint4 uy = ld_nc_v4(y + r * C + c0);
-      unpack8(uy, a);
+      unpack8(ld_nc_v4(y + r * C + c0), a);
       if (MODE == 0) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) { s0[i] += a[i]; s1[i] = fmaf(a[i], a[i], s1[i]); }
       } else {
         float g[8];
-        uint4 ug = ld_nc_v4(dz + r * C + c0);
-        unpack8(ug, g);
+        unpack8(ld_nc_v4(dz + r * C + c0), g);
         if (relu) {
           float zz[8];
-          uint4 uz = ld_nc_v4(z + r * C + c0);
-          unpack8(uz, zz);
+          unpack8(ld_nc_v4(z + r * C + c0), zz);
 #pragma unroll
           for (int i = 0; i < 8; ++i) g[i] = zz[i] > 0.f ? g[i] : 0.f;
         }
@@ -67,30 +99,37 @@ __global__ void bn_reduce_kernel(const __nv_bfloat16* __restrict__ y, const __nv
       }
     }
   }
+  // tree reduction over y in shared memory
   float* my = red + (threadIdx.y * blockDim.x + threadIdx.x) * 16;
 #pragma unroll
   for (int i = 0; i < 8; ++i) { my[i] = s0[i]; my[8 + i] = s1[i]; }
   __syncthreads();
-  if (threadIdx.y == 0 && cok) {
-    for (int yy = 1; yy < blockDim.y; ++yy) {
-      const float* o = red + (yy * blockDim.x + threadIdx.x) * 16;
+  for (int half = blockDim.y >> 1; half > 0; half >>= 1) {
+    if ((int)threadIdx.y < half) {
+      const float* o = red + ((threadIdx.y + half) * blockDim.x + threadIdx.x) * 16;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { s0[i] += o[i]; s1[i] += o[8 + i]; }
+      for (int i = 0; i < 16; ++i) my[i] += o[i];
     }
+    __syncthreads();
+  }
+  if (threadIdx.y == 0 && cok) {
+    float* dst = part + (size_t)blockIdx.x * 2 * C;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { red_add_f32(out0 + c0 + i, s0[i]); red_add_f32(out1 + c0 + i, s1[i]); }
+    for (int i = 0; i < 8; ++i) { dst[c0 + i] = my[i]; dst[C + c0 + i] = my[8 + i]; }
   }
 }
 
 // sums -> mean / invstd / fused scale+shift, running statistics update (Paddle momentum convention).
-__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sqsum,
+__global__ void bn_finalize_kernel(const float* __restrict__ part, int nblk,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float* mean,
                                    float* invstd, float* scale, float* shift, float* running_mean, float* running_var,
                                    float inv_count, float eps, float momentum, int C) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  float m = sum[c] * inv_count;
-  float v = fmaxf(sqsum[c] * inv_count - m * m, 0.f);
+  float sm = 0.f, sq = 0.f;
+  for (int b = 0; b < nblk; ++b) { sm += part[(size_t)b * 2 * C + c]; sq += part[(size_t)b * 2 * C + C + c]; }
+  float m = sm * inv_count;
+  float v = fmaxf(sq * inv_count - m * m, 0.f);
   float is = rsqrtf(v + eps);
   float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
   mean[c] = m; invstd[c] = is;
@@ -179,15 +218,26 @@ __global__ void axpy_f32_kernel(float* __restrict__ y, const float* __restrict__
     y[i] = fmaf(a, x[i], y[i]);
 }
 
+// sums[0|1][c] = sum_b part[b][0|1][c];  optionally dbeta += sums[0], dgamma += sums[1]
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int nblk, float* __restrict__ sums,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f, b = 0.f;
+  for (int k = 0; k < nblk; ++k) { a += part[(size_t)k * 2 * C + c]; b += part[(size_t)k * 2 * C + C + c]; }
+  sums[c] = a; sums[C + c] = b;
+  if (dbeta) dbeta[c] += a;
+  if (dgamma) dgamma[c] += b;
+}
+
 static void reduce_cfg(long long P, int C, dim3& grid, dim3& block, int& rows_per_block, int& smem) {
   int cg = C / 8;
-  int gx = cg < 64 ? cg : 64;
-  // round gx down to a power of two divisor-friendly size
-  int gy = 256 / gx;
-  if (gy < 1) gy = 1;
+  int gx = 1;
+  while (gx * 2 <= cg && gx < 64) gx *= 2;       // power of two <= min(cg, 64)
+  int gy = 256 / gx;                              // power of two (tree reduction)
   block = dim3(gx, gy);
   int cgb = (cg + gx - 1) / gx;
-  long long target_blocks = (long long)num_sms() * 8 / cgb;
+  long long target_blocks = (long long)num_sms() * 4 / cgb;
   if (target_blocks < 1) target_blocks = 1;
   long long rpb = (P + target_blocks - 1) / target_blocks;
   if (rpb < gy) rpb = gy;
@@ -208,22 +258,30 @@ static int ew_blocks(long long total8) {
 
 using namespace pb;
 
-// sum[c] += sum_p y[p,c];  sqsum[c] += sum_p y[p,c]^2      (accumulators must be zeroed by the caller)
-extern "C" int passl_b200_bn_stats(const void* y, float* sum, float* sqsum, long long P, int C, void* stream) {
+// number of row blocks (= partials per channel) the reduce kernels produce for a [P, C] tensor
+extern "C" int passl_b200_bn_reduce_blocks(long long P, int C) {
+  if (P <= 0 || C <= 0 || C % 8) return 0;
+  dim3 grid, block; int rpb, smem;
+  reduce_cfg(P, C, grid, block, rpb, smem);
+  return (int)grid.x;
+}
+
+// part[b][0][c] = sum over the rows of block b of y[p,c];  part[b][1][c] = same for y^2.   part: fp32 [nblk, 2, C]
+extern "C" int passl_b200_bn_stats(const void* y, float* part, long long P, int C, void* stream) {
   if (P <= 0 || C <= 0 || C % 8) return PB_ERR_BAD_ARG;
   dim3 grid, block; int rpb, smem;
   reduce_cfg(P, C, grid, block, rpb, smem);
   bn_reduce_kernel<0><<<grid, block, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(y), nullptr, nullptr,
-                                                                    nullptr, nullptr, sum, sqsum, P, C, rpb, 0);
+                                                                    nullptr, nullptr, part, P, C, rpb, 0);
   PB_LAUNCH_CHECK();
   return PB_OK;
 }
 
-extern "C" int passl_b200_bn_finalize(const float* sum, const float* sqsum, const float* gamma, const float* beta,
+extern "C" int passl_b200_bn_finalize(const float* part, int nblk, const float* gamma, const float* beta,
                                       float* mean, float* invstd, float* scale, float* shift, float* running_mean,
                                       float* running_var, long long count, float eps, float momentum, int C, void* stream) {
-  if (C <= 0 || count <= 0) return PB_ERR_BAD_ARG;
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sum, sqsum, gamma, beta, mean, invstd, scale, shift,
+  if (C <= 0 || count <= 0 || nblk <= 0) return PB_ERR_BAD_ARG;
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(part, nblk, gamma, beta, mean, invstd, scale, shift,
                                                                         running_mean, running_var, 1.f / (float)count, eps,
                                                                         momentum, C);
   PB_LAUNCH_CHECK();
@@ -261,16 +319,25 @@ extern "C" int passl_b200_bn_apply(const void* y, const void* residual, const fl
   return PB_OK;
 }
 
-// sum_g[c] += sum_p g[p,c];  sum_gx[c] += sum_p g[p,c]*xhat[p,c]   with g = dz * (z > 0 if relu)
+// part[b][0][c] = sum_p g[p,c];  part[b][1][c] = sum_p g[p,c]*xhat[p,c]   with g = dz * (z > 0 if relu);  part [nblk,2,C]
 extern "C" int passl_b200_bn_bwd_reduce(const void* y, const void* dz, const void* z, const float* mean, const float* invstd,
-                                        float* sum_g, float* sum_gx, long long P, int C, int relu, void* stream) {
+                                        float* part, long long P, int C, int relu, void* stream) {
   if (P <= 0 || C <= 0 || C % 8) return PB_ERR_BAD_ARG;
   if (relu && !z) return PB_ERR_BAD_ARG;
   dim3 grid, block; int rpb, smem;
   reduce_cfg(P, C, grid, block, rpb, smem);
   bn_reduce_kernel<1><<<grid, block, smem, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<const __nv_bfloat16*>(dz),
-      reinterpret_cast<const __nv_bfloat16*>(z), mean, invstd, sum_g, sum_gx, P, C, rpb, relu);
+      reinterpret_cast<const __nv_bfloat16*>(z), mean, invstd, part, P, C, rpb, relu);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+// sums [2, C] = totals of the partials; dbeta += sums[0], dgamma += sums[1] when given (fp32 gradient accumulators)
+extern "C" int passl_b200_bn_bwd_finalize(const float* part, int nblk, float* sums, float* dgamma, float* dbeta, int C,
+                                          void* stream) {
+  if (C <= 0 || nblk <= 0) return PB_ERR_BAD_ARG;
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(part, nblk, sums, dgamma, dbeta, C);
   PB_LAUNCH_CHECK();
   return PB_OK;
 }

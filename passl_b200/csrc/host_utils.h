@@ -23,7 +23,13 @@ enum : int {
     if (_e != cudaSuccess) return (int)_e;      \
   } while (0)
 
-#define PB_LAUNCH_CHECK() PB_CUDA_CHECK(cudaGetLastError())
+// every kernel launch site is followed by PB_LAUNCH_CHECK(): it also feeds the launch counter bench.py reports
+extern "C" long long passl_b200_launch_counter_add(long long n);
+#define PB_LAUNCH_CHECK()                       \
+  do {                                          \
+    passl_b200_launch_counter_add(1);           \
+    PB_CUDA_CHECK(cudaGetLastError());          \
+  } while (0)
 
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                         const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,

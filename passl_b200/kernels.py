@@ -250,22 +250,37 @@ def cast_bf16(x, out=None):
 # ------------------------------------------------------------------------------------------------------------
 # BatchNorm (channels-last bf16 [P, C]) and pooling
 # ------------------------------------------------------------------------------------------------------------
-def bn_stats(y2d, stats):
-    """stats: fp32 [2, C] zero-initialised accumulator (sum, sqsum)."""
+def bn_stats(y2d):
+    """Per-CTA partial sums of y and y^2: fp32 [nblk, 2, C] (summed by bn_finalize; no atomics)."""
     lib = _lib.load()
     P, C = y2d.shape
-    _lib.check(lib.passl_b200_bn_stats(_ptr(y2d), _ptr(stats[0]), _ptr(stats[1]), P, C, _stream()), "bn_stats")
+    nblk = lib.passl_b200_bn_reduce_blocks(P, C)
+    part = torch.empty((nblk, 2, C), dtype=torch.float32, device=y2d.device)
+    _lib.check(lib.passl_b200_bn_stats(_ptr(y2d), _ptr(part), P, C, _stream()), "bn_stats")
+    return part
 
 
-def bn_finalize(stats, gamma, beta, running_mean, running_var, count, eps=1e-5, momentum=0.9):
-    """-> fp32 [4, C] = (mean, invstd, scale, shift); updates running stats in place (may be None)."""
+def bn_finalize(part, gamma, beta, running_mean, running_var, count, eps=1e-5, momentum=0.9):
+    """part: fp32 [nblk, 2, C] partials (or [2, C] totals) -> fp32 [4, C] = (mean, invstd, scale, shift); updates the
+    running stats in place (may be None)."""
     lib = _lib.load()
-    C = stats.shape[1]
-    out = torch.empty((4, C), dtype=torch.float32, device=stats.device)
-    _lib.check(lib.passl_b200_bn_finalize(_ptr(stats[0]), _ptr(stats[1]), _ptr(gamma), _ptr(beta), _ptr(out[0]), _ptr(out[1]),
+    C = part.shape[-1]
+    nblk = part.shape[0] if part.dim() == 3 else 1
+    out = torch.empty((4, C), dtype=torch.float32, device=part.device)
+    _lib.check(lib.passl_b200_bn_finalize(_ptr(part), nblk, _ptr(gamma), _ptr(beta), _ptr(out[0]), _ptr(out[1]),
                                           _ptr(out[2]), _ptr(out[3]), _ptr(running_mean), _ptr(running_var), int(count),
                                           float(eps), float(momentum), C, _stream()), "bn_finalize")
     return out
+
+
+def colsum_accumulate(x2d, acc):
+    """acc[c] += sum_p x2d[p, c]  (bias gradients): reduce kernel partials + the finalize kernel's accumulate path."""
+    lib = _lib.load()
+    P, C = x2d.shape
+    part = bn_stats(x2d)
+    sums = torch.empty((2, C), dtype=torch.float32, device=x2d.device)
+    _lib.check(lib.passl_b200_bn_bwd_finalize(_ptr(part), part.shape[0], _ptr(sums), None, _ptr(acc), C, _stream()),
+               "bn_bwd_finalize")
 
 
 def bn_apply(y, msss, relu, residual=None, out=None, out_f32=None):
@@ -279,14 +294,19 @@ def bn_apply(y, msss, relu, residual=None, out=None, out_f32=None):
     return out if out is not None else out_f32
 
 
-def bn_bwd(y, dz, z, msss, gamma, relu, want_dres=False, grads_out=None):
-    """Returns (dy, dres, sums) with sums fp32 [2, C] = (dbeta, dgamma)."""
+def bn_bwd(y, dz, z, msss, gamma, relu, want_dres=False, dgamma=None, dbeta=None):
+    """Returns (dy, dres, sums) with sums fp32 [2, C] = (dbeta, dgamma) of this call; when the fp32 gradient buffers
+    dgamma / dbeta are given the totals are accumulated into them by the same tiny kernel."""
     lib = _lib.load()
     C = y.shape[-1]
     P = y.numel() // C
-    sums = grads_out if grads_out is not None else torch.zeros((2, C), dtype=torch.float32, device=y.device)
-    _lib.check(lib.passl_b200_bn_bwd_reduce(_ptr(y), _ptr(dz), _ptr(z), _ptr(msss[0]), _ptr(msss[1]), _ptr(sums[0]),
-                                            _ptr(sums[1]), P, C, int(relu), _stream()), "bn_bwd_reduce")
+    nblk = lib.passl_b200_bn_reduce_blocks(P, C)
+    part = torch.empty((nblk, 2, C), dtype=torch.float32, device=y.device)
+    _lib.check(lib.passl_b200_bn_bwd_reduce(_ptr(y), _ptr(dz), _ptr(z), _ptr(msss[0]), _ptr(msss[1]), _ptr(part), P, C,
+                                            int(relu), _stream()), "bn_bwd_reduce")
+    sums = torch.empty((2, C), dtype=torch.float32, device=y.device)
+    _lib.check(lib.passl_b200_bn_bwd_finalize(_ptr(part), nblk, _ptr(sums), _ptr(dgamma), _ptr(dbeta), C, _stream()),
+               "bn_bwd_finalize")
     dy = torch.empty_like(y)
     dres = torch.empty_like(y) if want_dres else None
     _lib.check(lib.passl_b200_bn_bwd_apply(_ptr(y), _ptr(dz), _ptr(z), _ptr(msss[0]), _ptr(msss[1]), _ptr(gamma), _ptr(sums[0]),
@@ -339,6 +359,26 @@ def avgpool_bwd(dy, x_shape):
     dx = torch.empty(x_shape, dtype=torch.bfloat16, device=dy.device)
     _lib.check(lib.passl_b200_avgpool_bwd(_ptr(dy.contiguous()), _ptr(dx), N, H * W, C, _stream()), "avgpool_bwd")
     return dx
+
+
+def ntxent_co2_fwd(S, n, m, rank, co2_weight=3.0):
+    """S fp32 [2n, 2m] -> (out fp32[4] = loss, acc1, contrast, co2; stats workspace for the backward)."""
+    lib = _lib.load()
+    assert S.dtype == torch.float32 and S.is_contiguous() and S.shape == (2 * n, 2 * m)
+    out = torch.empty(4, dtype=torch.float32, device=S.device)
+    nb = lib.passl_b200_ntxent_workspace_bytes(n)
+    ws = torch.empty(nb, dtype=torch.uint8, device=S.device)
+    _lib.check(lib.passl_b200_ntxent_co2_fwd(_ptr(S), n, m, rank, float(co2_weight), _ptr(out), _ptr(ws), nb, _stream()),
+               "ntxent_co2_fwd")
+    return out, ws
+
+
+def ntxent_co2_bwd(S, ws, n, m, rank, co2_weight=3.0, dloss=None):
+    lib = _lib.load()
+    dS = torch.empty(S.shape, dtype=torch.bfloat16, device=S.device)
+    _lib.check(lib.passl_b200_ntxent_co2_bwd(_ptr(S), n, m, rank, float(co2_weight), _ptr(dloss), _ptr(dS), _ptr(ws),
+                                             _stream()), "ntxent_co2_bwd")
+    return dS
 
 
 def cast_f32(x_bf16, out=None):

@@ -1,1 +1,2 @@
 from .moco import MoCo  # noqa: F401
+from .simclr import SimCLR  # noqa: F401

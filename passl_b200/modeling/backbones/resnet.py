@@ -41,9 +41,8 @@ class Stem(nn.Module):
         batch_stats = training and not bn.use_global_stats
         w = compute_copy(self.weight)
         if batch_stats:
-            stats = torch.zeros((2, 64), dtype=torch.float32, device=img.device)
             y = K.gemm(cols, w)
-            K.bn_stats(y, stats)
+            stats = K.bn_stats(y)
             msss = K.bn_finalize(stats, bn.weight, bn.bias, bn._mean, bn._variance, y.shape[0], eps=bn.eps, momentum=bn.momentum)
         else:
             y = K.gemm(cols, w)
@@ -59,10 +58,9 @@ class Stem(nn.Module):
         cols, y, z, msss, arg = ctx
         dz = K.maxpool_bwd(dout, arg, tuple(z.shape)) if arg is not None else dout
         bn = self.bn
-        dy, _, sums = K.bn_bwd(y, dz.view(y.shape), z.view(y.shape), msss, bn.weight, True)
-        if bn.weight.requires_grad:
-            K.axpy(grad_buffer(bn.bias), sums[0])
-            K.axpy(grad_buffer(bn.weight), sums[1])
+        tb = bn.weight.requires_grad
+        dy, _, _ = K.bn_bwd(y, dz.view(y.shape), z.view(y.shape), msss, bn.weight, True,
+                            dgamma=grad_buffer(bn.weight) if tb else None, dbeta=grad_buffer(bn.bias) if tb else None)
         if self.weight.requires_grad:
             K.gemm(dy, cols, a_t=True, b_t=True, out=grad_buffer(self.weight), accumulate=True,
                    splits=K.wgrad_splits(64, STEM_KPAD, dy.shape[0]))

@@ -113,9 +113,8 @@ class NonLinearNeckfc3(_NeckBase):
         ctxs = []
         h = h0
         for i, (fc, bn) in enumerate(((self.fc1, self.bn1), (self.fc2, self.bn2), (self.fc3, self.bn3))):
-            stats = torch.zeros((2, fc.cout), dtype=torch.float32, device=dev) if training else None
-            y, cf = fc.fwd(h, save=save, col_stats=(stats[0], stats[1]) if training else None)
-            h, cb = bn.fwd(y, stats=stats, training=training, save=save, out_f32=(i == 2))
+            y, cf = fc.fwd(h, save=save)
+            h, cb = bn.fwd(y, training=training, save=save, out_f32=(i == 2))
             ctxs.append((cf, cb))
         emb, _, inv = K.l2norm_fwd(h, mode="l2_normalize")
         return emb, (ctxs, feat_shape, emb, inv)

@@ -58,10 +58,9 @@ class ConvBN(nn.Module):
         bn = self.bn
         batch_stats = training and not bn.use_global_stats
         if batch_stats:
-            stats = torch.zeros((2, self.cout), dtype=torch.float32, device=x.device)
             y = K.conv2d_fwd(x, w, stride=self.stride, pad=self.pad)
             count = y.numel() // self.cout
-            K.bn_stats(y.view(count, self.cout), stats)
+            stats = K.bn_stats(y.view(count, self.cout))
             msss = K.bn_finalize(stats, bn.weight, bn.bias, bn._mean, bn._variance, count, eps=bn.eps, momentum=bn.momentum)
         else:
             y = K.conv2d_fwd(x, w, stride=self.stride, pad=self.pad)
@@ -75,11 +74,10 @@ class ConvBN(nn.Module):
         x, y, z, msss, has_res, batch_stats = ctx
         bn = self.bn
         assert batch_stats, "backward through a use_global_stats BatchNorm is not on the training path"
-        sums = torch.zeros((2, self.cout), dtype=torch.float32, device=y.device)
-        dy, dres, sums = K.bn_bwd(y, dz, z, msss, bn.weight, self.relu, want_dres=has_res, grads_out=sums)
-        if bn.weight is not None and bn.weight.requires_grad:
-            K.axpy(grad_buffer(bn.bias), sums[0])
-            K.axpy(grad_buffer(bn.weight), sums[1])
+        train_bn = bn.weight is not None and bn.weight.requires_grad
+        dy, dres, _ = K.bn_bwd(y, dz, z, msss, bn.weight, self.relu, want_dres=has_res,
+                               dgamma=grad_buffer(bn.weight) if train_bn else None,
+                               dbeta=grad_buffer(bn.bias) if train_bn else None)
         if self.weight.requires_grad:
             K.conv2d_wgrad(x, dy, tuple(self.weight.shape), stride=self.stride, pad=self.pad,
                            out=grad_buffer(self.weight), accumulate=True)
@@ -115,9 +113,7 @@ class Linear(nn.Module):
             K.gemm(dout_bf16, x, a_t=True, b_t=True, out=grad_buffer(self.weight), accumulate=True,
                    splits=K.wgrad_splits(self.cout, self.cin, M))
             if self.bias is not None:
-                s = torch.zeros((2, self.cout), dtype=torch.float32, device=x.device)
-                K.bn_stats(dout_bf16, s)
-                K.axpy(grad_buffer(self.bias), s[0])
+                K.colsum_accumulate(dout_bf16, grad_buffer(self.bias))
         if not need_dx:
             return None
         return K.gemm(dout_bf16, compute_copy(self.weight), b_t=True, aux=prev_act_out, aux_mode_name=prev_act)
@@ -136,8 +132,7 @@ class BatchNorm1D(nn.Module):
         batch_stats = training and not bn.use_global_stats
         if batch_stats:
             if stats is None:
-                stats = torch.zeros((2, self.c), dtype=torch.float32, device=y.device)
-                K.bn_stats(y, stats)
+                stats = K.bn_stats(y)
             msss = K.bn_finalize(stats, bn.weight, bn.bias, bn._mean, bn._variance, y.shape[0], eps=bn.eps, momentum=bn.momentum)
         else:
             msss = bn.global_affine()
@@ -152,8 +147,8 @@ class BatchNorm1D(nn.Module):
     def bwd(self, ctx, dz_bf16):
         y, z, msss = ctx
         bn = self.bn
-        dy, _, sums = K.bn_bwd(y, dz_bf16, z, msss, bn.weight, self.relu)
-        if bn.weight is not None and bn.weight.requires_grad:
-            K.axpy(grad_buffer(bn.bias), sums[0])
-            K.axpy(grad_buffer(bn.weight), sums[1])
+        train_bn = bn.weight is not None and bn.weight.requires_grad
+        dy, _, _ = K.bn_bwd(y, dz_bf16, z, msss, bn.weight, self.relu,
+                            dgamma=grad_buffer(bn.weight) if train_bn else None,
+                            dbeta=grad_buffer(bn.bias) if train_bn else None)
         return dy
