@@ -73,7 +73,8 @@ class ClockSampler(threading.Thread):
 def cpu_reference_step_time(steps, warmup, sample):
     import torch
     from oracle import simclr_step as S          # bench.py may execute oracle/ only here (cpu_baseline / --impl reference)
-    cores = os.cpu_count() or 1
+    # torch-CPU convolutions stop scaling (and thrash) far below the core count of the GPU host: cap the intra-op pool
+    cores = min(os.cpu_count() or 1, int(os.environ.get("PASSL_B200_CPU_THREADS", "32")))
     torch.set_num_threads(cores)
     p = S.init_params(0)
     vel = {}

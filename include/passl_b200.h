@@ -162,6 +162,28 @@ int passl_b200_bn_bwd_apply(const void* y, const void* dz, const void* z, const 
                             int C, int relu, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * LayerNorm over token rows [T, D] bf16 (paddle nn.LayerNorm, passl/models/vision_transformer.py:174,204-205; eps 1e-6).
+ * fwd saves mean / rstd (fp32 [T]); bwd writes dx and per-CTA partials [nblk, 2, D] = (dbeta, dgamma) that
+ * passl_b200_bn_bwd_finalize sums into the gradient buffers.  D % 8 == 0, D <= 2048.
+ * ------------------------------------------------------------------------------------------------------------- */
+int passl_b200_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                             long long T, int D, float eps, void* stream);
+int passl_b200_layernorm_bwd_blocks(long long T);
+int passl_b200_layernorm_bwd(const void* x, const void* dy, const float* gamma, const float* mean, const float* rstd, void* dx,
+                             float* part, long long T, int D, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Fused multi-head self-attention on tcgen05 (N <= 256 tokens, head dim 64 or 32): softmax(Q K^T * scale) V per
+ * (batch, head) without materialising [B,H,N,N] (passl/models/vision_transformer.py:142-153; causal = CLIP text mask,
+ * clip.py:288-290).  qkv: bf16 [B, N, 3, H, d] = the qkv Linear output as is; out: bf16 [B, N, H, d]; lse: fp32 [B, H, N].
+ * Backward recomputes the probabilities and writes dqkv in the packed layout.
+ * ------------------------------------------------------------------------------------------------------------- */
+int passl_b200_attention_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int d, float scale, int causal,
+                             void* stream);
+int passl_b200_attention_bwd(const void* qkv, const void* dO, const void* O, const float* lse, void* dqkv, int B, int N,
+                             int H, int d, float scale, int causal, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Stem / pooling.  im2col: reference NCHW fp32 images -> bf16 [N*Ho*Wo, Kpad] with K order (r, s, c), zero padded
  * (7x7/2 stem conv resnetimagenet.py:190-198; 16x16/16 patch embedding vision_transformer.py:231-236).
  * maxpool 3x3/2 pad 1 (resnetimagenet.py:198), arg-max tap saved as int8; global average pool (base_neck.py:52,79).

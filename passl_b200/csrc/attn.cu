@@ -1,0 +1,535 @@
+// Fused multi-head self-attention for short sequences (ViT / MAE / CLIP towers: N <= 256 tokens, d = 64 or 32) on tcgen05.
+//
+//   S = Q K^T * d^-1/2  ->  softmax  ->  O = P V        per (batch, head); the [B,H,N,N] score tensor never reaches HBM
+//   (the reference materialises it three times and keeps it for backward: passl/models/vision_transformer.py:145-153).
+//
+// Input is the packed output of the qkv Linear, qkv[b][n][s][h][e] (s = 0/1/2 for q/k/v) — exactly the reference's
+// reshape [B,N,3,H,d] (vision_transformer.py:144-146) — read in place through a 4-D TMA tensor map (no permute pass).
+// Output O[b][n][h][e] = [T, H*d] (the layout the proj Linear consumes) + LSE[b][h][n] (natural log) for the backward.
+//
+// One CTA (160 threads) per SM loops over (b, h) work items; the whole K / V of a head sits in shared memory:
+//   warp 4 lane 0 : TMA loads of Q (128-row blocks), K, V; issues MMA1  S[128 x NKP] = Q_blk . K^T      (K = d)
+//                                                          and MMA2  O[128 x d]   = P . V          (K = NKP keys)
+//   warps 0..3    : one query row per thread: tcgen05.ld S from TMEM (2 passes: max, exp2+sum), write P (bf16) into
+//                   shared memory in the SWIZZLE_128B K-major layout the MMA reads, then normalise O out of TMEM.
+#include "common.cuh"
+#include "host_utils.h"
+#include "../../include/passl_b200.h"
+
+#include <string.h>
+
+namespace pb {
+
+constexpr float kAttnLog2e = 1.4426950408889634f;
+constexpr float kAttnLn2 = 0.6931471805599453f;
+
+struct AttnParams {
+  CUtensorMap qkv_map;   // dims (d, 3H, N, B), box {d, 1, 128, 1}
+  CUtensorMap kv_map;    // same tensor, box {d, 1, NKP, 1}
+  __nv_bfloat16* out;    // [B, N, H, d]
+  float* lse;            // [B, H, N]
+  int B, N, H, d;
+  int NKP;               // keys padded to a multiple of 32 (<= 256)
+  int mblocks;           // ceil(N / 128)
+  int causal;
+  float scale;
+};
+
+__global__ void __launch_bounds__(160, 1) attn_fwd_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int rowB = p.d * 2;                         // bytes per Q/K/V row (128 or 64)
+  const uint32_t lt = (p.d == 64) ? 2u : 4u;        // SWIZZLE_128B / SWIZZLE_64B
+  const uint32_t sbo = 8u * rowB;                   // 8-row atom stride
+  uint8_t* q_s = smem;                              // [256][rowB]
+  uint8_t* k_s = q_s + 256 * rowB;                  // [256][rowB]
+  uint8_t* v_s = k_s + 256 * rowB;                  // [256][rowB]
+  uint8_t* p_s = v_s + 256 * rowB;                  // 4 chunks x [128][128 B]  (64 KB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p_s + 4 * 128 * 128);
+  uint64_t* load_full = bars;      // tx
+  uint64_t* s_full = bars + 1;     // MMA1 commit
+  uint64_t* p_full = bars + 2;     // 4 warp arrivals
+  uint64_t* o_full = bars + 3;     // MMA2 commit
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const uint32_t warp = warp_id(), lane = lane_id();
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&p.qkv_map);
+    tma_prefetch_desc(&p.kv_map);
+    mbar_init(load_full, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tm_s = tmem_base;          // S accumulator: columns [0, 256)
+  const uint32_t tm_o = tmem_base + 256;    // O accumulator: columns [256, 256 + d)
+
+  const int items = p.B * p.H;
+  uint32_t ph_load = 0, ph_s = 0, ph_p = 0, ph_o = 0;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      const uint32_t idesc1 = make_idesc_bf16(128, p.NKP, false, false);
+      const uint32_t idesc2 = make_idesc_bf16(128, p.d, false, true);
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int b = item / p.H, h = item - b * p.H;
+        // all MMAs of the previous item have completed (we waited on its last o_full below) -> smem reusable
+        mbar_arrive_expect_tx(load_full, (uint32_t)((p.mblocks * 128 + 2 * p.NKP) * rowB));
+        for (int mb = 0; mb < p.mblocks; ++mb) tma_load_4d(q_s + mb * 128 * rowB, &p.qkv_map, load_full, 0, h, mb * 128, b);
+        tma_load_4d(k_s, &p.kv_map, load_full, 0, p.H + h, 0, b);
+        tma_load_4d(v_s, &p.kv_map, load_full, 0, 2 * p.H + h, 0, b);
+        mbar_wait(load_full, ph_load); ph_load ^= 1;
+        tc_fence_after();
+        for (int mb = 0; mb < p.mblocks; ++mb) {
+          // MMA1: S = Q_mb K^T
+          const uint32_t qa = smem_u32(q_s + mb * 128 * rowB), ka = smem_u32(k_s);
+          for (int k = 0; k < p.d / 16; ++k)
+            umma_bf16(tm_s, make_smem_desc(qa + k * 32, 16, sbo, lt), make_smem_desc(ka + k * 32, 16, sbo, lt), idesc1, k > 0);
+          umma_commit(s_full);
+          // MMA2: O = P V   (after the softmax warps published P)
+          mbar_wait(p_full, ph_p); ph_p ^= 1;
+          // o_full of the previous block has necessarily completed here (the softmax warps consumed it before
+          // publishing this P): consume the phase now so this thread never lags the barrier by two phases.
+          if (mb > 0) { mbar_wait(o_full, ph_o); ph_o ^= 1; }
+          tc_fence_after();
+          const uint32_t pa = smem_u32(p_s), va = smem_u32(v_s);
+          for (int k = 0; k < p.NKP / 16; ++k) {
+            uint64_t da = make_smem_desc_sw128(pa + (k >> 2) * (128 * 128) + (k & 3) * 32, 16, 1024);
+            uint64_t db = make_smem_desc(va + k * 16 * rowB, 0, sbo, lt);   // MN-major: 16 keys = 2 atoms of 8 rows
+            umma_bf16(tm_o, da, db, idesc2, k > 0);
+          }
+          umma_commit(o_full);
+        }
+        // wait until the last MMA2 of this item has retired before the next item's TMA overwrites smem
+        mbar_wait(o_full, ph_o); ph_o ^= 1;
+      }
+    }
+  } else {
+    // ---------------- softmax / epilogue warps (0..3): thread = query row ----------------
+    const uint32_t q4 = warp;                         // TMEM lane quarter == warp id (0..3)
+    const int r = q4 * 32 + lane;                     // row within the 128-row block
+    const float c2 = p.scale * kAttnLog2e;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const int b = item / p.H, h = item - b * p.H;
+      for (int mb = 0; mb < p.mblocks; ++mb) {
+        const int row = mb * 128 + r;                 // query index
+        const bool row_ok = row < p.N;
+        const int jmax = p.causal ? (row + 1 < p.N ? row + 1 : p.N) : p.N;   // valid keys: j < jmax
+        mbar_wait(s_full, ph_s); ph_s ^= 1;
+        tc_fence_after();
+        const uint32_t ts = tm_s + ((q4 * 32u) << 16);
+        // pass 1: row maximum (log2 domain)
+        float m = -INFINITY;
+        for (int c = 0; c < p.NKP / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(ts + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c * 32 + j < jmax) m = fmaxf(m, __uint_as_float(v[j]) * c2);
+        }
+        if (!row_ok || m == -INFINITY) m = 0.f;
+        // pass 2: p = exp2(y - m), row sum, P -> smem (bf16, SWIZZLE_128B K-major: chunk of 64 keys = [128 rows][128 B])
+        float l = 0.f;
+        for (int c = 0; c < p.NKP / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(ts + c * 32, v);
+          tmem_ld_wait();
+          float e[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float pj = (c * 32 + j < jmax) ? exp2f(__uint_as_float(v[j]) * c2 - m) : 0.f;
+            // the tensor core multiplies the bf16-rounded probability: sum the same rounded values
+            e[j] = __bfloat162float(__float2bfloat16_rn(pj));
+            l += e[j];
+          }
+          const int chunk = (c * 32) >> 6;
+          uint8_t* base = p_s + chunk * (128 * 128) + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int j8 = ((c * 32) & 63) + g * 8;                // key offset within the 64-key chunk
+            uint4 u;
+            u.x = pack_bf16x2(e[g * 8 + 0], e[g * 8 + 1]);
+            u.y = pack_bf16x2(e[g * 8 + 2], e[g * 8 + 3]);
+            u.z = pack_bf16x2(e[g * 8 + 4], e[g * 8 + 5]);
+            u.w = pack_bf16x2(e[g * 8 + 6], e[g * 8 + 7]);
+            *reinterpret_cast<uint4*>(base + ((((j8 >> 3) ^ (r & 7)) & 7) << 4)) = u;
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+        // epilogue: O / l
+        mbar_wait(o_full, ph_o); ph_o ^= 1;
+        tc_fence_after();
+        const uint32_t to = tm_o + ((q4 * 32u) << 16);
+        const float inv = (l > 0.f) ? 1.f / l : 0.f;
+        __nv_bfloat16* op = p.out + (((size_t)b * p.N + row) * p.H + h) * p.d;
+        for (int c = 0; c < p.d / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(to + c * 32, v);
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 u;
+              u.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]) * inv, __uint_as_float(v[g * 8 + 1]) * inv);
+              u.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]) * inv, __uint_as_float(v[g * 8 + 3]) * inv);
+              u.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]) * inv, __uint_as_float(v[g * 8 + 5]) * inv);
+              u.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]) * inv, __uint_as_float(v[g * 8 + 7]) * inv);
+              *reinterpret_cast<uint4*>(op + c * 32 + g * 8) = u;
+            }
+          }
+        }
+        if (row_ok) p.lse[((size_t)b * p.H + h) * p.N + row] = (m + log2f(l)) * kAttnLn2;
+        tc_fence_before();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static int attn_make_maps(AttnParams& p, const void* qkv) {
+  const uint64_t d = p.d, H3 = 3ull * p.H;
+  uint64_t dims[4] = {d, H3, (uint64_t)p.N, (uint64_t)p.B};
+  uint64_t str[3] = {d * 2, H3 * d * 2, (uint64_t)p.N * H3 * d * 2};
+  uint32_t box_q[4] = {(uint32_t)p.d, 1, 128, 1};
+  uint32_t box_kv[4] = {(uint32_t)p.d, 1, (uint32_t)p.NKP, 1};
+  CUtensorMapSwizzle swz = (p.d == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  int rc = make_tmap_bf16(&p.qkv_map, qkv, 4, dims, str, box_q, swz);
+  if (rc) return rc;
+  return make_tmap_bf16(&p.kv_map, qkv, 4, dims, str, box_kv, swz);
+}
+
+}  // namespace pb
+
+using namespace pb;
+
+// qkv: bf16 [B, N, 3, H, d] (packed qkv Linear output);  out: bf16 [B, N, H, d];  lse: fp32 [B, H, N]
+extern "C" int passl_b200_attention_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int d, float scale,
+                                        int causal, void* stream) {
+  if (B <= 0 || N <= 0 || N > 256 || H <= 0 || (d != 64 && d != 32)) return PB_ERR_UNSUPPORTED;
+  if (reinterpret_cast<uintptr_t>(qkv) & 15) return PB_ERR_BAD_ARG;
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.out = reinterpret_cast<__nv_bfloat16*>(out); p.lse = lse;
+  p.B = B; p.N = N; p.H = H; p.d = d; p.causal = causal; p.scale = scale;
+  p.NKP = (N + 31) / 32 * 32;
+  p.mblocks = (N + 127) / 128;
+  int rc = attn_make_maps(p, qkv);
+  if (rc) return rc;
+  const int smem = 3 * 256 * d * 2 + 4 * 128 * 128 + 256 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    PB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 256 * 128 + 4 * 128 * 128 + 256 + 1024));
+    attr = true;
+  }
+  int grid = B * H < num_sms() ? B * H : num_sms();
+  attn_fwd_kernel<<<grid, 160, smem, (cudaStream_t)stream>>>(p);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+// ======================================================================================================================
+// Backward.  dqkv[b][n][s][h][e] (same packed layout as qkv) from dO[b][n][h][e], O, LSE.
+//   S = Q K^T, P = exp(S*scale - lse), dP = dO V^T, dS = P o (dP - delta) * scale, delta_i = sum_e dO_ie O_ie
+//   dV = P^T dO,  dK = dS^T Q,  dQ = dS K          (the reference keeps P in HBM; here it is recomputed per 128x128 tile)
+// Tiles: query blocks i and key blocks j of 128.  TMEM: S [0,128) dP [128,256) dQ_0/dQ_1 [256,384) dK_j [384,448) dV_j [448,512).
+// ======================================================================================================================
+namespace pb {
+
+struct AttnBwdParams {
+  CUtensorMap qkv_map;   // dims (d, 3H, N, B), box {d, 1, 128, 1}
+  CUtensorMap do_map;    // dims (d, H, N, B),  box {d, 1, 128, 1}
+  const __nv_bfloat16* dO;
+  const __nv_bfloat16* O;
+  const float* lse;
+  __nv_bfloat16* dqkv;
+  int B, N, H, d, mblocks, causal;
+  float scale;
+};
+
+__global__ void __launch_bounds__(160, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int rowB = p.d * 2;
+  const uint32_t lt = (p.d == 64) ? 2u : 4u;
+  const uint32_t sbo = 8u * rowB;
+  uint8_t* q_s = smem;
+  uint8_t* k_s = q_s + 256 * rowB;
+  uint8_t* v_s = k_s + 256 * rowB;
+  uint8_t* do_s = v_s + 256 * rowB;
+  uint8_t* p_s = do_s + 256 * rowB;          // 2 chunks x [128][128 B]
+  uint8_t* ds_s = p_s + 2 * 128 * 128;       // 2 chunks x [128][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ds_s + 2 * 128 * 128);
+  uint64_t* load_full = bars;       // tx
+  uint64_t* sp_full = bars + 1;     // S and dP ready            (MMA commit)
+  uint64_t* pd_full = bars + 2;     // P and dS written to smem   (4 warp arrivals)
+  uint64_t* kv_done = bars + 3;     // dK_j, dV_j complete        (MMA commit)
+  uint64_t* kv_free = bars + 4;     // dK_j, dV_j read out        (4 warp arrivals)
+  uint64_t* q_done = bars + 5;      // dQ complete                (MMA commit)
+  uint64_t* q_free = bars + 6;      // dQ read out                (4 warp arrivals)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7);
+
+  const uint32_t warp = warp_id(), lane = lane_id();
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&p.qkv_map);
+    tma_prefetch_desc(&p.do_map);
+    mbar_init(load_full, 1);
+    mbar_init(sp_full, 1);
+    mbar_init(pd_full, 4);
+    mbar_init(kv_done, 1);
+    mbar_init(kv_free, 4);
+    mbar_init(q_done, 1);
+    mbar_init(q_free, 4);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tm_s = tmem_base, tm_dp = tmem_base + 128, tm_dq = tmem_base + 256, tm_dk = tmem_base + 384,
+                 tm_dv = tmem_base + 448;
+  const int items = p.B * p.H;
+  const int nb = p.mblocks;
+  uint32_t ph_load = 0, ph_sp = 0, ph_pd = 0, ph_kvd = 0, ph_kvf = 0, ph_qd = 0, ph_qf = 0;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      const uint32_t id_s = make_idesc_bf16(128, 128, false, false);
+      const uint32_t id_kv = make_idesc_bf16(128, p.d, true, true);
+      const uint32_t id_q = make_idesc_bf16(128, p.d, false, true);
+      bool first_item = true;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int b = item / p.H, h = item - b * p.H;
+        // previous item's MMAs are all complete (q_done waited below), epilogue reads are TMEM-only -> smem reusable
+        mbar_arrive_expect_tx(load_full, (uint32_t)(4 * nb * 128 * rowB));
+        for (int mb = 0; mb < nb; ++mb) {
+          tma_load_4d(q_s + mb * 128 * rowB, &p.qkv_map, load_full, 0, h, mb * 128, b);
+          tma_load_4d(k_s + mb * 128 * rowB, &p.qkv_map, load_full, 0, p.H + h, mb * 128, b);
+          tma_load_4d(v_s + mb * 128 * rowB, &p.qkv_map, load_full, 0, 2 * p.H + h, mb * 128, b);
+          tma_load_4d(do_s + mb * 128 * rowB, &p.do_map, load_full, 0, h, mb * 128, b);
+        }
+        mbar_wait(load_full, ph_load); ph_load ^= 1;
+        tc_fence_after();
+        if (!first_item) { mbar_wait(q_free, ph_qf); ph_qf ^= 1; }   // dQ accumulators of the previous item were read out
+        for (int j = 0; j < nb; ++j) {
+          if (!(first_item && j == 0)) { mbar_wait(kv_free, ph_kvf); ph_kvf ^= 1; }   // dK/dV accumulators read out
+          for (int i = 0; i < nb; ++i) {
+            const uint32_t qa = smem_u32(q_s + i * 128 * rowB), doa = smem_u32(do_s + i * 128 * rowB);
+            const uint32_t ka = smem_u32(k_s + j * 128 * rowB), va = smem_u32(v_s + j * 128 * rowB);
+            for (int k = 0; k < p.d / 16; ++k)
+              umma_bf16(tm_s, make_smem_desc(qa + k * 32, 16, sbo, lt), make_smem_desc(ka + k * 32, 16, sbo, lt), id_s, k > 0);
+            for (int k = 0; k < p.d / 16; ++k)
+              umma_bf16(tm_dp, make_smem_desc(doa + k * 32, 16, sbo, lt), make_smem_desc(va + k * 32, 16, sbo, lt), id_s, k > 0);
+            umma_commit(sp_full);
+            mbar_wait(pd_full, ph_pd); ph_pd ^= 1;
+            tc_fence_after();
+            const uint32_t pa = smem_u32(p_s), dsa = smem_u32(ds_s);
+            for (int k = 0; k < 8; ++k) {   // K = 128 query rows
+              // dV_j += P^T dO_i ; dK_j += dS^T Q_i      (A = P / dS viewed MN-major: M = keys, K = query rows)
+              umma_bf16(tm_dv, make_smem_desc(pa + k * 2048, 128 * 128, 1024, 2), make_smem_desc(doa + k * 16 * rowB, 0, sbo, lt),
+                        id_kv, (i > 0 || k > 0));
+              umma_bf16(tm_dk, make_smem_desc(dsa + k * 2048, 128 * 128, 1024, 2), make_smem_desc(qa + k * 16 * rowB, 0, sbo, lt),
+                        id_kv, (i > 0 || k > 0));
+            }
+            for (int k = 0; k < 8; ++k)     // dQ_i += dS K_j   (A = dS K-major over keys, B = K_j MN-major)
+              umma_bf16(tm_dq + i * 64, make_smem_desc_sw128(dsa + (k >> 2) * (128 * 128) + (k & 3) * 32, 16, 1024),
+                        make_smem_desc(ka + k * 16 * rowB, 0, sbo, lt), id_q, (j > 0 || k > 0));
+          }
+          umma_commit(kv_done);
+        }
+        umma_commit(q_done);
+        // all MMAs of this item retired before the next item's TMA overwrites shared memory
+        // (q_done is also consumed by the epilogue warps; this thread waits one phase behind at most)
+        mbar_wait(q_done, ph_qd); ph_qd ^= 1;
+        first_item = false;
+      }
+    }
+  } else {
+    const uint32_t q4 = warp;
+    const int r = q4 * 32 + lane;
+    const float c2 = p.scale * kAttnLog2e;
+    const uint32_t lane_off = (q4 * 32u) << 16;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const int b = item / p.H, h = item - b * p.H;
+      // per-row constants for both query blocks: lse (log2 domain) and delta
+      float lse2[2], delta[2];
+      for (int i = 0; i < nb; ++i) {
+        const int row = i * 128 + r;
+        lse2[i] = 0.f; delta[i] = 0.f;
+        if (row < p.N) {
+          lse2[i] = p.lse[((size_t)b * p.H + h) * p.N + row] * kAttnLog2e;
+          const __nv_bfloat16* a = p.dO + (((size_t)b * p.N + row) * p.H + h) * p.d;
+          const __nv_bfloat16* o = p.O + (((size_t)b * p.N + row) * p.H + h) * p.d;
+          float s = 0.f;
+          for (int e = 0; e < p.d; e += 8) {
+            uint4 ua = *reinterpret_cast<const uint4*>(a + e), uo = *reinterpret_cast<const uint4*>(o + e);
+            float2 a0 = unpack_bf16x2(ua.x), a1 = unpack_bf16x2(ua.y), a2 = unpack_bf16x2(ua.z), a3 = unpack_bf16x2(ua.w);
+            float2 o0 = unpack_bf16x2(uo.x), o1 = unpack_bf16x2(uo.y), o2 = unpack_bf16x2(uo.z), o3 = unpack_bf16x2(uo.w);
+            s += a0.x * o0.x + a0.y * o0.y + a1.x * o1.x + a1.y * o1.y + a2.x * o2.x + a2.y * o2.y + a3.x * o3.x + a3.y * o3.y;
+          }
+          delta[i] = s;
+        }
+      }
+      for (int j = 0; j < nb; ++j) {
+        for (int i = 0; i < nb; ++i) {
+          const int row = i * 128 + r;
+          const bool row_ok = row < p.N;
+          mbar_wait(sp_full, ph_sp); ph_sp ^= 1;
+          tc_fence_after();
+          for (int c = 0; c < 4; ++c) {
+            uint32_t sv[32], dv[32];
+            tmem_ld_32x32(tm_s + lane_off + c * 32, sv);
+            tmem_ld_32x32(tm_dp + lane_off + c * 32, dv);
+            tmem_ld_wait();
+            float pe[32], de[32];
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) {
+              const int key = j * 128 + c * 32 + jj;
+              const bool ok = row_ok && key < p.N && (!p.causal || key <= row);
+              const float pv = ok ? exp2f(__uint_as_float(sv[jj]) * c2 - lse2[i]) : 0.f;
+              pe[jj] = pv;
+              de[jj] = pv * (__uint_as_float(dv[jj]) - delta[i]) * p.scale;
+            }
+            const int chunk = c >> 1;
+            const uint32_t roff = chunk * (128 * 128) + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int j8 = ((c * 32) & 63) + g * 8;
+              const uint32_t off = roff + ((((j8 >> 3) ^ (r & 7)) & 7) << 4);
+              uint4 u, w;
+              u.x = pack_bf16x2(pe[g * 8 + 0], pe[g * 8 + 1]); u.y = pack_bf16x2(pe[g * 8 + 2], pe[g * 8 + 3]);
+              u.z = pack_bf16x2(pe[g * 8 + 4], pe[g * 8 + 5]); u.w = pack_bf16x2(pe[g * 8 + 6], pe[g * 8 + 7]);
+              w.x = pack_bf16x2(de[g * 8 + 0], de[g * 8 + 1]); w.y = pack_bf16x2(de[g * 8 + 2], de[g * 8 + 3]);
+              w.z = pack_bf16x2(de[g * 8 + 4], de[g * 8 + 5]); w.w = pack_bf16x2(de[g * 8 + 6], de[g * 8 + 7]);
+              *reinterpret_cast<uint4*>(p_s + off) = u;
+              *reinterpret_cast<uint4*>(ds_s + off) = w;
+            }
+          }
+          tc_fence_before();
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(pd_full);
+        }
+        // dK_j / dV_j epilogue: TMEM lane = key row
+        mbar_wait(kv_done, ph_kvd); ph_kvd ^= 1;
+        tc_fence_after();
+        {
+          const int key = j * 128 + r;
+          __nv_bfloat16* dk = p.dqkv + ((((size_t)b * p.N + key) * 3 + 1) * p.H + h) * p.d;
+          __nv_bfloat16* dvp = p.dqkv + ((((size_t)b * p.N + key) * 3 + 2) * p.H + h) * p.d;
+          for (int c = 0; c < p.d / 32; ++c) {
+            uint32_t a[32], bq[32];
+            tmem_ld_32x32(tm_dk + lane_off + c * 32, a);
+            tmem_ld_32x32(tm_dv + lane_off + c * 32, bq);
+            tmem_ld_wait();
+            if (key < p.N) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                uint4 u, w;
+                u.x = pack_bf16x2(__uint_as_float(a[g * 8 + 0]), __uint_as_float(a[g * 8 + 1]));
+                u.y = pack_bf16x2(__uint_as_float(a[g * 8 + 2]), __uint_as_float(a[g * 8 + 3]));
+                u.z = pack_bf16x2(__uint_as_float(a[g * 8 + 4]), __uint_as_float(a[g * 8 + 5]));
+                u.w = pack_bf16x2(__uint_as_float(a[g * 8 + 6]), __uint_as_float(a[g * 8 + 7]));
+                w.x = pack_bf16x2(__uint_as_float(bq[g * 8 + 0]), __uint_as_float(bq[g * 8 + 1]));
+                w.y = pack_bf16x2(__uint_as_float(bq[g * 8 + 2]), __uint_as_float(bq[g * 8 + 3]));
+                w.z = pack_bf16x2(__uint_as_float(bq[g * 8 + 4]), __uint_as_float(bq[g * 8 + 5]));
+                w.w = pack_bf16x2(__uint_as_float(bq[g * 8 + 6]), __uint_as_float(bq[g * 8 + 7]));
+                *reinterpret_cast<uint4*>(dk + c * 32 + g * 8) = u;
+                *reinterpret_cast<uint4*>(dvp + c * 32 + g * 8) = w;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(kv_free);
+      }
+      // dQ epilogue
+      mbar_wait(q_done, ph_qd); ph_qd ^= 1;
+      tc_fence_after();
+      for (int i = 0; i < nb; ++i) {
+        const int row = i * 128 + r;
+        __nv_bfloat16* dq = p.dqkv + ((((size_t)b * p.N + row) * 3 + 0) * p.H + h) * p.d;
+        for (int c = 0; c < p.d / 32; ++c) {
+          uint32_t a[32];
+          tmem_ld_32x32(tm_dq + i * 64 + lane_off + c * 32, a);
+          tmem_ld_wait();
+          if (row < p.N) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 u;
+              u.x = pack_bf16x2(__uint_as_float(a[g * 8 + 0]), __uint_as_float(a[g * 8 + 1]));
+              u.y = pack_bf16x2(__uint_as_float(a[g * 8 + 2]), __uint_as_float(a[g * 8 + 3]));
+              u.z = pack_bf16x2(__uint_as_float(a[g * 8 + 4]), __uint_as_float(a[g * 8 + 5]));
+              u.w = pack_bf16x2(__uint_as_float(a[g * 8 + 6]), __uint_as_float(a[g * 8 + 7]));
+              *reinterpret_cast<uint4*>(dq + c * 32 + g * 8) = u;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(q_free);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace pb
+
+// dO, O: bf16 [B, N, H, d]; lse fp32 [B, H, N]; dqkv: bf16 [B, N, 3, H, d] (fully overwritten)
+extern "C" int passl_b200_attention_bwd(const void* qkv, const void* dO, const void* O, const float* lse, void* dqkv, int B,
+                                        int N, int H, int d, float scale, int causal, void* stream) {
+  if (B <= 0 || N <= 0 || N > 256 || H <= 0 || (d != 64 && d != 32)) return PB_ERR_UNSUPPORTED;
+  AttnBwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.dO = reinterpret_cast<const __nv_bfloat16*>(dO); p.O = reinterpret_cast<const __nv_bfloat16*>(O);
+  p.lse = lse; p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
+  p.B = B; p.N = N; p.H = H; p.d = d; p.causal = causal; p.scale = scale;
+  p.mblocks = (N + 127) / 128;
+  CUtensorMapSwizzle swz = (d == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  {
+    const uint64_t dd = d, H3 = 3ull * H;
+    uint64_t dims[4] = {dd, H3, (uint64_t)N, (uint64_t)B};
+    uint64_t str[3] = {dd * 2, H3 * dd * 2, (uint64_t)N * H3 * dd * 2};
+    uint32_t box[4] = {(uint32_t)d, 1, 128, 1};
+    int rc = make_tmap_bf16(&p.qkv_map, qkv, 4, dims, str, box, swz);
+    if (rc) return rc;
+    uint64_t dims2[4] = {dd, (uint64_t)H, (uint64_t)N, (uint64_t)B};
+    uint64_t str2[3] = {dd * 2, (uint64_t)H * dd * 2, (uint64_t)N * H * dd * 2};
+    rc = make_tmap_bf16(&p.do_map, dO, 4, dims2, str2, box, swz);
+    if (rc) return rc;
+  }
+  const int smem = 4 * 256 * d * 2 + 4 * 128 * 128 + 256 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    PB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 256 * 128 + 4 * 128 * 128 + 256 + 1024));
+    attr = true;
+  }
+  int grid = B * H < num_sms() ? B * H : num_sms();
+  attn_bwd_kernel<<<grid, 160, smem, (cudaStream_t)stream>>>(p);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}

@@ -10,8 +10,9 @@
 //           einsum('nc,mc->nm')/T + CE (passl/models/mocov3.py:187-198), CLIP logits + CE (clip.py:331-335).
 //
 // Work decomposition: CTA = (row group of MB*128 queries) x (contiguous slice of 64-key tiles).
-//   warp 0 lane 0 : TMA producer  (Q once, then key tiles through a STAGES ring, SWIZZLE_128B)
-//   warp 1 lane 0 : MMA issuer    (tcgen05.mma M=128 N=64 K=16; TMEM double-buffered per row block)
+//   warp 0 lane 0 : TMA producer  (key tiles through a STAGES ring, SWIZZLE_128B)
+//   warp 1 lane 0 : MMA issuer    (tcgen05.mma M=128 N=64 K=16, A = Q resident in TMEM (written once by the softmax warps
+//                                  with tcgen05.st) so only the key tile is read from shared memory; S double-buffered)
 //   warps 2..2+4*MB : softmax warps — tcgen05.ld 64 logits / thread / tile, online max+sum in the log2 domain,
 //                     rank counter for top-1 / top-5 accuracy.
 // Partials (m, l, cnt) per (row, slice) are merged by simce_finalize_kernel (shared with the fp32 variant).
@@ -29,7 +30,6 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
 struct InfoNceTcParams {
-  CUtensorMap q_map;  // [N, D] bf16, box {64, 128}
   CUtensorMap k_map;  // [K, D] bf16, box {64, 64}
   const __nv_bfloat16* Q;
   const __nv_bfloat16* Kmat;
@@ -48,15 +48,12 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int DC = p.D / 64;                       // 64-wide feature chunks
-  const int q_bytes = MB * 128 * p.D * 2;
   const int stage_bytes = NCE_BK * p.D * 2;
-  // stage count chosen on the host so that q_bytes + STAGES*stage_bytes fits; recompute the same way here
-  int STAGES = (200 * 1024 - q_bytes) / stage_bytes;
+  int STAGES = (200 * 1024) / stage_bytes;   // same rule as nce_plan() on the host
   if (STAGES > 8) STAGES = 8;
-  uint8_t* q_smem = smem;
-  uint8_t* k_smem = smem + q_bytes;
+  uint8_t* k_smem = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(k_smem + STAGES * stage_bytes);
-  uint64_t* q_full = bars;            // 1
+  uint64_t* q_ready = bars;           // 4*MB softmax-warp arrivals: Q rows are in TMEM
   uint64_t* k_full = bars + 1;        // STAGES
   uint64_t* k_empty = k_full + 8;     // STAGES
   uint64_t* s_full = k_empty + 8;     // 2
@@ -69,12 +66,12 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
   const int row_base = group * MB * 128;
   const int t_begin = (int)((long long)slice * p.tiles / p.slices);
   const int t_end = (int)((long long)(slice + 1) * p.tiles / p.slices);
-  constexpr uint32_t TMEM_COLS = 2 * MB * NCE_BK;  // 128 or 256
+  constexpr uint32_t TMEM_COLS = 512;
+  const uint32_t q_cols = p.D / 2;                 // bf16x2 per 32-bit TMEM column
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.q_map);
     tma_prefetch_desc(&p.k_map);
-    mbar_init(q_full, 1);
+    mbar_init(q_ready, 4 * MB);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
@@ -90,14 +87,12 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tm_q = tmem_base;                       // Q (A operand): block b at columns [b*q_cols, (b+1)*q_cols)
+  const uint32_t tm_s = tmem_base + MB * q_cols;         // S accumulators: (buf*MB + b) * 64
 
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer ----------------
-      mbar_arrive_expect_tx(q_full, (uint32_t)q_bytes);
-      for (int b = 0; b < MB; ++b)
-        for (int c = 0; c < DC; ++c)
-          tma_load_2d(q_smem + (b * DC + c) * (128 * 128), &p.q_map, q_full, c * 64, row_base + b * 128);
       int stage = 0;
       uint32_t phase = 0;
       for (int t = t_begin; t < t_end; ++t) {
@@ -112,7 +107,8 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
       constexpr uint32_t idesc = make_idesc_bf16(128, NCE_BK, false, false);
-      mbar_wait(q_full, 0);
+      mbar_wait(q_ready, 0);
+      tc_fence_after();
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -124,14 +120,12 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
         tc_fence_after();
         const uint32_t kb = smem_u32(k_smem + stage * stage_bytes);
         for (int b = 0; b < MB; ++b) {
-          const uint32_t d_tmem = tmem_base + (buf * MB + b) * NCE_BK;
-          const uint32_t qb = smem_u32(q_smem + b * DC * (128 * 128));
+          const uint32_t d_tmem = tm_s + (buf * MB + b) * NCE_BK;
           for (int c = 0; c < DC; ++c) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              uint64_t da = make_smem_desc_sw128(qb + c * (128 * 128) + k * 32, 16, 1024);
               uint64_t db = make_smem_desc_sw128(kb + c * (NCE_BK * 128) + k * 32, 16, 1024);
-              umma_bf16(d_tmem, da, db, idesc, (c > 0 || k > 0) ? 1u : 0u);
+              umma_bf16_ts(d_tmem, tm_q + b * q_cols + c * 32 + k * 8, db, idesc, (c > 0 || k > 0) ? 1u : 0u);
             }
           }
         }
@@ -149,33 +143,52 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
     const bool row_ok = row < p.N;
     const float c2 = p.scale * kLog2e;  // logits in the log2 domain: y = dot * c2
 
-    // target logit (positive pair or labelled column), fp32 accumulate over bf16 q
+    // Prologue: this thread's query row -> TMEM (A operand of every MMA) and its target logit (positive pair or labelled
+    // column), fp32 accumulation over the bf16 query.
     float tgt2 = 0.f;
     long long lab = -1;
     int ex = -1;
-    if (row_ok) {
-      const __nv_bfloat16* qr = p.Q + (size_t)row * p.D;
+    {
+      const __nv_bfloat16* qr = p.Q + (size_t)(row_ok ? row : 0) * p.D;
+      const float* pr = nullptr;
+      const __nv_bfloat16* kr = nullptr;
+      if (row_ok) {
+        if (p.P) pr = p.P + (size_t)row * p.D;
+        else { lab = p.label[row]; kr = p.Kmat + (size_t)lab * p.D; }
+        if (p.excl) ex = p.excl[row];
+      }
       float s = 0.f;
-      if (p.P) {
-        const float* pr = p.P + (size_t)row * p.D;
-        for (int d = 0; d < p.D; d += 8) {
-          uint4 u = *reinterpret_cast<const uint4*>(qr + d);
-          float4 a = *reinterpret_cast<const float4*>(pr + d), c = *reinterpret_cast<const float4*>(pr + d + 4);
-          float2 q0 = unpack_bf16x2(u.x), q1 = unpack_bf16x2(u.y), q2 = unpack_bf16x2(u.z), q3 = unpack_bf16x2(u.w);
-          s += q0.x * a.x + q0.y * a.y + q1.x * a.z + q1.y * a.w + q2.x * c.x + q2.y * c.y + q3.x * c.z + q3.y * c.w;
+      const uint32_t tq = tm_q + ((q4 * 32u) << 16) + b * q_cols;
+      for (int ch = 0; ch < DC; ++ch) {
+        uint32_t w[32];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          uint4 u = row_ok ? *reinterpret_cast<const uint4*>(qr + ch * 64 + g * 8) : make_uint4(0, 0, 0, 0);
+          w[g * 4 + 0] = u.x; w[g * 4 + 1] = u.y; w[g * 4 + 2] = u.z; w[g * 4 + 3] = u.w;
         }
-      } else {
-        lab = p.label[row];
-        const __nv_bfloat16* kr = p.Kmat + (size_t)lab * p.D;
-        for (int d = 0; d < p.D; d += 8) {
-          uint4 u = *reinterpret_cast<const uint4*>(qr + d), w = *reinterpret_cast<const uint4*>(kr + d);
-          float2 q0 = unpack_bf16x2(u.x), q1 = unpack_bf16x2(u.y), q2 = unpack_bf16x2(u.z), q3 = unpack_bf16x2(u.w);
-          float2 k0 = unpack_bf16x2(w.x), k1 = unpack_bf16x2(w.y), k2 = unpack_bf16x2(w.z), k3 = unpack_bf16x2(w.w);
-          s += q0.x * k0.x + q0.y * k0.y + q1.x * k1.x + q1.y * k1.y + q2.x * k2.x + q2.y * k2.y + q3.x * k3.x + q3.y * k3.y;
+        tmem_st_32x32(tq + ch * 32, w);
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float2 q0 = unpack_bf16x2(w[g * 4 + 0]), q1 = unpack_bf16x2(w[g * 4 + 1]), q2 = unpack_bf16x2(w[g * 4 + 2]),
+                         q3 = unpack_bf16x2(w[g * 4 + 3]);
+            const int d = ch * 64 + g * 8;
+            if (pr) {
+              const float4 a = *reinterpret_cast<const float4*>(pr + d), c = *reinterpret_cast<const float4*>(pr + d + 4);
+              s += q0.x * a.x + q0.y * a.y + q1.x * a.z + q1.y * a.w + q2.x * c.x + q2.y * c.y + q3.x * c.z + q3.y * c.w;
+            } else {
+              const uint4 kw = *reinterpret_cast<const uint4*>(kr + d);
+              const float2 k0 = unpack_bf16x2(kw.x), k1 = unpack_bf16x2(kw.y), k2 = unpack_bf16x2(kw.z), k3 = unpack_bf16x2(kw.w);
+              s += q0.x * k0.x + q0.y * k0.y + q1.x * k1.x + q1.y * k1.y + q2.x * k2.x + q2.y * k2.y + q3.x * k3.x + q3.y * k3.y;
+            }
+          }
         }
       }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(q_ready);
       tgt2 = s * c2;
-      if (p.excl) ex = p.excl[row];
     }
 
     float m = -INFINITY, l = 0.f;
@@ -186,7 +199,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
       const uint32_t bphase = (it >> 1) & 1;
       mbar_wait(&s_full[buf], bphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((q4 * 32u) << 16) + (buf * MB + b) * NCE_BK;
+      const uint32_t taddr = tm_s + ((q4 * 32u) << 16) + (buf * MB + b) * NCE_BK;
       uint32_t v[64];
       tmem_ld_32x32(taddr, v);
       tmem_ld_32x32(taddr + 32, v + 32);
@@ -252,10 +265,10 @@ static void nce_plan(int N, int K, int D, int& MB, int& groups, int& slices, int
   slices = num_sms() / groups;
   if (slices < 1) slices = 1;
   if (slices > tiles) slices = tiles;
-  int q_bytes = MB * 128 * D * 2, stage_bytes = NCE_BK * D * 2;
-  int stages = (200 * 1024 - q_bytes) / stage_bytes;
+  int stage_bytes = NCE_BK * D * 2;
+  int stages = (200 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
-  smem = q_bytes + stages * stage_bytes + 512 + 1024;
+  smem = stages * stage_bytes + 512 + 1024;
 }
 
 }  // namespace pb
@@ -291,13 +304,10 @@ extern "C" int passl_b200_infonce_tc_fwd(const void* Q, const void* Kmat, const 
   p.part_l = reinterpret_cast<float*>(ws); ws += (size_t)N * p.slices * 4;
   p.part_cnt = reinterpret_cast<int*>(ws);
   p.tgt = tgt;
-  uint64_t qd[2] = {(uint64_t)D, (uint64_t)N}, qs[1] = {(uint64_t)D * 2};
-  uint32_t qb[2] = {64, 128};
-  int rc = make_tmap_bf16(&p.q_map, Q, 2, qd, qs, qb);
-  if (rc) return rc;
+  uint64_t qs[1] = {(uint64_t)D * 2};
   uint64_t kd[2] = {(uint64_t)D, (uint64_t)K};
   uint32_t kbx[2] = {64, NCE_BK};
-  rc = make_tmap_bf16(&p.k_map, Kmat, 2, kd, qs, kbx);
+  int rc = make_tmap_bf16(&p.k_map, Kmat, 2, kd, qs, kbx);
   if (rc) return rc;
   int grid = p.row_groups * p.slices;
   static bool attr_done = false;
