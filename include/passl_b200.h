@@ -47,11 +47,12 @@ int passl_b200_gemm_bf16(const void* A, const void* B, void* out, int M, int N, 
                          const float* bias, const void* residual, int act, float alpha, int splits, float* col_sum,
                          float* col_sqsum, void* stream);
 /* + gate after the activation: aux (bf16, addressed like out), aux_mode 1 = ReLU mask (aux>0), 2 = *GELU'(aux),
- *   3 = *QuickGELU'(aux) — fuses the activation backward into the dgrad GEMM. */
+ *   3 = *QuickGELU'(aux) — fuses the activation backward into the dgrad GEMM;
+ *   preact_out (bf16, addressed like out, optional): the value before the activation, kept for that backward. */
 int passl_b200_gemm_bf16_ex(const void* A, const void* B, void* out, int M, int N, int K, int a_mn_major,
                             int b_mn_major, long long lda, long long ldb, long long ldc, int out_fp32, int atomic_add,
                             const float* bias, const void* residual, int act, float alpha, int splits, float* col_sum,
-                            float* col_sqsum, const void* aux, int aux_mode, void* stream);
+                            float* col_sqsum, const void* aux, int aux_mode, void* preact_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Convolution as implicit GEMM over NHWC bf16 (replaces paddle nn.Conv2D -> cuDNN fwd/dgrad/wgrad at
@@ -169,8 +170,9 @@ int passl_b200_bn_bwd_apply(const void* y, const void* dz, const void* z, const 
 int passl_b200_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                              long long T, int D, float eps, void* stream);
 int passl_b200_layernorm_bwd_blocks(long long T);
-int passl_b200_layernorm_bwd(const void* x, const void* dy, const float* gamma, const float* mean, const float* rstd, void* dx,
-                             float* part, long long T, int D, void* stream);
+/* dx = LN'(dy) + dres   (dres: optional bf16 [T, D] gradient of the residual connection, fused add) */
+int passl_b200_layernorm_bwd(const void* x, const void* dy, const float* gamma, const float* mean, const float* rstd,
+                             const void* dres, void* dx, float* part, long long T, int D, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Fused multi-head self-attention on tcgen05 (N <= 256 tokens, head dim 64 or 32): softmax(Q K^T * scale) V per

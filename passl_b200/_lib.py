@@ -21,7 +21,7 @@ SIGNATURES = {
                                      c_void_p]),
     "passl_b200_gemm_bf16_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll,
                                         c_int, c_int, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p, c_void_p,
-                                        c_void_p, c_int, c_void_p]),
+                                        c_void_p, c_int, c_void_p, c_void_p]),
     "passl_b200_conv2d_fwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 9 +
                                    [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "passl_b200_conv2d_dgrad_workspace_bytes": (c_ll, [c_int] * 4),
@@ -60,7 +60,7 @@ SIGNATURES = {
     "passl_b200_attention_bwd": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "passl_b200_layernorm_fwd": (c_int, [c_void_p] * 6 + [c_ll, c_int, c_float, c_void_p]),
     "passl_b200_layernorm_bwd_blocks": (c_int, [c_ll]),
-    "passl_b200_layernorm_bwd": (c_int, [c_void_p] * 7 + [c_ll, c_int, c_void_p]),
+    "passl_b200_layernorm_bwd": (c_int, [c_void_p] * 8 + [c_ll, c_int, c_void_p]),
     "passl_b200_im2col_nchw_f32": (c_int, [c_void_p, c_void_p] + [c_int] * 9 + [c_void_p]),
     "passl_b200_maxpool3x3s2_fwd": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
     "passl_b200_maxpool3x3s2_bwd": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),

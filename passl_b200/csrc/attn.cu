@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(160, 1) attn_fwd_kernel(const __grid_constant_
         }
         if (!row_ok || m == -INFINITY) m = 0.f;
         // pass 2: p = exp2(y - m), row sum, P -> smem (bf16, SWIZZLE_128B K-major: chunk of 64 keys = [128 rows][128 B])
-        float l = 0.f;
+        float l = 0.f, l_exact = 0.f;
         for (int c = 0; c < p.NKP / 32; ++c) {
           uint32_t v[32];
           tmem_ld_32x32(ts + c * 32, v);
@@ -145,9 +145,11 @@ __global__ void __launch_bounds__(160, 1) attn_fwd_kernel(const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float pj = (c * 32 + j < jmax) ? exp2f(__uint_as_float(v[j]) * c2 - m) : 0.f;
-            // the tensor core multiplies the bf16-rounded probability: sum the same rounded values
+            // the tensor core multiplies the bf16-rounded probability: normalise O by the sum of the same rounded values,
+            // but report the exact log-sum-exp (the backward recomputes P from it)
             e[j] = __bfloat162float(__float2bfloat16_rn(pj));
             l += e[j];
+            l_exact += pj;
           }
           const int chunk = (c * 32) >> 6;
           uint8_t* base = p_s + chunk * (128 * 128) + (r >> 3) * 1024 + (r & 7) * 128;
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(160, 1) attn_fwd_kernel(const __grid_constant_
             }
           }
         }
-        if (row_ok) p.lse[((size_t)b * p.H + h) * p.N + row] = (m + log2f(l)) * kAttnLn2;
+        if (row_ok) p.lse[((size_t)b * p.H + h) * p.N + row] = (m + log2f(l_exact)) * kAttnLn2;
         tc_fence_before();
       }
     }

@@ -66,6 +66,7 @@ struct GemmParams {
   // optional gate applied after the activation: 1 = ReLU mask (aux > 0), 2 = multiply by GELU'(aux), 3 = QuickGELU'(aux)
   const __nv_bfloat16* aux;     // same addressing as out
   int aux_mode;
+  __nv_bfloat16* preact;        // optional: value before the activation (bias added), same addressing as out (GELU backward)
   // optional per-column statistics of the stored value (BatchNorm batch stats): sum and sum of squares
   float* col_sum;
   float* col_sqsum;
@@ -301,6 +302,19 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (cc0 + j < col_lim) f[j] += __ldg(p.bias + oc0 + j);
+        }
+        if (p.preact && row_ok) {
+          __nv_bfloat16* pp = p.preact + row_off + oc0;
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8)
+            if (cc0 + j8 * 8 < col_lim) {
+              uint4 u;
+              u.x = pack_bf16x2(f[j8 * 8 + 0], f[j8 * 8 + 1]);
+              u.y = pack_bf16x2(f[j8 * 8 + 2], f[j8 * 8 + 3]);
+              u.z = pack_bf16x2(f[j8 * 8 + 4], f[j8 * 8 + 5]);
+              u.w = pack_bf16x2(f[j8 * 8 + 6], f[j8 * 8 + 7]);
+              *reinterpret_cast<uint4*>(pp + j8 * 8) = u;
+            }
         }
         if (p.act != ACT_NONE) {
 #pragma unroll

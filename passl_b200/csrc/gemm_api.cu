@@ -125,14 +125,14 @@ extern "C" int passl_b200_gemm_bf16(const void* A, const void* B, void* out, int
                                     int atomic_add, const float* bias, const void* residual, int act, float alpha,
                                     int splits, float* col_sum, float* col_sqsum, void* stream) {
   return passl_b200_gemm_bf16_ex(A, B, out, M, N, K, a_mn_major, b_mn_major, lda, ldb, ldc, out_fp32, atomic_add, bias,
-                                 residual, act, alpha, splits, col_sum, col_sqsum, nullptr, 0, stream);
+                                 residual, act, alpha, splits, col_sum, col_sqsum, nullptr, 0, nullptr, stream);
 }
 
 extern "C" int passl_b200_gemm_bf16_ex(const void* A, const void* B, void* out, int M, int N, int K, int a_mn_major,
                                        int b_mn_major, long long lda, long long ldb, long long ldc, int out_fp32,
                                        int atomic_add, const float* bias, const void* residual, int act, float alpha,
                                        int splits, float* col_sum, float* col_sqsum, const void* aux, int aux_mode,
-                                       void* stream) {
+                                       void* preact_out, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0) return PB_ERR_BAD_ARG;
   if ((lda % 8) || (ldb % 8) || (N % 8) || (ldc % (out_fp32 ? 4 : 8))) return PB_ERR_BAD_ARG;
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(out)) & 15) return PB_ERR_BAD_ARG;
@@ -155,6 +155,7 @@ extern "C" int passl_b200_gemm_bf16_ex(const void* A, const void* B, void* out, 
   set_epilogue(p, out, ldc, out_fp32, atomic_add, bias, residual, act, alpha, col_sum, col_sqsum);
   p.aux = reinterpret_cast<const __nv_bfloat16*>(aux);
   p.aux_mode = aux_mode;
+  p.preact = reinterpret_cast<__nv_bfloat16*>(preact_out);
   return launch_gemm(p, BN, 64, a_mn_major != 0, b_mn_major != 0, (cudaStream_t)stream);
 }
 

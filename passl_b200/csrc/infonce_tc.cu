@@ -30,6 +30,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
 struct InfoNceTcParams {
+  CUtensorMap q_map;  // [N, D] bf16, box {64, 128}
   CUtensorMap k_map;  // [K, D] bf16, box {64, 64}
   const __nv_bfloat16* Q;
   const __nv_bfloat16* Kmat;
@@ -48,17 +49,20 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int DC = p.D / 64;                       // 64-wide feature chunks
+  const int q_bytes = MB * 128 * p.D * 2;
   const int stage_bytes = NCE_BK * p.D * 2;
-  int STAGES = (200 * 1024) / stage_bytes;   // same rule as nce_plan() on the host
+  int STAGES = (200 * 1024 - q_bytes) / stage_bytes;   // same rule as nce_plan() on the host
   if (STAGES > 8) STAGES = 8;
-  uint8_t* k_smem = smem;
+  uint8_t* q_smem = smem;                              // staging only: rows go smem -> registers -> TMEM
+  uint8_t* k_smem = smem + q_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(k_smem + STAGES * stage_bytes);
   uint64_t* q_ready = bars;           // 4*MB softmax-warp arrivals: Q rows are in TMEM
   uint64_t* k_full = bars + 1;        // STAGES
   uint64_t* k_empty = k_full + 8;     // STAGES
   uint64_t* s_full = k_empty + 8;     // 2
   uint64_t* s_empty = s_full + 2;     // 2
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(s_empty + 2);
+  uint64_t* q_full = s_empty + 2;     // TMA: Q block staged in shared memory
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(q_full + 1);
 
   const uint32_t warp = warp_id(), lane = lane_id();
   const int group = blockIdx.x / p.slices;
@@ -70,8 +74,10 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
   const uint32_t q_cols = p.D / 2;                 // bf16x2 per 32-bit TMEM column
 
   if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.q_map);
     tma_prefetch_desc(&p.k_map);
     mbar_init(q_ready, 4 * MB);
+    mbar_init(q_full, 1);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
@@ -93,6 +99,10 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer ----------------
+      mbar_arrive_expect_tx(q_full, (uint32_t)q_bytes);
+      for (int b = 0; b < MB; ++b)
+        for (int c = 0; c < DC; ++c)
+          tma_load_2d(q_smem + (b * DC + c) * (128 * 128), &p.q_map, q_full, c * 64, row_base + b * 128);
       int stage = 0;
       uint32_t phase = 0;
       for (int t = t_begin; t < t_end; ++t) {
@@ -143,52 +153,60 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
     const bool row_ok = row < p.N;
     const float c2 = p.scale * kLog2e;  // logits in the log2 domain: y = dot * c2
 
-    // Prologue: this thread's query row -> TMEM (A operand of every MMA) and its target logit (positive pair or labelled
-    // column), fp32 accumulation over the bf16 query.
+    // Prologue (coalesced): Q block arrives by TMA in shared memory; each thread copies its own row smem -> registers ->
+    // TMEM (A operand of every MMA); target logits (positive pair or labelled column) are computed warp-cooperatively:
+    // for each of the warp's 32 rows the lanes split D, so global reads are whole 512 B / 256 B rows.
     float tgt2 = 0.f;
     long long lab = -1;
     int ex = -1;
     {
-      const __nv_bfloat16* qr = p.Q + (size_t)(row_ok ? row : 0) * p.D;
-      const float* pr = nullptr;
-      const __nv_bfloat16* kr = nullptr;
-      if (row_ok) {
-        if (p.P) pr = p.P + (size_t)row * p.D;
-        else { lab = p.label[row]; kr = p.Kmat + (size_t)lab * p.D; }
-        if (p.excl) ex = p.excl[row];
-      }
-      float s = 0.f;
+      const int rl = q4 * 32 + lane;                       // row inside the 128-row block
+      mbar_wait(q_full, 0);
       const uint32_t tq = tm_q + ((q4 * 32u) << 16) + b * q_cols;
       for (int ch = 0; ch < DC; ++ch) {
+        const uint8_t* base = q_smem + (b * DC + ch) * (128 * 128) + (rl >> 3) * 1024 + (rl & 7) * 128;
         uint32_t w[32];
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
-          uint4 u = row_ok ? *reinterpret_cast<const uint4*>(qr + ch * 64 + g * 8) : make_uint4(0, 0, 0, 0);
+          const uint4 u = *reinterpret_cast<const uint4*>(base + (((g ^ (rl & 7)) & 7) << 4));
           w[g * 4 + 0] = u.x; w[g * 4 + 1] = u.y; w[g * 4 + 2] = u.z; w[g * 4 + 3] = u.w;
         }
         tmem_st_32x32(tq + ch * 32, w);
-        if (row_ok) {
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float2 q0 = unpack_bf16x2(w[g * 4 + 0]), q1 = unpack_bf16x2(w[g * 4 + 1]), q2 = unpack_bf16x2(w[g * 4 + 2]),
-                         q3 = unpack_bf16x2(w[g * 4 + 3]);
-            const int d = ch * 64 + g * 8;
-            if (pr) {
-              const float4 a = *reinterpret_cast<const float4*>(pr + d), c = *reinterpret_cast<const float4*>(pr + d + 4);
-              s += q0.x * a.x + q0.y * a.y + q1.x * a.z + q1.y * a.w + q2.x * c.x + q2.y * c.y + q3.x * c.z + q3.y * c.w;
-            } else {
-              const uint4 kw = *reinterpret_cast<const uint4*>(kr + d);
-              const float2 k0 = unpack_bf16x2(kw.x), k1 = unpack_bf16x2(kw.y), k2 = unpack_bf16x2(kw.z), k3 = unpack_bf16x2(kw.w);
-              s += q0.x * k0.x + q0.y * k0.y + q1.x * k1.x + q1.y * k1.y + q2.x * k2.x + q2.y * k2.y + q3.x * k3.x + q3.y * k3.y;
-            }
-          }
-        }
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(q_ready);
-      tgt2 = s * c2;
+      if (row_ok) {
+        if (!p.P) lab = p.label[row];
+        if (p.excl) ex = p.excl[row];
+      }
+      float s_mine = 0.f;
+      for (int rr = 0; rr < 32; ++rr) {
+        const int r2 = q4 * 32 + rr;
+        const int grow = row_base + b * 128 + r2;
+        if (grow >= p.N) break;                              // warp-uniform
+        const long long lab_r = p.P ? 0 : __shfl_sync(0xffffffffu, lab, rr);
+        float part = 0.f;
+        for (int d4 = lane * 4; d4 < p.D; d4 += 128) {
+          const int ch = d4 >> 6, col = d4 & 63;
+          const uint8_t* qa = q_smem + (b * DC + ch) * (128 * 128) + (r2 >> 3) * 1024 + (r2 & 7) * 128 +
+                              ((((col >> 3) ^ (r2 & 7)) & 7) << 4) + (col & 7) * 2;
+          const uint2 qu = *reinterpret_cast<const uint2*>(qa);
+          const float2 q0 = unpack_bf16x2(qu.x), q1 = unpack_bf16x2(qu.y);
+          if (p.P) {
+            const float4 a = *reinterpret_cast<const float4*>(p.P + (size_t)grow * p.D + d4);
+            part += q0.x * a.x + q0.y * a.y + q1.x * a.z + q1.y * a.w;
+          } else {
+            const uint2 ku = *reinterpret_cast<const uint2*>(p.Kmat + (size_t)lab_r * p.D + d4);
+            const float2 k0 = unpack_bf16x2(ku.x), k1 = unpack_bf16x2(ku.y);
+            part += q0.x * k0.x + q0.y * k0.y + q1.x * k1.x + q1.y * k1.y;
+          }
+        }
+        part = warp_sum(part);
+        if (lane == rr) s_mine = part;
+      }
+      tgt2 = s_mine * c2;
     }
 
     float m = -INFINITY, l = 0.f;
@@ -265,10 +283,10 @@ static void nce_plan(int N, int K, int D, int& MB, int& groups, int& slices, int
   slices = num_sms() / groups;
   if (slices < 1) slices = 1;
   if (slices > tiles) slices = tiles;
-  int stage_bytes = NCE_BK * D * 2;
-  int stages = (200 * 1024) / stage_bytes;
+  int q_bytes = MB * 128 * D * 2, stage_bytes = NCE_BK * D * 2;
+  int stages = (200 * 1024 - q_bytes) / stage_bytes;
   if (stages > 8) stages = 8;
-  smem = stages * stage_bytes + 512 + 1024;
+  smem = q_bytes + stages * stage_bytes + 512 + 1024;
 }
 
 }  // namespace pb
@@ -278,7 +296,7 @@ using namespace pb;
 extern "C" long long passl_b200_infonce_tc_workspace_bytes(int N, int K, int D) {
   int MB, groups, slices, tiles, smem;
   nce_plan(N, K, D, MB, groups, slices, tiles, smem);
-  return (long long)N * slices * 12 + 256;
+  return (long long)N * slices * 12 + simce_finalize_scratch_bytes(N) + 256;
 }
 
 // Forward.  Q [N,D] bf16 (normalised queries), Kmat [K,D] bf16 keys, P [N,D] fp32 optional positive keys
@@ -304,10 +322,13 @@ extern "C" int passl_b200_infonce_tc_fwd(const void* Q, const void* Kmat, const 
   p.part_l = reinterpret_cast<float*>(ws); ws += (size_t)N * p.slices * 4;
   p.part_cnt = reinterpret_cast<int*>(ws);
   p.tgt = tgt;
-  uint64_t qs[1] = {(uint64_t)D * 2};
+  uint64_t qd[2] = {(uint64_t)D, (uint64_t)N}, qs[1] = {(uint64_t)D * 2};
+  uint32_t qbx[2] = {64, 128};
+  int rc = make_tmap_bf16(&p.q_map, Q, 2, qd, qs, qbx);
+  if (rc) return rc;
   uint64_t kd[2] = {(uint64_t)D, (uint64_t)K};
   uint32_t kbx[2] = {64, NCE_BK};
-  int rc = make_tmap_bf16(&p.k_map, Kmat, 2, kd, qs, kbx);
+  rc = make_tmap_bf16(&p.k_map, Kmat, 2, kd, qs, kbx);
   if (rc) return rc;
   int grid = p.row_groups * p.slices;
   static bool attr_done = false;
@@ -319,8 +340,8 @@ extern "C" int passl_b200_infonce_tc_fwd(const void* Q, const void* Kmat, const 
   if (MB == 2) infonce_tc_fwd_kernel<2><<<grid, 64 + 256, smem, st>>>(p);
   else infonce_tc_fwd_kernel<1><<<grid, 64 + 128, smem, st>>>(p);
   PB_LAUNCH_CHECK();
-  simce_finalize_kernel<<<1, 1024, 0, st>>>(p.part_m, p.part_l, p.part_cnt, tgt, N, p.slices, P ? 1 : 0, loss_scale,
-                                             lse, loss_rows, out_scalars);
-  PB_LAUNCH_CHECK();
+  PB_CUDA_CHECK(launch_simce_finalize(p.part_m, p.part_l, p.part_cnt, tgt, N, p.slices, P ? 1 : 0, loss_scale, lse,
+                                      loss_rows, out_scalars, reinterpret_cast<float*>(p.part_cnt + (size_t)N * p.slices), st));
+  passl_b200_launch_counter_add(1);
   return PB_OK;
 }

@@ -75,8 +75,9 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* __rest
 template <int MAXCH>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                                                      const float* __restrict__ gamma, const float* __restrict__ mean,
-                                                     const float* __restrict__ rstd, __nv_bfloat16* __restrict__ dx,
-                                                     float* __restrict__ part, long long T, int D, int rows_per_block) {
+                                                     const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ dres,
+                                                     __nv_bfloat16* __restrict__ dx, float* __restrict__ part, long long T,
+                                                     int D, int rows_per_block) {
   extern __shared__ float red[];  // [8 warps][2][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunks = D >> 3;
@@ -121,6 +122,12 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
         float o[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = rs * (g[j][e] - s1 - xh[j][e] * s2);
+        if (dres) {   // gradient arriving through the residual connection around this LayerNorm's branch
+          float rr[8];
+          ln_unpack8(ld_nc_v4(dres + row * D + c * 8), rr);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] += rr[e];
+        }
         *reinterpret_cast<uint4*>(dx + row * D + c * 8) = ln_pack8(o);
       }
     }
@@ -180,7 +187,8 @@ extern "C" int passl_b200_layernorm_bwd_blocks(long long T) {
 
 // part: fp32 [nblk, 2, D] partials (dbeta, dgamma) -> sum with passl_b200_bn_bwd_finalize
 extern "C" int passl_b200_layernorm_bwd(const void* x, const void* dy, const float* gamma, const float* mean,
-                                        const float* rstd, void* dx, float* part, long long T, int D, void* stream) {
+                                        const float* rstd, const void* dres, void* dx, float* part, long long T, int D,
+                                        void* stream) {
   if (T <= 0 || D <= 0 || D % 8 || D > 256 * LN_MAXCH) return PB_ERR_BAD_ARG;
   int blocks, rpb;
   ln_bwd_cfg(T, blocks, rpb);
@@ -194,10 +202,12 @@ extern "C" int passl_b200_layernorm_bwd(const void* x, const void* dy, const flo
   if (D <= 1024)
     ln_bwd_kernel<4><<<blocks, 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
                                                                  reinterpret_cast<const __nv_bfloat16*>(dy), gamma, mean, rstd,
+                                                                 reinterpret_cast<const __nv_bfloat16*>(dres),
                                                                  reinterpret_cast<__nv_bfloat16*>(dx), part, T, D, rpb);
   else
     ln_bwd_kernel<8><<<blocks, 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
                                                                  reinterpret_cast<const __nv_bfloat16*>(dy), gamma, mean, rstd,
+                                                                 reinterpret_cast<const __nv_bfloat16*>(dres),
                                                                  reinterpret_cast<__nv_bfloat16*>(dx), part, T, D, rpb);
   PB_LAUNCH_CHECK();
   return PB_OK;

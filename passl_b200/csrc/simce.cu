@@ -268,7 +268,7 @@ using namespace pb;
 
 extern "C" long long passl_b200_simce_workspace_bytes(int N, int K) {
   int s = pick_splits(N, K);
-  return (long long)N * s * 12 + (long long)N * 8 + 256;
+  return (long long)N * s * 12 + (long long)N * 8 + simce_finalize_scratch_bytes(N) + 256;
 }
 
 // Forward.  out_scalars[0..2] = {loss_scale * mean loss, acc1 %, acc5 %}; lse[N] and tgt[N] are saved for backward.
@@ -298,9 +298,9 @@ extern "C" int passl_b200_simce_fwd_f32(const float* A, const void* B, int b_is_
     simce_fwd_kernel<float><<<grid, 256, smem, st>>>(p);
   }
   PB_LAUNCH_CHECK();
-  simce_finalize_kernel<<<1, 1024, 0, st>>>(p.part_m, p.part_l, p.part_cnt, tgt, N, p.splits, P ? 1 : 0, loss_scale,
-                                             lse, loss_rows, out_scalars);
-  PB_LAUNCH_CHECK();
+  PB_CUDA_CHECK(launch_simce_finalize(p.part_m, p.part_l, p.part_cnt, tgt, N, p.splits, P ? 1 : 0, loss_scale, lse,
+                                      loss_rows, out_scalars, reinterpret_cast<float*>(p.part_cnt + (size_t)N * p.splits), st));
+  passl_b200_launch_counter_add(1);
   return PB_OK;
 }
 

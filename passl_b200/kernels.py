@@ -36,7 +36,7 @@ def workspace(nbytes, device, tag="default"):
 # GEMM
 # ------------------------------------------------------------------------------------------------------------
 def gemm(a, b, *, a_t=False, b_t=False, out=None, out_dtype=torch.bfloat16, bias=None, residual=None, act=None,
-         alpha=1.0, splits=1, accumulate=False, col_stats=None, aux=None, aux_mode_name="relu_mask"):
+         alpha=1.0, splits=1, accumulate=False, col_stats=None, aux=None, aux_mode_name="relu_mask", preact_out=None):
     """out[M,N] = act(alpha * A @ B^T + bias) + residual.
 
     a: [M,K] (or [K,M] when a_t), b: [N,K] (or [K,N] when b_t), bf16, last dim contiguous.
@@ -67,7 +67,8 @@ def gemm(a, b, *, a_t=False, b_t=False, out=None, out_dtype=torch.bfloat16, bias
         assert aux.dtype == torch.bfloat16 and aux.stride(0) == out.stride(0)
     code = lib.passl_b200_gemm_bf16_ex(_ptr(a), _ptr(b), _ptr(out), M, N, K, int(a_t), int(b_t), a.stride(0), b.stride(0),
                                        out.stride(0), int(out_fp32), atomic, _ptr(bias), _ptr(residual), ACT[act],
-                                       float(alpha), int(splits), _ptr(cs), _ptr(cq), _ptr(aux), aux_mode, _stream())
+                                       float(alpha), int(splits), _ptr(cs), _ptr(cq), _ptr(aux), aux_mode, _ptr(preact_out),
+                                       _stream())
     _lib.check(code, "gemm_bf16")
     return out
 

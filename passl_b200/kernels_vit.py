@@ -19,15 +19,15 @@ def layernorm_fwd(x, gamma, beta, eps=1e-6):
     return y, mean, rstd
 
 
-def layernorm_bwd(x, dy, gamma, mean, rstd, dgamma=None, dbeta=None):
+def layernorm_bwd(x, dy, gamma, mean, rstd, dgamma=None, dbeta=None, dres=None):
     """Returns dx bf16; accumulates dgamma / dbeta into the given fp32 buffers (or returns sums [2, D] = (dbeta, dgamma))."""
     lib = _lib.load()
     T, D = x.shape
     nblk = lib.passl_b200_layernorm_bwd_blocks(T)
     part = torch.empty((nblk, 2, D), dtype=torch.float32, device=x.device)
     dx = torch.empty_like(x)
-    _lib.check(lib.passl_b200_layernorm_bwd(_ptr(x), _ptr(dy.contiguous()), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(part),
-                                            T, D, _stream()), "layernorm_bwd")
+    _lib.check(lib.passl_b200_layernorm_bwd(_ptr(x), _ptr(dy.contiguous()), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dres), _ptr(dx),
+                                            _ptr(part), T, D, _stream()), "layernorm_bwd")
     sums = torch.empty((2, D), dtype=torch.float32, device=x.device)
     _lib.check(lib.passl_b200_bn_bwd_finalize(_ptr(part), nblk, _ptr(sums), _ptr(dgamma), _ptr(dbeta), D, _stream()),
                "ln_bwd_finalize")

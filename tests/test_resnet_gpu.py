@@ -116,6 +116,34 @@ def test_bottleneck_fwd_bwd_vs_oracle(inpl, planes, stride, ds):
         assert rel(got, ref) < 0.12, (name, rel(got, ref))
 
 
+def test_stem_fwd_bwd_vs_oracle():
+    from oracle import resnet as O
+    from passl_b200.modeling.backbones.resnet import Stem
+    torch.manual_seed(0)
+    stem = Stem(maxpool=True).cuda()
+    torch.nn.init.uniform_(stem.bn.weight, 0.5, 1.5)
+    torch.nn.init.normal_(stem.bn.bias, 0, 0.2)
+    img = torch.randn(8, 3, 64, 64, device="cuda")
+    out, ctx = stem.fwd(img)
+    dout = torch.randn_like(out)
+    for p_ in stem.parameters():
+        p_.grad = torch.zeros_like(p_)
+    stem.bwd(ctx, dout)
+    torch.cuda.synchronize()
+    p = {"stem." + k: v.requires_grad_(True) for k, v in O.params_from_cuda_module(stem).items()}
+    p["stem.weight"] = p["stem.weight"].detach().requires_grad_(True)
+    x = img.cpu().bfloat16().double()          # im2col rounds the pixels to bf16
+    y = O.conv_bn(x, p, "stem", stride=2, pad=3)
+    y = F.max_pool2d(y, 3, 2, 1)
+    y.backward(dout.float().cpu().double().permute(0, 3, 1, 2))
+    assert rel(out.permute(0, 3, 1, 2), y) < 1e-2
+    gw = stem.weight.grad[:, :147].reshape(64, 7, 7, 3).permute(0, 3, 1, 2)
+    assert cos(gw, p["stem.weight"].grad) > 0.995, cos(gw, p["stem.weight"].grad)
+    assert rel(gw, p["stem.weight"].grad) < 0.1, rel(gw, p["stem.weight"].grad)
+    assert cos(stem.bn.weight.grad, p["stem.bn.weight"].grad) > 0.995
+    assert cos(stem.bn.bias.grad, p["stem.bn.bias"].grad) > 0.995
+
+
 def test_resnet50_small_fwd_bwd_vs_oracle():
     from oracle import resnet as O
     from passl_b200.modeling import build_backbone, build_neck
@@ -143,7 +171,7 @@ def test_resnet50_small_fwd_bwd_vs_oracle():
     er.backward(g.cpu().double())
     assert rel(feat.permute(0, 3, 1, 2), fr) < 5e-2, rel(feat.permute(0, 3, 1, 2), fr)
     assert rel(emb, er) < 5e-2, rel(emb, er)
-    worst, allg, allr = 1.0, [], []
+    worst, allg, allr, report = 1.0, [], [], []
     for name, prm in list(net.named_parameters()):
         ref = p[name].grad
         got = prm.grad
@@ -153,8 +181,12 @@ def test_resnet50_small_fwd_bwd_vs_oracle():
             got = got.permute(0, 3, 1, 2)
         if ref.norm() > 0:
             worst = min(worst, cos(got, ref))
+            report.append("%-32s cos %.4f rel %.4f |ref| %.3e" % (name, cos(got, ref), rel(got, ref), ref.norm().item()))
             allg.append(got.double().flatten().cpu())
             allr.append(ref.double().flatten().cpu())
+    import os
+    os.makedirs("gpurun_out", exist_ok=True)
+    open("gpurun_out/resnet_e2e_grad_report.txt", "w").write("\n".join(report))
     # 50 layers of bf16 activations + batch statistics: individual early-layer gradients drift, the full gradient agrees
     assert cos(torch.cat(allg), torch.cat(allr)) > 0.95, cos(torch.cat(allg), torch.cat(allr))
     assert worst > 0.5, worst
