@@ -186,6 +186,29 @@ int passl_b200_attention_bwd(const void* qkv, const void* dO, const void* O, con
                              int H, int d, float scale, int causal, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * MAE (passl/models/mae.py).
+ *   mae_random_masking (:184-212): noise fp32 [B,L] -> ids_shuffle / ids_restore int64 [B,L] (argsort, stable), mask fp32
+ *       [B,L] (0 keep / 1 remove).  The Paddle RNG stream is not reproducible, so the noise is an input.
+ *   token_assemble_fwd/bwd (:214-266, vision_transformer.py:340-346): mode 0 ViT (cls + patches + pos), mode 1 MAE encoder
+ *       input (gather kept patches by ids_shuffle, + pos, prepend cls), mode 2 MAE decoder input (un-shuffle by ids_restore
+ *       with mask tokens, + decoder pos).  bwd: ids = ids_restore (mode 1) / ids_shuffle (mode 2); acc_tok / acc_pos are
+ *       fp32 gradient accumulators of the cls / mask token and of a learnable positional table (ids_tok = ids_restore).
+ *   mae_loss_fwd/bwd (:268-284): masked-patch MSE with optional norm_pix; pred rows may include the cls row
+ *       (pred_tokens = L+1, pred_off = 1), imgs fp32 NCHW, mask_sum = sum(mask).
+ * ------------------------------------------------------------------------------------------------------------- */
+int passl_b200_mae_random_masking(const float* noise, long long* ids_shuffle, long long* ids_restore, float* mask, int B, int L,
+                                  int len_keep, void* stream);
+int passl_b200_token_assemble_fwd(const void* src, const long long* ids, const float* pos, const float* tok, void* out, int B,
+                                  int Ls, int Lo, int D, int mode, int keep, void* stream);
+int passl_b200_token_assemble_bwd(const void* dout, const long long* ids, void* dsrc, float* acc_tok, float* acc_pos,
+                                  const long long* ids_tok, int B, int Ls, int Lo, int D, int mode, int keep, void* stream);
+long long passl_b200_mae_loss_workspace_bytes(int B, int L);
+int passl_b200_mae_loss_fwd(const void* pred, const float* imgs, const float* mask, float* loss, int B, int Hp, int P,
+                            int pred_tokens, int pred_off, int norm_pix, float mask_sum, void* workspace, void* stream);
+int passl_b200_mae_loss_bwd(const void* pred, const float* imgs, const float* mask, const float* dloss, void* dpred, int B,
+                            int Hp, int P, int pred_tokens, int pred_off, int norm_pix, float mask_sum, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Stem / pooling.  im2col: reference NCHW fp32 images -> bf16 [N*Ho*Wo, Kpad] with K order (r, s, c), zero padded
  * (7x7/2 stem conv resnetimagenet.py:190-198; 16x16/16 patch embedding vision_transformer.py:231-236).
  * maxpool 3x3/2 pad 1 (resnetimagenet.py:198), arg-max tap saved as int8; global average pool (base_neck.py:52,79).

@@ -56,6 +56,12 @@ SIGNATURES = {
     "passl_b200_bn_apply": (c_int, [c_void_p] * 6 + [c_ll, c_int, c_int, c_void_p]),
     "passl_b200_bn_bwd_reduce": (c_int, [c_void_p] * 6 + [c_ll, c_int, c_int, c_void_p]),
     "passl_b200_bn_bwd_apply": (c_int, [c_void_p] * 10 + [c_ll, c_int, c_int, c_void_p]),
+    "passl_b200_mae_random_masking": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),
+    "passl_b200_token_assemble_fwd": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),
+    "passl_b200_token_assemble_bwd": (c_int, [c_void_p] * 6 + [c_int] * 6 + [c_void_p]),
+    "passl_b200_mae_loss_workspace_bytes": (c_ll, [c_int, c_int]),
+    "passl_b200_mae_loss_fwd": (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_float, c_void_p, c_void_p]),
+    "passl_b200_mae_loss_bwd": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_float, c_void_p]),
     "passl_b200_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "passl_b200_attention_bwd": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "passl_b200_layernorm_fwd": (c_int, [c_void_p] * 6 + [c_ll, c_int, c_float, c_void_p]),

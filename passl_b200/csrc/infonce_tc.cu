@@ -182,29 +182,42 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
         if (p.excl) ex = p.excl[row];
       }
       float s_mine = 0.f;
-      for (int rr = 0; rr < 32; ++rr) {
-        const int r2 = q4 * 32 + rr;
-        const int grow = row_base + b * 128 + r2;
-        if (grow >= p.N) break;                              // warp-uniform
-        const long long lab_r = p.P ? 0 : __shfl_sync(0xffffffffu, lab, rr);
-        float part = 0.f;
+      const int rows_left = p.N - (row_base + b * 128 + q4 * 32);          // warp-uniform
+      const int nrows = rows_left < 32 ? (rows_left > 0 ? rows_left : 0) : 32;
+      for (int r0 = 0; r0 < nrows; r0 += 8) {
+        // 8 rows per batch: issue all global loads first (independent), then the dot products and warp reductions
         for (int d4 = lane * 4; d4 < p.D; d4 += 128) {
-          const int ch = d4 >> 6, col = d4 & 63;
-          const uint8_t* qa = q_smem + (b * DC + ch) * (128 * 128) + (r2 >> 3) * 1024 + (r2 & 7) * 128 +
-                              ((((col >> 3) ^ (r2 & 7)) & 7) << 4) + (col & 7) * 2;
-          const uint2 qu = *reinterpret_cast<const uint2*>(qa);
-          const float2 q0 = unpack_bf16x2(qu.x), q1 = unpack_bf16x2(qu.y);
-          if (p.P) {
-            const float4 a = *reinterpret_cast<const float4*>(p.P + (size_t)grow * p.D + d4);
-            part += q0.x * a.x + q0.y * a.y + q1.x * a.z + q1.y * a.w;
-          } else {
-            const uint2 ku = *reinterpret_cast<const uint2*>(p.Kmat + (size_t)lab_r * p.D + d4);
-            const float2 k0 = unpack_bf16x2(ku.x), k1 = unpack_bf16x2(ku.y);
-            part += q0.x * k0.x + q0.y * k0.y + q1.x * k1.x + q1.y * k1.y;
+          float4 pa[8];
+          uint2 pk[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int rr = r0 + u;
+            const int grow = row_base + b * 128 + q4 * 32 + (rr < nrows ? rr : 0);
+            if (p.P) pa[u] = *reinterpret_cast<const float4*>(p.P + (size_t)grow * p.D + d4);
+            else {
+              const long long lab_r = __shfl_sync(0xffffffffu, lab, rr < nrows ? rr : 0);
+              pk[u] = *reinterpret_cast<const uint2*>(p.Kmat + (size_t)lab_r * p.D + d4);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int rr = r0 + u;
+            const int r2 = q4 * 32 + (rr < nrows ? rr : 0);
+            const int ch = d4 >> 6, col = d4 & 63;
+            const uint8_t* qa = q_smem + (b * DC + ch) * (128 * 128) + (r2 >> 3) * 1024 + (r2 & 7) * 128 +
+                                ((((col >> 3) ^ (r2 & 7)) & 7) << 4) + (col & 7) * 2;
+            const uint2 qu = *reinterpret_cast<const uint2*>(qa);
+            const float2 q0 = unpack_bf16x2(qu.x), q1 = unpack_bf16x2(qu.y);
+            float part;
+            if (p.P) part = q0.x * pa[u].x + q0.y * pa[u].y + q1.x * pa[u].z + q1.y * pa[u].w;
+            else {
+              const float2 k0 = unpack_bf16x2(pk[u].x), k1 = unpack_bf16x2(pk[u].y);
+              part = q0.x * k0.x + q0.y * k0.y + q1.x * k1.x + q1.y * k1.y;
+            }
+            part = warp_sum(part);
+            if (lane == rr && rr < nrows) s_mine += part;
           }
         }
-        part = warp_sum(part);
-        if (lane == rr) s_mine = part;
       }
       tgt2 = s_mine * c2;
     }

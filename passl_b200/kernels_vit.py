@@ -54,3 +54,56 @@ def attention_bwd(qkv, dout, out, lse, B, N, H, d, scale=None, causal=False):
     _lib.check(lib.passl_b200_attention_bwd(_ptr(qkv), _ptr(dout.contiguous()), _ptr(out), _ptr(lse), _ptr(dqkv), B, N, H, d, scale,
                                             int(causal), _stream()), "attention_bwd")
     return dqkv
+
+
+# ------------------------------------------------------------------------------------------------------------
+# MAE: masking, token assembly, masked-patch MSE
+# ------------------------------------------------------------------------------------------------------------
+def mae_random_masking(noise, len_keep):
+    """noise fp32 [B, L] -> (ids_shuffle int64 [B,L], ids_restore int64 [B,L], mask fp32 [B,L])  (mae.py:184-212)."""
+    _need_cuda(noise)
+    lib = _lib.load()
+    B, L = noise.shape
+    assert noise.dtype == torch.float32 and noise.is_contiguous()
+    ids_shuffle = torch.empty((B, L), dtype=torch.int64, device=noise.device)
+    ids_restore = torch.empty((B, L), dtype=torch.int64, device=noise.device)
+    mask = torch.empty((B, L), dtype=torch.float32, device=noise.device)
+    _lib.check(lib.passl_b200_mae_random_masking(_ptr(noise), _ptr(ids_shuffle), _ptr(ids_restore), _ptr(mask), B, L, int(len_keep),
+                                                 _stream()), "mae_random_masking")
+    return ids_shuffle, ids_restore, mask
+
+
+TOKEN_MODE = {"vit": 0, "mae_enc": 1, "mae_dec": 2}
+
+
+def token_assemble_fwd(src, pos, tok, B, Ls, Lo, D, mode, ids=None, keep=0):
+    lib = _lib.load()
+    out = torch.empty((B * Lo, D), dtype=torch.bfloat16, device=src.device)
+    _lib.check(lib.passl_b200_token_assemble_fwd(_ptr(src), _ptr(ids), _ptr(pos), _ptr(tok), _ptr(out), B, Ls, Lo, D,
+                                                 TOKEN_MODE[mode], int(keep), _stream()), "token_assemble_fwd")
+    return out
+
+
+def token_assemble_bwd(dout, B, Ls, Lo, D, mode, ids=None, keep=0, acc_tok=None, acc_pos=None, ids_tok=None, need_dsrc=True):
+    lib = _lib.load()
+    dsrc = torch.empty((B * Ls, D), dtype=torch.bfloat16, device=dout.device) if need_dsrc else None
+    _lib.check(lib.passl_b200_token_assemble_bwd(_ptr(dout), _ptr(ids), _ptr(dsrc), _ptr(acc_tok), _ptr(acc_pos), _ptr(ids_tok), B, Ls,
+                                                 Lo, D, TOKEN_MODE[mode], int(keep), _stream()), "token_assemble_bwd")
+    return dsrc
+
+
+def mae_loss_fwd(pred, imgs, mask, B, Hp, P, pred_tokens, pred_off, norm_pix, mask_sum):
+    lib = _lib.load()
+    loss = torch.empty(1, dtype=torch.float32, device=pred.device)
+    ws = torch.empty(lib.passl_b200_mae_loss_workspace_bytes(B, Hp * Hp), dtype=torch.uint8, device=pred.device)
+    _lib.check(lib.passl_b200_mae_loss_fwd(_ptr(pred), _ptr(imgs), _ptr(mask), _ptr(loss), B, Hp, P, pred_tokens, pred_off,
+                                           int(norm_pix), float(mask_sum), _ptr(ws), _stream()), "mae_loss_fwd")
+    return loss
+
+
+def mae_loss_bwd(pred, imgs, mask, dloss, B, Hp, P, pred_tokens, pred_off, norm_pix, mask_sum):
+    lib = _lib.load()
+    dpred = torch.empty_like(pred)
+    _lib.check(lib.passl_b200_mae_loss_bwd(_ptr(pred), _ptr(imgs), _ptr(mask), _ptr(dloss), _ptr(dpred), B, Hp, P, pred_tokens,
+                                           pred_off, int(norm_pix), float(mask_sum), _stream()), "mae_loss_bwd")
+    return dpred
