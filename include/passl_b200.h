@@ -141,7 +141,7 @@ int passl_b200_cast_bf16_to_f32(const void* x, float* y, long long n, void* stre
  *   bn_apply      : z = relu?(y*scale + shift + residual)  (bf16 and/or fp32 output)
  *   bn_bwd_reduce : partials of sum_g = sum_p g, sum_gx = sum_p g*xhat with g = dz * (z>0 if relu)
  *   bn_bwd_finalize: sums [2,C] = totals (= dbeta, dgamma), accumulated into the gradient buffers when given
- *   bn_bwd_apply  : dy = gamma*invstd*(g - sum_g/P - xhat*sum_gx/P); dres = g (gradient of the residual branch)
+ *   bn_bwd_apply  : dy = gamma*invstd*(g - sum_g/P - xhat*sum_gx/P) = k1*g + k2*y + k3; dres = g (residual-branch gradient)
  * ------------------------------------------------------------------------------------------------------------- */
 int passl_b200_bn_reduce_blocks(long long P, int C);
 int passl_b200_bn_stats(const void* y, float* part, long long P, int C, void* stream);
@@ -157,9 +157,11 @@ int passl_b200_bn_apply(const void* y, const void* residual, const float* scale,
                         long long P, int C, int relu, void* stream);
 int passl_b200_bn_bwd_reduce(const void* y, const void* dz, const void* z, const float* mean, const float* invstd,
                              float* part, long long P, int C, int relu, void* stream);
-int passl_b200_bn_bwd_finalize(const float* part, int nblk, float* sums, float* dgamma, float* dbeta, int C, void* stream);
-int passl_b200_bn_bwd_apply(const void* y, const void* dz, const void* z, const float* mean, const float* invstd,
-                            const float* gamma, const float* sum_g, const float* sum_gx, void* dy, void* dres, long long P,
+/* gamma / mean / invstd / count / coef may be NULL/0 (LayerNorm and bias-gradient uses); with them, coef [3, C] receives the
+ * per-channel coefficients of  dy = k1*g + k2*y + k3  consumed by bn_bwd_apply. */
+int passl_b200_bn_bwd_finalize(const float* part, int nblk, float* sums, float* dgamma, float* dbeta, const float* gamma,
+                               const float* mean, const float* invstd, long long count, float* coef, int C, void* stream);
+int passl_b200_bn_bwd_apply(const void* y, const void* dz, const void* z, const float* coef, void* dy, void* dres, long long P,
                             int C, int relu, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------

@@ -124,10 +124,20 @@ __global__ void bn_finalize_kernel(const float* __restrict__ part, int nblk,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float* mean,
                                    float* invstd, float* scale, float* shift, float* running_mean, float* running_var,
                                    float inv_count, float eps, float momentum, int C) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  // block (32, 32): x = channel (coalesced partial reads), y = group of partials; smem tree over y
+  __shared__ float r0[32][33], r1[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
   float sm = 0.f, sq = 0.f;
-  for (int b = 0; b < nblk; ++b) { sm += part[(size_t)b * 2 * C + c]; sq += part[(size_t)b * 2 * C + C + c]; }
+  if (c < C)
+    for (int b = threadIdx.y; b < nblk; b += 32) { sm += part[(size_t)b * 2 * C + c]; sq += part[(size_t)b * 2 * C + C + c]; }
+  r0[threadIdx.y][threadIdx.x] = sm; r1[threadIdx.y][threadIdx.x] = sq;
+  __syncthreads();
+  for (int h = 16; h > 0; h >>= 1) {
+    if ((int)threadIdx.y < h) { r0[threadIdx.y][threadIdx.x] += r0[threadIdx.y + h][threadIdx.x]; r1[threadIdx.y][threadIdx.x] += r1[threadIdx.y + h][threadIdx.x]; }
+    __syncthreads();
+  }
+  if (threadIdx.y != 0 || c >= C) return;
+  sm = r0[0][threadIdx.x]; sq = r1[0][threadIdx.x];
   float m = sm * inv_count;
   float v = fmaxf(sq * inv_count - m * m, 0.f);
   float is = rsqrtf(v + eps);
@@ -170,13 +180,12 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const __nv_
   }
 }
 
-// dy = scale * (g - sum_g/P - xhat * sum_gx/P),  g = dz * relu_mask;   d_res = g (optional)
+// dy = k1*g + k2*y + k3 with g = dz * relu_mask (coef from bn_bwd_finalize_kernel);   d_res = g (optional)
 __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dz,
-                                    const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean,
-                                    const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                    const float* __restrict__ sum_g, const float* __restrict__ sum_gx,
+                                    const __nv_bfloat16* __restrict__ z, const float* __restrict__ coef,
                                     __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dres, long long total8,
-                                    int C8, float inv_count, int relu) {
+                                    int C8, int relu) {
+  const int C = C8 * 8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
     const int c0 = (int)(i % C8) * 8;
     float a[8], g[8];
@@ -189,15 +198,14 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, const _
       for (int j = 0; j < 8; ++j) g[j] = zz[j] > 0.f ? g[j] : 0.f;
     }
     if (dres) *reinterpret_cast<uint4*>(dres + i * 8) = pack8(g);
+    const float4 k1a = *reinterpret_cast<const float4*>(coef + c0), k1b = *reinterpret_cast<const float4*>(coef + c0 + 4);
+    const float4 k2a = *reinterpret_cast<const float4*>(coef + C + c0), k2b = *reinterpret_cast<const float4*>(coef + C + c0 + 4);
+    const float4 k3a = *reinterpret_cast<const float4*>(coef + 2 * C + c0), k3b = *reinterpret_cast<const float4*>(coef + 2 * C + c0 + 4);
     float o[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = c0 + j;
-      const float is = invstd[c];
-      const float xhat = (a[j] - mean[c]) * is;
-      const float ga = gamma ? gamma[c] : 1.f;
-      o[j] = ga * is * (g[j] - sum_g[c] * inv_count - xhat * sum_gx[c] * inv_count);
-    }
+    o[0] = fmaf(k1a.x, g[0], fmaf(k2a.x, a[0], k3a.x)); o[1] = fmaf(k1a.y, g[1], fmaf(k2a.y, a[1], k3a.y));
+    o[2] = fmaf(k1a.z, g[2], fmaf(k2a.z, a[2], k3a.z)); o[3] = fmaf(k1a.w, g[3], fmaf(k2a.w, a[3], k3a.w));
+    o[4] = fmaf(k1b.x, g[4], fmaf(k2b.x, a[4], k3b.x)); o[5] = fmaf(k1b.y, g[5], fmaf(k2b.y, a[5], k3b.y));
+    o[6] = fmaf(k1b.z, g[6], fmaf(k2b.z, a[6], k3b.z)); o[7] = fmaf(k1b.w, g[7], fmaf(k2b.w, a[7], k3b.w));
     *reinterpret_cast<uint4*>(dy + i * 8) = pack8(o);
   }
 }
@@ -218,16 +226,37 @@ __global__ void axpy_f32_kernel(float* __restrict__ y, const float* __restrict__
     y[i] = fmaf(a, x[i], y[i]);
 }
 
-// sums[0|1][c] = sum_b part[b][0|1][c];  optionally dbeta += sums[0], dgamma += sums[1]
+// sums[0|1][c] = sum_b part[b][0|1][c];  optionally dbeta += sums[0], dgamma += sums[1];  optionally the per-channel
+// coefficients of the BN input gradient  dy = k1*g + k2*y + k3  (k1 = gamma*invstd, k2 = -gamma*invstd^2*mean(g*xhat),
+// k3 = -k1*mean(g) - k2*mean):  coef [3, C].  Block (32, 32) like bn_finalize_kernel.
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int nblk, float* __restrict__ sums,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta, int C) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta, const float* __restrict__ gamma,
+                                       const float* __restrict__ mean, const float* __restrict__ invstd, float inv_count,
+                                       float* __restrict__ coef, int C) {
+  __shared__ float r0[32][33], r1[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
   float a = 0.f, b = 0.f;
-  for (int k = 0; k < nblk; ++k) { a += part[(size_t)k * 2 * C + c]; b += part[(size_t)k * 2 * C + C + c]; }
-  sums[c] = a; sums[C + c] = b;
+  if (c < C)
+    for (int k = threadIdx.y; k < nblk; k += 32) { a += part[(size_t)k * 2 * C + c]; b += part[(size_t)k * 2 * C + C + c]; }
+  r0[threadIdx.y][threadIdx.x] = a; r1[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  for (int h = 16; h > 0; h >>= 1) {
+    if ((int)threadIdx.y < h) { r0[threadIdx.y][threadIdx.x] += r0[threadIdx.y + h][threadIdx.x]; r1[threadIdx.y][threadIdx.x] += r1[threadIdx.y + h][threadIdx.x]; }
+    __syncthreads();
+  }
+  if (threadIdx.y != 0 || c >= C) return;
+  a = r0[0][threadIdx.x]; b = r1[0][threadIdx.x];
+  if (sums) { sums[c] = a; sums[C + c] = b; }
   if (dbeta) dbeta[c] += a;
   if (dgamma) dgamma[c] += b;
+  if (coef) {
+    const float is = invstd[c], ga = gamma ? gamma[c] : 1.f;
+    const float k1 = ga * is;
+    const float k2 = -ga * is * is * (b * inv_count);
+    coef[c] = k1;
+    coef[C + c] = k2;
+    coef[2 * C + c] = -k1 * (a * inv_count) - k2 * mean[c];
+  }
 }
 
 static void reduce_cfg(long long P, int C, dim3& grid, dim3& block, int& rows_per_block, int& smem) {
@@ -281,7 +310,7 @@ extern "C" int passl_b200_bn_finalize(const float* part, int nblk, const float* 
                                       float* mean, float* invstd, float* scale, float* shift, float* running_mean,
                                       float* running_var, long long count, float eps, float momentum, int C, void* stream) {
   if (C <= 0 || count <= 0 || nblk <= 0) return PB_ERR_BAD_ARG;
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(part, nblk, gamma, beta, mean, invstd, scale, shift,
+  bn_finalize_kernel<<<(C + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(part, nblk, gamma, beta, mean, invstd, scale, shift,
                                                                         running_mean, running_var, 1.f / (float)count, eps,
                                                                         momentum, C);
   PB_LAUNCH_CHECK();
@@ -334,24 +363,26 @@ extern "C" int passl_b200_bn_bwd_reduce(const void* y, const void* dz, const voi
 }
 
 // sums [2, C] = totals of the partials; dbeta += sums[0], dgamma += sums[1] when given (fp32 gradient accumulators)
-extern "C" int passl_b200_bn_bwd_finalize(const float* part, int nblk, float* sums, float* dgamma, float* dbeta, int C,
-                                          void* stream) {
+extern "C" int passl_b200_bn_bwd_finalize(const float* part, int nblk, float* sums, float* dgamma, float* dbeta,
+                                          const float* gamma, const float* mean, const float* invstd, long long count,
+                                          float* coef, int C, void* stream) {
   if (C <= 0 || nblk <= 0) return PB_ERR_BAD_ARG;
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(part, nblk, sums, dgamma, dbeta, C);
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(part, nblk, sums, dgamma, dbeta, gamma, mean,
+                                                                                    invstd, count > 0 ? 1.f / (float)count : 0.f,
+                                                                                    coef, C);
   PB_LAUNCH_CHECK();
   return PB_OK;
 }
 
-extern "C" int passl_b200_bn_bwd_apply(const void* y, const void* dz, const void* z, const float* mean, const float* invstd,
-                                       const float* gamma, const float* sum_g, const float* sum_gx, void* dy, void* dres,
+extern "C" int passl_b200_bn_bwd_apply(const void* y, const void* dz, const void* z, const float* coef, void* dy, void* dres,
                                        long long P, int C, int relu, void* stream) {
-  if (P <= 0 || C <= 0 || C % 8) return PB_ERR_BAD_ARG;
+  if (P <= 0 || C <= 0 || C % 8 || !coef) return PB_ERR_BAD_ARG;
   if (relu && !z) return PB_ERR_BAD_ARG;
   long long total8 = P * (C / 8);
   bn_bwd_apply_kernel<<<ew_blocks(total8), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<const __nv_bfloat16*>(dz),
-      reinterpret_cast<const __nv_bfloat16*>(z), mean, invstd, gamma, sum_g, sum_gx, reinterpret_cast<__nv_bfloat16*>(dy),
-      reinterpret_cast<__nv_bfloat16*>(dres), total8, C / 8, 1.f / (float)P, relu);
+      reinterpret_cast<const __nv_bfloat16*>(z), coef, reinterpret_cast<__nv_bfloat16*>(dy),
+      reinterpret_cast<__nv_bfloat16*>(dres), total8, C / 8, relu);
   PB_LAUNCH_CHECK();
   return PB_OK;
 }

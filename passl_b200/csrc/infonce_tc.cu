@@ -186,27 +186,32 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
       const int nrows = rows_left < 32 ? (rows_left > 0 ? rows_left : 0) : 32;
       for (int r0 = 0; r0 < nrows; r0 += 8) {
         // 8 rows per batch: issue all global loads first (independent), then the dot products and warp reductions
-        for (int d4 = lane * 4; d4 < p.D; d4 += 128) {
+        for (int dbase = 0; dbase < p.D; dbase += 128) {        // warp-uniform trip count: every lane reaches the shuffles
+          const int d4 = dbase + lane * 4;
+          const bool act = d4 < p.D;
           float4 pa[8];
           uint2 pk[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const int rr = r0 + u;
             const int grow = row_base + b * 128 + q4 * 32 + (rr < nrows ? rr : 0);
-            if (p.P) pa[u] = *reinterpret_cast<const float4*>(p.P + (size_t)grow * p.D + d4);
+            pa[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            pk[u] = make_uint2(0u, 0u);
+            if (p.P) { if (act) pa[u] = *reinterpret_cast<const float4*>(p.P + (size_t)grow * p.D + d4); }
             else {
               const long long lab_r = __shfl_sync(0xffffffffu, lab, rr < nrows ? rr : 0);
-              pk[u] = *reinterpret_cast<const uint2*>(p.Kmat + (size_t)lab_r * p.D + d4);
+              if (act) pk[u] = *reinterpret_cast<const uint2*>(p.Kmat + (size_t)lab_r * p.D + d4);
             }
           }
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const int rr = r0 + u;
             const int r2 = q4 * 32 + (rr < nrows ? rr : 0);
-            const int ch = d4 >> 6, col = d4 & 63;
+            const int dd = act ? d4 : 0;
+            const int ch = dd >> 6, col = dd & 63;
             const uint8_t* qa = q_smem + (b * DC + ch) * (128 * 128) + (r2 >> 3) * 1024 + (r2 & 7) * 128 +
                                 ((((col >> 3) ^ (r2 & 7)) & 7) << 4) + (col & 7) * 2;
-            const uint2 qu = *reinterpret_cast<const uint2*>(qa);
+            const uint2 qu = act ? *reinterpret_cast<const uint2*>(qa) : make_uint2(0u, 0u);
             const float2 q0 = unpack_bf16x2(qu.x), q1 = unpack_bf16x2(qu.y);
             float part;
             if (p.P) part = q0.x * pa[u].x + q0.y * pa[u].y + q1.x * pa[u].z + q1.y * pa[u].w;

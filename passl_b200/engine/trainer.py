@@ -1,0 +1,104 @@
+"""Trainer surface of the v1.1.0 tree (passl_v110/engine/trainer.py:72-337 + hooks/optimizer_hook.py:20-48 +
+hooks/log_hook.py): `Trainer(cfg).train()` iterates `outputs = model(*data)`, `outputs['loss'].backward()`, gradient sync,
+optimizer step, LR schedule and the `ips: ... images/sec` log line the reference's CI greps (passl/engine/loops/loop.py:102-118).
+
+Only what the hot path needs is here: synthetic or user-supplied iterables of (view_q, view_k) batches, the name-based model
+registry, the fused optimizers and the data-parallel gradient exchange.  Checkpoint / evaluation hooks are out of scope for
+round 1."""
+import time
+
+import torch
+
+from ..core.param_store import ParamStore
+from ..distributed import get_rank, get_world_size, grad_sync, param_sync
+from ..modeling import build_model
+from ..optimizer import CosineAnnealingDecay, build_optimizer
+
+
+class IterLoader:
+    """passl_v110/engine/trainer.py:48-69"""
+
+    def __init__(self, dataloader, epoch=0):
+        self._dataloader = dataloader
+        self.iter_loader = iter(self._dataloader)
+        self._epoch = epoch
+
+    @property
+    def epoch(self):
+        return self._epoch
+
+    def __next__(self):
+        try:
+            data = next(self.iter_loader)
+        except StopIteration:
+            self._epoch += 1
+            self.iter_loader = iter(self._dataloader)
+            data = next(self.iter_loader)
+        return data
+
+    def __len__(self):
+        return len(self._dataloader)
+
+
+class SyntheticTwoViews:
+    """Synthetic 3x224x224 two-view batches resident on the device (the metric's data source)."""
+
+    def __init__(self, batch_size, iters, device, size=224, seed=1234):
+        self.batch_size, self.iters, self.device, self.size = batch_size, iters, device, size
+        g = torch.Generator(device=device).manual_seed(seed + get_rank())
+        self.a = torch.randn(batch_size, 3, size, size, device=device, generator=g)
+        self.b = torch.randn(batch_size, 3, size, size, device=device, generator=g)
+
+    def __len__(self):
+        return self.iters
+
+    def __iter__(self):
+        for _ in range(self.iters):
+            yield self.a, self.b
+
+
+class Trainer:
+    def __init__(self, cfg, dataloader=None, device=None):
+        self.cfg = cfg
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.model = build_model(dict(cfg.model)).to(self.device)
+        enc = getattr(self.model, "encoder_q", None) or getattr(self.model, "encoder", None) or self.model
+        if hasattr(self.model, "build_param_stores"):
+            self.store, _ = self.model.build_param_stores()
+        else:
+            self.store = ParamStore(enc)
+        param_sync(self.store)
+        opt_cfg = dict(cfg.optimizer)
+        lr_cfg = dict(cfg.get("lr_scheduler", {}) or {})
+        self.lr_scheduler = None
+        if lr_cfg.get("name") == "CosineAnnealingDecay":
+            self.lr_scheduler = CosineAnnealingDecay(lr_cfg["learning_rate"], lr_cfg["T_max"])
+            opt_cfg.setdefault("lr", lr_cfg["learning_rate"])
+        self.optimizer = build_optimizer(opt_cfg, self.store)
+        self.batch_size = cfg.dataloader.train.sampler.batch_size
+        self.dataloader = dataloader or SyntheticTwoViews(self.batch_size, cfg.get("total_iters", 10), self.device)
+        self.log_interval = (cfg.get("log_config", {}) or {}).get("interval", 10)
+        self.current_iter = 0
+        self.outputs = None
+
+    def train(self):
+        loader = IterLoader(self.dataloader)
+        total = len(self.dataloader)
+        t0, seen = time.time(), 0
+        while self.current_iter < total:
+            data = next(loader)
+            self.optimizer.clear_grad()
+            self.outputs = self.model(*data, total_iters=total, current_iter=self.current_iter)
+            self.outputs['loss'].backward()                       # OptimizerHook.train_iter_end (optimizer_hook.py:25-48)
+            grad_sync(self.store)
+            self.optimizer.step()
+            self.current_iter += 1
+            seen += self.batch_size * get_world_size()
+            if self.current_iter % self.log_interval == 0 and get_rank() == 0:
+                torch.cuda.synchronize()
+                dt = time.time() - t0
+                msg = "[Train][Iter: {}/{}] lr: {:.5f}, loss: {:.5f}, batch_cost: {:.5f}s, ips: {:.5f} images/sec".format(
+                    self.current_iter, total, self.optimizer.get_lr(), float(self.outputs['loss']), dt / self.log_interval, seen / dt)
+                print(msg, flush=True)
+                t0, seen = time.time(), 0
+        return self.outputs

@@ -280,8 +280,8 @@ def colsum_accumulate(x2d, acc):
     P, C = x2d.shape
     part = bn_stats(x2d)
     sums = torch.empty((2, C), dtype=torch.float32, device=x2d.device)
-    _lib.check(lib.passl_b200_bn_bwd_finalize(_ptr(part), part.shape[0], _ptr(sums), None, _ptr(acc), C, _stream()),
-               "bn_bwd_finalize")
+    _lib.check(lib.passl_b200_bn_bwd_finalize(_ptr(part), part.shape[0], _ptr(sums), None, _ptr(acc), None, None, None, 0, None, C,
+                                              _stream()), "bn_bwd_finalize")
 
 
 def bn_apply(y, msss, relu, residual=None, out=None, out_f32=None):
@@ -306,12 +306,13 @@ def bn_bwd(y, dz, z, msss, gamma, relu, want_dres=False, dgamma=None, dbeta=None
     _lib.check(lib.passl_b200_bn_bwd_reduce(_ptr(y), _ptr(dz), _ptr(z), _ptr(msss[0]), _ptr(msss[1]), _ptr(part), P, C,
                                             int(relu), _stream()), "bn_bwd_reduce")
     sums = torch.empty((2, C), dtype=torch.float32, device=y.device)
-    _lib.check(lib.passl_b200_bn_bwd_finalize(_ptr(part), nblk, _ptr(sums), _ptr(dgamma), _ptr(dbeta), C, _stream()),
-               "bn_bwd_finalize")
+    coef = torch.empty((3, C), dtype=torch.float32, device=y.device)
+    _lib.check(lib.passl_b200_bn_bwd_finalize(_ptr(part), nblk, _ptr(sums), _ptr(dgamma), _ptr(dbeta), _ptr(gamma), _ptr(msss[0]),
+                                              _ptr(msss[1]), P, _ptr(coef), C, _stream()), "bn_bwd_finalize")
     dy = torch.empty_like(y)
     dres = torch.empty_like(y) if want_dres else None
-    _lib.check(lib.passl_b200_bn_bwd_apply(_ptr(y), _ptr(dz), _ptr(z), _ptr(msss[0]), _ptr(msss[1]), _ptr(gamma), _ptr(sums[0]),
-                                           _ptr(sums[1]), _ptr(dy), _ptr(dres), P, C, int(relu), _stream()), "bn_bwd_apply")
+    _lib.check(lib.passl_b200_bn_bwd_apply(_ptr(y), _ptr(dz), _ptr(z), _ptr(coef), _ptr(dy), _ptr(dres), P, C, int(relu), _stream()),
+               "bn_bwd_apply")
     return dy, dres, sums
 
 

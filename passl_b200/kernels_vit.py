@@ -29,8 +29,8 @@ def layernorm_bwd(x, dy, gamma, mean, rstd, dgamma=None, dbeta=None, dres=None):
     _lib.check(lib.passl_b200_layernorm_bwd(_ptr(x), _ptr(dy.contiguous()), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dres), _ptr(dx),
                                             _ptr(part), T, D, _stream()), "layernorm_bwd")
     sums = torch.empty((2, D), dtype=torch.float32, device=x.device)
-    _lib.check(lib.passl_b200_bn_bwd_finalize(_ptr(part), nblk, _ptr(sums), _ptr(dgamma), _ptr(dbeta), D, _stream()),
-               "ln_bwd_finalize")
+    _lib.check(lib.passl_b200_bn_bwd_finalize(_ptr(part), nblk, _ptr(sums), _ptr(dgamma), _ptr(dbeta), None, None, None, 0, None, D,
+                                              _stream()), "ln_bwd_finalize")
     return dx, sums
 
 

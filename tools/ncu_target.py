@@ -34,3 +34,17 @@ elif what == "infonce":
     for i in range(4):
         out, lse, tgt, _ = K.infonce_tc_fwd(qb, queue, pos=k, scale=1 / T)
     torch.cuda.synchronize()
+if what == "conv":
+    B = 128
+    x = torch.randn(B, 56, 56, 64, device="cuda").bfloat16()
+    w = torch.randn(64, 3, 3, 64, device="cuda").bfloat16()
+    y = K.conv2d_fwd(x, w, stride=1, pad=1)
+    dy = torch.randn_like(y)
+    dw = torch.zeros(64, 3, 3, 64, device="cuda")
+    x2 = torch.randn(B, 14, 14, 1024, device="cuda").bfloat16()
+    w2 = torch.randn(256, 1, 1, 1024, device="cuda").bfloat16()
+    for i in range(2):
+        K.conv2d_fwd(x, w, stride=1, pad=1, out=y)
+        K.conv2d_wgrad(x, dy, (64, 3, 3, 64), stride=1, pad=1, out=dw, accumulate=True)
+        K.conv2d_fwd(x2, w2)
+    torch.cuda.synchronize()
