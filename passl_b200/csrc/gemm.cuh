@@ -190,16 +190,40 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
           b_tap = n_blk / p.n_blocks_per_tap;
           b_row0 = (n_blk - b_tap * p.n_blocks_per_tap) * BN;
         }
-        for (int kit = k_begin; kit < k_end; ++kit) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * S::STAGE_BYTES;
-          uint8_t* sb = sa + S::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(p.a.tx_bytes + p.b.tx_bytes));
-          issue_operand_load<128, BK>(p.a, p.geom, sa, &full_bar[stage], m_blk * 128, m_blk, 0, kit);
-          issue_operand_load<BN, BK>(p.b, p.geom, sb, &full_bar[stage], b_row0, n_blk, b_tap, kit);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
+        const uint32_t tx = (uint32_t)(p.a.tx_bytes + p.b.tx_bytes);
+        if (p.a.mode == OP_PATCH_K && p.b.mode == OP_MAT_K) {
+          // implicit-GEMM convolution fast path: patch decoded once per tile, (tap, chunk) advanced with counters —
+          // this single thread's instruction latency is on the critical path of every pipeline stage
+          int n0, h0, w0;
+          decode_patch(p.geom, m_blk, n0, h0, w0);
+          int tap = k_begin / p.a.cchunks, cc = k_begin - tap * p.a.cchunks;
+          for (int kit = k_begin; kit < k_end; ++kit) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * S::STAGE_BYTES;
+            mbar_arrive_expect_tx(&full_bar[stage], tx);
+            tma_load_4d(sa, &p.a.maps[p.a.map[tap]], &full_bar[stage], cc * 64, w0 + p.a.dw[tap], h0 + p.a.dh[tap], n0);
+            tma_load_2d(sa + S::A_BYTES, &p.b.maps[0], &full_bar[stage], kit * BK, b_row0);
+            if (++cc == p.a.cchunks) { cc = 0; ++tap; }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        } else if (p.a.mode == OP_MAT_K && p.b.mode == OP_MAT_K) {
+          for (int kit = k_begin; kit < k_end; ++kit) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * S::STAGE_BYTES;
+            mbar_arrive_expect_tx(&full_bar[stage], tx);
+            tma_load_2d(sa, &p.a.maps[0], &full_bar[stage], kit * BK, m_blk * 128);
+            tma_load_2d(sa + S::A_BYTES, &p.b.maps[0], &full_bar[stage], kit * BK, b_row0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        } else {
+          for (int kit = k_begin; kit < k_end; ++kit) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * S::STAGE_BYTES;
+            uint8_t* sb = sa + S::A_BYTES;
+            mbar_arrive_expect_tx(&full_bar[stage], tx);
+            issue_operand_load<128, BK>(p.a, p.geom, sa, &full_bar[stage], m_blk * 128, m_blk, 0, kit);
+            issue_operand_load<BN, BK>(p.b, p.geom, sb, &full_bar[stage], b_row0, n_blk, b_tap, kit);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -208,6 +232,14 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
     if (lane == 0) {
       // ================= MMA issuer =================
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, A_MN, B_MN);
+      // descriptor of stage 0 / k-step 0; later stages and k-steps only add to the 14-bit start-address field
+      const uint32_t smem0 = smem_u32(smem);
+      const uint64_t da0 = A_MN ? make_smem_desc_sw128(smem0, BK * 128, 1024) : make_smem_desc_sw128(smem0, 16, 1024);
+      const uint64_t db0 = B_MN ? make_smem_desc_sw128(smem0 + S::A_BYTES, BK * 128, 1024)
+                                : make_smem_desc_sw128(smem0 + S::A_BYTES, 16, 1024);
+      constexpr uint64_t kStepA = (A_MN ? 2048 : 32) >> 4, kStepB = (B_MN ? 2048 : 32) >> 4;
+      constexpr uint64_t kStage = S::STAGE_BYTES >> 4;
+      constexpr int KSTEPS_FULL = BK / 16;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -223,16 +255,16 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
         for (int kit = k_begin; kit < k_end; ++kit) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
-          const uint32_t sb = sa + S::A_BYTES;
-          for (int k = 0; k < p.k_steps; ++k) {
-            // K-major: +32 B per 16-element K step inside the 128 B swizzle row.
-            // MN-major: +2048 B per 16 k-rows (two 8-row atoms); LBO = chunk stride (BK rows x 128 B).
-            uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * 2048, BK * 128, 1024)
-                               : make_smem_desc_sw128(sa + k * 32, 16, 1024);
-            uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * 2048, BK * 128, 1024)
-                               : make_smem_desc_sw128(sb + k * 32, 16, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (kit > k_begin || k > 0) ? 1u : 0u);
+          // K-major: +32 B per 16-element K step inside the 128 B swizzle row.
+          // MN-major: +2048 B per 16 k-rows (two 8-row atoms); LBO = chunk stride (BK rows x 128 B).
+          const uint64_t da = da0 + (uint64_t)stage * kStage, db = db0 + (uint64_t)stage * kStage;
+          if (p.k_steps == KSTEPS_FULL) {
+#pragma unroll
+            for (int k = 0; k < KSTEPS_FULL; ++k)
+              umma_bf16(d_tmem, da + k * kStepA, db + k * kStepB, idesc, (kit > k_begin || k > 0) ? 1u : 0u);
+          } else {
+            for (int k = 0; k < p.k_steps; ++k)
+              umma_bf16(d_tmem, da + k * kStepA, db + k * kStepB, idesc, (kit > k_begin || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
           if (++stage == STAGES) {

@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
       constexpr uint32_t idesc = make_idesc_bf16(128, NCE_BK, false, false);
+      const uint64_t db0 = make_smem_desc_sw128(smem_u32(k_smem), 16, 1024);   // stage 0, chunk 0, k-step 0
       mbar_wait(q_ready, 0);
       tc_fence_after();
       int stage = 0;
@@ -128,15 +129,15 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
         mbar_wait(&s_empty[buf], bphase ^ 1);
         mbar_wait(&k_full[stage], phase);
         tc_fence_after();
-        const uint32_t kb = smem_u32(k_smem + stage * stage_bytes);
+        const uint64_t dbs = db0 + (uint64_t)((stage * stage_bytes) >> 4);
         for (int b = 0; b < MB; ++b) {
           const uint32_t d_tmem = tm_s + (buf * MB + b) * NCE_BK;
+          const uint32_t a_tmem = tm_q + b * q_cols;
           for (int c = 0; c < DC; ++c) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              uint64_t db = make_smem_desc_sw128(kb + c * (NCE_BK * 128) + k * 32, 16, 1024);
-              umma_bf16_ts(d_tmem, tm_q + b * q_cols + c * 32 + k * 8, db, idesc, (c > 0 || k > 0) ? 1u : 0u);
-            }
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ts(d_tmem, a_tmem + c * 32 + k * 8, dbs + (uint64_t)((c * (NCE_BK * 128) + k * 32) >> 4), idesc,
+                           (c > 0 || k > 0) ? 1u : 0u);
           }
         }
         umma_commit(&k_empty[stage]);
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
     // Prologue (coalesced): Q block arrives by TMA in shared memory; each thread copies its own row smem -> registers ->
     // TMEM (A operand of every MMA); target logits (positive pair or labelled column) are computed warp-cooperatively:
     // for each of the warp's 32 rows the lanes split D, so global reads are whole 512 B / 256 B rows.
-    float tgt2 = 0.f;
+    float tgt2 = 0.f, tgt_raw = 0.f;
     long long lab = -1;
     int ex = -1;
     {
@@ -225,6 +226,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
         }
       }
       tgt2 = s_mine * c2;
+      tgt_raw = s_mine;
     }
 
     float m = -INFINITY, l = 0.f;
@@ -248,16 +250,39 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
       const int key0 = t * NCE_BK;
       const bool special = (key0 + NCE_BK > p.K) || (ex >= key0 && ex < key0 + NCE_BK) ||
                            (lab >= key0 && lab < key0 + NCE_BK);
-      float y[64];
-      float mx = -INFINITY;
       if (!special) {
+        // fast path (instruction diet): work on the raw dot products — max is monotone in the positive scale, the scaling
+        // and the max subtraction fold into one FFMA in front of ex2, the rank counter uses set.gt + FADD on 4 chains.
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+        float c0 = 0.f, c1 = 0.f, c2n = 0.f, c3 = 0.f;
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
-          y[j] = __uint_as_float(v[j]) * c2;
-          mx = fmaxf(mx, y[j]);
-          cnt += (y[j] > tgt2) ? 1 : 0;
+        for (int j = 0; j < 64; j += 4) {
+          const float a0 = __uint_as_float(v[j]), a1 = __uint_as_float(v[j + 1]), a2 = __uint_as_float(v[j + 2]),
+                      a3 = __uint_as_float(v[j + 3]);
+          mx0 = fmaxf(mx0, a0); mx1 = fmaxf(mx1, a1); mx2 = fmaxf(mx2, a2); mx3 = fmaxf(mx3, a3);
+          float g0, g1, g2, g3;
+          asm("set.gt.f32.f32 %0, %1, %2;" : "=f"(g0) : "f"(a0), "f"(tgt_raw));
+          asm("set.gt.f32.f32 %0, %1, %2;" : "=f"(g1) : "f"(a1), "f"(tgt_raw));
+          asm("set.gt.f32.f32 %0, %1, %2;" : "=f"(g2) : "f"(a2), "f"(tgt_raw));
+          asm("set.gt.f32.f32 %0, %1, %2;" : "=f"(g3) : "f"(a3), "f"(tgt_raw));
+          c0 += g0; c1 += g1; c2n += g2; c3 += g3;
         }
+        cnt += (int)((c0 + c1) + (c2n + c3));
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c2;
+        const float mn = fmaxf(m, mx);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 64; j += 4) {
+          s0 += exp2f(fmaf(__uint_as_float(v[j]), c2, -mn));
+          s1 += exp2f(fmaf(__uint_as_float(v[j + 1]), c2, -mn));
+          s2 += exp2f(fmaf(__uint_as_float(v[j + 2]), c2, -mn));
+          s3 += exp2f(fmaf(__uint_as_float(v[j + 3]), c2, -mn));
+        }
+        l = l * exp2f(m - mn) + ((s0 + s1) + (s2 + s3));
+        m = mn;
       } else {
+        float y[64];
+        float mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < 64; ++j) {
           const int key = key0 + j;
@@ -266,14 +291,14 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
           mx = fmaxf(mx, y[j]);
           cnt += (ok && key != lab && y[j] > tgt2) ? 1 : 0;
         }
-      }
-      if (mx > -INFINITY) {
-        const float mn = fmaxf(m, mx);
-        float s = 0.f;
+        if (mx > -INFINITY) {
+          const float mn = fmaxf(m, mx);
+          float s = 0.f;
 #pragma unroll
-        for (int j = 0; j < 64; ++j) s += exp2f(y[j] - mn);
-        l = l * exp2f(m - mn) + s;
-        m = mn;
+          for (int j = 0; j < 64; ++j) s += exp2f(y[j] - mn);
+          l = l * exp2f(m - mn) + s;
+          m = mn;
+        }
       }
     }
     if (row_ok) {
