@@ -1,0 +1,187 @@
+"""MoCo v3 (passl/models/mocov3.py:37-297; cross-check tasks/ssl/mocov3/builder_moco.py:18-159) on the B200 kernels.
+
+  base_encoder   = ViT (fixed 2-D sin-cos position embedding, mocov3.py:58-91) + 3-layer projector MLP (Linear(no bias)-BN1D-ReLU x2,
+                   Linear-BN1D(no affine)), predictor = 2-layer MLP of the same kind (mocov3.py:136-169)
+  momentum_encoder = EMA copy of base_encoder (projector included), cosine momentum schedule (builder_moco.py:74-80)
+  loss           = ctr(q1, k2) + ctr(q2, k1),  ctr: normalize -> all_gather(k) (no grad) -> q.k^T/T -> labels arange(N)+N*rank
+                   -> CE * 2T   (mocov3.py:187-198)   — computed by the fused tcgen05 InfoNCE kernel (label mode).
+The reference wraps `nn.Sequential(base_encoder, predictor)` in its CosineEMA with momentum weighting the *source*
+(mocov3.py:133-134, averaged_model.py:165-186); set `reference_ema_quirk=True` to reproduce that formula.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from .. import kernels as K
+from ..core.param_store import ParamStore
+from ..distributed import concat_all_gather, get_rank
+from ..loss.contrastive import gathered_infonce, normalize
+from ..nn.layers import BatchNorm1D, Linear
+from .mae import get_2d_sincos_pos_embed
+from .vision_transformer import VisionTransformer
+
+
+class _MLPFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, x, anchor):
+        out, saved = module._run_forward(x, training=module.training, save=True)
+        ctx.module, ctx.saved = module, saved
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dx = ctx.module._run_backward(ctx.saved, dout.contiguous())
+        ctx.saved = None
+        return None, dx, None
+
+
+class MLPBN(nn.Module):
+    """_build_mlp (mocov3.py:136-158): Linear(bias=False) -> BN1D -> ReLU ... -> Linear(bias=False) -> BN1D(no affine).
+    bf16 [B, in] -> fp32 [B, out]."""
+
+    def __init__(self, num_layers, input_dim, mlp_dim, output_dim, last_bn=True):
+        super().__init__()
+        fcs, bns = [], []
+        for l in range(num_layers):
+            d1 = input_dim if l == 0 else mlp_dim
+            d2 = output_dim if l == num_layers - 1 else mlp_dim
+            fcs.append(Linear(d1, d2, bias=False))
+            if l < num_layers - 1:
+                bns.append(BatchNorm1D(d2, relu=True))
+            else:
+                bns.append(BatchNorm1D(d2, relu=False, affine=False) if last_bn else None)
+        self.fcs, self.bns = nn.ModuleList(fcs), nn.ModuleList([b for b in bns if b is not None])
+        self.last_bn = last_bn
+
+    def _run_forward(self, x, training=True, save=True):
+        if x.dtype != torch.bfloat16:
+            x = K.cast_bf16(x.contiguous())
+        ctxs, h, n = [], x, len(self.fcs)
+        for i, fc in enumerate(self.fcs):
+            y, cf = fc.fwd(h, save=save)
+            if i < len(self.bns):
+                h, cb = self.bns[i].fwd(y, training=training, save=save, out_f32=(i == n - 1))
+            else:
+                h, cb = K.cast_f32(y), None
+            ctxs.append((cf, cb))
+        return h, ctxs
+
+    def _run_backward(self, ctxs, dout):
+        d = K.cast_bf16(dout)
+        for i in reversed(range(len(self.fcs))):
+            cf, cb = ctxs[i]
+            if cb is not None:
+                d = self.bns[i].bwd(cb, d)
+            d = self.fcs[i].bwd(cf, d)
+        return d
+
+    def forward(self, x):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return _MLPFn.apply(self, x, self.fcs[0].weight)
+        out, _ = self._run_forward(x, training=self.training, save=False)
+        return out
+
+
+class MoCoV3ViT(VisionTransformer):
+    """ViT with the fixed 2-D sin-cos position embedding (mocov3.py:37-91)."""
+
+    def __init__(self, **kwargs):
+        kwargs.setdefault("learnable_pos", False)
+        super().__init__(**kwargs)
+        g = int(self.patch_embed.num_patches ** .5)
+        with torch.no_grad():
+            self.pos_embed.copy_(torch.from_numpy(get_2d_sincos_pos_embed(self.embed_dim, g, True)).float().unsqueeze(0))
+        self.pos_embed.requires_grad = False
+
+
+class _Encoder(nn.Module):
+    def __init__(self, vit, head):
+        super().__init__()
+        self.vit, self.head = vit, head
+
+    def forward(self, x):
+        return self.head(self.vit(x))
+
+
+class MoCoV3Pretrain(nn.Module):
+    def __init__(self, base_encoder, dim=256, mlp_dim=4096, T=1.0, base_momentum=0.99, max_steps=1000,
+                 reference_ema_quirk=False):
+        super().__init__()
+        self.T, self.base_momentum, self.max_steps, self.quirk = T, base_momentum, max_steps, reference_ema_quirk
+        vit_q, vit_k = base_encoder(), base_encoder()
+        hidden = vit_q.embed_dim
+        self.base_encoder = _Encoder(vit_q, MLPBN(3, hidden, mlp_dim, dim))
+        self.predictor = MLPBN(2, dim, mlp_dim, dim)
+        self.momentum_encoder = _Encoder(vit_k, MLPBN(3, hidden, mlp_dim, dim))
+        for pq, pk in zip(self.base_encoder.parameters(), self.momentum_encoder.parameters()):
+            pk.data.copy_(pq.data)
+            pk.requires_grad = False
+        self.steps = 0
+        self._stores = None
+
+    def build_param_stores(self):
+        """flat storage: (base_encoder + predictor) trainable, momentum encoder EMA target"""
+        self._trainable = nn.ModuleList([self.base_encoder, self.predictor])
+        st = ParamStore(self._trainable, with_grad=True)
+        sk = ParamStore(self.momentum_encoder, with_grad=False)
+        # EMA runs over the base_encoder prefix of the trainable buffer: both stores enumerate base_encoder params in the same order
+        self._ema_numel = sk.numel
+        self._stores = (st, sk)
+        return st, sk
+
+    @torch.no_grad()
+    def _update_momentum_encoder(self):
+        st, sk = self._stores
+        if self.quirk:      # averaged*(1-m') + source*m' with m' cosine from base to end 0 (averaged_model.py:165-186)
+            m_src = self.base_momentum * (math.cos(math.pi * self.steps / float(self.max_steps)) + 1) / 2
+            m = 1.0 - m_src
+        else:               # builder_moco.py:74-80 / main_moco.py adjust_moco_momentum
+            m = 1. - 0.5 * (1. + math.cos(math.pi * self.steps / float(self.max_steps))) * (1. - self.base_momentum)
+        K.ema_update(sk.master, st.master[:self._ema_numel], m, k_bf16=sk.bf16)
+        self.steps += 1
+
+    def contrastive_loss(self, q, k):
+        q = normalize(q)
+        with torch.no_grad():
+            k = concat_all_gather(normalize(k))
+        N = q.shape[0]
+        labels = torch.arange(N, dtype=torch.int64, device=q.device) + N * get_rank()
+        loss, _, _ = gathered_infonce(q, k, labels, 1.0 / self.T, loss_scale=2 * self.T)
+        return loss
+
+    def forward(self, inputs):
+        assert isinstance(inputs, list)
+        x1, x2 = inputs[0], inputs[1]
+        if self._stores is None:
+            self.build_param_stores()
+        q1 = self.predictor(self.base_encoder(x1))
+        q2 = self.predictor(self.base_encoder(x2))
+        with torch.no_grad():
+            self._update_momentum_encoder()
+            k1 = self.momentum_encoder(x1)
+            k2 = self.momentum_encoder(x2)
+        return _Add.apply(self.contrastive_loss(q1, k2), self.contrastive_loss(q2, k1))
+
+
+class _Add(torch.autograd.Function):
+    """loss_a + loss_b on device scalars through the axpy kernel (no torch math on the path)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        out = a.detach().clone().reshape(1)
+        K.axpy(out, b.detach().reshape(1).contiguous(), 1.0)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+def mocov3_vit_base_pretrain(**kwargs):
+    """mocov3.py:288-297"""
+    def enc():
+        return MoCoV3ViT(patch_size=16, embed_dim=768, depth=12, num_heads=12, mlp_ratio=4, qkv_bias=True, epsilon=1e-6)
+    kw = dict(dim=256, mlp_dim=4096, T=0.2)
+    kw.update(kwargs)
+    return MoCoV3Pretrain(enc, **kw)

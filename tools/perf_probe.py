@@ -108,5 +108,46 @@ def main():
         json.dump(res, f, indent=1)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "vit"):
     main()
+
+
+def probe_vit():
+    import torch
+    from passl_b200 import kernels_vit as V
+    res = {}
+    for (B, N, H, d) in [(512, 197, 12, 64), (512, 50, 12, 64), (256, 197, 16, 32)]:
+        qkv = torch.randn(B * N, 3 * H * d, device="cuda").bfloat16()
+        out, lse = V.attention_fwd(qkv, B, N, H, d)
+        dout = torch.randn_like(out)
+        f = timeit(lambda: V.attention_fwd(qkv, B, N, H, d), iters=10)
+        b = timeit(lambda: V.attention_bwd(qkv, dout, out, lse, B, N, H, d), iters=10)
+        fl = 4.0 * B * H * N * N * d
+        print("attention B%d N%d H%d d%d: fwd %.3f ms %.0f TF/s | bwd %.3f ms %.0f TF/s (2.5x fwd flops)" %
+              (B, N, H, d, f, fl / f / 1e9, b, 2.5 * fl / b / 1e9), flush=True)
+        res["attn_%d_%d_%d_%d" % (B, N, H, d)] = dict(fwd_ms=f, bwd_ms=b, fwd_tflops=fl / f / 1e9)
+    from passl_b200.core import ParamStore
+    from passl_b200.models import build_model
+    from passl_b200.optimizer import AdamW
+    for B in (128, 512):
+        m = build_model(dict(name="mae_vit_base_patch16", norm_pix_loss=True)).cuda()
+        st = ParamStore(m)
+        opt = AdamW(st, lr=1.5e-4, beta2=0.95, weight_decay=0.05)
+        imgs = torch.randn(B, 3, 224, 224, device="cuda")
+
+        def step():
+            opt.clear_grad()
+            loss, _, _ = m(imgs, 0.75)
+            loss.backward()
+            opt.step()
+        ms = timeit(step, iters=5, warmup=2, flush=False)
+        print("MAE ViT-B/16 B=%d full step %.2f ms -> %.0f img/s ; mem %.1f GB" % (B, ms, B / ms * 1e3, torch.cuda.max_memory_allocated() / 2**30), flush=True)
+        res["mae_B%d" % B] = dict(step_ms=ms, ips=B / ms * 1e3)
+        del m, st, opt
+        torch.cuda.empty_cache()
+    import json
+    json.dump(res, open("gpurun_out/perf_probe_vit.json", "w"), indent=1)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "vit":
+    probe_vit()
