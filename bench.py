@@ -213,9 +213,11 @@ def run_ours(args):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches)}
 
-    if rank == 0:
-        line["clocks"] = sampler.summary()
-        # ---- roofline of the dominant kernel: instrumented (untimed) step with CUDA events around every tcgen05 launch ---
+    # ---- roofline of the dominant kernel: instrumented (untimed) step with CUDA events around every tcgen05 launch.
+    #      Every rank runs the step (it contains collectives); only rank 0 reports.
+    if True:
+        if rank == 0:
+            line["clocks"] = sampler.summary()
         rec = []
         orig = {n: getattr(K, n) for n in ("gemm", "conv2d_fwd", "conv2d_dgrad", "conv2d_wgrad")}
 
@@ -248,6 +250,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         for n, f in orig.items():
             setattr(K, n, f)
+    if rank == 0:
         tc_ms = sum(s.elapsed_time(e) for s, e, _ in rec)
         tc_flops = sum(f for _, _, f in rec)
         ach = tc_flops / (tc_ms / 1e3) / 1e12

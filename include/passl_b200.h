@@ -94,6 +94,8 @@ int passl_b200_simce_bwd_f32(const float* A, const void* B, int b_is_bf16, const
  * once.  D multiple of 64, <= 512.
  * ------------------------------------------------------------------------------------------------------------- */
 long long passl_b200_infonce_tc_workspace_bytes(int N, int K, int D);
+/* developer hook: per-CTA timeline (uint64 [grid*16], %globaltimer ns) written by subsequent launches; NULL disables */
+int passl_b200_infonce_tc_set_debug(void* buf);
 int passl_b200_infonce_tc_fwd(const void* Q, const void* Kmat, const float* P, const long long* label, const int* excl,
                               float scale, float loss_scale, int N, int K, int D, float* lse, float* tgt,
                               float* loss_rows, float* out_scalars, void* workspace, long long workspace_bytes,

@@ -35,6 +35,7 @@ SIGNATURES = {
                                          c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll,
                                          c_void_p]),
     "passl_b200_infonce_tc_workspace_bytes": (c_ll, [c_int, c_int, c_int]),
+    "passl_b200_infonce_tc_set_debug": (c_int, [c_void_p]),
     "passl_b200_infonce_tc_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_int,
                                           c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
     "passl_b200_ntxent_workspace_bytes": (c_ll, [c_int]),

@@ -74,24 +74,30 @@ __global__ void __launch_bounds__(160, 1) attn_fwd_kernel(const __grid_constant_
   uint32_t ph_load = 0, ph_s = 0, ph_p = 0, ph_o = 0;
 
   if (warp == 4) {
-    if (lane == 0) {
+    {   // warp-uniform control loop; TMA / tcgen05 issue elect-predicated
       const uint32_t idesc1 = make_idesc_bf16(128, p.NKP, false, false);
       const uint32_t idesc2 = make_idesc_bf16(128, p.d, false, true);
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int b = item / p.H, h = item - b * p.H;
         // all MMAs of the previous item have completed (we waited on its last o_full below) -> smem reusable
-        mbar_arrive_expect_tx(load_full, (uint32_t)((p.mblocks * 128 + 2 * p.NKP) * rowB));
-        for (int mb = 0; mb < p.mblocks; ++mb) tma_load_4d(q_s + mb * 128 * rowB, &p.qkv_map, load_full, 0, h, mb * 128, b);
-        tma_load_4d(k_s, &p.kv_map, load_full, 0, p.H + h, 0, b);
-        tma_load_4d(v_s, &p.kv_map, load_full, 0, 2 * p.H + h, 0, b);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(load_full, (uint32_t)((p.mblocks * 128 + 2 * p.NKP) * rowB));
+          for (int mb = 0; mb < p.mblocks; ++mb) tma_load_4d(q_s + mb * 128 * rowB, &p.qkv_map, load_full, 0, h, mb * 128, b);
+          tma_load_4d(k_s, &p.kv_map, load_full, 0, p.H + h, 0, b);
+          tma_load_4d(v_s, &p.kv_map, load_full, 0, 2 * p.H + h, 0, b);
+        }
+        __syncwarp();
         mbar_wait(load_full, ph_load); ph_load ^= 1;
         tc_fence_after();
         for (int mb = 0; mb < p.mblocks; ++mb) {
           // MMA1: S = Q_mb K^T
           const uint32_t qa = smem_u32(q_s + mb * 128 * rowB), ka = smem_u32(k_s);
-          for (int k = 0; k < p.d / 16; ++k)
-            umma_bf16(tm_s, make_smem_desc(qa + k * 32, 16, sbo, lt), make_smem_desc(ka + k * 32, 16, sbo, lt), idesc1, k > 0);
-          umma_commit(s_full);
+          if (elect_one()) {
+            for (int k = 0; k < p.d / 16; ++k)
+              umma_bf16(tm_s, make_smem_desc(qa + k * 32, 16, sbo, lt), make_smem_desc(ka + k * 32, 16, sbo, lt), idesc1, k > 0);
+            umma_commit(s_full);
+          }
+          __syncwarp();
           // MMA2: O = P V   (after the softmax warps published P)
           mbar_wait(p_full, ph_p); ph_p ^= 1;
           // o_full of the previous block has necessarily completed here (the softmax warps consumed it before
@@ -99,12 +105,15 @@ __global__ void __launch_bounds__(160, 1) attn_fwd_kernel(const __grid_constant_
           if (mb > 0) { mbar_wait(o_full, ph_o); ph_o ^= 1; }
           tc_fence_after();
           const uint32_t pa = smem_u32(p_s), va = smem_u32(v_s);
-          for (int k = 0; k < p.NKP / 16; ++k) {
-            uint64_t da = make_smem_desc_sw128(pa + (k >> 2) * (128 * 128) + (k & 3) * 32, 16, 1024);
-            uint64_t db = make_smem_desc(va + k * 16 * rowB, 0, sbo, lt);   // MN-major: 16 keys = 2 atoms of 8 rows
-            umma_bf16(tm_o, da, db, idesc2, k > 0);
+          if (elect_one()) {
+            for (int k = 0; k < p.NKP / 16; ++k) {
+              uint64_t da = make_smem_desc_sw128(pa + (k >> 2) * (128 * 128) + (k & 3) * 32, 16, 1024);
+              uint64_t db = make_smem_desc(va + k * 16 * rowB, 0, sbo, lt);   // MN-major: 16 keys = 2 atoms of 8 rows
+              umma_bf16(tm_o, da, db, idesc2, k > 0);
+            }
+            umma_commit(o_full);
           }
-          umma_commit(o_full);
+          __syncwarp();
         }
         // wait until the last MMA2 of this item has retired before the next item's TMA overwrites smem
         mbar_wait(o_full, ph_o); ph_o ^= 1;
@@ -311,7 +320,7 @@ __global__ void __launch_bounds__(160, 1) attn_bwd_kernel(const __grid_constant_
   uint32_t ph_load = 0, ph_sp = 0, ph_pd = 0, ph_kvd = 0, ph_kvf = 0, ph_qd = 0, ph_qf = 0;
 
   if (warp == 4) {
-    if (lane == 0) {
+    {   // warp-uniform control loop; TMA / tcgen05 issue elect-predicated
       const uint32_t id_s = make_idesc_bf16(128, 128, false, false);
       const uint32_t id_kv = make_idesc_bf16(128, p.d, true, true);
       const uint32_t id_q = make_idesc_bf16(128, p.d, false, true);
@@ -319,13 +328,16 @@ __global__ void __launch_bounds__(160, 1) attn_bwd_kernel(const __grid_constant_
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int b = item / p.H, h = item - b * p.H;
         // previous item's MMAs are all complete (q_done waited below), epilogue reads are TMEM-only -> smem reusable
-        mbar_arrive_expect_tx(load_full, (uint32_t)(4 * nb * 128 * rowB));
-        for (int mb = 0; mb < nb; ++mb) {
-          tma_load_4d(q_s + mb * 128 * rowB, &p.qkv_map, load_full, 0, h, mb * 128, b);
-          tma_load_4d(k_s + mb * 128 * rowB, &p.qkv_map, load_full, 0, p.H + h, mb * 128, b);
-          tma_load_4d(v_s + mb * 128 * rowB, &p.qkv_map, load_full, 0, 2 * p.H + h, mb * 128, b);
-          tma_load_4d(do_s + mb * 128 * rowB, &p.do_map, load_full, 0, h, mb * 128, b);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(load_full, (uint32_t)(4 * nb * 128 * rowB));
+          for (int mb = 0; mb < nb; ++mb) {
+            tma_load_4d(q_s + mb * 128 * rowB, &p.qkv_map, load_full, 0, h, mb * 128, b);
+            tma_load_4d(k_s + mb * 128 * rowB, &p.qkv_map, load_full, 0, p.H + h, mb * 128, b);
+            tma_load_4d(v_s + mb * 128 * rowB, &p.qkv_map, load_full, 0, 2 * p.H + h, mb * 128, b);
+            tma_load_4d(do_s + mb * 128 * rowB, &p.do_map, load_full, 0, h, mb * 128, b);
+          }
         }
+        __syncwarp();
         mbar_wait(load_full, ph_load); ph_load ^= 1;
         tc_fence_after();
         if (!first_item) { mbar_wait(q_free, ph_qf); ph_qf ^= 1; }   // dQ accumulators of the previous item were read out
@@ -334,14 +346,18 @@ __global__ void __launch_bounds__(160, 1) attn_bwd_kernel(const __grid_constant_
           for (int i = 0; i < nb; ++i) {
             const uint32_t qa = smem_u32(q_s + i * 128 * rowB), doa = smem_u32(do_s + i * 128 * rowB);
             const uint32_t ka = smem_u32(k_s + j * 128 * rowB), va = smem_u32(v_s + j * 128 * rowB);
-            for (int k = 0; k < p.d / 16; ++k)
-              umma_bf16(tm_s, make_smem_desc(qa + k * 32, 16, sbo, lt), make_smem_desc(ka + k * 32, 16, sbo, lt), id_s, k > 0);
-            for (int k = 0; k < p.d / 16; ++k)
-              umma_bf16(tm_dp, make_smem_desc(doa + k * 32, 16, sbo, lt), make_smem_desc(va + k * 32, 16, sbo, lt), id_s, k > 0);
-            umma_commit(sp_full);
+            if (elect_one()) {
+              for (int k = 0; k < p.d / 16; ++k)
+                umma_bf16(tm_s, make_smem_desc(qa + k * 32, 16, sbo, lt), make_smem_desc(ka + k * 32, 16, sbo, lt), id_s, k > 0);
+              for (int k = 0; k < p.d / 16; ++k)
+                umma_bf16(tm_dp, make_smem_desc(doa + k * 32, 16, sbo, lt), make_smem_desc(va + k * 32, 16, sbo, lt), id_s, k > 0);
+              umma_commit(sp_full);
+            }
+            __syncwarp();
             mbar_wait(pd_full, ph_pd); ph_pd ^= 1;
             tc_fence_after();
             const uint32_t pa = smem_u32(p_s), dsa = smem_u32(ds_s);
+            if (elect_one()) {
             for (int k = 0; k < 8; ++k) {   // K = 128 query rows
               // dV_j += P^T dO_i ; dK_j += dS^T Q_i      (A = P / dS viewed MN-major: M = keys, K = query rows)
               umma_bf16(tm_dv, make_smem_desc(pa + k * 2048, 128 * 128, 1024, 2), make_smem_desc(doa + k * 16 * rowB, 0, sbo, lt),
@@ -352,10 +368,12 @@ __global__ void __launch_bounds__(160, 1) attn_bwd_kernel(const __grid_constant_
             for (int k = 0; k < 8; ++k)     // dQ_i += dS K_j   (A = dS K-major over keys, B = K_j MN-major)
               umma_bf16(tm_dq + i * 64, make_smem_desc_sw128(dsa + (k >> 2) * (128 * 128) + (k & 3) * 32, 16, 1024),
                         make_smem_desc(ka + k * 16 * rowB, 0, sbo, lt), id_q, (j > 0 || k > 0));
+            if (i == nb - 1) umma_commit(kv_done);
+            if (i == nb - 1 && j == nb - 1) umma_commit(q_done);
+            }
+            __syncwarp();
           }
-          umma_commit(kv_done);
         }
-        umma_commit(q_done);
         // all MMAs of this item retired before the next item's TMA overwrites shared memory
         // (q_done is also consumed by the epilogue warps; this thread waits one phase behind at most)
         mbar_wait(q_done, ph_qd); ph_qd ^= 1;

@@ -173,8 +173,11 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  // Role loops are warp-uniform (all 32 lanes run the control flow and the barrier waits); only the TMA / tcgen05 issue is
+  // predicated on elect.sync.  With `if (lane == 0)` around the whole loop the operands are per-thread values and ptxas wraps
+  // every UTCHMMA / UTMALDG in an ELECT + R2UR.BROADCAST waterfall loop (~200 cycles per MMA issue on the critical path).
   if (warp == 0) {
-    if (lane == 0) {
+    {
       // ================= TMA producer =================
       int stage = 0;
       uint32_t phase = 0;
@@ -200,9 +203,12 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
           for (int kit = k_begin; kit < k_end; ++kit) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * S::STAGE_BYTES;
-            mbar_arrive_expect_tx(&full_bar[stage], tx);
-            tma_load_4d(sa, &p.a.maps[p.a.map[tap]], &full_bar[stage], cc * 64, w0 + p.a.dw[tap], h0 + p.a.dh[tap], n0);
-            tma_load_2d(sa + S::A_BYTES, &p.b.maps[0], &full_bar[stage], kit * BK, b_row0);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&full_bar[stage], tx);
+              tma_load_4d(sa, &p.a.maps[p.a.map[tap]], &full_bar[stage], cc * 64, w0 + p.a.dw[tap], h0 + p.a.dh[tap], n0);
+              tma_load_2d(sa + S::A_BYTES, &p.b.maps[0], &full_bar[stage], kit * BK, b_row0);
+            }
+            __syncwarp();
             if (++cc == p.a.cchunks) { cc = 0; ++tap; }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -210,9 +216,12 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
           for (int kit = k_begin; kit < k_end; ++kit) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * S::STAGE_BYTES;
-            mbar_arrive_expect_tx(&full_bar[stage], tx);
-            tma_load_2d(sa, &p.a.maps[0], &full_bar[stage], kit * BK, m_blk * 128);
-            tma_load_2d(sa + S::A_BYTES, &p.b.maps[0], &full_bar[stage], kit * BK, b_row0);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&full_bar[stage], tx);
+              tma_load_2d(sa, &p.a.maps[0], &full_bar[stage], kit * BK, m_blk * 128);
+              tma_load_2d(sa + S::A_BYTES, &p.b.maps[0], &full_bar[stage], kit * BK, b_row0);
+            }
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         } else {
@@ -220,16 +229,19 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * S::STAGE_BYTES;
             uint8_t* sb = sa + S::A_BYTES;
-            mbar_arrive_expect_tx(&full_bar[stage], tx);
-            issue_operand_load<128, BK>(p.a, p.geom, sa, &full_bar[stage], m_blk * 128, m_blk, 0, kit);
-            issue_operand_load<BN, BK>(p.b, p.geom, sb, &full_bar[stage], b_row0, n_blk, b_tap, kit);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&full_bar[stage], tx);
+              issue_operand_load<128, BK>(p.a, p.geom, sa, &full_bar[stage], m_blk * 128, m_blk, 0, kit);
+              issue_operand_load<BN, BK>(p.b, p.geom, sb, &full_bar[stage], b_row0, n_blk, b_tap, kit);
+            }
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // ================= MMA issuer =================
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, A_MN, B_MN);
       // descriptor of stage 0 / k-step 0; later stages and k-steps only add to the 14-bit start-address field
@@ -258,21 +270,24 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
           // K-major: +32 B per 16-element K step inside the 128 B swizzle row.
           // MN-major: +2048 B per 16 k-rows (two 8-row atoms); LBO = chunk stride (BK rows x 128 B).
           const uint64_t da = da0 + (uint64_t)stage * kStage, db = db0 + (uint64_t)stage * kStage;
-          if (p.k_steps == KSTEPS_FULL) {
+          if (elect_one()) {
+            if (p.k_steps == KSTEPS_FULL) {
 #pragma unroll
-            for (int k = 0; k < KSTEPS_FULL; ++k)
-              umma_bf16(d_tmem, da + k * kStepA, db + k * kStepB, idesc, (kit > k_begin || k > 0) ? 1u : 0u);
-          } else {
-            for (int k = 0; k < p.k_steps; ++k)
-              umma_bf16(d_tmem, da + k * kStepA, db + k * kStepB, idesc, (kit > k_begin || k > 0) ? 1u : 0u);
+              for (int k = 0; k < KSTEPS_FULL; ++k)
+                umma_bf16(d_tmem, da + k * kStepA, db + k * kStepB, idesc, (kit > k_begin || k > 0) ? 1u : 0u);
+            } else {
+              for (int k = 0; k < p.k_steps; ++k)
+                umma_bf16(d_tmem, da + k * kStepA, db + k * kStepB, idesc, (kit > k_begin || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
+            if (kit == k_end - 1) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
           }
-          umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
       }
     }
   } else {

@@ -42,7 +42,15 @@ struct InfoNceTcParams {
   int row_groups, slices, tiles;
   float* part_m; float* part_l; int* part_cnt;  // [N, slices]
   float* tgt;                                   // [N]
+  unsigned long long* dbg;                      // optional per-CTA timeline (globaltimer ns), 16 slots per CTA
 };
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define NCE_STAMP(slot) do { if (p.dbg) p.dbg[blockIdx.x * 16 + (slot)] = gtime(); } while (0)
 
 template <int MB>
 __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const __grid_constant__ InfoNceTcParams p) {
@@ -88,38 +96,48 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
     }
     fence_barrier_init();
   }
+  if (threadIdx.x == 64) NCE_STAMP(0);
   if (warp == 1) tmem_alloc(tmem_ptr, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (threadIdx.x == 64) NCE_STAMP(1);
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t tm_q = tmem_base;                       // Q (A operand): block b at columns [b*q_cols, (b+1)*q_cols)
   const uint32_t tm_s = tmem_base + MB * q_cols;         // S accumulators: (buf*MB + b) * 64
 
+  // role loops are warp-uniform; only the TMA / tcgen05 issue is elect-predicated (keeps descriptors in uniform registers)
   if (warp == 0) {
-    if (lane == 0) {
+    {
       // ---------------- TMA producer ----------------
-      mbar_arrive_expect_tx(q_full, (uint32_t)q_bytes);
-      for (int b = 0; b < MB; ++b)
-        for (int c = 0; c < DC; ++c)
-          tma_load_2d(q_smem + (b * DC + c) * (128 * 128), &p.q_map, q_full, c * 64, row_base + b * 128);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(q_full, (uint32_t)q_bytes);
+        for (int b = 0; b < MB; ++b)
+          for (int c = 0; c < DC; ++c)
+            tma_load_2d(q_smem + (b * DC + c) * (128 * 128), &p.q_map, q_full, c * 64, row_base + b * 128);
+      }
+      __syncwarp();
       int stage = 0;
       uint32_t phase = 0;
       for (int t = t_begin; t < t_end; ++t) {
         mbar_wait(&k_empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&k_full[stage], (uint32_t)stage_bytes);
-        for (int c = 0; c < DC; ++c)
-          tma_load_2d(k_smem + stage * stage_bytes + c * (NCE_BK * 128), &p.k_map, &k_full[stage], c * 64, t * NCE_BK);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&k_full[stage], (uint32_t)stage_bytes);
+          for (int c = 0; c < DC; ++c)
+            tma_load_2d(k_smem + stage * stage_bytes + c * (NCE_BK * 128), &p.k_map, &k_full[stage], c * 64, t * NCE_BK);
+        }
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // ---------------- MMA issuer ----------------
       constexpr uint32_t idesc = make_idesc_bf16(128, NCE_BK, false, false);
       const uint64_t db0 = make_smem_desc_sw128(smem_u32(k_smem), 16, 1024);   // stage 0, chunk 0, k-step 0
       mbar_wait(q_ready, 0);
       tc_fence_after();
+      if (lane == 0) NCE_STAMP(14);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -130,6 +148,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
         mbar_wait(&k_full[stage], phase);
         tc_fence_after();
         const uint64_t dbs = db0 + (uint64_t)((stage * stage_bytes) >> 4);
+        if (elect_one()) {
         for (int b = 0; b < MB; ++b) {
           const uint32_t d_tmem = tm_s + (buf * MB + b) * NCE_BK;
           const uint32_t a_tmem = tm_q + b * q_cols;
@@ -142,6 +161,8 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
         }
         umma_commit(&k_empty[stage]);
         umma_commit(&s_full[buf]);
+        }
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -163,6 +184,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
     {
       const int rl = q4 * 32 + lane;                       // row inside the 128-row block
       mbar_wait(q_full, 0);
+      if (threadIdx.x == 64) NCE_STAMP(2);
       const uint32_t tq = tm_q + ((q4 * 32u) << 16) + b * q_cols;
       for (int ch = 0; ch < DC; ++ch) {
         const uint8_t* base = q_smem + (b * DC + ch) * (128 * 128) + (rl >> 3) * 1024 + (rl & 7) * 128;
@@ -178,6 +200,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(q_ready);
+      if (threadIdx.x == 64) NCE_STAMP(3);
       if (row_ok) {
         if (!p.P) lab = p.label[row];
         if (p.excl) ex = p.excl[row];
@@ -227,6 +250,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
       }
       tgt2 = s_mine * c2;
       tgt_raw = s_mine;
+      if (threadIdx.x == 64) NCE_STAMP(4);
     }
 
     float m = -INFINITY, l = 0.f;
@@ -237,6 +261,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
       const uint32_t bphase = (it >> 1) & 1;
       mbar_wait(&s_full[buf], bphase);
       tc_fence_after();
+      if (threadIdx.x == 64 && it < 8) NCE_STAMP(5 + it);
       const uint32_t taddr = tm_s + ((q4 * 32u) << 16) + (buf * MB + b) * NCE_BK;
       uint32_t v[64];
       tmem_ld_32x32(taddr, v);
@@ -301,6 +326,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
         }
       }
     }
+    if (threadIdx.x == 64) NCE_STAMP(13);
     if (row_ok) {
       // back to the natural-log domain used by simce_finalize_kernel
       p.part_m[(size_t)row * p.slices + slice] = m * kLn2;
@@ -336,6 +362,10 @@ static void nce_plan(int N, int K, int D, int& MB, int& groups, int& slices, int
 
 using namespace pb;
 
+static unsigned long long* g_nce_dbg = nullptr;
+// developer hook: per-CTA timeline buffer (uint64 [grid * 16]) filled by the next launches; NULL disables
+extern "C" int passl_b200_infonce_tc_set_debug(void* buf) { g_nce_dbg = reinterpret_cast<unsigned long long*>(buf); return 0; }
+
 extern "C" long long passl_b200_infonce_tc_workspace_bytes(int N, int K, int D) {
   int MB, groups, slices, tiles, smem;
   nce_plan(N, K, D, MB, groups, slices, tiles, smem);
@@ -365,6 +395,7 @@ extern "C" int passl_b200_infonce_tc_fwd(const void* Q, const void* Kmat, const 
   p.part_l = reinterpret_cast<float*>(ws); ws += (size_t)N * p.slices * 4;
   p.part_cnt = reinterpret_cast<int*>(ws);
   p.tgt = tgt;
+  p.dbg = g_nce_dbg;
   uint64_t qd[2] = {(uint64_t)D, (uint64_t)N}, qs[1] = {(uint64_t)D * 2};
   uint32_t qbx[2] = {64, 128};
   int rc = make_tmap_bf16(&p.q_map, Q, 2, qd, qs, qbx);

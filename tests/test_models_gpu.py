@@ -13,7 +13,7 @@ def test_mocov3_small_step():
     def enc():
         return MoCoV3ViT(img_size=64, patch_size=16, embed_dim=128, depth=2, num_heads=2, qkv_bias=True, epsilon=1e-6)
     torch.manual_seed(0)
-    m = MoCoV3Pretrain(enc, dim=64, mlp_dim=256, T=0.2, max_steps=10).cuda()
+    m = MoCoV3Pretrain(enc, dim=128, mlp_dim=256, T=0.2, max_steps=10).cuda()
     st, sk = m.build_param_stores()
     opt = AdamW(st, lr=1e-3, weight_decay=0.1)
     k0 = sk.master.clone()
