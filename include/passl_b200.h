@@ -213,6 +213,38 @@ int passl_b200_mae_loss_bwd(const void* pred, const float* imgs, const float* ma
                             int Hp, int P, int pred_tokens, int pred_off, int norm_pix, float mask_sum, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * CLIP (passl_v110/modeling/backbones/clip.py:299-338, heads/clip_head.py:27-35, architectures/CLIPWrapper.py:45-51).
+ *   embedding_fwd   replaces nn.Embedding gather + "+ positional_embedding" (clip.py:300-303): ids int64 [T] (T = B*L),
+ *                   table fp32 [V,D], pos fp32 [L,D] -> out bf16 [T,D].   embedding_bwd scatters dout into dtable
+ *                   (fp32 L2 reductions) and accumulates dpos; either may be NULL.
+ *   eot_gather      replaces text.argmax(-1) + the per-sample Python gather loop (clip.py:307-311): idx int32 [B] (first
+ *                   maximum), out[b] = x[b*L + idx[b]].   eot_gather_bwd writes the full dx (zeros elsewhere).
+ *   clip_ce         replaces exp(logit_scale), the two logits matmul scalings, both CrossEntropyLoss calls and the
+ *                   logit_scale clip (clip.py:316-335, clip_head.py:29-35) on C = I_n T_n^T fp32 [n,n] (n % 4 == 0):
+ *                   out3 = {img_loss, text_loss, loss}; logit_scale is read on the device and, if clamp != 0, clipped to
+ *                   [-4.6, 4.6] after use.  clip_ce_bwd: dC bf16 [n,n] = d loss / d C, *dlogit_scale += d loss / d logit_scale.
+ *                   The same workspace must be passed to fwd and bwd (it carries s and the row / column LSE).
+ * ------------------------------------------------------------------------------------------------------------- */
+int passl_b200_embedding_fwd(const long long* ids, const float* table, const float* pos, void* out, long long T, int L, int D,
+                             int V, void* stream);
+int passl_b200_embedding_bwd(const long long* ids, const void* dout, float* dtable, float* dpos, long long T, int L, int D, int V,
+                             void* stream);
+int passl_b200_eot_gather_fwd(const long long* ids, const void* x, void* out, int* idx, int B, int L, int D, void* stream);
+int passl_b200_eot_gather_bwd(const int* idx, const void* dout, void* dx, int B, int L, int D, void* stream);
+long long passl_b200_clip_ce_workspace_bytes(int n);
+int passl_b200_clip_ce_fwd(const float* C, float* logit_scale, float* out3, int n, int clamp, void* workspace,
+                           long long workspace_bytes, void* stream);
+int passl_b200_clip_ce_bwd(const float* C, const float* dloss, void* dC, float* dlogit_scale, int n, void* workspace,
+                           long long workspace_bytes, void* stream);
+/* mean softmax cross entropy on materialised fp32 logits [n,m] with int64 labels — nn.CrossEntropyLoss() as the heads call it
+ * with explicit logits (clip_head.py:29-32, contrastive_head.py:52-53).  workspace >= 4*n bytes; row_lse [n] feeds the backward:
+ * dlogits = dloss/n * (softmax - onehot). */
+int passl_b200_rows_ce_fwd(const float* logits, const long long* labels, float* loss, float* row_lse, int n, int m,
+                           void* workspace, long long workspace_bytes, void* stream);
+int passl_b200_rows_ce_bwd(const float* logits, const long long* labels, const float* row_lse, const float* dloss, float* dlogits,
+                           int n, int m, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Stem / pooling.  im2col: reference NCHW fp32 images -> bf16 [N*Ho*Wo, Kpad] with K order (r, s, c), zero padded
  * (7x7/2 stem conv resnetimagenet.py:190-198; 16x16/16 patch embedding vision_transformer.py:231-236).
  * maxpool 3x3/2 pad 1 (resnetimagenet.py:198), arg-max tap saved as int8; global average pool (base_neck.py:52,79).

@@ -63,6 +63,15 @@ SIGNATURES = {
     "passl_b200_mae_loss_workspace_bytes": (c_ll, [c_int, c_int]),
     "passl_b200_mae_loss_fwd": (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_float, c_void_p, c_void_p]),
     "passl_b200_mae_loss_bwd": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_float, c_void_p]),
+    "passl_b200_embedding_fwd": (c_int, [c_void_p] * 4 + [c_ll, c_int, c_int, c_int, c_void_p]),
+    "passl_b200_embedding_bwd": (c_int, [c_void_p] * 4 + [c_ll, c_int, c_int, c_int, c_void_p]),
+    "passl_b200_eot_gather_fwd": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),
+    "passl_b200_eot_gather_bwd": (c_int, [c_void_p] * 3 + [c_int] * 3 + [c_void_p]),
+    "passl_b200_clip_ce_workspace_bytes": (c_ll, [c_int]),
+    "passl_b200_clip_ce_fwd": (c_int, [c_void_p] * 3 + [c_int, c_int, c_void_p, c_ll, c_void_p]),
+    "passl_b200_clip_ce_bwd": (c_int, [c_void_p] * 4 + [c_int, c_void_p, c_ll, c_void_p]),
+    "passl_b200_rows_ce_fwd": (c_int, [c_void_p] * 4 + [c_int, c_int, c_void_p, c_ll, c_void_p]),
+    "passl_b200_rows_ce_bwd": (c_int, [c_void_p] * 5 + [c_int, c_int, c_void_p]),
     "passl_b200_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "passl_b200_attention_bwd": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "passl_b200_layernorm_fwd": (c_int, [c_void_p] * 6 + [c_ll, c_int, c_float, c_void_p]),

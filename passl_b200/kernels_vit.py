@@ -107,3 +107,70 @@ def mae_loss_bwd(pred, imgs, mask, dloss, B, Hp, P, pred_tokens, pred_off, norm_
     _lib.check(lib.passl_b200_mae_loss_bwd(_ptr(pred), _ptr(imgs), _ptr(mask), _ptr(dloss), _ptr(dpred), B, Hp, P, pred_tokens,
                                            pred_off, int(norm_pix), float(mask_sum), _stream()), "mae_loss_bwd")
     return dpred
+
+
+# CLIP: token embedding, EOT pooling, symmetric cross entropy
+# ------------------------------------------------------------------------------------------------------------
+def embedding_fwd(ids, table, pos):
+    """ids int64 [B, L], table fp32 [V, D], pos fp32 [L, D] -> bf16 [B*L, D] = table[ids] + pos  (clip.py:300-303)."""
+    _need_cuda(ids, table)
+    lib = _lib.load()
+    B, L = ids.shape
+    V, D = table.shape
+    assert ids.dtype == torch.int64 and ids.is_contiguous() and table.dtype == torch.float32 and pos.shape == (L, D)
+    out = torch.empty((B * L, D), dtype=torch.bfloat16, device=table.device)
+    _lib.check(lib.passl_b200_embedding_fwd(_ptr(ids), _ptr(table), _ptr(pos), _ptr(out), B * L, L, D, V, _stream()), "embedding_fwd")
+    return out
+
+
+def embedding_bwd(ids, dout, dtable=None, dpos=None):
+    """Accumulates d table (fp32 [V, D]) and d pos (fp32 [L, D]) from dout bf16 [B*L, D]."""
+    lib = _lib.load()
+    B, L = ids.shape
+    D = dout.shape[1]
+    V = dtable.shape[0] if dtable is not None else 1 << 30
+    _lib.check(lib.passl_b200_embedding_bwd(_ptr(ids), _ptr(dout), _ptr(dtable), _ptr(dpos), B * L, L, D, V, _stream()),
+               "embedding_bwd")
+
+
+def eot_gather_fwd(ids, x):
+    """ids int64 [B, L], x bf16 [B*L, D] -> (x[b, argmax(ids[b])] bf16 [B, D], idx int32 [B])  (clip.py:307-311)."""
+    lib = _lib.load()
+    B, L = ids.shape
+    D = x.shape[1]
+    out = torch.empty((B, D), dtype=torch.bfloat16, device=x.device)
+    idx = torch.empty(B, dtype=torch.int32, device=x.device)
+    _lib.check(lib.passl_b200_eot_gather_fwd(_ptr(ids), _ptr(x), _ptr(out), _ptr(idx), B, L, D, _stream()), "eot_gather_fwd")
+    return out, idx
+
+
+def eot_gather_bwd(idx, dout, L):
+    lib = _lib.load()
+    B, D = dout.shape
+    dx = torch.empty((B * L, D), dtype=torch.bfloat16, device=dout.device)
+    _lib.check(lib.passl_b200_eot_gather_bwd(_ptr(idx), _ptr(dout), _ptr(dx), B, L, D, _stream()), "eot_gather_bwd")
+    return dx
+
+
+def clip_ce_fwd(C, logit_scale, clamp=True):
+    """C fp32 [n, n] cosine similarities, logit_scale fp32 [1] (log domain, read + clamped on the device)
+    -> (out3 fp32 [3] = img_loss, text_loss, loss; workspace to hand to clip_ce_bwd)."""
+    _need_cuda(C)
+    lib = _lib.load()
+    n = C.shape[0]
+    assert C.dtype == torch.float32 and C.is_contiguous() and C.shape == (n, n) and logit_scale.dtype == torch.float32
+    wsb = lib.passl_b200_clip_ce_workspace_bytes(n)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=C.device)
+    out3 = torch.empty(3, dtype=torch.float32, device=C.device)
+    _lib.check(lib.passl_b200_clip_ce_fwd(_ptr(C), _ptr(logit_scale), _ptr(out3), n, int(clamp), _ptr(ws), wsb, _stream()), "clip_ce_fwd")
+    return out3, ws
+
+
+def clip_ce_bwd(C, ws, dloss=None, dlogit_scale=None):
+    """-> dC bf16 [n, n]; accumulates d loss / d logit_scale into dlogit_scale (fp32 [1])."""
+    lib = _lib.load()
+    n = C.shape[0]
+    dC = torch.empty((n, n), dtype=torch.bfloat16, device=C.device)
+    _lib.check(lib.passl_b200_clip_ce_bwd(_ptr(C), _ptr(dloss), _ptr(dC), _ptr(dlogit_scale), n, _ptr(ws), ws.numel(), _stream()),
+               "clip_ce_bwd")
+    return dC

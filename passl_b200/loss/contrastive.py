@@ -74,3 +74,37 @@ def normalize(x, eps=1e-12):
 def l2_normalize(x, eps=1e-12):
     """passl/nn/norm.py:18-40: x / sqrt(sum x^2 + eps)."""
     return _L2Normalize.apply(x, "l2_normalize", eps)
+
+
+class _LogitsCE(torch.autograd.Function):
+    """nn.CrossEntropyLoss()(logits, labels) on materialised logits (reference head signatures, clip_head.py:29-32)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels):
+        from .. import _lib
+        lib = _lib.load()
+        x = logits.detach().float().contiguous()
+        n, m = x.shape
+        lb = labels.to(torch.int64).contiguous()
+        loss = torch.empty(1, dtype=torch.float32, device=x.device)
+        lse = torch.empty(n, dtype=torch.float32, device=x.device)
+        ws = torch.empty(n, dtype=torch.float32, device=x.device)
+        _lib.check(lib.passl_b200_rows_ce_fwd(K._ptr(x), K._ptr(lb), K._ptr(loss), K._ptr(lse), n, m, K._ptr(ws), n * 4, K._stream()),
+                   "rows_ce_fwd")
+        ctx.saved = (x, lb, lse)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, dloss):
+        from .. import _lib
+        lib = _lib.load()
+        x, lb, lse = ctx.saved
+        dx = torch.empty_like(x)
+        _lib.check(lib.passl_b200_rows_ce_bwd(K._ptr(x), K._ptr(lb), K._ptr(lse), K._ptr(dloss.contiguous().float().reshape(1)),
+                                              K._ptr(dx), x.shape[0], x.shape[1], K._stream()), "rows_ce_bwd")
+        return dx, None
+
+
+def logits_cross_entropy(logits, labels):
+    K._need_cuda(logits)
+    return _LogitsCE.apply(logits, labels)

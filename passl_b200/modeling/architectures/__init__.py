@@ -1,2 +1,3 @@
 from .moco import MoCo  # noqa: F401
 from .simclr import SimCLR  # noqa: F401
+from .clip_wrapper import CLIP, CLIPHead, CLIPWrapper  # noqa: F401

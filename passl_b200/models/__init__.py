@@ -5,6 +5,7 @@ import copy
 from .vision_transformer import VisionTransformer, ViT_base_patch16_224  # noqa: F401
 from .mae import MaskedAutoencoderViT, mae_vit_base_patch16  # noqa: F401
 from .mocov3 import MoCoV3Pretrain, MoCoV3ViT, mocov3_vit_base_pretrain  # noqa: F401
+from .clip import CLIP, CLIPHead, CLIPWrapper, CLIPVisionTransformer, CLIPTextTransformer  # noqa: F401
 from ..modeling.backbones.resnet import ResNet  # noqa: F401
 
 

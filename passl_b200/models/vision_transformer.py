@@ -99,12 +99,12 @@ class Block(nn.Module):
 class PatchEmbed(nn.Module):
     """Conv2D(k = s = patch) as im2col + GEMM (vision_transformer.py:209-249); weight [embed, p, p, c] flattened (p,q,c)."""
 
-    def __init__(self, img_size=224, patch_size=16, in_chans=3, embed_dim=768):
+    def __init__(self, img_size=224, patch_size=16, in_chans=3, embed_dim=768, bias=True):
         super().__init__()
         self.img_size, self.patch_size = (img_size, img_size), (patch_size, patch_size)
         self.num_patches = (img_size // patch_size) ** 2
         self.kdim = patch_size * patch_size * in_chans
-        self.proj = Linear(self.kdim, embed_dim)
+        self.proj = Linear(self.kdim, embed_dim, bias=bias)
         # mae.py:133-137: xavier_uniform on the weight viewed as [embed, -1]
         nn.init.xavier_uniform_(self.proj.weight)
 

@@ -89,9 +89,10 @@ class LarsMomentumOptimizer(_FlatOptimizer):
 class AdamW(_FlatOptimizer):
     """passl/optimizer/adamw.py:52-138 (decoupled decay, bias correction); no decay on 1-d tensors by default."""
 
-    def __init__(self, store, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01, no_decay=None, lr_ratio=None):
+    def __init__(self, store, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01, no_decay=None, lr_ratio=None,
+                 epsilon=None):
         super().__init__(store, lr)
-        self.beta1, self.beta2, self.eps = beta1, beta2, eps
+        self.beta1, self.beta2, self.eps = beta1, beta2, (eps if epsilon is None else epsilon)   # `epsilon`: the YAML key
         self.m = torch.zeros_like(store.master)
         self.v = torch.zeros_like(store.master)
         pats = [re.compile(p) for p in (no_decay or [])]

@@ -1,0 +1,201 @@
+"""CLIP path on the GPU (SURVEY §8 a10 + f-4): token embedding, EOT pooling, symmetric CE kernels, and the two-tower model against
+the float64 oracle twin (oracle/clip.py) and the golden CLIPHead vectors produced by the reference source."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_heads.npz"))
+
+
+def _cos(a, b):
+    a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-300))
+
+
+def test_clip_loss_vs_reference_golden():
+    """img / text features of the golden case -> fused loss; reference CLIPHead output (bf16 GEMM: 1e-2 relative)."""
+    from passl_b200.models.clip import CLIPHead
+    img = torch.tensor(G["clip_img"], dtype=torch.float32, device="cuda")
+    txt = torch.tensor(G["clip_txt"], dtype=torch.float32, device="cuda")
+    ls = torch.nn.Parameter(torch.tensor([float(G["clip_logit_scale"])], device="cuda"))
+    out = CLIPHead().forward_fused(img, txt, ls)
+    for k, g in (("img_loss", "clip_img_loss"), ("text_loss", "clip_text_loss"), ("loss", "clip_loss")):
+        np.testing.assert_allclose(out[k].item(), float(G[g]), rtol=1e-2)
+
+
+@pytest.mark.parametrize("n,d", [(20, 64), (256, 512), (1024, 512)])
+def test_clip_loss_grads_vs_oracle(n, d):
+    import oracle.clip as OC
+    from passl_b200.models.clip import CLIPHead
+    torch.manual_seed(n)
+    img = torch.randn(n, d, device="cuda")
+    txt = 0.6 * img + 0.4 * torch.randn(n, d, device="cuda")
+    ls0 = float(np.log(1 / 0.07))
+    img.requires_grad_(True)
+    txt.requires_grad_(True)
+    ls = torch.nn.Parameter(torch.tensor([ls0], device="cuda"))
+    out = CLIPHead().forward_fused(img, txt, ls)
+    out["loss"].backward()
+    # oracle on the bf16-rounded normalised features is not expressible; compare against the exact fp64 path with bf16 tolerances
+    i64 = img.detach().double().cpu().requires_grad_(True)
+    t64 = txt.detach().double().cpu().requires_grad_(True)
+    l64 = torch.tensor([ls0], dtype=torch.float64, requires_grad=True)
+    il, tl, ls_after = OC.clip_forward(i64, t64, l64)
+    ref = OC.clip_head(il, tl)
+    ref["loss"].backward()
+    for k in ("img_loss", "text_loss", "loss"):
+        np.testing.assert_allclose(out[k].item(), ref[k].item(), rtol=1e-2)
+    assert _cos(img.grad, i64.grad) > 0.995 and _cos(txt.grad, t64.grad) > 0.995
+    np.testing.assert_allclose(img.grad.norm().item(), i64.grad.norm().item(), rtol=3e-2)
+    np.testing.assert_allclose(ls.grad.item(), l64.grad.item(), rtol=3e-2, atol=2e-3)
+    assert abs(ls.item() - ls0) < 1e-6                       # inside [-4.6, 4.6]: untouched
+
+
+def test_logit_scale_clamped_on_device():
+    """clip.py:316-318: the forward uses the unclamped value, then the parameter is clipped to [-4.6, 4.6]."""
+    import oracle.clip as OC
+    from passl_b200.models.clip import CLIPHead
+    torch.manual_seed(1)
+    img, txt = torch.randn(32, 64, device="cuda"), torch.randn(32, 64, device="cuda")
+    ls = torch.nn.Parameter(torch.tensor([5.0], device="cuda"))
+    out = CLIPHead().forward_fused(img, txt, ls)
+    il, tl, ls_after = OC.clip_forward(img.double().cpu(), txt.double().cpu(), torch.tensor([5.0], dtype=torch.float64))
+    np.testing.assert_allclose(out["loss"].item(), OC.clip_head(il, tl)["loss"].item(), rtol=2e-2)
+    assert abs(ls.item() - 4.6) < 1e-6 and abs(ls_after.item() - 4.6) < 1e-12
+
+
+def test_logits_cross_entropy_reference_signature():
+    """CLIPHead.forward(img_logits, text_logits, img_labels, text_labels) on materialised logits: golden, exact fp32 path."""
+    from passl_b200.models.clip import CLIPHead
+    import oracle.contrastive as OCn
+    il, tl = OCn.clip_logits(G["clip_img"], G["clip_txt"], float(G["clip_logit_scale"]))
+    n = il.shape[0]
+    a = torch.tensor(il, dtype=torch.float32, device="cuda", requires_grad=True)
+    b = torch.tensor(tl, dtype=torch.float32, device="cuda", requires_grad=True)
+    lab = torch.arange(n, device="cuda")
+    out = CLIPHead()(a, b, lab, lab)
+    np.testing.assert_allclose(out["img_loss"].item(), float(G["clip_img_loss"]), rtol=1e-5)
+    np.testing.assert_allclose(out["text_loss"].item(), float(G["clip_text_loss"]), rtol=1e-5)
+    np.testing.assert_allclose(out["loss"].item(), float(G["clip_loss"]), rtol=1e-5)
+    out["loss"].backward()
+    a64 = torch.tensor(il, dtype=torch.float64, requires_grad=True)
+    torch.nn.functional.cross_entropy(a64, torch.arange(n)).backward()
+    np.testing.assert_allclose(a.grad.cpu().numpy(), a64.grad.numpy(), rtol=1e-4, atol=1e-7)
+
+
+def test_embedding_and_eot_pooling_bit_exact_indices():
+    from passl_b200 import kernels_vit as V
+    torch.manual_seed(3)
+    B, L, D, Vc = 9, 77, 512, 1000
+    ids = torch.randint(1, Vc - 1, (B, L), device="cuda")
+    eot = torch.randint(1, L, (B,), device="cuda")
+    ids[torch.arange(B), eot] = Vc - 1                           # EOT = highest id (clip.py:306)
+    ids[0, :] = 5                                                # all equal: argmax returns the first position
+    ids[1, 10], ids[1, 20] = Vc - 1, Vc - 1                      # tie: first occurrence wins
+    ids[1, eot[1]] = 7
+    table = torch.randn(Vc, D, device="cuda")
+    pos = torch.randn(L, D, device="cuda") * 0.01
+    x = V.embedding_fwd(ids, table, pos)
+    ref = (table[ids] + pos).reshape(B * L, D)
+    assert torch.equal(x, ref.bfloat16())
+    out, idx = V.eot_gather_fwd(ids, x)
+    want = ids.argmax(dim=-1)
+    want[0] = 0
+    want[1] = 10
+    assert torch.equal(idx.long(), want)                         # bit-exact integer indices
+    assert torch.equal(out, x.view(B, L, D)[torch.arange(B), want])
+    # backward: scatter to the EOT rows, embedding-table / positional gradients
+    dout = torch.randn(B, D, device="cuda").bfloat16()
+    dx = V.eot_gather_bwd(idx, dout, L)
+    refdx = torch.zeros(B, L, D, device="cuda", dtype=torch.bfloat16)
+    refdx[torch.arange(B), want] = dout
+    assert torch.equal(dx, refdx.view(B * L, D))
+    g = torch.randn(B * L, D, device="cuda").bfloat16()
+    dtable = torch.zeros(Vc, D, device="cuda")
+    dpos = torch.zeros(L, D, device="cuda")
+    V.embedding_bwd(ids, g, dtable=dtable, dpos=dpos)
+    rt = torch.zeros(Vc, D, device="cuda", dtype=torch.float64).index_add_(0, ids.flatten(), g.double())
+    torch.testing.assert_close(dtable.double(), rt, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(dpos.double(), g.double().view(B, L, D).sum(0), rtol=1e-5, atol=1e-5)
+
+
+CFG = dict(embed_dim=64, image_resolution=64, vision_layers=2, vision_width=128, vision_patch_size=16, pre_norm=True, proj=True,
+           patch_bias=False, context_length=16, vocab_size=1000, transformer_width=128, transformer_heads=2, transformer_layers=2,
+           qkv_bias=True)
+
+
+def _export(model):
+    import oracle.vit as OV
+    p = OV.export_params(model)
+    for name in ("text.token_embedding", "text.positional_embedding"):       # read as fp32 by the gather kernel (not GEMM operands)
+        t = dict(model.named_parameters())[name]
+        p[name] = t.detach().double().cpu().requires_grad_(True)
+    return p
+
+
+def test_clip_small_model_vs_oracle_twin():
+    import oracle.clip as OC
+    from passl_b200.core import ParamStore
+    from passl_b200.modeling import build_model
+    torch.manual_seed(0)
+    m = build_model(dict(name="CLIPWrapper", architecture=dict(name="CLIP", **CFG), head=dict(name="CLIPHead"))).cuda()
+    with torch.no_grad():                                        # tame the reference's (2*depth)x proj init for a conditioned check
+        for blk in m.model.text.blocks:
+            blk.proj.weight.mul_(0.1)
+            blk.fc2.weight.mul_(0.1)
+    st = ParamStore(m)
+    n = 16
+    img = torch.randn(n, 3, 64, 64, device="cuda")
+    text = torch.randint(1, 998, (n, 16), device="cuda")
+    text[torch.arange(n), torch.randint(1, 16, (n,))] = 999
+    st.zero_grad()
+    out = m(img, text)
+    out["loss"].backward()
+    p = _export(m.model)
+    cfg = dict(patch_size=16, width=128, depth=2, num_heads=2, pre_norm=True, text_width=128, text_layers=2, text_heads=2)
+    ref = OC.clip_train_iter(img.double().cpu(), text.cpu(), p, cfg)
+    ref["loss"].backward()
+    np.testing.assert_allclose(out["loss"].item(), ref["loss"].item(), rtol=2e-2)
+    np.testing.assert_allclose(out["img_loss"].item(), ref["img_loss"].item(), rtol=2e-2)
+    named = dict(m.model.named_parameters())
+    worst = 1.0
+    for name in ("visual.proj.weight", "visual.blocks.1.fc2.weight", "visual.blocks.0.qkv.weight", "visual.patch_embed.proj.weight",
+                 "visual.class_embedding", "visual.positional_embedding", "visual.norm_pre.weight", "text.text_projection.weight",
+                 "text.blocks.1.fc1.weight", "text.blocks.0.qkv.weight", "text.blocks.0.qkv.bias", "text.ln_final.weight",
+                 "text.positional_embedding", "text.token_embedding"):
+        g = named[name].grad
+        assert g is not None and torch.isfinite(g).all(), name
+        c = _cos(g, p[name].grad)
+        worst = min(worst, c)
+        assert c > 0.97, (name, c)
+    np.testing.assert_allclose(named["logit_scale"].grad.item(), p["logit_scale"].grad.item(), rtol=5e-2, atol=5e-3)
+
+
+def test_clip_vit_b16_shape_step():
+    """BASELINE config C5 shapes at a small batch: ViT-B/16 image tower (197 tokens), 12-layer causal text tower (77 tokens, 8 heads)."""
+    from passl_b200.core import ParamStore
+    from passl_b200.modeling import build_model
+    from passl_b200.optimizer import AdamW
+    torch.manual_seed(0)
+    arch = dict(name="CLIP", embed_dim=512, image_resolution=224, vision_layers=12, vision_width=768, vision_patch_size=16,
+                pre_norm=True, proj=True, patch_bias=False, context_length=77, vocab_size=49408, transformer_width=512,
+                transformer_heads=8, transformer_layers=12, qkv_bias=True)
+    m = build_model(dict(name="CLIPWrapper", architecture=arch, head=dict(name="CLIPHead"))).cuda()
+    st = ParamStore(m)
+    opt = AdamW(st, lr=1e-4, beta2=0.98, epsilon=1e-8, weight_decay=0.0005)
+    n = 8
+    img = torch.randn(n, 3, 224, 224, device="cuda")
+    text = torch.randint(1, 49407, (n, 77), device="cuda")
+    text[torch.arange(n), torch.randint(1, 77, (n,))] = 49407
+    losses = []
+    for it in range(2):
+        opt.clear_grad()
+        out = m(img, text)
+        out["loss"].backward()
+        opt.step()
+        losses.append(out["loss"].item())
+    assert all(np.isfinite(losses)), losses
+    assert st.grad.abs().sum().item() > 0 and torch.isfinite(st.grad).all()
