@@ -221,19 +221,25 @@ def run_ours(args):
         rec = []
         orig = {n: getattr(K, n) for n in ("gemm", "conv2d_fwd", "conv2d_dgrad", "conv2d_wgrad")}
 
-        def flops_of(name, a, kw, res):
+        def cost_of(name, a, kw, res):
+            """(algorithmic FLOPs, algorithmic HBM bytes) of one launch: operands read once, output written once."""
+            def nb(t):
+                return 0 if t is None else t.numel() * t.element_size()
+            extra = nb(kw.get("residual")) + nb(kw.get("aux")) + nb(kw.get("preact_out"))
             if name == "gemm":
                 A, Bm = a[0], a[1]
                 Kd = A.shape[0] if kw.get("a_t") else A.shape[1]
-                return 2.0 * res.shape[0] * res.shape[1] * Kd
+                acc = nb(res) if kw.get("accumulate") else 0
+                return 2.0 * res.shape[0] * res.shape[1] * Kd, nb(A) + nb(Bm) + nb(res) + acc + extra
             if name == "conv2d_fwd":
                 x, w = a[0], a[1]
-                return 2.0 * res.numel() * w.shape[1] * w.shape[2] * w.shape[3]
+                return 2.0 * res.numel() * w.shape[1] * w.shape[2] * w.shape[3], nb(x) + nb(w) + nb(res) + extra
             if name == "conv2d_dgrad":
                 dy, w = a[0], a[1]
-                return 2.0 * dy.numel() * w.shape[1] * w.shape[2] * w.shape[3]
+                acc = nb(res) if kw.get("accumulate") else 0
+                return 2.0 * dy.numel() * w.shape[1] * w.shape[2] * w.shape[3], nb(dy) + nb(w) + nb(res) + acc
             x, dy, ws = a[0], a[1], a[2]
-            return 2.0 * dy.numel() * ws[1] * ws[2] * ws[3]
+            return 2.0 * dy.numel() * ws[1] * ws[2] * ws[3], nb(x) + nb(dy) + 2 * nb(res)
 
         def wrap(name):
             def f(*a, **kw):
@@ -241,25 +247,55 @@ def run_ours(args):
                 s.record()
                 r = orig[name](*a, **kw)
                 e.record()
-                rec.append((s, e, flops_of(name, a, kw, r)))
+                rec.append((s, e) + cost_of(name, a, kw, r))
                 return r
             return f
+        from passl_b200.core import streams
+        side_was = streams.ENABLED
+        streams.ENABLED = False                         # serial launches: per-launch durations are not inflated by overlap
         for n in orig:
             setattr(K, n, wrap(n))
         step(view_a, view_b)
         torch.cuda.synchronize()
         for n, f in orig.items():
             setattr(K, n, f)
+        streams.ENABLED = side_was
     if rank == 0:
-        tc_ms = sum(s.elapsed_time(e) for s, e, _ in rec)
-        tc_flops = sum(f for _, _, f in rec)
-        ach = tc_flops / (tc_ms / 1e3) / 1e12
-        line["roofline"] = {"kernel": "gemm_tcgen05_kernel (implicit-GEMM conv fwd/dgrad/wgrad + linears)", "bound": "tensor",
-                            "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
-                            "traffic": None, "peak_source": pk["src"] + " (sustained: kernel timed inside a long step)",
-                            "launches": len(rec), "share_of_step": tc_ms / (ms / args.steps),
-                            "flops_per_step": tc_flops,
-                            "note": "sum of algorithmic FLOPs of all %d tcgen05 launches of one step / sum of their CUDA-event durations" % len(rec)}
+        # Every tcgen05 launch is classed by ITS binding roofline: t_tensor = FLOPs / bf16 peak, t_hbm = bytes / HBM peak.
+        # ResNet-50's 1x1 convolutions at 56^2 / 28^2 have < 218 FLOP/B and are HBM-bound even on tensor cores.
+        pk_tf, pk_bw = pk["bf16_sustained"] * 1e12, pk["hbm_gbs"] * 1e9
+        cls = {"tensor": [0.0, 0.0, 0.0, 0], "hbm": [0.0, 0.0, 0.0, 0]}      # ms, flops, bytes, launches
+        t_bind = 0.0
+        for s_, e_, fl, by in rec:
+            dt = s_.elapsed_time(e_)
+            k = "tensor" if fl / pk_tf >= by / pk_bw else "hbm"
+            c = cls[k]
+            c[0] += dt; c[1] += fl; c[2] += by; c[3] += 1
+            t_bind += max(fl / pk_tf, by / pk_bw) * 1e3
+        tc_ms = cls["tensor"][0] + cls["hbm"][0]
+        tc_flops = cls["tensor"][1] + cls["hbm"][1]
+
+        def roof(k):
+            ms_k, fl, by, nl = cls[k]
+            if k == "tensor":
+                ach, peak, unit = fl / (ms_k / 1e3) / 1e12 if ms_k else 0.0, pk["bf16_sustained"], "TFLOP/s"
+            else:
+                ach, peak, unit = by / (ms_k / 1e3) / 1e9 if ms_k else 0.0, pk["hbm_gbs"], "GB/s"
+            return {"kernel": "gemm_tcgen05_kernel (implicit-GEMM conv fwd/dgrad/wgrad + linears), %s-bound launches" % k,
+                    "bound": k, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "traffic": None,
+                    "peak_source": pk["src"], "launches": nl, "share_of_step": ms_k / (ms / args.steps)}
+        dom = "hbm" if cls["hbm"][0] >= cls["tensor"][0] else "tensor"
+        other = "tensor" if dom == "hbm" else "hbm"
+        line["roofline"] = roof(dom)
+        line["roofline"].update({
+            "all_launches": len(rec), "all_share_of_step": tc_ms / (ms / args.steps), "flops_per_step": tc_flops,
+            "all_tflops": tc_flops / (tc_ms / 1e3) / 1e12,
+            "frac_of_binding_roofline_all_launches": t_bind / tc_ms,
+            "note": "one instrumented step (side stream off), CUDA events around each of the %d tcgen05 launches; each launch is "
+                    "classed by its binding roofline (algorithmic FLOPs / bf16 peak vs algorithmic bytes / HBM peak); this object "
+                    "is the class with the larger time share, roofline_other the rest; traffic from profiles/ (ncu --set full)"
+                    % len(rec)})
+        line["roofline_other"] = roof(other)
         # ---- fused InfoNCE (MoCo C3 shape) against the HBM roofline: CUDA-graph replay, events on the capture stream --------
         N, D, Kq, T = 256, 128, 65536, 0.2
         q = torch.nn.functional.normalize(torch.randn(N, D, device=dev), dim=1)

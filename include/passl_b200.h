@@ -220,9 +220,9 @@ int passl_b200_mae_loss_bwd(const void* pred, const float* imgs, const float* ma
  *   eot_gather      replaces text.argmax(-1) + the per-sample Python gather loop (clip.py:307-311): idx int32 [B] (first
  *                   maximum), out[b] = x[b*L + idx[b]].   eot_gather_bwd writes the full dx (zeros elsewhere).
  *   clip_ce         replaces exp(logit_scale), the two logits matmul scalings, both CrossEntropyLoss calls and the
- *                   logit_scale clip (clip.py:316-335, clip_head.py:29-35) on C = I_n T_n^T fp32 [n,n] (n % 4 == 0):
+ *                   logit_scale clip (clip.py:316-335, clip_head.py:29-35) on C = I_n T_n^T fp32, n x n valid in an ld x ld buffer (ld % 4 == 0):
  *                   out3 = {img_loss, text_loss, loss}; logit_scale is read on the device and, if clamp != 0, clipped to
- *                   [-4.6, 4.6] after use.  clip_ce_bwd: dC bf16 [n,n] = d loss / d C, *dlogit_scale += d loss / d logit_scale.
+ *                   [-4.6, 4.6] after use.  clip_ce_bwd: dC bf16 [ld,ld] = d loss / d C (zero in the padding), *dlogit_scale += d loss / d logit_scale.
  *                   The same workspace must be passed to fwd and bwd (it carries s and the row / column LSE).
  * ------------------------------------------------------------------------------------------------------------- */
 int passl_b200_embedding_fwd(const long long* ids, const float* table, const float* pos, void* out, long long T, int L, int D,
@@ -231,10 +231,10 @@ int passl_b200_embedding_bwd(const long long* ids, const void* dout, float* dtab
                              void* stream);
 int passl_b200_eot_gather_fwd(const long long* ids, const void* x, void* out, int* idx, int B, int L, int D, void* stream);
 int passl_b200_eot_gather_bwd(const int* idx, const void* dout, void* dx, int B, int L, int D, void* stream);
-long long passl_b200_clip_ce_workspace_bytes(int n);
-int passl_b200_clip_ce_fwd(const float* C, float* logit_scale, float* out3, int n, int clamp, void* workspace,
+long long passl_b200_clip_ce_workspace_bytes(int ld);
+int passl_b200_clip_ce_fwd(const float* C, float* logit_scale, float* out3, int n, int ld, int clamp, void* workspace,
                            long long workspace_bytes, void* stream);
-int passl_b200_clip_ce_bwd(const float* C, const float* dloss, void* dC, float* dlogit_scale, int n, void* workspace,
+int passl_b200_clip_ce_bwd(const float* C, const float* dloss, void* dC, float* dlogit_scale, int n, int ld, void* workspace,
                            long long workspace_bytes, void* stream);
 /* mean softmax cross entropy on materialised fp32 logits [n,m] with int64 labels — nn.CrossEntropyLoss() as the heads call it
  * with explicit logits (clip_head.py:29-32, contrastive_head.py:52-53).  workspace >= 4*n bytes; row_lse [n] feeds the backward:

@@ -68,8 +68,8 @@ SIGNATURES = {
     "passl_b200_eot_gather_fwd": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),
     "passl_b200_eot_gather_bwd": (c_int, [c_void_p] * 3 + [c_int] * 3 + [c_void_p]),
     "passl_b200_clip_ce_workspace_bytes": (c_ll, [c_int]),
-    "passl_b200_clip_ce_fwd": (c_int, [c_void_p] * 3 + [c_int, c_int, c_void_p, c_ll, c_void_p]),
-    "passl_b200_clip_ce_bwd": (c_int, [c_void_p] * 4 + [c_int, c_void_p, c_ll, c_void_p]),
+    "passl_b200_clip_ce_fwd": (c_int, [c_void_p] * 3 + [c_int, c_int, c_int, c_void_p, c_ll, c_void_p]),
+    "passl_b200_clip_ce_bwd": (c_int, [c_void_p] * 4 + [c_int, c_int, c_void_p, c_ll, c_void_p]),
     "passl_b200_rows_ce_fwd": (c_int, [c_void_p] * 4 + [c_int, c_int, c_void_p, c_ll, c_void_p]),
     "passl_b200_rows_ce_bwd": (c_int, [c_void_p] * 5 + [c_int, c_int, c_void_p]),
     "passl_b200_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),

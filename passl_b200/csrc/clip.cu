@@ -134,15 +134,16 @@ __global__ void eot_scatter_kernel(const int* __restrict__ idx, const __nv_bfloa
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// symmetric cross entropy on C [n, n] fp32 (cosine similarities); logits S = s*C, s = exp(*logit_scale)
-// workspace (floats): [0] s used by this forward, [1..3] pad, [4..4+n) row lse, [4+n..4+2n) col lse, then partials
+// symmetric cross entropy on C fp32 (cosine similarities, n x n valid inside an ld x ld buffer, ld % 4 == 0 — the GEMM pads
+// odd batch sizes); logits S = s*C, s = exp(*logit_scale)
+// workspace (floats): [0] s used by this forward, [1..3] pad, [4..4+ld) row lse, [4+ld..4+2ld) col lse, then partials
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void clip_ce_rows_kernel(const float* __restrict__ C, const float* __restrict__ logit_scale, float* __restrict__ row_lse,
-                                    int n) {
+                                    int n, int ld) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= n) return;
   const float s = __expf(*logit_scale);
-  const float* r = C + (size_t)row * n;
+  const float* r = C + (size_t)row * ld;
   float m = -INFINITY, z = 0.f;
   for (int j = lane; j < n; j += 32) {
     const float v = s * r[j];
@@ -153,15 +154,17 @@ __global__ void clip_ce_rows_kernel(const float* __restrict__ C, const float* __
   for (int o = 16; o > 0; o >>= 1) {
     const float om = __shfl_xor_sync(0xffffffffu, m, o), oz = __shfl_xor_sync(0xffffffffu, z, o);
     const float nm = fmaxf(m, om);
-    z = z * __expf(m - nm) + oz * __expf(om - nm);
-    m = nm;
+    if (nm > -INFINITY) {
+      z = z * __expf(m - nm) + oz * __expf(om - nm);
+      m = nm;
+    }
   }
   if (lane == 0) row_lse[row] = m + __logf(z);
 }
 
 // 32 columns per CTA, 32 row-lanes: coalesced over columns, online max/sum over rows
 __global__ void clip_ce_cols_kernel(const float* __restrict__ C, const float* __restrict__ logit_scale, float* __restrict__ col_lse,
-                                    int n) {
+                                    int n, int ld) {
   __shared__ float sm[32][33], sz[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + tx;
@@ -169,7 +172,7 @@ __global__ void clip_ce_cols_kernel(const float* __restrict__ C, const float* __
   float m = -INFINITY, z = 0.f;
   if (col < n) {
     for (int i = ty; i < n; i += 32) {
-      const float v = s * C[(size_t)i * n + col];
+      const float v = s * C[(size_t)i * ld + col];
       if (v > m) { z = z * __expf(m - v); m = v; }
       z += __expf(v - m);
     }
@@ -193,15 +196,15 @@ __global__ void clip_ce_cols_kernel(const float* __restrict__ C, const float* __
 
 // single CTA: losses = mean(lse - diag); records s and clamps the parameter (clip.py:316-318)
 __global__ void clip_ce_finalize_kernel(const float* __restrict__ C, float* __restrict__ logit_scale, float* __restrict__ ws,
-                                        float* __restrict__ out3, int n, int clamp) {
+                                        float* __restrict__ out3, int n, int ld, int clamp) {
   __shared__ float sa[32], sb[32];
   const float ls = *logit_scale;
   const float s = __expf(ls);
   const float* row_lse = ws + 4;
-  const float* col_lse = ws + 4 + n;
+  const float* col_lse = ws + 4 + ld;
   float a = 0.f, b = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float d = s * C[(size_t)i * n + i];
+    const float d = s * C[(size_t)i * ld + i];
     a += row_lse[i] - d;
     b += col_lse[i] - d;
   }
@@ -216,38 +219,42 @@ __global__ void clip_ce_finalize_kernel(const float* __restrict__ C, float* __re
     out3[1] = Bs / n;          // text_loss
     out3[2] = (A + Bs) / n;    // loss
     ws[0] = s;
-    ws[1] = 0.f;
     if (clamp) *logit_scale = fminf(fmaxf(ls, -4.6f), 4.6f);
   }
 }
 
-// dC = s * dS (bf16), dS = dloss/n * (exp(S-row_lse) + exp(S-col_lse) - 2*[i==j]);  dlogit_scale += sum(dS * S)
+// dC = s * dS (bf16, zero in the padding), dS = dloss/n * (exp(S-row_lse) + exp(S-col_lse) - 2*[i==j]);  dlogit_scale += sum(dS*S)
 __global__ void clip_ce_bwd_kernel(const float* __restrict__ C, const float* __restrict__ ws, const float* __restrict__ dloss,
-                                   __nv_bfloat16* __restrict__ dC, float* __restrict__ part, int n) {
+                                   __nv_bfloat16* __restrict__ dC, float* __restrict__ part, int n, int ld) {
   __shared__ float sred[32];
   const float s = ws[0];
   const float* row_lse = ws + 4;
-  const float* col_lse = ws + 4 + n;
+  const float* col_lse = ws + 4 + ld;
   const float g = (dloss ? *dloss : 1.f) / n;
-  const long long total = (long long)n * n / 4;
+  const int lq = ld / 4;
+  const long long total = (long long)ld * lq;
   float acc = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long e = i * 4;
-    const int r = (int)(e / n), c0 = (int)(e - (long long)r * n);
-    const float4 cv = *reinterpret_cast<const float4*>(C + e);
-    const float4 cl = *reinterpret_cast<const float4*>(col_lse + c0);
-    const float rl = row_lse[r];
-    const float v[4] = {cv.x, cv.y, cv.z, cv.w};
-    const float l[4] = {cl.x, cl.y, cl.z, cl.w};
-    float d[4];
+    const int r = (int)(i / lq), c0 = (int)(i - (long long)r * lq) * 4;
+    const long long e = (long long)r * ld + c0;
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < n && c0 < n) {
+      const float4 cv = *reinterpret_cast<const float4*>(C + e);
+      const float4 cl = *reinterpret_cast<const float4*>(col_lse + c0);
+      const float rl = row_lse[r];
+      const float v[4] = {cv.x, cv.y, cv.z, cv.w};
+      const float l[4] = {cl.x, cl.y, cl.z, cl.w};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float S = s * v[k];
-      float ds = __expf(S - rl) + __expf(S - l[k]);
-      if (c0 + k == r) ds -= 2.f;
-      ds *= g;
-      acc += ds * S;
-      d[k] = s * ds;
+      for (int k = 0; k < 4; ++k) {
+        if (c0 + k < n) {
+          const float S = s * v[k];
+          float ds = __expf(S - rl) + __expf(S - l[k]);
+          if (c0 + k == r) ds -= 2.f;
+          ds *= g;
+          acc += ds * S;
+          d[k] = s * ds;
+        }
+      }
     }
     uint2 o;
     o.x = pack_bf16x2(d[0], d[1]);
@@ -384,33 +391,33 @@ extern "C" int passl_b200_eot_gather_bwd(const int* idx, const void* dout, void*
   return 0;
 }
 
-extern "C" long long passl_b200_clip_ce_workspace_bytes(int n) { return (4LL + 2LL * n + kClipBwdBlocks) * 4; }
+extern "C" long long passl_b200_clip_ce_workspace_bytes(int ld) { return (4LL + 2LL * ld + kClipBwdBlocks) * 4; }
 
-extern "C" int passl_b200_clip_ce_fwd(const float* C, float* logit_scale, float* out3, int n, int clamp, void* workspace,
+extern "C" int passl_b200_clip_ce_fwd(const float* C, float* logit_scale, float* out3, int n, int ld, int clamp, void* workspace,
                                       long long workspace_bytes, void* stream) {
-  if (n <= 0 || n % 4 || !C || !logit_scale || !out3) return PB_ERR_BAD_ARG;
-  if (workspace_bytes < passl_b200_clip_ce_workspace_bytes(n)) return PB_ERR_WORKSPACE;
+  if (n <= 0 || ld < n || ld % 4 || !C || !logit_scale || !out3) return PB_ERR_BAD_ARG;
+  if (workspace_bytes < passl_b200_clip_ce_workspace_bytes(ld)) return PB_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   float* ws = reinterpret_cast<float*>(workspace);
-  clip_ce_rows_kernel<<<(n + 7) / 8, 256, 0, st>>>(C, logit_scale, ws + 4, n);
+  clip_ce_rows_kernel<<<(n + 7) / 8, 256, 0, st>>>(C, logit_scale, ws + 4, n, ld);
   PB_LAUNCH_CHECK();
-  clip_ce_cols_kernel<<<(n + 31) / 32, 1024, 0, st>>>(C, logit_scale, ws + 4 + n, n);
+  clip_ce_cols_kernel<<<(n + 31) / 32, 1024, 0, st>>>(C, logit_scale, ws + 4 + ld, n, ld);
   PB_LAUNCH_CHECK();
-  clip_ce_finalize_kernel<<<1, 256, 0, st>>>(C, logit_scale, ws, out3, n, clamp);
+  clip_ce_finalize_kernel<<<1, 256, 0, st>>>(C, logit_scale, ws, out3, n, ld, clamp);
   PB_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int passl_b200_clip_ce_bwd(const float* C, const float* dloss, void* dC, float* dlogit_scale, int n, void* workspace,
-                                      long long workspace_bytes, void* stream) {
-  if (n <= 0 || n % 4 || !C || !dC) return PB_ERR_BAD_ARG;
-  if (workspace_bytes < passl_b200_clip_ce_workspace_bytes(n)) return PB_ERR_WORKSPACE;
+extern "C" int passl_b200_clip_ce_bwd(const float* C, const float* dloss, void* dC, float* dlogit_scale, int n, int ld,
+                                      void* workspace, long long workspace_bytes, void* stream) {
+  if (n <= 0 || ld < n || ld % 4 || !C || !dC) return PB_ERR_BAD_ARG;
+  if (workspace_bytes < passl_b200_clip_ce_workspace_bytes(ld)) return PB_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   float* ws = reinterpret_cast<float*>(workspace);
-  float* part = ws + 4 + 2 * (size_t)n;
-  long long want = ((long long)n * n / 4 + 255) / 256;
+  float* part = ws + 4 + 2 * (size_t)ld;
+  long long want = ((long long)ld * ld / 4 + 255) / 256;
   const int nblk = (int)(want < kClipBwdBlocks ? want : kClipBwdBlocks);
-  clip_ce_bwd_kernel<<<nblk, 256, 0, st>>>(C, ws, dloss, reinterpret_cast<__nv_bfloat16*>(dC), part, n);
+  clip_ce_bwd_kernel<<<nblk, 256, 0, st>>>(C, ws, dloss, reinterpret_cast<__nv_bfloat16*>(dC), part, n, ld);
   PB_LAUNCH_CHECK();
   if (dlogit_scale) {
     clip_ce_bwd_finalize_kernel<<<1, 256, 0, st>>>(part, nblk, dlogit_scale);

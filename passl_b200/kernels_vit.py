@@ -152,25 +152,28 @@ def eot_gather_bwd(idx, dout, L):
     return dx
 
 
-def clip_ce_fwd(C, logit_scale, clamp=True):
-    """C fp32 [n, n] cosine similarities, logit_scale fp32 [1] (log domain, read + clamped on the device)
+def clip_ce_fwd(C, logit_scale, n=None, clamp=True):
+    """C fp32 [ld, ld] cosine similarities (top-left n x n valid), logit_scale fp32 [1] (log domain, read + clamped on the device)
     -> (out3 fp32 [3] = img_loss, text_loss, loss; workspace to hand to clip_ce_bwd)."""
     _need_cuda(C)
     lib = _lib.load()
-    n = C.shape[0]
-    assert C.dtype == torch.float32 and C.is_contiguous() and C.shape == (n, n) and logit_scale.dtype == torch.float32
-    wsb = lib.passl_b200_clip_ce_workspace_bytes(n)
+    ld = C.shape[0]
+    n = ld if n is None else n
+    assert C.dtype == torch.float32 and C.is_contiguous() and C.shape == (ld, ld) and logit_scale.dtype == torch.float32
+    wsb = lib.passl_b200_clip_ce_workspace_bytes(ld)
     ws = torch.empty(wsb, dtype=torch.uint8, device=C.device)
     out3 = torch.empty(3, dtype=torch.float32, device=C.device)
-    _lib.check(lib.passl_b200_clip_ce_fwd(_ptr(C), _ptr(logit_scale), _ptr(out3), n, int(clamp), _ptr(ws), wsb, _stream()), "clip_ce_fwd")
+    _lib.check(lib.passl_b200_clip_ce_fwd(_ptr(C), _ptr(logit_scale), _ptr(out3), n, ld, int(clamp), _ptr(ws), wsb, _stream()),
+               "clip_ce_fwd")
     return out3, ws
 
 
-def clip_ce_bwd(C, ws, dloss=None, dlogit_scale=None):
-    """-> dC bf16 [n, n]; accumulates d loss / d logit_scale into dlogit_scale (fp32 [1])."""
+def clip_ce_bwd(C, ws, n=None, dloss=None, dlogit_scale=None):
+    """-> dC bf16 [ld, ld] (zero outside n x n); accumulates d loss / d logit_scale into dlogit_scale (fp32 [1])."""
     lib = _lib.load()
-    n = C.shape[0]
-    dC = torch.empty((n, n), dtype=torch.bfloat16, device=C.device)
-    _lib.check(lib.passl_b200_clip_ce_bwd(_ptr(C), _ptr(dloss), _ptr(dC), _ptr(dlogit_scale), n, _ptr(ws), ws.numel(), _stream()),
+    ld = C.shape[0]
+    n = ld if n is None else n
+    dC = torch.empty((ld, ld), dtype=torch.bfloat16, device=C.device)
+    _lib.check(lib.passl_b200_clip_ce_bwd(_ptr(C), _ptr(dloss), _ptr(dC), _ptr(dlogit_scale), n, ld, _ptr(ws), ws.numel(), _stream()),
                "clip_ce_bwd")
     return dC

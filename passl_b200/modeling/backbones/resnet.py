@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 
 from ... import kernels as K
+from ...core.streams import join
 from ...core.param_store import compute_copy, grad_buffer
 from ...nn.layers import BatchNormState, ConvBN, _kaiming_normal_fan_out
 from ..registry import BACKBONES
@@ -157,6 +158,7 @@ class ResNet(nn.Module):
         for blk, c in zip(reversed(self.blocks), reversed(ctxs)):
             d = blk.bwd(c, d)
         self.stem.bwd(cs, d)
+        join()          # the weight-gradient GEMMs ran on the side stream (core/streams.py)
 
     def forward(self, img):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):

@@ -23,7 +23,7 @@ from ..nn.layers import Linear
 from .vision_transformer import Block, LayerNorm, PatchEmbed, _linear_bwd
 
 
-def _trunc_normal_(t, std=1.0):
+def _trunc_normal_(t, std=0.02):       # vision_transformer.py(v110):31  TruncatedNormal(std=0.02)
     nn.init.trunc_normal_(t, mean=0.0, std=std, a=-2.0, b=2.0)
 
 
@@ -160,27 +160,39 @@ class CLIPTextTransformer(_Tower):
         V.embedding_bwd(text, d, dtable=grad_buffer(self.token_embedding), dpos=grad_buffer(self.positional_embedding))
 
 
+def _pad_rows(x, n_pad):
+    if x.shape[0] == n_pad:
+        return x
+    out = torch.zeros((n_pad, x.shape[1]), dtype=x.dtype, device=x.device)
+    out[:x.shape[0]].copy_(x)
+    return out
+
+
 class _ClipLossFn(torch.autograd.Function):
-    """normalise -> C = I_n T_n^T (tcgen05 GEMM, fp32) -> symmetric CE with exp(logit_scale) applied on the device."""
+    """normalise -> C = I_n T_n^T (tcgen05 GEMM, fp32) -> symmetric CE with exp(logit_scale) applied on the device.
+    Batches that are not a multiple of 8 are zero-padded for the GEMM; the CE kernels only see the valid n x n block."""
 
     @staticmethod
     def forward(ctx, img_f, txt_f, logit_scale, clamp):
+        n = img_f.shape[0]
+        n_pad = (n + 7) // 8 * 8
         _, ib, iinv = K.l2norm_fwd(img_f.contiguous(), mode="clip", want_bf16=True)
         _, tb, tinv = K.l2norm_fwd(txt_f.contiguous(), mode="clip", want_bf16=True)
-        C = K.gemm(ib, tb, out_dtype=torch.float32)                       # [n, n] cosine similarities
-        out3, ws = V.clip_ce_fwd(C, logit_scale.data, clamp=clamp)
-        ctx.saved = (ib, tb, iinv, tinv, C, ws, logit_scale)
+        ibp, tbp = _pad_rows(ib, n_pad), _pad_rows(tb, n_pad)
+        C = K.gemm(ibp, tbp, out_dtype=torch.float32)                     # [n_pad, n_pad] cosine similarities
+        out3, ws = V.clip_ce_fwd(C, logit_scale.data, n=n, clamp=clamp)
+        ctx.saved = (ib, tb, ibp, tbp, iinv, tinv, C, ws, logit_scale, n)
         return out3[0], out3[1], out3[2]
 
     @staticmethod
     def backward(ctx, d_img, d_txt, d_loss):
         # img_loss / text_loss are reported values (clip_head.py:33-34); the training signal is d(loss)
-        ib, tb, iinv, tinv, C, ws, logit_scale = ctx.saved
+        ib, tb, ibp, tbp, iinv, tinv, C, ws, logit_scale, n = ctx.saved
         ctx.saved = None
         dls = grad_buffer(logit_scale) if logit_scale.requires_grad else None
-        dC = V.clip_ce_bwd(C, ws, dloss=d_loss.contiguous().float().reshape(1), dlogit_scale=dls)
-        dI_n = K.gemm(dC, tb, b_t=True, out_dtype=torch.float32)          # dC   @ T_n
-        dT_n = K.gemm(dC, ib, a_t=True, b_t=True, out_dtype=torch.float32)  # dC^T @ I_n
+        dC = V.clip_ce_bwd(C, ws, n=n, dloss=d_loss.contiguous().float().reshape(1), dlogit_scale=dls)
+        dI_n = K.gemm(dC, tbp, b_t=True, out_dtype=torch.float32)[:n]               # dC   @ T_n
+        dT_n = K.gemm(dC, ibp, a_t=True, b_t=True, out_dtype=torch.float32)[:n]     # dC^T @ I_n
         yi = torch.empty(ib.shape, dtype=torch.float32, device=ib.device)
         yt = torch.empty(tb.shape, dtype=torch.float32, device=tb.device)
         K.cast_f32(ib, yi)

@@ -15,6 +15,7 @@ import torch.nn as nn
 
 from .. import kernels as K
 from ..core.param_store import compute_copy, grad_buffer
+from ..core.streams import side_stream
 
 
 def _kaiming_normal_fan_out(w, fan_out):
@@ -79,8 +80,9 @@ class ConvBN(nn.Module):
                                dgamma=grad_buffer(bn.weight) if train_bn else None,
                                dbeta=grad_buffer(bn.bias) if train_bn else None)
         if self.weight.requires_grad:
-            K.conv2d_wgrad(x, dy, tuple(self.weight.shape), stride=self.stride, pad=self.pad,
-                           out=grad_buffer(self.weight), accumulate=True)
+            with side_stream(x, dy):      # off the dgrad critical path: overlaps the next unit's HBM-bound BN backward
+                K.conv2d_wgrad(x, dy, tuple(self.weight.shape), stride=self.stride, pad=self.pad,
+                               out=grad_buffer(self.weight), accumulate=True)
         dx = None
         if need_dx:
             dx = K.conv2d_dgrad(dy, compute_copy(self.weight), tuple(x.shape), stride=self.stride, pad=self.pad,

@@ -77,9 +77,9 @@ def test_logits_cross_entropy_reference_signature():
     b = torch.tensor(tl, dtype=torch.float32, device="cuda", requires_grad=True)
     lab = torch.arange(n, device="cuda")
     out = CLIPHead()(a, b, lab, lab)
-    np.testing.assert_allclose(out["img_loss"].item(), float(G["clip_img_loss"]), rtol=1e-5)
-    np.testing.assert_allclose(out["text_loss"].item(), float(G["clip_text_loss"]), rtol=1e-5)
-    np.testing.assert_allclose(out["loss"].item(), float(G["clip_loss"]), rtol=1e-5)
+    np.testing.assert_allclose(out["img_loss"].item(), float(G["clip_img_loss"]), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(out["text_loss"].item(), float(G["clip_text_loss"]), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(out["loss"].item(), float(G["clip_loss"]), rtol=1e-4, atol=1e-6)
     out["loss"].backward()
     a64 = torch.tensor(il, dtype=torch.float64, requires_grad=True)
     torch.nn.functional.cross_entropy(a64, torch.arange(n)).backward()

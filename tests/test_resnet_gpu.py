@@ -99,6 +99,8 @@ def test_bottleneck_fwd_bwd_vs_oracle(inpl, planes, stride, ds):
     for p in blk.parameters():
         p.grad = torch.zeros_like(p)
     dx = blk.bwd(ctx, dout)
+    from passl_b200.core.streams import join
+    join()
     torch.cuda.synchronize()
     p = O.params_from_cuda_module(blk)
     p = {"b." + k: v.requires_grad_(True) for k, v in p.items()}
@@ -129,6 +131,8 @@ def test_stem_fwd_bwd_vs_oracle():
     for p_ in stem.parameters():
         p_.grad = torch.zeros_like(p_)
     stem.bwd(ctx, dout)
+    from passl_b200.core.streams import join
+    join()
     torch.cuda.synchronize()
     w = stem.weight.detach().float().cpu()[:, :147].reshape(64, 7, 7, 3).bfloat16().double().permute(0, 3, 1, 2).contiguous()
     p = {"stem.weight": w.requires_grad_(True),
