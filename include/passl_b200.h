@@ -40,8 +40,12 @@ long long passl_b200_launch_counter_add(long long n);
  *   A: a_mn_major==0 -> [M,K] row-major (lda);  ==1 -> [K,M] row-major (lda)      bf16
  *   B: b_mn_major==0 -> [N,K] row-major (ldb);  ==1 -> [K,N] row-major (ldb)      bf16
  *   out: bf16 (out_fp32==0) or fp32; atomic_add (fp32 only) accumulates with red.add (needed for splits>1)
- *   col_sum / col_sqsum: optional fp32 [N] accumulators of per-column sum / sum of squares of the stored values
+ *   col_sum: optional fp32 [gemm_stats_rows()][2][N] per-CTA partials of the per-column sum / sum of squares of the stored bf16
+ *            values (BatchNorm batch statistics fused into the producing GEMM: bf16 out, splits == 1); zeroed and filled by the
+ *            call, row b written only by CTA b (no atomics); feed it to bn_finalize with nblk = gemm_stats_rows().
+ *            col_sqsum is reserved (pass NULL).
  * ------------------------------------------------------------------------------------------------------------- */
+int passl_b200_gemm_stats_rows(void);
 int passl_b200_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K, int a_mn_major,
                          int b_mn_major, long long lda, long long ldb, long long ldc, int out_fp32, int atomic_add,
                          const float* bias, const void* residual, int act, float alpha, int splits, float* col_sum,
@@ -138,7 +142,7 @@ int passl_b200_cast_bf16_to_f32(const void* x, float* y, long long n, void* stre
  * running = momentum*running + (1-momentum)*batch (momentum 0.9), biased batch variance.
  *   bn_reduce_blocks : nblk = number of per-CTA partials the two reduce kernels write for a [P, C] tensor
  *   bn_stats      : part[b][0][c] = sum_p y, part[b][1][c] = sum_p y^2 over the rows of CTA b (fp32 [nblk,2,C]; no atomics,
- *                   deterministic; a [1,2,C] buffer filled by the GEMM/conv col_sum/col_sqsum epilogue is also accepted)
+ *                   deterministic); the GEMM / conv forward can emit the same partials from its epilogue (col_sum, gemm_stats_rows() rows)
  *   bn_finalize   : sums the partials -> mean, invstd, scale = gamma*invstd, shift = beta - mean*scale, running stats
  *   bn_apply      : z = relu?(y*scale + shift + residual)  (bf16 and/or fp32 output)
  *   bn_bwd_reduce : partials of sum_g = sum_p g, sum_gx = sum_p g*xhat with g = dz * (z>0 if relu)

@@ -16,6 +16,7 @@ SIGNATURES = {
     "passl_b200_version": (c_int, []),
     "passl_b200_launch_count": (c_ll, []),
     "passl_b200_launch_counter_add": (c_ll, [c_ll]),
+    "passl_b200_gemm_stats_rows": (c_int, []),
     "passl_b200_gemm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll,
                                      c_int, c_int, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p, c_void_p,
                                      c_void_p]),

@@ -26,6 +26,12 @@ enum OperandMode : int {
 enum ActMode : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_QUICKGELU = 3 };
 
 constexpr int kMaxTaps = 12;
+constexpr int kEpiWarps = 8;                       // epilogue warps (2 per TMEM lane quarter)
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
+constexpr int kEpiStride = 80;                     // bytes per staged row: 32 bf16 + 16 B pad (conflict-free 16 B accesses)
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory"); }
+
 
 struct PatchGeom {
   int TN, TH, TW;    // patch box: images x rows x cols  (TN*TH*TW <= 128)
@@ -67,9 +73,10 @@ struct GemmParams {
   const __nv_bfloat16* aux;     // same addressing as out
   int aux_mode;
   __nv_bfloat16* preact;        // optional: value before the activation (bias added), same addressing as out (GELU backward)
-  // optional per-column statistics of the stored value (BatchNorm batch stats): sum and sum of squares
+  // optional per-column statistics of the stored bf16 value (BatchNorm batch stats): per-CTA partials [gridDim.x][2][N]
+  // (sum, sum of squares), zero-initialised by the host; CTA b only ever touches row b -> no atomics, deterministic per grid
   float* col_sum;
-  float* col_sqsum;
+  float* col_sqsum;     // unused (kept for ABI stability of the struct users)
 };
 
 template <int BN, int BK, bool A_MN, bool B_MN>
@@ -82,7 +89,9 @@ struct GemmSmem {
   static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+  static constexpr int EPI_BYTES = kEpiWarps * 32 * kEpiStride;          // per-warp staging tiles of the epilogue
+  static constexpr int STAT_BYTES = 2 * BN * 4;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + STAT_BYTES + 1024;  // + alignment slack
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 };
 
@@ -133,7 +142,7 @@ __device__ __forceinline__ void issue_operand_load(const GemmOperand& op, const 
 }
 
 template <int BN, int BK, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   using S = GemmSmem<BN, BK, A_MN, B_MN>;
   constexpr int STAGES = S::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -143,6 +152,8 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint8_t* epi_stage = smem + STAGES * S::STAGE_BYTES + S::BAR_BYTES;              // 8 warps x 32 rows x kEpiStride
+  float* epi_stats = reinterpret_cast<float*>(epi_stage + S::EPI_BYTES);             // [2][BN] column sum / sum of squares
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
@@ -163,7 +174,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -291,8 +302,24 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
       }
     }
   } else {
-    // ================= epilogue warps (2..5) =================
-    const uint32_t q = warp & 3;  // TMEM lane quarter this warp may access
+    // ================= epilogue warps (2..9) =================
+    // Eight warps: warp w may only touch TMEM lanes 32*(w%4).., so two warps share each lane quarter and split the 32-column
+    // chunks of the accumulator between them (chunk & 1 == half).  bf16 outputs are staged through a padded per-warp smem
+    // tile so that global stores (and residual loads) are row-coalesced 64 B segments issued 8 rows per instruction instead
+    // of 32 different rows per instruction — the epilogue of the K-small 1x1 convolutions is LSU-wavefront bound otherwise.
+    const uint32_t e = warp - 2;
+    const uint32_t q = warp & 3;
+    const uint32_t half = e >> 2;
+    uint8_t* stg = epi_stage + e * (32 * kEpiStride);
+    const uint32_t stg_u32 = smem_u32(stg);
+    const bool staged = !p.out_fp32;
+    const bool do_stats = staged && p.col_sum != nullptr;
+    const int etid = (int)(e * 32 + lane);
+    if (do_stats) {
+      for (int i = etid; i < 2 * BN; i += 256) epi_stats[i] = 0.f;
+      epi_bar_sync();
+    }
+    int prev_nblk = -1;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       int rest = tile / p.splits;
@@ -320,6 +347,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
         row_ok = m < p.M;
         row_off = (long long)m * p.ldc;
       }
+      const long long row_off_pub = row_ok ? row_off : -1;   // what the other lanes see through shuffles
       int col0 = n_blk * BN;
       int col_lim = p.N;  // exclusive bound on the logical column index
       long long col_base = col0;
@@ -330,18 +358,43 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
         col_lim = p.n_per_tap;
         col_base = (long long)tap * p.n_per_tap + c0;
       }
+      if (do_stats && n_blk != prev_nblk) {
+        if (prev_nblk >= 0) {           // this CTA moves to another column block: fold its partial sums into its global row
+          epi_bar_sync();
+          float* part = p.col_sum + (size_t)blockIdx.x * 2 * p.N;
+          for (int i = etid; i < BN; i += 256) {
+            const int col = prev_nblk * BN + i;
+            if (col < p.N) { part[col] += epi_stats[i]; part[p.N + col] += epi_stats[BN + i]; }
+            epi_stats[i] = 0.f;
+            epi_stats[BN + i] = 0.f;
+          }
+          epi_bar_sync();
+        }
+        prev_nblk = n_blk;
+      }
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((q * 32u) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_addr + c * 32, v);
-        tmem_ld_wait();
+      for (int c = (int)half; c < BN / 32; c += 2) {
         const int cc0 = col0 + c * 32;           // logical column of v[0] (within tap)
         const long long oc0 = col_base + c * 32; // output column of v[0]
         if (cc0 >= col_lim) break;
+        uint32_t v[32];
+        tmem_ld_32x32(t_addr + c * 32, v);
+        // residual: row-coalesced loads (8 rows x 64 B per instruction) issued before waiting for the TMEM read
+        const int crow = (int)(lane >> 2), cch = (int)(lane & 3);
+        uint4 rr[4];
+        if (staged && p.residual) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const long long ro = __shfl_sync(0xffffffffu, row_off_pub, i * 8 + crow);
+            rr[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (ro >= 0 && cc0 + cch * 8 < col_lim) rr[i] = ld_nc_v4(p.residual + ro + oc0 + cch * 8);
+          }
+        }
+        tmem_ld_wait();
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
@@ -377,43 +430,30 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
               float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
               a[0] = a0.x; a[1] = a0.y; a[2] = a1.x; a[3] = a1.y; a[4] = a2.x; a[5] = a2.y; a[6] = a3.x; a[7] = a3.y;
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                float& v = f[j8 * 8 + e];
-                if (p.aux_mode == 1) v = a[e] > 0.f ? v : 0.f;
-                else if (p.aux_mode == 2) v *= 0.5f * (1.f + erff(a[e] * 0.70710678118654752f)) + a[e] * 0.3989422804014327f * __expf(-0.5f * a[e] * a[e]);
-                else { float sg = 1.f / (1.f + __expf(-1.702f * a[e])); v *= sg * (1.f + 1.702f * a[e] * (1.f - sg)); }
+              for (int ee = 0; ee < 8; ++ee) {
+                float& vv = f[j8 * 8 + ee];
+                if (p.aux_mode == 1) vv = a[ee] > 0.f ? vv : 0.f;
+                else if (p.aux_mode == 2) vv *= 0.5f * (1.f + erff(a[ee] * 0.70710678118654752f)) + a[ee] * 0.3989422804014327f * __expf(-0.5f * a[ee] * a[ee]);
+                else { float sg = 1.f / (1.f + __expf(-1.702f * a[ee])); vv *= sg * (1.f + 1.702f * a[ee] * (1.f - sg)); }
               }
             }
           }
         }
-        if (p.residual && row_ok) {
-          const __nv_bfloat16* rp = p.residual + row_off + oc0;
+        if (!staged) {
+          // fp32 outputs (split-K / wgrad accumulation, fp32 features): direct per-row path
+          if (p.residual && row_ok) {
+            const __nv_bfloat16* rp = p.residual + row_off + oc0;
 #pragma unroll
-          for (int j8 = 0; j8 < 4; ++j8) {
-            if (cc0 + j8 * 8 < col_lim) {
-              uint4 u = *reinterpret_cast<const uint4*>(rp + j8 * 8);
-              float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
-              f[j8 * 8 + 0] += a0.x; f[j8 * 8 + 1] += a0.y; f[j8 * 8 + 2] += a1.x; f[j8 * 8 + 3] += a1.y;
-              f[j8 * 8 + 4] += a2.x; f[j8 * 8 + 5] += a2.y; f[j8 * 8 + 6] += a3.x; f[j8 * 8 + 7] += a3.y;
+            for (int j8 = 0; j8 < 4; ++j8) {
+              if (cc0 + j8 * 8 < col_lim) {
+                uint4 u = *reinterpret_cast<const uint4*>(rp + j8 * 8);
+                float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+                f[j8 * 8 + 0] += a0.x; f[j8 * 8 + 1] += a0.y; f[j8 * 8 + 2] += a1.x; f[j8 * 8 + 3] += a1.y;
+                f[j8 * 8 + 4] += a2.x; f[j8 * 8 + 5] += a2.y; f[j8 * 8 + 6] += a3.x; f[j8 * 8 + 7] += a3.y;
+              }
             }
           }
-        }
-        if (p.col_sum) {
-          // per-column batch statistics of the value that will be stored (rounded to bf16 if bf16 out)
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = row_ok ? f[j] : 0.f;
-            if (!p.out_fp32) x = __bfloat162float(__float2bfloat16_rn(x));
-            float s = warp_sum(x);
-            float s2 = warp_sum(x * x);
-            if (lane == j && cc0 + j < col_lim) {
-              red_add_f32(p.col_sum + oc0 + j, s);
-              red_add_f32(p.col_sqsum + oc0 + j, s2);
-            }
-          }
-        }
-        if (row_ok) {
-          if (p.out_fp32) {
+          if (row_ok) {
             float* op = reinterpret_cast<float*>(p.out) + row_off + oc0;
             if (p.atomic_add) {
 #pragma unroll
@@ -425,24 +465,69 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
                 if (cc0 + j4 * 4 < col_lim)
                   *reinterpret_cast<float4*>(op + j4 * 4) = make_float4(f[j4 * 4], f[j4 * 4 + 1], f[j4 * 4 + 2], f[j4 * 4 + 3]);
             }
-          } else {
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + row_off + oc0;
+          }
+          continue;
+        }
+        // ---- staged bf16 path ----
+        if (p.residual) {
 #pragma unroll
-            for (int j8 = 0; j8 < 4; ++j8)
-              if (cc0 + j8 * 8 < col_lim) {
-                uint4 u;
-                u.x = pack_bf16x2(f[j8 * 8 + 0], f[j8 * 8 + 1]);
-                u.y = pack_bf16x2(f[j8 * 8 + 2], f[j8 * 8 + 3]);
-                u.z = pack_bf16x2(f[j8 * 8 + 4], f[j8 * 8 + 5]);
-                u.w = pack_bf16x2(f[j8 * 8 + 6], f[j8 * 8 + 7]);
-                *reinterpret_cast<uint4*>(op + j8 * 8) = u;
-              }
+          for (int i = 0; i < 4; ++i) st_shared_v4(stg_u32 + (i * 8 + crow) * kEpiStride + cch * 16, rr[i]);
+          __syncwarp();
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            const uint4 u = ld_shared_v4(stg_u32 + lane * kEpiStride + j8 * 16);
+            float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+            f[j8 * 8 + 0] += a0.x; f[j8 * 8 + 1] += a0.y; f[j8 * 8 + 2] += a1.x; f[j8 * 8 + 3] += a1.y;
+            f[j8 * 8 + 4] += a2.x; f[j8 * 8 + 5] += a2.y; f[j8 * 8 + 6] += a3.x; f[j8 * 8 + 7] += a3.y;
+          }
+          __syncwarp();
+        }
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+          uint4 u = make_uint4(0u, 0u, 0u, 0u);                 // rows outside the tensor contribute zeros to the statistics
+          if (row_ok) {
+            u.x = pack_bf16x2(f[j8 * 8 + 0], f[j8 * 8 + 1]);
+            u.y = pack_bf16x2(f[j8 * 8 + 2], f[j8 * 8 + 3]);
+            u.z = pack_bf16x2(f[j8 * 8 + 4], f[j8 * 8 + 5]);
+            u.w = pack_bf16x2(f[j8 * 8 + 6], f[j8 * 8 + 7]);
+          }
+          st_shared_v4(stg_u32 + lane * kEpiStride + j8 * 16, u);
+        }
+        __syncwarp();
+        if (do_stats) {
+          // per-column batch statistics of the bf16 values being stored: lane = column, 32 rows from the staged tile
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+          for (int rr_ = 0; rr_ < 32; ++rr_) {
+            const float x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(stg + rr_ * kEpiStride + lane * 2));
+            s1 += x;
+            s2 = fmaf(x, x, s2);
+          }
+          if (cc0 + (int)lane < col_lim) {
+            atomicAdd(&epi_stats[c * 32 + lane], s1);
+            atomicAdd(&epi_stats[BN + c * 32 + lane], s2);
           }
         }
+        __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const long long ro = __shfl_sync(0xffffffffu, row_off_pub, i * 8 + crow);
+          if (ro >= 0 && cc0 + cch * 8 < col_lim)
+            *reinterpret_cast<uint4*>(outp + ro + oc0 + cch * 8) = ld_shared_v4(stg_u32 + (i * 8 + crow) * kEpiStride + cch * 16);
+        }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+    if (do_stats && prev_nblk >= 0) {
+      epi_bar_sync();
+      float* part = p.col_sum + (size_t)blockIdx.x * 2 * p.N;
+      for (int i = etid; i < BN; i += 256) {
+        const int col = prev_nblk * BN + i;
+        if (col < p.N) { part[col] += epi_stats[i]; part[p.N + col] += epi_stats[BN + i]; }
+      }
     }
   }
 

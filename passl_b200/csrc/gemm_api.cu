@@ -19,7 +19,11 @@ static int launch_gemm_t(const GemmParams& p, cudaStream_t st) {
   int tiles = p.m_blocks * p.n_blocks * p.splits;
   int grid = tiles < num_sms() ? tiles : num_sms();
   if (grid <= 0) return PB_OK;
-  kern<<<grid, 192, S::TOTAL, st>>>(p);
+  if (p.col_sum) {
+    if (p.out_fp32 || p.n_blocks_per_tap > 0 || p.splits != 1) return PB_ERR_UNSUPPORTED;
+    PB_CUDA_CHECK(cudaMemsetAsync(p.col_sum, 0, (size_t)num_sms() * 2 * p.N * sizeof(float), st));
+  }
+  kern<<<grid, kGemmThreads, S::TOTAL, st>>>(p);
   PB_LAUNCH_CHECK();
   return PB_OK;
 }
@@ -158,6 +162,8 @@ extern "C" int passl_b200_gemm_bf16_ex(const void* A, const void* B, void* out, 
   p.preact = reinterpret_cast<__nv_bfloat16*>(preact_out);
   return launch_gemm(p, BN, 64, a_mn_major != 0, b_mn_major != 0, (cudaStream_t)stream);
 }
+
+extern "C" int passl_b200_gemm_stats_rows(void) { return num_sms(); }
 
 // ==============================================================================================
 // Convolution forward (implicit GEMM), NHWC bf16, weights [Cout, R, S, Cin] bf16.

@@ -58,9 +58,7 @@ def gemm(a, b, *, a_t=False, b_t=False, out=None, out_dtype=torch.bfloat16, bias
         out = (torch.zeros if (accumulate or splits > 1) else torch.empty)((M, N), dtype=out_dtype, device=a.device)
     out_fp32 = out.dtype == torch.float32
     atomic = 1 if (accumulate or splits > 1) else 0
-    cs = cq = None
-    if col_stats is not None:
-        cs, cq = col_stats
+    cs, cq = col_stats, None          # col_stats: fp32 [gemm_stats_rows(), 2, N] partials buffer (see stats_buffer)
     aux_mode = 0
     if aux is not None:
         aux_mode = {"relu_mask": 1, "gelu_grad": 2, "quick_gelu_grad": 3}[aux_mode_name]
@@ -71,6 +69,12 @@ def gemm(a, b, *, a_t=False, b_t=False, out=None, out_dtype=torch.bfloat16, bias
                                        _stream())
     _lib.check(code, "gemm_bf16")
     return out
+
+
+def stats_buffer(C, device):
+    """Partials buffer for BatchNorm statistics fused into the producing GEMM / conv epilogue: [rows, 2, C] fp32."""
+    rows = _lib.load().passl_b200_gemm_stats_rows()
+    return torch.empty((rows, 2, C), dtype=torch.float32, device=device)
 
 
 def wgrad_splits(M, N, K):
@@ -93,9 +97,7 @@ def conv2d_fwd(x, w, stride=1, pad=0, bias=None, residual=None, act=None, col_st
     Wo = (W + 2 * pad - S) // stride + 1
     if out is None:
         out = torch.empty((N, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.device)
-    cs = cq = None
-    if col_stats is not None:
-        cs, cq = col_stats
+    cs, cq = col_stats, None          # fp32 [gemm_stats_rows(), 2, Cout] partials buffer (see stats_buffer)
     code = lib.passl_b200_conv2d_fwd_bf16(_ptr(x), _ptr(w), _ptr(out), N, H, W, Cin, Cout, R, S, stride, pad, _ptr(bias),
                                           _ptr(residual), ACT[act], _ptr(cs), _ptr(cq), _stream())
     _lib.check(code, "conv2d_fwd_bf16")

@@ -59,9 +59,10 @@ class ConvBN(nn.Module):
         bn = self.bn
         batch_stats = training and not bn.use_global_stats
         if batch_stats:
-            y = K.conv2d_fwd(x, w, stride=self.stride, pad=self.pad)
+            # batch statistics come out of the conv epilogue (per-CTA partials of the bf16 values it stores): no extra pass over y
+            stats = K.stats_buffer(self.cout, x.device)
+            y = K.conv2d_fwd(x, w, stride=self.stride, pad=self.pad, col_stats=stats)
             count = y.numel() // self.cout
-            stats = K.bn_stats(y.view(count, self.cout))
             msss = K.bn_finalize(stats, bn.weight, bn.bias, bn._mean, bn._variance, count, eps=bn.eps, momentum=bn.momentum)
         else:
             y = K.conv2d_fwd(x, w, stride=self.stride, pad=self.pad)

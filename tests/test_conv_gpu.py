@@ -102,12 +102,33 @@ def test_conv_fwd_fused_epilogue():
     case = (2, 28, 28, 128, 256, 3, 1, 1)
     x, w = _mk(case, 3)
     res = torch.randn(2, 28, 28, 256, device="cuda").bfloat16()
-    cs = torch.zeros(256, device="cuda")
-    cq = torch.zeros(256, device="cuda")
-    out = K_.conv2d_fwd(x, w, stride=1, pad=1, residual=res, act="relu", col_stats=(cs, cq))
+    part = K_.stats_buffer(256, "cuda")
+    out = K_.conv2d_fwd(x, w, stride=1, pad=1, residual=res, act="relu", col_stats=part)
     torch.cuda.synchronize()
+    cs, cq = part[:, 0].sum(0), part[:, 1].sum(0)
     ref = torch.relu(_ref(x, w, 1, 1)) + res.float()
     _check(out, ref, "conv fused")
     o = out.float().reshape(-1, 256)
     assert torch.allclose(cs, o.sum(0), rtol=1e-3, atol=0.5)
     assert torch.allclose(cq, (o * o).sum(0), rtol=1e-3, atol=2.0)
+
+
+@pytest.mark.parametrize("case", [(8, 56, 56, 64, 256, 1, 1, 0), (4, 14, 14, 256, 1024, 1, 1, 0), (3, 28, 28, 128, 128, 3, 1, 1),
+                                  (2, 56, 56, 256, 512, 1, 2, 0), (5, 7, 7, 512, 2048, 1, 1, 0)])
+def test_conv_fwd_fused_bn_statistics(case):
+    """Statistics emitted by the conv epilogue == statistics of the stored bf16 tensor (what bn_stats would read back), including
+    column blocks that move between CTAs (Cout > 256) and ragged last tiles."""
+    from passl_b200 import kernels as K_
+    x, w = _mk(case, 11)
+    N, H, W, Cin, Cout, R, stride, pad = case
+    part = K_.stats_buffer(Cout, "cuda")
+    y = K_.conv2d_fwd(x, w, stride=stride, pad=pad, col_stats=part)
+    y_plain = K_.conv2d_fwd(x, w, stride=stride, pad=pad)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y_plain)
+    o = y.double().reshape(-1, Cout)
+    s1, s2 = part[:, 0].double().sum(0), part[:, 1].double().sum(0)
+    assert torch.allclose(s1, o.sum(0), rtol=1e-4, atol=1e-2 * o.abs().sum(0).max().item() / o.shape[0] ** 0.5 + 1e-2)
+    assert torch.allclose(s2, (o * o).sum(0), rtol=1e-4, atol=1e-3)
+    ref_part = K_.bn_stats(y.view(-1, Cout))
+    assert torch.allclose(s1.float(), ref_part[:, 0].sum(0), rtol=1e-4, atol=0.5)

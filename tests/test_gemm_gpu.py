@@ -67,10 +67,11 @@ def test_gemm_splitk_atomic_and_colstats():
     torch.cuda.synchronize()
     bad, msg = _err_report(out, ref, "splitk")
     assert not bad, msg
-    cs = torch.zeros(N, device="cuda")
-    cq = torch.zeros(N, device="cuda")
-    out2 = K_.gemm(a, b, col_stats=(cs, cq))
+    part = K_.stats_buffer(N, "cuda")                      # per-CTA partials [rows, 2, N], zeroed by the call
+    part.fill_(7.0)
+    out2 = K_.gemm(a, b, col_stats=part)
     torch.cuda.synchronize()
     o = out2.float()
+    cs, cq = part[:, 0].sum(0), part[:, 1].sum(0)
     assert torch.allclose(cs, o.sum(0), rtol=1e-3, atol=1e-1), (cs - o.sum(0)).abs().max()
     assert torch.allclose(cq, (o * o).sum(0), rtol=1e-3, atol=1.0), (cq - (o * o).sum(0)).abs().max()

@@ -55,9 +55,9 @@ def main():
             fl = 2.0 * B * Ho * Ho * Cout * R * R * Cin
             y = K.conv2d_fwd(x, w, stride=s, pad=p)
             dy = torch.randn_like(y)
-            cs = torch.zeros(2, Cout, device="cuda")
+            cs = K.stats_buffer(Cout, "cuda")
             f = timeit(lambda: K.conv2d_fwd(x, w, stride=s, pad=p, out=y))
-            fs = timeit(lambda: K.conv2d_fwd(x, w, stride=s, pad=p, out=y, col_stats=(cs[0], cs[1])))
+            fs = timeit(lambda: K.conv2d_fwd(x, w, stride=s, pad=p, out=y, col_stats=cs))
             dxb = torch.empty_like(x)
             d = timeit(lambda: K.conv2d_dgrad(dy, w, tuple(x.shape), stride=s, pad=p, out=dxb))
             dw = torch.zeros(Cout, R, R, Cin, device="cuda")
