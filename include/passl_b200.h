@@ -66,6 +66,20 @@ int passl_b200_gemm_bf16_ex(const void* A, const void* B, void* out, int M, int 
 int passl_b200_conv2d_fwd_bf16(const void* x, const void* w, void* out, int N, int H, int W, int Cin, int Cout, int R,
                                int S, int stride, int pad, const float* bias, const void* residual, int act,
                                float* col_sum, float* col_sqsum, void* stream);
+/* rectangular filter, separate row / column padding, explicit output extent, stride 1 (the repacked 7x7/2 stem below) */
+int passl_b200_conv2d_fwd_rect_bf16(const void* x, const void* w, void* out, int N, int H, int W, int Cin, int Cout, int R,
+                                    int S, int pad_h, int pad_w, int Ho, int Wo, const float* bias, int act, float* col_sum,
+                                    void* stream);
+int passl_b200_conv2d_wgrad_rect_bf16(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int R,
+                                      int S, int pad_h, int pad_w, int Ho, int Wo, int zero_first, void* stream);
+/* ResNet stem conv 7x7/2 pad 3, 3 -> 64 (resnetimagenet.py:190-198) without an im2col matrix:
+ *   stem_pack_input : NCHW fp32 [N,3,H,W] -> xp bf16 [N,H/2,W/2,64], xp[n,i,q,((dj*2+a)*2+b)*4+c] = img[n,c,2i+a,2(q+dj-2)+b]
+ *   stem_pack_weight: w fp32 [64,kpad] ((r,s,c) order) -> wp bf16 [64,4,64] so that
+ *                     conv7x7/2(img, w) == conv2d_fwd_rect(xp, wp, R=4, S=1, pad_h=2, pad_w=0, Ho=H/2, Wo=W/2)
+ *   stem_unpack_wgrad: dw[64,kpad] += fold(dwp fp32 [64,4,64])  (dwp from conv2d_wgrad_rect on xp) */
+int passl_b200_stem_pack_input(const float* img, void* xp, int N, int H, int W, void* stream);
+int passl_b200_stem_pack_weight(const float* w, void* wp, int kpad, void* stream);
+int passl_b200_stem_unpack_wgrad(const float* dwp, float* dw, int kpad, void* stream);
 long long passl_b200_conv2d_dgrad_workspace_bytes(int Cin, int Cout, int R, int S);
 int passl_b200_conv2d_dgrad_bf16(const void* dy, const void* w, void* dx, void* workspace, int N, int H, int W, int Cin,
                                  int Cout, int R, int S, int stride, int pad, int accumulate, void* stream);
@@ -273,6 +287,14 @@ int passl_b200_lars_momentum(float* p, const float* g, float* v, void* p_bf16, c
 int passl_b200_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, const int* block_seg, const float* seg_wd,
                      const float* seg_lr_ratio, float lr, float beta1, float beta2, float eps, int step, float grad_scale,
                      long long n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Developer probe (not a reference entry point): one tcgen05.mma over a row-shifted view of a SWIZZLE_128B tile, used by
+ * tests/test_umma_probe_gpu.py to pin the shared-memory descriptor semantics (start address not 1024-aligned, SBO != 1024,
+ * base_offset bits) that the halo-tile convolution kernels rely on.  A bf16 [256,64], B bf16 [64,64], out fp32 [128,64].
+ * ------------------------------------------------------------------------------------------------------------- */
+int passl_b200_umma_probe(const void* A, const void* B, float* out, int shift_rows, int sbo_bytes, int base_offset, int a_mn,
+                          void* stream);
 
 #ifdef __cplusplus
 }

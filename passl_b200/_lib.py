@@ -25,6 +25,11 @@ SIGNATURES = {
                                         c_void_p, c_int, c_void_p, c_void_p]),
     "passl_b200_conv2d_fwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 9 +
                                    [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "passl_b200_conv2d_fwd_rect_bf16": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 11 + [c_void_p, c_int, c_void_p, c_void_p]),
+    "passl_b200_conv2d_wgrad_rect_bf16": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 12 + [c_void_p]),
+    "passl_b200_stem_pack_input": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "passl_b200_stem_pack_weight": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "passl_b200_stem_unpack_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "passl_b200_conv2d_dgrad_workspace_bytes": (c_ll, [c_int] * 4),
     "passl_b200_conv2d_dgrad_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 10 + [c_void_p]),
     "passl_b200_conv2d_wgrad_bf16": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 10 + [c_void_p]),
@@ -73,6 +78,7 @@ SIGNATURES = {
     "passl_b200_clip_ce_bwd": (c_int, [c_void_p] * 4 + [c_int, c_int, c_void_p, c_ll, c_void_p]),
     "passl_b200_rows_ce_fwd": (c_int, [c_void_p] * 4 + [c_int, c_int, c_void_p, c_ll, c_void_p]),
     "passl_b200_rows_ce_bwd": (c_int, [c_void_p] * 5 + [c_int, c_int, c_void_p]),
+    "passl_b200_umma_probe": (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p]),
     "passl_b200_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "passl_b200_attention_bwd": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "passl_b200_layernorm_fwd": (c_int, [c_void_p] * 6 + [c_ll, c_int, c_float, c_void_p]),

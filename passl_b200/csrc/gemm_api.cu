@@ -169,15 +169,14 @@ extern "C" int passl_b200_gemm_stats_rows(void) { return num_sms(); }
 // Convolution forward (implicit GEMM), NHWC bf16, weights [Cout, R, S, Cin] bf16.
 //   out[n, p, q, co] = epilogue( sum_{r,s,ci} x[n, p*stride + r - pad, q*stride + s - pad, ci] * w[co, r, s, ci] )
 // ==============================================================================================
-extern "C" int passl_b200_conv2d_fwd_bf16(const void* x, const void* w, void* out, int N, int H, int W, int Cin,
-                                          int Cout, int R, int S, int stride, int pad, const float* bias,
-                                          const void* residual, int act, float* col_sum, float* col_sqsum,
-                                          void* stream) {
+static int conv_fwd_impl(const void* x, const void* w, void* out, int N, int H, int W, int Cin, int Cout, int R, int S,
+                         int stride, int pad_h, int pad_w, int Ho, int Wo, const float* bias, const void* residual, int act,
+                         float* col_sum, float* col_sqsum, void* stream) {
   if (Cin % 64 || Cout % 8 || R * S > kMaxTaps) return PB_ERR_UNSUPPORTED;
-  const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
+  const int pad = pad_h;
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  if (R == 1 && S == 1 && stride == 1 && pad == 0) {
+  if (R == 1 && S == 1 && stride == 1 && pad_h == 0 && pad_w == 0 && Ho == H && Wo == W) {
     return passl_b200_gemm_bf16(x, w, out, N * H * W, Cout, Cin, 0, 0, Cin, Cin, Cout, 0, 0, bias, residual, act,
                                 1.f, 1, col_sum, col_sqsum, stream);
   }
@@ -194,7 +193,7 @@ extern "C" int passl_b200_conv2d_fwd_bf16(const void* x, const void* w, void* ou
   for (int r = 0; r < R; ++r)
     for (int s = 0; s < S; ++s) {
       int t = r * S + s;
-      int th = r - pad, tw = s - pad;
+      int th = r - pad, tw = s - pad_w;
       p.a.dh[t] = (signed char)floordiv(th, stride);
       p.a.dw[t] = (signed char)floordiv(tw, stride);
       p.a.map[t] = (signed char)(stride == 1 ? 0 : posmod(th, 2) * 2 + posmod(tw, 2));
@@ -208,6 +207,24 @@ extern "C" int passl_b200_conv2d_fwd_bf16(const void* x, const void* w, void* ou
   set_epilogue(p, out, Cout, 0, 0, bias, residual, act, 1.f, col_sum, col_sqsum);
   p.out_pixel = 1; p.OH = Ho; p.OW = Wo; p.osh = 1; p.osw = 1; p.oh0 = 0; p.ow0 = 0;
   return launch_gemm(p, BN, 64, false, false, (cudaStream_t)stream);
+}
+
+extern "C" int passl_b200_conv2d_fwd_bf16(const void* x, const void* w, void* out, int N, int H, int W, int Cin,
+                                          int Cout, int R, int S, int stride, int pad, const float* bias,
+                                          const void* residual, int act, float* col_sum, float* col_sqsum,
+                                          void* stream) {
+  const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
+  return conv_fwd_impl(x, w, out, N, H, W, Cin, Cout, R, S, stride, pad, pad, Ho, Wo, bias, residual, act, col_sum, col_sqsum,
+                       stream);
+}
+
+// Rectangular filters with separate row / column padding and an explicit output extent (stride 1): the W-unfolded
+// space-to-depth form of the 7x7/2 stem is a 4x1 convolution over 64 channels with rows padded (2, 1).
+extern "C" int passl_b200_conv2d_fwd_rect_bf16(const void* x, const void* w, void* out, int N, int H, int W, int Cin,
+                                               int Cout, int R, int S, int pad_h, int pad_w, int Ho, int Wo,
+                                               const float* bias, int act, float* col_sum, void* stream) {
+  if (Ho <= 0 || Wo <= 0 || Ho > H + 2 * pad_h - R + 1 + R || Wo > W + 2 * pad_w - S + 1 + S) return PB_ERR_BAD_ARG;
+  return conv_fwd_impl(x, w, out, N, H, W, Cin, Cout, R, S, 1, pad_h, pad_w, Ho, Wo, bias, nullptr, act, col_sum, nullptr, stream);
 }
 
 // ==============================================================================================
@@ -330,14 +347,13 @@ extern "C" int passl_b200_conv2d_dgrad_bf16(const void* dy, const void* w, void*
 //     sum_{n,p,q} dy[n,p,q,co] * x[n, p*stride + r - pad, q*stride + s - pad, ci]
 // K = output pixels (patch tiles), split across CTAs.
 // ==============================================================================================
-extern "C" int passl_b200_conv2d_wgrad_bf16(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin,
-                                            int Cout, int R, int S, int stride, int pad, int zero_first,
-                                            void* stream) {
+static int conv_wgrad_impl(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int R, int S,
+                           int stride, int pad_h, int pad_w, int Ho, int Wo, int zero_first, void* stream) {
   if (Cin % 8 || Cout % 8 || R * S > kMaxTaps || (stride != 1 && stride != 2)) return PB_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
-  const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
+  const int pad = pad_h;
   if (zero_first) PB_CUDA_CHECK(cudaMemsetAsync(dw, 0, (size_t)Cout * R * S * Cin * 4, st));
-  if (R == 1 && S == 1 && stride == 1 && pad == 0) {
+  if (R == 1 && S == 1 && stride == 1 && pad_h == 0 && pad_w == 0 && Ho == H && Wo == W) {
     int P = N * H * W;
     int mb = (Cout + 127) / 128;
     int BNg = pick_bn(mb, Cin);
@@ -374,7 +390,7 @@ extern "C" int passl_b200_conv2d_wgrad_bf16(const void* x, const void* dy, float
   for (int r = 0; r < R; ++r)
     for (int s = 0; s < S; ++s) {
       int t = r * S + s;
-      int th = r - pad, tw = s - pad;
+      int th = r - pad, tw = s - pad_w;
       p.b.dh[t] = (signed char)floordiv(th, stride);
       p.b.dw[t] = (signed char)floordiv(tw, stride);
       p.b.map[t] = (signed char)(stride == 1 ? 0 : posmod(th, 2) * 2 + posmod(tw, 2));
@@ -383,4 +399,18 @@ extern "C" int passl_b200_conv2d_wgrad_bf16(const void* x, const void* dy, float
   if (rc) return rc;
   set_epilogue(p, dw, (long long)R * S * Cin, 1, 1, nullptr, nullptr, ACT_NONE, 1.f, nullptr, nullptr);
   return launch_gemm(p, BN, 128, true, true, st);
+}
+
+extern "C" int passl_b200_conv2d_wgrad_bf16(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin,
+                                            int Cout, int R, int S, int stride, int pad, int zero_first,
+                                            void* stream) {
+  const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
+  return conv_wgrad_impl(x, dy, dw, N, H, W, Cin, Cout, R, S, stride, pad, pad, Ho, Wo, zero_first, stream);
+}
+
+extern "C" int passl_b200_conv2d_wgrad_rect_bf16(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin,
+                                                 int Cout, int R, int S, int pad_h, int pad_w, int Ho, int Wo, int zero_first,
+                                                 void* stream) {
+  if (Ho <= 0 || Wo <= 0) return PB_ERR_BAD_ARG;
+  return conv_wgrad_impl(x, dy, dw, N, H, W, Cin, Cout, R, S, 1, pad_h, pad_w, Ho, Wo, zero_first, stream);
 }

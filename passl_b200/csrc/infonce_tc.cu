@@ -42,6 +42,7 @@ struct InfoNceTcParams {
   int row_groups, slices, tiles;
   float* part_m; float* part_l; int* part_cnt;  // [N, slices]
   float* tgt;                                   // [N]
+  const float* tgt_raw;                         // [N] raw target dot products from infonce_target_kernel (PDL producer)
   unsigned long long* dbg;                      // optional per-CTA timeline (globaltimer ns), 16 slots per CTA
 };
 
@@ -51,6 +52,39 @@ __device__ __forceinline__ unsigned long long gtime() {
   return t;
 }
 #define NCE_STAMP(slot) do { if (p.dbg) p.dbg[blockIdx.x * 16 + (slot)] = gtime(); } while (0)
+
+// Target logits <q_i, k+_i> (MoCo: P = positive keys, fp32) or <q_i, K[label_i]> (MoCo v3 / CLIP), one warp per row with whole-row
+// coalesced loads.  Runs as the programmatic-dependent-launch PRODUCER of the main kernel: it releases its dependents at once,
+// so the main kernel's setup (barriers, TMEM, Q staging, first key tiles) overlaps it; the main kernel waits
+// (griddepcontrol.wait) just before it needs the 1 KB of results.  Previously every CTA recomputed all its rows' targets
+// (148 x 128 KB of L2 reads, ~8 us of latency-bound prologue).
+__global__ void __launch_bounds__(256) infonce_target_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __restrict__ Kmat,
+                                                             const float* __restrict__ P, const long long* __restrict__ label,
+                                                             float* __restrict__ tgt_raw, int N, int K, int D) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= N) return;
+  float acc = 0.f;
+  long long lab = 0;
+  if (!P) {
+    lab = label[row];
+    lab = lab < 0 ? 0 : (lab >= K ? K - 1 : lab);
+  }
+  for (int d4 = lane * 4; d4 < D; d4 += 128) {
+    const uint2 qu = *reinterpret_cast<const uint2*>(Q + (size_t)row * D + d4);
+    const float2 q0 = unpack_bf16x2(qu.x), q1 = unpack_bf16x2(qu.y);
+    if (P) {
+      const float4 pa = *reinterpret_cast<const float4*>(P + (size_t)row * D + d4);
+      acc += q0.x * pa.x + q0.y * pa.y + q1.x * pa.z + q1.y * pa.w;
+    } else {
+      const uint2 ku = *reinterpret_cast<const uint2*>(Kmat + (size_t)lab * D + d4);
+      const float2 k0 = unpack_bf16x2(ku.x), k1 = unpack_bf16x2(ku.y);
+      acc += q0.x * k0.x + q0.y * k0.y + q1.x * k1.x + q1.y * k1.y;
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) tgt_raw[row] = acc;
+}
 
 template <int MB>
 __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const __grid_constant__ InfoNceTcParams p) {
@@ -72,6 +106,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
   uint64_t* q_full = s_empty + 2;     // TMA: Q block staged in shared memory
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(q_full + 1);
 
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the finalize grid may be scheduled early (it waits for us)
   const uint32_t warp = warp_id(), lane = lane_id();
   const int group = blockIdx.x / p.slices;
   const int slice = blockIdx.x - group * p.slices;
@@ -175,9 +210,8 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
     const bool row_ok = row < p.N;
     const float c2 = p.scale * kLog2e;  // logits in the log2 domain: y = dot * c2
 
-    // Prologue (coalesced): Q block arrives by TMA in shared memory; each thread copies its own row smem -> registers ->
-    // TMEM (A operand of every MMA); target logits (positive pair or labelled column) are computed warp-cooperatively:
-    // for each of the warp's 32 rows the lanes split D, so global reads are whole 512 B / 256 B rows.
+    // Prologue: Q block arrives by TMA in shared memory; each thread copies its own row smem -> registers -> TMEM (A operand
+    // of every MMA); the target logit of the row (positive pair or labelled column) is read from the producer kernel's output.
     float tgt2 = 0.f, tgt_raw = 0.f;
     long long lab = -1;
     int ex = -1;
@@ -205,49 +239,9 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
         if (!p.P) lab = p.label[row];
         if (p.excl) ex = p.excl[row];
       }
-      float s_mine = 0.f;
-      const int rows_left = p.N - (row_base + b * 128 + q4 * 32);          // warp-uniform
-      const int nrows = rows_left < 32 ? (rows_left > 0 ? rows_left : 0) : 32;
-      for (int r0 = 0; r0 < nrows; r0 += 8) {
-        // 8 rows per batch: issue all global loads first (independent), then the dot products and warp reductions
-        for (int dbase = 0; dbase < p.D; dbase += 128) {        // warp-uniform trip count: every lane reaches the shuffles
-          const int d4 = dbase + lane * 4;
-          const bool act = d4 < p.D;
-          float4 pa[8];
-          uint2 pk[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int rr = r0 + u;
-            const int grow = row_base + b * 128 + q4 * 32 + (rr < nrows ? rr : 0);
-            pa[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            pk[u] = make_uint2(0u, 0u);
-            if (p.P) { if (act) pa[u] = *reinterpret_cast<const float4*>(p.P + (size_t)grow * p.D + d4); }
-            else {
-              const long long lab_r = __shfl_sync(0xffffffffu, lab, rr < nrows ? rr : 0);
-              if (act) pk[u] = *reinterpret_cast<const uint2*>(p.Kmat + (size_t)lab_r * p.D + d4);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int rr = r0 + u;
-            const int r2 = q4 * 32 + (rr < nrows ? rr : 0);
-            const int dd = act ? d4 : 0;
-            const int ch = dd >> 6, col = dd & 63;
-            const uint8_t* qa = q_smem + (b * DC + ch) * (128 * 128) + (r2 >> 3) * 1024 + (r2 & 7) * 128 +
-                                ((((col >> 3) ^ (r2 & 7)) & 7) << 4) + (col & 7) * 2;
-            const uint2 qu = act ? *reinterpret_cast<const uint2*>(qa) : make_uint2(0u, 0u);
-            const float2 q0 = unpack_bf16x2(qu.x), q1 = unpack_bf16x2(qu.y);
-            float part;
-            if (p.P) part = q0.x * pa[u].x + q0.y * pa[u].y + q1.x * pa[u].z + q1.y * pa[u].w;
-            else {
-              const float2 k0 = unpack_bf16x2(pk[u].x), k1 = unpack_bf16x2(pk[u].y);
-              part = q0.x * k0.x + q0.y * k0.y + q1.x * k1.x + q1.y * k1.y;
-            }
-            part = warp_sum(part);
-            if (lane == rr && rr < nrows) s_mine += part;
-          }
-        }
-      }
+      // targets come from infonce_target_kernel (PDL producer): block here, as late as possible, until that grid has completed
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      const float s_mine = row_ok ? __ldcg(p.tgt_raw + row) : 0.f;
       tgt2 = s_mine * c2;
       tgt_raw = s_mine;
       if (threadIdx.x == 64) NCE_STAMP(4);
@@ -369,7 +363,7 @@ extern "C" int passl_b200_infonce_tc_set_debug(void* buf) { g_nce_dbg = reinterp
 extern "C" long long passl_b200_infonce_tc_workspace_bytes(int N, int K, int D) {
   int MB, groups, slices, tiles, smem;
   nce_plan(N, K, D, MB, groups, slices, tiles, smem);
-  return (long long)N * slices * 12 + simce_finalize_scratch_bytes(N) + 256;
+  return (long long)N * slices * 12 + simce_finalize_scratch_bytes(N) + (long long)N * 4 + 512;
 }
 
 // Forward.  Q [N,D] bf16 (normalised queries), Kmat [K,D] bf16 keys, P [N,D] fp32 optional positive keys
@@ -411,11 +405,28 @@ extern "C" int passl_b200_infonce_tc_fwd(const void* Q, const void* Kmat, const 
     PB_CUDA_CHECK(cudaFuncSetAttribute(infonce_tc_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done = true;
   }
-  if (MB == 2) infonce_tc_fwd_kernel<2><<<grid, 64 + 256, smem, st>>>(p);
-  else infonce_tc_fwd_kernel<1><<<grid, 64 + 128, smem, st>>>(p);
+  // three launches chained by programmatic dependent launch: ticket memset -> target -> main (PDL) -> finalize (PDL)
+  float* scratch = reinterpret_cast<float*>(p.part_cnt + (size_t)N * p.slices);
+  const int fin_blk = (N + 7) / 8;
+  float* tgt_raw = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + ((simce_finalize_scratch_bytes(N) + 15) & ~15LL));
+  p.tgt_raw = tgt_raw;
+  PB_CUDA_CHECK(cudaMemsetAsync(scratch + (size_t)fin_blk * 3, 0, 4, st));
+  infonce_target_kernel<<<fin_blk, 256, 0, st>>>(p.Q, p.Kmat, P, label, tgt_raw, N, K, D);
   PB_LAUNCH_CHECK();
+  {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + 128 * MB); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (MB == 2) PB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, infonce_tc_fwd_kernel<2>, p));
+    else PB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, infonce_tc_fwd_kernel<1>, p));
+    PB_LAUNCH_CHECK();
+  }
   PB_CUDA_CHECK(launch_simce_finalize(p.part_m, p.part_l, p.part_cnt, tgt, N, p.slices, P ? 1 : 0, loss_scale, lse,
-                                      loss_rows, out_scalars, reinterpret_cast<float*>(p.part_cnt + (size_t)N * p.slices), st));
+                                      loss_rows, out_scalars, scratch, st, /*pdl=*/true));
   passl_b200_launch_counter_add(1);
   return PB_OK;
 }

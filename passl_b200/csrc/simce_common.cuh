@@ -1,5 +1,6 @@
 // Shared pieces of the fused similarity-softmax-CE kernels (fp32 SIMT variant and tcgen05 bf16 variant).
 #pragma once
+#include <string.h>
 #include "common.cuh"
 #include "host_utils.h"
 
@@ -11,6 +12,9 @@ namespace pb {
 static __global__ void __launch_bounds__(256) simce_finalize_kernel(const float* part_m, const float* part_l, const int* part_cnt,
                                       const float* tgt, int N, int splits, int extra_col, float loss_scale, float* lse_out,
                                       float* loss_rows, float* out, float* scratch) {
+  // programmatic dependent launch: when launched with the PDL attribute this grid may start while the producer of the partials
+  // is still running; the wait returns once that grid has completed and flushed (no-op for ordinary launches)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   // one warp per row (8 rows per CTA, all rows of the batch in flight at once), lanes over the split partials
   __shared__ float red[3][8];
   __shared__ bool is_last;
@@ -76,15 +80,29 @@ static __global__ void __launch_bounds__(256) simce_finalize_kernel(const float*
 static inline long long simce_finalize_scratch_bytes(int N) { return ((long long)((N + 7) / 8) * 3 + 4) * 4; }
 
 // scratch must hold simce_finalize_scratch_bytes(N); its ticket word is zeroed here once per call (stream ordered)
+// pdl: the ticket word was already zeroed by the caller BEFORE the producer kernel and this launch carries the programmatic
+// stream serialization attribute (it must directly follow the producer in the stream).
 static inline cudaError_t launch_simce_finalize(const float* part_m, const float* part_l, const int* part_cnt, const float* tgt,
                                                 int N, int splits, int extra_col, float loss_scale, float* lse_out,
-                                                float* loss_rows, float* out, float* scratch, cudaStream_t st) {
+                                                float* loss_rows, float* out, float* scratch, cudaStream_t st,
+                                                bool pdl = false) {
   const int nblk = (N + 7) / 8;
-  cudaError_t e = cudaMemsetAsync(scratch + (size_t)nblk * 3, 0, 4, st);
-  if (e != cudaSuccess) return e;
-  simce_finalize_kernel<<<nblk, 256, 0, st>>>(part_m, part_l, part_cnt, tgt, N, splits, extra_col, loss_scale, lse_out,
-                                              loss_rows, out, scratch);
-  return cudaGetLastError();
+  if (!pdl) {
+    cudaError_t e = cudaMemsetAsync(scratch + (size_t)nblk * 3, 0, 4, st);
+    if (e != cudaSuccess) return e;
+    simce_finalize_kernel<<<nblk, 256, 0, st>>>(part_m, part_l, part_cnt, tgt, N, splits, extra_col, loss_scale, lse_out,
+                                                loss_rows, out, scratch);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(nblk); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, simce_finalize_kernel, part_m, part_l, part_cnt, tgt, N, splits, extra_col, loss_scale, lse_out,
+                            loss_rows, out, scratch);
 }
 
 // per-row gradient scale: grow[i] = dloss * factor

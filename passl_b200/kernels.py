@@ -136,6 +136,47 @@ def conv2d_wgrad(x, dy, w_shape, stride=1, pad=0, out=None, accumulate=False):
 
 
 # ------------------------------------------------------------------------------------------------------------
+# ResNet stem (7x7/2, 3 -> 64) as a 4x1 convolution over the W-unfolded space-to-depth repack (csrc/stem.cu)
+# ------------------------------------------------------------------------------------------------------------
+def stem_pack_input(img):
+    """NCHW fp32 [N,3,H,W] -> bf16 [N,H/2,W/2,64]."""
+    _need_cuda(img)
+    lib = _lib.load()
+    N, C, H, W = img.shape
+    assert C == 3 and img.dtype == torch.float32 and img.is_contiguous()
+    xp = torch.empty((N, H // 2, W // 2, 64), dtype=torch.bfloat16, device=img.device)
+    _lib.check(lib.passl_b200_stem_pack_input(_ptr(img), _ptr(xp), N, H, W, _stream()), "stem_pack_input")
+    return xp
+
+
+def stem_pack_weight(w):
+    """fp32 [64, kpad] ((r,s,c) order) -> bf16 [64,4,1,64]."""
+    lib = _lib.load()
+    wp = torch.empty((64, 4, 1, 64), dtype=torch.bfloat16, device=w.device)
+    _lib.check(lib.passl_b200_stem_pack_weight(_ptr(w), _ptr(wp), w.shape[1], _stream()), "stem_pack_weight")
+    return wp
+
+
+def stem_conv_fwd(xp, wp, col_stats=None):
+    lib = _lib.load()
+    N, H, W, _ = xp.shape
+    out = torch.empty((N, H, W, 64), dtype=torch.bfloat16, device=xp.device)
+    _lib.check(lib.passl_b200_conv2d_fwd_rect_bf16(_ptr(xp), _ptr(wp), _ptr(out), N, H, W, 64, 64, 4, 1, 2, 0, H, W, None, 0,
+                                                   _ptr(col_stats), _stream()), "conv2d_fwd_rect_bf16")
+    return out
+
+
+def stem_conv_wgrad(xp, dy, dw_acc):
+    """dw_acc fp32 [64, kpad] += d/dw of the stem for dy bf16 [N,H/2,W/2,64]."""
+    lib = _lib.load()
+    N, H, W, _ = xp.shape
+    dwp = torch.empty((64, 4, 1, 64), dtype=torch.float32, device=xp.device)
+    _lib.check(lib.passl_b200_conv2d_wgrad_rect_bf16(_ptr(xp), _ptr(dy), _ptr(dwp), N, H, W, 64, 64, 4, 1, 2, 0, H, W, 1, _stream()),
+               "conv2d_wgrad_rect_bf16")
+    _lib.check(lib.passl_b200_stem_unpack_wgrad(_ptr(dwp), _ptr(dw_acc), dw_acc.shape[1], _stream()), "stem_unpack_wgrad")
+
+
+# ------------------------------------------------------------------------------------------------------------
 # Fused similarity / softmax / CE (fp32 SIMT variant)
 # ------------------------------------------------------------------------------------------------------------
 def simce_fwd(a, b, *, pos=None, label=None, excl=None, scale=1.0, loss_scale=1.0, want_rows=False):

@@ -132,3 +132,33 @@ def test_conv_fwd_fused_bn_statistics(case):
     assert torch.allclose(s2, (o * o).sum(0), rtol=1e-4, atol=1e-3)
     ref_part = K_.bn_stats(y.view(-1, Cout))
     assert torch.allclose(s1.float(), ref_part[:, 0].sum(0), rtol=1e-4, atol=0.5)
+
+
+@pytest.mark.parametrize("N,HW", [(4, 64), (2, 224), (3, 96)])
+def test_stem_repack_conv_matches_conv7x7(N, HW):
+    """7x7/2 pad 3 stem through the W-unfolded space-to-depth repack (csrc/stem.cu) == F.conv2d on bf16-rounded operands,
+    forward and weight gradient (resnetimagenet.py:190-198)."""
+    from passl_b200 import kernels as K_
+    g = torch.Generator(device="cuda").manual_seed(5)
+    img = torch.randn(N, 3, HW, HW, device="cuda", generator=g)
+    w = torch.randn(64, 7, 7, 3, device="cuda", generator=g) / 147 ** 0.5
+    W2 = torch.zeros(64, 152, device="cuda")
+    W2[:, :147] = w.reshape(64, 147)
+    xp = K_.stem_pack_input(img)
+    wp = K_.stem_pack_weight(W2)
+    part = K_.stats_buffer(64, "cuda")
+    y = K_.stem_conv_fwd(xp, wp, col_stats=part)
+    xr = img.bfloat16().float().requires_grad_(True)
+    wr = w.bfloat16().float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    ref = F.conv2d(xr, wr, stride=2, padding=3)
+    _check(y, ref.permute(0, 2, 3, 1), "stem fwd")
+    o = y.float().reshape(-1, 64)
+    assert torch.allclose(part[:, 0].sum(0), o.sum(0), rtol=1e-3, atol=0.5)
+    dy = torch.randn(y.shape, device="cuda", generator=g).bfloat16()
+    dw = torch.zeros(64, 152, device="cuda")
+    dw[:, :147] = 1.0                                           # accumulate semantics
+    K_.stem_conv_wgrad(xp, dy, dw)
+    ref.backward(dy.float().permute(0, 3, 1, 2))
+    dw_ref = wr.grad.permute(0, 2, 3, 1).reshape(64, 147) + 1.0
+    _check(dw[:, :147], dw_ref, "stem wgrad", rel=1e-2)
+    assert torch.equal(dw[:, 147:], torch.zeros(64, 5, device="cuda"))

@@ -34,6 +34,20 @@ def timeit(fn, iters=10, warmup=3, flush=True):
 def main():
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     res = {}
+    if what in ("membw",):
+        # directional HBM bandwidth (torch library kernels, measurement only): pure read, pure write, copy, on 4 GiB buffers
+        n = 1 << 30
+        a = torch.empty(n, dtype=torch.float32, device="cuda").normal_()
+        b = torch.empty_like(a)
+        t = timeit(lambda: a.sum(), flush=False)
+        print("read  4 GiB: %.3f ms  %.0f GB/s" % (t, 4 * n / t / 1e6))
+        t = timeit(lambda: b.zero_(), flush=False)
+        print("write 4 GiB: %.3f ms  %.0f GB/s" % (t, 4 * n / t / 1e6))
+        t = timeit(lambda: b.copy_(a), flush=False)
+        print("copy  4+4 GiB: %.3f ms  %.0f GB/s" % (t, 8 * n / t / 1e6))
+        y = torch.randn(1024 * 56 * 56, 256, device="cuda").bfloat16()
+        t = timeit(lambda: K.bn_stats(y), flush=False)
+        print("bn_stats read 1.64 GB: %.3f ms %.0f GB/s" % (t, y.numel() * 2 / t / 1e6))
     if what in ("all", "gemm"):
         for (M, N, K_) in [(8192, 8192, 8192), (4096, 4096, 4096), (100352, 64, 576), (100352, 256, 64), (25088, 512, 128),
                            (16384, 2304, 768), (16384, 768, 3072), (16384, 3072, 768)]:
