@@ -159,7 +159,10 @@ int passl_b200_cast_bf16_to_f32(const void* x, float* y, long long n, void* stre
  *                   deterministic); the GEMM / conv forward can emit the same partials from its epilogue (col_sum, gemm_stats_rows() rows)
  *   bn_finalize   : sums the partials -> mean, invstd, scale = gamma*invstd, shift = beta - mean*scale, running stats
  *   bn_apply      : z = relu?(y*scale + shift + residual)  (bf16 and/or fp32 output)
- *   bn_bwd_reduce : partials of sum_g = sum_p g, sum_gx = sum_p g*xhat with g = dz * (z>0 if relu)
+ *   bn_bwd_reduce : partials of sum_g = sum_p g, sum_gx = sum_p g*xhat with g = dz * (z>0 if relu).  relu: 0 none, 1 mask
+ *                   read from z (bf16, needed when a residual was added before the ReLU), 2 mask recomputed from y as
+ *                   fma(y, scale, shift) > 0 — `z` then points to the fp32 [2, C] (scale, shift) rows and the activation
+ *                   tensor is never read (same convention in bn_bwd_apply)
  *   bn_bwd_finalize: sums [2,C] = totals (= dbeta, dgamma), accumulated into the gradient buffers when given
  *   bn_bwd_apply  : dy = gamma*invstd*(g - sum_g/P - xhat*sum_gx/P) = k1*g + k2*y + k3; dres = g (residual-branch gradient)
  * ------------------------------------------------------------------------------------------------------------- */

@@ -34,12 +34,21 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const __nv_bfloat16* __r
   const int cg = blockIdx.y * blockDim.x + threadIdx.x;  // channel group
   const int c0 = cg * 8;
   const bool cok = c0 < C;
-  float s0[8], s1[8], mu[8], is[8];
+  float s0[8], s1[8], mu[8], is[8], sc[8], sh[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { s0[i] = 0.f; s1[i] = 0.f; mu[i] = 0.f; is[i] = 1.f; }
+  for (int i = 0; i < 8; ++i) { s0[i] = 0.f; s1[i] = 0.f; mu[i] = 0.f; is[i] = 1.f; sc[i] = 0.f; sh[i] = 0.f; }
   if (MODE == 1 && cok) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) { mu[i] = mean[c0 + i]; is[i] = invstd[c0 + i]; }
+  }
+  // relu == 2: the ReLU mask is recomputed from y (z = relu(fma(y, scale, shift)) has no residual term), so z is never read;
+  // the `z` argument then carries the fp32 [2, C] (scale, shift) rows of the forward pass
+  const bool recompute = (MODE == 1) && relu == 2;
+  const bool read_z = (MODE == 1) && relu == 1;
+  if (recompute && cok) {
+    const float* ss = reinterpret_cast<const float*>(z);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sc[i] = ss[c0 + i]; sh[i] = ss[C + c0 + i]; }
   }
   const long long r_begin = (long long)blockIdx.x * rows_per_block;
   long long r_end = r_begin + rows_per_block;
@@ -55,7 +64,7 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const __nv_bfloat16* __r
         uy[u] = ld_nc_v4(y + (r + u * step) * C + c0);
         if (MODE == 1) {
           ug[u] = ld_nc_v4(dz + (r + u * step) * C + c0);
-          if (relu) uz[u] = ld_nc_v4(z + (r + u * step) * C + c0);
+          if (read_z) uz[u] = ld_nc_v4(z + (r + u * step) * C + c0);
         }
       }
 #pragma unroll
@@ -68,11 +77,14 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const __nv_bfloat16* __r
         } else {
           float g[8];
           unpack8(ug[u], g);
-          if (relu) {
+          if (read_z) {
             float zz[8];
             unpack8(uz[u], zz);
 #pragma unroll
             for (int i = 0; i < 8; ++i) g[i] = zz[i] > 0.f ? g[i] : 0.f;
+          } else if (recompute) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g[i] = fmaf(a[i], sc[i], sh[i]) > 0.f ? g[i] : 0.f;
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) { s0[i] += g[i]; s1[i] = fmaf(g[i], (a[i] - mu[i]) * is[i], s1[i]); }
@@ -88,11 +100,14 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const __nv_bfloat16* __r
       } else {
         float g[8];
         unpack8(ld_nc_v4(dz + r * C + c0), g);
-        if (relu) {
+        if (read_z) {
           float zz[8];
           unpack8(ld_nc_v4(z + r * C + c0), zz);
 #pragma unroll
           for (int i = 0; i < 8; ++i) g[i] = zz[i] > 0.f ? g[i] : 0.f;
+        } else if (recompute) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g[i] = fmaf(a[i], sc[i], sh[i]) > 0.f ? g[i] : 0.f;
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) { s0[i] += g[i]; s1[i] = fmaf(g[i], (a[i] - mu[i]) * is[i], s1[i]); }
@@ -191,11 +206,19 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, const _
     float a[8], g[8];
     unpack8(ld_nc_v4(y + i * 8), a);
     unpack8(ld_nc_v4(dz + i * 8), g);
-    if (relu) {
+    if (relu == 1) {
       float zz[8];
       unpack8(ld_nc_v4(z + i * 8), zz);
 #pragma unroll
       for (int j = 0; j < 8; ++j) g[j] = zz[j] > 0.f ? g[j] : 0.f;
+    } else if (relu == 2) {       // mask recomputed from y: `z` carries fp32 [2, C] (scale, shift)
+      const float* ss = reinterpret_cast<const float*>(z);
+      const float4 sa = *reinterpret_cast<const float4*>(ss + c0), sb = *reinterpret_cast<const float4*>(ss + c0 + 4);
+      const float4 ha = *reinterpret_cast<const float4*>(ss + C + c0), hb = *reinterpret_cast<const float4*>(ss + C + c0 + 4);
+      const float scv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+      const float shv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = fmaf(a[j], scv[j], shv[j]) > 0.f ? g[j] : 0.f;
     }
     if (dres) *reinterpret_cast<uint4*>(dres + i * 8) = pack8(g);
     const float4 k1a = *reinterpret_cast<const float4*>(coef + c0), k1b = *reinterpret_cast<const float4*>(coef + c0 + 4);

@@ -346,6 +346,10 @@ def bn_bwd(y, dz, z, msss, gamma, relu, want_dres=False, dgamma=None, dbeta=None
     P = y.numel() // C
     nblk = lib.passl_b200_bn_reduce_blocks(P, C)
     part = torch.empty((nblk, 2, C), dtype=torch.float32, device=y.device)
+    relu = int(relu)
+    if relu and not want_dres:
+        # no residual entered the ReLU: z = relu(fma(y, scale, shift)) — recompute the mask from y, never read z (msss rows 2, 3)
+        relu, z = 2, msss[2:4]
     _lib.check(lib.passl_b200_bn_bwd_reduce(_ptr(y), _ptr(dz), _ptr(z), _ptr(msss[0]), _ptr(msss[1]), _ptr(part), P, C,
                                             int(relu), _stream()), "bn_bwd_reduce")
     sums = torch.empty((2, C), dtype=torch.float32, device=y.device)

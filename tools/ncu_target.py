@@ -48,3 +48,19 @@ if what == "conv":
         K.conv2d_wgrad(x, dy, (64, 3, 3, 64), stride=1, pad=1, out=dw, accumulate=True)
         K.conv2d_fwd(x2, w2)
     torch.cuda.synchronize()
+
+if what == "c3":
+    # layer1 conv3 shape (1x1, 64 -> 256) at B=256: the K-small, write-heavy GEMM class (HBM-bound)
+    M = 256 * 56 * 56
+    x = torch.randn(M, 64, device="cuda").bfloat16()
+    w = torch.randn(256, 64, device="cuda").bfloat16()
+    part = K.stats_buffer(256, "cuda")
+    y = torch.empty(M, 256, device="cuda", dtype=torch.bfloat16)
+    for i in range(3):
+        K.gemm(x, w, out=y, col_stats=part)
+    # layer1 conv1 of the next block (256 -> 64): read-heavy
+    w2 = torch.randn(64, 256, device="cuda").bfloat16()
+    y2 = torch.empty(M, 64, device="cuda", dtype=torch.bfloat16)
+    for i in range(3):
+        K.gemm(y, w2, out=y2)
+    torch.cuda.synchronize()
