@@ -373,9 +373,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         prev_nblk = n_blk;
       }
 
+      // rows this lane touches in the row-coalesced phases (8 rows x 64 B per instruction): fetched once per tile
+      const int crow = (int)(lane >> 2), cch = (int)(lane & 3);
+      long long ro4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ro4[i] = __shfl_sync(0xffffffffu, row_off_pub, i * 8 + crow);
+
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((q * 32u) << 16) + acc * BN;
+      const bool unit_alpha = p.alpha == 1.f;
 #pragma unroll 1
       for (int c = (int)half; c < BN / 32; c += 2) {
         const int cc0 = col0 + c * 32;           // logical column of v[0] (within tap)
@@ -384,20 +391,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         uint32_t v[32];
         tmem_ld_32x32(t_addr + c * 32, v);
         // residual: row-coalesced loads (8 rows x 64 B per instruction) issued before waiting for the TMEM read
-        const int crow = (int)(lane >> 2), cch = (int)(lane & 3);
+        const bool col_ok = cc0 + cch * 8 < col_lim;
         uint4 rr[4];
         if (staged && p.residual) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const long long ro = __shfl_sync(0xffffffffu, row_off_pub, i * 8 + crow);
             rr[i] = make_uint4(0u, 0u, 0u, 0u);
-            if (ro >= 0 && cc0 + cch * 8 < col_lim) rr[i] = ld_nc_v4(p.residual + ro + oc0 + cch * 8);
+            if (ro4[i] >= 0 && col_ok) rr[i] = ld_nc_v4(p.residual + ro4[i] + oc0 + cch * 8);
           }
         }
         tmem_ld_wait();
         float f[32];
+        if (unit_alpha) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+        }
         if (p.bias) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
@@ -495,25 +506,31 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         }
         __syncwarp();
         if (do_stats) {
-          // per-column batch statistics of the bf16 values being stored: lane = column, 32 rows from the staged tile
-          float s1 = 0.f, s2 = 0.f;
-#pragma unroll 8
-          for (int rr_ = 0; rr_ < 32; ++rr_) {
-            const float x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(stg + rr_ * kEpiStride + lane * 2));
-            s1 += x;
-            s2 = fmaf(x, x, s2);
+          // per-column batch statistics of the bf16 values being stored, from the staged tile: lane = (row parity, column pair);
+          // 16 rows x one 32-bit word (2 columns) each, then the two row parities are folded with one shuffle round
+          const uint32_t wsel = lane & 15u, rpar = lane >> 4;
+          float sa = 0.f, sb = 0.f, qa = 0.f, qb = 0.f;
+#pragma unroll
+          for (int rr_ = 0; rr_ < 16; ++rr_) {
+            const uint32_t wv = *reinterpret_cast<const uint32_t*>(stg + (rr_ * 2 + rpar) * kEpiStride + wsel * 4);
+            const float x0 = __uint_as_float(wv << 16), x1 = __uint_as_float(wv & 0xffff0000u);
+            sa += x0; sb += x1;
+            qa = fmaf(x0, x0, qa); qb = fmaf(x1, x1, qb);
           }
-          if (cc0 + (int)lane < col_lim) {
-            atomicAdd(&epi_stats[c * 32 + lane], s1);
-            atomicAdd(&epi_stats[BN + c * 32 + lane], s2);
+          sa += __shfl_xor_sync(0xffffffffu, sa, 16); sb += __shfl_xor_sync(0xffffffffu, sb, 16);
+          qa += __shfl_xor_sync(0xffffffffu, qa, 16); qb += __shfl_xor_sync(0xffffffffu, qb, 16);
+          if (rpar == 0 && cc0 + (int)wsel * 2 < col_lim) {     // N % 8 == 0: column pairs are never split by the bound
+            atomicAdd(&epi_stats[c * 32 + wsel * 2], sa);
+            atomicAdd(&epi_stats[c * 32 + wsel * 2 + 1], sb);
+            atomicAdd(&epi_stats[BN + c * 32 + wsel * 2], qa);
+            atomicAdd(&epi_stats[BN + c * 32 + wsel * 2 + 1], qb);
           }
         }
         __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const long long ro = __shfl_sync(0xffffffffu, row_off_pub, i * 8 + crow);
-          if (ro >= 0 && cc0 + cch * 8 < col_lim)
-            *reinterpret_cast<uint4*>(outp + ro + oc0 + cch * 8) = ld_shared_v4(stg_u32 + (i * 8 + crow) * kEpiStride + cch * 16);
+          if (ro4[i] >= 0 && col_ok)
+            *reinterpret_cast<uint4*>(outp + ro4[i] + oc0 + cch * 8) = ld_shared_v4(stg_u32 + (i * 8 + crow) * kEpiStride + cch * 16);
         }
         __syncwarp();
       }
