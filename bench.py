@@ -320,37 +320,41 @@ def run_ours(args):
         line["roofline_other"] = roof(other)
         # ---- fused InfoNCE (MoCo C3 shape) against the HBM roofline: CUDA-graph replay, events on the capture stream --------
         N, D, Kq, T = 256, 128, 65536, 0.2
+        NQ = 8                                            # 8 distinct queues (8 x 16.8 MB = 134 MB > 126 MB L2): none is L2 resident
         q = torch.nn.functional.normalize(torch.randn(N, D, device=dev), dim=1)
         kpos = torch.nn.functional.normalize(torch.randn(N, D, device=dev), dim=1)
-        queue = torch.nn.functional.normalize(torch.randn(Kq, D, device=dev), dim=1).bfloat16()
+        queues = [torch.nn.functional.normalize(torch.randn(Kq, D, device=dev), dim=1).bfloat16() for _ in range(NQ)]
         qb = q.bfloat16()
-        K.infonce_tc_fwd(qb, queue, pos=kpos, scale=1 / T)
+        K.infonce_tc_fwd(qb, queues[0], pos=kpos, scale=1 / T)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
         gph = torch.cuda.CUDAGraph()
         st = torch.cuda.Stream()
         st.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(st):
-            K.infonce_tc_fwd(qb, queue, pos=kpos, scale=1 / T)
+            K.infonce_tc_fwd(qb, queues[0], pos=kpos, scale=1 / T)
             with torch.cuda.graph(gph, stream=st):
-                K.infonce_tc_fwd(qb, queue, pos=kpos, scale=1 / T)
+                for qq in queues:                         # one graph = NQ back-to-back forward calls over different queues
+                    K.infonce_tc_fwd(qb, qq, pos=kpos, scale=1 / T)
         torch.cuda.synchronize()
         ts = []
         for _ in range(20):
-            flush.zero_()                              # L2 flush between iterations (queue is 16.8 MB < L2)
+            flush.zero_()                              # L2 flush between replays
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             gph.replay()
             e.record()
             torch.cuda.synchronize()
-            ts.append(s.elapsed_time(e))
+            ts.append(s.elapsed_time(e) / NQ)
         ts.sort()
         t_med = ts[len(ts) // 2]
         alg_bytes = (2 * N * D + D * Kq) * 2 + 4 * N
         gbs = alg_bytes / (t_med / 1e3) / 1e9
-        line["roofline_infonce"] = {"kernel": "infonce_tc_fwd_kernel<2> + simce_finalize_kernel (MoCo C3: N=256, K=65536, D=128, bf16)",
+        line["roofline_infonce"] = {"kernel": "infonce_target_kernel + infonce_tc_fwd_kernel<2> + simce_finalize_kernel (MoCo C3: N=256, K=65536, D=128, bf16)",
                                     "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
                                     "traffic": None, "algorithmic_bytes": alg_bytes, "us_per_launch": t_med * 1e3,
-                                    "peak_source": pk["src"] + " (burst: kernel timed alone, L2 flushed between replays)"}
+                                    "peak_source": pk["src"] + " (burst)",
+                                    "method": "CUDA graph of %d forward calls over %d different queues (working set %d MB > L2, flushed "
+                                              "between replays), device time / %d" % (NQ, NQ, NQ * D * Kq * 2 >> 20, NQ)}
         # ---- cpu_baseline (N=1 only): bounded sample of the same iteration on the host cores -------------------------------
         if world == 1 and not args.no_cpu_baseline:
             ips, dt, cores = cpu_reference_step_time(1, 1, 8)

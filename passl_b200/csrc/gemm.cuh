@@ -73,10 +73,12 @@ struct GemmParams {
   const __nv_bfloat16* aux;     // same addressing as out
   int aux_mode;
   __nv_bfloat16* preact;        // optional: value before the activation (bias added), same addressing as out (GELU backward)
-  // optional per-column statistics of the stored bf16 value (BatchNorm batch stats): per-CTA partials [gridDim.x][2][N]
-  // (sum, sum of squares), zero-initialised by the host; CTA b only ever touches row b -> no atomics, deterministic per grid
+  // optional per-column statistics of the stored bf16 value (BatchNorm batch stats): partials [4 * gridDim.x][2][N] (sum, sum of
+  // squares), zero-initialised by the host; row 4*b + q is only touched by the two epilogue warps of lane quarter q of CTA b, on
+  // disjoint columns -> no atomics, deterministic per grid
   float* col_sum;
   float* col_sqsum;     // unused (kept for ABI stability of the struct users)
+  int dbg;              // developer perf experiments (PASSL_B200_EPI_DEBUG): 1 skip stats, 2 skip global stores, 4 skip staging
 };
 
 template <int BN, int BK, bool A_MN, bool B_MN>
@@ -313,12 +315,29 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     uint8_t* stg = epi_stage + e * (32 * kEpiStride);
     const uint32_t stg_u32 = smem_u32(stg);
     const bool staged = !p.out_fp32;
-    const bool do_stats = staged && p.col_sum != nullptr;
-    const int etid = (int)(e * 32 + lane);
-    if (do_stats) {
-      for (int i = etid; i < 2 * BN; i += 256) epi_stats[i] = 0.f;
-      epi_bar_sync();
-    }
+    const bool do_stats = staged && p.col_sum != nullptr && !(p.dbg & 1);
+    // BatchNorm statistics: per-warp register accumulators (lanes 0..15 own the column pairs of each of the warp's chunks), kept
+    // across tiles while the CTA stays on one column block and folded into the warp's own global partial row (row = CTA*4 + lane
+    // quarter; the two warps of a quarter own disjoint columns) — no atomics, no barriers
+    constexpr int NCH = (BN / 64) > 0 ? (BN / 64) : 1;        // 32-column chunks per epilogue warp
+    float sacc[NCH][4];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) { sacc[i][0] = 0.f; sacc[i][1] = 0.f; sacc[i][2] = 0.f; sacc[i][3] = 0.f; }
+    auto flush_stats = [&](int nblk_) {
+      float* part = p.col_sum + ((size_t)blockIdx.x * 4 + q) * 2 * p.N;
+      if (lane < 16) {
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+          const int col = nblk_ * BN + ((int)half + 2 * i) * 32 + (int)lane * 2;
+          if (col < p.N) {
+            part[col] += sacc[i][0]; part[col + 1] += sacc[i][1];
+            part[p.N + col] += sacc[i][2]; part[p.N + col + 1] += sacc[i][3];
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) { sacc[i][0] = 0.f; sacc[i][1] = 0.f; sacc[i][2] = 0.f; sacc[i][3] = 0.f; }
+    };
     int prev_nblk = -1;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -359,17 +378,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         col_base = (long long)tap * p.n_per_tap + c0;
       }
       if (do_stats && n_blk != prev_nblk) {
-        if (prev_nblk >= 0) {           // this CTA moves to another column block: fold its partial sums into its global row
-          epi_bar_sync();
-          float* part = p.col_sum + (size_t)blockIdx.x * 2 * p.N;
-          for (int i = etid; i < BN; i += 256) {
-            const int col = prev_nblk * BN + i;
-            if (col < p.N) { part[col] += epi_stats[i]; part[p.N + col] += epi_stats[BN + i]; }
-            epi_stats[i] = 0.f;
-            epi_stats[BN + i] = 0.f;
-          }
-          epi_bar_sync();
-        }
+        if (prev_nblk >= 0) flush_stats(prev_nblk);   // this CTA moves to another column block
         prev_nblk = n_blk;
       }
 
@@ -379,27 +388,36 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
 #pragma unroll
       for (int i = 0; i < 4; ++i) ro4[i] = __shfl_sync(0xffffffffu, row_off_pub, i * 8 + crow);
 
+      // residual tiles are fetched one chunk ahead with row-coalesced loads (8 rows x 64 B per instruction); the first one is
+      // issued before waiting for the accumulator so that its DRAM latency hides behind the MMA
+      const bool use_res = staged && p.residual != nullptr;
+      auto load_res = [&](int c_, uint4 (&dst)[4]) {
+        const bool okc = (c_ < BN / 32) && (col0 + c_ * 32 + cch * 8 < col_lim);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          dst[i] = make_uint4(0u, 0u, 0u, 0u);
+          if (ro4[i] >= 0 && okc) dst[i] = ld_nc_v4(p.residual + ro4[i] + col_base + c_ * 32 + cch * 8);
+        }
+      };
+      uint4 rr[4];
+      if (use_res) load_res((int)half, rr);
+
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((q * 32u) << 16) + acc * BN;
       const bool unit_alpha = p.alpha == 1.f;
-#pragma unroll 1
-      for (int c = (int)half; c < BN / 32; c += 2) {
+#pragma unroll
+      for (int ci = 0; ci < NCH; ++ci) {
+        const int c = (int)half + 2 * ci;
+        if (c >= BN / 32) break;
         const int cc0 = col0 + c * 32;           // logical column of v[0] (within tap)
         const long long oc0 = col_base + c * 32; // output column of v[0]
         if (cc0 >= col_lim) break;
         uint32_t v[32];
         tmem_ld_32x32(t_addr + c * 32, v);
-        // residual: row-coalesced loads (8 rows x 64 B per instruction) issued before waiting for the TMEM read
         const bool col_ok = cc0 + cch * 8 < col_lim;
-        uint4 rr[4];
-        if (staged && p.residual) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            rr[i] = make_uint4(0u, 0u, 0u, 0u);
-            if (ro4[i] >= 0 && col_ok) rr[i] = ld_nc_v4(p.residual + ro4[i] + oc0 + cch * 8);
-          }
-        }
+        uint4 rn[4];
+        if (use_res) load_res(c + 2, rn);        // next chunk of this warp
         tmem_ld_wait();
         float f[32];
         if (unit_alpha) {
@@ -480,7 +498,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           continue;
         }
         // ---- staged bf16 path ----
-        if (p.residual) {
+        if (use_res) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) st_shared_v4(stg_u32 + (i * 8 + crow) * kEpiStride + cch * 16, rr[i]);
           __syncwarp();
@@ -493,6 +511,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           }
           __syncwarp();
         }
+        if (p.dbg & 4) continue;
 #pragma unroll
         for (int j8 = 0; j8 < 4; ++j8) {
           uint4 u = make_uint4(0u, 0u, 0u, 0u);                 // rows outside the tensor contribute zeros to the statistics
@@ -512,25 +531,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           float sa = 0.f, sb = 0.f, qa = 0.f, qb = 0.f;
 #pragma unroll
           for (int rr_ = 0; rr_ < 16; ++rr_) {
-            const uint32_t wv = *reinterpret_cast<const uint32_t*>(stg + (rr_ * 2 + rpar) * kEpiStride + wsel * 4);
+            const uint32_t wv = ld_shared_u32(stg_u32 + (rr_ * 2 + rpar) * kEpiStride + wsel * 4);
             const float x0 = __uint_as_float(wv << 16), x1 = __uint_as_float(wv & 0xffff0000u);
             sa += x0; sb += x1;
             qa = fmaf(x0, x0, qa); qb = fmaf(x1, x1, qb);
           }
           sa += __shfl_xor_sync(0xffffffffu, sa, 16); sb += __shfl_xor_sync(0xffffffffu, sb, 16);
           qa += __shfl_xor_sync(0xffffffffu, qa, 16); qb += __shfl_xor_sync(0xffffffffu, qb, 16);
-          if (rpar == 0 && cc0 + (int)wsel * 2 < col_lim) {     // N % 8 == 0: column pairs are never split by the bound
-            atomicAdd(&epi_stats[c * 32 + wsel * 2], sa);
-            atomicAdd(&epi_stats[c * 32 + wsel * 2 + 1], sb);
-            atomicAdd(&epi_stats[BN + c * 32 + wsel * 2], qa);
-            atomicAdd(&epi_stats[BN + c * 32 + wsel * 2 + 1], qb);
-          }
+          sacc[ci][0] += sa; sacc[ci][1] += sb; sacc[ci][2] += qa; sacc[ci][3] += qb;
         }
         __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
+        if (!(p.dbg & 2)) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (ro4[i] >= 0 && col_ok)
-            *reinterpret_cast<uint4*>(outp + ro4[i] + oc0 + cch * 8) = ld_shared_v4(stg_u32 + (i * 8 + crow) * kEpiStride + cch * 16);
+          for (int i = 0; i < 4; ++i) {
+            if (ro4[i] >= 0 && col_ok)
+              *reinterpret_cast<uint4*>(outp + ro4[i] + oc0 + cch * 8) = ld_shared_v4(stg_u32 + (i * 8 + crow) * kEpiStride + cch * 16);
+          }
         }
         __syncwarp();
       }
@@ -538,14 +554,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
-    if (do_stats && prev_nblk >= 0) {
-      epi_bar_sync();
-      float* part = p.col_sum + (size_t)blockIdx.x * 2 * p.N;
-      for (int i = etid; i < BN; i += 256) {
-        const int col = prev_nblk * BN + i;
-        if (col < p.N) { part[col] += epi_stats[i]; part[p.N + col] += epi_stats[BN + i]; }
-      }
-    }
+    if (do_stats && prev_nblk >= 0) flush_stats(prev_nblk);
   }
 
   tc_fence_before();

@@ -1,4 +1,5 @@
 // C-ABI launchers for the tcgen05 GEMM / implicit-GEMM convolution kernel (see gemm.cuh).
+#include <stdlib.h>
 #include "gemm.cuh"
 #include "host_utils.h"
 #include "../../include/passl_b200.h"
@@ -19,9 +20,12 @@ static int launch_gemm_t(const GemmParams& p, cudaStream_t st) {
   int tiles = p.m_blocks * p.n_blocks * p.splits;
   int grid = tiles < num_sms() ? tiles : num_sms();
   if (grid <= 0) return PB_OK;
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("PASSL_B200_EPI_DEBUG"); dbg = e ? atoi(e) : 0; }
+  const_cast<GemmParams&>(p).dbg = dbg;
   if (p.col_sum) {
     if (p.out_fp32 || p.n_blocks_per_tap > 0 || p.splits != 1) return PB_ERR_UNSUPPORTED;
-    PB_CUDA_CHECK(cudaMemsetAsync(p.col_sum, 0, (size_t)num_sms() * 2 * p.N * sizeof(float), st));
+    PB_CUDA_CHECK(cudaMemsetAsync(p.col_sum, 0, (size_t)num_sms() * 4 * 2 * p.N * sizeof(float), st));
   }
   kern<<<grid, kGemmThreads, S::TOTAL, st>>>(p);
   PB_LAUNCH_CHECK();
@@ -163,7 +167,7 @@ extern "C" int passl_b200_gemm_bf16_ex(const void* A, const void* B, void* out, 
   return launch_gemm(p, BN, 64, a_mn_major != 0, b_mn_major != 0, (cudaStream_t)stream);
 }
 
-extern "C" int passl_b200_gemm_stats_rows(void) { return num_sms(); }
+extern "C" int passl_b200_gemm_stats_rows(void) { return 4 * num_sms(); }
 
 // ==============================================================================================
 // Convolution forward (implicit GEMM), NHWC bf16, weights [Cout, R, S, Cin] bf16.
