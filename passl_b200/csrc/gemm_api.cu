@@ -351,6 +351,10 @@ extern "C" int passl_b200_conv2d_dgrad_bf16(const void* dy, const void* w, void*
 //     sum_{n,p,q} dy[n,p,q,co] * x[n, p*stride + r - pad, q*stride + s - pad, ci]
 // K = output pixels (patch tiles), split across CTAs.
 // ==============================================================================================
+namespace pb {
+int launch_wgrad3x3_halo(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, cudaStream_t st);
+}
+
 static int conv_wgrad_impl(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int R, int S,
                            int stride, int pad_h, int pad_w, int Ho, int Wo, int zero_first, void* stream) {
   if (Cin % 8 || Cout % 8 || R * S > kMaxTaps || (stride != 1 && stride != 2)) return PB_ERR_UNSUPPORTED;
@@ -367,6 +371,15 @@ static int conv_wgrad_impl(const void* x, const void* dy, float* dw, int N, int 
     if (splits > kit / 4) splits = kit / 4 > 0 ? kit / 4 : 1;
     return passl_b200_gemm_bf16(dy, x, dw, Cout, Cin, P, 1, 1, Cout, Cin, Cin, 1, 1, nullptr, nullptr, ACT_NONE, 1.f,
                                 splits, nullptr, nullptr, stream);
+  }
+  if (R == 3 && S == 3 && stride == 1 && pad_h == 1 && pad_w == 1 && Ho == H && Wo == W) {
+    // halo-tile kernel (wgrad_halo.cu): one TMA halo load serves all taps; falls through when the shape is outside its contract
+    static int no_halo = -1;
+    if (no_halo < 0) { const char* e = getenv("PASSL_B200_NO_HALO"); no_halo = e ? atoi(e) : 0; }
+    if (!no_halo) {
+      int rc = launch_wgrad3x3_halo(x, dy, dw, N, H, W, Cin, Cout, st);
+      if (rc != PB_ERR_UNSUPPORTED) return rc;
+    }
   }
   GemmParams p;
   memset(&p, 0, sizeof(p));

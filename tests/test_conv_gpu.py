@@ -162,3 +162,23 @@ def test_stem_repack_conv_matches_conv7x7(N, HW):
     dw_ref = wr.grad.permute(0, 2, 3, 1).reshape(64, 147) + 1.0
     _check(dw[:, :147], dw_ref, "stem wgrad", rel=1e-2)
     assert torch.equal(dw[:, 147:], torch.zeros(64, 5, device="cuda"))
+
+
+@pytest.mark.parametrize("case", [(2, 56, 56, 64, 64, 3, 1, 1), (3, 13, 20, 64, 128, 3, 1, 1), (9, 14, 14, 256, 256, 3, 1, 1),
+                                  (2, 28, 28, 128, 72, 3, 1, 1), (33, 16, 16, 128, 128, 3, 1, 1)])
+def test_conv_wgrad_halo_tile_kernel(case):
+    """3x3 / stride 1 weight gradient through the halo-tile kernel (wgrad_halo.cu): ragged tiles (W % 16, H % 8 != 0), Cout < 128,
+    Cout % 64 != 0, many images (split-K), accumulation into a non-zero buffer."""
+    from passl_b200 import kernels as K_
+    N, H, W, Cin, Cout, R, stride, pad = case
+    g = torch.Generator(device="cuda").manual_seed(17)
+    x = torch.randn(N, H, W, Cin, device="cuda", generator=g).bfloat16()
+    dy = (torch.randn(N, H, W, Cout, device="cuda", generator=g) / (N * H * W) ** 0.5).bfloat16()
+    xr = x.float().permute(0, 3, 1, 2).contiguous()
+    wr = torch.zeros(Cout, Cin, 3, 3, device="cuda", requires_grad=True)
+    F.conv2d(xr, wr, stride=1, padding=1).backward(dy.float().permute(0, 3, 1, 2).contiguous())
+    dw_ref = wr.grad.permute(0, 2, 3, 1).contiguous()
+    dw = torch.full((Cout, 3, 3, Cin), 0.5, device="cuda")
+    K_.conv2d_wgrad(x, dy, (Cout, 3, 3, Cin), stride=1, pad=1, out=dw, accumulate=True)
+    torch.cuda.synchronize()
+    _check(dw, dw_ref + 0.5, "halo wgrad %s" % (case,), rel=1e-2)
