@@ -66,6 +66,9 @@ int passl_b200_gemm_bf16_ex(const void* A, const void* B, void* out, int M, int 
 int passl_b200_conv2d_fwd_bf16(const void* x, const void* w, void* out, int N, int H, int W, int Cin, int Cout, int R,
                                int S, int stride, int pad, const float* bias, const void* residual, int act,
                                float* col_sum, float* col_sqsum, void* stream);
+/* 3x3 / stride 1 / pad 1 weight gradients use the halo-tile kernel (wgrad_halo.cu) when the problem is large enough to amortise
+ * its per-item epilogue; tuning knob: 0 auto (default), 1 whenever the shape is supported, 2 never. */
+int passl_b200_wgrad_halo_mode(int mode);
 /* rectangular filter, separate row / column padding, explicit output extent, stride 1 (the repacked 7x7/2 stem below) */
 int passl_b200_conv2d_fwd_rect_bf16(const void* x, const void* w, void* out, int N, int H, int W, int Cin, int Cout, int R,
                                     int S, int pad_h, int pad_w, int Ho, int Wo, const float* bias, int act, float* col_sum,

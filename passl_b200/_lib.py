@@ -25,6 +25,7 @@ SIGNATURES = {
                                         c_void_p, c_int, c_void_p, c_void_p]),
     "passl_b200_conv2d_fwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 9 +
                                    [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "passl_b200_wgrad_halo_mode": (c_int, [c_int]),
     "passl_b200_conv2d_fwd_rect_bf16": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 11 + [c_void_p, c_int, c_void_p, c_void_p]),
     "passl_b200_conv2d_wgrad_rect_bf16": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 12 + [c_void_p]),
     "passl_b200_stem_pack_input": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

@@ -374,12 +374,8 @@ static int conv_wgrad_impl(const void* x, const void* dy, float* dw, int N, int 
   }
   if (R == 3 && S == 3 && stride == 1 && pad_h == 1 && pad_w == 1 && Ho == H && Wo == W) {
     // halo-tile kernel (wgrad_halo.cu): one TMA halo load serves all taps; falls through when the shape is outside its contract
-    static int no_halo = -1;
-    if (no_halo < 0) { const char* e = getenv("PASSL_B200_NO_HALO"); no_halo = e ? atoi(e) : 0; }
-    if (!no_halo) {
-      int rc = launch_wgrad3x3_halo(x, dy, dw, N, H, W, Cin, Cout, st);
-      if (rc != PB_ERR_UNSUPPORTED) return rc;
-    }
+    int rc = launch_wgrad3x3_halo(x, dy, dw, N, H, W, Cin, Cout, st);
+    if (rc != PB_ERR_UNSUPPORTED) return rc;
   }
   GemmParams p;
   memset(&p, 0, sizeof(p));

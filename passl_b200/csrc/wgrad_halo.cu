@@ -184,9 +184,11 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_halo_kernel(const __grid_cons
   }
 }
 
+int g_wgrad_halo_mode = 0;   // 0 auto (size heuristic), 1 always when the shape is supported, 2 never
+
 // returns PB_ERR_UNSUPPORTED when the shape is outside the kernel's contract (the caller then takes the generic path)
 int launch_wgrad3x3_halo(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, cudaStream_t st) {
-  if (Cin % 64 || Cout % 8 || H < 12 || W < 12) return PB_ERR_UNSUPPORTED;
+  if (g_wgrad_halo_mode == 2 || Cin % 64 || Cout % 8 || H < 12 || W < 12) return PB_ERR_UNSUPPORTED;
   WgradHaloParams p;
   memset(&p, 0, sizeof(p));
   p.dw = dw; p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
@@ -196,9 +198,13 @@ int launch_wgrad3x3_halo(const void* x, const void* dy, float* dw, int N, int H,
   p.m_blocks = (Cout + 127) / 128;
   p.ci_blocks = Cin / 64;
   const int base = p.m_blocks * p.ci_blocks * 2;
+  // every work item ends with a 128 x 320 fp32 red.add epilogue: it needs a long K loop to amortise it, and the grid needs enough
+  // items to fill the SMs — small batches stay on the generic kernel (measured: B=64 halo 2x slower, B=1024 halo 1.4x faster)
   int splits = (2 * num_sms() + base - 1) / base;
-  if (splits > p.k_total / 4) splits = p.k_total / 4;
+  const int min_iters = g_wgrad_halo_mode == 1 ? 2 : 24;
+  if (splits > p.k_total / min_iters) splits = p.k_total / min_iters;
   if (splits < 1) splits = 1;
+  if (g_wgrad_halo_mode != 1 && base * splits < (2 * num_sms()) / 3) return PB_ERR_UNSUPPORTED;
   p.splits = splits;
   {
     uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};
@@ -227,3 +233,9 @@ int launch_wgrad3x3_halo(const void* x, const void* dy, float* dw, int N, int H,
 }
 
 }  // namespace pb
+
+extern "C" int passl_b200_wgrad_halo_mode(int mode) {
+  if (mode < 0 || mode > 2) return PB_ERR_BAD_ARG;
+  pb::g_wgrad_halo_mode = mode;
+  return PB_OK;
+}

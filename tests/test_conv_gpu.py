@@ -169,7 +169,8 @@ def test_stem_repack_conv_matches_conv7x7(N, HW):
 def test_conv_wgrad_halo_tile_kernel(case):
     """3x3 / stride 1 weight gradient through the halo-tile kernel (wgrad_halo.cu): ragged tiles (W % 16, H % 8 != 0), Cout < 128,
     Cout % 64 != 0, many images (split-K), accumulation into a non-zero buffer."""
-    from passl_b200 import kernels as K_
+    from passl_b200 import kernels as K_, _lib
+    _lib.load().passl_b200_wgrad_halo_mode(1)                     # small test shapes would otherwise take the generic kernel
     N, H, W, Cin, Cout, R, stride, pad = case
     g = torch.Generator(device="cuda").manual_seed(17)
     x = torch.randn(N, H, W, Cin, device="cuda", generator=g).bfloat16()
@@ -179,6 +180,9 @@ def test_conv_wgrad_halo_tile_kernel(case):
     F.conv2d(xr, wr, stride=1, padding=1).backward(dy.float().permute(0, 3, 1, 2).contiguous())
     dw_ref = wr.grad.permute(0, 2, 3, 1).contiguous()
     dw = torch.full((Cout, 3, 3, Cin), 0.5, device="cuda")
-    K_.conv2d_wgrad(x, dy, (Cout, 3, 3, Cin), stride=1, pad=1, out=dw, accumulate=True)
-    torch.cuda.synchronize()
+    try:
+        K_.conv2d_wgrad(x, dy, (Cout, 3, 3, Cin), stride=1, pad=1, out=dw, accumulate=True)
+        torch.cuda.synchronize()
+    finally:
+        _lib.load().passl_b200_wgrad_halo_mode(0)
     _check(dw, dw_ref + 0.5, "halo wgrad %s" % (case,), rel=1e-2)
