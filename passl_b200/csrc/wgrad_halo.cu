@@ -235,7 +235,7 @@ int launch_wgrad3x3_halo(const void* x, const void* dy, float* dw, int N, int H,
 }  // namespace pb
 
 extern "C" int passl_b200_wgrad_halo_mode(int mode) {
-  if (mode < 0 || mode > 2) return PB_ERR_BAD_ARG;
+  if (mode < 0 || mode > 2) return pb::PB_ERR_BAD_ARG;
   pb::g_wgrad_halo_mode = mode;
-  return PB_OK;
+  return pb::PB_OK;
 }
