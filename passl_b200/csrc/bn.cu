@@ -26,7 +26,7 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 //   MODE 0 (stats)      : a = y,               second = y*y
 //   MODE 1 (bwd reduce) : a = dz*mask,         second = a * (y - mean) * invstd
 template <int MODE>
-__global__ void __launch_bounds__(256) bn_reduce_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dz,
+__global__ void __launch_bounds__(256, 2) bn_reduce_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dz,
                                  const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean,
                                  const float* __restrict__ invstd, float* __restrict__ part,
                                  long long P, int C, int rows_per_block, int relu) {
@@ -37,13 +37,13 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const __nv_bfloat16* __r
   float s0[8], s1[8], mu[8], is[8], sc[8], sh[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s0[i] = 0.f; s1[i] = 0.f; mu[i] = 0.f; is[i] = 1.f; sc[i] = 0.f; sh[i] = 0.f; }
-  if (MODE == 1 && cok) {
+  if (MODE >= 1 && cok) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) { mu[i] = mean[c0 + i]; is[i] = invstd[c0 + i]; }
   }
   // relu == 2: the ReLU mask is recomputed from y (z = relu(fma(y, scale, shift)) has no residual term), so z is never read;
   // the `z` argument then carries the fp32 [2, C] (scale, shift) rows of the forward pass
-  const bool recompute = (MODE == 1) && relu == 2;
+  constexpr bool recompute = (MODE == 2);                 // separate instantiation: the z-reading variant keeps its registers
   const bool read_z = (MODE == 1) && relu == 1;
   if (recompute && cok) {
     const float* ss = reinterpret_cast<const float*>(z);
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const __nv_bfloat16* __r
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         uy[u] = ld_nc_v4(y + (r + u * step) * C + c0);
-        if (MODE == 1) {
+        if (MODE >= 1) {
           ug[u] = ld_nc_v4(dz + (r + u * step) * C + c0);
           if (read_z) uz[u] = ld_nc_v4(z + (r + u * step) * C + c0);
         }
@@ -378,9 +378,14 @@ extern "C" int passl_b200_bn_bwd_reduce(const void* y, const void* dz, const voi
   if (relu && !z) return PB_ERR_BAD_ARG;
   dim3 grid, block; int rpb, smem;
   reduce_cfg(P, C, grid, block, rpb, smem);
-  bn_reduce_kernel<1><<<grid, block, smem, (cudaStream_t)stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<const __nv_bfloat16*>(dz),
-      reinterpret_cast<const __nv_bfloat16*>(z), mean, invstd, part, P, C, rpb, relu);
+  if (relu == 2)
+    bn_reduce_kernel<2><<<grid, block, smem, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<const __nv_bfloat16*>(dz),
+        reinterpret_cast<const __nv_bfloat16*>(z), mean, invstd, part, P, C, rpb, relu);
+  else
+    bn_reduce_kernel<1><<<grid, block, smem, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<const __nv_bfloat16*>(dz),
+        reinterpret_cast<const __nv_bfloat16*>(z), mean, invstd, part, P, C, rpb, relu);
   PB_LAUNCH_CHECK();
   return PB_OK;
 }

@@ -352,7 +352,8 @@ extern "C" int passl_b200_conv2d_dgrad_bf16(const void* dy, const void* w, void*
 // K = output pixels (patch tiles), split across CTAs.
 // ==============================================================================================
 namespace pb {
-int launch_wgrad3x3_halo(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, cudaStream_t st);
+int launch_wgrad_halo(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int R, int S, int pad_h,
+                      int pad_w, cudaStream_t st);
 }
 
 static int conv_wgrad_impl(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int R, int S,
@@ -372,9 +373,9 @@ static int conv_wgrad_impl(const void* x, const void* dy, float* dw, int N, int 
     return passl_b200_gemm_bf16(dy, x, dw, Cout, Cin, P, 1, 1, Cout, Cin, Cin, 1, 1, nullptr, nullptr, ACT_NONE, 1.f,
                                 splits, nullptr, nullptr, stream);
   }
-  if (R == 3 && S == 3 && stride == 1 && pad_h == 1 && pad_w == 1 && Ho == H && Wo == W) {
+  if (stride == 1 && Ho == H && Wo == W && R * S > 1) {
     // halo-tile kernel (wgrad_halo.cu): one TMA halo load serves all taps; falls through when the shape is outside its contract
-    int rc = launch_wgrad3x3_halo(x, dy, dw, N, H, W, Cin, Cout, st);
+    int rc = launch_wgrad_halo(x, dy, dw, N, H, W, Cin, Cout, R, S, pad_h, pad_w, st);
     if (rc != PB_ERR_UNSUPPORTED) return rc;
   }
   GemmParams p;

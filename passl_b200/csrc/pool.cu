@@ -77,7 +77,8 @@ __global__ void maxpool3x3s2_fwd_kernel(const __nv_bfloat16* __restrict__ x, __n
         const int w = ow * 2 + s - 1;
         if (w < 0 || w >= W) continue;
         float v[8];
-        unpack8p(ld_nc_v4(x + (((long long)n * H + h) * W + w) * C + cg * 8), v);
+        // L1-allocating load: the 3x3/2 windows of neighbouring outputs overlap (each input pixel is read 2.25x)
+        unpack8p(__ldg(reinterpret_cast<const uint4*>(x + (((long long)n * H + h) * W + w) * C + cg * 8)), v);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           if (v[j] > best[j] || arg[j] < 0) { best[j] = v[j]; arg[j] = r * 3 + s; }
@@ -115,9 +116,9 @@ __global__ void maxpool3x3s2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, co
         const int s = w - (ow * 2 - 1);
         if (s < 0 || s > 2) continue;
         const long long o = (((long long)n * Ho + oh) * Wo + ow) * C8 + cg;
-        uint2 a = *reinterpret_cast<const uint2*>(argmax + o * 8);
+        const uint2 a = __ldg(reinterpret_cast<const uint2*>(argmax + o * 8));   // cached: 4 input pixels share each window
         float g[8];
-        unpack8p(ld_nc_v4(dy + o * 8), g);
+        unpack8p(__ldg(reinterpret_cast<const uint4*>(dy + o * 8)), g);
         const int tap = r * 3 + s;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {

@@ -1,4 +1,4 @@
-// 3x3 / stride 1 / pad 1 convolution weight gradient with a HALO tile: one TMA load of the (8+2) x (16+2) input patch serves all
+// Stride-1 convolution weight gradient (3x3 pad 1; also the 4x1 repacked stem) with a HALO tile: one TMA load of the (8+R-1) x (16+S-1) input patch serves all
 // filter taps as row-shifted views of the same SWIZZLE_128B shared-memory tile (descriptor semantics pinned by umma_probe.cu).
 //
 //   dw[co, r, s, ci] += sum_{n,h,w} dy[n, h, w, co] * x[n, h + r - 1, w + s - 1, ci]      (resnetimagenet.py:112-131 conv2 backward)
@@ -35,9 +35,12 @@ struct WgradHaloParams {
   int hb, wb;            // pixel tiles per image
   int k_total;           // N * hb * wb
   int m_blocks, ci_blocks, splits;
+  int R, S, pad_h, pad_w;   // filter taps (R*S <= 10) and padding: halo tile = (TH + R - 1) x (TW + S - 1) pixels
+  int groups, tpg;          // tap groups per (m, ci) block and taps per group (<= 5: 5 x 64 TMEM columns)
+  int halo_w, halo_rows;
 };
 
-__global__ void __launch_bounds__(192, 1) wgrad3x3_halo_kernel(const __grid_constant__ WgradHaloParams p) {
+__global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constant__ WgradHaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WH_STAGES * WH_STAGE_BYTES);
@@ -46,7 +49,7 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_halo_kernel(const __grid_cons
   uint64_t* acc_empty = acc_full + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 1);
   const uint32_t warp = warp_id(), lane = lane_id();
-  const int total_items = p.m_blocks * p.ci_blocks * 2 * p.splits;
+  const int total_items = p.m_blocks * p.ci_blocks * p.groups * p.splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.dy_map);
@@ -69,8 +72,8 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_halo_kernel(const __grid_cons
   auto decode = [&](int item, int& m_blk, int& ci_blk, int& grp, int& k_begin, int& k_end) {
     const int split = item % p.splits;
     int rest = item / p.splits;
-    grp = rest & 1;
-    rest >>= 1;
+    grp = rest % p.groups;
+    rest /= p.groups;
     ci_blk = rest % p.ci_blocks;
     m_blk = rest / p.ci_blocks;
     k_begin = (int)(((long long)split * p.k_total) / p.splits);
@@ -92,11 +95,11 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_halo_kernel(const __grid_cons
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * WH_STAGE_BYTES;
         if (elect_one()) {
-          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(WH_A_BYTES + WH_HALO_ROWS * 128));
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(WH_A_BYTES + p.halo_rows * 128));
           const int h0 = ih * WH_TH, w0 = iw * WH_TW;
           tma_load_4d(sa, &p.dy_map, &full_bar[stage], m_blk * 128, w0, h0, n);
           tma_load_4d(sa + 128 * 128, &p.dy_map, &full_bar[stage], m_blk * 128 + 64, w0, h0, n);
-          tma_load_4d(sa + WH_A_BYTES, &p.x_map, &full_bar[stage], ci_blk * 64, w0 - 1, h0 - 1, n);
+          tma_load_4d(sa + WH_A_BYTES, &p.x_map, &full_bar[stage], ci_blk * 64, w0 - p.pad_w, h0 - p.pad_h, n);
         }
         __syncwarp();
         if (++iw == p.wb) { iw = 0; if (++ih == p.hb) { ih = 0; ++n; } }
@@ -114,7 +117,8 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_halo_kernel(const __grid_cons
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
       int m_blk, ci_blk, grp, k_begin, k_end;
       decode(item, m_blk, ci_blk, grp, k_begin, k_end);
-      const int tap0 = grp ? 5 : 0, ntap = grp ? 4 : 5;
+      const int tap0 = grp * p.tpg;
+      const int ntap = (p.R * p.S - tap0) < p.tpg ? (p.R * p.S - tap0) : p.tpg;
       mbar_wait(acc_empty, (it & 1) ^ 1);      // epilogue of the previous item has drained the accumulators
       tc_fence_after();
       for (int kt = k_begin; kt < k_end; ++kt) {
@@ -125,12 +129,12 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_halo_kernel(const __grid_cons
         if (elect_one()) {
           for (int t = 0; t < ntap; ++t) {
             const int tap = tap0 + t;
-            const int r = tap / 3, s = tap - r * 3;
+            const int r = tap / p.S, s = tap - r * p.S;
             const uint32_t d_tmem = tmem_base + t * 64;
 #pragma unroll
             for (int h = 0; h < WH_TH; ++h) {
               const uint64_t da = das + (uint64_t)((h * 16 * 128) >> 4);
-              const uint64_t db = dbs + (uint64_t)((((h + r) * (WH_TW + 2) + s) * 128) >> 4);
+              const uint64_t db = dbs + (uint64_t)((((h + r) * p.halo_w + s) * 128) >> 4);
               umma_bf16(d_tmem, da, db, idesc, (kt > k_begin || h > 0) ? 1u : 0u);
             }
           }
@@ -148,7 +152,8 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_halo_kernel(const __grid_cons
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
       int m_blk, ci_blk, grp, k_begin, k_end;
       decode(item, m_blk, ci_blk, grp, k_begin, k_end);
-      const int tap0 = grp ? 5 : 0, ntap = grp ? 4 : 5;
+      const int tap0 = grp * p.tpg;
+      const int ntap = (p.R * p.S - tap0) < p.tpg ? (p.R * p.S - tap0) : p.tpg;
       const int co = m_blk * 128 + (int)(q * 32 + lane);
       const bool row_ok = co < p.Cout;
       mbar_wait(acc_full, it & 1);
@@ -156,7 +161,7 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_halo_kernel(const __grid_cons
       if (k_end > k_begin) {
         for (int t = 0; t < ntap; ++t) {
           const int tap = tap0 + t;
-          float* dst = p.dw + ((size_t)co * 9 + tap) * p.Cin + ci_blk * 64;
+          float* dst = p.dw + ((size_t)co * (p.R * p.S) + tap) * p.Cin + ci_blk * 64;
 #pragma unroll 1
           for (int c = 0; c < 2; ++c) {
             uint32_t v[32];
@@ -187,17 +192,24 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_halo_kernel(const __grid_cons
 int g_wgrad_halo_mode = 0;   // 0 auto (size heuristic), 1 always when the shape is supported, 2 never
 
 // returns PB_ERR_UNSUPPORTED when the shape is outside the kernel's contract (the caller then takes the generic path)
-int launch_wgrad3x3_halo(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, cudaStream_t st) {
-  if (g_wgrad_halo_mode == 2 || Cin % 64 || Cout % 8 || H < 12 || W < 12) return PB_ERR_UNSUPPORTED;
+int launch_wgrad_halo(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int R, int S, int pad_h,
+                      int pad_w, cudaStream_t st) {
+  if (g_wgrad_halo_mode == 2 || Cin % 64 || Cout % 8 || H < 12 || W < 12 || R * S > 10 || R * S < 2) return PB_ERR_UNSUPPORTED;
   WgradHaloParams p;
   memset(&p, 0, sizeof(p));
   p.dw = dw; p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  p.R = R; p.S = S; p.pad_h = pad_h; p.pad_w = pad_w;
+  p.groups = (R * S + 4) / 5;
+  p.tpg = (R * S + p.groups - 1) / p.groups;
+  p.halo_w = WH_TW + S - 1;
+  p.halo_rows = (WH_TH + R - 1) * p.halo_w;
+  if (p.halo_rows * 128 > WH_B_BYTES) return PB_ERR_UNSUPPORTED;
   p.hb = (H + WH_TH - 1) / WH_TH;
   p.wb = (W + WH_TW - 1) / WH_TW;
   p.k_total = N * p.hb * p.wb;
   p.m_blocks = (Cout + 127) / 128;
   p.ci_blocks = Cin / 64;
-  const int base = p.m_blocks * p.ci_blocks * 2;
+  const int base = p.m_blocks * p.ci_blocks * p.groups;
   // every work item ends with a 128 x 320 fp32 red.add epilogue: it needs a long K loop to amortise it, and the grid needs enough
   // items to fill the SMs — small batches stay on the generic kernel (measured: B=64 halo 2x slower, B=1024 halo 1.4x faster)
   int splits = (2 * num_sms() + base - 1) / base;
@@ -216,18 +228,18 @@ int launch_wgrad3x3_halo(const void* x, const void* dy, float* dw, int N, int H,
   {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
     uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
-    uint32_t box[4] = {64, WH_TW + 2, WH_TH + 2, 1};
+    uint32_t box[4] = {64, (uint32_t)p.halo_w, (uint32_t)(WH_TH + R - 1), 1};
     int rc = make_tmap_bf16(&p.x_map, x, 4, dims, str, box);
     if (rc) return rc;
   }
   static bool attr = false;
   if (!attr) {
-    PB_CUDA_CHECK(cudaFuncSetAttribute(wgrad3x3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WH_SMEM));
+    PB_CUDA_CHECK(cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WH_SMEM));
     attr = true;
   }
   const int items = base * splits;
   const int grid = items < num_sms() ? items : num_sms();
-  wgrad3x3_halo_kernel<<<grid, 192, WH_SMEM, st>>>(p);
+  wgrad_halo_kernel<<<grid, 192, WH_SMEM, st>>>(p);
   PB_LAUNCH_CHECK();
   return PB_OK;
 }

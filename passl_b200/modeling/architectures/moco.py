@@ -29,9 +29,11 @@ def freeze_batchnorm_statictis(layer):
 
 @MODELS.register()
 class MoCo(nn.Module):
-    def __init__(self, backbone, neck=None, head=None, dim=128, K=65536, m=0.999, T=0.07, queue_dtype="bf16"):
+    def __init__(self, backbone, neck=None, head=None, dim=128, K=65536, m=0.999, T=0.07, queue_dtype="bf16",
+                 literal_shuffle_bn=False):
         super().__init__()
         self.K, self.m, self.T = K, m, T
+        self.literal_shuffle_bn = literal_shuffle_bn    # run the reference's shuffle protocol even though it cannot change k
         self.encoder_q = nn.Sequential(build_backbone(backbone), build_neck(neck))
         self.encoder_k = nn.Sequential(build_backbone(backbone), build_neck(neck))
         self.backbone = self.encoder_q[0]
@@ -83,6 +85,33 @@ class MoCo(nn.Module):
         self.flush_queue()
         return super().state_dict(*a, **kw)
 
+    # -- shuffle-BN (moco.py:107-152): same protocol over torch.distributed; off by default because encoder_k normalises with
+    #    global statistics, so k does not depend on which samples share a GPU -------------------------------------------------
+    @torch.no_grad()
+    def _batch_shuffle_ddp(self, x):
+        """all-gather the batch, rank 0 draws the permutation and broadcasts it, every rank keeps its slice of the shuffle."""
+        import torch.distributed as dist
+        from ...distributed import get_rank
+        batch_size_this = x.shape[0]
+        x_gather = concat_all_gather(x)
+        batch_size_all = x_gather.shape[0]
+        num_gpus = batch_size_all // batch_size_this
+        idx_shuffle = torch.randperm(batch_size_all, device=x.device)
+        if get_world_size() > 1:
+            dist.broadcast(idx_shuffle, src=0)
+        idx_unshuffle = torch.argsort(idx_shuffle)
+        idx_this = idx_shuffle.view(num_gpus, -1)[get_rank()]
+        return x_gather.index_select(0, idx_this), idx_unshuffle
+
+    @torch.no_grad()
+    def _batch_unshuffle_ddp(self, x, idx_unshuffle):
+        from ...distributed import get_rank
+        batch_size_this = x.shape[0]
+        x_gather = concat_all_gather(x)
+        num_gpus = x_gather.shape[0] // batch_size_this
+        idx_this = idx_unshuffle.view(num_gpus, -1)[get_rank()]
+        return x_gather.index_select(0, idx_this)
+
     def train_iter(self, *inputs, **kwargs):
         img_q, img_k = inputs
         self.flush_queue()
@@ -90,9 +119,13 @@ class MoCo(nn.Module):
         q = normalize(q)
         with torch.no_grad():
             self._momentum_update_key_encoder()
-            # shuffle-BN elided: encoder_k BN uses global statistics, results do not depend on batch composition
-            k = self.encoder_k(img_k)
-            k = normalize(k)
+            if self.literal_shuffle_bn and get_world_size() > 1:
+                im_k, idx_unshuffle = self._batch_shuffle_ddp(img_k)
+                k = normalize(self.encoder_k(im_k))
+                k = self._batch_unshuffle_ddp(k, idx_unshuffle)
+            else:   # elided: encoder_k BN uses global statistics, k does not depend on the batch composition
+                k = self.encoder_k(img_k)
+                k = normalize(k)
         queue = self._queue_bf16 if self._queue_bf16 is not None else self.queue
         outputs = self.head.forward_fused(q, k, queue)
         self._dequeue_and_enqueue(k)

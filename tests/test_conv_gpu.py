@@ -186,3 +186,29 @@ def test_conv_wgrad_halo_tile_kernel(case):
     finally:
         _lib.load().passl_b200_wgrad_halo_mode(0)
     _check(dw, dw_ref + 0.5, "halo wgrad %s" % (case,), rel=1e-2)
+
+
+def test_stem_wgrad_through_halo_kernel():
+    """The 4x1 repacked-stem weight gradient through the halo-tile kernel (rows padded (2, 1), no column taps)."""
+    from passl_b200 import kernels as K_, _lib
+    g = torch.Generator(device="cuda").manual_seed(9)
+    img = torch.randn(6, 3, 96, 96, device="cuda", generator=g)
+    w = torch.randn(64, 7, 7, 3, device="cuda", generator=g) / 147 ** 0.5
+    xp = K_.stem_pack_input(img)
+    dy = (torch.randn(6, 48, 48, 64, device="cuda", generator=g) / 100).bfloat16()
+    dw_generic = torch.zeros(64, 152, device="cuda")
+    _lib.load().passl_b200_wgrad_halo_mode(2)
+    try:
+        K_.stem_conv_wgrad(xp, dy, dw_generic)
+        _lib.load().passl_b200_wgrad_halo_mode(1)
+        dw_halo = torch.zeros(64, 152, device="cuda")
+        K_.stem_conv_wgrad(xp, dy, dw_halo)
+        torch.cuda.synchronize()
+    finally:
+        _lib.load().passl_b200_wgrad_halo_mode(0)
+    xr = img.bfloat16().float()
+    wr = w.permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    F.conv2d(xr, wr, stride=2, padding=3).backward(dy.float().permute(0, 3, 1, 2))
+    dw_ref = wr.grad.permute(0, 2, 3, 1).reshape(64, 147)
+    _check(dw_halo[:, :147], dw_ref, "stem wgrad halo", rel=1e-2)
+    _check(dw_generic[:, :147], dw_ref, "stem wgrad generic", rel=1e-2)

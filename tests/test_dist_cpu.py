@@ -58,6 +58,18 @@ def _worker(rank, world, port, ret):
         dist.all_reduce(t)
         full, _, _ = OC.mocov3_contrastive_loss(q_all, k_all, 0.2, rank=0)
         assert abs(t.item() / world - full) < 1e-12
+        # 5. shuffle-BN protocol (moco.py:107-152): one permutation shared by all ranks, un-shuffle restores every rank's own rows
+        from passl_b200.modeling.architectures.moco import MoCo
+        torch.manual_seed(100 + rank)                      # ranks draw DIFFERENT permutations; rank 0's must win (broadcast)
+        xs = (torch.arange(5).float()[:, None] + 100 * rank).repeat(1, 3)
+        sh, idx_un = MoCo._batch_shuffle_ddp(None, xs)
+        all_sh = D.concat_all_gather(sh)
+        assert sorted(all_sh[:, 0].tolist()) == sorted(D.concat_all_gather(xs)[:, 0].tolist())   # a permutation of the global batch
+        idx_all = [torch.zeros_like(idx_un) for _ in range(world)]
+        dist.all_gather(idx_all, idx_un)
+        assert all(torch.equal(i, idx_un) for i in idx_all)
+        back = MoCo._batch_unshuffle_ddp(None, sh, idx_un)
+        assert torch.equal(back, xs)
         ret[rank] = "ok"
     except Exception as e:  # pragma: no cover
         ret[rank] = repr(e)
