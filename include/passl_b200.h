@@ -165,7 +165,8 @@ int passl_b200_cast_bf16_to_f32(const void* x, float* y, long long n, void* stre
  *   bn_bwd_reduce : partials of sum_g = sum_p g, sum_gx = sum_p g*xhat with g = dz * (z>0 if relu).  relu: 0 none, 1 mask
  *                   read from z (bf16, needed when a residual was added before the ReLU), 2 mask recomputed from y as
  *                   fma(y, scale, shift) > 0 — `z` then points to the fp32 [2, C] (scale, shift) rows and the activation
- *                   tensor is never read (same convention in bn_bwd_apply)
+ *                   tensor is never read; 3 mask from the 1-bit-per-element tensor written by bn_apply_mask (`z` points to it):
+ *                   16x less traffic than reading z back for the residual units (same conventions in bn_bwd_apply)
  *   bn_bwd_finalize: sums [2,C] = totals (= dbeta, dgamma), accumulated into the gradient buffers when given
  *   bn_bwd_apply  : dy = gamma*invstd*(g - sum_g/P - xhat*sum_gx/P) = k1*g + k2*y + k3; dres = g (residual-branch gradient)
  * ------------------------------------------------------------------------------------------------------------- */
@@ -181,6 +182,8 @@ int passl_b200_bn_global_affine(const float* running_mean, const float* running_
 int passl_b200_axpy_f32(float* y, const float* x, float a, long long n, void* stream);
 int passl_b200_bn_apply(const void* y, const void* residual, const float* scale, const float* shift, void* z, float* z_f32,
                         long long P, int C, int relu, void* stream);
+int passl_b200_bn_apply_mask(const void* y, const void* residual, const float* scale, const float* shift, void* z, void* relu_mask,
+                             long long P, int C, int relu, void* stream);
 int passl_b200_bn_bwd_reduce(const void* y, const void* dz, const void* z, const float* mean, const float* invstd,
                              float* part, long long P, int C, int relu, void* stream);
 /* gamma / mean / invstd / count / coef may be NULL/0 (LayerNorm and bias-gradient uses); with them, coef [3, C] receives the

@@ -62,6 +62,7 @@ SIGNATURES = {
     "passl_b200_bn_global_affine": (c_int, [c_void_p] * 8 + [c_float, c_int, c_void_p]),
     "passl_b200_axpy_f32": (c_int, [c_void_p, c_void_p, c_float, c_ll, c_void_p]),
     "passl_b200_bn_apply": (c_int, [c_void_p] * 6 + [c_ll, c_int, c_int, c_void_p]),
+    "passl_b200_bn_apply_mask": (c_int, [c_void_p] * 6 + [c_ll, c_int, c_int, c_void_p]),
     "passl_b200_bn_bwd_reduce": (c_int, [c_void_p] * 6 + [c_ll, c_int, c_int, c_void_p]),
     "passl_b200_bn_bwd_apply": (c_int, [c_void_p] * 6 + [c_ll, c_int, c_int, c_void_p]),
     "passl_b200_mae_random_masking": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),

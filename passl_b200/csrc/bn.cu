@@ -45,6 +45,9 @@ __global__ void __launch_bounds__(256, 2) bn_reduce_kernel(const __nv_bfloat16* 
   // the `z` argument then carries the fp32 [2, C] (scale, shift) rows of the forward pass
   constexpr bool recompute = (MODE == 2);                 // separate instantiation: the z-reading variant keeps its registers
   const bool read_z = (MODE == 1) && relu == 1;
+  constexpr bool read_bits = (MODE == 3);                 // relu == 3: `z` carries the 1-bit-per-element mask written by bn_apply_mask
+  const unsigned char* zbits = reinterpret_cast<const unsigned char*>(z);
+  const int C8r = C / 8;
   if (recompute && cok) {
     const float* ss = reinterpret_cast<const float*>(z);
 #pragma unroll
@@ -59,12 +62,14 @@ __global__ void __launch_bounds__(256, 2) bn_reduce_kernel(const __nv_bfloat16* 
     const long long step = blockDim.y;
     for (; r + (U - 1) * step < r_end; r += U * step) {
       uint4 uy[U], ug[U], uz[U];
+      unsigned ub[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         uy[u] = ld_nc_v4(y + (r + u * step) * C + c0);
         if (MODE >= 1) {
           ug[u] = ld_nc_v4(dz + (r + u * step) * C + c0);
           if (read_z) uz[u] = ld_nc_v4(z + (r + u * step) * C + c0);
+          if (read_bits) ub[u] = zbits[(r + u * step) * C8r + cg];
         }
       }
 #pragma unroll
@@ -85,6 +90,9 @@ __global__ void __launch_bounds__(256, 2) bn_reduce_kernel(const __nv_bfloat16* 
           } else if (recompute) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) g[i] = fmaf(a[i], sc[i], sh[i]) > 0.f ? g[i] : 0.f;
+          } else if (read_bits) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g[i] = ((ub[u] >> i) & 1u) ? g[i] : 0.f;
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) { s0[i] += g[i]; s1[i] = fmaf(g[i], (a[i] - mu[i]) * is[i], s1[i]); }
@@ -108,6 +116,10 @@ __global__ void __launch_bounds__(256, 2) bn_reduce_kernel(const __nv_bfloat16* 
         } else if (recompute) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) g[i] = fmaf(a[i], sc[i], sh[i]) > 0.f ? g[i] : 0.f;
+        } else if (read_bits) {
+          const unsigned mb = zbits[r * C8r + cg];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g[i] = ((mb >> i) & 1u) ? g[i] : 0.f;
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) { s0[i] += g[i]; s1[i] = fmaf(g[i], (a[i] - mu[i]) * is[i], s1[i]); }
@@ -168,7 +180,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ part, int nblk,
 __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ residual,
                                 const float* __restrict__ scale, const float* __restrict__ shift,
                                 __nv_bfloat16* __restrict__ z, float* __restrict__ z_f32, long long total8, int C8,
-                                int relu) {
+                                int relu, unsigned char* __restrict__ mask) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
     const int c0 = (int)(i % C8) * 8;
     float a[8];
@@ -182,6 +194,12 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const __nv_
       unpack8(ld_nc_v4(residual + i * 8), r);
 #pragma unroll
       for (int j = 0; j < 8; ++j) a[j] += r[j];
+    }
+    if (mask) {             // 1 bit per element: the ReLU mask the backward needs (16x smaller than reading z back)
+      unsigned m = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m |= (a[j] > 0.f ? 1u : 0u) << j;
+      mask[i] = (unsigned char)m;
     }
     if (relu) {
 #pragma unroll
@@ -211,6 +229,10 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, const _
       unpack8(ld_nc_v4(z + i * 8), zz);
 #pragma unroll
       for (int j = 0; j < 8; ++j) g[j] = zz[j] > 0.f ? g[j] : 0.f;
+    } else if (relu == 3) {       // `z` carries the 1-bit-per-element mask written by bn_apply_mask
+      const unsigned mb = reinterpret_cast<const unsigned char*>(z)[i];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = ((mb >> j) & 1u) ? g[j] : 0.f;
     } else if (relu == 2) {       // mask recomputed from y: `z` carries fp32 [2, C] (scale, shift)
       const float* ss = reinterpret_cast<const float*>(z);
       const float4 sa = *reinterpret_cast<const float4*>(ss + c0), sb = *reinterpret_cast<const float4*>(ss + c0 + 4);
@@ -366,7 +388,19 @@ extern "C" int passl_b200_bn_apply(const void* y, const void* residual, const fl
   long long total8 = P * (C / 8);
   bn_apply_kernel<<<ew_blocks(total8), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<const __nv_bfloat16*>(residual), scale, shift,
-      reinterpret_cast<__nv_bfloat16*>(z), z_f32, total8, C / 8, relu);
+      reinterpret_cast<__nv_bfloat16*>(z), z_f32, total8, C / 8, relu, nullptr);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+// same + relu_mask [P*C/8] bytes: bit j of byte i = (pre-ReLU value of element 8i+j > 0)
+extern "C" int passl_b200_bn_apply_mask(const void* y, const void* residual, const float* scale, const float* shift, void* z,
+                                        void* relu_mask, long long P, int C, int relu, void* stream) {
+  if (P <= 0 || C <= 0 || C % 8 || !relu_mask) return PB_ERR_BAD_ARG;
+  long long total8 = P * (C / 8);
+  bn_apply_kernel<<<ew_blocks(total8), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<const __nv_bfloat16*>(residual), scale, shift,
+      reinterpret_cast<__nv_bfloat16*>(z), nullptr, total8, C / 8, relu, reinterpret_cast<unsigned char*>(relu_mask));
   PB_LAUNCH_CHECK();
   return PB_OK;
 }
@@ -378,7 +412,11 @@ extern "C" int passl_b200_bn_bwd_reduce(const void* y, const void* dz, const voi
   if (relu && !z) return PB_ERR_BAD_ARG;
   dim3 grid, block; int rpb, smem;
   reduce_cfg(P, C, grid, block, rpb, smem);
-  if (relu == 2)
+  if (relu == 3)
+    bn_reduce_kernel<3><<<grid, block, smem, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<const __nv_bfloat16*>(dz),
+        reinterpret_cast<const __nv_bfloat16*>(z), mean, invstd, part, P, C, rpb, relu);
+  else if (relu == 2)
     bn_reduce_kernel<2><<<grid, block, smem, (cudaStream_t)stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<const __nv_bfloat16*>(dz),
         reinterpret_cast<const __nv_bfloat16*>(z), mean, invstd, part, P, C, rpb, relu);

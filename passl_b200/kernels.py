@@ -338,7 +338,19 @@ def bn_apply(y, msss, relu, residual=None, out=None, out_f32=None):
     return out if out is not None else out_f32
 
 
-def bn_bwd(y, dz, z, msss, gamma, relu, want_dres=False, dgamma=None, dbeta=None):
+def bn_apply_mask(y, msss, residual=None):
+    """z = relu(y*scale + shift + residual) plus the ReLU mask as 1 bit per element (uint8 [P*C/8]) for the backward."""
+    lib = _lib.load()
+    C = y.shape[-1]
+    P = y.numel() // C
+    out = torch.empty_like(y)
+    mask = torch.empty(P * C // 8, dtype=torch.uint8, device=y.device)
+    _lib.check(lib.passl_b200_bn_apply_mask(_ptr(y), _ptr(residual), _ptr(msss[2]), _ptr(msss[3]), _ptr(out), _ptr(mask), P, C, 1,
+                                            _stream()), "bn_apply_mask")
+    return out, mask
+
+
+def bn_bwd(y, dz, z, msss, gamma, relu, want_dres=False, dgamma=None, dbeta=None, mask_bits=None):
     """Returns (dy, dres, sums) with sums fp32 [2, C] = (dbeta, dgamma) of this call; when the fp32 gradient buffers
     dgamma / dbeta are given the totals are accumulated into them by the same tiny kernel."""
     lib = _lib.load()
@@ -347,7 +359,9 @@ def bn_bwd(y, dz, z, msss, gamma, relu, want_dres=False, dgamma=None, dbeta=None
     nblk = lib.passl_b200_bn_reduce_blocks(P, C)
     part = torch.empty((nblk, 2, C), dtype=torch.float32, device=y.device)
     relu = int(relu)
-    if relu and not want_dres:
+    if relu and mask_bits is not None:
+        relu, z = 3, mask_bits          # 1-bit mask from bn_apply_mask: the activation tensor is never read
+    elif relu and not want_dres:
         # no residual entered the ReLU: z = relu(fma(y, scale, shift)) — recompute the mask from y, never read z (msss rows 2, 3)
         relu, z = 2, msss[2:4]
     _lib.check(lib.passl_b200_bn_bwd_reduce(_ptr(y), _ptr(dz), _ptr(z), _ptr(msss[0]), _ptr(msss[1]), _ptr(part), P, C,

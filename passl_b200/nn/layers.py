@@ -67,19 +67,24 @@ class ConvBN(nn.Module):
         else:
             y = K.conv2d_fwd(x, w, stride=self.stride, pad=self.pad)
             msss = bn.global_affine()
-        z = K.bn_apply(y, msss, self.relu, residual=residual)
-        ctx = (x, y, z, msss, residual is not None, batch_stats) if save else None
+        mask = None
+        if residual is not None and self.relu and save:
+            # residual units: the backward needs relu'(.) of the SUM — keep it as 1 bit per element instead of re-reading z
+            z, mask = K.bn_apply_mask(y, msss, residual=residual)
+        else:
+            z = K.bn_apply(y, msss, self.relu, residual=residual)
+        ctx = (x, y, z if mask is None else None, msss, residual is not None, batch_stats, mask) if save else None
         return z, ctx
 
     def bwd(self, ctx, dz, need_dx=True, dx_out=None, accumulate=False):
         """Returns (dx, dres).  dx is written into dx_out (accumulated when accumulate) if given."""
-        x, y, z, msss, has_res, batch_stats = ctx
+        x, y, z, msss, has_res, batch_stats, mask = ctx
         bn = self.bn
         assert batch_stats, "backward through a use_global_stats BatchNorm is not on the training path"
         train_bn = bn.weight is not None and bn.weight.requires_grad
         dy, dres, _ = K.bn_bwd(y, dz, z, msss, bn.weight, self.relu, want_dres=has_res,
                                dgamma=grad_buffer(bn.weight) if train_bn else None,
-                               dbeta=grad_buffer(bn.bias) if train_bn else None)
+                               dbeta=grad_buffer(bn.bias) if train_bn else None, mask_bits=mask)
         if self.weight.requires_grad:
             with side_stream(x, dy):      # off the dgrad critical path: overlaps the next unit's HBM-bound BN backward
                 K.conv2d_wgrad(x, dy, tuple(self.weight.shape), stride=self.stride, pad=self.pad,
