@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+bash tools/gpu_check.sh tests/test_gemm_gpu.py tests/test_conv_gpu.py 2>&1 | grep -E "^==|passed|failed|^E  |Error" | head -30
+timeout 120 python tools/epi_probe.py 2>&1 | tail -1
+timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_1gpu.log 2>&1; tail -1 gpurun_out/bench_1gpu.log | cut -c1-300
