@@ -84,3 +84,22 @@ def test_known_answers():
     full, _, _ = OC.mocov3_contrastive_loss(qa, ka, 0.2, rank=0)
     parts = [OC.mocov3_contrastive_loss(qa[r * 8:(r + 1) * 8], ka, 0.2, rank=r)[0] for r in range(4)]
     np.testing.assert_allclose(np.mean(parts), full, rtol=1e-12)
+
+
+def test_clip_torch_twin_matches_reference_head():
+    """oracle/clip.py (the differentiable torch twin used by the GPU model tests) reproduces the reference CLIPHead golden values and
+    the logit_scale clamp of clip.py:316-318."""
+    import torch
+    import oracle.clip as OCL
+    img = torch.tensor(G["clip_img"], dtype=torch.float64)
+    txt = torch.tensor(G["clip_txt"], dtype=torch.float64)
+    ls = torch.tensor([float(G["clip_logit_scale"])], dtype=torch.float64)
+    il, tl, ls_after = OCL.clip_forward(img, txt, ls)
+    o = OCL.clip_head(il, tl)
+    np.testing.assert_allclose(o["img_loss"].item(), G["clip_img_loss"], rtol=1e-9)
+    np.testing.assert_allclose(o["text_loss"].item(), G["clip_text_loss"], rtol=1e-9)
+    np.testing.assert_allclose(o["loss"].item(), G["clip_loss"], rtol=1e-9)
+    assert ls_after.item() == ls.item()                                  # ln(1/0.07) = 2.659 is inside [-4.6, 4.6]
+    assert OCL.clip_forward(img, txt, torch.tensor([7.0], dtype=torch.float64))[2].item() == 4.6
+    m = OCL.build_attention_mask(5)
+    assert torch.isinf(m[0, 1]) and m[1, 0] == 0 and m[3, 3] == 0          # clip.py:293-295: strictly upper triangle = -inf

@@ -64,3 +64,15 @@ if what == "c3":
     for i in range(3):
         K.gemm(y, w2, out=y2)
     torch.cuda.synchronize()
+
+if what == "c3res":
+    M = 256 * 56 * 56
+    x = torch.randn(M, 64, device="cuda").bfloat16()
+    w = torch.randn(256, 64, device="cuda").bfloat16()
+    res = torch.randn(M, 256, device="cuda").bfloat16()
+    y = torch.empty(M, 256, device="cuda", dtype=torch.bfloat16)
+    for i in range(2):
+        K.gemm(x, w, out=y, residual=res)
+    for i in range(2):
+        K.gemm(x, w, out=y)
+    torch.cuda.synchronize()
