@@ -81,6 +81,11 @@ struct GemmParams {
   // disjoint columns -> no atomics, deterministic per grid
   float* col_sum;
   float* col_sqsum;     // unused (kept for ABI stability of the struct users)
+  // residual through the tensor pipe: when res_iters > 0 the producer appends res_iters (= 128 / 64) pipeline iterations per tile
+  // that load an identity slice as A and the residual tile (MN-major) as B, so that D += I * R — the residual is prefetched as
+  // deep as the operands (a register prefetch in the epilogue cannot cover the ~4 us DRAM latency of a saturated HBM)
+  CUtensorMap res_map, eye_map;
+  int res_iters;
   int dbg;              // developer perf experiments (PASSL_B200_EPI_DEBUG): 1 skip stats, 2 skip global stores, 4 skip staging
 };
 
@@ -197,6 +202,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       // ================= TMA producer =================
       int stage = 0;
       uint32_t phase = 0;
+      auto produce_residual = [&](int m_blk, int n_blk) {
+        for (int r = 0; r < p.res_iters; ++r) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * S::STAGE_BYTES;
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(S::A_BYTES + S::B_BYTES));
+            tma_load_2d(sa, &p.eye_map, &full_bar[stage], r * 64, 0);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(sa + S::A_BYTES + j * (64 * 128), &p.res_map, &full_bar[stage], n_blk * BN + 64 * j, m_blk * 128 + r * 64);
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      };
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int split = tile % p.splits;
         int rest = tile / p.splits;
@@ -254,6 +274,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
+        produce_residual(m_blk, n_blk);
       }
     }
   } else if (warp == 1) {
@@ -268,6 +289,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       constexpr uint64_t kStepA = (A_MN ? 2048 : 32) >> 4, kStepB = (B_MN ? 2048 : 32) >> 4;
       constexpr uint64_t kStage = S::STAGE_BYTES >> 4;
       constexpr int KSTEPS_FULL = BK / 16;
+      // residual iterations: A = identity slice (K-major), B = residual rows (MN-major, 64-column chunks 8 KB apart)
+      constexpr uint32_t idesc_res = make_idesc_bf16(128, BN, false, true);
+      const uint64_t da_res0 = make_smem_desc_sw128(smem0, 16, 1024);
+      const uint64_t db_res0 = make_smem_desc_sw128(smem0 + S::A_BYTES, 64 * 128, 1024);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -296,7 +321,23 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                 umma_bf16(d_tmem, da + k * kStepA, db + k * kStepB, idesc, (kit > k_begin || k > 0) ? 1u : 0u);
             }
             umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
-            if (kit == k_end - 1) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+            if (kit == k_end - 1 && p.res_iters == 0) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+          }
+          __syncwarp();
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        for (int r = 0; r < p.res_iters; ++r) {       // D += I * R  (64 residual rows per iteration)
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = da_res0 + (uint64_t)stage * kStage, db = db_res0 + (uint64_t)stage * kStage;
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + k * 2, db + k * 128, idesc_res, 1u);
+            umma_commit(&empty_bar[stage]);
+            if (r == p.res_iters - 1) umma_commit(&tmem_full[acc]);
           }
           __syncwarp();
           if (++stage == STAGES) {
@@ -393,7 +434,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
 
       // residual tiles are fetched one chunk ahead with row-coalesced loads (8 rows x 64 B per instruction); the first one is
       // issued before waiting for the accumulator so that its DRAM latency hides behind the MMA
-      const bool use_res = staged && p.residual != nullptr;
+      const bool use_res = staged && p.residual != nullptr && p.res_iters == 0;
       auto load_res = [&](int c_, uint4 (&dst)[4]) {
         const bool okc = (c_ < BN / 32) && (col0 + c_ * 32 + cch * 8 < col_lim);
 #pragma unroll

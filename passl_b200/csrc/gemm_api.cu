@@ -8,6 +8,51 @@
 
 namespace pb {
 
+// 128 x 128 bf16 identity used as the A operand of the residual-through-the-tensor-pipe iterations (gemm.cuh, res_iters)
+__device__ __nv_bfloat16 g_eye128[128 * 128];
+__global__ void eye128_init_kernel() {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 128 * 128) g_eye128[i] = __float2bfloat16_rn((i / 128) == (i % 128) ? 1.f : 0.f);
+}
+static int eye128_ptr(const void** out, cudaStream_t st) {
+  static void* ptr = nullptr;
+  if (!ptr) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    PB_CUDA_CHECK(cudaStreamIsCapturing(st, &cs));
+    if (cs != cudaStreamCaptureStatusNone) { *out = nullptr; return PB_OK; }   // cannot initialise inside a capture: epilogue path
+    PB_CUDA_CHECK(cudaGetSymbolAddress(&ptr, g_eye128));
+    eye128_init_kernel<<<64, 256, 0, st>>>();
+    PB_LAUNCH_CHECK();
+    PB_CUDA_CHECK(cudaStreamSynchronize(st));     // once per process: later launches may come from other streams
+  }
+  *out = ptr;
+  return PB_OK;
+}
+
+// route the residual through the MMA when the epilogue semantics allow it (out = A.B + bias + residual, bf16, plain row-major)
+static int setup_residual_mma(GemmParams& p, const void* residual, long long ldc, cudaStream_t st) {
+  p.res_iters = 0;
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("PASSL_B200_NO_RES_MMA"); off = e ? atoi(e) : 0; }
+  if (off || !residual || p.out_fp32 || p.out_pixel || p.act != ACT_NONE || p.alpha != 1.f || p.aux || p.preact || p.splits != 1 ||
+      p.n_blocks_per_tap > 0 || (reinterpret_cast<uintptr_t>(residual) & 15))
+    return PB_OK;
+  const void* eye = nullptr;
+  int rc = eye128_ptr(&eye, st);
+  if (rc) return rc;
+  if (!eye) return PB_OK;
+  uint64_t ed[2] = {128, 128}, es[1] = {256};
+  uint32_t eb[2] = {64, 128};
+  rc = make_tmap_bf16(&p.eye_map, eye, 2, ed, es, eb);
+  if (rc) return rc;
+  uint64_t rd[2] = {(uint64_t)p.N, (uint64_t)p.M}, rs[1] = {(uint64_t)ldc * 2};
+  uint32_t rb[2] = {64, 64};
+  rc = make_tmap_bf16(&p.res_map, residual, 2, rd, rs, rb);
+  if (rc) return rc;
+  p.res_iters = 2;
+  return PB_OK;
+}
+
 template <int BN, int BK, bool A_MN, bool B_MN>
 static int launch_gemm_t(const GemmParams& p, cudaStream_t st) {
   using S = GemmSmem<BN, BK, A_MN, B_MN>;
@@ -164,6 +209,8 @@ extern "C" int passl_b200_gemm_bf16_ex(const void* A, const void* B, void* out, 
   p.aux = reinterpret_cast<const __nv_bfloat16*>(aux);
   p.aux_mode = aux_mode;
   p.preact = reinterpret_cast<__nv_bfloat16*>(preact_out);
+  r = setup_residual_mma(p, residual, ldc, (cudaStream_t)stream);
+  if (r) return r;
   return launch_gemm(p, BN, 64, a_mn_major != 0, b_mn_major != 0, (cudaStream_t)stream);
 }
 
