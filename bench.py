@@ -303,8 +303,18 @@ def run_ours(args):
                 ach, peak, unit = fl / (ms_k / 1e3) / 1e12 if ms_k else 0.0, pk["bf16_sustained"], "TFLOP/s"
             else:
                 ach, peak, unit = by / (ms_k / 1e3) / 1e9 if ms_k else 0.0, pk["hbm_gbs"], "GB/s"
+            # traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE representative launch of the class from the committed
+            # `ncu --set full` capture (profiles/r01_ncu_c3_full_summary.txt): hbm class = 1x1 conv 64->256 at 56^2, B=256
+            # (M=802816, N=256, K=64, fused BN statistics): 104.1 MB read + 357.7 MB written by kernel end vs 102.8 + 411.0 MB
+            # algorithmic (the rest of the output is still dirty in L2) — no re-reads.  tensor class: 3x3 conv 64->64 at 56^2, B=128
+            # (profiles/r01_ncu_conv_full_summary.txt): 51.5 MB read vs 51.4 MB algorithmic input.
+            traffic = {"hbm": {"bytes": 461.8e6, "algorithmic_bytes": 513.8e6, "launch": "gemm<256,64,0,0> M=802816 N=256 K=64 +BN stats",
+                               "source": "profiles/r01_ncu_c3_full_summary.txt"},
+                       "tensor": {"bytes": 57.2e6, "algorithmic_bytes": 102.8e6, "launch": "conv3x3 64->64 56^2 B=128 fwd",
+                                  "source": "profiles/r01_ncu_conv_full_summary.txt"}}[k]
             return {"kernel": "gemm_tcgen05_kernel (implicit-GEMM conv fwd/dgrad/wgrad + linears), %s-bound launches" % k,
-                    "bound": k, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "traffic": None,
+                    "bound": k, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "traffic": traffic["bytes"],
+                    "traffic_detail": traffic,
                     "peak_source": pk["src"], "launches": nl, "share_of_step": ms_k / (ms / args.steps)}
         dom = "hbm" if cls["hbm"][0] >= cls["tensor"][0] else "tensor"
         other = "tensor" if dom == "hbm" else "hbm"
@@ -351,7 +361,8 @@ def run_ours(args):
         gbs = alg_bytes / (t_med / 1e3) / 1e9
         line["roofline_infonce"] = {"kernel": "infonce_target_kernel + infonce_tc_fwd_kernel<2> + simce_finalize_kernel (MoCo C3: N=256, K=65536, D=128, bf16)",
                                     "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
-                                    "traffic": None, "algorithmic_bytes": alg_bytes, "us_per_launch": t_med * 1e3,
+                                    # dram__bytes_read.sum + write of infonce_tc_fwd_kernel, profiles/r01_ncu_full_infonce_run8.txt
+                                    "traffic": 17.04e6, "algorithmic_bytes": alg_bytes, "us_per_launch": t_med * 1e3,
                                     "peak_source": pk["src"] + " (burst)",
                                     "method": "CUDA graph of %d forward calls over %d different queues (working set %d MB > L2, flushed "
                                               "between replays), device time / %d" % (NQ, NQ, NQ * D * Kq * 2 >> 20, NQ)}
