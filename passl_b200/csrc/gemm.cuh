@@ -33,8 +33,6 @@ constexpr int kEpiWarps = 8;                       // epilogue warps (2 per TMEM
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 constexpr int kEpiStride = 80;                     // bytes per staged row: 32 bf16 + 16 B pad (conflict-free 16 B accesses)
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory"); }
-
 
 struct PatchGeom {
   int TN, TH, TW;    // patch box: images x rows x cols  (TN*TH*TW <= 128)
@@ -100,8 +98,7 @@ struct GemmSmem {
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int BAR_BYTES = 256;
   static constexpr int EPI_BYTES = kEpiWarps * 32 * kEpiStride;          // per-warp staging tiles of the epilogue
-  static constexpr int STAT_BYTES = 2 * BN * 4;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + STAT_BYTES + 1024;  // + alignment slack
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024;  // + alignment slack
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 };
 
@@ -163,7 +160,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   uint8_t* epi_stage = smem + STAGES * S::STAGE_BYTES + S::BAR_BYTES;              // 8 warps x 32 rows x kEpiStride
-  float* epi_stats = reinterpret_cast<float*>(epi_stage + S::EPI_BYTES);             // [2][BN] column sum / sum of squares
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();

@@ -3,8 +3,10 @@ hooks/log_hook.py): `Trainer(cfg).train()` iterates `outputs = model(*data)`, `o
 optimizer step, LR schedule and the `ips: ... images/sec` log line the reference's CI greps (passl/engine/loops/loop.py:102-118).
 
 Only what the hot path needs is here: synthetic or user-supplied iterables of (view_q, view_k) batches, the name-based model
-registry, the fused optimizers and the data-parallel gradient exchange.  Checkpoint / evaluation hooks are out of scope for
-round 1."""
+registry, the fused optimizers, the data-parallel gradient exchange and checkpoint / resume in the spirit of
+hooks/checkpoint_hook.py:22-49 (`{output_dir}/iter_{N}.pd` holding model, optimizer, lr-scheduler state and the iteration; torch
+serialisation — the Paddle `.pdparams` pickle layout is SURVEY §8 f-3, not done).  Evaluation hooks are out of scope."""
+import os
 import time
 
 import torch
@@ -80,6 +82,33 @@ class Trainer:
         self.log_interval = (cfg.get("log_config", {}) or {}).get("interval", 10)
         self.current_iter = 0
         self.outputs = None
+        self.output_dir = cfg.get("output_dir", None)
+        self.checkpoint_interval = (cfg.get("checkpoint", {}) or {}).get("interval", 0)
+
+    # -- checkpoint / resume (rank 0 writes; every rank can load) ----------------------------------------------------------------
+    def save(self, path=None):
+        if path is None:
+            path = os.path.join(self.output_dir or ".", "iter_%d.pd" % self.current_iter)
+        if get_rank() == 0:
+            os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+            torch.save({"iter": self.current_iter, "state_dict": self.model.state_dict(),
+                        "optimizer": self.optimizer.state_dict(),
+                        "lr_scheduler": None if self.lr_scheduler is None else {"last_epoch": self.lr_scheduler.last_epoch}}, path)
+        return path
+
+    def resume(self, path):
+        ck = torch.load(path, map_location=self.device)
+        self.model.load_state_dict(ck["state_dict"])
+        for st in (getattr(self.model, "_stores", None) or (self.store,)):
+            if st is not None:
+                st.refresh_bf16()                        # parameters are views of the flat fp32 master: refresh the bf16 mirror
+        if hasattr(self.model, "_queue_bf16") and self.model._queue_bf16 is not None:
+            from .. import kernels as K
+            self.model._queue_bf16 = K.cast_bf16(self.model.queue)
+        self.optimizer.set_state_dict(ck["optimizer"])
+        if self.lr_scheduler is not None and ck.get("lr_scheduler"):
+            self.lr_scheduler.last_epoch = ck["lr_scheduler"]["last_epoch"]
+        self.current_iter = int(ck["iter"])
 
     def train(self):
         loader = IterLoader(self.dataloader)
@@ -92,6 +121,8 @@ class Trainer:
             self.outputs['loss'].backward()                       # OptimizerHook.train_iter_end (optimizer_hook.py:25-48)
             grad_sync(self.store)
             self.optimizer.step()
+            if self.lr_scheduler is not None:                      # LRSchedulerHook (by iteration)
+                self.optimizer.set_lr(self.lr_scheduler.step())
             self.current_iter += 1
             seen += self.batch_size * get_world_size()
             if self.current_iter % self.log_interval == 0 and get_rank() == 0:
@@ -101,4 +132,6 @@ class Trainer:
                     self.current_iter, total, self.optimizer.get_lr(), float(self.outputs['loss']), dt / self.log_interval, seen / dt)
                 print(msg, flush=True)
                 t0, seen = time.time(), 0
+            if self.checkpoint_interval and self.current_iter % self.checkpoint_interval == 0:
+                self.save()
         return self.outputs

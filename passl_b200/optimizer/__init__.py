@@ -39,6 +39,19 @@ class _FlatOptimizer:
     def set_lr(self, lr):
         self.lr = float(lr)
 
+    def set_state_dict(self, state):
+        """Inverse of state_dict() (paddle optimizer API name): restores the flat moment buffers, step counter and lr."""
+        for k, v in state.items():
+            cur = getattr(self, "_step" if k == "step" else k, None)
+            if torch.is_tensor(cur) and torch.is_tensor(v):
+                cur.copy_(v.to(cur.device))
+            elif k == "step":
+                self._step = int(v)
+            elif k == "lr":
+                self.lr = float(v)
+
+    load_state_dict = set_state_dict
+
     def get_lr(self):
         return self.lr
 

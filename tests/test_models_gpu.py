@@ -71,3 +71,30 @@ def test_trainer_surface_moco(tmp_path):
     assert np.isfinite(float(out["loss"])) and "acc1" in out and "acc5" in out
     tr.model.flush_queue()
     assert int(tr.model.queue_ptr.item()) == (4 * 16) % 1024
+
+
+def test_trainer_checkpoint_resume(tmp_path):
+    """save -> fresh Trainer -> resume reproduces parameters, optimizer state, queue pointer and the next step's loss."""
+    from passl_b200.engine import trainer as T
+    from passl_b200.utils.config import get_config
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    over = ["model.K=1024", "dataloader.train.sampler.batch_size=16", "total_iters=2", "log_config.interval=100",
+            "output_dir=%s" % tmp_path]
+    cfg = get_config(os.path.join(root, "configs/moco/moco_v2_r50.yaml"), over)
+    data = T.SyntheticTwoViews(16, 2, torch.device("cuda"), size=64)
+    tr = T.Trainer(cfg, dataloader=data)
+    tr.train()
+    path = tr.save()
+    tr.model.flush_queue()
+    ptr_saved = int(tr.model.queue_ptr.item())
+    # one more step on the original
+    tr.dataloader = T.SyntheticTwoViews(16, 3, torch.device("cuda"), size=64)
+    out_a = tr.train()
+    cfg2 = get_config(os.path.join(root, "configs/moco/moco_v2_r50.yaml"), over)
+    tr2 = T.Trainer(cfg2, dataloader=T.SyntheticTwoViews(16, 3, torch.device("cuda"), size=64))
+    tr2.resume(path)
+    assert tr2.current_iter == 2 and int(tr2.model.queue_ptr.item()) == ptr_saved
+    out_b = tr2.train()
+    np.testing.assert_allclose(float(out_b["loss"]), float(out_a["loss"]), rtol=2e-3)
+    torch.testing.assert_close(tr2.store.master, tr.store.master, rtol=1e-3, atol=1e-4)
