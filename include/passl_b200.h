@@ -279,6 +279,9 @@ int passl_b200_rows_ce_bwd(const float* logits, const long long* labels, const f
 int passl_b200_im2col_nchw_f32(const float* x, void* out, int N, int C, int H, int W, int R, int S, int stride, int pad,
                                int Kpad, void* stream);
 int passl_b200_maxpool3x3s2_fwd(const void* x, void* y, void* argmax, int N, int H, int W, int C, void* stream);
+/* stem tail fused: y = maxpool3x3/2(relu(x*scale + shift)) (BatchNorm apply + ReLU + MaxPool2D of resnetimagenet.py:196-198) */
+int passl_b200_bn_relu_maxpool3x3s2_fwd(const void* x, const float* scale, const float* shift, void* y, void* argmax, int N, int H,
+                                       int W, int C, void* stream);
 int passl_b200_maxpool3x3s2_bwd(const void* dy, const void* argmax, void* dx, int N, int H, int W, int C, void* stream);
 int passl_b200_avgpool_fwd(const void* x, void* y_bf16, float* y_f32, int N, int HW, int C, void* stream);
 int passl_b200_avgpool_bwd(const void* dy, void* dx, int N, int HW, int C, void* stream);

@@ -88,6 +88,7 @@ SIGNATURES = {
     "passl_b200_layernorm_bwd": (c_int, [c_void_p] * 8 + [c_ll, c_int, c_void_p]),
     "passl_b200_im2col_nchw_f32": (c_int, [c_void_p, c_void_p] + [c_int] * 9 + [c_void_p]),
     "passl_b200_maxpool3x3s2_fwd": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
+    "passl_b200_bn_relu_maxpool3x3s2_fwd": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
     "passl_b200_maxpool3x3s2_bwd": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
     "passl_b200_avgpool_fwd": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 3 + [c_void_p]),
     "passl_b200_avgpool_bwd": (c_int, [c_void_p, c_void_p] + [c_int] * 3 + [c_void_p]),

@@ -92,6 +92,53 @@ __global__ void maxpool3x3s2_fwd_kernel(const __nv_bfloat16* __restrict__ x, __n
   }
 }
 
+// Stem tail fused: out = maxpool3x3/2(relu(y * scale + shift)) without materialising the normalised activation (the BN backward
+// recomputes the ReLU mask from y, the pool backward only needs the arg-max tap): saves one write + one read of [N,112,112,64].
+__global__ void bn_relu_maxpool3x3s2_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale,
+                                                const float* __restrict__ shift, __nv_bfloat16* __restrict__ y,
+                                                signed char* __restrict__ argmax, int N, int H, int W, int C, int Ho, int Wo) {
+  const int C8 = C / 8;
+  const long long total = (long long)N * Ho * Wo * C8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % C8);
+    long long p = i / C8;
+    const int ow = (int)(p % Wo);
+    p /= Wo;
+    const int oh = (int)(p % Ho);
+    const int n = (int)(p / Ho);
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = __ldg(scale + cg * 8 + j); sh[j] = __ldg(shift + cg * 8 + j); }
+    float best[8];
+    int arg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; arg[j] = -1; }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int h = oh * 2 + r - 1;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int w = ow * 2 + s - 1;
+        if (w < 0 || w >= W) continue;
+        float v[8];
+        unpack8p(__ldg(reinterpret_cast<const uint4*>(x + (((long long)n * H + h) * W + w) * C + cg * 8)), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          // same rounding as bn_apply followed by the pool: the pooled tensor holds bf16(relu(fma))
+          const float z = __bfloat162float(__float2bfloat16_rn(fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f)));
+          if (z > best[j] || arg[j] < 0) { best[j] = z; arg[j] = r * 3 + s; }
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(y + i * 8) = pack8p(best);
+    uint2 a;
+    a.x = (arg[0] & 0xff) | ((arg[1] & 0xff) << 8) | ((arg[2] & 0xff) << 16) | ((arg[3] & 0xff) << 24);
+    a.y = (arg[4] & 0xff) | ((arg[5] & 0xff) << 8) | ((arg[6] & 0xff) << 16) | ((arg[7] & 0xff) << 24);
+    *reinterpret_cast<uint2*>(argmax + i * 8) = a;
+  }
+}
+
 __global__ void maxpool3x3s2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const signed char* __restrict__ argmax,
                                         __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int Ho, int Wo) {
   const int C8 = C / 8;
@@ -203,6 +250,17 @@ extern "C" int passl_b200_maxpool3x3s2_fwd(const void* x, void* y, void* argmax,
   maxpool3x3s2_fwd_kernel<<<ew_blocks_p(total), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), reinterpret_cast<signed char*>(argmax), N,
       H, W, C, Ho, Wo);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+extern "C" int passl_b200_bn_relu_maxpool3x3s2_fwd(const void* x, const float* scale, const float* shift, void* y, void* argmax, int N,
+                                                  int H, int W, int C, void* stream) {
+  if (N <= 0 || C % 8 || !scale || !shift) return PB_ERR_BAD_ARG;
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  long long total = (long long)N * Ho * Wo * (C / 8);
+  bn_relu_maxpool3x3s2_fwd_kernel<<<ew_blocks_p(total), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), scale, shift, reinterpret_cast<__nv_bfloat16*>(y),
+      reinterpret_cast<signed char*>(argmax), N, H, W, C, Ho, Wo);
   PB_LAUNCH_CHECK();
   return PB_OK;
 }

@@ -399,6 +399,18 @@ def maxpool_fwd(x):
     return y, arg
 
 
+def bn_relu_maxpool_fwd(y, msss):
+    """maxpool3x3/2(relu(y*scale + shift)) for the stem: NHWC bf16 y -> (pooled, argmax int8)."""
+    lib = _lib.load()
+    N, H, W, C = y.shape
+    Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    out = torch.empty((N, Ho, Wo, C), dtype=torch.bfloat16, device=y.device)
+    arg = torch.empty((N, Ho, Wo, C), dtype=torch.int8, device=y.device)
+    _lib.check(lib.passl_b200_bn_relu_maxpool3x3s2_fwd(_ptr(y), _ptr(msss[2]), _ptr(msss[3]), _ptr(out), _ptr(arg), N, H, W, C,
+                                                       _stream()), "bn_relu_maxpool3x3s2_fwd")
+    return out, arg
+
+
 def maxpool_bwd(dy, arg, x_shape):
     lib = _lib.load()
     N, H, W, C = x_shape

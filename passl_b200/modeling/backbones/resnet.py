@@ -50,19 +50,23 @@ class Stem(nn.Module):
         else:
             y = K.stem_conv_fwd(cols, w).view(N * Ho * Wo, 64)
             msss = bn.global_affine()
-        z = K.bn_apply(y, msss, True).view(N, Ho, Wo, 64)
         if self.maxpool:
-            out, arg = K.maxpool_fwd(z)
+            # BN apply + ReLU + max-pool in one kernel: the normalised 112^2 activation is never written (the backward
+            # recomputes the ReLU mask from y and only needs the pool's arg-max)
+            z = None
+            out, arg = K.bn_relu_maxpool_fwd(y.view(N, Ho, Wo, 64), msss)
         else:
+            z = K.bn_apply(y, msss, True).view(N, Ho, Wo, 64)
             out, arg = z, None
         return out, ((cols, y, z, msss, arg) if save else None)
 
     def bwd(self, ctx, dout):
         cols, y, z, msss, arg = ctx
-        dz = K.maxpool_bwd(dout, arg, tuple(z.shape)) if arg is not None else dout
+        N, Ho, Wo, _ = cols.shape
+        dz = K.maxpool_bwd(dout, arg, (N, Ho, Wo, 64)) if arg is not None else dout
         bn = self.bn
         tb = bn.weight.requires_grad
-        dy, _, _ = K.bn_bwd(y, dz.view(y.shape), z.view(y.shape), msss, bn.weight, True,
+        dy, _, _ = K.bn_bwd(y, dz.view(y.shape), None if z is None else z.view(y.shape), msss, bn.weight, True,
                             dgamma=grad_buffer(bn.weight) if tb else None, dbeta=grad_buffer(bn.bias) if tb else None)
         if self.weight.requires_grad:
             K.stem_conv_wgrad(cols, dy.view(cols.shape[0], cols.shape[1], cols.shape[2], 64), grad_buffer(self.weight))

@@ -233,3 +233,17 @@ def test_moco_train_iter_smoke_and_state():
     # key encoder followed the EMA of the (updated) query encoder: k1 = m*k0 + (1-m)*q0 after the first step
     assert (sk.master - k_before).abs().max() > 0
     assert torch.equal(sq.bf16, sq.master.bfloat16())                        # bf16 mirror refreshed by the optimizer kernel
+
+
+def test_fused_bn_relu_maxpool_matches_unfused():
+    """Stem tail: maxpool(relu(bn(y))) in one kernel == bn_apply followed by maxpool_fwd, bit for bit (values and arg-max taps)."""
+    import torch
+    from passl_b200 import kernels as K
+    torch.manual_seed(3)
+    y = torch.randn(3, 30, 30, 64, device="cuda").bfloat16()
+    msss = torch.randn(4, 64, device="cuda")
+    msss[2] = torch.randn(64, device="cuda")            # scale of either sign
+    z = K.bn_apply(y, msss, True)
+    ref, ref_arg = K.maxpool_fwd(z)
+    out, arg = K.bn_relu_maxpool_fwd(y, msss)
+    assert torch.equal(out, ref) and torch.equal(arg, ref_arg)
