@@ -59,6 +59,26 @@ class SyntheticTwoViews:
             yield self.a, self.b
 
 
+class SyntheticImageText:
+    """Synthetic (image, text) batches for the CLIP path: N(0,1) images, random token ids with the EOT id (vocab - 1) at a random
+    position >= 1 (SURVEY §8d synthetic-input spec)."""
+
+    def __init__(self, batch_size, iters, device, size=224, context_length=77, vocab_size=49408, seed=1234):
+        self.iters = iters
+        g = torch.Generator(device=device).manual_seed(seed + get_rank())
+        self.img = torch.randn(batch_size, 3, size, size, device=device, generator=g)
+        self.text = torch.randint(1, vocab_size - 1, (batch_size, context_length), device=device, generator=g)
+        eot = torch.randint(1, context_length, (batch_size,), device=device, generator=g)
+        self.text[torch.arange(batch_size, device=device), eot] = vocab_size - 1
+
+    def __len__(self):
+        return self.iters
+
+    def __iter__(self):
+        for _ in range(self.iters):
+            yield self.img, self.text
+
+
 class Trainer:
     def __init__(self, cfg, dataloader=None, device=None):
         self.cfg = cfg
@@ -78,7 +98,16 @@ class Trainer:
             opt_cfg.setdefault("lr", lr_cfg["learning_rate"])
         self.optimizer = build_optimizer(opt_cfg, self.store)
         self.batch_size = cfg.dataloader.train.sampler.batch_size
-        self.dataloader = dataloader or SyntheticTwoViews(self.batch_size, cfg.get("total_iters", 10), self.device)
+        if dataloader is None:
+            iters = cfg.get("total_iters", 10)
+            ds = ((cfg.dataloader.train.get("dataset", {}) or {}).get("name", "")) if "dataloader" in cfg else ""
+            if ds == "TextImageDataset":
+                arch = cfg.model.architecture
+                dataloader = SyntheticImageText(self.batch_size, iters, self.device, size=arch.image_resolution,
+                                                context_length=arch.context_length, vocab_size=arch.vocab_size)
+            else:
+                dataloader = SyntheticTwoViews(self.batch_size, iters, self.device)
+        self.dataloader = dataloader
         self.log_interval = (cfg.get("log_config", {}) or {}).get("interval", 10)
         self.current_iter = 0
         self.outputs = None

@@ -98,3 +98,21 @@ def test_trainer_checkpoint_resume(tmp_path):
     out_b = tr2.train()
     np.testing.assert_allclose(float(out_b["loss"]), float(out_a["loss"]), rtol=2e-3)
     torch.testing.assert_close(tr2.store.master, tr.store.master, rtol=1e-3, atol=1e-4)
+
+
+def test_trainer_surface_clip():
+    """configs/clip (reference keys) -> Trainer with the synthetic image-text loader: a few AdamW steps on a shrunken CLIP."""
+    from passl_b200.engine.trainer import Trainer
+    from passl_b200.utils.config import get_config
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    a = "model.architecture."
+    cfg = get_config(os.path.join(root, "configs/clip/vit-b-16.yaml"),
+                     [a + "vision_layers=2", a + "vision_width=128", a + "image_resolution=64", a + "embed_dim=64",
+                      a + "transformer_width=128", a + "transformer_heads=2", a + "transformer_layers=2", a + "context_length=16",
+                      a + "vocab_size=1000", "dataloader.train.sampler.batch_size=16", "total_iters=3", "log_config.interval=100"])
+    tr = Trainer(cfg)
+    out = tr.train()
+    assert np.isfinite(float(out["loss"])) and np.isfinite(float(out["img_loss"])) and np.isfinite(float(out["text_loss"]))
+    assert 0 < float(out["loss"]) < 2 * np.log(16) + 2.0
+    assert abs(tr.model.model.logit_scale.item()) <= 4.6 + 1e-6
