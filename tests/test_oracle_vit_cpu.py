@@ -1,0 +1,41 @@
+"""Cross-oracle for the transformer block: oracle/vit.py `block` (restating passl/models/vision_transformer.py:116-206) and
+oracle/clip.py `block` (QuickGELU, additive causal mask) against torch.nn.TransformerEncoderLayer(norm_first=True) — an independent
+implementation of the same pre-LN block — with copied weights in float64."""
+import torch
+import torch.nn as nn
+
+
+def _layer_and_params(D, H, act, pre="b."):
+    torch.manual_seed(0)
+    layer = nn.TransformerEncoderLayer(D, H, dim_feedforward=4 * D, dropout=0.0, activation=act, batch_first=True,
+                                       norm_first=True, layer_norm_eps=1e-6).double().eval()
+    for prm in layer.parameters():
+        nn.init.normal_(prm, std=0.2)
+    p = {pre + "norm1.weight": layer.norm1.weight, pre + "norm1.bias": layer.norm1.bias,
+         pre + "qkv.weight": layer.self_attn.in_proj_weight, pre + "qkv.bias": layer.self_attn.in_proj_bias,
+         pre + "proj.weight": layer.self_attn.out_proj.weight, pre + "proj.bias": layer.self_attn.out_proj.bias,
+         pre + "norm2.weight": layer.norm2.weight, pre + "norm2.bias": layer.norm2.bias,
+         pre + "fc1.weight": layer.linear1.weight, pre + "fc1.bias": layer.linear1.bias,
+         pre + "fc2.weight": layer.linear2.weight, pre + "fc2.bias": layer.linear2.bias}
+    return layer, {k: v.detach() for k, v in p.items()}
+
+
+def test_vit_block_matches_torch_encoder_layer():
+    import oracle.vit as OV
+    layer, p = _layer_and_params(64, 4, "gelu")
+    x = torch.randn(3, 17, 64, dtype=torch.float64)
+    with torch.no_grad():
+        ref = layer(x)
+    got = OV.block(x, p, "b.", 4, eps=1e-6)
+    torch.testing.assert_close(got, ref, rtol=1e-9, atol=1e-9)
+
+
+def test_clip_block_quickgelu_causal_matches_torch_encoder_layer():
+    import oracle.clip as OC
+    layer, p = _layer_and_params(64, 2, OC.quick_gelu)
+    x = torch.randn(2, 11, 64, dtype=torch.float64)
+    mask = OC.build_attention_mask(11)
+    with torch.no_grad():
+        ref = layer(x, src_mask=mask)
+    got = OC.block(x, p, "b.", 2, eps=1e-6, attn_mask=mask)
+    torch.testing.assert_close(got, ref, rtol=1e-9, atol=1e-9)
