@@ -301,6 +301,26 @@ int passl_b200_adamw(float* p, const float* g, float* m, float* v, void* p_bf16,
                      long long n, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Embedding exchange over NVLink peer memory (replaces the NCCL all_gather / reduce_scatter behind
+ * moco.py:198-210 and passl/distributed/nn/functional.py:100-127 when the ranks share a node): one kernel that signals through
+ * flags in peer memory and reads every rank's shard with P2P loads.  data_ptrs / flag_ptrs are HOST arrays of `world` device
+ * pointers = this process's mappings (peer_buffer_open) of each rank's data buffer and flag row (uint32[world], zeroed once); `epoch` increases by one per exchange on a slot; use two slots alternately (see passl_b200/distributed/peer.py).
+ *   peer_allgather          out[q*shard_bytes ...] = rank q's shard
+ *   peer_reduce_scatter_f32 out[i] = sum_q (rank q's buffer)[rank*shard_elems + i]
+ * ------------------------------------------------------------------------------------------------------------- */
+/* exchange buffers: the only device memory the library allocates itself (a CUDA IPC handle needs the base of a cudaMalloc
+ * allocation); create exports a 64-byte handle, open maps a peer's buffer with the current device as accessor */
+int passl_b200_peer_buffer_create(long long bytes, void** base, unsigned char* handle64);
+int passl_b200_peer_buffer_open(const unsigned char* handle64, void** mapped);
+int passl_b200_peer_buffer_close(void* mapped);
+int passl_b200_peer_buffer_destroy(void* base);
+/* `shard` / `grad_all` (local device memory) is first copied into this rank's slot, then the kernel signals and gathers */
+int passl_b200_peer_allgather(const void* shard, const void* const* data_ptrs, void* const* flag_ptrs, void* out, long long shard_bytes,
+                              int rank, int world, unsigned epoch, void* stream);
+int passl_b200_peer_reduce_scatter_f32(const float* grad_all, const void* const* data_ptrs, void* const* flag_ptrs, float* out,
+                                       long long shard_elems, int rank, int world, unsigned epoch, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Developer probe (not a reference entry point): one tcgen05.mma over a row-shifted view of a SWIZZLE_128B tile, used by
  * tests/test_umma_probe_gpu.py to pin the shared-memory descriptor semantics (start address not 1024-aligned, SBO != 1024,
  * base_offset bits) that the halo-tile convolution kernels rely on.  A bf16 [256,64], B bf16 [64,64], out fp32 [128,64].

@@ -80,6 +80,12 @@ SIGNATURES = {
     "passl_b200_clip_ce_bwd": (c_int, [c_void_p] * 4 + [c_int, c_int, c_void_p, c_ll, c_void_p]),
     "passl_b200_rows_ce_fwd": (c_int, [c_void_p] * 4 + [c_int, c_int, c_void_p, c_ll, c_void_p]),
     "passl_b200_rows_ce_bwd": (c_int, [c_void_p] * 5 + [c_int, c_int, c_void_p]),
+    "passl_b200_peer_buffer_create": (c_int, [c_ll, c_void_p, c_void_p]),
+    "passl_b200_peer_buffer_open": (c_int, [c_void_p, c_void_p]),
+    "passl_b200_peer_buffer_close": (c_int, [c_void_p]),
+    "passl_b200_peer_buffer_destroy": (c_int, [c_void_p]),
+    "passl_b200_peer_allgather": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, ctypes.c_uint, c_void_p]),
+    "passl_b200_peer_reduce_scatter_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, ctypes.c_uint, c_void_p]),
     "passl_b200_umma_probe": (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p]),
     "passl_b200_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "passl_b200_attention_bwd": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),

@@ -1,0 +1,82 @@
+"""Peer-memory embedding exchange (csrc/peer.cu, distributed/peer.py).  Needs >= 2 GPUs and a torchrun launch:
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 -m pytest tests/test_peer_gpu.py -q -m gpu
+In a single-process run (the default `pytest -m gpu`) it is skipped."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.skipif(int(os.environ.get("WORLD_SIZE", "1")) < 2, reason="needs torchrun with >= 2 ranks")
+def test_peer_allgather_and_reduce_scatter_match_nccl():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    if not dist.is_initialized():
+        dist.init_process_group("nccl")
+    from passl_b200.distributed import all_gather as nccl_all_gather
+    from passl_b200.distributed.peer import PeerExchange
+    n, d = 512, 128
+    ex = PeerExchange(n, d)
+    for it in range(5):                                      # several epochs: both slots, flag reuse
+        g = torch.Generator(device="cuda").manual_seed(100 * it + rank)
+        x = torch.randn(n, d, device="cuda", generator=g, requires_grad=True)
+        x2 = x.detach().clone().requires_grad_(True)
+        got = ex.all_gather(x)
+        ref = nccl_all_gather(x2)
+        assert torch.equal(got, ref)                         # pure data movement: bit-exact
+        w = torch.randn(world * n, d, device="cuda", generator=g)
+        (got * w).sum().backward()
+        (ref * w).sum().backward()
+        torch.testing.assert_close(x.grad, x2.grad, rtol=1e-6, atol=1e-6)    # summation order may differ from NCCL's
+    ex.close()
+
+
+@pytest.mark.skipif(int(os.environ.get("WORLD_SIZE", "1")) < 2, reason="needs torchrun with >= 2 ranks")
+def test_simclr_head_peer_exchange_equals_nccl_and_timing():
+    """SimCLRContrastiveHead with all-gathered negatives: peer-memory exchange == NCCL exchange (loss and gradient); also prints the
+    latency of both exchanges at the bench shape (1024 x 128 fp32 per rank)."""
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    if not dist.is_initialized():
+        dist.init_process_group("nccl")
+    from passl_b200.distributed import concat_all_gather
+    from passl_b200.distributed.peer import PeerExchange
+    from passl_b200.modeling.heads.simclr_contrastive_head import SimCLRContrastiveHead
+    n, d = 256, 128
+    g = torch.Generator(device="cuda").manual_seed(7 + rank)
+    con = torch.nn.functional.normalize(torch.randn(2 * n, d, device="cuda", generator=g), dim=1)
+    outs = []
+    for peer in (False, True):
+        x = con.clone().requires_grad_(True)
+        head = SimCLRContrastiveHead(temperature=0.1, multi_rank=True, peer_exchange=peer)
+        o = head.forward_fused(x, n)
+        o["loss"].backward()
+        outs.append((o["loss"].item(), o["acc1"].item(), x.grad.clone()))
+        if peer:
+            head._ex.close()
+    assert abs(outs[0][0] - outs[1][0]) < 1e-5 * max(1.0, abs(outs[0][0])) and outs[0][1] == outs[1][1]
+    torch.testing.assert_close(outs[0][2], outs[1][2], rtol=1e-4, atol=1e-6)
+    # latency at the bench shape
+    ex = PeerExchange(1024, 128)
+    x = torch.randn(1024, 128, device="cuda")
+    def t(fn, it=50):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize(); dist.barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(it):
+            fn()
+        e.record(); torch.cuda.synchronize()
+        return s.elapsed_time(e) / it * 1e3
+    t_nccl = t(lambda: concat_all_gather(x))
+    t_peer = t(lambda: ex.gather(x))
+    if rank == 0:
+        msg = "embedding all-gather 1024x128 fp32 x %d ranks: NCCL %.1f us, peer-memory kernel %.1f us" % (world, t_nccl, t_peer)
+        print(msg)
+        os.makedirs("gpurun_out", exist_ok=True)
+        open("gpurun_out/peer_exchange_latency.txt", "w").write(msg + "\n")
+    ex.close()
