@@ -1,0 +1,119 @@
+"""Golden vectors for the necks: run the REFERENCE'S OWN neck classes
+(/root/reference/passl_v110/modeling/necks/base_neck.py:43-94,209-237, read in place, never copied) over the torch-backed paddle
+shim with seeded weights, and store inputs / weights / outputs in tests/golden/reference_necks.npz.
+
+    python tests/golden/make_golden_necks.py          (build container only; the GPU box has no /root/reference)
+
+Paddle layer semantics restated for the shim (paddle 2.4 docs): nn.Linear stores weight [in, out] and computes x @ W + b;
+nn.BatchNorm1D in training mode normalises with the biased batch variance, epsilon 1e-5; AdaptiveAvgPool2D((1,1)) = mean over H, W;
+fluid.layers.squeeze(x, axes=[]) removes all size-1 dims; fluid.layers.l2_normalize(x, axis, epsilon=1e-12) = x / sqrt(sum x^2 + eps).
+The reference initialisers are replaced by explicit seeded weights (stored in the file), so no Paddle RNG is involved."""
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import paddle_shim  # noqa: E402
+import make_golden  # noqa: E402
+
+
+def extend_shim():
+    nn = sys.modules["paddle.nn"]
+    layers = sys.modules["paddle.fluid.layers"]
+
+    class Linear(nn.Layer):
+        def __init__(self, in_features, out_features, **kw):
+            super().__init__()
+            self.weight = torch.nn.Parameter(torch.zeros(in_features, out_features, dtype=torch.float64))   # paddle: [in, out]
+            self.bias = torch.nn.Parameter(torch.zeros(out_features, dtype=torch.float64))
+
+        def forward(self, x):
+            return x @ self.weight + self.bias
+
+    class ReLU(nn.Layer):
+        def forward(self, x):
+            return torch.relu(x)
+
+    class BatchNorm1D(nn.Layer):
+        def __init__(self, num_features, momentum=0.9, epsilon=1e-5, **kw):
+            super().__init__()
+            self.weight = torch.nn.Parameter(torch.ones(num_features, dtype=torch.float64))
+            self.bias = torch.nn.Parameter(torch.zeros(num_features, dtype=torch.float64))
+            self.epsilon = epsilon
+
+        def forward(self, x):                                   # training mode: batch statistics, biased variance
+            mean = x.mean(dim=0)
+            var = x.var(dim=0, unbiased=False)
+            return (x - mean) / torch.sqrt(var + self.epsilon) * self.weight + self.bias
+
+    class AdaptiveAvgPool2D(nn.Layer):
+        def __init__(self, output_size):
+            super().__init__()
+            assert tuple(output_size) == (1, 1)
+
+        def forward(self, x):
+            return x.mean(dim=(2, 3), keepdim=True)
+
+    nn.Linear, nn.ReLU, nn.BatchNorm1D, nn.AdaptiveAvgPool2D = Linear, ReLU, BatchNorm1D, AdaptiveAvgPool2D
+    for name in ("BatchNorm2D", "GroupNorm", "SyncBatchNorm", "Conv2D"):
+        setattr(nn, name, type(name, (nn.Layer,), {}))
+    layers.squeeze = lambda x, axes: x.squeeze() if not axes else x.squeeze(*axes)
+    # the initialisers are replaced by explicit seeded weights below
+    init = types.ModuleType("passl_v110.modules.init")
+    for fn in ("init_backbone_weight", "normal_init", "kaiming_init", "constant_", "reset_parameters", "xavier_init",
+               "init_backbone_weight_simclr"):
+        setattr(init, fn, lambda *a, **k: None)
+    sys.modules["passl_v110.modules.init"] = init
+    torch.nn.Module.sublayers = lambda self: list(self.modules())[1:]
+
+
+def seeded(module, rng):
+    """Overwrite every parameter with seeded values; returns {name: array} (paddle layout)."""
+    out = {}
+    for name, p in module.named_parameters():
+        if p.dim() == 2:
+            v = rng.randn(*p.shape) / np.sqrt(p.shape[0])
+        elif name.endswith("weight"):
+            v = 1.0 + 0.2 * rng.randn(*p.shape)
+        else:
+            v = 0.1 * rng.randn(*p.shape)
+        with torch.no_grad():
+            p.copy_(torch.from_numpy(v))
+        out[name] = v
+    return out
+
+
+def main():
+    make_golden.setup()
+    extend_shim()
+    mod = importlib.import_module("passl_v110.modeling.necks.base_neck")
+    rng = np.random.RandomState(2024)
+    out = {}
+    # NonLinearNeckV1 (MoCo v2): avgpool -> fc -> relu -> fc
+    neck = mod.NonLinearNeckV1(in_channels=32, hid_channels=48, out_channels=16, with_avg_pool=True)
+    for k, v in seeded(neck, rng).items():
+        out["v1_" + k] = v
+    x = rng.randn(6, 32, 3, 3)
+    out["v1_x"], out["v1_y"] = x, neck(torch.from_numpy(x)).detach().numpy()
+    # LinearNeck: avgpool -> fc
+    neck = mod.LinearNeck(in_channels=32, out_channels=16, with_avg_pool=True)
+    for k, v in seeded(neck, rng).items():
+        out["lin_" + k] = v
+    out["lin_x"], out["lin_y"] = x, neck(torch.from_numpy(x)).detach().numpy()
+    # NonLinearNeckfc3 (SimCLR): fc-bn-relu, fc-bn-relu, fc-bn, l2_normalize
+    neck = mod.NonLinearNeckfc3(in_channels=32, hid_channels=40, out_channels=24)
+    for k, v in seeded(neck, rng).items():
+        out["fc3_" + k] = v
+    x3 = rng.randn(10, 32, 1, 1)
+    out["fc3_x"], out["fc3_y"] = x3, neck(torch.from_numpy(x3)).detach().numpy()
+    np.savez_compressed(os.path.join(HERE, "reference_necks.npz"), **out)
+    print("wrote reference_necks.npz with", sorted(out))
+
+
+if __name__ == "__main__":
+    main()
