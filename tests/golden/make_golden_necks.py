@@ -117,3 +117,24 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def gen_mocov3_loss():
+    """MoCoV3Pretrain.contrastive_loss (passl/models/mocov3.py:187-198) called as an unbound method on a stub `self` (T,
+    concat_all_gather) — world size 1 in the shim, so labels are arange(N); stored in tests/golden/reference_mocov3.npz."""
+    mod = importlib.import_module("passl.models.mocov3")
+    out = {}
+    rng = np.random.RandomState(77)
+    for tag, (N, D, T) in {"a": (12, 32, 0.2), "b": (33, 256, 1.0)}.items():
+        q, k = rng.randn(N, D), 0.5 * rng.randn(N, D)
+        k[: N // 2] += q[: N // 2]
+        stub = types.SimpleNamespace(T=T)
+        stub.concat_all_gather = lambda t_: mod.MoCoV3Pretrain.concat_all_gather(stub, t_)
+        loss = mod.MoCoV3Pretrain.contrastive_loss(stub, torch.from_numpy(q), torch.from_numpy(k))
+        out["q_" + tag], out["k_" + tag], out["T_" + tag], out["loss_" + tag] = q, k, np.float64(T), loss.detach().numpy()
+    np.savez_compressed(os.path.join(HERE, "reference_mocov3.npz"), **out)
+    print("wrote reference_mocov3.npz", {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items() if k.startswith("loss")})
+
+
+if __name__ == "__main__":
+    gen_mocov3_loss()

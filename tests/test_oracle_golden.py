@@ -103,3 +103,13 @@ def test_clip_torch_twin_matches_reference_head():
     assert OCL.clip_forward(img, txt, torch.tensor([7.0], dtype=torch.float64))[2].item() == 4.6
     m = OCL.build_attention_mask(5)
     assert torch.isinf(m[0, 1]) and m[1, 0] == 0 and m[3, 3] == 0          # clip.py:293-295: strictly upper triangle = -inf
+
+
+def test_mocov3_contrastive_loss_vs_reference_method():
+    """oracle mocov3_contrastive_loss == MoCoV3Pretrain.contrastive_loss of the reference source (tests/golden/reference_mocov3.npz,
+    generated by tests/golden/make_golden_necks.py calling the reference method over the shim)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_mocov3.npz"))
+    for tag in ("a", "b"):
+        loss, _, labels = OC.mocov3_contrastive_loss(g["q_" + tag], g["k_" + tag], float(g["T_" + tag]), rank=0)
+        np.testing.assert_allclose(loss, g["loss_" + tag], rtol=1e-12)
+        assert np.array_equal(labels, np.arange(g["q_" + tag].shape[0]))
