@@ -59,6 +59,50 @@ def extend_shim():
         def forward(self, x):
             return x.mean(dim=(2, 3), keepdim=True)
 
+    class LayerNorm(nn.Layer):
+        def __init__(self, normalized_shape, epsilon=1e-5, **kw):
+            super().__init__()
+            d = normalized_shape if isinstance(normalized_shape, int) else normalized_shape[-1]
+            self.weight = torch.nn.Parameter(torch.ones(d, dtype=torch.float64))
+            self.bias = torch.nn.Parameter(torch.zeros(d, dtype=torch.float64))
+            self.epsilon = epsilon
+
+        def forward(self, x):
+            mean = x.mean(dim=-1, keepdim=True)
+            var = x.var(dim=-1, unbiased=False, keepdim=True)
+            return (x - mean) / torch.sqrt(var + self.epsilon) * self.weight + self.bias
+
+    class GELU(nn.Layer):                                      # paddle.nn.GELU(approximate=False): exact erf form
+        def forward(self, x):
+            return 0.5 * x * (1.0 + torch.erf(x / 2 ** 0.5))
+
+    class Dropout(nn.Layer):
+        def __init__(self, p=0.0, **kw):
+            super().__init__()
+            assert p == 0.0, "the pretrain configs of the hot path use rate 0"
+
+        def forward(self, x):
+            return x
+
+    class Identity(nn.Layer):
+        def forward(self, x):
+            return x
+
+    nn.LayerNorm, nn.GELU, nn.Dropout, nn.Identity = LayerNorm, GELU, Dropout, Identity
+    _Lin = Linear
+
+    class LinearB(_Lin):                                       # bias_attr=False -> no bias
+        def __init__(self, in_features, out_features, bias_attr=None, **kw):
+            super().__init__(in_features, out_features)
+            if bias_attr is False:
+                self.bias = None
+
+        def forward(self, x):
+            y = x @ self.weight
+            return y if self.bias is None else y + self.bias
+    Linear = LinearB
+    _reshape = torch.Tensor.reshape
+    torch.Tensor.matmul = lambda self, other: self @ other
     nn.Linear, nn.ReLU, nn.BatchNorm1D, nn.AdaptiveAvgPool2D = Linear, ReLU, BatchNorm1D, AdaptiveAvgPool2D
     for name in ("BatchNorm2D", "GroupNorm", "SyncBatchNorm", "Conv2D"):
         setattr(nn, name, type(name, (nn.Layer,), {}))
@@ -136,5 +180,58 @@ def gen_mocov3_loss():
     print("wrote reference_mocov3.npz", {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items() if k.startswith("loss")})
 
 
+def gen_vit_block():
+    """passl/models/vision_transformer.py:159-206 `Block` (Attention :116-156, Mlp :84-113) with seeded weights:
+    tests/golden/reference_vit_block.npz (weights in the paddle layout [in, out])."""
+    vt = importlib.import_module("passl.models.vision_transformer")
+
+    class _NoInit(types.ModuleType):                           # initialisers replaced by explicit seeded weights
+        def __getattr__(self, n):
+            return lambda *a, **k: None
+    vt.init = _NoInit("init")
+    rng = np.random.RandomState(5)
+    out = {}
+    for tag, (D, H, N) in {"a": (64, 4, 7), "b": (96, 3, 50)}.items():
+        blk = vt.Block(dim=D, num_heads=H, mlp_ratio=4, qkv_bias=True, epsilon=1e-6)
+        for k, v in seeded(blk, rng).items():
+            out["%s_%s" % (tag, k)] = v
+        x = rng.randn(3, N, D)
+        out[tag + "_x"], out[tag + "_y"] = x, blk(torch.from_numpy(x)).detach().numpy()
+        out[tag + "_heads"] = np.int64(H)
+    np.savez_compressed(os.path.join(HERE, "reference_vit_block.npz"), **out)
+    print("wrote reference_vit_block.npz", sorted(k for k in out if k.startswith("a_")))
+
+
+def gen_clip_block():
+    """v110 `Block` (passl_v110/modeling/backbones/vision_transformer.py:141-183: QuickGELU MLP, additive attention mask) with the
+    causal mask of clip.py:293-295 and without a mask: tests/golden/reference_clip_block.npz."""
+    import paddle                                              # the shim
+    F_ = sys.modules["paddle.nn.functional"]
+    F_.sigmoid = torch.sigmoid
+    for pk in ("paddle.nn", "paddle.fluid", "paddle.nn.functional", "paddle.fluid.layers"):
+        sys.modules[pk].__path__ = []                            # let `<pkg>.<sub>` imports resolve to placeholders
+    lay = paddle_shim._Permissive("paddle.nn.layer")
+    lay.__path__ = []
+    tr = paddle_shim._Permissive("paddle.nn.layer.transformer")
+    tr._convert_attention_mask = lambda mask, dtype: mask        # paddle: converts bool / int masks to additive float; float stays
+    sys.modules["paddle.nn.layer"], sys.modules["paddle.nn.layer.transformer"] = lay, tr
+    vt = importlib.import_module("passl_v110.modeling.backbones.vision_transformer")
+    vt._convert_attention_mask = tr._convert_attention_mask
+    rng = np.random.RandomState(11)
+    out = {}
+    for tag, (D, H, N, causal) in {"causal": (64, 2, 9, True), "plain": (64, 4, 13, False)}.items():
+        mask = torch.triu(torch.full((N, N), float("-inf"), dtype=torch.float64), 1) if causal else None
+        blk = vt.Block(dim=D, num_heads=H, mlp_ratio=4.0, qkv_bias=True, attn_mask=mask, epsilon=1e-5)
+        for k, v in seeded(blk, rng).items():
+            out["%s_%s" % (tag, k)] = v
+        x = rng.randn(2, N, D)
+        out[tag + "_x"], out[tag + "_y"] = x, blk(torch.from_numpy(x)).detach().numpy()
+        out[tag + "_heads"] = np.int64(H)
+    np.savez_compressed(os.path.join(HERE, "reference_clip_block.npz"), **out)
+    print("wrote reference_clip_block.npz", sorted(k for k in out if k.startswith("causal_"))[:6], "...")
+
+
 if __name__ == "__main__":
     gen_mocov3_loss()
+    gen_vit_block()
+    gen_clip_block()
