@@ -4,9 +4,10 @@ necks/base_neck.py:43-94,209-237 in NCHW float32/float64, driven by explicit par
 loaded into the CUDA path.  Paddle semantics restated: BatchNorm train mode normalises with the biased batch variance,
 eps 1e-5; running = 0.9*running + 0.1*batch (biased variance, as paddle's CPU batch_norm kernel); use_global_stats=True
 normalises with the running statistics (passl_v110/modules/freeze.py:17-23).
-Parity status: the reference has no tensor-level fixture for the backbone and Paddle cannot run here, so this file
-is pinned against an independent implementation of the same v1.5 topology instead: torchvision's resnet50 with copied weights,
-train-mode and eval-mode BatchNorm, float64, agreement to 1e-9 (tests/test_oracle_resnet_cpu.py).
+Parity status: pinned (tests/test_oracle_resnet_cpu.py, tests/test_oracle_necks_cpu.py) against (1) golden outputs of the
+reference's own ResNet / neck classes executed over the torch-backed paddle shim (reduced-width network built by the reference's
+`_make_layer` + `BottleneckBlock`; NonLinearNeckV1 / LinearNeck / NonLinearNeckfc3), and (2) torchvision's resnet50 (same v1.5
+topology) with copied weights, train-mode and eval-mode BatchNorm, float64, 1e-9.  Paddle itself cannot run here.
 """
 import torch
 import torch.nn.functional as F

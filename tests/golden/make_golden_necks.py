@@ -231,7 +231,88 @@ def gen_clip_block():
     print("wrote reference_clip_block.npz", sorted(k for k in out if k.startswith("causal_"))[:6], "...")
 
 
+def gen_resnet_layer():
+    """The reference's vendored ResNet code (passl_v110/modeling/backbones/resnetimagenet.py:93-246): a reduced-width network built
+    by the reference's own `ResNet._make_layer` + `BottleneckBlock` (stem conv7x7/2 + BN + ReLU + max-pool, then one stage of 2
+    blocks at stride 1 and one stage of 2 blocks at stride 2, widths 8 / 16 so the weights fit in a fixture), train-mode BatchNorm:
+    tests/golden/reference_resnet_layers.npz.  Paddle semantics restated in the shim: Conv2D = cross-correlation with zero padding,
+    weight [Cout, Cin, R, S]; BatchNorm2D train mode = biased batch variance, epsilon 1e-5; MaxPool2D(3, 2, 1) pads with -inf."""
+    nn = sys.modules["paddle.nn"]
+    Fn = torch.nn.functional
+
+    class Conv2D(nn.Layer):
+        def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias_attr=None, **kw):
+            super().__init__()
+            assert groups == 1 and dilation == 1 and bias_attr is False
+            self.weight = torch.nn.Parameter(torch.zeros(out_channels, in_channels, kernel_size, kernel_size, dtype=torch.float64))
+            self.stride, self.padding = stride, padding
+
+        def forward(self, x):
+            return Fn.conv2d(x, self.weight, stride=self.stride, padding=self.padding)
+
+    class BatchNorm2D(nn.Layer):
+        def __init__(self, num_features, momentum=0.9, epsilon=1e-5, **kw):
+            super().__init__()
+            self.weight = torch.nn.Parameter(torch.ones(num_features, dtype=torch.float64))
+            self.bias = torch.nn.Parameter(torch.zeros(num_features, dtype=torch.float64))
+            self.epsilon = epsilon
+
+        def forward(self, x):
+            mean = x.mean(dim=(0, 2, 3), keepdim=True)
+            var = x.var(dim=(0, 2, 3), unbiased=False, keepdim=True)
+            return (x - mean) / torch.sqrt(var + self.epsilon) * self.weight.view(1, -1, 1, 1) + self.bias.view(1, -1, 1, 1)
+
+    class MaxPool2D(nn.Layer):
+        def __init__(self, kernel_size, stride, padding):
+            super().__init__()
+            self.k, self.s, self.p = kernel_size, stride, padding
+
+        def forward(self, x):
+            return Fn.max_pool2d(x, self.k, self.s, self.p)
+    nn.Conv2D, nn.BatchNorm2D, nn.MaxPool2D = Conv2D, BatchNorm2D, MaxPool2D
+    rn = importlib.import_module("passl_v110.modeling.backbones.resnetimagenet")
+
+    class Tiny(rn.ResNet):                                   # same methods, reduced widths: only __init__'s channel table changes
+        def __init__(self):
+            nn.Layer.__init__(self)
+            self.num_classes, self.with_pool, self._norm_layer = 0, False, nn.BatchNorm2D
+            self.inplanes, self.dilation = 16, 1
+            self.conv1 = nn.Conv2D(3, self.inplanes, kernel_size=7, stride=2, padding=3, bias_attr=False)
+            self.bn1 = self._norm_layer(self.inplanes)
+            self.relu = nn.ReLU()
+            self.maxpool = nn.MaxPool2D(kernel_size=3, stride=2, padding=1)
+            self.layer1 = self._make_layer(rn.BottleneckBlock, 8, 2)
+            self.layer2 = self._make_layer(rn.BottleneckBlock, 16, 2, stride=2)
+
+        def forward(self, x):
+            x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+            return self.layer2(self.layer1(x))
+    rng = np.random.RandomState(31)
+    net = Tiny()
+    out = {"w_" + k: v for k, v in seeded_conv(net, rng).items()}
+    x = rng.randn(3, 3, 40, 40)
+    out["x"], out["y"] = x, net(torch.from_numpy(x)).detach().numpy()
+    np.savez_compressed(os.path.join(HERE, "reference_resnet_layers.npz"), **out)
+    print("wrote reference_resnet_layers.npz:", len(out) - 2, "parameters, y", out["y"].shape)
+
+
+def seeded_conv(module, rng):
+    out = {}
+    for name, p in module.named_parameters():
+        if p.dim() == 4:
+            v = rng.randn(*p.shape) / np.sqrt(p.shape[1] * p.shape[2] * p.shape[3])
+        elif name.endswith("weight"):
+            v = 1.0 + 0.2 * rng.randn(*p.shape)
+        else:
+            v = 0.1 * rng.randn(*p.shape)
+        with torch.no_grad():
+            p.copy_(torch.from_numpy(v))
+        out[name] = v
+    return out
+
+
 if __name__ == "__main__":
     gen_mocov3_loss()
     gen_vit_block()
     gen_clip_block()
+    gen_resnet_layer()

@@ -68,3 +68,35 @@ def test_oracle_resnet50_global_stats_matches_torchvision_eval_mode():
             x = layer(x)
         got = OR.resnet_forward(img, _export_torchvision(net), ugs=True)
     torch.testing.assert_close(got, x, rtol=1e-9, atol=1e-9)
+
+
+def test_oracle_matches_reference_resnet_code_reduced_width():
+    """oracle/resnet.py against golden output of the reference's OWN ResNet code (resnetimagenet.py `_make_layer` +
+    `BottleneckBlock` + stem, reduced widths; tests/golden/make_golden_necks.py gen_resnet_layer)."""
+    import os
+    import numpy as np
+    import oracle.resnet as OR
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_resnet_layers.npz"))
+    p = {}
+    blocks = {"layer1.0": 0, "layer1.1": 1, "layer2.0": 2, "layer2.1": 3}
+    for key in g.files:
+        if not key.startswith("w_"):
+            continue
+        name, v = key[2:], torch.from_numpy(g[key])
+        if name == "conv1.weight":
+            p["stem.weight"] = v
+        elif name.startswith("bn1."):
+            p["stem.bn." + name[4:]] = v
+        else:
+            lay, rest = name[:8], name[9:]
+            pre = "blocks.%d." % blocks[lay]
+            if rest.startswith("downsample.0."):
+                p[pre + "downsample.weight"] = v
+            elif rest.startswith("downsample.1."):
+                p[pre + "downsample.bn." + rest[13:]] = v
+            elif rest.startswith("conv"):
+                p[pre + rest] = v                                   # conv{k}.weight
+            else:                                                   # bn{k}.weight / bias
+                p[pre + "conv" + rest[2] + ".bn." + rest[4:]] = v
+    y = OR.resnet_forward(torch.from_numpy(g["x"]), p, layers=(2, 2))
+    np.testing.assert_allclose(y.numpy(), g["y"], rtol=1e-9, atol=1e-11)
