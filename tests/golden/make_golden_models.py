@@ -2,7 +2,7 @@
 (/root/reference/passl_v110/modeling/necks/base_neck.py:43-94,209-237, read in place, never copied) over the torch-backed paddle
 shim with seeded weights, and store inputs / weights / outputs in tests/golden/reference_necks.npz.
 
-    python tests/golden/make_golden_necks.py          (build container only; the GPU box has no /root/reference)
+    python tests/golden/make_golden_models.py          (build container only; the GPU box has no /root/reference)
 
 Paddle layer semantics restated for the shim (paddle 2.4 docs): nn.Linear stores weight [in, out] and computes x @ W + b;
 nn.BatchNorm1D in training mode normalises with the biased batch variance, epsilon 1e-5; AdaptiveAvgPool2D((1,1)) = mean over H, W;

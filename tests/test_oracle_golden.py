@@ -107,7 +107,7 @@ def test_clip_torch_twin_matches_reference_head():
 
 def test_mocov3_contrastive_loss_vs_reference_method():
     """oracle mocov3_contrastive_loss == MoCoV3Pretrain.contrastive_loss of the reference source (tests/golden/reference_mocov3.npz,
-    generated by tests/golden/make_golden_necks.py calling the reference method over the shim)."""
+    generated by tests/golden/make_golden_models.py calling the reference method over the shim)."""
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_mocov3.npz"))
     for tag in ("a", "b"):
         loss, _, labels = OC.mocov3_contrastive_loss(g["q_" + tag], g["k_" + tag], float(g["T_" + tag]), rank=0)

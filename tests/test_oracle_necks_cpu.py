@@ -1,5 +1,5 @@
 """oracle/resnet.py necks against golden vectors produced by the reference's own neck classes
-(tests/golden/make_golden_necks.py: passl_v110/modeling/necks/base_neck.py run over the paddle shim)."""
+(tests/golden/make_golden_models.py: passl_v110/modeling/necks/base_neck.py run over the paddle shim)."""
 import os
 
 import numpy as np

@@ -72,7 +72,7 @@ def test_oracle_resnet50_global_stats_matches_torchvision_eval_mode():
 
 def test_oracle_matches_reference_resnet_code_reduced_width():
     """oracle/resnet.py against golden output of the reference's OWN ResNet code (resnetimagenet.py `_make_layer` +
-    `BottleneckBlock` + stem, reduced widths; tests/golden/make_golden_necks.py gen_resnet_layer)."""
+    `BottleneckBlock` + stem, reduced widths; tests/golden/make_golden_models.py gen_resnet_layer)."""
     import os
     import numpy as np
     import oracle.resnet as OR

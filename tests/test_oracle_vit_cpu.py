@@ -43,7 +43,7 @@ def test_clip_block_quickgelu_causal_matches_torch_encoder_layer():
 
 def test_vit_block_matches_reference_block_class():
     """oracle/vit.py `block` against golden vectors from the reference's own `Block` / `Attention` / `Mlp` classes
-    (passl/models/vision_transformer.py:84-206 run over the paddle shim, tests/golden/make_golden_necks.py)."""
+    (passl/models/vision_transformer.py:84-206 run over the paddle shim, tests/golden/make_golden_models.py)."""
     import os
     import numpy as np
     import oracle.vit as OV
