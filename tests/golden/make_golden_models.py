@@ -311,8 +311,72 @@ def seeded_conv(module, rng):
     return out
 
 
+def gen_mae_model():
+    """The reference's whole MaskedAutoencoderViT (passl/models/mae.py:37-290: PatchEmbed, pos-embeds, random_masking with the
+    noise supplied through paddle.rand, encoder, decoder, forward_loss) at a reduced size, seeded weights, norm_pix_loss on and off:
+    tests/golden/reference_mae_model.npz (weights in the paddle layouts: Linear [in, out], Conv2D [E, C, p, p])."""
+    import paddle
+    nn = sys.modules["paddle.nn"]
+    Fn = torch.nn.functional
+
+    class Conv2Db(nn.Layer):                                   # patch embedding: kernel = stride = patch, with bias
+        def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, bias_attr=None, **kw):
+            super().__init__()
+            k = kernel_size if isinstance(kernel_size, (tuple, list)) else (kernel_size, kernel_size)
+            self.weight = torch.nn.Parameter(torch.zeros(out_channels, in_channels, k[0], k[1], dtype=torch.float64))
+            self.bias = None if bias_attr is False else torch.nn.Parameter(torch.zeros(out_channels, dtype=torch.float64))
+            self.stride, self.padding = stride, padding
+
+        def forward(self, x):
+            return Fn.conv2d(x, self.weight, self.bias, stride=self.stride, padding=self.padding)
+    nn.Conv2D = Conv2Db
+    nn.LayerList = torch.nn.ModuleList
+    torch.Tensor._share_buffer_to = lambda self, other: None    # paddle-internal aliasing used only by the initialisers
+    nn.Layer.create_parameter = lambda self, shape, **kw: torch.nn.Parameter(torch.zeros(tuple(shape), dtype=torch.float64),
+                                                                             requires_grad=False)   # forward-only goldens
+
+    class _NoInit(types.ModuleType):
+        def __getattr__(self, n):
+            return lambda *a, **k: None
+    vt = importlib.import_module("passl.models.vision_transformer")
+    vt.init = _NoInit("init")
+    mae = importlib.import_module("passl.models.mae")
+    mae.init = _NoInit("init")
+    rng = np.random.RandomState(19)
+    out = {}
+    N, IMG, P = 4, 32, 8
+    imgs, noise = rng.randn(N, 3, IMG, IMG), rng.rand(N, (IMG // P) ** 2)
+    paddle.rand = lambda shape, **kw: torch.from_numpy(noise)
+    _orig_no_grad = torch.Tensor.copy_
+    for npl in (0, 1):
+        net = mae.MaskedAutoencoderViT(img_size=IMG, patch_size=P, in_chans=3, embed_dim=32, depth=2, num_heads=2,
+                                       decoder_embed_dim=16, decoder_depth=1, decoder_num_heads=2, mlp_ratio=4.,
+                                       norm_pix_loss=bool(npl))
+        if npl == 0:
+            for name, prm in net.named_parameters():
+                if "pos_embed" in name:                        # fixed sin-cos tables from initialize_weights(): keep, and record
+                    out["w_" + name] = prm.detach().numpy().copy()
+                    continue
+                if prm.dim() >= 2:
+                    v = rng.randn(*prm.shape) / np.sqrt(np.prod(prm.shape[1:]) if prm.dim() == 4 else prm.shape[0])
+                elif name.endswith("weight"):
+                    v = 1.0 + 0.2 * rng.randn(*prm.shape)
+                else:
+                    v = 0.1 * rng.randn(*prm.shape)
+                out["w_" + name] = v
+        with torch.no_grad():
+            for name, prm in net.named_parameters():
+                prm.copy_(torch.from_numpy(out["w_" + name]).reshape(prm.shape))
+        loss, pred, mask = net(torch.from_numpy(imgs), mask_ratio=0.75)
+        out["loss%d" % npl], out["pred%d" % npl], out["mask%d" % npl] = loss.detach().numpy(), pred.detach().numpy(), mask.numpy()
+    out["imgs"], out["noise"] = imgs, noise
+    np.savez_compressed(os.path.join(HERE, "reference_mae_model.npz"), **out)
+    print("wrote reference_mae_model.npz: loss", float(out["loss0"]), float(out["loss1"]), "pred", out["pred0"].shape)
+
+
 if __name__ == "__main__":
     gen_mocov3_loss()
     gen_vit_block()
     gen_clip_block()
     gen_resnet_layer()
+    gen_mae_model()
