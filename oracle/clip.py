@@ -45,7 +45,8 @@ def encode_image(img, p, cfg, pre="visual."):
     ps, W = cfg["patch_size"], cfg["width"]
     g = img.shape[2] // ps
     x = img.reshape(B, 3, g, ps, g, ps).permute(0, 2, 4, 3, 5, 1).reshape(B, g * g, ps * ps * 3)     # (p, q, c) order
-    x = x.bfloat16().to(img.dtype)                                                                    # im2col emits bf16 operands
+    if cfg.get("round_pixels", True):
+        x = x.bfloat16().to(img.dtype)                                                                # im2col emits bf16 operands
     x = F.linear(x, p[pre + "patch_embed.proj.weight"], p.get(pre + "patch_embed.proj.bias"))
     x = torch.cat([p[pre + "class_embedding"].expand(B, -1, -1), x], dim=1) + p[pre + "positional_embedding"]
     if cfg.get("pre_norm", False):

@@ -374,9 +374,77 @@ def gen_mae_model():
     print("wrote reference_mae_model.npz: loss", float(out["loss0"]), float(out["loss1"]), "pred", out["pred0"].shape)
 
 
+def gen_clip_model():
+    """The reference's whole CLIP model (passl_v110/modeling/backbones/clip.py:184-338 with the v110 VisionTransformer /
+    Transformer of backbones/vision_transformer.py) + CLIPHead (heads/clip_head.py:27-35) at a reduced size with seeded weights:
+    image / text features, both logit matrices, the three losses and the clamped logit_scale — tests/golden/reference_clip_model.npz."""
+    import paddle
+    nn = sys.modules["paddle.nn"]
+
+    class Embedding(nn.Layer):
+        def __init__(self, num_embeddings, embedding_dim, **kw):
+            super().__init__()
+            self.weight = torch.nn.Parameter(torch.zeros(num_embeddings, embedding_dim, dtype=torch.float64))
+
+        def forward(self, ids):
+            return self.weight[ids]
+    nn.Embedding = Embedding
+    nn.Layer.add_parameter = lambda self, name, prm: None          # create_parameter results are already attributes
+    paddle.shape = lambda x: list(x.shape)
+    paddle.get_default_dtype = lambda: "float32"
+    tens = paddle_shim._Permissive("paddle.tensor")
+    tens.triu = torch.triu
+    paddle.tensor = tens
+    sys.modules["paddle.tensor"] = tens
+    _norm = torch.Tensor.norm
+    torch.Tensor.norm = lambda self, p=2, axis=None, keepdim=False, **kw: _norm(self, p=p, dim=axis if axis is not None else kw.get("dim"),
+                                                                               keepdim=keepdim)
+    clip = importlib.import_module("passl_v110.modeling.backbones.clip")
+    head_mod = importlib.import_module("passl_v110.modeling.heads.clip_head")
+    cfg = dict(embed_dim=16, image_resolution=32, vision_layers=2, vision_width=64, vision_patch_size=8, pre_norm=True, proj=True,
+               patch_bias=False, context_length=8, vocab_size=50, transformer_width=32, transformer_heads=2, transformer_layers=2,
+               qkv_bias=True)
+    net = clip.CLIP(**cfg)
+    rng = np.random.RandomState(41)
+    out = {}
+    with torch.no_grad():
+        for name, prm in net.named_parameters():
+            if name == "logit_scale":
+                v = np.array([np.log(1 / 0.07)])
+            elif prm.dim() >= 2:
+                fan = np.prod(prm.shape[1:]) if prm.dim() == 4 else prm.shape[-2] if name.endswith("weight") and prm.dim() == 2 else prm.shape[-1]
+                v = rng.randn(*prm.shape) / np.sqrt(fan)
+            elif name.endswith("weight"):
+                v = 1.0 + 0.2 * rng.randn(*prm.shape)
+            else:
+                v = 0.1 * rng.randn(*prm.shape)
+            prm.copy_(torch.from_numpy(np.asarray(v, dtype=np.float64)).reshape(prm.shape))
+            out["w_" + name] = np.asarray(v, dtype=np.float64).reshape(tuple(prm.shape))
+    n = 6
+    img = rng.randn(n, 3, 32, 32)
+    text = rng.randint(1, 49, size=(n, 8)).astype(np.int64)
+    text[np.arange(n), rng.randint(1, 8, size=n)] = 49              # EOT = highest id (clip.py:306)
+    out["img"], out["text"] = img, text
+    ti, tt = torch.from_numpy(img), torch.from_numpy(text)
+    out["image_features"] = net.encode_image(ti).detach().numpy()
+    out["text_features"] = net.encode_text(tt).detach().numpy()
+    il, tl = net(ti, tt, is_train=True)
+    out["image_logits"], out["text_logits"] = il.detach().numpy(), tl.detach().numpy()
+    out["logit_scale_after"] = net.logit_scale.detach().numpy().copy()
+    labels = torch.arange(n)
+    o = head_mod.CLIPHead()(il, tl, labels, labels)
+    for k in ("img_loss", "text_loss", "loss"):
+        out[k] = o[k].detach().numpy()
+    for k, v in cfg.items():
+        out["cfg_" + k] = np.int64(v)
+    np.savez_compressed(os.path.join(HERE, "reference_clip_model.npz"), **out)
+    print("wrote reference_clip_model.npz: loss", float(out["loss"]), "features", out["image_features"].shape, out["text_features"].shape)
+
+
 if __name__ == "__main__":
     gen_mocov3_loss()
     gen_vit_block()
     gen_clip_block()
     gen_resnet_layer()
     gen_mae_model()
+    gen_clip_model()
