@@ -4,7 +4,9 @@ backbones/vision_transformer.py:95-183 (v110 Attention with additive attn_mask, 
 (VisionTransformer.forward_features on the `proj` path), base_transformer.py:25-28 (QuickGELU), heads/clip_head.py:27-35
 (CLIPHead) and architectures/CLIPWrapper.py:45-51 (labels = arange).  Driven by a parameter dict exported from the CUDA module
 (oracle.vit.export_params: 2-D weights rounded to bf16 = what the tensor cores multiply; weights stored [out, in]).
-The head itself is pinned against the reference source by tests/golden (clip_* entries of reference_heads.npz)."""
+Pinned against the reference's own source run over the paddle shim: CLIPHead (reference_heads.npz), the v110 Block with / without
+the causal mask (reference_clip_block.npz) and the whole CLIP model + head at a reduced size (reference_clip_model.npz: both towers,
+logits, losses, logit_scale clamp) — tests/test_oracle_vit_cpu.py, tests/test_oracle_clip_model_cpu.py."""
 import math
 
 import torch

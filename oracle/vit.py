@@ -4,7 +4,9 @@ passl/models/mae.py:214-290 (forward_encoder, forward_decoder, forward_loss, for
 the CUDA module (weights rounded to bf16 = what the tensor cores multiply).  Paddle semantics restated: nn.Linear y = xW+b
 (weights here are stored [out, in]), nn.LayerNorm(epsilon), nn.GELU exact erf, softmax over the last axis, Tensor.var unbiased.
 The masking noise is an input (Paddle's RNG stream is not reproducible).  patchify / random_masking / forward_loss are pinned
-against the reference source through oracle/mae.py + tests/golden (numpy); this file is the differentiable torch twin."""
+against the reference source through oracle/mae.py + tests/golden (numpy); this file is the differentiable torch twin, itself
+pinned against the reference's `Block` class (reference_vit_block.npz) and whole `MaskedAutoencoderViT` (reference_mae_model.npz)
+run over the paddle shim (tests/test_oracle_vit_cpu.py, tests/test_oracle_mae_model_cpu.py)."""
 import torch
 import torch.nn.functional as F
 
