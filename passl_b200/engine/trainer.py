@@ -118,6 +118,12 @@ class Trainer:
     def save(self, path=None):
         if path is None:
             path = os.path.join(self.output_dir or ".", "iter_%d.pd" % self.current_iter)
+        if get_rank() == 0 and path.endswith(".pdparams"):
+            # the reference's own container / parameter names / layouts (MoCo ResNet path), see utils/checkpoint.py
+            from ..utils import checkpoint as C
+            os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+            C.save_pdparams(C.moco_to_paddle(self.model), path)
+            return path
         if get_rank() == 0:
             os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
             torch.save({"iter": self.current_iter, "state_dict": self.model.state_dict(),
