@@ -5,7 +5,8 @@ optimizer step, LR schedule and the `ips: ... images/sec` log line the reference
 Only what the hot path needs is here: synthetic or user-supplied iterables of (view_q, view_k) batches, the name-based model
 registry, the fused optimizers, the data-parallel gradient exchange and checkpoint / resume in the spirit of
 hooks/checkpoint_hook.py:22-49 (`{output_dir}/iter_{N}.pd` holding model, optimizer, lr-scheduler state and the iteration; torch
-serialisation — the Paddle `.pdparams` pickle layout is SURVEY §8 f-3, not done).  Evaluation hooks are out of scope."""
+serialisation; a path ending in `.pdparams` is written / read in the reference's own container, names and layouts through
+utils/checkpoint.py).  Evaluation hooks are out of scope."""
 import os
 import time
 
@@ -119,10 +120,10 @@ class Trainer:
         if path is None:
             path = os.path.join(self.output_dir or ".", "iter_%d.pd" % self.current_iter)
         if get_rank() == 0 and path.endswith(".pdparams"):
-            # the reference's own container / parameter names / layouts (MoCo ResNet path), see utils/checkpoint.py
+            # the reference's own container / parameter names / layouts, see utils/checkpoint.py
             from ..utils import checkpoint as C
             os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
-            C.save_pdparams(C.moco_to_paddle(self.model), path)
+            C.save_pdparams(C.to_paddle_state(self.model), path)
             return path
         if get_rank() == 0:
             os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
@@ -131,15 +132,23 @@ class Trainer:
                         "lr_scheduler": None if self.lr_scheduler is None else {"last_epoch": self.lr_scheduler.last_epoch}}, path)
         return path
 
-    def resume(self, path):
-        ck = torch.load(path, map_location=self.device)
-        self.model.load_state_dict(ck["state_dict"])
+    def _weights_changed(self):
         for st in (getattr(self.model, "_stores", None) or (self.store,)):
             if st is not None:
                 st.refresh_bf16()                        # parameters are views of the flat fp32 master: refresh the bf16 mirror
         if hasattr(self.model, "_queue_bf16") and self.model._queue_bf16 is not None:
             from .. import kernels as K
             self.model._queue_bf16 = K.cast_bf16(self.model.queue)
+
+    def resume(self, path):
+        if path.endswith(".pdparams"):                   # weights only, in the reference's container (pretrained / converted files)
+            from ..utils import checkpoint as C
+            C.load_paddle_state(self.model, C.load_pdparams(path))
+            self._weights_changed()
+            return
+        ck = torch.load(path, map_location=self.device)
+        self.model.load_state_dict(ck["state_dict"])
+        self._weights_changed()
         self.optimizer.set_state_dict(ck["optimizer"])
         if self.lr_scheduler is not None and ck.get("lr_scheduler"):
             self.lr_scheduler.last_epoch = ck["lr_scheduler"]["last_epoch"]

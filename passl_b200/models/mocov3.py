@@ -18,8 +18,23 @@ from ..core.param_store import ParamStore
 from ..distributed import concat_all_gather, get_rank
 from ..loss.contrastive import gathered_infonce, normalize
 from ..nn.layers import BatchNorm1D, Linear
-from .mae import get_2d_sincos_pos_embed
 from .vision_transformer import VisionTransformer
+
+
+def mocov3_sincos_pos_embed(embed_dim, grid_h, grid_w, temperature=10000.0):
+    """Fixed position table of MoCo v3 (mocov3.py:67-91), [1, 1 + grid_h*grid_w, embed_dim] fp32, class-token row zero.
+
+    Row p of the table is [sin(a w), cos(a w), sin(b w), cos(b w)] with frequencies w_i = temperature^(-i / (D/4)) and
+    (a, b) = (p // grid_h, p % grid_h): the reference meshgrids (arange(w), arange(h)) with 'ij' indexing and flattens, so the
+    slow coordinate comes first.  This differs from the MAE table (models/mae.py) by the order of the two halves."""
+    assert embed_dim % 4 == 0, "Embed dimension must be divisible by 4 for 2D sin-cos position embedding"
+    pos_dim = embed_dim // 4
+    omega = 1.0 / (temperature ** (torch.arange(pos_dim, dtype=torch.float64) / pos_dim))
+    p = torch.arange(grid_h * grid_w, dtype=torch.float64)
+    a, b = torch.div(p, grid_h, rounding_mode="floor"), torch.remainder(p, grid_h)
+    oa, ob = a[:, None] * omega[None], b[:, None] * omega[None]
+    table = torch.cat([oa.sin(), oa.cos(), ob.sin(), ob.cos()], dim=1)
+    return torch.cat([torch.zeros(1, embed_dim, dtype=torch.float64), table], dim=0).unsqueeze(0).float()
 
 
 class _MLPFn(torch.autograd.Function):
@@ -91,7 +106,7 @@ class MoCoV3ViT(VisionTransformer):
         super().__init__(**kwargs)
         g = int(self.patch_embed.num_patches ** .5)
         with torch.no_grad():
-            self.pos_embed.copy_(torch.from_numpy(get_2d_sincos_pos_embed(self.embed_dim, g, True)).float().unsqueeze(0))
+            self.pos_embed.copy_(mocov3_sincos_pos_embed(self.embed_dim, g, g))
         self.pos_embed.requires_grad = False
 
 

@@ -448,3 +448,30 @@ if __name__ == "__main__":
     gen_resnet_layer()
     gen_mae_model()
     gen_clip_model()
+
+
+def gen_mocov3_pos_embed():
+    """MoCoV3ViT.build_2d_sincos_position_embedding (passl/models/mocov3.py:67-91) called as an unbound method on a stub `self`
+    (patch_embed sizes, embed_dim, create_parameter) — the fixed position table of MoCo v3, which is NOT the MAE table (meshgrid
+    indexing differs); square and non-square grids -> tests/golden/reference_mocov3_pos.npz."""
+    import paddle
+    paddle.meshgrid = lambda *xs: torch.meshgrid(*xs, indexing="ij")          # paddle.meshgrid is 'ij'-indexed
+    paddle.sin, paddle.cos = torch.sin, torch.cos
+    mod = importlib.import_module("passl.models.mocov3")
+    out = {}
+    for tag, (ih, iw, p, dim) in {"a": (112, 112, 8, 64), "b": (32, 32, 8, 768), "c": (24, 40, 8, 32)}.items():
+        box = {}
+
+        class _P:
+            def set_value(self, v):
+                box["v"] = v
+        stub = types.SimpleNamespace(patch_embed=types.SimpleNamespace(img_size=(ih, iw), patch_size=(p, p)), embed_dim=dim,
+                                     create_parameter=lambda shape: _P())
+        mod.MoCoV3ViT.build_2d_sincos_position_embedding(stub)
+        out["cfg_" + tag], out["pos_" + tag] = np.array([ih // p, iw // p, dim]), box["v"].numpy()
+    np.savez_compressed(os.path.join(HERE, "reference_mocov3_pos.npz"), **out)
+    print("wrote reference_mocov3_pos.npz", {k: v.shape for k, v in out.items() if k.startswith("pos")})
+
+
+if __name__ == "__main__":
+    gen_mocov3_pos_embed()
