@@ -101,9 +101,12 @@ class MLPBN(nn.Module):
 class MoCoV3ViT(VisionTransformer):
     """ViT with the fixed 2-D sin-cos position embedding (mocov3.py:37-91)."""
 
-    def __init__(self, **kwargs):
+    def __init__(self, stop_grad_conv1=False, **kwargs):
         kwargs.setdefault("learnable_pos", False)
         super().__init__(**kwargs)
+        if stop_grad_conv1:                          # mocov3.py:63-65: the patch projection stays at its random initialisation
+            self.patch_embed.proj.weight.requires_grad = False
+            self.patch_embed.proj.bias.requires_grad = False
         g = int(self.patch_embed.num_patches ** .5)
         with torch.no_grad():
             self.pos_embed.copy_(mocov3_sincos_pos_embed(self.embed_dim, g, g))
@@ -196,7 +199,8 @@ class _Add(torch.autograd.Function):
 def mocov3_vit_base_pretrain(**kwargs):
     """mocov3.py:288-297"""
     def enc():
-        return MoCoV3ViT(patch_size=16, embed_dim=768, depth=12, num_heads=12, mlp_ratio=4, qkv_bias=True, epsilon=1e-6)
+        return MoCoV3ViT(patch_size=16, embed_dim=768, depth=12, num_heads=12, mlp_ratio=4, qkv_bias=True, epsilon=1e-6,
+                         stop_grad_conv1=True)       # mocov3.py:289
     kw = dict(dim=256, mlp_dim=4096, T=0.2)
     kw.update(kwargs)
     return MoCoV3Pretrain(enc, **kw)

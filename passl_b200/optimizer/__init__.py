@@ -18,10 +18,30 @@ def _wd_table(store, weight_decay, exclude):
     pats = [re.compile(p) for p in (exclude or [])]
 
     def fn(name, p):
+        if not p.requires_grad:                      # frozen tensors take no step at all (passl/optimizer/__init__.py:88-91,117)
+            return 0.0
         if p.dim() <= 1 and exclude is None:
             return weight_decay
         return 0.0 if any(r.search(name) for r in pats) else weight_decay
     return store.segment_values(fn)
+
+
+def trainable_ranges(store):
+    """[(offset, numel)] of the maximal runs of trainable tensors in the flat buffer (alignment padding included).  Frozen
+    tensors (pos-embeddings, stop_grad_conv1, frozen stages) live in the same buffer but must see neither the gradient step nor
+    weight decay — the reference's group builder drops stop_gradient parameters (passl/optimizer/__init__.py:88-91,117) and
+    adamw.py:57-59 skips parameters without a gradient."""
+    runs, start = [], None
+    bounds = list(store.offsets[1:]) + [store.numel]
+    for p, o, e in zip(store.params, store.offsets, bounds):
+        if p.requires_grad:
+            start = o if start is None else start
+        elif start is not None:
+            runs.append((start, o - start))
+            start = None
+    if start is not None:
+        runs.append((start, store.numel - start))
+    return runs
 
 
 class _FlatOptimizer:
@@ -63,12 +83,15 @@ class Momentum(_FlatOptimizer):
         super().__init__(store, lr)
         self.momentum, self.weight_decay = momentum, weight_decay
         self.velocity = torch.zeros_like(store.master)
+        self._ranges = trainable_ranges(store)       # the scalar-decay kernel has no per-tensor table: skip frozen runs on the host
 
     def step(self):
         lib, s = _lib.load(), self.store
-        _lib.check(lib.passl_b200_sgd_momentum(s.master.data_ptr(), s.grad.data_ptr(), self.velocity.data_ptr(),
-                                               s.bf16.data_ptr(), self.lr, self.momentum, self.weight_decay, self.grad_scale,
-                                               s.numel, torch.cuda.current_stream().cuda_stream), "sgd_momentum")
+        st = torch.cuda.current_stream().cuda_stream
+        for off, n in self._ranges:                  # one launch when nothing is frozen (the usual case)
+            _lib.check(lib.passl_b200_sgd_momentum(s.master.data_ptr() + 4 * off, s.grad.data_ptr() + 4 * off,
+                                                   self.velocity.data_ptr() + 4 * off, s.bf16.data_ptr() + 2 * off, self.lr,
+                                                   self.momentum, self.weight_decay, self.grad_scale, n, st), "sgd_momentum")
         self._step += 1
 
     def state_dict(self):
@@ -109,8 +132,8 @@ class AdamW(_FlatOptimizer):
         self.m = torch.zeros_like(store.master)
         self.v = torch.zeros_like(store.master)
         pats = [re.compile(p) for p in (no_decay or [])]
-        self.seg_wd = store.segment_values(
-            lambda n, p: 0.0 if (p.dim() <= 1 or any(r.search(n) for r in pats)) else weight_decay)
+        self.seg_wd = store.segment_values(          # frozen tensors: zero gradient + zero decay = no step (adamw.py:57-59)
+            lambda n, p: 0.0 if (not p.requires_grad or p.dim() <= 1 or any(r.search(n) for r in pats)) else weight_decay)
         self.seg_lr = store.segment_values(lr_ratio) if lr_ratio is not None else None
 
     def step(self):

@@ -11,12 +11,16 @@ def test_mocov3_small_step():
     from passl_b200.optimizer import AdamW
 
     def enc():
-        return MoCoV3ViT(img_size=64, patch_size=16, embed_dim=128, depth=2, num_heads=2, qkv_bias=True, epsilon=1e-6)
+        return MoCoV3ViT(img_size=64, patch_size=16, embed_dim=128, depth=2, num_heads=2, qkv_bias=True, epsilon=1e-6,
+                         stop_grad_conv1=True)
     torch.manual_seed(0)
     m = MoCoV3Pretrain(enc, dim=128, mlp_dim=256, T=0.2, max_steps=10).cuda()
     st, sk = m.build_param_stores()
     opt = AdamW(st, lr=1e-3, weight_decay=0.1)
     k0 = sk.master.clone()
+    vit = m.base_encoder.vit
+    frozen0 = [t.detach().clone() for t in (vit.pos_embed, vit.patch_embed.proj.weight, vit.patch_embed.proj.bias)]
+    w0 = vit.blocks[0].qkv.weight.detach().clone()
     losses = []
     for it in range(3):
         x1 = torch.randn(16, 3, 64, 64, device="cuda")
@@ -33,6 +37,55 @@ def test_mocov3_small_step():
     assert st.grad.abs().sum().item() > 0
     # the momentum encoder never receives gradients
     assert all(p.grad is None for p in m.momentum_encoder.parameters())
+    # frozen tensors (fixed sin-cos table, stop_grad_conv1 patch projection: mocov3.py:63-65,91) see neither step nor weight decay
+    for t0, t in zip(frozen0, (vit.pos_embed, vit.patch_embed.proj.weight, vit.patch_embed.proj.bias)):
+        assert torch.equal(t0, t.detach())
+    assert not torch.equal(w0, vit.blocks[0].qkv.weight.detach())
+
+
+def test_optimizers_leave_frozen_tensors_alone():
+    """A frozen tensor in the flat buffer takes no step and no weight decay under any optimizer (the reference's group builder drops
+    stop_gradient parameters, passl/optimizer/__init__.py:88-91); its trainable neighbours follow the plain update rule."""
+    from passl_b200.core import ParamStore
+    from passl_b200.optimizer import AdamW, LarsMomentumOptimizer, Momentum
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = torch.nn.Parameter(torch.randn(40, 50))
+            self.frozen = torch.nn.Parameter(torch.randn(3, 700), requires_grad=False)
+            self.b = torch.nn.Parameter(torch.randn(64, 33))
+            self.frozen_tail = torch.nn.Parameter(torch.randn(1, 5, 8), requires_grad=False)
+    for make in (lambda s: Momentum(s, lr=0.1, momentum=0.9, weight_decay=0.01),
+                 lambda s: LarsMomentumOptimizer(s, lr=0.1, lars_weight_decay=0.01, exclude_from_weight_decay=()),
+                 lambda s: AdamW(s, lr=0.1, weight_decay=0.5)):
+        torch.manual_seed(5)
+        m = M().cuda()
+        st = ParamStore(m)
+        opt = make(st)
+        before = {k: v.detach().clone() for k, v in m.named_parameters()}
+        for _ in range(2):
+            opt.clear_grad()
+            m.a.grad.add_(torch.randn_like(m.a))
+            m.b.grad.add_(torch.randn_like(m.b))
+            opt.step()
+        assert torch.equal(before["frozen"], m.frozen.detach()) and torch.equal(before["frozen_tail"], m.frozen_tail.detach())
+        assert not torch.equal(before["a"], m.a.detach()) and not torch.equal(before["b"], m.b.detach())
+        assert torch.equal(m.frozen.bf16.float(), m.frozen.detach().bfloat16().float())
+    # Momentum rule on the trainable tensors, checked in full: v = mu v + (g + wd p); p -= lr v
+    torch.manual_seed(6)
+    m = M().cuda()
+    st = ParamStore(m)
+    opt = Momentum(st, lr=0.1, momentum=0.9, weight_decay=0.01)
+    p, v = m.b.detach().clone().double(), torch.zeros_like(m.b, dtype=torch.float64)
+    for _ in range(3):
+        opt.clear_grad()
+        g = torch.randn_like(m.b)
+        m.b.grad.add_(g)
+        opt.step()
+        v = 0.9 * v + (g.double() + 0.01 * p)
+        p = p - 0.1 * v
+    assert (m.b.detach().double() - p).abs().max().item() < 1e-5
 
 
 def test_mae_vit_base_shape_step():
@@ -98,6 +151,39 @@ def test_trainer_checkpoint_resume(tmp_path):
     out_b = tr2.train()
     np.testing.assert_allclose(float(out_b["loss"]), float(out_a["loss"]), rtol=2e-3)
     torch.testing.assert_close(tr2.store.master, tr.store.master, rtol=1e-3, atol=1e-4)
+
+
+def test_trainer_pdparams_weights_roundtrip(tmp_path):
+    """Weights written in the reference's container / names / layouts (utils/checkpoint.py) and read back into a fresh Trainer give
+    the same parameters (fp32 master and the bf16 mirror the kernels read) and the same loss on the same batch."""
+    from passl_b200.engine import trainer as T
+    from passl_b200.utils import checkpoint as C
+    from passl_b200.utils.config import get_config
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    over = ["model.K=1024", "dataloader.train.sampler.batch_size=16", "total_iters=2", "log_config.interval=100"]
+    tr = T.Trainer(get_config(os.path.join(root, "configs/moco/moco_v2_r50.yaml"), over),
+                   dataloader=T.SyntheticTwoViews(16, 2, torch.device("cuda"), size=64))
+    tr.train()
+    path = tr.save(str(tmp_path / "epoch_1.pdparams"))
+    state = C.load_pdparams(path)
+    assert state["encoder_q.0.conv1.weight"].shape == (64, 3, 7, 7) and state["queue"].shape == (128, 1024)
+    tr2 = T.Trainer(get_config(os.path.join(root, "configs/moco/moco_v2_r50.yaml"), over),
+                    dataloader=T.SyntheticTwoViews(16, 2, torch.device("cuda"), size=64))
+    tr2.resume(path)
+    tr.model.flush_queue()
+    for (k, a), (_, b) in zip(tr.model.state_dict().items(), tr2.model.state_dict().items()):
+        if k.endswith("stem.weight"):
+            a, b = a[:, :147], b[:, :147]
+        assert torch.equal(a, b), k
+    qa, qb = tr.model.encoder_q[0].blocks[3].conv2.weight, tr2.model.encoder_q[0].blocks[3].conv2.weight
+    assert torch.equal(qa.bf16, qb.bf16)                                   # the compute mirror was refreshed
+    torch.manual_seed(9)
+    x1 = torch.randn(16, 3, 64, 64, device="cuda")
+    x2 = x1 + 0.1 * torch.randn_like(x1)
+    la = tr.model(x1, x2)["loss"].item()
+    lb = tr2.model(x1, x2)["loss"].item()
+    assert abs(la - lb) <= 1e-3 * abs(la), (la, lb)
 
 
 def test_trainer_surface_clip():
