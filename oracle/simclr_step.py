@@ -64,8 +64,11 @@ def simclr_head_loss(h1, h2, T):
     return (loss_a + loss_b).mean() + 3 * (kl1 + kl2)
 
 
-def train_step(p, velocity, img_q, img_k, lr=0.1, T=0.1, momentum=0.9, lars_wd=1e-4, lars_coeff=0.001):
-    """One iteration: forward, backward, LarsMomentum update (python loop per tensor, like the reference). Returns loss."""
+def train_step(p, velocity, img_q, img_k, lr=0.1, T=0.1, momentum=0.9, lars_wd=1e-4, lars_coeff=0.001, exclude=None):
+    """One iteration: forward, backward, LarsMomentum update (python loop per tensor, like the reference). Returns loss.
+    `exclude(name) -> bool` marks tensors without decay / trust ratio; None = every tensor decays, which is what the SimCLR YAML's
+    exclude list amounts to in the reference (its substrings match none of Paddle's generated names, see
+    passl_b200/optimizer/naming.py)."""
     img = torch.cat([img_q, img_k])                                  # simclr.py:55
     feat = R.resnet_forward(img, p, with_pool=True)
     con = R.neck_fc3(feat, p, prefix="neck.")
@@ -75,7 +78,7 @@ def train_step(p, velocity, img_q, img_k, lr=0.1, T=0.1, momentum=0.9, lars_wd=1
     grads = torch.autograd.grad(loss, list(p.values()))
     with torch.no_grad():
         for (name, w), g in zip(p.items(), grads):
-            wd = 0.0 if (name.endswith(".bias") or ".bn." in name) else lars_wd
+            wd = 0.0 if (exclude is not None and exclude(name)) else lars_wd
             pn, gn = w.norm(), g.norm()
             local_lr = lr * lars_coeff * pn / (gn + wd * pn) if (wd > 0 and pn > 0 and gn > 0) else lr
             v = velocity.setdefault(name, torch.zeros_like(w))

@@ -18,6 +18,7 @@ class ParamStore:
         device = device or params[0].device
         self.params = params
         self.names = [n for n, _ in module.named_parameters()]
+        self.module = module                         # optimizers derive Paddle-style auto names from the module tree
         self.offsets, off = [], 0
         for p in params:
             self.offsets.append(off)

@@ -15,7 +15,7 @@ import torch
 from ..core.param_store import ParamStore
 from ..distributed import get_rank, get_world_size, grad_sync, param_sync
 from ..modeling import build_model
-from ..optimizer import CosineAnnealingDecay, build_optimizer
+from ..optimizer import build_lr_scheduler, build_lr_scheduler_simclr, build_optimizer
 
 
 class IterLoader:
@@ -91,13 +91,6 @@ class Trainer:
         else:
             self.store = ParamStore(enc)
         param_sync(self.store)
-        opt_cfg = dict(cfg.optimizer)
-        lr_cfg = dict(cfg.get("lr_scheduler", {}) or {})
-        self.lr_scheduler = None
-        if lr_cfg.get("name") == "CosineAnnealingDecay":
-            self.lr_scheduler = CosineAnnealingDecay(lr_cfg["learning_rate"], lr_cfg["T_max"])
-            opt_cfg.setdefault("lr", lr_cfg["learning_rate"])
-        self.optimizer = build_optimizer(opt_cfg, self.store)
         self.batch_size = cfg.dataloader.train.sampler.batch_size
         if dataloader is None:
             iters = cfg.get("total_iters", 10)
@@ -108,6 +101,20 @@ class Trainer:
                                                 context_length=arch.context_length, vocab_size=arch.vocab_size)
             else:
                 dataloader = SyntheticTwoViews(self.batch_size, iters, self.device)
+        # LR schedule (engine/trainer.py:140-166 of the reference): epoch-denominated YAML keys become iterations through
+        # iters_per_epoch = len(dataloader); the SimCLR recipe derives rate, warm-up and horizon from batch size and image count
+        self.epochs = cfg.get("epochs", 1)
+        self.iters_per_epoch = cfg.get("iters_per_epoch", None) or len(dataloader)
+        opt_cfg = dict(cfg.optimizer)
+        lr_cfg = dict(cfg.get("lr_scheduler", {}) or {})
+        self.lr_scheduler = None
+        if lr_cfg:
+            if cfg.get("use_simclr_iters", False):
+                self.lr_scheduler = build_lr_scheduler_simclr(lr_cfg, self.iters_per_epoch, self.batch_size * 8, self.epochs, 0)
+            else:
+                self.lr_scheduler = build_lr_scheduler(lr_cfg, self.iters_per_epoch)
+            opt_cfg["lr"] = self.lr_scheduler()      # the scheduler object is the optimizer's learning rate (solver/builder.py:88)
+        self.optimizer = build_optimizer(opt_cfg, self.store)
         self.dataloader = dataloader
         self.log_interval = (cfg.get("log_config", {}) or {}).get("interval", 10)
         self.current_iter = 0
@@ -151,7 +158,7 @@ class Trainer:
         self._weights_changed()
         self.optimizer.set_state_dict(ck["optimizer"])
         if self.lr_scheduler is not None and ck.get("lr_scheduler"):
-            self.lr_scheduler.last_epoch = ck["lr_scheduler"]["last_epoch"]
+            self.lr_scheduler.set_state_dict(ck["lr_scheduler"])
         self.current_iter = int(ck["iter"])
 
     def train(self):
@@ -173,7 +180,7 @@ class Trainer:
                 torch.cuda.synchronize()
                 dt = time.time() - t0
                 msg = "[Train][Iter: {}/{}] lr: {:.5f}, loss: {:.5f}, batch_cost: {:.5f}s, ips: {:.5f} images/sec".format(
-                    self.current_iter, total, self.optimizer.get_lr(), float(self.outputs['loss']), dt / self.log_interval, seen / dt)
+                    self.current_iter, total, self.optimizer.get_lr(), float(self.outputs['loss'].detach()), dt / self.log_interval, seen / dt)
                 print(msg, flush=True)
                 t0, seen = time.time(), 0
             if self.checkpoint_interval and self.current_iter % self.checkpoint_interval == 0:

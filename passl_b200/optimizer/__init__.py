@@ -1,28 +1,36 @@
 """Optimizers over ParamStore flat buffers — one fused kernel per step.
 
 API follows the reference's torch-style optimizers (passl/optimizer/optimizer.py:32-233): ``step()``, ``clear_grad()``,
-``lr`` attribute driven by an LR scheduler, ``state_dict()``.  Weight-decay exclusion is expressed per tensor
-(regex on the parameter name), like the reference's param-group builder (passl/optimizer/__init__.py:124-215) and
-v110's ``exclude_from_weight_decay`` (configs/simclr/simclr_r50_IM.yaml:117-119).
+``lr`` attribute driven by an LR scheduler (optimizer/lr.py), ``state_dict()``.  Weight-decay exclusion is a per-tensor table:
+AdamW follows the reference's param-group rule (1-d tensors and `no_decay` names undecayed, frozen tensors skipped —
+passl/optimizer/__init__.py:124-215, tasks/ssl/mae/util/optim_factory.py:21-38); LARS follows v110's
+``exclude_from_weight_decay`` substring list over Paddle's generated parameter names (optimizer/naming.py).
 """
-import math
 import re
 
 import torch
 
 from .. import _lib, kernels as K
 from ..distributed import get_world_size
+from .lr import (CosineAnnealingDecay, LinearWarmup, MultiStepDecay, build_lr_scheduler,  # noqa: F401
+                 build_lr_scheduler_simclr, build_lr_scheduler_v2)
 
 
-def _wd_table(store, weight_decay, exclude):
-    pats = [re.compile(p) for p in (exclude or [])]
+def _wd_table(store, weight_decay, exclude=None, exclude_structured=None):
+    """Per-tensor decay table.  `exclude`: substrings of the Paddle-style auto name (`conv2d_3.w_0`, `batch_norm2d_3.b_0`,
+    `linear_0.b_0`), the reference's LARS semantics — see optimizer/naming.py; `exclude_structured`: regexes on the state_dict
+    key (`blocks.3.conv1.bn.weight`), for callers who want to name tensors the PyTorch way."""
+    from .naming import paddle_auto_names
+    subs = list(exclude or [])
+    pats = [re.compile(p) for p in (exclude_structured or [])]
+    auto = dict(zip(store.names, paddle_auto_names(store.module))) if subs else {}
 
     def fn(name, p):
         if not p.requires_grad:                      # frozen tensors take no step at all (passl/optimizer/__init__.py:88-91,117)
             return 0.0
-        if p.dim() <= 1 and exclude is None:
-            return weight_decay
-        return 0.0 if any(r.search(name) for r in pats) else weight_decay
+        if any(s in auto[name] for s in subs) or any(r.search(name) for r in pats):
+            return 0.0
+        return weight_decay
     return store.segment_values(fn)
 
 
@@ -99,14 +107,16 @@ class Momentum(_FlatOptimizer):
 
 
 class LarsMomentumOptimizer(_FlatOptimizer):
-    """paddle LarsMomentum as configured by passl_v110/solver/optimizer.py:20-26 and momentum_lars.py:56-114."""
+    """paddle.fluid LarsMomentumOptimizer as configured by passl_v110/solver/optimizer.py:25 and the SimCLR YAML
+    (configs/simclr/simclr_r50_IM.yaml:116-120); update rule of passl/optimizer/momentum_lars.py:56-114.  Tensors whose decay is
+    zero take the plain momentum step (no trust ratio), like the lars_momentum op."""
 
     def __init__(self, store, lr=0.1, momentum=0.9, lars_weight_decay=1e-4, lars_coeff=0.001, epsilon=0.0,
-                 exclude_from_weight_decay=("scale", "offset", r"\.bias", r"bn\.weight", r"bn\.bias")):
+                 exclude_from_weight_decay=None, exclude_structured=None):
         super().__init__(store, lr)
         self.momentum, self.coeff, self.eps = momentum, lars_coeff, epsilon
         self.velocity = torch.zeros_like(store.master)
-        self.seg_wd = _wd_table(store, lars_weight_decay, list(exclude_from_weight_decay))
+        self.seg_wd = _wd_table(store, lars_weight_decay, exclude_from_weight_decay, exclude_structured)
         self.norms = torch.zeros(2 * len(store.params), dtype=torch.float32, device=store.master.device)
 
     def step(self):
@@ -147,20 +157,6 @@ class AdamW(_FlatOptimizer):
 
     def state_dict(self):
         return dict(m=self.m, v=self.v, step=self._step, lr=self.lr)
-
-
-class CosineAnnealingDecay:
-    """paddle.optimizer.lr.CosineAnnealingDecay(learning_rate, T_max) (configs/moco/moco_v2_r50.yaml:84-87)."""
-
-    def __init__(self, learning_rate, T_max, eta_min=0.0):
-        self.base, self.T_max, self.eta_min, self.last_epoch = learning_rate, T_max, eta_min, 0
-
-    def get_lr(self):
-        return self.eta_min + (self.base - self.eta_min) * (1 + math.cos(math.pi * self.last_epoch / self.T_max)) / 2
-
-    def step(self):
-        self.last_epoch += 1
-        return self.get_lr()
 
 
 def build_optimizer(cfg, store):

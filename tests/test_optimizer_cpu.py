@@ -31,9 +31,35 @@ def test_trainable_ranges_skip_frozen_runs():
 def test_weight_decay_tables_zero_frozen_tensors():
     st = ParamStore(_M())
     assert AdamW(st, lr=1e-3, weight_decay=0.5).seg_wd.tolist() == [0.5, 0.0, 0.5, 0.0, 0.0]       # 1-d `c` undecayed, f1 / f2 frozen
-    lars = LarsMomentumOptimizer(st, lr=0.1, lars_weight_decay=1e-4, exclude_from_weight_decay=("^c$",))
+    lars = LarsMomentumOptimizer(st, lr=0.1, lars_weight_decay=1e-4, exclude_structured=("^c$",))
     assert [round(v, 6) for v in lars.seg_wd.tolist()] == [1e-4, 0.0, 1e-4, 0.0, 0.0]
+    lars = LarsMomentumOptimizer(st, lr=0.1, lars_weight_decay=1e-4)                 # fluid default: nothing excluded but frozen
+    assert [round(v, 6) for v in lars.seg_wd.tolist()] == [1e-4, 0.0, 1e-4, 1e-4, 0.0]
     # frozen tensors have no gradient view: nothing can be accumulated into them by accident
     m = _M()
     ParamStore(m)
     assert m.f1.grad is None and m.f2.grad is None and m.a.grad is not None
+
+
+def test_lars_exclude_list_matches_paddle_generated_names():
+    """`exclude_from_weight_decay` is a list of substrings of Paddle's generated parameter names (optimizer/naming.py).  On the SimCLR
+    encoder (ResNet-50 + fc3 neck) the SimCLR YAML's list (configs/simclr/simclr_r50_IM.yaml:120) therefore excludes nothing, while
+    the BYOL YAML's list (configs/moco_byol/moco_byol_r50_IM.yaml:122) excludes every BatchNorm tensor and every bias."""
+    from collections import Counter
+    from passl_b200.modeling import build_model
+    from passl_b200.optimizer.naming import paddle_auto_names
+    model = build_model(dict(name="SimCLR", backbone=dict(name="ResNet", depth=50, with_pool=True),
+                             neck=dict(name="NonLinearNeckfc3", in_channels=2048, hid_channels=2048, out_channels=128, with_avg_pool=False),
+                             head=dict(name="SimCLRContrastiveHead", temperature=0.1)))
+    names = paddle_auto_names(model.encoder)
+    kinds = Counter((n.rsplit("_", 2)[0], n.rsplit(".", 1)[1]) for n in names)
+    assert kinds == {("conv2d", "w_0"): 53, ("batch_norm2d", "w_0"): 53, ("batch_norm2d", "b_0"): 53, ("linear", "w_0"): 3,
+                     ("linear", "b_0"): 3, ("batch_norm1d", "w_0"): 3, ("batch_norm1d", "b_0"): 3}
+    assert names[0] == "conv2d_0.w_0" and len(set(names)) == len(names) == 171
+    st = ParamStore(model.encoder)
+    simclr = LarsMomentumOptimizer(st, exclude_from_weight_decay=["scale", "offset", ".bias"])
+    byol = LarsMomentumOptimizer(st, exclude_from_weight_decay=["batch_norm", ".b_0"])
+    assert int((simclr.seg_wd == 0).sum()) == 0
+    assert int((byol.seg_wd == 0).sum()) == 2 * 53 + 2 * 3 + 3
+    by_name = dict(zip(st.names, byol.seg_wd.tolist()))
+    assert by_name["0.blocks.0.conv1.weight"] > 0 and by_name["0.blocks.0.conv1.bn.weight"] == 0 and by_name["1.fc1.bias"] == 0
