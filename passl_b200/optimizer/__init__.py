@@ -133,17 +133,42 @@ class LarsMomentumOptimizer(_FlatOptimizer):
 
 
 class AdamW(_FlatOptimizer):
-    """passl/optimizer/adamw.py:52-138 (decoupled decay, bias correction); no decay on 1-d tensors by default."""
+    """Decoupled-decay Adam with bias correction (the `adamw` op behind passl/optimizer/adamw.py:52-138 and paddle.optimizer.AdamW).
+
+    Which tensors decay follows the reference's three AdamW call paths:
+      * v2.5 `passl.optimizer.AdamW` (MoCo v3 YAML) and v110 `paddle.optimizer.AdamW` (CLIP YAML): EVERY trainable tensor decays,
+        1-d ones included, unless its state_dict name contains one of the substrings in `no_weight_decay_name`
+        (passl/optimizer/utils/group_params.py:175) / `exclude_from_weight_decay` (passl_v110/solver/builder.py:204-214);
+      * MAE pre-training builds its groups with add_weight_decay: 1-d tensors and `*.bias` undecayed
+        (tasks/ssl/mae/util/optim_factory.py:21-38) -> `one_dim_no_decay=True`;
+      * frozen tensors are never in a group.
+    `no_decay` takes regexes on the state_dict name for callers who prefer them; `betas` / `eps` / `epsilon` cover both YAML
+    spellings; `use_master_param` / `exp_avg_force_fp32` are accepted and moot (master weights and moments are always fp32 here)."""
 
     def __init__(self, store, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01, no_decay=None, lr_ratio=None,
-                 epsilon=None):
+                 epsilon=None, betas=None, one_dim_no_decay=False, exclude_from_weight_decay=None, no_weight_decay_name=None,
+                 use_master_param=True, exp_avg_force_fp32=True):
         super().__init__(store, lr)
-        self.beta1, self.beta2, self.eps = beta1, beta2, (eps if epsilon is None else epsilon)   # `epsilon`: the YAML key
+        if betas is not None:
+            if isinstance(betas, str):                   # the YAML spells it "(0.9, 0.999)"
+                import ast
+                betas = ast.literal_eval(betas)
+            beta1, beta2 = (float(b) for b in betas)
+        self.beta1, self.beta2, self.eps = beta1, beta2, float(eps if epsilon is None else epsilon)
         self.m = torch.zeros_like(store.master)
         self.v = torch.zeros_like(store.master)
         pats = [re.compile(p) for p in (no_decay or [])]
-        self.seg_wd = store.segment_values(          # frozen tensors: zero gradient + zero decay = no step (adamw.py:57-59)
-            lambda n, p: 0.0 if (not p.requires_grad or p.dim() <= 1 or any(r.search(n) for r in pats)) else weight_decay)
+        subs = list(exclude_from_weight_decay or []) + list(no_weight_decay_name or [])
+
+        def decay(n, p):
+            if not p.requires_grad:
+                return 0.0
+            if one_dim_no_decay and (p.dim() <= 1 or n.endswith(".bias")):
+                return 0.0
+            if any(s_ in n for s_ in subs) or any(r.search(n) for r in pats):
+                return 0.0
+            return weight_decay
+        self.seg_wd = store.segment_values(decay)
         self.seg_lr = store.segment_values(lr_ratio) if lr_ratio is not None else None
 
     def step(self):

@@ -96,7 +96,7 @@ def test_mae_vit_base_shape_step():
     torch.manual_seed(0)
     m = build_model(dict(name="mae_vit_base_patch16", norm_pix_loss=True)).cuda()
     st = ParamStore(m)
-    opt = AdamW(st, lr=1.5e-4, beta2=0.95, weight_decay=0.05)
+    opt = AdamW(st, lr=1.5e-4, beta2=0.95, weight_decay=0.05, one_dim_no_decay=True)       # MAE recipe (optim_factory.py:21-38)
     imgs = torch.randn(8, 3, 224, 224, device="cuda")
     l0 = None
     for it in range(3):

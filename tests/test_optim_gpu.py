@@ -90,7 +90,7 @@ def test_adamw_matches_oracle():
     from passl_b200.optimizer import AdamW
     m, st, ref = _setup(2)
     ratio = {"w1": 0.5, "b1": 0.5}
-    opt = AdamW(st, lr=1.5e-3, beta1=0.9, beta2=0.95, eps=1e-8, weight_decay=0.05, no_decay=["^zero$"],
+    opt = AdamW(st, lr=1.5e-3, beta1=0.9, beta2=0.95, eps=1e-8, weight_decay=0.05, no_decay=["^zero$"], one_dim_no_decay=True,
                 lr_ratio=lambda n, p: ratio.get(n, 1.0))
     wd = {n: (0.0 if (v.dim() <= 1 or n == "zero") else 0.05) for n, v in ref.items()}
     mom = {n: (torch.zeros_like(v), torch.zeros_like(v)) for n, v in ref.items()}

@@ -30,7 +30,12 @@ def test_trainable_ranges_skip_frozen_runs():
 
 def test_weight_decay_tables_zero_frozen_tensors():
     st = ParamStore(_M())
-    assert AdamW(st, lr=1e-3, weight_decay=0.5).seg_wd.tolist() == [0.5, 0.0, 0.5, 0.0, 0.0]       # 1-d `c` undecayed, f1 / f2 frozen
+    # MAE rule: 1-d `c` undecayed; default (MoCo v3 / CLIP recipes): every trainable tensor decays; f1 / f2 frozen either way
+    assert AdamW(st, lr=1e-3, weight_decay=0.5, one_dim_no_decay=True).seg_wd.tolist() == [0.5, 0.0, 0.5, 0.0, 0.0]
+    assert AdamW(st, lr=1e-3, weight_decay=0.5).seg_wd.tolist() == [0.5, 0.0, 0.5, 0.5, 0.0]
+    assert AdamW(st, lr=1e-3, weight_decay=0.5, no_weight_decay_name=["b"]).seg_wd.tolist() == [0.5, 0.0, 0.0, 0.5, 0.0]
+    o = AdamW(st, betas="(0.9, 0.95)", eps=1e-6, use_master_param=True, exp_avg_force_fp32=True)
+    assert (o.beta1, o.beta2, o.eps) == (0.9, 0.95, 1e-6)
     lars = LarsMomentumOptimizer(st, lr=0.1, lars_weight_decay=1e-4, exclude_structured=("^c$",))
     assert [round(v, 6) for v in lars.seg_wd.tolist()] == [1e-4, 0.0, 1e-4, 0.0, 0.0]
     lars = LarsMomentumOptimizer(st, lr=0.1, lars_weight_decay=1e-4)                 # fluid default: nothing excluded but frozen

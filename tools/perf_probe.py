@@ -146,7 +146,7 @@ def probe_vit():
     for B in (128, 512):
         m = build_model(dict(name="mae_vit_base_patch16", norm_pix_loss=True)).cuda()
         st = ParamStore(m)
-        opt = AdamW(st, lr=1.5e-4, beta2=0.95, weight_decay=0.05)
+        opt = AdamW(st, lr=1.5e-4, beta2=0.95, weight_decay=0.05, one_dim_no_decay=True)
         imgs = torch.randn(B, 3, 224, 224, device="cuda")
 
         def step():
