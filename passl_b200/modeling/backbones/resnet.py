@@ -9,6 +9,8 @@ stem max-pool).  Input is the reference's NCHW fp32 image batch; output is NHWC 
 The whole backbone is ONE autograd node: forward chains the fused conv+BN(+ReLU/+residual) units, backward walks them
 in reverse with hand-written dgrad / wgrad / BN-backward kernels and accumulates parameter gradients in place.
 """
+import math
+
 import torch
 import torch.nn as nn
 
@@ -143,6 +145,13 @@ class ResNet(nn.Module):
         if zero_init_residual:          # passl/models/resnet.py:68-73, resnet.py(v110):81-86
             for blk in self.blocks:
                 nn.init.zeros_(blk.conv3.bn.weight)
+        if frozen_stages >= 0:          # resnet.py(v110):90-105 — linear-probe / detection fine-tuning, not the pre-training path
+            raise NotImplementedError("frozen_stages >= 0 (frozen stem / stages with global-statistics BatchNorm) is not built: "
+                                      "the explicit backward here runs through every stage")
+        if pretrained is not None:      # resnet.py(v110):63-72: a .pdparams state dict, optionally wrapped in {'state_dict': ...}
+            from ...utils import checkpoint as C
+            state = C.load_pdparams(pretrained)
+            C.resnet_from_paddle(self, state["state_dict"] if isinstance(state.get("state_dict"), dict) else state)
 
     # -- explicit forward / backward -------------------------------------------------------------------------
     def _run_forward(self, img, training=True, save=True):
@@ -180,3 +189,12 @@ class ResNetsimclr(ResNet):
         kw.setdefault("stem_maxpool", False)
         kw.setdefault("with_pool", True)
         super().__init__(depth=depth, **kw)
+        # every Conv2D of resnetcifar.py carries XavierNormal(fan_in=None, fan_out=0) (resnetcifar.py:137-141,261-264) and the
+        # subclass leaves init_parameters() commented out (resnetsimclr.py:62): std = sqrt(2 / (fan_in + 0)), fan_in = Cin*k*k —
+        # not the fan_out rule of the MoCo backbone
+        with torch.no_grad():
+            self.stem.weight.zero_()
+            self.stem.weight[:, :STEM_K].normal_(0.0, math.sqrt(2.0 / STEM_K))
+            for m in self.modules():
+                if isinstance(m, ConvBN):
+                    m.weight.normal_(0.0, math.sqrt(2.0 / (m.cin * m.k * m.k)))

@@ -20,7 +20,7 @@ from .. import kernels as K
 from .. import kernels_vit as V
 from ..core.param_store import compute_copy, grad_buffer
 from ..nn.layers import Linear
-from .vision_transformer import Block, LayerNorm, PatchEmbed, _linear_bwd
+from .vision_transformer import Block, LayerNorm, PatchEmbed, _check_unbuilt_options, _linear_bwd
 
 
 def _trunc_normal_(t, std=0.02):       # vision_transformer.py(v110):31  TruncatedNormal(std=0.02)
@@ -55,6 +55,7 @@ class CLIPVisionTransformer(_Tower):
                  qkv_bias=True, pre_norm=False, proj=True, patch_bias=True, epsilon=1e-5, **kwargs):
         super().__init__()
         assert proj, "the feature-map output path (proj=None) is outside the CLIP hot path"
+        _check_unbuilt_options(kwargs)
         self.width = self.num_features = width
         self.patch_embed = PatchEmbed(img_size, patch_size, in_chans, width, bias=patch_bias)
         L = self.patch_embed.num_patches

@@ -135,6 +135,21 @@ class _EncoderFn(torch.autograd.Function):
         return None, None, None
 
 
+def _check_unbuilt_options(kwargs):
+    """Constructor keys of the reference ViTs (vision_transformer.py:256-275) whose only built value is the pre-training default:
+    dropout / stochastic depth are 0 on every self-supervised recipe here, so a non-zero request must fail instead of being
+    dropped on the floor.  `norm_layer` is accepted (always LayerNorm with the `epsilon` given)."""
+    inert = {"drop_rate": (0, 0.0), "attn_drop_rate": (0, 0.0), "drop_path_rate": (0, 0.0), "qk_scale": (None,),
+             "representation_size": (None,)}
+    for k, v in kwargs.items():
+        if k == "norm_layer":
+            continue
+        if k not in inert:
+            raise TypeError("unexpected keyword argument %r" % k)
+        if v not in inert[k]:
+            raise NotImplementedError("%s=%r is not built (only %r)" % (k, v, inert[k][0]))
+
+
 class VisionTransformer(nn.Module):
     """passl/models/vision_transformer.py:252-363 (feature extractor: returns the cls token after the final norm)."""
 
@@ -142,6 +157,7 @@ class VisionTransformer(nn.Module):
                  mlp_ratio=4, qkv_bias=False, epsilon=1e-5, learnable_pos=True, **kwargs):
         super().__init__()
         assert class_num <= 0, "the classification head is outside the self-supervised hot path"
+        _check_unbuilt_options(kwargs)
         self.num_features = self.embed_dim = embed_dim
         self.patch_embed = PatchEmbed(img_size, patch_size, in_chans, embed_dim)
         L = self.patch_embed.num_patches

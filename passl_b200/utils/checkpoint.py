@@ -152,7 +152,14 @@ def load_pdparams(path):
     with open(path, "rb") as f:
         obj = pickle.load(f, encoding="latin1")
     obj.pop("StructuredToParameterName@@", None)
-    return {k: np.asarray(v) for k, v in obj.items()}
+    return {k: (load_nested(v) if isinstance(v, dict) else np.asarray(v)) for k, v in obj.items()}
+
+
+def load_nested(obj):
+    """v110 checkpoints wrap the weights as {'state_dict': {...}, 'epoch': n, ...} (hooks/checkpoint_hook.py:22-49)."""
+    obj = dict(obj)
+    obj.pop("StructuredToParameterName@@", None)
+    return {k: (load_nested(v) if isinstance(v, dict) else np.asarray(v)) for k, v in obj.items()}
 
 
 # ---------------------------------------------------------------------------------------------------------------------------------

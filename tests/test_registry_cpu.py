@@ -64,3 +64,34 @@ def test_clip_vit_b16_parameter_count():
                 transformer_heads=8, transformer_layers=12, qkv_bias=True)
     m = build_model(dict(name="CLIPWrapper", architecture=arch, head=dict(name="CLIPHead")))
     assert _count(m) == 149620737
+
+
+def test_conv_init_rules_of_the_two_backbones():
+    """MoCo's ResNet: kaiming-normal fan_out (backbones/resnet.py:75-80); ResNetsimclr: XavierNormal(fan_out=0) = sqrt(2 / fan_in)
+    on every conv, init_parameters() left commented out (resnetcifar.py:137-141, resnetsimclr.py:62)."""
+    import math
+    import torch
+    from passl_b200.modeling.backbones.resnet import ResNet, ResNetsimclr
+    torch.manual_seed(0)
+    a, b = ResNet(depth=50), ResNetsimclr(depth=50)
+    for net, rule in ((a, lambda m: 2.0 / (m.cout * m.k * m.k)), (b, lambda m: 2.0 / (m.cin * m.k * m.k))):
+        for name in ("blocks.0.conv1", "blocks.3.conv2", "blocks.15.conv3", "blocks.3.downsample"):
+            m = net.get_submodule(name)
+            assert abs(m.weight.std().item() / math.sqrt(rule(m)) - 1) < 0.05, (type(net).__name__, name)
+    assert abs(a.stem.weight[:, :147].std().item() / math.sqrt(2.0 / (64 * 49)) - 1) < 0.05
+    assert abs(b.stem.weight[:, :147].std().item() / math.sqrt(2.0 / 147) - 1) < 0.05
+    assert b.stem.weight[:, 147:].abs().sum() == 0 and not b.stem.maxpool and a.stem.maxpool
+
+
+def test_unbuilt_constructor_options_fail_loudly():
+    """Dropout / stochastic depth / frozen stages are not built: asking for them raises instead of being ignored."""
+    import pytest
+    from passl_b200.modeling.backbones.resnet import ResNet
+    from passl_b200.models.vision_transformer import VisionTransformer
+    VisionTransformer(img_size=32, patch_size=8, embed_dim=64, depth=1, num_heads=2, drop_rate=0.0, drop_path_rate=0, norm_layer="nn.LayerNorm")
+    with pytest.raises(NotImplementedError):
+        VisionTransformer(img_size=32, patch_size=8, embed_dim=64, depth=1, num_heads=2, drop_path_rate=0.1)
+    with pytest.raises(TypeError):
+        VisionTransformer(img_size=32, patch_size=8, embed_dim=64, depth=1, num_heads=2, no_such_option=1)
+    with pytest.raises(NotImplementedError):
+        ResNet(depth=50, frozen_stages=1)
