@@ -67,6 +67,8 @@ class MLPBN(nn.Module):
             else:
                 bns.append(BatchNorm1D(d2, relu=False, affine=False) if last_bn else None)
         self.fcs, self.bns = nn.ModuleList(fcs), nn.ModuleList([b for b in bns if b is not None])
+        for fc in self.fcs:                              # paddle nn.Linear default: Xavier-uniform weight (bias_attr=False here)
+            nn.init.xavier_uniform_(fc.weight)
         self.last_bn = last_bn
 
     def _run_forward(self, x, training=True, save=True):
@@ -104,6 +106,19 @@ class MoCoV3ViT(VisionTransformer):
     def __init__(self, stop_grad_conv1=False, **kwargs):
         kwargs.setdefault("learnable_pos", False)
         super().__init__(**kwargs)
+        # weight initialisation of mocov3.py:43-61: q, k, v treated as three separate Xavier-uniform matrices, every other Linear
+        # Xavier-uniform with zero bias (the Block constructor already does that), cls_token ~ N(0, 1e-6), patch projection
+        # uniform with the fan of a [3 p p] -> [D] matrix
+        with torch.no_grad():
+            D = self.embed_dim
+            for blk in self.blocks:
+                val = math.sqrt(6.0 / float(D + D))              # weight.shape[1] // 3 + weight.shape[0] of the [in, 3 out] matrix
+                blk.qkv.weight.uniform_(-val, val)
+            self.cls_token.normal_(std=1e-6)
+            pw = self.patch_embed.proj.weight
+            val = math.sqrt(6.0 / float(pw.shape[1] + D))        # 3 * prod(patch_size) + embed_dim
+            pw.uniform_(-val, val)
+            self.patch_embed.proj.bias.zero_()
         if stop_grad_conv1:                          # mocov3.py:63-65: the patch projection stays at its random initialisation
             self.patch_embed.proj.weight.requires_grad = False
             self.patch_embed.proj.bias.requires_grad = False

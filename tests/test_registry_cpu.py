@@ -95,3 +95,26 @@ def test_unbuilt_constructor_options_fail_loudly():
         VisionTransformer(img_size=32, patch_size=8, embed_dim=64, depth=1, num_heads=2, no_such_option=1)
     with pytest.raises(NotImplementedError):
         ResNet(depth=50, frozen_stages=1)
+
+
+def test_mocov3_vit_initialisation_rules():
+    """mocov3.py:43-61: q / k / v as three Xavier-uniform matrices, cls_token ~ N(0, 1e-6), patch projection uniform with fan
+    3 p^2 + D; the MLP heads keep paddle's Linear default (Xavier-uniform, no bias); the momentum encoder starts as a copy."""
+    import functools
+    import math
+    import torch
+    from passl_b200.models.mocov3 import MoCoV3Pretrain, MoCoV3ViT
+    torch.manual_seed(0)
+    D = 256
+    m = MoCoV3Pretrain(functools.partial(MoCoV3ViT, img_size=64, patch_size=16, embed_dim=D, depth=2, num_heads=4, qkv_bias=True,
+                                         stop_grad_conv1=True), dim=64, mlp_dim=512)
+    v = m.base_encoder.vit
+    for w, bound in ((v.blocks[1].qkv.weight, math.sqrt(6 / (2 * D))), (v.patch_embed.proj.weight, math.sqrt(6 / (3 * 16 * 16 + D))),
+                     (v.blocks[0].fc1.weight, math.sqrt(6 / (D + 4 * D))), (m.predictor.fcs[0].weight, math.sqrt(6 / (64 + 512))),
+                     (m.base_encoder.head.fcs[2].weight, math.sqrt(6 / (512 + 64)))):
+        assert 0.97 * bound < w.abs().max().item() <= bound
+        assert abs(w.std().item() / (bound / math.sqrt(3)) - 1) < 0.05                   # uniform(-b, b): std = b / sqrt(3)
+    assert v.cls_token.std().item() < 3e-6 and v.blocks[0].qkv.bias.abs().sum() == 0 and v.patch_embed.proj.bias.abs().sum() == 0
+    assert not v.patch_embed.proj.weight.requires_grad and not v.pos_embed.requires_grad
+    for a, b in zip(m.base_encoder.parameters(), m.momentum_encoder.parameters()):
+        assert torch.equal(a, b) and not b.requires_grad
