@@ -147,21 +147,33 @@ class MoCoV3Pretrain(nn.Module):
         self.base_encoder = _Encoder(vit_q, MLPBN(3, hidden, mlp_dim, dim))
         self.predictor = MLPBN(2, dim, mlp_dim, dim)
         self.momentum_encoder = _Encoder(vit_k, MLPBN(3, hidden, mlp_dim, dim))
-        for pq, pk in zip(self.base_encoder.parameters(), self.momentum_encoder.parameters()):
-            pk.data.copy_(pq.data)
-            pk.requires_grad = False
+        # The reference wraps Sequential(base_encoder, predictor) in CosineEMA and calls THAT for the keys (mocov3.py:133-134,
+        # 224-225; averaged_model.py:59-61), so its targets also pass through an averaged copy of the predictor.  Literal mode
+        # (reference_ema_quirk) keeps that copy; the default is the textbook momentum encoder of builder_moco.py:36-60.
+        self.momentum_predictor = MLPBN(2, dim, mlp_dim, dim) if reference_ema_quirk else None
+        pairs = [(self.base_encoder, self.momentum_encoder)] + ([(self.predictor, self.momentum_predictor)] if reference_ema_quirk else [])
+        for src, dst in pairs:
+            for pq, pk in zip(src.parameters(), dst.parameters()):
+                pk.data.copy_(pq.data)
+                pk.requires_grad = False
         self.steps = 0
         self._stores = None
 
     def build_param_stores(self):
-        """flat storage: (base_encoder + predictor) trainable, momentum encoder EMA target"""
-        self._trainable = nn.ModuleList([self.base_encoder, self.predictor])
+        """flat storage: (base_encoder + predictor) trainable, momentum encoder (+ its predictor copy in literal mode) EMA target"""
+        # containers only for enumeration: kept out of the module tree so state_dict() lists every tensor once
+        self.__dict__["_trainable"] = nn.ModuleList([self.base_encoder, self.predictor])
         st = ParamStore(self._trainable, with_grad=True)
-        sk = ParamStore(self.momentum_encoder, with_grad=False)
-        # EMA runs over the base_encoder prefix of the trainable buffer: both stores enumerate base_encoder params in the same order
+        self.__dict__["_averaged"] = nn.ModuleList([self.momentum_encoder] + ([self.momentum_predictor] if self.quirk else []))
+        sk = ParamStore(self._averaged, with_grad=False)
+        # EMA runs over a prefix of the trainable buffer: both stores enumerate their tensors in the same order
         self._ema_numel = sk.numel
         self._stores = (st, sk)
         return st, sk
+
+    def _keys(self, x):
+        k = self.momentum_encoder(x)
+        return self.momentum_predictor(k) if self.quirk else k
 
     @torch.no_grad()
     def _update_momentum_encoder(self):
@@ -192,8 +204,8 @@ class MoCoV3Pretrain(nn.Module):
         q2 = self.predictor(self.base_encoder(x2))
         with torch.no_grad():
             self._update_momentum_encoder()
-            k1 = self.momentum_encoder(x1)
-            k2 = self.momentum_encoder(x2)
+            k1 = self._keys(x1)
+            k2 = self._keys(x2)
         return _Add.apply(self.contrastive_loss(q1, k2), self.contrastive_loss(q2, k1))
 
 

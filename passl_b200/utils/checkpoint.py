@@ -310,14 +310,15 @@ def _mlpbn_from_paddle(mlp, state, prefix):
 def mocov3_to_paddle(model, in_chans=3):
     """MoCoV3Pretrain -> reference names: base_encoder.* (ViT with head = projector Sequential), predictor.*, and the EMA copy under
     momentum_encoder.model.0.* (averaged_model.py:36 keeps `self.model = deepcopy(Sequential(base_encoder, predictor))`).  The
-    reference's EMA also carries a predictor copy (model.1.*) that its forward never reads; it is exported as the live predictor."""
+    reference's EMA also averages a predictor copy (model.1.*) and sends the keys through it; in literal mode
+    (reference_ema_quirk) that copy exists here and is exported, otherwise the live predictor stands in for it."""
     out = {}
     for ours, ref in (("base_encoder", "base_encoder."), ("momentum_encoder", "momentum_encoder.model.0.")):
         enc = getattr(model, ours)
         out.update(vit_to_paddle(enc.vit, ref, in_chans))
         _mlpbn_to_paddle(enc.head, ref + "head.", out)
     _mlpbn_to_paddle(model.predictor, "predictor.", out)
-    _mlpbn_to_paddle(model.predictor, "momentum_encoder.model.1.", out)
+    _mlpbn_to_paddle(getattr(model, "momentum_predictor", None) or model.predictor, "momentum_encoder.model.1.", out)
     out["momentum_encoder.steps"] = np.asarray(model.steps, dtype=np.int64)
     return out
 
@@ -328,6 +329,8 @@ def mocov3_from_paddle(model, state, in_chans=3):
         vit_from_paddle(enc.vit, state, ref, in_chans)
         _mlpbn_from_paddle(enc.head, state, ref + "head.")
     _mlpbn_from_paddle(model.predictor, state, "predictor.")
+    if getattr(model, "momentum_predictor", None) is not None:
+        _mlpbn_from_paddle(model.momentum_predictor, state, "momentum_encoder.model.1.")
     model.steps = int(np.asarray(state.get("momentum_encoder.steps", 0)))
 
 

@@ -138,17 +138,20 @@ def test_mocov3_position_table_is_the_reference_one():
         assert got.shape == G["pos_" + t].shape and np.abs(got - G["pos_" + t]).max() < 1e-6
 
 
-def _small_mocov3():
+def _small_mocov3(literal=False):
     import functools
     from passl_b200.models.mocov3 import MoCoV3Pretrain, MoCoV3ViT
     return MoCoV3Pretrain(functools.partial(MoCoV3ViT, img_size=32, patch_size=8, embed_dim=64, depth=1, num_heads=2, qkv_bias=True),
-                          dim=32, mlp_dim=48)
+                          dim=32, mlp_dim=48, reference_ema_quirk=literal)
 
 
-def test_mocov3_roundtrip(tmp_path):
+@pytest.mark.parametrize("literal", [False, True])
+def test_mocov3_roundtrip(tmp_path, literal):
+    """literal: the averaged predictor copy of the reference's CosineEMA(Sequential(encoder, predictor)) is a tensor set of its own
+    (momentum_encoder.model.1.*); otherwise the live predictor is written under those names."""
     from passl_b200.utils import checkpoint as C
     torch.manual_seed(1)
-    a, b = _small_mocov3(), _small_mocov3()
+    a, b = _small_mocov3(literal), _small_mocov3(literal)
     for t in list(a.parameters()) + [bf for bf in a.buffers() if bf.dtype.is_floating_point]:
         t.data.normal_()
     a.steps = 7
@@ -157,6 +160,9 @@ def test_mocov3_roundtrip(tmp_path):
     C.mocov3_from_paddle(b, C.load_pdparams(path))
     sa, sb = a.state_dict(), b.state_dict()
     assert b.steps == 7 and all(torch.equal(sa[k], sb[k]) for k in sa)
+    st = C.load_pdparams(path)
+    same = np.array_equal(st["momentum_encoder.model.1.0.weight"], st["predictor.0.weight"])
+    assert same != literal and ("momentum_predictor.fcs.0.weight" in sa) == literal
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="needs the reference tree (build container only)")

@@ -6,7 +6,15 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def test_mocov3_small_step():
+def ParamStoreNumel(module):
+    """flat-buffer size of a module: every tensor padded to 1024 elements"""
+    return sum((p.numel() + 1023) // 1024 * 1024 for p in module.parameters())
+
+
+@pytest.mark.parametrize("literal", [False, True])
+def test_mocov3_small_step(literal):
+    """literal=True: the reference's CosineEMA(Sequential(base_encoder, predictor)) — keys pass through an averaged predictor copy
+    and the source is weighted by the cosine momentum (mocov3.py:133-134,224-225, averaged_model.py:165-186)."""
     from passl_b200.models.mocov3 import MoCoV3Pretrain, MoCoV3ViT
     from passl_b200.optimizer import AdamW
 
@@ -14,8 +22,9 @@ def test_mocov3_small_step():
         return MoCoV3ViT(img_size=64, patch_size=16, embed_dim=128, depth=2, num_heads=2, qkv_bias=True, epsilon=1e-6,
                          stop_grad_conv1=True)
     torch.manual_seed(0)
-    m = MoCoV3Pretrain(enc, dim=128, mlp_dim=256, T=0.2, max_steps=10).cuda()
+    m = MoCoV3Pretrain(enc, dim=128, mlp_dim=256, T=0.2, max_steps=10, reference_ema_quirk=literal).cuda()
     st, sk = m.build_param_stores()
+    assert sk.numel == (st.numel if literal else ParamStoreNumel(m.base_encoder))
     opt = AdamW(st, lr=1e-3, weight_decay=0.1)
     k0 = sk.master.clone()
     vit = m.base_encoder.vit
@@ -37,6 +46,12 @@ def test_mocov3_small_step():
     assert st.grad.abs().sum().item() > 0
     # the momentum encoder never receives gradients
     assert all(p.grad is None for p in m.momentum_encoder.parameters())
+    if literal:
+        # after step t the averaged copy is avg (1 - mu_t) + src mu_t with mu_t = 0.99 (cos(pi t / max_steps) + 1) / 2: with the
+        # source weighted that heavily the averaged predictor sits within a few per cent of the live one
+        pa, pl = m.momentum_predictor.fcs[0].weight.detach(), m.predictor.fcs[0].weight.detach()
+        assert not torch.equal(pa, pl) and (pa - pl).norm() < 0.2 * (pl - m.predictor.fcs[0].weight.detach().mean()).norm()
+        assert len([k for k in m.state_dict() if k.startswith("_")]) == 0          # enumeration containers stay out of state_dict
     # frozen tensors (fixed sin-cos table, stop_grad_conv1 patch projection: mocov3.py:63-65,91) see neither step nor weight decay
     for t0, t in zip(frozen0, (vit.pos_embed, vit.patch_embed.proj.weight, vit.patch_embed.proj.bias)):
         assert torch.equal(t0, t.detach())
