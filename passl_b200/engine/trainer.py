@@ -123,14 +123,18 @@ class Trainer:
         self.checkpoint_interval = (cfg.get("checkpoint", {}) or {}).get("interval", 0)
 
     # -- checkpoint / resume (rank 0 writes; every rank can load) ----------------------------------------------------------------
-    def save(self, path=None):
+    def save(self, path=None, paddle_format=False):
         if path is None:
             path = os.path.join(self.output_dir or ".", "iter_%d.pd" % self.current_iter)
-        if get_rank() == 0 and path.endswith(".pdparams"):
-            # the reference's own container / parameter names / layouts, see utils/checkpoint.py
-            from ..utils import checkpoint as C
-            os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
-            C.save_pdparams(C.to_paddle_state(self.model), path)
+        if path.endswith(".pdparams") or paddle_format:
+            # the reference's own containers / parameter names / layouts, see utils/checkpoint.py
+            if get_rank() == 0:
+                from ..utils import checkpoint as C
+                os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+                if path.endswith(".pdparams"):
+                    C.save_pdparams(C.to_paddle_state(self.model), path)
+                else:                                    # v110 `epoch_N.pd` (hooks/checkpoint_hook.py:22-49), without optimizer state
+                    C.save_v110_checkpoint(path, self.model, self.current_iter // max(1, self.iters_per_epoch) + 1, self.lr_scheduler)
             return path
         if get_rank() == 0:
             os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
@@ -148,10 +152,18 @@ class Trainer:
             self.model._queue_bf16 = K.cast_bf16(self.model.queue)
 
     def resume(self, path):
-        if path.endswith(".pdparams"):                   # weights only, in the reference's container (pretrained / converted files)
-            from ..utils import checkpoint as C
-            C.load_paddle_state(self.model, C.load_pdparams(path))
+        from ..utils import checkpoint as C
+        if path.endswith(".pdparams") or C.is_paddle_pickle(path):
+            # the reference's containers: a bare .pdparams weights file, or a v110 `epoch_N.pd` training checkpoint
+            # (engine/trainer.py:419-437).  Weights, epoch and LR-schedule position are restored; optimizer moments are not.
+            ck = C.load_v110_checkpoint(path)
+            C.load_paddle_state(self.model, ck["state_dict"])
             self._weights_changed()
+            if ck.get("epoch") is not None:
+                self.current_iter = (ck["epoch"] - 1) * self.iters_per_epoch
+            if self.lr_scheduler is not None and ck.get("lr_scheduler"):
+                self.lr_scheduler.set_state_dict(ck["lr_scheduler"])
+                self.optimizer.set_lr(self.lr_scheduler())
             return
         ck = torch.load(path, map_location=self.device)
         self.model.load_state_dict(ck["state_dict"])

@@ -387,3 +387,37 @@ def to_paddle_state(model):
 def load_paddle_state(model, state):
     """Inverse of to_paddle_state: fills `model` from a reference state dict (e.g. load_pdparams(path))."""
     _dispatch(model)[1](model, state)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# v110 training checkpoints (`epoch_N.pd`, hooks/checkpoint_hook.py:22-49 + engine/trainer.py:419-431): a plain pickle of
+# {'epoch': n, 'state_dict': {name: ndarray}, 'optimizer': {...}, 'lr_scheduler': {'last_epoch': .., 'last_lr': ..}}.
+# The optimizer entry holds Paddle's accumulator tensors under Paddle-internal names; it is neither written nor read here
+# (momentum / Adam moments restart from zero after such a resume — the torch-format checkpoint of engine/trainer.py keeps them).
+# ---------------------------------------------------------------------------------------------------------------------------------
+def is_paddle_pickle(path):
+    """True for the reference's pickle containers, False for this package's torch.save archives (zip: 'PK' magic)."""
+    with open(path, "rb") as f:
+        return f.read(2) != b"PK"
+
+
+def save_v110_checkpoint(path, model, epoch, lr_scheduler=None):
+    obj = {"epoch": int(epoch), "state_dict": {k: np.asarray(v) for k, v in to_paddle_state(model).items()}}
+    if lr_scheduler is not None:
+        obj["lr_scheduler"] = dict(lr_scheduler.state_dict())
+    with open(path, "wb") as f:
+        pickle.dump(obj, f, protocol=2)
+
+
+def load_v110_checkpoint(path):
+    """-> dict with 'state_dict' (always), and 'epoch' / 'lr_scheduler' when the file has them; a bare weights file
+    (.pdparams) comes back as {'state_dict': weights}, like the reference's Trainer.load (engine/trainer.py:433-437)."""
+    obj = load_pdparams(path)
+    if isinstance(obj.get("state_dict"), dict):
+        out = {"state_dict": obj["state_dict"]}
+        if obj.get("epoch") is not None:
+            out["epoch"] = int(np.asarray(obj["epoch"]))
+        if isinstance(obj.get("lr_scheduler"), dict):
+            out["lr_scheduler"] = {k: np.asarray(v).item() for k, v in obj["lr_scheduler"].items() if np.asarray(v).ndim == 0}
+        return out
+    return {"state_dict": obj}

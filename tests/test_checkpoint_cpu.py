@@ -246,3 +246,38 @@ def test_dispatch_covers_every_model_family():
     assert set(C.to_paddle_state(m)) == set(C.mocov3_to_paddle(m))
     with pytest.raises(NotImplementedError):
         C.to_paddle_state(torch.nn.Linear(2, 2))
+
+
+def test_v110_training_checkpoint_container(tmp_path):
+    """`epoch_N.pd` of the v110 trainer: a plain pickle {'epoch', 'state_dict', 'lr_scheduler', ...} (hooks/checkpoint_hook.py:22-49);
+    written without optimizer state, read back with or without the wrapper, and told apart from this package's torch archives."""
+    import pickle
+    from passl_b200.optimizer import build_lr_scheduler
+    from passl_b200.utils import checkpoint as C
+    torch.manual_seed(2)
+    a, b = _small_mocov3(), _small_mocov3()
+    for t in a.parameters():
+        t.data.normal_()
+    sched = build_lr_scheduler(dict(name="CosineAnnealingDecay", learning_rate=0.03, T_max=5), 13)
+    for _ in range(26):
+        sched.step()
+    path = str(tmp_path / "epoch_3.pd")
+    C.save_v110_checkpoint(path, a, 3, sched)
+    raw = pickle.load(open(path, "rb"))
+    assert set(raw) == {"epoch", "state_dict", "lr_scheduler"} and raw["epoch"] == 3 and raw["lr_scheduler"]["last_epoch"] == 26
+    assert isinstance(raw["state_dict"]["base_encoder.blocks.0.attn.qkv.weight"], np.ndarray)
+    assert C.is_paddle_pickle(path)
+    ck = C.load_v110_checkpoint(path)
+    C.load_paddle_state(b, ck["state_dict"])
+    assert ck["epoch"] == 3 and ck["lr_scheduler"]["last_epoch"] == 26
+    assert all(torch.equal(v, b.state_dict()[k]) for k, v in a.state_dict().items())
+    fresh = build_lr_scheduler(dict(name="CosineAnnealingDecay", learning_rate=0.03, T_max=5), 13)
+    fresh.set_state_dict(ck["lr_scheduler"])
+    assert fresh() == sched()
+    # a bare weights file comes back under 'state_dict' too; torch archives are not mistaken for pickles
+    bare = str(tmp_path / "w.pdparams")
+    C.save_pdparams(C.to_paddle_state(a), bare)
+    assert set(C.load_v110_checkpoint(bare)) == {"state_dict"}
+    tpath = str(tmp_path / "iter_2.pd")
+    torch.save({"iter": 2}, tpath)
+    assert not C.is_paddle_pickle(tpath)

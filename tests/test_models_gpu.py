@@ -220,6 +220,15 @@ def test_trainer_pdparams_weights_roundtrip(tmp_path):
     la = tr.model(x1, x2)["loss"].item()
     lb = tr2.model(x1, x2)["loss"].item()
     assert abs(la - lb) <= 1e-3 * abs(la), (la, lb)
+    # the v110 training-checkpoint container (`epoch_N.pd`: pickle with epoch, state_dict, lr_scheduler): position restored too
+    path2 = tr.save(str(tmp_path / "epoch_1.pd"), paddle_format=True)
+    assert C.is_paddle_pickle(path2) and not C.is_paddle_pickle(tr.save(str(tmp_path / "iter_x.pd")))
+    tr3 = T.Trainer(get_config(os.path.join(root, "configs/moco/moco_v2_r50.yaml"), over),
+                    dataloader=T.SyntheticTwoViews(16, 2, torch.device("cuda"), size=64))
+    tr3.resume(path2)
+    assert tr3.current_iter == 2 and tr3.lr_scheduler.last_epoch == tr.lr_scheduler.last_epoch and tr3.optimizer.lr == tr.optimizer.lr
+    tr.model.flush_queue()
+    assert torch.equal(tr3.model.queue, tr.model.queue) and torch.equal(tr3.store.master, tr.store.master)
 
 
 def test_trainer_surface_clip():
