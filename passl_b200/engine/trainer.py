@@ -151,6 +151,16 @@ class Trainer:
             from .. import kernels as K
             self.model._queue_bf16 = K.cast_bf16(self.model.queue)
 
+    def load(self, weight_path):
+        """Weights only (engine/trainer.py:433-444): a .pdparams file, a v110 checkpoint (its 'state_dict' entry) or this package's
+        own checkpoint; iteration, schedule and optimizer state are left as constructed."""
+        from ..utils import checkpoint as C
+        if weight_path.endswith(".pdparams") or C.is_paddle_pickle(weight_path):
+            C.load_paddle_state(self.model, C.load_v110_checkpoint(weight_path)["state_dict"])
+        else:
+            self.model.load_state_dict(torch.load(weight_path, map_location=self.device)["state_dict"])
+        self._weights_changed()
+
     def resume(self, path):
         from ..utils import checkpoint as C
         if path.endswith(".pdparams") or C.is_paddle_pickle(path):

@@ -92,10 +92,13 @@ def get_config(fname, overrides=None, show=False):
     return config
 
 
-def parse_args():
-    """passl/utils/config.py:151-173: -c config, -o overrides, -p profiler options."""
+def parse_args(argv=None):
+    """passl/utils/config.py:151-173: -c config, -o overrides, -p profiler options; --resume / --load of the v110 CLI."""
     parser = argparse.ArgumentParser("passl_b200 train script")
-    parser.add_argument('-c', '--config', type=str, default='configs/config.yaml', help='config file path')
+    parser.add_argument('-c', '--config', '--config-file', dest='config', type=str, default='configs/config.yaml', help='config file path')
     parser.add_argument('-o', '--override', action='append', default=[], help='config options to be overridden')
     parser.add_argument('-p', '--profiler_options', type=str, default=None, help='profiler options "key1=value1;key2=value2"')
-    return parser.parse_args()
+    # passl_v110/utils/options.py:35-49 (training-path subset; --evaluate-only / --export are outside the hot path)
+    parser.add_argument('--resume', type=str, default=None, help='checkpoint to continue from (weights, schedule position, iteration)')
+    parser.add_argument('--load', type=str, default=None, help='weights to start from (.pdparams / epoch_N.pd / this package\'s iter_N.pd)')
+    return parser.parse_args(argv)

@@ -225,6 +225,10 @@ def test_trainer_pdparams_weights_roundtrip(tmp_path):
     assert C.is_paddle_pickle(path2) and not C.is_paddle_pickle(tr.save(str(tmp_path / "iter_x.pd")))
     tr3 = T.Trainer(get_config(os.path.join(root, "configs/moco/moco_v2_r50.yaml"), over),
                     dataloader=T.SyntheticTwoViews(16, 2, torch.device("cuda"), size=64))
+    tr4 = T.Trainer(get_config(os.path.join(root, "configs/moco/moco_v2_r50.yaml"), over),
+                    dataloader=T.SyntheticTwoViews(16, 2, torch.device("cuda"), size=64))
+    tr4.load(path2)                                                        # weights only: position / schedule stay as constructed
+    assert tr4.current_iter == 0 and torch.equal(tr4.store.master, tr.store.master)
     tr3.resume(path2)
     assert tr3.current_iter == 2 and tr3.lr_scheduler.last_epoch == tr.lr_scheduler.last_epoch and tr3.optimizer.lr == tr.optimizer.lr
     tr.model.flush_queue()

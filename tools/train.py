@@ -18,7 +18,12 @@ def main():
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         dist.init_process_group("nccl")
-    Trainer(cfg).train()
+    trainer = Trainer(cfg)
+    if args.resume:                      # tools_v110/train.py:35-40: continue a run, or start from weights only
+        trainer.resume(args.resume)
+    elif args.load:
+        trainer.load(args.load)
+    trainer.train()
 
 
 if __name__ == "__main__":
