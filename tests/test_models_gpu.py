@@ -136,7 +136,7 @@ def test_trainer_surface_moco(tmp_path):
     from passl_b200.engine import trainer as T
     tr = Trainer(cfg, dataloader=T.SyntheticTwoViews(16, 4, torch.device("cuda"), size=64))
     out = tr.train()
-    assert np.isfinite(float(out["loss"])) and "acc1" in out and "acc5" in out
+    assert np.isfinite(float(out["loss"].detach())) and "acc1" in out and "acc5" in out
     tr.model.flush_queue()
     assert int(tr.model.queue_ptr.item()) == (4 * 16) % 1024
 
@@ -184,7 +184,7 @@ def test_trainer_surface_simclr_recipe():
     assert int((tr.optimizer.seg_wd == 0).sum()) == 0
     w0 = tr.store.master.clone()
     out = tr.train()
-    assert np.isfinite(float(out["loss"])) and torch.isfinite(tr.store.master).all()
+    assert np.isfinite(float(out["loss"].detach())) and torch.isfinite(tr.store.master).all()
     assert abs(tr.optimizer.lr - 0.75 * peak) < 1e-9         # three scheduler steps into a four-step warm-up
     assert not torch.equal(w0, tr.store.master)
 
@@ -248,6 +248,6 @@ def test_trainer_surface_clip():
                       a + "vocab_size=1000", "dataloader.train.sampler.batch_size=16", "total_iters=3", "log_config.interval=100"])
     tr = Trainer(cfg)
     out = tr.train()
-    assert np.isfinite(float(out["loss"])) and np.isfinite(float(out["img_loss"])) and np.isfinite(float(out["text_loss"]))
-    assert 0 < float(out["loss"]) < 2 * np.log(16) + 2.0
+    assert np.isfinite(float(out["loss"].detach())) and np.isfinite(float(out["img_loss"])) and np.isfinite(float(out["text_loss"]))
+    assert 0 < float(out["loss"].detach()) < 2 * np.log(16) + 2.0
     assert abs(tr.model.model.logit_scale.item()) <= 4.6 + 1e-6
