@@ -16,7 +16,7 @@ import torch.nn as nn
 
 from ... import kernels as K
 from ...core.streams import join
-from ...core.param_store import compute_copy, grad_buffer
+from ...core.param_store import grad_buffer
 from ...nn.layers import BatchNormState, ConvBN, _kaiming_normal_fan_out
 from ..registry import BACKBONES
 

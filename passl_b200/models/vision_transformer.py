@@ -7,8 +7,6 @@ Backward is hand-written: dgrad GEMMs (GELU' fused in the fc2-dgrad epilogue), w
 gradient buffer, attention backward with recomputed probabilities, LayerNorm backward with the residual-gradient add fused.
 Dropout / drop-path rates are 0 in every pretrain config of the hot path and are not implemented.
 """
-import math
-
 import torch
 import torch.nn as nn
 

@@ -1,5 +1,6 @@
 """Perf experiment: K-small write-heavy GEMM (layer1 conv3 shape) with parts of the epilogue disabled (PASSL_B200_EPI_DEBUG)."""
-import os, sys, time
+import os
+import sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from passl_b200 import kernels as K
