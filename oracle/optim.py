@@ -11,10 +11,10 @@ restated here and anchored on the reference's call sites:
                              configs/simclr/simclr_r50_IM.yaml:116-120 (lars_coeff 0.001, lars_weight_decay, exclude list)
   adamw(p, g, m, v)          _C_ops.adamw called by passl/optimizer/adamw.py:101-137 with the attributes epsilon, beta1, beta2,
                              with_decay, coeff = weight_decay, lr_ratio = 1.0, and beta^step passed in as beta1_pow / beta2_pow
-  momentum_lars_v25          the v2.5 tree's own Python rule, passl/optimizer/momentum_lars.py:96-114 (not the SimCLR-v110 one)
 
 PARITY UNPINNED for the three C++ rules: no golden vector can be produced without PaddlePaddle; the pin is the published formula
-plus the call sites above.  momentum_lars_v25 follows reference Python line by line.
+plus the call sites above.  (The v2.5 tree's own Python LARS, passl/optimizer/momentum_lars.py:96-114, is a different rule —
+trust ratio on ||g + wd p|| — and is not what the SimCLR recipe of the v110 tree runs; it is not built.)
 """
 import torch
 
@@ -43,14 +43,3 @@ def adamw(p, g, m, v, lr, beta1, beta2, eps, wd, step, lr_ratio=1.0):
     v = beta2 * v + (1 - beta2) * g * g
     denom = v.sqrt() / (1 - beta2 ** step) ** 0.5 + eps
     return p - lr / (1 - beta1 ** step) * m / denom, m, v
-
-
-def momentum_lars_v25(p, g, exp_avg, lr, mu, wd, trust=0.001):
-    """passl/optimizer/momentum_lars.py:96-111: tensors with ndim > 1 get g <- (g + wd p) * trust ||p|| / ||g + wd p||."""
-    if p.ndim > 1:
-        g = g + wd * p
-        pn, un = p.norm(), g.norm()
-        q = trust * pn / un if (pn > 0 and un > 0) else torch.ones(())
-        g = g * q
-    exp_avg = exp_avg * mu + g
-    return p - lr * exp_avg, exp_avg
