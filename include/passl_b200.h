@@ -321,6 +321,29 @@ int passl_b200_peer_reduce_scatter_f32(const float* grad_all, const void* const*
                                        long long shard_elems, int rank, int world, unsigned epoch, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Image input stage: the per-view image ops right before the backbone, on decoded uint8 HWC RGB images that are
+ * already in device memory.  `src` packs the images back to back; image n starts at byte src_off[n] and is src_h[n] x src_w[n].
+ * An item m is one output view: item_img[m] names its source image, item_box[4m..4m+3] = (top, left, crop_h, crop_w) is the box the
+ * host drew (RandomResizedCrop.get_params, passl_v110/datasets/preprocess/transforms.py:517-557).  All index arrays are device int32.
+ *   resized_crop_u8     RandomResizedCrop's image op = PIL crop + Image.resize((S, S), BILINEAR | BICUBIC) (configs/simclr/
+ *                       simclr_r50_IM.yaml:35-39): Pillow's two-pass 8-bit resampler (libImaging/Resample.c) with its fixed-point
+ *                       taps, bit-exact.  dst uint8 [items, S, S, 3].  interpolation 0 bilinear, 1 bicubic.  kmax >=
+ *                       resample_kmax(largest crop side, S, interpolation); max_crop_h >= the largest crop_h.  After the call
+ *                       the first int of the workspace is a status word: bit 0 = a box outside its image, bit 1 = kmax too small
+ *                       (the affected items are written as zeros).
+ *   views_finalize_f32  RandomGrayscale (img.convert('L') replicated, transforms.py:150-170) where gray[m], RandomHorizontalFlip
+ *                       where flip[m], Transpose HWC->CHW and NormalizeImage (x * scale - mean) / std evaluated in double and
+ *                       stored as float32 (transforms.py:462-467).  out fp32 [items, 3, S, S]; mean3 / std3 are HOST float[3].
+ * ------------------------------------------------------------------------------------------------------------- */
+int passl_b200_resample_kmax(int max_crop, int out_size, int interpolation);
+long long passl_b200_resized_crop_workspace_bytes(int items, int out_size, int max_crop_h, int kmax);
+int passl_b200_resized_crop_u8(const void* src, const long long* src_off, const int* src_h, const int* src_w, const int* item_img,
+                               const int* item_box, void* dst, void* workspace, long long workspace_bytes, int items, int out_size,
+                               int max_crop_h, int kmax, int interpolation, void* stream);
+int passl_b200_views_finalize_f32(const void* img, const int* gray, const int* flip, float* out, int items, int size, double scale,
+                                  const float* mean3, const float* std3, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Developer probe (not a reference entry point): one tcgen05.mma over a row-shifted view of a SWIZZLE_128B tile, used by
  * tests/test_umma_probe_gpu.py to pin the shared-memory descriptor semantics (start address not 1024-aligned, SBO != 1024,
  * base_offset bits) that the halo-tile convolution kernels rely on.  A bf16 [256,64], B bf16 [64,64], out fp32 [128,64].

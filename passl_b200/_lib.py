@@ -87,6 +87,10 @@ SIGNATURES = {
     "passl_b200_peer_allgather": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, ctypes.c_uint, c_void_p]),
     "passl_b200_peer_reduce_scatter_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, ctypes.c_uint, c_void_p]),
     "passl_b200_umma_probe": (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p]),
+    "passl_b200_resample_kmax": (c_int, [c_int] * 3),
+    "passl_b200_resized_crop_workspace_bytes": (c_ll, [c_int] * 4),
+    "passl_b200_resized_crop_u8": (c_int, [c_void_p] * 8 + [c_ll] + [c_int] * 5 + [c_void_p]),
+    "passl_b200_views_finalize_f32": (c_int, [c_void_p] * 4 + [c_int] * 2 + [ctypes.c_double] + [c_void_p] * 3),
     "passl_b200_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "passl_b200_attention_bwd": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "passl_b200_layernorm_fwd": (c_int, [c_void_p] * 6 + [c_ll, c_int, c_float, c_void_p]),

@@ -1,0 +1,180 @@
+// Per-element arithmetic of the image input stage (input_stage.cu), written so that the SAME source also compiles as plain host C++:
+// tests/test_input_stage_host_cpu.py builds it with g++ (-ffp-contract=off) and checks it against Pillow, which validates the
+// arithmetic and indexing of the kernels' bodies without a GPU.  On the device every double operation is an explicitly rounded
+// intrinsic (never contracted into FMA), so both builds produce the integers Pillow's libImaging/Resample.c produces.
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define PB_HD __host__ __device__ __forceinline__
+#else
+#define PB_HD inline
+#endif
+
+namespace pb {
+namespace istage {
+
+constexpr int kPrecisionBits = 32 - 8 - 2;
+
+#if defined(__CUDA_ARCH__)
+PB_HD double rn_add(double a, double b) { return __dadd_rn(a, b); }
+PB_HD double rn_sub(double a, double b) { return __dsub_rn(a, b); }
+PB_HD double rn_mul(double a, double b) { return __dmul_rn(a, b); }
+PB_HD double rn_div(double a, double b) { return __ddiv_rn(a, b); }
+PB_HD int trunc_int(double a) { return __double2int_rz(a); }
+PB_HD float to_float(double a) { return __double2float_rn(a); }
+#else
+PB_HD double rn_add(double a, double b) { return a + b; }
+PB_HD double rn_sub(double a, double b) { return a - b; }
+PB_HD double rn_mul(double a, double b) { return a * b; }
+PB_HD double rn_div(double a, double b) { return a / b; }
+PB_HD int trunc_int(double a) { return (int)a; }
+PB_HD float to_float(double a) { return (float)a; }
+#endif
+
+struct ItemGeom {
+  int top, left, ch, cw;      // crop box inside the source image
+  int src_h, src_w;
+  long long src_off;          // byte offset of the image in the packed source buffer
+};
+
+PB_HD ItemGeom item_geom(const long long* src_off, const int* src_h, const int* src_w, const int* item_img, const int* item_box,
+                         int m) {
+  ItemGeom g;
+  const int n = item_img[m];
+  g.src_off = src_off[n];
+  g.src_h = src_h[n];
+  g.src_w = src_w[n];
+  g.top = item_box[4 * m + 0];
+  g.left = item_box[4 * m + 1];
+  g.ch = item_box[4 * m + 2];
+  g.cw = item_box[4 * m + 3];
+  return g;
+}
+
+PB_HD bool geom_ok(const ItemGeom& g) {
+  return g.ch > 0 && g.cw > 0 && g.top >= 0 && g.left >= 0 && g.top + g.ch <= g.src_h && g.left + g.cw <= g.src_w;
+}
+
+// filter(x): bilinear triangle (support 1) or Pillow's bicubic with a = -0.5 (support 2); every operation rounded on its own
+PB_HD double resample_filter(double x, int bicubic) {
+  if (x < 0.0) x = -x;
+  if (!bicubic) return x < 1.0 ? rn_sub(1.0, x) : 0.0;
+  if (x < 1.0) {                                                  // ((a + 2) x - (a + 3)) x x + 1
+    double t = rn_sub(rn_mul(1.5, x), 2.5);
+    t = rn_mul(rn_mul(t, x), x);
+    return rn_add(t, 1.0);
+  }
+  if (x < 2.0) {                                                  // (((x - 5) x + 8) x - 4) a
+    double t = rn_add(rn_mul(rn_sub(x, 5.0), x), 8.0);
+    t = rn_sub(rn_mul(t, x), 4.0);
+    return rn_mul(t, -0.5);
+  }
+  return 0.0;
+}
+
+// Resample.c precompute_coeffs + normalize_coeffs_8bpc for ONE output index xx of a box (0, in_size) -> S.
+// b[0] = first source index, b[1] = tap count, k[0..kmax) fixed-point taps.  Returns 0, or 2 when kmax is too small.
+PB_HD int resample_window(int in_size, int S, int xx, int bicubic, int kmax, int* b, int* k) {
+  const double scale = rn_div((double)in_size, (double)S);
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = rn_mul(bicubic ? 2.0 : 1.0, filterscale);
+  const int ksize = (int)ceil(support) * 2 + 1;
+  if (ksize > kmax) {
+    b[0] = 0;
+    b[1] = 0;
+    return 2;
+  }
+  const double center = rn_mul((double)xx + 0.5, scale);           // in0 = 0
+  const double ss = rn_div(1.0, filterscale);
+  int xmin = trunc_int(rn_add(rn_sub(center, support), 0.5));
+  if (xmin < 0) xmin = 0;
+  int xmax = trunc_int(rn_add(rn_add(center, support), 0.5));
+  if (xmax > in_size) xmax = in_size;
+  xmax -= xmin;
+  double ww = 0.0;
+  for (int x = 0; x < xmax; ++x) {
+    const double arg = rn_mul(rn_add(rn_sub((double)(x + xmin), center), 0.5), ss);
+    ww = rn_add(ww, resample_filter(arg, bicubic));
+  }
+  for (int x = 0; x < xmax; ++x) {                                 // recomputed instead of stored: no double scratch needed
+    const double arg = rn_mul(rn_add(rn_sub((double)(x + xmin), center), 0.5), ss);
+    double w = resample_filter(arg, bicubic);
+    if (ww != 0.0) w = rn_div(w, ww);
+    const double scaled = rn_mul(w, (double)(1 << kPrecisionBits));
+    k[x] = trunc_int(w < 0.0 ? rn_add(-0.5, scaled) : rn_add(0.5, scaled));
+  }
+  for (int x = xmax; x < kmax; ++x) k[x] = 0;
+  b[0] = xmin;
+  b[1] = xmax;
+  return 0;
+}
+
+PB_HD unsigned char clip8(int acc) {
+  const int v = acc >> kPrecisionBits;
+  return (unsigned char)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+// table layout shared by the three resample kernels: bounds [items][2 axes][S][2], taps [items][2][S][kmax]
+PB_HD long long window_index(int m, int axis, int S, int xx) { return (long long)(m * 2 + axis) * S + xx; }
+
+// horizontal pass, one output pixel: tmp[m][y][xx][0..3) from row (top + y) of the crop
+PB_HD void h_pass_pixel(const unsigned char* src, const ItemGeom& g, const int* bounds, const int* taps, unsigned char* tmp, int m,
+                        int y, int xx, int S, int kmax, int max_crop_h) {
+  const int* b = bounds + window_index(m, 0, S, xx) * 2;
+  const int* k = taps + window_index(m, 0, S, xx) * kmax;
+  const int x0 = b[0], cnt = b[1];
+  const unsigned char* row = src + g.src_off + ((long long)(g.top + y) * g.src_w + g.left + x0) * 3;
+  int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+  for (int x = 0; x < cnt; ++x) {
+    const int w = k[x];
+    a0 += (int)row[3 * x + 0] * w;
+    a1 += (int)row[3 * x + 1] * w;
+    a2 += (int)row[3 * x + 2] * w;
+  }
+  unsigned char* o = tmp + (((long long)m * max_crop_h + y) * S + xx) * 3;
+  o[0] = clip8(a0);
+  o[1] = clip8(a1);
+  o[2] = clip8(a2);
+}
+
+// vertical pass, one output pixel: dst[m][yy][x][0..3) from column x of the intermediate
+PB_HD void v_pass_pixel(const unsigned char* tmp, const int* bounds, const int* taps, unsigned char* dst, int m, int yy, int x, int S,
+                        int kmax, int max_crop_h) {
+  const int* b = bounds + window_index(m, 1, S, yy) * 2;
+  const int* k = taps + window_index(m, 1, S, yy) * kmax;
+  const int y0 = b[0], cnt = b[1];
+  const unsigned char* col = tmp + (((long long)m * max_crop_h + y0) * S + x) * 3;
+  int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+  for (int y = 0; y < cnt; ++y) {
+    const int w = k[y];
+    const unsigned char* p = col + (long long)y * S * 3;
+    a0 += (int)p[0] * w;
+    a1 += (int)p[1] * w;
+    a2 += (int)p[2] * w;
+  }
+  unsigned char* o = dst + (((long long)m * S + yy) * S + x) * 3;
+  o[0] = clip8(a0);
+  o[1] = clip8(a1);
+  o[2] = clip8(a2);
+}
+
+// NormalizeImage table entry: float32((v * scale - mean) / std) with the arithmetic in double (transforms.py:462-467)
+PB_HD float normalize_entry(int v, double scale, float mean, float stdv) {
+  return to_float(rn_div(rn_sub(rn_mul((double)v, scale), (double)mean), (double)stdv));
+}
+
+// finalize, one output pixel: grayscale (Convert.c rgb2l) where gray, mirrored source column where flip, CHW planes from `lut`
+PB_HD void finalize_pixel(const unsigned char* img, const float* lut, float* out, int m, int y, int x, int S, int gray, int flip) {
+  const int xs = flip ? S - 1 - x : x;
+  const unsigned char* p = img + (((long long)m * S + y) * S + xs) * 3;
+  int r = p[0], g = p[1], b = p[2];
+  if (gray) r = g = b = (r * 19595 + g * 38470 + b * 7471 + 0x8000) >> 16;
+  float* o = out + (long long)m * 3 * S * S + (long long)y * S + x;
+  o[0] = lut[r];
+  o[(long long)S * S] = lut[256 + g];
+  o[2LL * S * S] = lut[512 + b];
+}
+
+}  // namespace istage
+}  // namespace pb

@@ -1,0 +1,153 @@
+"""Image input stage on the device: decoded uint8 HWC images in HBM -> two augmented, normalised NCHW views.
+
+Reference (CPU workers, per sample; passl_v110/datasets/imagenet.py:46-63 with configs/simclr/simclr_r50_IM.yaml:35-83):
+`sample1 = transform(sample); sample2 = transform(sample)` with transform = RandomResizedCrop, then per view
+`RandomApply(ColorJitter) -> RandomGrayscale -> RandomApply(GaussianBlur) -> RandomHorizontalFlip -> Transpose -> NormalizeImage`.
+
+Built here: the crop-box draw on the host (same algorithm and `random` call order as transforms.py:517-557), crop + Pillow-exact
+resize, grayscale, flip, CHW + normalise on the GPU (csrc/input_stage.cu).  ColorJitter and GaussianBlur are not built: the
+stage is the geometric + photometric-normalisation part of the recipe, and because those two ops also draw random numbers, a
+run of this stage does not consume the `random` stream the way a full reference worker would.
+Decisions are drawn per sample in the order: box of view 1, box of view 2, grayscale 1, flip 1, grayscale 2, flip 2.
+"""
+import math
+import random
+
+import torch
+
+from .. import _lib
+
+INTERPOLATION = {"bilinear": 0, "bicubic": 1}
+
+
+def random_resized_crop_params(width, height, scale=(0.08, 1.0), ratio=(3. / 4., 4. / 3.), rng=random):
+    """(top, left, crop_h, crop_w) like RandomResizedCrop.get_params (transforms.py:517-557): up to ten draws of an area fraction
+    and a log-uniform aspect ratio, first box that fits placed uniformly; else the largest centred box within the ratio range."""
+    log_lo, log_hi = math.log(ratio[0]), math.log(ratio[1])
+    for _ in range(10):
+        target = rng.uniform(scale[0], scale[1]) * (width * height)
+        aspect = math.exp(rng.uniform(log_lo, log_hi))
+        cw = int(round(math.sqrt(target * aspect)))
+        ch = int(round(math.sqrt(target / aspect)))
+        if cw <= width and ch <= height:
+            top = rng.randint(0, height - ch)
+            left = rng.randint(0, width - cw)
+            return top, left, ch, cw
+    whole = width / height
+    if whole < min(ratio):
+        cw, ch = width, int(round(width / min(ratio)))
+    elif whole > max(ratio):
+        cw, ch = int(round(height * max(ratio))), height
+    else:
+        cw, ch = width, height
+    return (height - ch) // 2, (width - cw) // 2, ch, cw
+
+
+class ImageBatch:
+    """Decoded RGB images of different sizes packed back to back in one uint8 device buffer."""
+
+    def __init__(self, images, device=None):
+        """images: sequence of uint8 [H, W, 3] tensors / arrays (host or device)."""
+        ts = [torch.as_tensor(im) for im in images]
+        for t in ts:
+            if t.dtype != torch.uint8 or t.dim() != 3 or t.shape[2] != 3:
+                raise ValueError("images must be uint8 [H, W, 3], got %s %s" % (t.dtype, tuple(t.shape)))
+        device = device or torch.device("cuda", torch.cuda.current_device())
+        self.heights = [int(t.shape[0]) for t in ts]
+        self.widths = [int(t.shape[1]) for t in ts]
+        sizes = [h * w * 3 for h, w in zip(self.heights, self.widths)]
+        offs = [0]
+        for s in sizes[:-1]:
+            offs.append(offs[-1] + s)
+        self.data = torch.cat([t.reshape(-1).to(device, non_blocking=True) for t in ts])
+        self.src_off = torch.tensor(offs, dtype=torch.int64, device=device)
+        self.src_h = torch.tensor(self.heights, dtype=torch.int32, device=device)
+        self.src_w = torch.tensor(self.widths, dtype=torch.int32, device=device)
+        self.device = device
+
+    def __len__(self):
+        return len(self.heights)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def resized_crop_u8(batch, item_img, item_box, size=224, interpolation="bilinear", check=True):
+    """Crop + PIL-exact resize of `len(item_img)` views.  item_img: source index per view, item_box: (top, left, h, w) per view
+    (host lists).  -> uint8 [items, size, size, 3] on the device."""
+    if not batch.data.is_cuda:
+        raise _lib.PasslB200Error("passl_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    lib = _lib.load()
+    items = len(item_img)
+    for n, (t, l, h, w) in zip(item_img, item_box):
+        if not (0 <= n < len(batch)) or h <= 0 or w <= 0 or t < 0 or l < 0 or t + h > batch.heights[n] or l + w > batch.widths[n]:
+            raise ValueError("crop box (top=%d, left=%d, h=%d, w=%d) does not lie inside image %d" % (t, l, h, w, n))
+    inter = INTERPOLATION[interpolation]
+    max_h = max(b[2] for b in item_box)
+    kmax = lib.passl_b200_resample_kmax(max(max(b[2], b[3]) for b in item_box), size, inter)
+    dev = batch.device
+    d_img = torch.tensor(list(item_img), dtype=torch.int32, device=dev)
+    d_box = torch.tensor([list(b) for b in item_box], dtype=torch.int32, device=dev).reshape(-1)
+    nbytes = lib.passl_b200_resized_crop_workspace_bytes(items, size, max_h, kmax)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    out = torch.empty((items, size, size, 3), dtype=torch.uint8, device=dev)
+    _lib.check(lib.passl_b200_resized_crop_u8(batch.data.data_ptr(), batch.src_off.data_ptr(), batch.src_h.data_ptr(),
+                                              batch.src_w.data_ptr(), d_img.data_ptr(), d_box.data_ptr(), out.data_ptr(),
+                                              ws.data_ptr(), nbytes, items, size, max_h, kmax, inter, _stream()), "resized_crop_u8")
+    if check:                                            # one int back from the device: bad boxes / short tap table
+        status = int(ws[:4].view(torch.int32).item())
+        if status:
+            raise _lib.PasslB200Error("resized_crop_u8: device status %d (1 = box outside its image, 2 = kmax too small)" % status)
+    return out
+
+
+def views_finalize(views_u8, gray, flip, scale=1.0 / 255.0, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
+    """uint8 [items, S, S, 3] -> fp32 [items, 3, S, S]: grayscale where gray[m], mirror where flip[m], (x * scale - mean) / std."""
+    import ctypes
+    if not views_u8.is_cuda:
+        raise _lib.PasslB200Error("passl_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    lib = _lib.load()
+    items, S = views_u8.shape[0], views_u8.shape[1]
+    assert views_u8.dtype == torch.uint8 and views_u8.shape == (items, S, S, 3) and views_u8.is_contiguous()
+    dev = views_u8.device
+    d_gray = torch.tensor([int(bool(g)) for g in gray], dtype=torch.int32, device=dev)
+    d_flip = torch.tensor([int(bool(f)) for f in flip], dtype=torch.int32, device=dev)
+    assert d_gray.numel() == items and d_flip.numel() == items
+    out = torch.empty((items, 3, S, S), dtype=torch.float32, device=dev)
+    m3 = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    s3 = (ctypes.c_float * 3)(*[float(v) for v in std])
+    _lib.check(lib.passl_b200_views_finalize_f32(views_u8.data_ptr(), d_gray.data_ptr(), d_flip.data_ptr(), out.data_ptr(), items, S,
+                                                 float(scale), ctypes.cast(m3, ctypes.c_void_p), ctypes.cast(s3, ctypes.c_void_p),
+                                                 _stream()), "views_finalize_f32")
+    return out
+
+
+class TwoViewInputStage:
+    """`(view_1, view_2) = stage(images)`: both fp32 [N, 3, size, size] on the device, ready for MoCo / SimCLR `train_iter`."""
+
+    def __init__(self, size=224, scale=(0.08, 1.0), ratio=(3. / 4., 4. / 3.), interpolation="bilinear", gray_p=0.2, flip_p=0.5,
+                 norm_scale=1.0 / 255.0, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225), rng=random):
+        self.size, self.scale, self.ratio, self.interpolation = size, tuple(scale), tuple(ratio), interpolation
+        self.gray_p, self.flip_p, self.norm_scale, self.mean, self.std, self.rng = gray_p, flip_p, norm_scale, mean, std, rng
+
+    def draw(self, batch):
+        """Host-side random decisions for one batch -> (item_img, item_box, gray, flip); views of sample n are items n and N + n."""
+        N = len(batch)
+        box1, box2, g1, g2, f1, f2 = [], [], [], [], [], []
+        for n in range(N):
+            box1.append(random_resized_crop_params(batch.widths[n], batch.heights[n], self.scale, self.ratio, self.rng))
+            box2.append(random_resized_crop_params(batch.widths[n], batch.heights[n], self.scale, self.ratio, self.rng))
+            g1.append(self.rng.random() < self.gray_p)
+            f1.append(self.rng.random() < self.flip_p)
+            g2.append(self.rng.random() < self.gray_p)
+            f2.append(self.rng.random() < self.flip_p)
+        return list(range(N)) * 2, box1 + box2, g1 + g2, f1 + f2
+
+    def __call__(self, images):
+        batch = images if isinstance(images, ImageBatch) else ImageBatch(images)
+        item_img, item_box, gray, flip = self.draw(batch)
+        u8 = resized_crop_u8(batch, item_img, item_box, self.size, self.interpolation)
+        out = views_finalize(u8, gray, flip, self.norm_scale, self.mean, self.std)
+        N = len(batch)
+        return out[:N], out[N:]

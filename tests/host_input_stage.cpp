@@ -1,0 +1,57 @@
+// Host build of the image input stage's per-element bodies (passl_b200/csrc/input_stage_core.h) — TEST INFRASTRUCTURE.
+// The loops below stand where the CUDA kernels' thread indexing stands (input_stage.cu); everything inside them is the shared
+// source.  Built by tests/test_input_stage_host_cpu.py with g++ -O2 -ffp-contract=off and compared with Pillow / the oracle.
+#include <vector>
+
+#include "../passl_b200/csrc/input_stage_core.h"
+
+using namespace pb::istage;
+
+extern "C" int host_resized_crop_u8(const unsigned char* src, const long long* src_off, const int* src_h, const int* src_w,
+                                    const int* item_img, const int* item_box, unsigned char* dst, int items, int S, int max_crop_h,
+                                    int kmax, int bicubic) {
+  std::vector<int> bounds((size_t)items * 2 * S * 2), taps((size_t)items * 2 * S * kmax);
+  std::vector<unsigned char> tmp((size_t)items * max_crop_h * S * 3);
+  int status = 0;
+  for (int m = 0; m < items; ++m) {
+    const ItemGeom g = item_geom(src_off, src_h, src_w, item_img, item_box, m);
+    for (int axis = 0; axis < 2; ++axis)
+      for (int xx = 0; xx < S; ++xx) {
+        int* b = bounds.data() + window_index(m, axis, S, xx) * 2;
+        int* k = taps.data() + window_index(m, axis, S, xx) * kmax;
+        if (!geom_ok(g)) { b[0] = b[1] = 0; status |= 1; continue; }
+        status |= resample_window(axis == 0 ? g.cw : g.ch, S, xx, bicubic, kmax, b, k);
+      }
+  }
+  for (int m = 0; m < items; ++m) {
+    const ItemGeom g = item_geom(src_off, src_h, src_w, item_img, item_box, m);
+    for (int y = 0; y < max_crop_h; ++y)
+      for (int xx = 0; xx < S; ++xx) {
+        if (!geom_ok(g) || y >= g.ch) continue;
+        h_pass_pixel(src, g, bounds.data(), taps.data(), tmp.data(), m, y, xx, S, kmax, max_crop_h);
+      }
+  }
+  for (int m = 0; m < items; ++m) {
+    const ItemGeom g = item_geom(src_off, src_h, src_w, item_img, item_box, m);
+    for (int yy = 0; yy < S; ++yy)
+      for (int x = 0; x < S; ++x) {
+        const int* b = bounds.data() + window_index(m, 1, S, yy) * 2;
+        if (!geom_ok(g) || b[1] == 0) {
+          unsigned char* o = dst + (((long long)m * S + yy) * S + x) * 3;
+          o[0] = o[1] = o[2] = 0;
+          continue;
+        }
+        v_pass_pixel(tmp.data(), bounds.data(), taps.data(), dst, m, yy, x, S, kmax, max_crop_h);
+      }
+  }
+  return status;
+}
+
+extern "C" void host_views_finalize_f32(const unsigned char* img, const int* gray, const int* flip, float* out, int items, int S,
+                                        double scale, const float* mean3, const float* std3) {
+  float lut[3 * 256];
+  for (int i = 0; i < 3 * 256; ++i) lut[i] = normalize_entry(i & 255, scale, mean3[i >> 8], std3[i >> 8]);
+  for (int m = 0; m < items; ++m)
+    for (int y = 0; y < S; ++y)
+      for (int x = 0; x < S; ++x) finalize_pixel(img, lut, out, m, y, x, S, gray[m], flip[m]);
+}

@@ -1,0 +1,124 @@
+"""The per-element bodies of the CUDA input-stage kernels (passl_b200/csrc/input_stage_core.h) compiled as host C++ and run here
+without a GPU: ragged source images, several views per image, bilinear and bicubic, against Pillow itself (bit-exact uint8) and the
+oracle's float stage (bit-exact float32).  The CUDA kernels add only the thread-index decomposition on top of this source; the
+`-m gpu` test (tests/test_zz_input_stage_gpu.py) runs the same cases through the C ABI."""
+import ctypes
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle.input_stage as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+Image = pytest.importorskip("PIL.Image")
+
+
+def make_cases(seed=0):
+    """-> dict(src, src_off, src_h, src_w, item_img, item_box, images): three ragged images, nine views incl. the edge boxes."""
+    rng = np.random.RandomState(seed)
+    shapes = [(375, 500), (64, 48), (300, 224)]
+    images = [rng.randint(0, 256, size=(h, w, 3)).astype(np.uint8) for h, w in shapes]
+    images[0][:180] = (images[0][:180] // 128) * 255                               # hard edges (bicubic over/undershoot -> clip)
+    off = np.cumsum([0] + [im.size for im in images[:-1]]).astype(np.int64)
+    items = [(0, (10, 20, 200, 300)), (0, (0, 0, 375, 500)), (0, (300, 400, 75, 100)), (0, (100, 100, 1, 1)),
+             (1, (0, 0, 64, 48)), (1, (5, 7, 30, 20)), (2, (0, 0, 300, 224)), (2, (38, 0, 224, 224)), (2, (299, 223, 1, 1))]
+    return dict(src=np.concatenate([im.reshape(-1) for im in images]), src_off=off,
+                src_h=np.array([s[0] for s in shapes], dtype=np.int32), src_w=np.array([s[1] for s in shapes], dtype=np.int32),
+                item_img=np.array([i for i, _ in items], dtype=np.int32), item_box=np.array([b for _, b in items], dtype=np.int32),
+                images=images)
+
+
+def kmax_for(max_crop, S, bicubic):
+    return int(np.ceil((2.0 if bicubic else 1.0) * max(1.0, max_crop / S))) * 2 + 1
+
+
+@pytest.fixture(scope="module")
+def hostlib(tmp_path_factory):
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    out = str(tmp_path_factory.mktemp("host_istage") / "libhost_istage.so")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-std=c++14", "-o", out,
+                           os.path.join(HERE, "host_input_stage.cpp")])
+    return ctypes.CDLL(out)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+@pytest.mark.parametrize("bicubic", [0, 1])
+@pytest.mark.parametrize("S", [224, 32])
+def test_host_build_of_the_kernel_bodies_is_pillow_exact(hostlib, bicubic, S):
+    c = make_cases()
+    n = len(c["item_img"])
+    max_h, max_side = int(c["item_box"][:, 2].max()), int(c["item_box"][:, 2:].max())
+    dst = np.full((n, S, S, 3), 77, dtype=np.uint8)
+    st = hostlib.host_resized_crop_u8(_p(c["src"]), _p(c["src_off"]), _p(c["src_h"]), _p(c["src_w"]), _p(c["item_img"]),
+                                      _p(c["item_box"]), _p(dst), n, S, max_h, kmax_for(max_side, S, bicubic), bicubic)
+    assert st == 0
+    name = "bicubic" if bicubic else "bilinear"
+    for m in range(n):
+        i, j, h, w = (int(v) for v in c["item_box"][m])
+        pil = Image.fromarray(c["images"][c["item_img"][m]]).crop((j, i, j + w, i + h)).resize((S, S), getattr(Image, name.upper()))
+        assert np.array_equal(dst[m], np.asarray(pil)), (m, name)
+        assert np.array_equal(dst[m], O.resized_crop_u8(c["images"][c["item_img"][m]], i, j, h, w, S, name))
+    # float stage: grayscale / flip / CHW / normalise
+    gray = np.array([0, 1, 0, 1, 0, 0, 1, 0, 1], dtype=np.int32)
+    flip = np.array([0, 0, 1, 1, 0, 1, 0, 1, 0], dtype=np.int32)
+    mean, std = np.float32([0.485, 0.456, 0.406]), np.float32([0.229, 0.224, 0.225])
+    out = np.zeros((n, 3, S, S), dtype=np.float32)
+    hostlib.host_views_finalize_f32(_p(dst), _p(gray), _p(flip), _p(out), n, S, ctypes.c_double(1.0 / 255.0), _p(mean), _p(std))
+    for m in range(n):
+        img = dst[m]
+        if gray[m]:
+            img = O.grayscale3_u8(img)
+        if flip[m]:
+            img = O.hflip_u8(img)
+        assert np.array_equal(out[m], O.transpose_normalize(img)), m
+
+
+def test_status_word_reports_bad_boxes_and_short_kmax(hostlib):
+    c = make_cases()
+    n, S = len(c["item_img"]), 16
+    dst = np.zeros((n, S, S, 3), dtype=np.uint8)
+    box = c["item_box"].copy()
+    box[2] = (300, 400, 76, 100)                                                     # one row past the image
+    st = hostlib.host_resized_crop_u8(_p(c["src"]), _p(c["src_off"]), _p(c["src_h"]), _p(c["src_w"]), _p(c["item_img"]), _p(box),
+                                      _p(dst), n, S, 375, kmax_for(500, S, 0), 0)
+    assert st == 1 and dst[2].max() == 0 and dst[0].max() > 0
+    st = hostlib.host_resized_crop_u8(_p(c["src"]), _p(c["src_off"]), _p(c["src_h"]), _p(c["src_w"]), _p(c["item_img"]),
+                                      _p(c["item_box"]), _p(dst), n, S, 375, 5, 0)
+    assert st == 2 and dst[1].max() == 0 and dst[3].max() > 0                        # 500 -> 16 needs 65 taps; the 1x1 crop needs 3
+
+
+def test_product_sampler_and_draw_order():
+    """passl_b200.data.random_resized_crop_params equals the reference's get_params (same `random` calls in the same order), and
+    TwoViewInputStage.draw consumes the stream as documented: box 1, box 2, gray 1, flip 1, gray 2, flip 2 per sample."""
+    import random
+    from passl_b200.data import ImageBatch, TwoViewInputStage, random_resized_crop_params
+    G = np.load(os.path.join(HERE, "golden", "reference_crop_params.npz"))
+    for tag in "abcdef":
+        W, H, s0, s1, r0, r1, seed = G["args_" + tag]
+        random.seed(int(seed))
+        got = [random_resized_crop_params(int(W), int(H), (s0, s1), (r0, r1), random) for _ in range(64)]
+        assert np.array_equal(np.array(got), G["boxes_" + tag]), tag
+    images = [np.zeros((h, w, 3), dtype=np.uint8) for h, w in [(240, 320), (100, 50)]]
+    batch = ImageBatch(images, device="cpu")
+    assert batch.src_off.tolist() == [0, 240 * 320 * 3] and batch.data.numel() == 240 * 320 * 3 + 100 * 50 * 3
+    stage = TwoViewInputStage(size=64, rng=random.Random(3))
+    item_img, item_box, gray, flip = stage.draw(batch)
+    r = random.Random(3)
+    want_box, want_g, want_f = {}, {}, {}
+    for n, (h, w) in enumerate([(240, 320), (100, 50)]):
+        want_box[n] = random_resized_crop_params(w, h, rng=r)
+        want_box[2 + n] = random_resized_crop_params(w, h, rng=r)
+        want_g[n], want_f[n] = r.random() < 0.2, r.random() < 0.5
+        want_g[2 + n], want_f[2 + n] = r.random() < 0.2, r.random() < 0.5
+    assert item_img == [0, 1, 0, 1]
+    assert [tuple(b) for b in item_box] == [want_box[m] for m in range(4)]
+    assert gray == [want_g[m] for m in range(4)] and flip == [want_f[m] for m in range(4)]
+    with pytest.raises(ValueError):
+        ImageBatch([np.zeros((4, 4), dtype=np.uint8)], device="cpu")

@@ -1,0 +1,77 @@
+"""The image input stage through the C ABI on the GPU (csrc/input_stage.cu): the cases of tests/test_input_stage_host_cpu.py — ragged
+source images, edge boxes, both filters — bit-exact against Pillow / the oracle, the float stage bit-exact against the oracle, and
+the two-view stage end to end.  (Named to sort last: it is the newest row of SURVEY.md §8, f-2.)"""
+import os
+import random
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+
+
+@pytest.mark.parametrize("interp", ["bilinear", "bicubic"])
+@pytest.mark.parametrize("S", [224, 32])
+def test_resized_crop_and_finalize_match_the_oracle(interp, S):
+    import oracle.input_stage as O
+    from test_input_stage_host_cpu import make_cases
+    from passl_b200.data import ImageBatch, resized_crop_u8, views_finalize
+    c = make_cases()
+    batch = ImageBatch(c["images"])
+    boxes = [tuple(int(v) for v in b) for b in c["item_box"]]
+    idx = [int(i) for i in c["item_img"]]
+    u8 = resized_crop_u8(batch, idx, boxes, S, interp)
+    got = u8.cpu().numpy()
+    for m, (n, (i, j, h, w)) in enumerate(zip(idx, boxes)):
+        assert np.array_equal(got[m], O.resized_crop_u8(c["images"][n], i, j, h, w, S, interp)), (m, interp)
+    gray = [0, 1, 0, 1, 0, 0, 1, 0, 1]
+    flip = [0, 0, 1, 1, 0, 1, 0, 1, 0]
+    out = views_finalize(u8, gray, flip).cpu().numpy()
+    for m in range(len(idx)):
+        img = got[m]
+        if gray[m]:
+            img = O.grayscale3_u8(img)
+        if flip[m]:
+            img = O.hflip_u8(img)
+        assert np.array_equal(out[m], O.transpose_normalize(img)), m
+
+
+def test_bad_box_is_refused_on_the_host_and_flagged_on_the_device():
+    from test_input_stage_host_cpu import make_cases
+    from passl_b200 import _lib
+    from passl_b200.data import ImageBatch, resized_crop_u8
+    c = make_cases()
+    batch = ImageBatch(c["images"])
+    with pytest.raises(ValueError):
+        resized_crop_u8(batch, [0], [(300, 400, 76, 100)], 32)
+    # the device-side guard, reached by lying to the host check about the image size
+    batch.heights[0] += 1
+    with pytest.raises(_lib.PasslB200Error):
+        resized_crop_u8(batch, [0, 1], [(300, 400, 76, 100), (0, 0, 64, 48)], 32)
+
+
+def test_two_view_stage_end_to_end():
+    """N images -> (view_1, view_2); every view equals the oracle applied with the decisions the stage drew."""
+    import oracle.input_stage as O
+    from passl_b200.data import ImageBatch, TwoViewInputStage
+    rng = np.random.RandomState(5)
+    images = [rng.randint(0, 256, size=(int(h), int(w), 3)).astype(np.uint8) for h, w in [(240, 320), (333, 250), (128, 128), (96, 400)]]
+    stage = TwoViewInputStage(size=64, scale=(0.2, 1.0), interpolation="bicubic", rng=random.Random(11))
+    twin = TwoViewInputStage(size=64, scale=(0.2, 1.0), interpolation="bicubic", rng=random.Random(11))
+    batch = ImageBatch(images)
+    v1, v2 = stage(batch)
+    item_img, item_box, gray, flip = twin.draw(batch)
+    assert v1.shape == (4, 3, 64, 64) and v2.shape == (4, 3, 64, 64) and v1.dtype == torch.float32
+    both = torch.cat([v1, v2]).cpu().numpy()
+    for m, (n, (i, j, h, w)) in enumerate(zip(item_img, item_box)):
+        img = O.resized_crop_u8(images[n], i, j, h, w, 64, "bicubic")
+        if gray[m]:
+            img = O.grayscale3_u8(img)
+        if flip[m]:
+            img = O.hflip_u8(img)
+        assert np.array_equal(both[m], O.transpose_normalize(img)), m
+    assert not np.array_equal(both[0], both[4])                                   # two different views of sample 0
