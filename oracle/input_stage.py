@@ -134,3 +134,80 @@ def get_params(width, height, scale, ratio, rng):
     else:
         cw, ch = width, height
     return (height - ch) // 2, (width - cw) // 2, ch, cw
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# ColorJitter pixel arithmetic (configs/simclr/simclr_r50_IM.yaml:41-48: brightness 0.4, contrast 0.4, saturation 0.4, hue 0.1).
+# paddle.vision's PIL backend calls ImageEnhance.{Brightness, Contrast, Color}(img).enhance(factor) and, for hue, shifts the H plane
+# of img.convert('HSV') by uint8(hue_factor * 255) with wrap-around and converts back.  Restated from Pillow (libImaging/Blend.c,
+# Convert.c rgb2hsv / hsv2rgb, ImageEnhance.py, ImageStat.py) and pinned bit-exact against Pillow: the HSV conversions over all 2^24
+# colours, the blend over all (a, b) byte pairs for hundreds of factors (tests/test_oracle_input_stage_cpu.py).
+# ---------------------------------------------------------------------------------------------------------------------------------
+def blend_u8(degenerate, img, alpha):
+    """Image.blend(degenerate, img, alpha): float32 a + alpha * (b - a), truncated; clipped to [0, 255] when alpha is outside [0, 1]."""
+    al = np.float32(alpha)
+    a = degenerate.astype(np.float32)
+    t = a + al * (img.astype(np.int32) - degenerate.astype(np.int32)).astype(np.float32)
+    if 0 <= alpha <= 1.0:
+        return t.astype(np.int64).astype(np.uint8)
+    return np.where(t <= 0, 0, np.where(t >= 255.0, 255, t.astype(np.int64))).astype(np.uint8)
+
+
+def luma_u8(img):
+    r, g, b = (img[..., c].astype(np.int64) for c in range(3))
+    return ((r * 19595 + g * 38470 + b * 7471 + 0x8000) >> 16).astype(np.uint8)
+
+
+def adjust_brightness(img, factor):
+    return blend_u8(np.zeros_like(img), img, factor)
+
+
+def adjust_contrast(img, factor):
+    L = luma_u8(img)
+    mean = int(float(L.astype(np.int64).sum()) / L.size + 0.5)                  # ImageStat mean of the L image, rounded half up
+    return blend_u8(np.full_like(img, mean), img, factor)
+
+
+def adjust_saturation(img, factor):
+    L = luma_u8(img)
+    return blend_u8(np.stack([L, L, L], axis=-1), img, factor)
+
+
+def rgb_to_hsv_u8(img):
+    """Convert.c rgb2hsv: channel ratios in float32, hue assembled in double and rounded to float32, scaled by 255.0 in double."""
+    f32, f64 = np.float32, np.float64
+    r, g, b = (img[..., c].astype(np.int32) for c in range(3))
+    maxc, minc = np.maximum(r, np.maximum(g, b)), np.minimum(r, np.minimum(g, b))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        cr = (maxc - minc).astype(f32)
+        s = cr / maxc.astype(f32)
+        rc, gc, bc = ((maxc - c).astype(f32) / cr for c in (r, g, b))
+        h = np.where(r == maxc, bc.astype(f64) - gc.astype(f64),
+                     np.where(g == maxc, 2.0 + rc.astype(f64) - bc.astype(f64), 4.0 + gc.astype(f64) - rc.astype(f64))).astype(f32)
+        h = np.fmod(h.astype(f64) / 6.0 + 1.0, 1.0).astype(f32)
+        uh = np.clip((h.astype(f64) * 255.0).astype(np.int64), 0, 255)
+        us = np.clip((s.astype(f64) * 255.0).astype(np.int64), 0, 255)
+    gray = maxc == minc
+    return np.stack([np.where(gray, 0, uh), np.where(gray, 0, us), maxc], axis=-1).astype(np.uint8)
+
+
+def hsv_to_rgb_u8(hsv):
+    """Convert.c hsv2rgb (colorsys sextants): p, q, t = round(v (1 - s..)), C round() = half away from zero."""
+    f32, f64 = np.float32, np.float64
+    h, s, v = (hsv[..., c].astype(np.int32) for c in range(3))
+    hd = h.astype(f64) * 6.0 / 255.0
+    i = np.floor(hd).astype(np.int64)
+    f = (hd - i).astype(f32).astype(f64)
+    fs = (s.astype(f64) / 255.0).astype(f32).astype(f64)
+    p, q, t = (np.clip(np.floor(v * x + 0.5), 0, 255).astype(np.int64) for x in (1.0 - fs, 1.0 - fs * f, 1.0 - fs * (1.0 - f)))
+    k = i % 6
+    out = np.stack([np.choose(k, [v, q, p, p, t, v]), np.choose(k, [t, v, v, q, p, p]), np.choose(k, [p, p, t, v, v, q])], axis=-1)
+    return np.where((s == 0)[..., None], np.stack([v, v, v], axis=-1), out).astype(np.uint8)
+
+
+def adjust_hue(img, hue_factor):
+    """H plane += uint8(hue_factor * 255) modulo 256 (numpy uint8 cast of the product: truncation toward zero, then wrap)."""
+    hsv = rgb_to_hsv_u8(img)
+    shift = np.array(hue_factor * 255).astype(np.int64).astype(np.uint8)       # np.uint8(float): C cast, negative values wrap
+    hsv[..., 0] = hsv[..., 0] + shift
+    return hsv_to_rgb_u8(hsv)

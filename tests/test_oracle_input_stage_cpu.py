@@ -57,3 +57,42 @@ def test_transpose_normalize_definition():
     for c in range(3):
         want = ((img[..., c].astype(np.float64) * (1.0 / 255.0) - np.float64(mean[c])) / np.float64(std[c])).astype(np.float32)
         assert np.array_equal(out[c], want)
+
+
+# ------------------------------------------------------------------ ColorJitter arithmetic vs Pillow -------------------------------
+def test_hsv_conversions_are_pillow_exact_over_all_colours():
+    v = np.arange(1 << 24, dtype=np.uint32)
+    cube = np.stack([(v >> 16) & 255, (v >> 8) & 255, v & 255], -1).astype(np.uint8).reshape(4096, 4096, 3)
+    assert np.array_equal(O.rgb_to_hsv_u8(cube), np.asarray(Image.fromarray(cube, "RGB").convert("HSV")))
+    assert np.array_equal(O.hsv_to_rgb_u8(cube), np.asarray(Image.fromarray(cube, "HSV").convert("RGB")))
+
+
+def test_blend_is_pillow_exact_over_all_byte_pairs():
+    a = np.repeat(np.arange(256, dtype=np.uint8)[:, None], 256, 1)
+    b = np.ascontiguousarray(a.T)
+    rng = random.Random(0)
+    for alpha in [0.0, 1.0, 0.5, 0.6, 1.4, 1.7999, 0.2000001, 1e-3, 2.0, 1.0000001] + [rng.uniform(0.0, 2.0) for _ in range(200)]:
+        want = np.asarray(Image.blend(Image.fromarray(a, "L"), Image.fromarray(b, "L"), alpha))
+        assert np.array_equal(O.blend_u8(a, b, alpha), want), alpha
+
+
+def test_colour_jitter_ops_match_pillow_enhancers():
+    from PIL import ImageEnhance
+    rng = np.random.RandomState(11)
+    r = random.Random(5)
+    for shape in [(64, 64), (37, 91)]:
+        img = rng.randint(0, 256, size=shape + (3,)).astype(np.uint8)
+        img[: shape[0] // 3] //= 4                                                 # a dark band: moves the contrast mean
+        pil = Image.fromarray(img)
+        for _ in range(12):
+            f = r.uniform(0.6, 1.4)
+            assert np.array_equal(O.adjust_brightness(img, f), np.asarray(ImageEnhance.Brightness(pil).enhance(f)))
+            assert np.array_equal(O.adjust_contrast(img, f), np.asarray(ImageEnhance.Contrast(pil).enhance(f)))
+            assert np.array_equal(O.adjust_saturation(img, f), np.asarray(ImageEnhance.Color(pil).enhance(f)))
+            hf = r.uniform(-0.1, 0.1)
+            h, s, v = pil.convert("HSV").split()                                   # the PIL path of paddle's adjust_hue
+            np_h = np.array(h, dtype=np.uint8)
+            with np.errstate(over="ignore"):
+                np_h += np.array(hf * 255).astype(np.uint8)
+            want = Image.merge("HSV", (Image.fromarray(np_h, "L"), s, v)).convert("RGB")
+            assert np.array_equal(O.adjust_hue(img, hf), np.asarray(want)), hf
