@@ -342,6 +342,14 @@ int passl_b200_resized_crop_u8(const void* src, const long long* src_off, const 
                                int max_crop_h, int kmax, int interpolation, void* stream);
 int passl_b200_views_finalize_f32(const void* img, const int* gray, const int* flip, float* out, int items, int size, double scale,
                                   const float* mean3, const float* std3, void* stream);
+/*   color_jitter_u8     ColorJitter (configs/simclr/simclr_r50_IM.yaml:41-48; paddle.vision over Pillow): per view up to four ops
+ *                       in the order the host drew, in place on uint8 [items, S, S, 3].  ops int32 [items][4]: 0 none, 1 brightness,
+ *                       2 contrast, 3 saturation (ImageEnhance blends, libImaging/Blend.c), 4 hue (HSV round trip of Convert.c with
+ *                       the H plane shifted).  factors fp32 [items][4]: the blend factor, or for hue the shift
+ *                       uint8(hue_factor * 255) the host computed.  workspace >= 8 * items bytes (exact luma sums for the contrast
+ *                       mean); contrast_positions: bit p set when some view has contrast at position p (0xF is always safe). */
+int passl_b200_color_jitter_u8(void* img, const int* ops, const float* factors, void* workspace, long long workspace_bytes, int items,
+                               int size, int contrast_positions, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Developer probe (not a reference entry point): one tcgen05.mma over a row-shifted view of a SWIZZLE_128B tile, used by

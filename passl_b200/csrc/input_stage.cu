@@ -102,6 +102,41 @@ __global__ void views_finalize_kernel(const unsigned char* __restrict__ img, con
   }
 }
 
+// ---- ColorJitter: up to four ops per view in a host-drawn order; the contrast op needs the mean luma of the view as it stands
+// when the op runs, so every position is (optional) exact integer luma sum -> in-place per-pixel op --------------------------------
+__global__ void luma_sum_kernel(const unsigned char* __restrict__ img, const int* __restrict__ ops,
+                                unsigned long long* __restrict__ sums, int S, int pos) {
+  const int m = blockIdx.y;
+  if (ops[4 * m + pos] != JIT_CONTRAST) return;
+  const long long n = (long long)S * S;
+  const unsigned char* base = img + (long long)m * n * 3;
+  unsigned long long acc = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc += (unsigned long long)luma_byte(base[3 * i], base[3 * i + 1], base[3 * i + 2]);
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ unsigned long long part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += part[w];
+    atomicAdd(sums + m, t);
+  }
+}
+
+__global__ void jitter_apply_kernel(unsigned char* __restrict__ img, const int* __restrict__ ops, const float* __restrict__ factors,
+                                    const unsigned long long* __restrict__ sums, int S, int pos) {
+  const int m = blockIdx.y;
+  const int op = ops[4 * m + pos];
+  if (op == JIT_NONE) return;
+  const long long n = (long long)S * S;
+  const float factor = factors[4 * m + pos];
+  const int mean = op == JIT_CONTRAST ? contrast_mean(sums[m], n) : 0;
+  unsigned char* base = img + (long long)m * n * 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    jitter_pixel(base + 3 * i, op, factor, mean);
+}
+
 static inline int grid_for(long long total, int block) {
   long long blocks = (total + block - 1) / block;
   const long long cap = 148LL * 32;
@@ -177,5 +212,27 @@ extern "C" int passl_b200_views_finalize_f32(const void* img, const int* gray, c
       reinterpret_cast<const unsigned char*>(img), gray, flip, out, items, size, scale, mean3[0], mean3[1], mean3[2], std3[0],
       std3[1], std3[2]);
   PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+extern "C" int passl_b200_color_jitter_u8(void* img, const int* ops, const float* factors, void* workspace, long long workspace_bytes,
+                                          int items, int size, int contrast_positions, void* stream) {
+  if (items <= 0 || size <= 0 || !img || !ops || !factors || !workspace) return PB_ERR_BAD_ARG;
+  if (workspace_bytes < (long long)items * (long long)sizeof(unsigned long long)) return PB_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* sums = reinterpret_cast<unsigned long long*>(workspace);
+  const long long n = (long long)size * size;
+  int bx = (int)((n + 255) / 256);
+  if (bx > 64) bx = 64;
+  const dim3 grid(bx, items);
+  for (int pos = 0; pos < 4; ++pos) {
+    if (contrast_positions & (1 << pos)) {
+      PB_CUDA_CHECK(cudaMemsetAsync(sums, 0, (size_t)items * sizeof(unsigned long long), st));
+      luma_sum_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const unsigned char*>(img), ops, sums, size, pos);
+      PB_LAUNCH_CHECK();
+    }
+    jitter_apply_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<unsigned char*>(img), ops, factors, sums, size, pos);
+    PB_LAUNCH_CHECK();
+  }
   return PB_OK;
 }

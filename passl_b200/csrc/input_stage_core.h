@@ -176,5 +176,109 @@ PB_HD void finalize_pixel(const unsigned char* img, const float* lut, float* out
   o[2LL * S * S] = lut[512 + b];
 }
 
+// ---- ColorJitter (configs/simclr/simclr_r50_IM.yaml:41-48): Pillow's ImageEnhance blends and HSV round trip --------------------
+#if defined(__CUDA_ARCH__)
+PB_HD float rnf_add(float a, float b) { return __fadd_rn(a, b); }
+PB_HD float rnf_mul(float a, float b) { return __fmul_rn(a, b); }
+PB_HD float rnf_div(float a, float b) { return __fdiv_rn(a, b); }
+#else
+PB_HD float rnf_add(float a, float b) { return a + b; }
+PB_HD float rnf_mul(float a, float b) { return a * b; }
+PB_HD float rnf_div(float a, float b) { return a / b; }
+#endif
+
+enum JitterOp : int { JIT_NONE = 0, JIT_BRIGHTNESS = 1, JIT_CONTRAST = 2, JIT_SATURATION = 3, JIT_HUE = 4 };
+
+// Blend.c: out = a + alpha (b - a) in float32, truncated; clipped when alpha lies outside [0, 1] (a = degenerate, b = image)
+PB_HD unsigned char blend_byte(int a, int b, float alpha) {
+  const float t = rnf_add((float)a, rnf_mul(alpha, (float)(b - a)));
+  if (alpha >= 0.f && alpha <= 1.f) return (unsigned char)(int)t;
+  if (t <= 0.f) return 0;
+  if (t >= 255.f) return 255;
+  return (unsigned char)(int)t;
+}
+
+PB_HD int luma_byte(int r, int g, int b) { return (r * 19595 + g * 38470 + b * 7471 + 0x8000) >> 16; }
+
+// ImageStat mean of the L plane rounded half up: the grey level ImageEnhance.Contrast blends towards
+PB_HD int contrast_mean(unsigned long long luma_sum, long long count) {
+  return (int)(rn_add(rn_div((double)luma_sum, (double)count), 0.5));
+}
+
+// Convert.c rgb2hsv: ratios in float32, hue assembled in double, rounded to float32, scaled by 255.0 in double
+PB_HD void rgb_to_hsv(int r, int g, int b, int* h, int* s, int* v) {
+  const int maxc = r > g ? (r > b ? r : b) : (g > b ? g : b);
+  const int minc = r < g ? (r < b ? r : b) : (g < b ? g : b);
+  *v = maxc;
+  if (minc == maxc) {
+    *h = 0;
+    *s = 0;
+    return;
+  }
+  const float cr = (float)(maxc - minc);
+  const float sf = rnf_div(cr, (float)maxc);
+  const float rc = rnf_div((float)(maxc - r), cr), gc = rnf_div((float)(maxc - g), cr), bc = rnf_div((float)(maxc - b), cr);
+  double hd;
+  if (r == maxc) hd = rn_sub((double)bc, (double)gc);
+  else if (g == maxc) hd = rn_sub(rn_add(2.0, (double)rc), (double)bc);
+  else hd = rn_sub(rn_add(4.0, (double)gc), (double)rc);
+  const float hf = to_float(hd);
+  const double turn = rn_add(rn_div((double)hf, 6.0), 1.0);        // in [5/6, 11/6]: fmod(x, 1.0) = x - floor(x), exact
+  const float hfrac = to_float(rn_sub(turn, floor(turn)));
+  int uh = trunc_int(rn_mul((double)hfrac, 255.0));
+  int us = trunc_int(rn_mul((double)sf, 255.0));
+  *h = uh < 0 ? 0 : (uh > 255 ? 255 : uh);
+  *s = us < 0 ? 0 : (us > 255 ? 255 : us);
+}
+
+PB_HD int round_clip8(double x) {                                  // C round() of a non-negative value, then CLIP8
+  const int v = (int)floor(rn_add(x, 0.5));
+  return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+
+// Convert.c hsv2rgb (colorsys sextants)
+PB_HD void hsv_to_rgb(int h, int s, int v, int* r, int* g, int* b) {
+  if (s == 0) {
+    *r = *g = *b = v;
+    return;
+  }
+  const double hd = rn_div(rn_mul((double)h, 6.0), 255.0);
+  const int i = (int)floor(hd);
+  const double f = (double)to_float(rn_sub(hd, (double)i));
+  const double fs = (double)to_float(rn_div((double)s, 255.0));
+  const int p = round_clip8(rn_mul((double)v, rn_sub(1.0, fs)));
+  const int q = round_clip8(rn_mul((double)v, rn_sub(1.0, rn_mul(fs, f))));
+  const int t = round_clip8(rn_mul((double)v, rn_sub(1.0, rn_mul(fs, rn_sub(1.0, f)))));
+  switch (i % 6) {
+    case 0: *r = v; *g = t; *b = p; break;
+    case 1: *r = q; *g = v; *b = p; break;
+    case 2: *r = p; *g = v; *b = t; break;
+    case 3: *r = p; *g = q; *b = v; break;
+    case 4: *r = t; *g = p; *b = v; break;
+    default: *r = v; *g = p; *b = q; break;
+  }
+}
+
+// one pixel of one jitter op, in place.  `factor` is the blend factor (a C float, as Pillow receives it); for JIT_HUE it carries the
+// H-plane shift paddle's adjust_hue computes on the host, np.uint8(hue_factor * 255) in 0..255 (double product, truncation toward
+// zero, wrap).  `mean` = contrast_mean of the view as it stands before this op.
+PB_HD void jitter_pixel(unsigned char* p, int op, float factor, int mean) {
+  int r = p[0], g = p[1], b = p[2];
+  if (op == JIT_BRIGHTNESS) {
+    p[0] = blend_byte(0, r, factor); p[1] = blend_byte(0, g, factor); p[2] = blend_byte(0, b, factor);
+  } else if (op == JIT_CONTRAST) {
+    p[0] = blend_byte(mean, r, factor); p[1] = blend_byte(mean, g, factor); p[2] = blend_byte(mean, b, factor);
+  } else if (op == JIT_SATURATION) {
+    const int L = luma_byte(r, g, b);
+    p[0] = blend_byte(L, r, factor); p[1] = blend_byte(L, g, factor); p[2] = blend_byte(L, b, factor);
+  } else if (op == JIT_HUE) {
+    int h, s, v;
+    rgb_to_hsv(r, g, b, &h, &s, &v);
+    h = (h + (int)factor) & 255;
+    hsv_to_rgb(h, s, v, &r, &g, &b);
+    p[0] = (unsigned char)r; p[1] = (unsigned char)g; p[2] = (unsigned char)b;
+  }
+}
+
 }  // namespace istage
 }  // namespace pb

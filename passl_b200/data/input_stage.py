@@ -4,11 +4,11 @@ Reference (CPU workers, per sample; passl_v110/datasets/imagenet.py:46-63 with c
 `sample1 = transform(sample); sample2 = transform(sample)` with transform = RandomResizedCrop, then per view
 `RandomApply(ColorJitter) -> RandomGrayscale -> RandomApply(GaussianBlur) -> RandomHorizontalFlip -> Transpose -> NormalizeImage`.
 
-Built here: the crop-box draw on the host (same algorithm and `random` call order as transforms.py:517-557), crop + Pillow-exact
-resize, grayscale, flip, CHW + normalise on the GPU (csrc/input_stage.cu).  ColorJitter and GaussianBlur are not built: the
-stage is the geometric + photometric-normalisation part of the recipe, and because those two ops also draw random numbers, a
-run of this stage does not consume the `random` stream the way a full reference worker would.
-Decisions are drawn per sample in the order: box of view 1, box of view 2, grayscale 1, flip 1, grayscale 2, flip 2.
+Built here: the crop-box draw on the host (same algorithm and `random` call order as transforms.py:517-557), then on the GPU
+(csrc/input_stage.cu) crop + Pillow-exact resize, ColorJitter (Pillow's ImageEnhance blends and HSV hue shift), grayscale, flip,
+CHW + normalise — every pixel op bit-exact against Pillow.  GaussianBlur (cv2, 23x23) is not built, and ColorJitter's use of
+the `random` stream restates PaddlePaddle code that is not in the reference tree; so pixel arithmetic is pinned, the exact
+sequence of random draws of a full reference worker is not.
 """
 import math
 import random
@@ -123,31 +123,100 @@ def views_finalize(views_u8, gray, flip, scale=1.0 / 255.0, mean=(0.485, 0.456, 
     return out
 
 
+JITTER_OPS = {"brightness": 1, "contrast": 2, "saturation": 3, "hue": 4}
+
+
+def color_jitter_plan(brightness=0.4, contrast=0.4, saturation=0.4, hue=0.1, rng=random):
+    """One ColorJitter application -> [(op, factor)] in execution order.
+
+    Restates paddle.vision.transforms.ColorJitter (PaddlePaddle, not in the reference tree, so the consumption of the `random`
+    stream below is unpinned): the four single-op transforms are put in a list, `random.shuffle`d, and each draws its factor with
+    `random.uniform` when it runs — brightness / contrast / saturation from [max(0, 1 - v), 1 + v], hue from [-v, v]; an amount of
+    0 keeps its slot in the shuffle but draws nothing."""
+    slots = [("brightness", brightness), ("contrast", contrast), ("saturation", saturation), ("hue", hue)]
+    rng.shuffle(slots)
+    plan = []
+    for name, amount in slots:
+        if not amount:
+            continue
+        lo, hi = (-amount, amount) if name == "hue" else (max(0.0, 1.0 - amount), 1.0 + amount)
+        plan.append((JITTER_OPS[name], rng.uniform(lo, hi)))
+    return plan
+
+
+def color_jitter_u8(views_u8, plans):
+    """In-place ColorJitter of uint8 [items, S, S, 3] views; plans[m] = [(op, factor)] (at most four) or [] for an untouched view.
+    Blend factors are passed as C floats like Pillow receives them; the hue shift is uint8(hue_factor * 255) computed here."""
+    if not views_u8.is_cuda:
+        raise _lib.PasslB200Error("passl_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    lib = _lib.load()
+    items, S = views_u8.shape[0], views_u8.shape[1]
+    assert views_u8.dtype == torch.uint8 and views_u8.shape == (items, S, S, 3) and views_u8.is_contiguous() and len(plans) == items
+    ops, factors, contrast_positions = [], [], 0
+    for plan in plans:
+        if len(plan) > 4:
+            raise ValueError("at most four jitter ops per view")
+        row_o, row_f = [0, 0, 0, 0], [0.0, 0.0, 0.0, 0.0]
+        for pos, (op, f) in enumerate(plan):
+            row_o[pos] = int(op)
+            row_f[pos] = float(int(f * 255) & 255) if op == JITTER_OPS["hue"] else float(f)
+            if op == JITTER_OPS["contrast"]:
+                contrast_positions |= 1 << pos
+        ops.append(row_o)
+        factors.append(row_f)
+    if not any(any(r) for r in ops):
+        return views_u8
+    dev = views_u8.device
+    d_ops = torch.tensor(ops, dtype=torch.int32, device=dev)
+    d_fac = torch.tensor(factors, dtype=torch.float32, device=dev)
+    ws = torch.empty(8 * items, dtype=torch.uint8, device=dev)
+    _lib.check(lib.passl_b200_color_jitter_u8(views_u8.data_ptr(), d_ops.data_ptr(), d_fac.data_ptr(), ws.data_ptr(), ws.numel(), items, S,
+                                              contrast_positions, _stream()), "color_jitter_u8")
+    return views_u8
+
+
 class TwoViewInputStage:
     """`(view_1, view_2) = stage(images)`: both fp32 [N, 3, size, size] on the device, ready for MoCo / SimCLR `train_iter`."""
 
-    def __init__(self, size=224, scale=(0.08, 1.0), ratio=(3. / 4., 4. / 3.), interpolation="bilinear", gray_p=0.2, flip_p=0.5,
+    def __init__(self, size=224, scale=(0.08, 1.0), ratio=(3. / 4., 4. / 3.), interpolation="bilinear", jitter_p=0.0,
+                 brightness=0.4, contrast=0.4, saturation=0.4, hue=0.1, gray_p=0.2, blur_p=0.0, flip_p=0.5,
                  norm_scale=1.0 / 255.0, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225), rng=random):
+        """SimCLR recipe (configs/simclr/simclr_r50_IM.yaml:35-61): scale=(0.1, 1), interpolation='bicubic', jitter_p=0.8, gray_p=0.2,
+        flip_p=0.5 (and blur_p=0.5, which is not built); MoCo v2 / CLIP recipes use the defaults with their own scale."""
+        if blur_p:
+            raise NotImplementedError("GaussianBlur (cv2.GaussianBlur with a 23x23 kernel, transforms.py:173-191) is not built")
         self.size, self.scale, self.ratio, self.interpolation = size, tuple(scale), tuple(ratio), interpolation
+        self.jitter_p, self.jitter = jitter_p, dict(brightness=brightness, contrast=contrast, saturation=saturation, hue=hue)
         self.gray_p, self.flip_p, self.norm_scale, self.mean, self.std, self.rng = gray_p, flip_p, norm_scale, mean, std, rng
 
+    def _draw_view(self):
+        """RandomApply(ColorJitter) -> RandomGrayscale -> RandomHorizontalFlip decisions of one view, in pipeline order."""
+        rng, plan = self.rng, []
+        if self.jitter_p and not (self.jitter_p < rng.random()):         # RandomApply: `if self.p < random.random(): return img`
+            plan = color_jitter_plan(rng=rng, **self.jitter)
+        gray = rng.random() < self.gray_p
+        flip = rng.random() < self.flip_p
+        return plan, gray, flip
+
     def draw(self, batch):
-        """Host-side random decisions for one batch -> (item_img, item_box, gray, flip); views of sample n are items n and N + n."""
+        """Host-side random decisions for one batch -> (item_img, item_box, gray, flip, plans); views of sample n are items n and
+        N + n.  Per sample: box of view 1, box of view 2 (the dataset calls the crop transform twice first, imagenet.py:57-58), then
+        the decisions of view 1, then those of view 2."""
         N = len(batch)
-        box1, box2, g1, g2, f1, f2 = [], [], [], [], [], []
+        box1, box2, d1, d2 = [], [], [], []
         for n in range(N):
             box1.append(random_resized_crop_params(batch.widths[n], batch.heights[n], self.scale, self.ratio, self.rng))
             box2.append(random_resized_crop_params(batch.widths[n], batch.heights[n], self.scale, self.ratio, self.rng))
-            g1.append(self.rng.random() < self.gray_p)
-            f1.append(self.rng.random() < self.flip_p)
-            g2.append(self.rng.random() < self.gray_p)
-            f2.append(self.rng.random() < self.flip_p)
-        return list(range(N)) * 2, box1 + box2, g1 + g2, f1 + f2
+            d1.append(self._draw_view())
+            d2.append(self._draw_view())
+        both = d1 + d2
+        return list(range(N)) * 2, box1 + box2, [d[1] for d in both], [d[2] for d in both], [d[0] for d in both]
 
     def __call__(self, images):
         batch = images if isinstance(images, ImageBatch) else ImageBatch(images)
-        item_img, item_box, gray, flip = self.draw(batch)
+        item_img, item_box, gray, flip, plans = self.draw(batch)
         u8 = resized_crop_u8(batch, item_img, item_box, self.size, self.interpolation)
+        u8 = color_jitter_u8(u8, plans)
         out = views_finalize(u8, gray, flip, self.norm_scale, self.mean, self.std)
         N = len(batch)
         return out[:N], out[N:]

@@ -55,3 +55,33 @@ extern "C" void host_views_finalize_f32(const unsigned char* img, const int* gra
     for (int y = 0; y < S; ++y)
       for (int x = 0; x < S; ++x) finalize_pixel(img, lut, out, m, y, x, S, gray[m], flip[m]);
 }
+
+// colour jitter: ops / factors [items][4]; per position a luma sum over the view (only used by the contrast op), then the op
+extern "C" void host_color_jitter_u8(unsigned char* img, const int* ops, const float* factors, int items, int S) {
+  for (int pos = 0; pos < 4; ++pos)
+    for (int m = 0; m < items; ++m) {
+      const int op = ops[4 * m + pos];
+      if (op == JIT_NONE) continue;
+      unsigned char* base = img + (long long)m * S * S * 3;
+      unsigned long long sum = 0;
+      for (long long i = 0; i < (long long)S * S; ++i) sum += (unsigned long long)luma_byte(base[3 * i], base[3 * i + 1], base[3 * i + 2]);
+      const int mean = contrast_mean(sum, (long long)S * S);
+      for (long long i = 0; i < (long long)S * S; ++i) jitter_pixel(base + 3 * i, op, factors[4 * m + pos], mean);
+    }
+}
+
+extern "C" void host_rgb_to_hsv(const unsigned char* in, unsigned char* out, long long n) {
+  for (long long i = 0; i < n; ++i) {
+    int h, s, v;
+    rgb_to_hsv(in[3 * i], in[3 * i + 1], in[3 * i + 2], &h, &s, &v);
+    out[3 * i] = (unsigned char)h; out[3 * i + 1] = (unsigned char)s; out[3 * i + 2] = (unsigned char)v;
+  }
+}
+
+extern "C" void host_hsv_to_rgb(const unsigned char* in, unsigned char* out, long long n) {
+  for (long long i = 0; i < n; ++i) {
+    int r, g, b;
+    hsv_to_rgb(in[3 * i], in[3 * i + 1], in[3 * i + 2], &r, &g, &b);
+    out[3 * i] = (unsigned char)r; out[3 * i + 1] = (unsigned char)g; out[3 * i + 2] = (unsigned char)b;
+  }
+}

@@ -108,17 +108,87 @@ def test_product_sampler_and_draw_order():
     images = [np.zeros((h, w, 3), dtype=np.uint8) for h, w in [(240, 320), (100, 50)]]
     batch = ImageBatch(images, device="cpu")
     assert batch.src_off.tolist() == [0, 240 * 320 * 3] and batch.data.numel() == 240 * 320 * 3 + 100 * 50 * 3
-    stage = TwoViewInputStage(size=64, rng=random.Random(3))
-    item_img, item_box, gray, flip = stage.draw(batch)
+    stage = TwoViewInputStage(size=64, jitter_p=0.8, rng=random.Random(3))
+    item_img, item_box, gray, flip, plans = stage.draw(batch)
     r = random.Random(3)
-    want_box, want_g, want_f = {}, {}, {}
+
+    def view():                                          # RandomApply(ColorJitter) -> RandomGrayscale -> RandomHorizontalFlip
+        plan = []
+        if not (0.8 < r.random()):
+            slots = [("brightness", 0.4), ("contrast", 0.4), ("saturation", 0.4), ("hue", 0.1)]
+            r.shuffle(slots)
+            for name, v in slots:
+                lo, hi = (-v, v) if name == "hue" else (max(0.0, 1 - v), 1 + v)
+                plan.append(({"brightness": 1, "contrast": 2, "saturation": 3, "hue": 4}[name], r.uniform(lo, hi)))
+        return plan, r.random() < 0.2, r.random() < 0.5
+    want = {}
     for n, (h, w) in enumerate([(240, 320), (100, 50)]):
-        want_box[n] = random_resized_crop_params(w, h, rng=r)
-        want_box[2 + n] = random_resized_crop_params(w, h, rng=r)
-        want_g[n], want_f[n] = r.random() < 0.2, r.random() < 0.5
-        want_g[2 + n], want_f[2 + n] = r.random() < 0.2, r.random() < 0.5
+        b1, b2 = random_resized_crop_params(w, h, rng=r), random_resized_crop_params(w, h, rng=r)
+        want[n], want[2 + n] = (b1,) + view(), (b2,) + view()
     assert item_img == [0, 1, 0, 1]
-    assert [tuple(b) for b in item_box] == [want_box[m] for m in range(4)]
-    assert gray == [want_g[m] for m in range(4)] and flip == [want_f[m] for m in range(4)]
+    for m in range(4):
+        assert (tuple(item_box[m]), plans[m], gray[m], flip[m]) == want[m], m
+    assert any(len(p) == 4 for p in plans) and all(sorted(op for op, _ in p) == [1, 2, 3, 4] for p in plans if p)
+    with pytest.raises(NotImplementedError):
+        TwoViewInputStage(blur_p=0.5)
     with pytest.raises(ValueError):
         ImageBatch([np.zeros((4, 4), dtype=np.uint8)], device="cpu")
+
+
+def hue_shift(hue_factor):
+    """np.uint8(hue_factor * 255) of paddle's adjust_hue: truncation toward zero, then wrap"""
+    return int(hue_factor * 255) & 255
+
+
+def jitter_cases(seed=3, items=6, S=24):
+    """random views + a 4-op plan per view (shuffled order, some ops absent) -> (img u8 [items,S,S,3], ops, factors, plan)"""
+    import random
+    rng, r = np.random.RandomState(seed), random.Random(seed)
+    img = rng.randint(0, 256, size=(items, S, S, 3)).astype(np.uint8)
+    img[1, : S // 2] //= 5
+    img[2] = 200                                                                       # flat view: grey -> hue / saturation no-ops
+    ops, factors, plan = np.zeros((items, 4), dtype=np.int32), np.zeros((items, 4), dtype=np.float32), []
+    for m in range(items):
+        order = [1, 2, 3, 4]
+        r.shuffle(order)
+        if m == 4:
+            order = [2, 0, 2, 0]                                                       # contrast twice: the mean must be re-taken
+        row = []
+        for pos, op in enumerate(order):
+            f = r.uniform(-0.1, 0.1) if op == 4 else r.uniform(0.6, 1.4)
+            if m == 5 and pos == 0:
+                f = 1.9 if op != 4 else 0.5                                            # extrapolating blend -> clipping branch
+            ops[m, pos] = op
+            factors[m, pos] = hue_shift(f) if op == 4 else f
+            row.append((op, f))
+        plan.append(row)
+    return img, ops, factors, plan
+
+
+def oracle_jitter(view, row):
+    for op, f in row:
+        if op == 1:
+            view = O.adjust_brightness(view, float(np.float32(f)))
+        elif op == 2:
+            view = O.adjust_contrast(view, float(np.float32(f)))
+        elif op == 3:
+            view = O.adjust_saturation(view, float(np.float32(f)))
+        elif op == 4:
+            view = O.adjust_hue(view, f)
+    return view
+
+
+def test_host_build_of_colour_jitter_bodies(hostlib):
+    v = np.arange(1 << 24, dtype=np.uint32)
+    cube = np.ascontiguousarray(np.stack([(v >> 16) & 255, (v >> 8) & 255, v & 255], -1).astype(np.uint8))
+    out = np.empty_like(cube)
+    hostlib.host_rgb_to_hsv(_p(cube), _p(out), ctypes.c_longlong(cube.shape[0]))
+    assert np.array_equal(out.reshape(4096, 4096, 3), np.asarray(Image.fromarray(cube.reshape(4096, 4096, 3), "RGB").convert("HSV")))
+    hostlib.host_hsv_to_rgb(_p(cube), _p(out), ctypes.c_longlong(cube.shape[0]))
+    assert np.array_equal(out.reshape(4096, 4096, 3), np.asarray(Image.fromarray(cube.reshape(4096, 4096, 3), "HSV").convert("RGB")))
+    img, ops, factors, plan = jitter_cases()
+    got = img.copy()
+    hostlib.host_color_jitter_u8(_p(got), _p(ops), _p(factors), img.shape[0], img.shape[1])
+    for m in range(img.shape[0]):
+        assert np.array_equal(got[m], oracle_jitter(img[m], plan[m])), (m, plan[m])
+    assert not np.array_equal(got[0], img[0]) and np.array_equal(got[2][..., 0], got[2][..., 1])

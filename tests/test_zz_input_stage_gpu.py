@@ -57,21 +57,40 @@ def test_bad_box_is_refused_on_the_host_and_flagged_on_the_device():
 def test_two_view_stage_end_to_end():
     """N images -> (view_1, view_2); every view equals the oracle applied with the decisions the stage drew."""
     import oracle.input_stage as O
+    from test_input_stage_host_cpu import oracle_jitter
     from passl_b200.data import ImageBatch, TwoViewInputStage
     rng = np.random.RandomState(5)
     images = [rng.randint(0, 256, size=(int(h), int(w), 3)).astype(np.uint8) for h, w in [(240, 320), (333, 250), (128, 128), (96, 400)]]
-    stage = TwoViewInputStage(size=64, scale=(0.2, 1.0), interpolation="bicubic", rng=random.Random(11))
-    twin = TwoViewInputStage(size=64, scale=(0.2, 1.0), interpolation="bicubic", rng=random.Random(11))
+    stage = TwoViewInputStage(size=64, scale=(0.2, 1.0), interpolation="bicubic", jitter_p=0.6, rng=random.Random(11))
+    twin = TwoViewInputStage(size=64, scale=(0.2, 1.0), interpolation="bicubic", jitter_p=0.6, rng=random.Random(11))
     batch = ImageBatch(images)
     v1, v2 = stage(batch)
-    item_img, item_box, gray, flip = twin.draw(batch)
+    item_img, item_box, gray, flip, plans = twin.draw(batch)
+    assert any(plans) and not all(plans)                                            # some views jittered, some not (jitter_p 0.6)
     assert v1.shape == (4, 3, 64, 64) and v2.shape == (4, 3, 64, 64) and v1.dtype == torch.float32
     both = torch.cat([v1, v2]).cpu().numpy()
     for m, (n, (i, j, h, w)) in enumerate(zip(item_img, item_box)):
-        img = O.resized_crop_u8(images[n], i, j, h, w, 64, "bicubic")
+        img = oracle_jitter(O.resized_crop_u8(images[n], i, j, h, w, 64, "bicubic"), plans[m])
         if gray[m]:
             img = O.grayscale3_u8(img)
         if flip[m]:
             img = O.hflip_u8(img)
         assert np.array_equal(both[m], O.transpose_normalize(img)), m
     assert not np.array_equal(both[0], both[4])                                   # two different views of sample 0
+
+
+def test_colour_jitter_kernels_match_the_oracle():
+    """ColorJitter through the C ABI: shuffled op orders, contrast twice (mean re-taken), extrapolating blend, flat grey view."""
+    from test_input_stage_host_cpu import jitter_cases, oracle_jitter
+    from passl_b200.data import color_jitter_u8
+    img, ops, factors, plan = jitter_cases()
+    dev = torch.from_numpy(img.copy()).cuda()
+    got = color_jitter_u8(dev, [[(op, f) for op, f in row if op] for row in plan]).cpu().numpy()
+    for m in range(img.shape[0]):
+        assert np.array_equal(got[m], oracle_jitter(img[m], [(op, f) for op, f in plan[m] if op])), (m, plan[m])
+    assert not np.array_equal(got[0], img[0])
+    big = torch.randint(0, 256, (3, 224, 224, 3), dtype=torch.uint8, device="cuda")   # several blocks per view: exact luma sums
+    ref = big.cpu().numpy()
+    out = color_jitter_u8(big.clone(), [[(2, 1.3)], [], [(3, 0.7), (2, 0.8)]]).cpu().numpy()
+    assert np.array_equal(out[1], ref[1])
+    assert np.array_equal(out[0], oracle_jitter(ref[0], [(2, 1.3)])) and np.array_equal(out[2], oracle_jitter(ref[2], [(3, 0.7), (2, 0.8)]))
