@@ -211,3 +211,37 @@ def adjust_hue(img, hue_factor):
     shift = np.array(hue_factor * 255).astype(np.int64).astype(np.uint8)       # np.uint8(float): C cast, negative values wrap
     hsv[..., 0] = hsv[..., 0] + shift
     return hsv_to_rgb_u8(hsv)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# GaussianBlur (transforms.py:173-191, default path): cv2.GaussianBlur(np.array(x), (23, 23), sigma), sigma ~ np.random.uniform.
+# For uint8 images OpenCV runs its "bit-exact" fixed-point filter (imgproc/src/smooth.dispatch.cpp, smooth.simd.hpp,
+# fixedpoint.inl.hpp; OpenCV 4.13 in this image): the normalised Gaussian taps are turned into 8.8 fixed point by error diffusion
+# from the edge inwards with the centre tap taking the remainder (taps sum to exactly 256), the horizontal pass keeps 8.8 results
+# unrounded, the vertical pass rounds once: (sum + 2^15) >> 16; borders are BORDER_REFLECT_101.  Restated below and pinned against
+# cv2.GaussianBlur itself over thousands of sigmas in [0.1, 2] (tests/test_oracle_input_stage_cpu.py).
+# ---------------------------------------------------------------------------------------------------------------------------------
+def gaussian_taps_fixed(ksize, sigma, bits=8):
+    half = (ksize - 1) // 2
+    scale = -0.5 / (sigma * sigma)
+    vals = [math.exp(scale * float((i - half) ** 2)) for i in range(half)]
+    norm = 1.0 / (2.0 * sum(vals) + 1.0)
+    taps, err, total = [0] * ksize, 0.0, 0
+    for i in range(half):
+        adj = vals[i] * norm * float(1 << bits) + err
+        q = int(round(adj))                                      # cvRound: ties to even, like Python's round()
+        err = adj - q
+        taps[i] = taps[ksize - 1 - i] = q
+        total += q
+    taps[half] = (1 << bits) - 2 * total
+    return np.array(taps, dtype=np.int64)
+
+
+def gaussian_blur_u8(img, ksize, sigma):
+    k = gaussian_taps_fixed(ksize, sigma)
+    r = ksize // 2
+    H, W = img.shape[:2]
+    pad = np.pad(img.astype(np.int64), ((r, r), (r, r), (0, 0)), mode="reflect")      # numpy 'reflect' = BORDER_REFLECT_101
+    hres = sum(k[i] * pad[:, i:i + W] for i in range(ksize))
+    out = sum(k[j] * hres[j:j + H] for j in range(ksize))
+    return ((out + (1 << 15)) >> 16).astype(np.uint8)

@@ -96,3 +96,19 @@ def test_colour_jitter_ops_match_pillow_enhancers():
                 np_h += np.array(hf * 255).astype(np.uint8)
             want = Image.merge("HSV", (Image.fromarray(np_h, "L"), s, v)).convert("RGB")
             assert np.array_equal(O.adjust_hue(img, hf), np.asarray(want)), hf
+
+
+def test_gaussian_blur_is_opencv_bit_exact():
+    cv2 = pytest.importorskip("cv2")
+    rng, r = np.random.RandomState(0), random.Random(0)
+    sigmas = [0.1, 2.0, 0.1000001, 1.9999999, 0.5, 1.0, 1.5, 0.25, 0.75, 0.3, 1.2] + [r.uniform(0.1, 2.0) for _ in range(1500)]
+    for sigma in sigmas:
+        img = rng.randint(0, 256, size=(24, 25, 3)).astype(np.uint8)
+        assert np.array_equal(O.gaussian_blur_u8(img, 23, sigma), cv2.GaussianBlur(img, (23, 23), sigma)), repr(sigma)
+    img = rng.randint(0, 256, size=(224, 224, 3)).astype(np.uint8)
+    img[:100] = (img[:100] // 128) * 255
+    for sigma in (0.1, 0.77, 2.0):
+        assert np.array_equal(O.gaussian_blur_u8(img, 23, sigma), cv2.GaussianBlur(img, (23, 23), sigma))
+    for sigma in (0.1, 0.9, 2.0):
+        taps = O.gaussian_taps_fixed(23, sigma)
+        assert taps.sum() == 256 and (taps >= 0).all() and np.array_equal(taps, taps[::-1])
