@@ -345,11 +345,20 @@ int passl_b200_views_finalize_f32(const void* img, const int* gray, const int* f
 /*   color_jitter_u8     ColorJitter (configs/simclr/simclr_r50_IM.yaml:41-48; paddle.vision over Pillow): per view up to four ops
  *                       in the order the host drew, in place on uint8 [items, S, S, 3].  ops int32 [items][4]: 0 none, 1 brightness,
  *                       2 contrast, 3 saturation (ImageEnhance blends, libImaging/Blend.c), 4 hue (HSV round trip of Convert.c with
- *                       the H plane shifted).  factors fp32 [items][4]: the blend factor, or for hue the shift
- *                       uint8(hue_factor * 255) the host computed.  workspace >= 8 * items bytes (exact luma sums for the contrast
- *                       mean); contrast_positions: bit p set when some view has contrast at position p (0xF is always safe). */
+ *                       the H plane shifted), 5 grayscale (convert('L') replicated; for views that are blurred afterwards).
+ *                       factors fp32 [items][4]: the blend factor, or for hue the shift uint8(hue_factor * 255) the host computed.
+ *                       workspace >= 8 * items bytes (exact luma sums for the contrast mean); contrast_positions: bit p set when
+ *                       some view has contrast at position p (0xF is always safe). */
 int passl_b200_color_jitter_u8(void* img, const int* ops, const float* factors, void* workspace, long long workspace_bytes, int items,
                                int size, int contrast_positions, void* stream);
+/*   gaussian_blur_u8    GaussianBlur (transforms.py:173-191: cv2.GaussianBlur(x, (23, 23), sigma) on uint8): OpenCV's fixed-point
+ *                       filter, in place on uint8 [items, S, S, 3].  taps int32 [items][ksize]: the 8.8 fixed-point Gaussian row of
+ *                       each view (sum 256; computed on the host from its sigma, passl_b200.data.gaussian_taps_fixed); apply int32
+ *                       [items]: 0 leaves the view untouched.  Borders BORDER_REFLECT_101, one rounding at the end
+ *                       ((sum + 2^15) >> 16).  workspace >= gaussian_blur_workspace_bytes (16-bit intermediate). */
+long long passl_b200_gaussian_blur_workspace_bytes(int items, int size);
+int passl_b200_gaussian_blur_u8(void* img, const int* taps, const int* apply, void* workspace, long long workspace_bytes, int items,
+                                int size, int ksize, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Developer probe (not a reference entry point): one tcgen05.mma over a row-shifted view of a SWIZZLE_128B tile, used by

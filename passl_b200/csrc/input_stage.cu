@@ -137,6 +137,25 @@ __global__ void jitter_apply_kernel(unsigned char* __restrict__ img, const int* 
     jitter_pixel(base + 3 * i, op, factor, mean);
 }
 
+// ---- GaussianBlur: per view a host-computed 8.8 tap row (or apply[m] == 0); two passes with a 16-bit intermediate ---------------
+__global__ void blur_h_kernel(const unsigned char* __restrict__ img, const int* __restrict__ taps, const int* __restrict__ apply,
+                              unsigned short* __restrict__ tmp16, int S, int ksize) {
+  const int m = blockIdx.y;
+  if (!apply[m]) return;
+  const long long n = (long long)S * S;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    blur_h_pixel(img, taps + (long long)m * ksize, tmp16, m, (int)(i / S), (int)(i % S), S, ksize);
+}
+
+__global__ void blur_v_kernel(const unsigned short* __restrict__ tmp16, const int* __restrict__ taps, const int* __restrict__ apply,
+                              unsigned char* __restrict__ img, int S, int ksize) {
+  const int m = blockIdx.y;
+  if (!apply[m]) return;
+  const long long n = (long long)S * S;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    blur_v_pixel(tmp16, taps + (long long)m * ksize, img, m, (int)(i / S), (int)(i % S), S, ksize);
+}
+
 static inline int grid_for(long long total, int block) {
   long long blocks = (total + block - 1) / block;
   const long long cap = 148LL * 32;
@@ -234,5 +253,27 @@ extern "C" int passl_b200_color_jitter_u8(void* img, const int* ops, const float
     jitter_apply_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<unsigned char*>(img), ops, factors, sums, size, pos);
     PB_LAUNCH_CHECK();
   }
+  return PB_OK;
+}
+
+extern "C" long long passl_b200_gaussian_blur_workspace_bytes(int items, int size) {
+  if (items <= 0 || size <= 0) return 0;
+  return (long long)items * size * size * 3 * (long long)sizeof(unsigned short);
+}
+
+extern "C" int passl_b200_gaussian_blur_u8(void* img, const int* taps, const int* apply, void* workspace, long long workspace_bytes,
+                                           int items, int size, int ksize, void* stream) {
+  if (items <= 0 || size <= 0 || ksize < 1 || !(ksize & 1) || !img || !taps || !apply || !workspace) return PB_ERR_BAD_ARG;
+  if (workspace_bytes < passl_b200_gaussian_blur_workspace_bytes(items, size)) return PB_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n = (long long)size * size;
+  int bx = (int)((n + 255) / 256);
+  if (bx > 64) bx = 64;
+  const dim3 grid(bx, items);
+  unsigned short* tmp16 = reinterpret_cast<unsigned short*>(workspace);
+  blur_h_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const unsigned char*>(img), taps, apply, tmp16, size, ksize);
+  PB_LAUNCH_CHECK();
+  blur_v_kernel<<<grid, 256, 0, st>>>(tmp16, taps, apply, reinterpret_cast<unsigned char*>(img), size, ksize);
+  PB_LAUNCH_CHECK();
   return PB_OK;
 }

@@ -187,7 +187,7 @@ PB_HD float rnf_mul(float a, float b) { return a * b; }
 PB_HD float rnf_div(float a, float b) { return a / b; }
 #endif
 
-enum JitterOp : int { JIT_NONE = 0, JIT_BRIGHTNESS = 1, JIT_CONTRAST = 2, JIT_SATURATION = 3, JIT_HUE = 4 };
+enum JitterOp : int { JIT_NONE = 0, JIT_BRIGHTNESS = 1, JIT_CONTRAST = 2, JIT_SATURATION = 3, JIT_HUE = 4, JIT_GRAY = 5 };
 
 // Blend.c: out = a + alpha (b - a) in float32, truncated; clipped when alpha lies outside [0, 1] (a = degenerate, b = image)
 PB_HD unsigned char blend_byte(int a, int b, float alpha) {
@@ -277,7 +277,54 @@ PB_HD void jitter_pixel(unsigned char* p, int op, float factor, int mean) {
     h = (h + (int)factor) & 255;
     hsv_to_rgb(h, s, v, &r, &g, &b);
     p[0] = (unsigned char)r; p[1] = (unsigned char)g; p[2] = (unsigned char)b;
+  } else if (op == JIT_GRAY) {                                    // RandomGrayscale when it has to run before the blur
+    p[0] = p[1] = p[2] = (unsigned char)luma_byte(r, g, b);
   }
+}
+
+// ---- GaussianBlur (transforms.py:173-191 -> cv2.GaussianBlur on uint8): OpenCV's fixed-point filter.  Taps are 8.8 fixed point
+// (sum exactly 256, computed on the host), the horizontal pass keeps unrounded 8.8 values (<= 255 * 256 fits 16 bits), the vertical
+// pass rounds once: (sum + 2^15) >> 16.  Borders: BORDER_REFLECT_101 (cv::borderInterpolate).
+PB_HD int reflect101(int p, int len) {
+  if (len == 1) return 0;
+  while ((unsigned)p >= (unsigned)len) p = p < 0 ? -p : 2 * len - 2 - p;
+  return p;
+}
+
+// horizontal pass, one pixel: tmp16[m][y][x][c] = sum_i taps[i] * img[m][y][reflect(x + i - r)][c]
+PB_HD void blur_h_pixel(const unsigned char* img, const int* taps, unsigned short* tmp16, int m, int y, int x, int S, int ksize) {
+  const int r = ksize / 2;
+  const unsigned char* row = img + ((long long)m * S + y) * S * 3;
+  int a0 = 0, a1 = 0, a2 = 0;
+  for (int i = 0; i < ksize; ++i) {
+    const unsigned char* p = row + 3 * reflect101(x + i - r, S);
+    const int w = taps[i];
+    a0 += w * p[0];
+    a1 += w * p[1];
+    a2 += w * p[2];
+  }
+  unsigned short* o = tmp16 + (((long long)m * S + y) * S + x) * 3;
+  o[0] = (unsigned short)a0;
+  o[1] = (unsigned short)a1;
+  o[2] = (unsigned short)a2;
+}
+
+// vertical pass, one pixel: img[m][y][x][c] = (sum_j taps[j] * tmp16[m][reflect(y + j - r)][x][c] + 2^15) >> 16
+PB_HD void blur_v_pixel(const unsigned short* tmp16, const int* taps, unsigned char* img, int m, int y, int x, int S, int ksize) {
+  const int r = ksize / 2;
+  const unsigned short* base = tmp16 + (long long)m * S * S * 3 + (long long)x * 3;
+  unsigned int a0 = 0, a1 = 0, a2 = 0;
+  for (int j = 0; j < ksize; ++j) {
+    const unsigned short* p = base + (long long)reflect101(y + j - r, S) * S * 3;
+    const unsigned int w = (unsigned int)taps[j];
+    a0 += w * p[0];
+    a1 += w * p[1];
+    a2 += w * p[2];
+  }
+  unsigned char* o = img + (((long long)m * S + y) * S + x) * 3;
+  o[0] = (unsigned char)((a0 + (1u << 15)) >> 16);
+  o[1] = (unsigned char)((a1 + (1u << 15)) >> 16);
+  o[2] = (unsigned char)((a2 + (1u << 15)) >> 16);
 }
 
 }  // namespace istage

@@ -175,28 +175,78 @@ def color_jitter_u8(views_u8, plans):
     return views_u8
 
 
+def grayscale_u8(views_u8, flags):
+    """In-place RandomGrayscale (convert('L') replicated) of the flagged views — used when a grey view is blurred afterwards; views
+    that are not blurred get their grayscale in views_finalize."""
+    return color_jitter_u8(views_u8, [[(5, 0.0)] if f else [] for f in flags])
+
+
+def gaussian_taps_fixed(ksize, sigma):
+    """The 8.8 fixed-point tap row OpenCV's uint8 GaussianBlur uses for (ksize, sigma): normalised exp(-x^2 / 2 sigma^2) taps scaled
+    by 256 and rounded by error diffusion from the edge inwards (ties to even), the centre tap taking the remainder so that the row
+    sums to exactly 256 (imgproc/src/smooth.dispatch.cpp getGaussianKernelFixedPoint_ED).  Checked against cv2.GaussianBlur in the tests."""
+    if ksize < 1 or ksize % 2 == 0 or not sigma > 0:
+        raise ValueError("ksize must be odd and sigma positive, got %r, %r" % (ksize, sigma))
+    half = (ksize - 1) // 2
+    scale = -0.5 / (sigma * sigma)
+    weights = [math.exp(scale * float((i - half) ** 2)) for i in range(half)]
+    norm = 1.0 / (2.0 * sum(weights) + 1.0)
+    taps, carry, used = [0] * ksize, 0.0, 0
+    for i, w in enumerate(weights):
+        exact = w * norm * 256.0 + carry
+        q = int(round(exact))
+        carry = exact - q
+        taps[i] = taps[ksize - 1 - i] = q
+        used += q
+    taps[half] = 256 - 2 * used
+    return taps
+
+
+def gaussian_blur_u8(views_u8, sigmas, ksize=23):
+    """In-place cv2-exact GaussianBlur of uint8 [items, S, S, 3] views; sigmas[m] = None leaves view m untouched."""
+    if not views_u8.is_cuda:
+        raise _lib.PasslB200Error("passl_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    lib = _lib.load()
+    items, S = views_u8.shape[0], views_u8.shape[1]
+    assert views_u8.dtype == torch.uint8 and views_u8.shape == (items, S, S, 3) and views_u8.is_contiguous() and len(sigmas) == items
+    if all(sg is None for sg in sigmas):
+        return views_u8
+    dev = views_u8.device
+    taps = torch.tensor([gaussian_taps_fixed(ksize, sg) if sg is not None else [0] * ksize for sg in sigmas], dtype=torch.int32, device=dev)
+    apply = torch.tensor([int(sg is not None) for sg in sigmas], dtype=torch.int32, device=dev)
+    nbytes = lib.passl_b200_gaussian_blur_workspace_bytes(items, S)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    _lib.check(lib.passl_b200_gaussian_blur_u8(views_u8.data_ptr(), taps.data_ptr(), apply.data_ptr(), ws.data_ptr(), nbytes, items, S,
+                                               ksize, _stream()), "gaussian_blur_u8")
+    return views_u8
+
+
 class TwoViewInputStage:
     """`(view_1, view_2) = stage(images)`: both fp32 [N, 3, size, size] on the device, ready for MoCo / SimCLR `train_iter`."""
 
     def __init__(self, size=224, scale=(0.08, 1.0), ratio=(3. / 4., 4. / 3.), interpolation="bilinear", jitter_p=0.0,
-                 brightness=0.4, contrast=0.4, saturation=0.4, hue=0.1, gray_p=0.2, blur_p=0.0, flip_p=0.5,
-                 norm_scale=1.0 / 255.0, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225), rng=random):
+                 brightness=0.4, contrast=0.4, saturation=0.4, hue=0.1, gray_p=0.2, blur_p=0.0, blur_sigma=(0.1, 2.0), blur_ksize=23,
+                 flip_p=0.5, norm_scale=1.0 / 255.0, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225), rng=random, np_rng=None):
         """SimCLR recipe (configs/simclr/simclr_r50_IM.yaml:35-61): scale=(0.1, 1), interpolation='bicubic', jitter_p=0.8, gray_p=0.2,
-        flip_p=0.5 (and blur_p=0.5, which is not built); MoCo v2 / CLIP recipes use the defaults with their own scale."""
-        if blur_p:
-            raise NotImplementedError("GaussianBlur (cv2.GaussianBlur with a 23x23 kernel, transforms.py:173-191) is not built")
+        blur_p=0.5, flip_p=0.5; MoCo v2 / CLIP recipes use the defaults with their own scale.  `rng` plays Python's `random` module,
+        `np_rng` numpy's (the reference draws the blur sigma with np.random.uniform, transforms.py:182)."""
+        import numpy as np
         self.size, self.scale, self.ratio, self.interpolation = size, tuple(scale), tuple(ratio), interpolation
         self.jitter_p, self.jitter = jitter_p, dict(brightness=brightness, contrast=contrast, saturation=saturation, hue=hue)
-        self.gray_p, self.flip_p, self.norm_scale, self.mean, self.std, self.rng = gray_p, flip_p, norm_scale, mean, std, rng
+        self.gray_p, self.blur_p, self.blur_sigma, self.blur_ksize, self.flip_p = gray_p, blur_p, tuple(blur_sigma), blur_ksize, flip_p
+        self.norm_scale, self.mean, self.std, self.rng, self.np_rng = norm_scale, mean, std, rng, (np_rng if np_rng is not None else np.random)
 
     def _draw_view(self):
-        """RandomApply(ColorJitter) -> RandomGrayscale -> RandomHorizontalFlip decisions of one view, in pipeline order."""
-        rng, plan = self.rng, []
-        if self.jitter_p and not (self.jitter_p < rng.random()):         # RandomApply: `if self.p < random.random(): return img`
+        """RandomApply(ColorJitter) -> RandomGrayscale -> RandomApply(GaussianBlur) -> RandomHorizontalFlip decisions of one view, in
+        pipeline order.  RandomApply skips when `p < random.random()` (transforms.py:138-143)."""
+        rng, plan, sigma = self.rng, [], None
+        if self.jitter_p and not (self.jitter_p < rng.random()):
             plan = color_jitter_plan(rng=rng, **self.jitter)
         gray = rng.random() < self.gray_p
+        if self.blur_p and not (self.blur_p < rng.random()):
+            sigma = float(self.np_rng.uniform(self.blur_sigma[0], self.blur_sigma[1]))
         flip = rng.random() < self.flip_p
-        return plan, gray, flip
+        return plan, gray, sigma, flip
 
     def draw(self, batch):
         """Host-side random decisions for one batch -> (item_img, item_box, gray, flip, plans); views of sample n are items n and
@@ -210,13 +260,22 @@ class TwoViewInputStage:
             d1.append(self._draw_view())
             d2.append(self._draw_view())
         both = d1 + d2
-        return list(range(N)) * 2, box1 + box2, [d[1] for d in both], [d[2] for d in both], [d[0] for d in both]
+        self.last_sigmas = [d[2] for d in both]
+        return list(range(N)) * 2, box1 + box2, [d[1] for d in both], [d[3] for d in both], [d[0] for d in both]
 
     def __call__(self, images):
         batch = images if isinstance(images, ImageBatch) else ImageBatch(images)
         item_img, item_box, gray, flip, plans = self.draw(batch)
         u8 = resized_crop_u8(batch, item_img, item_box, self.size, self.interpolation)
         u8 = color_jitter_u8(u8, plans)
+        # grayscale sits between jitter and blur in the recipe; it commutes with nothing after it, so it is applied here when a
+        # blurred view is also grey, and left to the finalize kernel otherwise
+        if any(sg is not None for sg in self.last_sigmas):
+            pre_gray = [g and sg is not None for g, sg in zip(gray, self.last_sigmas)]
+            if any(pre_gray):
+                u8 = grayscale_u8(u8, pre_gray)
+                gray = [g and not p for g, p in zip(gray, pre_gray)]
+            u8 = gaussian_blur_u8(u8, self.last_sigmas, self.blur_ksize)
         out = views_finalize(u8, gray, flip, self.norm_scale, self.mean, self.std)
         N = len(batch)
         return out[:N], out[N:]

@@ -85,3 +85,17 @@ extern "C" void host_hsv_to_rgb(const unsigned char* in, unsigned char* out, lon
     out[3 * i] = (unsigned char)r; out[3 * i + 1] = (unsigned char)g; out[3 * i + 2] = (unsigned char)b;
   }
 }
+
+extern "C" void host_gaussian_blur_u8(unsigned char* img, const int* taps, const int* apply, int items, int S, int ksize) {
+  std::vector<unsigned short> tmp16((size_t)items * S * S * 3);
+  for (int m = 0; m < items; ++m) {
+    if (!apply[m]) continue;
+    for (int y = 0; y < S; ++y)
+      for (int x = 0; x < S; ++x) blur_h_pixel(img, taps + (long long)m * ksize, tmp16.data(), m, y, x, S, ksize);
+  }
+  for (int m = 0; m < items; ++m) {
+    if (!apply[m]) continue;
+    for (int y = 0; y < S; ++y)
+      for (int x = 0; x < S; ++x) blur_v_pixel(tmp16.data(), taps + (long long)m * ksize, img, m, y, x, S, ksize);
+  }
+}

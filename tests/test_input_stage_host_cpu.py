@@ -108,9 +108,9 @@ def test_product_sampler_and_draw_order():
     images = [np.zeros((h, w, 3), dtype=np.uint8) for h, w in [(240, 320), (100, 50)]]
     batch = ImageBatch(images, device="cpu")
     assert batch.src_off.tolist() == [0, 240 * 320 * 3] and batch.data.numel() == 240 * 320 * 3 + 100 * 50 * 3
-    stage = TwoViewInputStage(size=64, jitter_p=0.8, rng=random.Random(3))
+    stage = TwoViewInputStage(size=64, jitter_p=0.8, blur_p=0.7, rng=random.Random(3), np_rng=np.random.RandomState(8))
     item_img, item_box, gray, flip, plans = stage.draw(batch)
-    r = random.Random(3)
+    r, nr = random.Random(3), np.random.RandomState(8)
 
     def view():                                          # RandomApply(ColorJitter) -> RandomGrayscale -> RandomHorizontalFlip
         plan = []
@@ -120,17 +120,18 @@ def test_product_sampler_and_draw_order():
             for name, v in slots:
                 lo, hi = (-v, v) if name == "hue" else (max(0.0, 1 - v), 1 + v)
                 plan.append(({"brightness": 1, "contrast": 2, "saturation": 3, "hue": 4}[name], r.uniform(lo, hi)))
-        return plan, r.random() < 0.2, r.random() < 0.5
+        g = r.random() < 0.2
+        sigma = float(nr.uniform(0.1, 2.0)) if not (0.7 < r.random()) else None       # RandomApply(GaussianBlur) + np.random sigma
+        return plan, g, r.random() < 0.5, sigma
     want = {}
     for n, (h, w) in enumerate([(240, 320), (100, 50)]):
         b1, b2 = random_resized_crop_params(w, h, rng=r), random_resized_crop_params(w, h, rng=r)
         want[n], want[2 + n] = (b1,) + view(), (b2,) + view()
     assert item_img == [0, 1, 0, 1]
     for m in range(4):
-        assert (tuple(item_box[m]), plans[m], gray[m], flip[m]) == want[m], m
+        assert (tuple(item_box[m]), plans[m], gray[m], flip[m], stage.last_sigmas[m]) == want[m], m
+    assert any(sg is not None for sg in stage.last_sigmas) and any(sg is None for sg in stage.last_sigmas)
     assert any(len(p) == 4 for p in plans) and all(sorted(op for op, _ in p) == [1, 2, 3, 4] for p in plans if p)
-    with pytest.raises(NotImplementedError):
-        TwoViewInputStage(blur_p=0.5)
     with pytest.raises(ValueError):
         ImageBatch([np.zeros((4, 4), dtype=np.uint8)], device="cpu")
 
@@ -192,3 +193,33 @@ def test_host_build_of_colour_jitter_bodies(hostlib):
     for m in range(img.shape[0]):
         assert np.array_equal(got[m], oracle_jitter(img[m], plan[m])), (m, plan[m])
     assert not np.array_equal(got[0], img[0]) and np.array_equal(got[2][..., 0], got[2][..., 1])
+
+
+def test_host_build_of_gaussian_blur_bodies_is_opencv_exact(hostlib):
+    cv2 = pytest.importorskip("cv2")
+    import random
+    from passl_b200.data import gaussian_taps_fixed
+    rng, r = np.random.RandomState(2), random.Random(2)
+    for S in (24, 64):
+        items = 5
+        img = rng.randint(0, 256, size=(items, S, S, 3)).astype(np.uint8)
+        img[1, : S // 2] = (img[1, : S // 2] // 128) * 255
+        sigmas = [0.1, 2.0, None, r.uniform(0.1, 2.0), r.uniform(0.1, 2.0)]
+        for sg in sigmas:
+            if sg is not None:
+                assert gaussian_taps_fixed(23, sg) == [int(v) for v in O.gaussian_taps_fixed(23, sg)]
+        taps = np.array([gaussian_taps_fixed(23, sg) if sg is not None else [0] * 23 for sg in sigmas], dtype=np.int32)
+        apply = np.array([int(sg is not None) for sg in sigmas], dtype=np.int32)
+        got = img.copy()
+        hostlib.host_gaussian_blur_u8(_p(got), _p(taps), _p(apply), items, S, 23)
+        for m, sg in enumerate(sigmas):
+            want = img[m] if sg is None else cv2.GaussianBlur(img[m], (23, 23), sg)
+            assert np.array_equal(got[m], want), (S, m, sg)
+    # a view narrower than the kernel radius: repeated reflection like cv::borderInterpolate
+    small = rng.randint(0, 256, size=(1, 7, 7, 3)).astype(np.uint8)
+    taps = np.array([gaussian_taps_fixed(23, 1.7)], dtype=np.int32)
+    got = small.copy()
+    hostlib.host_gaussian_blur_u8(_p(got), _p(taps), _p(np.array([1], dtype=np.int32)), 1, 7, 23)
+    assert np.array_equal(got[0], cv2.GaussianBlur(small[0], (23, 23), 1.7))
+    with pytest.raises(ValueError):
+        gaussian_taps_fixed(22, 1.0)

@@ -61,18 +61,23 @@ def test_two_view_stage_end_to_end():
     from passl_b200.data import ImageBatch, TwoViewInputStage
     rng = np.random.RandomState(5)
     images = [rng.randint(0, 256, size=(int(h), int(w), 3)).astype(np.uint8) for h, w in [(240, 320), (333, 250), (128, 128), (96, 400)]]
-    stage = TwoViewInputStage(size=64, scale=(0.2, 1.0), interpolation="bicubic", jitter_p=0.6, rng=random.Random(11))
-    twin = TwoViewInputStage(size=64, scale=(0.2, 1.0), interpolation="bicubic", jitter_p=0.6, rng=random.Random(11))
+    kw = dict(size=64, scale=(0.2, 1.0), interpolation="bicubic", jitter_p=0.6, gray_p=0.5, blur_p=0.5)
+    stage = TwoViewInputStage(rng=random.Random(11), np_rng=np.random.RandomState(4), **kw)
+    twin = TwoViewInputStage(rng=random.Random(11), np_rng=np.random.RandomState(4), **kw)
     batch = ImageBatch(images)
     v1, v2 = stage(batch)
     item_img, item_box, gray, flip, plans = twin.draw(batch)
     assert any(plans) and not all(plans)                                            # some views jittered, some not (jitter_p 0.6)
+    sig = twin.last_sigmas
+    assert any(s_ is not None and g for s_, g in zip(sig, gray)) and any(s_ is None and g for s_, g in zip(sig, gray))
     assert v1.shape == (4, 3, 64, 64) and v2.shape == (4, 3, 64, 64) and v1.dtype == torch.float32
     both = torch.cat([v1, v2]).cpu().numpy()
     for m, (n, (i, j, h, w)) in enumerate(zip(item_img, item_box)):
         img = oracle_jitter(O.resized_crop_u8(images[n], i, j, h, w, 64, "bicubic"), plans[m])
         if gray[m]:
             img = O.grayscale3_u8(img)
+        if twin.last_sigmas[m] is not None:                                       # pipeline order: jitter, grayscale, blur, flip
+            img = O.gaussian_blur_u8(img, 23, twin.last_sigmas[m])
         if flip[m]:
             img = O.hflip_u8(img)
         assert np.array_equal(both[m], O.transpose_normalize(img)), m
@@ -94,3 +99,18 @@ def test_colour_jitter_kernels_match_the_oracle():
     out = color_jitter_u8(big.clone(), [[(2, 1.3)], [], [(3, 0.7), (2, 0.8)]]).cpu().numpy()
     assert np.array_equal(out[1], ref[1])
     assert np.array_equal(out[0], oracle_jitter(ref[0], [(2, 1.3)])) and np.array_equal(out[2], oracle_jitter(ref[2], [(3, 0.7), (2, 0.8)]))
+
+
+def test_gaussian_blur_kernels_match_the_oracle():
+    """cv2.GaussianBlur's fixed-point uint8 path through the C ABI: several sigmas, an untouched view, reflect-101 borders."""
+    import oracle.input_stage as O
+    from passl_b200.data import gaussian_blur_u8
+    rng = np.random.RandomState(6)
+    for S in (24, 224):
+        img = rng.randint(0, 256, size=(4, S, S, 3)).astype(np.uint8)
+        img[1, : S // 2] = (img[1, : S // 2] // 128) * 255
+        sigmas = [0.1, 2.0, None, 0.8371]
+        got = gaussian_blur_u8(torch.from_numpy(img.copy()).cuda(), sigmas).cpu().numpy()
+        for m, sg in enumerate(sigmas):
+            want = img[m] if sg is None else O.gaussian_blur_u8(img[m], 23, sg)
+            assert np.array_equal(got[m], want), (S, m)
