@@ -83,6 +83,8 @@ def resized_crop_u8(batch, item_img, item_box, size=224, interpolation="bilinear
     for n, (t, l, h, w) in zip(item_img, item_box):
         if not (0 <= n < len(batch)) or h <= 0 or w <= 0 or t < 0 or l < 0 or t + h > batch.heights[n] or l + w > batch.widths[n]:
             raise ValueError("crop box (top=%d, left=%d, h=%d, w=%d) does not lie inside image %d" % (t, l, h, w, n))
+    if interpolation not in INTERPOLATION:
+        raise NotImplementedError("interpolation %r (built: %s)" % (interpolation, sorted(INTERPOLATION)))
     inter = INTERPOLATION[interpolation]
     max_h = max(b[2] for b in item_box)
     kmax = lib.passl_b200_resample_kmax(max(max(b[2], b[3]) for b in item_box), size, inter)
@@ -221,32 +223,44 @@ def gaussian_blur_u8(views_u8, sigmas, ksize=23):
     return views_u8
 
 
-class TwoViewInputStage:
-    """`(view_1, view_2) = stage(images)`: both fp32 [N, 3, size, size] on the device, ready for MoCo / SimCLR `train_iter`."""
+class ViewRecipe:
+    """The per-view part of the recipe: RandomApply(ColorJitter) -> RandomGrayscale -> RandomApply(GaussianBlur) -> RandomHorizontalFlip
+    -> Transpose -> NormalizeImage (the `view_trans1` / `view_trans2` lists of the reference YAMLs)."""
 
-    def __init__(self, size=224, scale=(0.08, 1.0), ratio=(3. / 4., 4. / 3.), interpolation="bilinear", jitter_p=0.0,
-                 brightness=0.4, contrast=0.4, saturation=0.4, hue=0.1, gray_p=0.2, blur_p=0.0, blur_sigma=(0.1, 2.0), blur_ksize=23,
-                 flip_p=0.5, norm_scale=1.0 / 255.0, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225), rng=random, np_rng=None):
-        """SimCLR recipe (configs/simclr/simclr_r50_IM.yaml:35-61): scale=(0.1, 1), interpolation='bicubic', jitter_p=0.8, gray_p=0.2,
-        blur_p=0.5, flip_p=0.5; MoCo v2 / CLIP recipes use the defaults with their own scale.  `rng` plays Python's `random` module,
-        `np_rng` numpy's (the reference draws the blur sigma with np.random.uniform, transforms.py:182)."""
-        import numpy as np
-        self.size, self.scale, self.ratio, self.interpolation = size, tuple(scale), tuple(ratio), interpolation
+    def __init__(self, jitter_p=0.0, brightness=0.4, contrast=0.4, saturation=0.4, hue=0.1, gray_p=0.2, blur_p=0.0,
+                 blur_sigma=(0.1, 2.0), blur_ksize=23, flip_p=0.5, norm_scale=1.0 / 255.0, mean=(0.485, 0.456, 0.406),
+                 std=(0.229, 0.224, 0.225)):
         self.jitter_p, self.jitter = jitter_p, dict(brightness=brightness, contrast=contrast, saturation=saturation, hue=hue)
         self.gray_p, self.blur_p, self.blur_sigma, self.blur_ksize, self.flip_p = gray_p, blur_p, tuple(blur_sigma), blur_ksize, flip_p
-        self.norm_scale, self.mean, self.std, self.rng, self.np_rng = norm_scale, mean, std, rng, (np_rng if np_rng is not None else np.random)
+        self.norm_scale, self.mean, self.std = norm_scale, tuple(mean), tuple(std)
 
-    def _draw_view(self):
-        """RandomApply(ColorJitter) -> RandomGrayscale -> RandomApply(GaussianBlur) -> RandomHorizontalFlip decisions of one view, in
-        pipeline order.  RandomApply skips when `p < random.random()` (transforms.py:138-143)."""
-        rng, plan, sigma = self.rng, [], None
+    def draw(self, rng, np_rng):
+        """-> (jitter plan, gray, blur sigma or None, flip), drawn in pipeline order.  RandomApply skips when `p < random.random()`
+        (transforms.py:138-143); the blur sigma comes from numpy's generator (transforms.py:182)."""
+        plan, sigma = [], None
         if self.jitter_p and not (self.jitter_p < rng.random()):
             plan = color_jitter_plan(rng=rng, **self.jitter)
         gray = rng.random() < self.gray_p
         if self.blur_p and not (self.blur_p < rng.random()):
-            sigma = float(self.np_rng.uniform(self.blur_sigma[0], self.blur_sigma[1]))
+            sigma = float(np_rng.uniform(self.blur_sigma[0], self.blur_sigma[1]))
         flip = rng.random() < self.flip_p
         return plan, gray, sigma, flip
+
+
+class TwoViewInputStage:
+    """`(view_1, view_2) = stage(images)`: both fp32 [N, 3, size, size] on the device, ready for MoCo / SimCLR `train_iter`."""
+
+    def __init__(self, size=224, scale=(0.08, 1.0), ratio=(3. / 4., 4. / 3.), interpolation="bilinear", rng=random, np_rng=None,
+                 view1=None, view2=None, **view_kwargs):
+        """SimCLR recipe (configs/simclr/simclr_r50_IM.yaml:35-83): scale=(0.1, 1), interpolation='bicubic', jitter_p=0.8, gray_p=0.2,
+        blur_p=0.5, flip_p=0.5; MoCo v2 (configs/moco/moco_v2_r50.yaml:34-80): scale=(0.2, 1), bilinear, same view lists.  Keyword
+        arguments of ViewRecipe given here apply to both views; `view1` / `view2` take ready ViewRecipe objects when the two lists
+        differ.  `rng` plays Python's `random` module, `np_rng` numpy's."""
+        import numpy as np
+        self.size, self.scale, self.ratio, self.interpolation = size, tuple(scale), tuple(ratio), interpolation
+        self.views = (view1 or ViewRecipe(**view_kwargs), view2 or ViewRecipe(**view_kwargs))
+        self.rng, self.np_rng = rng, (np_rng if np_rng is not None else np.random)
+        self.last_sigmas = []
 
     def draw(self, batch):
         """Host-side random decisions for one batch -> (item_img, item_box, gray, flip, plans); views of sample n are items n and
@@ -257,8 +271,8 @@ class TwoViewInputStage:
         for n in range(N):
             box1.append(random_resized_crop_params(batch.widths[n], batch.heights[n], self.scale, self.ratio, self.rng))
             box2.append(random_resized_crop_params(batch.widths[n], batch.heights[n], self.scale, self.ratio, self.rng))
-            d1.append(self._draw_view())
-            d2.append(self._draw_view())
+            d1.append(self.views[0].draw(self.rng, self.np_rng))
+            d2.append(self.views[1].draw(self.rng, self.np_rng))
         both = d1 + d2
         self.last_sigmas = [d[2] for d in both]
         return list(range(N)) * 2, box1 + box2, [d[1] for d in both], [d[3] for d in both], [d[0] for d in both]
@@ -266,16 +280,96 @@ class TwoViewInputStage:
     def __call__(self, images):
         batch = images if isinstance(images, ImageBatch) else ImageBatch(images)
         item_img, item_box, gray, flip, plans = self.draw(batch)
+        N = len(batch)
         u8 = resized_crop_u8(batch, item_img, item_box, self.size, self.interpolation)
         u8 = color_jitter_u8(u8, plans)
-        # grayscale sits between jitter and blur in the recipe; it commutes with nothing after it, so it is applied here when a
-        # blurred view is also grey, and left to the finalize kernel otherwise
+        # grayscale sits between jitter and blur in the recipe and does not commute with the blur's rounding: a view that is both
+        # grey and blurred gets its grayscale here, every other grey view in the finalize kernel
         if any(sg is not None for sg in self.last_sigmas):
             pre_gray = [g and sg is not None for g, sg in zip(gray, self.last_sigmas)]
             if any(pre_gray):
                 u8 = grayscale_u8(u8, pre_gray)
                 gray = [g and not p for g, p in zip(gray, pre_gray)]
-            u8 = gaussian_blur_u8(u8, self.last_sigmas, self.blur_ksize)
-        out = views_finalize(u8, gray, flip, self.norm_scale, self.mean, self.std)
-        N = len(batch)
-        return out[:N], out[N:]
+            ksizes = {v.blur_ksize for v in self.views}
+            assert len(ksizes) == 1, "both views must use the same blur kernel size"
+            u8 = gaussian_blur_u8(u8, self.last_sigmas, ksizes.pop())
+        outs = []
+        for v, recipe in enumerate(self.views):                          # the two view lists may normalise differently
+            sl = slice(v * N, (v + 1) * N)
+            outs.append(views_finalize(u8[sl], gray[sl], flip[sl], recipe.norm_scale, recipe.mean, recipe.std))
+        return outs[0], outs[1]
+
+
+def _fraction(text):
+    """NormalizeImage's `scale: 1.0/255.0` is a string the reference eval()s (transforms.py:459); only `a` or `a/b` is accepted."""
+    if isinstance(text, (int, float)):
+        return float(text)
+    parts = str(text).split("/")
+    if len(parts) > 2:
+        raise ValueError("cannot read scale %r" % (text,))
+    return float(parts[0]) / (float(parts[1]) if len(parts) == 2 else 1.0)
+
+
+def _view_recipe_from_list(items):
+    """One `view_trans*` list -> ViewRecipe.  The list must be the supported pipeline, in its order; anything else is refused."""
+    kw, stage = {}, 0
+    order = ["jitter", "gray", "blur", "flip", "transpose", "normalize"]
+
+    def at(step):
+        nonlocal stage
+        i = order.index(step)
+        if i < stage:
+            raise NotImplementedError("transform order not supported: %s after %s" % (step, order[stage - 1]))
+        stage = i + 1
+    for t in items:
+        t = dict(t)
+        name = t.pop("name")
+        if name == "RandomApply":
+            inner = [dict(x) for x in t["transforms"]]
+            if len(inner) != 1:
+                raise NotImplementedError("RandomApply with %d transforms" % len(inner))
+            iname = inner[0].pop("name")
+            if iname == "ColorJitter":
+                at("jitter")
+                kw.update(jitter_p=t.get("p", 0.5), **{k: inner[0].get(k, 0) for k in ("brightness", "contrast", "saturation", "hue")})
+            elif iname == "GaussianBlur":
+                at("blur")
+                if inner[0].get("_PIL", False):
+                    raise NotImplementedError("GaussianBlur(_PIL=True): only the default cv2 path is built")
+                kw.update(blur_p=t.get("p", 0.5), blur_sigma=tuple(inner[0].get("sigma", (0.1, 2.0))))
+            else:
+                raise NotImplementedError("RandomApply(%s)" % iname)
+        elif name == "RandomGrayscale":
+            at("gray")
+            kw["gray_p"] = t.get("p", 0.1)
+        elif name == "RandomHorizontalFlip":
+            at("flip")
+            kw["flip_p"] = t.get("prob", 0.5)
+        elif name == "Transpose":
+            at("transpose")
+        elif name == "NormalizeImage":
+            at("normalize")
+            kw.update(norm_scale=_fraction(t.get("scale", 1.0)), mean=tuple(t.get("mean", (0.0,) * 3)), std=tuple(t.get("std", (1.0,) * 3)))
+        else:
+            raise NotImplementedError("transform %s is not built in the device input stage" % name)
+    kw.setdefault("gray_p", 0.0)
+    kw.setdefault("flip_p", 0.0)
+    return ViewRecipe(**kw)
+
+
+def build_input_stage(dataset_cfg, rng=random, np_rng=None):
+    """The `dataloader.train.dataset` section of a two-view YAML (configs/moco/moco_v2_r50.yaml:29-80, configs/simclr/
+    simclr_r50_IM.yaml:29-83: `transforms` = [RandomResizedCrop], `view_trans1`, `view_trans2`) -> TwoViewInputStage."""
+    crop = [dict(t) for t in dataset_cfg["transforms"]]
+    if len(crop) != 1 or crop[0].get("name") != "RandomResizedCrop":
+        raise NotImplementedError("`transforms` must be a single RandomResizedCrop, got %s" % [t.get("name") for t in crop])
+    c = crop[0]
+    size = c["size"]
+    if isinstance(size, (list, tuple)):
+        if len(set(size)) != 1:
+            raise NotImplementedError("non-square output size %r" % (size,))
+        size = size[0]
+    return TwoViewInputStage(size=int(size), scale=tuple(c.get("scale", (0.08, 1.0))), ratio=tuple(c.get("ratio", (3. / 4., 4. / 3.))),
+                             interpolation=c.get("interpolation", "bilinear"), rng=rng, np_rng=np_rng,
+                             view1=_view_recipe_from_list(dataset_cfg["view_trans1"]),
+                             view2=_view_recipe_from_list(dataset_cfg["view_trans2"]))

@@ -223,3 +223,27 @@ def test_host_build_of_gaussian_blur_bodies_is_opencv_exact(hostlib):
     assert np.array_equal(got[0], cv2.GaussianBlur(small[0], (23, 23), 1.7))
     with pytest.raises(ValueError):
         gaussian_taps_fixed(22, 1.0)
+
+
+def test_build_input_stage_from_the_reference_yaml_sections():
+    """`dataloader.train.dataset` of the MoCo v2 / SimCLR YAMLs (the reference's own transform lists) -> the device stage."""
+    from passl_b200.data import build_input_stage
+    from passl_b200.utils.config import get_config
+    root = os.path.dirname(HERE)
+    for f, scale, interp in (("configs/moco/moco_v2_r50.yaml", (0.2, 1.0), "bilinear"), ("configs/simclr/simclr_r50_IM.yaml", (0.1, 1.0), "bicubic")):
+        st = build_input_stage(get_config(os.path.join(root, f), []).dataloader.train.dataset)
+        assert (st.size, st.scale, st.ratio, st.interpolation) == (224, scale, (3. / 4., 4. / 3.), interp)
+        for v in st.views:
+            assert (v.jitter_p, v.gray_p, v.blur_p, v.blur_sigma, v.blur_ksize, v.flip_p) == (0.8, 0.2, 0.5, (0.1, 2.0), 23, 0.5)
+            assert v.jitter == dict(brightness=0.4, contrast=0.4, saturation=0.4, hue=0.1)
+            assert v.norm_scale == 1.0 / 255.0 and v.mean == (0.485, 0.456, 0.406) and v.std == (0.229, 0.224, 0.225)
+    crop = [dict(name="RandomResizedCrop", size=96)]
+    plain = [dict(name="RandomHorizontalFlip"), dict(name="Transpose"), dict(name="NormalizeImage", scale="1.0/255.0", mean=[0.5] * 3, std=[0.5] * 3)]
+    st = build_input_stage(dict(transforms=crop, view_trans1=plain, view_trans2=[dict(name="RandomGrayscale")] + plain))
+    assert st.views[0].gray_p == 0.0 and st.views[1].gray_p == 0.1 and st.views[0].jitter_p == 0.0 and st.scale == (0.08, 1.0)
+    with pytest.raises(NotImplementedError):                                           # an op the stage does not have
+        build_input_stage(dict(transforms=crop, view_trans1=[dict(name="Solarization")], view_trans2=plain))
+    with pytest.raises(NotImplementedError):                                           # supported ops in another order
+        build_input_stage(dict(transforms=crop, view_trans1=[dict(name="RandomHorizontalFlip"), dict(name="RandomGrayscale")], view_trans2=plain))
+    with pytest.raises(NotImplementedError):
+        build_input_stage(dict(transforms=[dict(name="Resize", size=224)], view_trans1=plain, view_trans2=plain))
