@@ -373,3 +373,44 @@ def build_input_stage(dataset_cfg, rng=random, np_rng=None):
                              interpolation=c.get("interpolation", "bilinear"), rng=rng, np_rng=np_rng,
                              view1=_view_recipe_from_list(dataset_cfg["view_trans1"]),
                              view2=_view_recipe_from_list(dataset_cfg["view_trans2"]))
+
+
+class SyntheticDecodedImages:
+    """Stand-in for the decode step: per iteration a list of `batch_size` random uint8 HWC images of mixed sizes, created once on
+    the device (there is no ImageNet and no JPEG decoder in this environment; sizes follow typical ImageNet aspect ratios)."""
+
+    SHAPES = ((375, 500), (500, 375), (333, 500), (500, 333), (256, 256), (480, 640))
+
+    def __init__(self, batch_size, iters, device, seed=1234):
+        self.iters = iters
+        g = torch.Generator(device=device).manual_seed(seed)
+        self.images = [torch.randint(0, 256, self.SHAPES[i % len(self.SHAPES)] + (3,), dtype=torch.uint8, device=device, generator=g)
+                       for i in range(batch_size)]
+
+    def __len__(self):
+        return self.iters
+
+    def __iter__(self):
+        for _ in range(self.iters):
+            yield self.images
+
+
+class DeviceAugmentedTwoViews:
+    """Loader for the Trainer: decoded uint8 images in, `(view_1, view_2)` out, every iteration through the device input stage —
+    the place of `ImageNet.__getitem__` + the DataLoader workers (passl_v110/datasets/imagenet.py:46-63)."""
+
+    def __init__(self, source, stage):
+        self.source, self.stage = source, stage
+        self._packed = {}
+
+    def __len__(self):
+        return len(self.source)
+
+    def __iter__(self):
+        for images in self.source:
+            key = id(images)                                         # a source that re-yields the same list is packed once
+            batch = self._packed.get(key)
+            if batch is None:
+                batch = ImageBatch(images)
+                self._packed = {key: batch}
+            yield self.stage(batch)

@@ -99,6 +99,11 @@ class Trainer:
                 arch = cfg.model.architecture
                 dataloader = SyntheticImageText(self.batch_size, iters, self.device, size=arch.image_resolution,
                                                 context_length=arch.context_length, vocab_size=arch.vocab_size)
+            elif cfg.dataloader.train.get("device_input_stage", False):
+                # decoded uint8 images -> two augmented views on the GPU, recipe taken from the YAML's transform lists (f-2)
+                from ..data import DeviceAugmentedTwoViews, SyntheticDecodedImages, build_input_stage
+                dataloader = DeviceAugmentedTwoViews(SyntheticDecodedImages(self.batch_size, iters, self.device),
+                                                     build_input_stage(cfg.dataloader.train.dataset))
             else:
                 dataloader = SyntheticTwoViews(self.batch_size, iters, self.device)
         # LR schedule (engine/trainer.py:140-166 of the reference): epoch-denominated YAML keys become iterations through

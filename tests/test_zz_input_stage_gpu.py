@@ -114,3 +114,20 @@ def test_gaussian_blur_kernels_match_the_oracle():
         for m, sg in enumerate(sigmas):
             want = img[m] if sg is None else O.gaussian_blur_u8(img[m], 23, sg)
             assert np.array_equal(got[m], want), (S, m)
+
+
+def test_trainer_with_the_device_input_stage():
+    """configs/moco + `dataloader.train.device_input_stage=True`: uint8 images -> device stage (recipe from the YAML) -> MoCo steps."""
+    from passl_b200.engine.trainer import Trainer
+    from passl_b200.utils.config import get_config
+    root = os.path.dirname(HERE)
+    cfg = get_config(os.path.join(root, "configs/moco/moco_v2_r50.yaml"),
+                     ["model.K=1024", "dataloader.train.sampler.batch_size=16", "dataloader.train.device_input_stage=True",
+                      "dataloader.train.dataset.transforms.0.size=64", "total_iters=3", "log_config.interval=100"])
+    tr = Trainer(cfg)
+    assert type(tr.dataloader).__name__ == "DeviceAugmentedTwoViews" and tr.dataloader.stage.size == 64
+    v1, v2 = next(iter(tr.dataloader))
+    assert v1.shape == (16, 3, 64, 64) and v1.dtype == torch.float32 and torch.isfinite(v1).all() and not torch.equal(v1, v2)
+    assert abs(v1.mean().item()) < 1.5 and 0.01 < v1.std().item() < 3.0            # normalised pixel statistics of resampled noise
+    out = tr.train()
+    assert np.isfinite(float(out["loss"].detach()))
