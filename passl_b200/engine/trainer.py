@@ -7,7 +7,9 @@ registry, the fused optimizers, the data-parallel gradient exchange and checkpoi
 hooks/checkpoint_hook.py:22-49 (`{output_dir}/iter_{N}.pd` holding model, optimizer, lr-scheduler state and the iteration; torch
 serialisation; a path ending in `.pdparams` is written / read in the reference's own container, names and layouts through
 utils/checkpoint.py).  Evaluation hooks are out of scope."""
+import math
 import os
+import sys
 import time
 
 import torch
@@ -206,9 +208,13 @@ class Trainer:
             if self.current_iter % self.log_interval == 0 and get_rank() == 0:
                 torch.cuda.synchronize()
                 dt = time.time() - t0
+                loss_value = float(self.outputs['loss'].detach())
                 msg = "[Train][Iter: {}/{}] lr: {:.5f}, loss: {:.5f}, batch_cost: {:.5f}s, ips: {:.5f} images/sec".format(
-                    self.current_iter, total, self.optimizer.get_lr(), float(self.outputs['loss'].detach()), dt / self.log_interval, seen / dt)
+                    self.current_iter, total, self.optimizer.get_lr(), loss_value, dt / self.log_interval, seen / dt)
                 print(msg, flush=True)
+                if not math.isfinite(loss_value):            # tasks/ssl/mae/engine_pretrain.py:73-75; checked where the loss is
+                    print("Loss is {}, stopping training".format(loss_value), flush=True)      # read back anyway (log steps)
+                    sys.exit(1)
                 t0, seen = time.time(), 0
             if self.checkpoint_interval and self.current_iter % self.checkpoint_interval == 0:
                 self.save()
