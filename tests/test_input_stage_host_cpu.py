@@ -193,6 +193,13 @@ def test_host_build_of_colour_jitter_bodies(hostlib):
     for m in range(img.shape[0]):
         assert np.array_equal(got[m], oracle_jitter(img[m], plan[m])), (m, plan[m])
     assert not np.array_equal(got[0], img[0]) and np.array_equal(got[2][..., 0], got[2][..., 1])
+    # op 5: the in-place grayscale used for views that are blurred afterwards
+    g_ops = np.zeros((img.shape[0], 4), dtype=np.int32)
+    g_ops[[0, 3], 0] = 5
+    got = img.copy()
+    hostlib.host_color_jitter_u8(_p(got), _p(g_ops), _p(np.zeros((img.shape[0], 4), dtype=np.float32)), img.shape[0], img.shape[1])
+    for m in range(img.shape[0]):
+        assert np.array_equal(got[m], O.grayscale3_u8(img[m]) if m in (0, 3) else img[m]), m
 
 
 def test_host_build_of_gaussian_blur_bodies_is_opencv_exact(hostlib):
