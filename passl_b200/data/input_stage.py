@@ -73,11 +73,15 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _need_cuda(t):
+    if not t.is_cuda:
+        raise _lib.PasslB200Error("passl_b200 kernels need CUDA tensors (there is no CPU fallback)")
+
+
 def resized_crop_u8(batch, item_img, item_box, size=224, interpolation="bilinear", check=True):
     """Crop + PIL-exact resize of `len(item_img)` views.  item_img: source index per view, item_box: (top, left, h, w) per view
     (host lists).  -> uint8 [items, size, size, 3] on the device."""
-    if not batch.data.is_cuda:
-        raise _lib.PasslB200Error("passl_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    _need_cuda(batch.data)
     lib = _lib.load()
     items = len(item_img)
     for n, (t, l, h, w) in zip(item_img, item_box):
@@ -107,8 +111,7 @@ def resized_crop_u8(batch, item_img, item_box, size=224, interpolation="bilinear
 def views_finalize(views_u8, gray, flip, scale=1.0 / 255.0, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
     """uint8 [items, S, S, 3] -> fp32 [items, 3, S, S]: grayscale where gray[m], mirror where flip[m], (x * scale - mean) / std."""
     import ctypes
-    if not views_u8.is_cuda:
-        raise _lib.PasslB200Error("passl_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    _need_cuda(views_u8)
     lib = _lib.load()
     items, S = views_u8.shape[0], views_u8.shape[1]
     assert views_u8.dtype == torch.uint8 and views_u8.shape == (items, S, S, 3) and views_u8.is_contiguous()
@@ -149,8 +152,7 @@ def color_jitter_plan(brightness=0.4, contrast=0.4, saturation=0.4, hue=0.1, rng
 def color_jitter_u8(views_u8, plans):
     """In-place ColorJitter of uint8 [items, S, S, 3] views; plans[m] = [(op, factor)] (at most four) or [] for an untouched view.
     Blend factors are passed as C floats like Pillow receives them; the hue shift is uint8(hue_factor * 255) computed here."""
-    if not views_u8.is_cuda:
-        raise _lib.PasslB200Error("passl_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    _need_cuda(views_u8)
     lib = _lib.load()
     items, S = views_u8.shape[0], views_u8.shape[1]
     assert views_u8.dtype == torch.uint8 and views_u8.shape == (items, S, S, 3) and views_u8.is_contiguous() and len(plans) == items
@@ -206,8 +208,7 @@ def gaussian_taps_fixed(ksize, sigma):
 
 def gaussian_blur_u8(views_u8, sigmas, ksize=23):
     """In-place cv2-exact GaussianBlur of uint8 [items, S, S, 3] views; sigmas[m] = None leaves view m untouched."""
-    if not views_u8.is_cuda:
-        raise _lib.PasslB200Error("passl_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    _need_cuda(views_u8)
     lib = _lib.load()
     items, S = views_u8.shape[0], views_u8.shape[1]
     assert views_u8.dtype == torch.uint8 and views_u8.shape == (items, S, S, 3) and views_u8.is_contiguous() and len(sigmas) == items

@@ -99,3 +99,68 @@ extern "C" void host_gaussian_blur_u8(unsigned char* img, const int* taps, const
       for (int x = 0; x < S; ++x) blur_v_pixel(tmp16.data(), taps + (long long)m * ksize, img, m, y, x, S, ksize);
   }
 }
+
+// ---- the same entry points as the CUDA library, by their ABI names and signatures (checked against include/passl_b200.h by the
+// compiler), running the shared bodies on host memory: tests/test_input_stage_host_cpu.py points the Python wrappers of
+// passl_b200/data at this library to exercise their argument marshalling and the stage's orchestration without a GPU ------------
+#include <math.h>
+#include <string.h>
+
+#include "../include/passl_b200.h"
+
+extern "C" int passl_b200_resample_kmax(int max_crop, int out_size, int interpolation) {
+  if (max_crop <= 0 || out_size <= 0) return -1;
+  double scale = (double)max_crop / out_size;
+  if (scale < 1.0) scale = 1.0;
+  return (int)ceil((interpolation ? 2.0 : 1.0) * scale) * 2 + 1;
+}
+
+extern "C" long long passl_b200_resized_crop_workspace_bytes(int items, int out_size, int max_crop_h, int kmax) {
+  return (items <= 0 || out_size <= 0 || max_crop_h <= 0 || kmax <= 0) ? 0 : 256;
+}
+
+extern "C" int passl_b200_resized_crop_u8(const void* src, const long long* src_off, const int* src_h, const int* src_w,
+                                          const int* item_img, const int* item_box, void* dst, void* workspace,
+                                          long long workspace_bytes, int items, int out_size, int max_crop_h, int kmax,
+                                          int interpolation, void* stream) {
+  (void)stream;
+  if (items <= 0 || out_size <= 0 || max_crop_h <= 0 || kmax < 3 || (interpolation != 0 && interpolation != 1)) return -1;
+  if (workspace_bytes < 256) return -4;
+  const int status = host_resized_crop_u8((const unsigned char*)src, src_off, src_h, src_w, item_img, item_box, (unsigned char*)dst,
+                                          items, out_size, max_crop_h, kmax, interpolation);
+  memcpy(workspace, &status, sizeof(int));
+  return 0;
+}
+
+extern "C" int passl_b200_views_finalize_f32(const void* img, const int* gray, const int* flip, float* out, int items, int size,
+                                             double scale, const float* mean3, const float* std3, void* stream) {
+  (void)stream;
+  if (items <= 0 || size <= 0) return -1;
+  host_views_finalize_f32((const unsigned char*)img, gray, flip, out, items, size, scale, mean3, std3);
+  return 0;
+}
+
+extern "C" int passl_b200_color_jitter_u8(void* img, const int* ops, const float* factors, void* workspace, long long workspace_bytes,
+                                          int items, int size, int contrast_positions, void* stream) {
+  (void)stream; (void)workspace;
+  if (items <= 0 || size <= 0) return -1;
+  if (workspace_bytes < 8LL * items) return -4;
+  for (int m = 0; m < items; ++m)                              // the host must have announced every contrast position
+    for (int pos = 0; pos < 4; ++pos)
+      if (ops[4 * m + pos] == JIT_CONTRAST && !(contrast_positions & (1 << pos))) return -1;
+  host_color_jitter_u8((unsigned char*)img, ops, factors, items, size);
+  return 0;
+}
+
+extern "C" long long passl_b200_gaussian_blur_workspace_bytes(int items, int size) {
+  return (items <= 0 || size <= 0) ? 0 : (long long)items * size * size * 3 * 2;
+}
+
+extern "C" int passl_b200_gaussian_blur_u8(void* img, const int* taps, const int* apply, void* workspace, long long workspace_bytes,
+                                           int items, int size, int ksize, void* stream) {
+  (void)stream; (void)workspace;
+  if (items <= 0 || size <= 0 || ksize < 1 || !(ksize & 1)) return -1;
+  if (workspace_bytes < passl_b200_gaussian_blur_workspace_bytes(items, size)) return -4;
+  host_gaussian_blur_u8((unsigned char*)img, taps, apply, items, size, ksize);
+  return 0;
+}

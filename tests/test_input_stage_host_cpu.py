@@ -254,3 +254,73 @@ def test_build_input_stage_from_the_reference_yaml_sections():
         build_input_stage(dict(transforms=crop, view_trans1=[dict(name="RandomHorizontalFlip"), dict(name="RandomGrayscale")], view_trans2=plain))
     with pytest.raises(NotImplementedError):
         build_input_stage(dict(transforms=[dict(name="Resize", size=224)], view_trans1=plain, view_trans2=plain))
+
+
+@pytest.fixture()
+def stage_on_host(hostlib, monkeypatch):
+    """passl_b200.data's wrappers bound to the host build: same ABI names / ctypes signatures, host memory, no stream."""
+    from passl_b200 import _lib
+    from passl_b200.data import input_stage as IS
+    for name in ("passl_b200_resample_kmax", "passl_b200_resized_crop_workspace_bytes", "passl_b200_resized_crop_u8",
+                 "passl_b200_views_finalize_f32", "passl_b200_color_jitter_u8", "passl_b200_gaussian_blur_workspace_bytes",
+                 "passl_b200_gaussian_blur_u8"):
+        fn = getattr(hostlib, name)
+        fn.restype, fn.argtypes = _lib.SIGNATURES[name]
+    monkeypatch.setattr(IS._lib, "load", lambda: hostlib)
+    monkeypatch.setattr(IS, "_stream", lambda: 0)
+    monkeypatch.setattr(IS, "_need_cuda", lambda t: None)
+    return IS
+
+
+def test_python_wrappers_and_stage_orchestration_on_the_host_build(stage_on_host):
+    """The GPU tests of tests/test_zz_input_stage_gpu.py, with the library swapped for its host build: argument marshalling of every
+    wrapper, the status word, and TwoViewInputStage.__call__ (jitter -> grayscale-before-blur -> blur -> finalize per view list)."""
+    import random
+    import torch
+    IS = stage_on_host
+    c = make_cases()
+    batch = IS.ImageBatch(c["images"], device="cpu")
+    boxes = [tuple(int(v) for v in b) for b in c["item_box"]]
+    idx = [int(i) for i in c["item_img"]]
+    for interp in ("bilinear", "bicubic"):
+        u8 = IS.resized_crop_u8(batch, idx, boxes, 32, interp)
+        for m, (n, (i, j, h, w)) in enumerate(zip(idx, boxes)):
+            assert np.array_equal(u8[m].numpy(), O.resized_crop_u8(c["images"][n], i, j, h, w, 32, interp)), (m, interp)
+    with pytest.raises(ValueError):
+        IS.resized_crop_u8(batch, [0], [(300, 400, 76, 100)], 32)
+    batch.heights[0] += 1                                                               # lie to the host check: device status word
+    with pytest.raises(IS._lib.PasslB200Error):
+        IS.resized_crop_u8(batch, [0, 1], [(300, 400, 76, 100), (0, 0, 64, 48)], 32)
+    batch.heights[0] -= 1
+    img, ops, factors, plan = jitter_cases()
+    got = IS.color_jitter_u8(torch.from_numpy(img.copy()), [[(op, f) for op, f in row if op] for row in plan]).numpy()
+    for m in range(img.shape[0]):
+        assert np.array_equal(got[m], oracle_jitter(img[m], [(op, f) for op, f in plan[m] if op])), m
+    sig = [0.1, None, 1.37, 2.0, None, 0.5]
+    got = IS.gaussian_blur_u8(torch.from_numpy(img.copy()), sig).numpy()
+    for m, sg in enumerate(sig):
+        assert np.array_equal(got[m], img[m] if sg is None else O.gaussian_blur_u8(img[m], 23, sg)), m
+    # the whole two-view stage, both view lists different (view 2 never blurs, other normalisation)
+    rng = np.random.RandomState(5)
+    images = [rng.randint(0, 256, size=(int(h), int(w), 3)).astype(np.uint8) for h, w in [(240, 320), (333, 250), (128, 128), (96, 400)]]
+    v1 = dict(jitter_p=0.6, gray_p=0.5, blur_p=0.6)
+    v2 = dict(jitter_p=0.6, gray_p=0.5, blur_p=0.0, mean=(0.5, 0.5, 0.5), std=(0.25, 0.25, 0.25))
+    mk = lambda: IS.TwoViewInputStage(size=48, scale=(0.2, 1.0), interpolation="bicubic", rng=random.Random(11),   # noqa: E731
+                                      np_rng=np.random.RandomState(4), view1=IS.ViewRecipe(**v1), view2=IS.ViewRecipe(**v2))
+    stage, twin = mk(), mk()
+    b2 = IS.ImageBatch(images, device="cpu")
+    out1, out2 = stage(b2)
+    item_img, item_box, gray, flip, plans = twin.draw(b2)
+    sig = twin.last_sigmas
+    assert any(s_ is not None and g for s_, g in zip(sig, gray)) and any(s_ is None and g for s_, g in zip(sig, gray)) and any(plans)
+    both = torch.cat([out1, out2]).numpy()
+    for m, (n, (i, j, h, w)) in enumerate(zip(item_img, item_box)):
+        x = oracle_jitter(O.resized_crop_u8(images[n], i, j, h, w, 48, "bicubic"), plans[m])
+        if gray[m]:
+            x = O.grayscale3_u8(x)
+        if sig[m] is not None:
+            x = O.gaussian_blur_u8(x, 23, sig[m])
+        if flip[m]:
+            x = O.hflip_u8(x)
+        kw = {} if m < 4 else dict(mean=v2["mean"], std=v2["std"])
+        assert np.array_equal(both[m], O.transpose_normalize(x, **kw)), m
