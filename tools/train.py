@@ -18,6 +18,13 @@ def main():
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         dist.init_process_group("nccl")
+    if "Global" in cfg:                  # v2.5 schema (Global / Model / Optimizer / LRScheduler / DataLoader): tools/train.py:25-32
+        from passl_b200.engine.engine import Engine
+        engine = Engine(cfg, mode="train")
+        if args.resume:
+            engine.resume(args.resume)
+        engine.train()
+        return
     trainer = Trainer(cfg)
     if args.resume:                      # tools_v110/train.py:35-40: continue a run, or start from weights only
         trainer.resume(args.resume)
