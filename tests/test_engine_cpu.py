@@ -119,3 +119,15 @@ def test_max_train_step_and_unbuilt_options(engine, monkeypatch):
         Engine(get_config(CFG, ["Global.accum_steps=2"]), device="cpu")
     with pytest.raises(NotImplementedError):
         Engine(get_config(CFG, []), mode="eval", device="cpu")
+
+
+def test_mae_pretrain_entry_arguments_and_rates():
+    """tools/mae_pretrain.py: the reference's argument names and its lr = blr * total batch / 256 rule (main_pretrain.py:239-243)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mae_pretrain", os.path.join(os.path.dirname(HERE), "tools", "mae_pretrain.py"))
+    M = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(M)
+    a = M.get_args_parser().parse_args(["--batch_size", "512", "--blr", "1.5e-4", "--norm_pix_loss", "--mask_ratio", "0.75"])
+    assert M.effective_lr(a, 8) == (1.5e-4 * 4096 / 256, 4096) and a.norm_pix_loss and a.model == "mae_vit_base_patch16"
+    assert (a.weight_decay, a.warmup_epochs, a.min_lr, a.input_size) == (0.05, 40, 0.0, 224)
+    assert M.effective_lr(M.get_args_parser().parse_args(["--lr", "0.001"]), 2) == (0.001, 128)
