@@ -129,6 +129,8 @@ class Engine:
         return loss
 
     def train(self):
+        from ..utils.profiler import StepProfiler
+        profiler = StepProfiler(self.config.get("profiler_options", None))    # config.profiler_options = args.profiler_options
         steps_per_epoch = len(self.train_dataloader)
         self.model.train()
         for epoch_id in range(self.cur_epoch_id + 1, self.epochs + 1):
@@ -141,6 +143,7 @@ class Engine:
                               flush=True)
                     return self.global_step
                 self.global_step += 1
+                profiler.step()
                 loss = self.train_one_step(batch)
                 seen += self.batch_size * get_world_size()
                 if (batch_idx + 1) % self.print_batch_step == 0 or batch_idx + 1 == steps_per_epoch:

@@ -191,10 +191,13 @@ class Trainer:
         self.current_iter = int(ck["iter"])
 
     def train(self):
+        from ..utils.profiler import StepProfiler
+        profiler = StepProfiler(self.cfg.get("profiler_options", None))       # -p "batch_range=[a, b]; ..." (tools/train.py:30)
         loader = IterLoader(self.dataloader)
         total = len(self.dataloader)
         t0, seen = time.time(), 0
         while self.current_iter < total:
+            profiler.step()
             data = next(loader)
             self.optimizer.clear_grad()
             self.outputs = self.model(*data, total_iters=total, current_iter=self.current_iter)

@@ -131,3 +131,34 @@ def test_mae_pretrain_entry_arguments_and_rates():
     assert M.effective_lr(a, 8) == (1.5e-4 * 4096 / 256, 4096) and a.norm_pix_loss and a.model == "mae_vit_base_patch16"
     assert (a.weight_decay, a.warmup_epochs, a.min_lr, a.input_size) == (0.05, 40, 0.0, 224)
     assert M.effective_lr(M.get_args_parser().parse_args(["--lr", "0.001"]), 2) == (0.001, 128)
+
+
+def test_profiler_options_and_step_window(tmp_path):
+    """utils/profiler.py: the reference's option-string grammar (profiler.py:46-72) and the step window, on a recording backend."""
+    from passl_b200.utils.profiler import ProfilerOptions, StepProfiler
+    o = ProfilerOptions("batch_range=[3, 5]; tracer_option=OpDetail; profile_path=%s; exit_on_finished=false" % (tmp_path / "p.txt"))
+    assert o["batch_range"] == [3, 5] and o["tracer_option"] == "OpDetail" and o["exit_on_finished"] is False and o["state"] == "All"
+    assert ProfilerOptions("batch_range=[7,2]")["batch_range"] == [10, 20]                 # invalid range: default kept
+    with pytest.raises(ValueError):
+        o["no_such_key"]
+    events = []
+
+    class _Rec:
+        class nvtx:
+            range_push = staticmethod(lambda name: events.append(("push", name)))
+            range_pop = staticmethod(lambda: events.append(("pop",)))
+
+        class profiler:
+            start = staticmethod(lambda: events.append(("start",)))
+            stop = staticmethod(lambda: events.append(("stop",)))
+        synchronize = staticmethod(lambda: None)
+    p = StepProfiler("batch_range=[3, 5]; profile_path=%s; exit_on_finished=false" % (tmp_path / "p.txt"), backend=_Rec)
+    for _ in range(8):
+        p.step()
+    assert events == [("start",), ("push", "step_3"), ("pop",), ("push", "step_4"), ("pop",), ("stop",)]
+    assert "profiled steps [3, 5)" in open(tmp_path / "p.txt").read()
+    q = StepProfiler("batch_range=[0, 1]; profile_path=%s" % (tmp_path / "q.txt"), backend=_Rec)
+    q.step()
+    with pytest.raises(SystemExit):
+        q.step()
+    StepProfiler(None).step()                                                             # disabled: no-op

@@ -15,6 +15,7 @@ from passl_b200.utils import config as cfg_util  # noqa: E402
 def main():
     args = cfg_util.parse_args()
     cfg = cfg_util.get_config(args.config, overrides=args.override)
+    cfg["profiler_options"] = args.profiler_options
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         dist.init_process_group("nccl")
