@@ -1,104 +1,116 @@
-"""YAML config -> nested AttrDict with dotted `-o key=value` overrides: same semantics and error messages as
-passl/utils/config.py:24-173 (string values literal_eval'd, list indices in override paths, new keys reported)."""
+"""YAML config files -> attribute-style nested mappings, with `-o a.b.0.c=value` overrides from the command line.
+
+Behaviour follows the reference's loader (passl/utils/config.py:24-173) because the YAML files are shared with it: string scalars
+that are Python literals become those literals ("(0.9, 0.999)" -> tuple, "1e-8" -> float, "None" -> None; "1.0/255.0" stays a
+string), override paths may index into lists, an override may create keys that the file does not have (it says so), and override
+values are parsed the same way as file values (plus YAML's own `null` / `true` / `false`)."""
 import argparse
+import ast
+import copy
 import os
-from ast import literal_eval
 
 import yaml
 
 
 class AttrDict(dict):
-    def __getattr__(self, key):
-        try:
-            return self[key]
-        except KeyError:
-            raise AttributeError(key)
+    """dict whose keys are also attributes (cfg.model.backbone.depth)."""
 
-    def __setattr__(self, key, value):
-        if key in self.__dict__:
-            self.__dict__[key] = value
-        else:
-            self[key] = value
+    def __getattr__(self, name):
+        if name in self:
+            return self[name]
+        raise AttributeError(name)
+
+    def __setattr__(self, name, value):
+        self[name] = value
 
     def __deepcopy__(self, memo):
-        import copy
-        return AttrDict({copy.deepcopy(k, memo): copy.deepcopy(v, memo) for k, v in self.items()})
+        return AttrDict((copy.deepcopy(k, memo), copy.deepcopy(v, memo)) for k, v in self.items())
 
 
-def create_attr_dict(yaml_config):
-    for key, value in yaml_config.items():
-        if type(value) is dict:
-            yaml_config[key] = value = AttrDict(value)
-        if isinstance(value, str):
-            try:
-                value = literal_eval(value)
-            except BaseException:
-                pass
-        if isinstance(value, AttrDict):
-            create_attr_dict(yaml_config[key])
-        else:
-            yaml_config[key] = value
+def _literal(text):
+    """A string that spells a Python literal -> the literal; anything else unchanged."""
+    if not isinstance(text, str):
+        return text
+    try:
+        return ast.literal_eval(text)
+    except (ValueError, SyntaxError, TypeError, MemoryError, RecursionError):
+        return text
 
 
-def parse_config(cfg_file):
-    with open(cfg_file, 'r') as fopen:
-        yaml_config = AttrDict(yaml.load(fopen, Loader=yaml.SafeLoader))
-    create_attr_dict(yaml_config)
-    return yaml_config
+def _attrify(node):
+    """Recursively: mappings -> AttrDict, string leaves -> literals.  Lists keep their identity (their mapping items are converted)."""
+    if isinstance(node, dict):
+        return AttrDict((k, _attrify(v)) for k, v in node.items())
+    if isinstance(node, list):
+        return [_attrify(v) if isinstance(v, (dict, list)) else v for v in node]
+    return _literal(node)
 
 
-def override(dl, ks, v):
-    def str2num(v):
+def _override_value(text):
+    value = _literal(text)
+    if isinstance(value, str):                       # not a Python literal: let YAML read null / true / plain words
         try:
-            return eval(v)
-        except Exception:
-            return v
-    assert isinstance(dl, (list, dict)), ("{} should be a list or a dict")
-    assert len(ks) > 0, ('lenght of keys should larger than 0')
-    if isinstance(dl, list):
-        k = str2num(ks[0])
-        if len(ks) == 1:
-            assert k < len(dl), ('index({}) out of range({})'.format(k, dl))
-            dl[k] = str2num(v)
+            parsed = yaml.safe_load(value)
+        except yaml.YAMLError:
+            return value
+        return value if isinstance(parsed, (dict, list)) else parsed
+    return value
+
+
+def _set_by_path(root, path, value, option):
+    node = root
+    for depth, part in enumerate(path):
+        last = depth == len(path) - 1
+        if isinstance(node, list):
+            index = int(part)
+            if not -len(node) <= index < len(node):
+                raise IndexError("override %r: index %d is outside a list of %d items" % (option, index, len(node)))
+            if last:
+                node[index] = value
+            else:
+                node = node[index]
+        elif isinstance(node, dict):
+            if last:
+                if part not in node:
+                    print("override %r adds the new key %r" % (option, part))
+                node[part] = value
+            else:
+                if part not in node:
+                    node[part] = AttrDict()
+                node = node[part]
         else:
-            override(dl[k], ks[1:], v)
-    else:
-        if len(ks) == 1:
-            if not ks[0] in dl:
-                print('A new filed ({}) detected!'.format(ks[0], dl))
-            dl[ks[0]] = str2num(v)
-        else:
-            if ks[0] not in dl:
-                dl[ks[0]] = AttrDict()
-            override(dl[ks[0]], ks[1:], v)
+            raise TypeError("override %r: %r is a %s, cannot descend into it" % (option, ".".join(path[:depth]), type(node).__name__))
 
 
 def override_config(config, options=None):
-    if options is not None:
-        for opt in options:
-            assert isinstance(opt, str), ("option({}) should be a str".format(opt))
-            assert "=" in opt, ("option({}) should contain a =to distinguish between key and value".format(opt))
-            pair = opt.split('=')
-            assert len(pair) == 2, ("there can be only a = in the option")
-            key, value = pair
-            override(config, key.split('.'), value)
+    for option in options or []:
+        if not isinstance(option, str) or option.count("=") < 1:
+            raise ValueError("override %r must look like key.path=value" % (option,))
+        key, _, text = option.partition("=")
+        if not key:
+            raise ValueError("override %r has an empty key" % (option,))
+        _set_by_path(config, key.split("."), _override_value(text), option)
     return config
+
+
+def parse_config(path):
+    with open(path, "r") as f:
+        return _attrify(yaml.safe_load(f) or {})
 
 
 def get_config(fname, overrides=None, show=False):
-    assert os.path.exists(fname), ('config file({}) is not exist'.format(fname))
-    config = parse_config(fname)
-    override_config(config, overrides)
-    return config
+    if not os.path.exists(fname):
+        raise FileNotFoundError("config file %s does not exist" % fname)
+    return override_config(parse_config(fname), overrides)
 
 
 def parse_args(argv=None):
-    """passl/utils/config.py:151-173: -c config, -o overrides, -p profiler options; --resume / --load of the v110 CLI."""
-    parser = argparse.ArgumentParser("passl_b200 train script")
-    parser.add_argument('-c', '--config', '--config-file', dest='config', type=str, default='configs/config.yaml', help='config file path')
-    parser.add_argument('-o', '--override', action='append', default=[], help='config options to be overridden')
-    parser.add_argument('-p', '--profiler_options', type=str, default=None, help='profiler options "key1=value1;key2=value2"')
-    # passl_v110/utils/options.py:35-49 (training-path subset; --evaluate-only / --export are outside the hot path)
-    parser.add_argument('--resume', type=str, default=None, help='checkpoint to continue from (weights, schedule position, iteration)')
-    parser.add_argument('--load', type=str, default=None, help='weights to start from (.pdparams / epoch_N.pd / this package\'s iter_N.pd)')
-    return parser.parse_args(argv)
+    """The train entry's flags: -c / -o / -p of the v2.5 CLI (passl/utils/config.py:151-173), --resume / --load of the v110 one
+    (passl_v110/utils/options.py:35-49; --evaluate-only / --export are outside the training path)."""
+    ap = argparse.ArgumentParser("passl_b200 train script")
+    ap.add_argument("-c", "--config", "--config-file", dest="config", type=str, default="configs/config.yaml", help="config file path")
+    ap.add_argument("-o", "--override", action="append", default=[], help="key.path=value, repeatable")
+    ap.add_argument("-p", "--profiler_options", type=str, default=None, help='step window, e.g. "batch_range=[10, 20]; profile_path=run.txt"')
+    ap.add_argument("--resume", type=str, default=None, help="checkpoint to continue from (weights, schedule position, iteration)")
+    ap.add_argument("--load", type=str, default=None, help="weights to start from (.pdparams / epoch_N.pd / this package's iter_N.pd)")
+    return ap.parse_args(argv)
