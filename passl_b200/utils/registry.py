@@ -1,54 +1,60 @@
-"""Name -> class registry with the reference's API (passl_v110/utils/registry.py:25-133)."""
-import inspect
+"""Name -> class tables behind the config-driven construction (`backbone: {name: ResNet, depth: 50}`).
+
+Same surface as the reference's registries (passl_v110/utils/registry.py:25-133) because the YAML files and the `@X.register()`
+decorators are shared vocabulary: `Registry(name)`, `.register()` as decorator or call, `.get(name)`, and
+`build_from_config(cfg, registry, default_args)` = look the class up by `cfg['name']` and call it with the remaining keys."""
 
 
-class Registry(object):
+class Registry:
     def __init__(self, name):
         self._name = name
-        self._obj_map = {}
+        self._table = {}
 
-    def _do_register(self, name, obj):
-        assert name not in self._obj_map, \
-            "An object named '{}' was already registered in '{}' registry!".format(name, self._name)
-        self._obj_map[name] = obj
+    def __repr__(self):
+        return "Registry(%r, %d entries)" % (self._name, len(self._table))
+
+    def __contains__(self, key):
+        return key in self._table
+
+    def names(self):
+        return sorted(self._table)
+
+    def _add(self, obj, key=None):
+        key = key or obj.__name__
+        if key in self._table:
+            raise AssertionError("An object named '%s' was already registered in '%s' registry!" % (key, self._name))
+        self._table[key] = obj
+        return obj
 
     def register(self, obj=None, name=None):
-        if obj is None:
-            def deco(func_or_class, name=name):
-                self._do_register(name or func_or_class.__name__, func_or_class)
-                return func_or_class
-            return deco
-        self._do_register(name or obj.__name__, obj)
+        """`@R.register()`, `@R.register(name='x')` or `R.register(cls)`."""
+        if obj is not None:
+            self._add(obj, name)
+            return None
+        return lambda target: self._add(target, name)
 
     def get(self, name):
-        ret = self._obj_map.get(name)
-        if ret is None:
-            raise KeyError("No object named '{}' found in '{}' registry!".format(name, self._name))
-        return ret
-
-    def __contains__(self, name):
-        return name in self._obj_map
+        try:
+            return self._table[name]
+        except KeyError:
+            raise KeyError("No object named '%s' found in '%s' registry! (known: %s)" % (name, self._name, ", ".join(self.names()))) from None
 
 
 def build_from_config(cfg, registry, default_args=None):
-    """Instantiate ``registry[cfg['name']](**rest_of_cfg)`` — same contract and errors as the reference (:88-133)."""
+    """cfg: mapping with a 'name' (a registered name, or a class) plus constructor keywords; default_args fill missing keywords."""
     if not isinstance(cfg, dict):
-        raise TypeError(f'cfg must be a dict, but got {type(cfg)}')
-    if 'name' not in cfg and (default_args is None or 'name' not in default_args):
-        raise KeyError(f'`cfg` or `default_args` must contain the key "name", but got {cfg}\n{default_args}')
+        raise TypeError("cfg must be a dict, but got %s" % type(cfg))
     if not isinstance(registry, Registry):
-        raise TypeError(f'registry must be an Registry object, but got {type(registry)}')
-    if not (isinstance(default_args, dict) or default_args is None):
-        raise TypeError(f'default_args must be a dict or None, but got {type(default_args)}')
-    args = dict(cfg)
-    if default_args is not None:
-        for k, v in default_args.items():
-            args.setdefault(k, v)
-    cls_name = args.pop('name')
-    if isinstance(cls_name, str):
-        obj_cls = registry.get(cls_name)
-    elif inspect.isclass(cls_name):
-        obj_cls = cls_name
-    else:
-        raise TypeError(f'name must be a str or valid name, but got {type(cls_name)}')
-    return obj_cls(**args)
+        raise TypeError("registry must be an Registry object, but got %s" % type(registry))
+    if default_args is not None and not isinstance(default_args, dict):
+        raise TypeError("default_args must be a dict or None, but got %s" % type(default_args))
+    kwargs = dict(default_args or {})
+    kwargs.update(cfg)
+    if "name" not in kwargs:
+        raise KeyError('`cfg` or `default_args` must contain the key "name", but got %s\n%s' % (cfg, default_args))
+    target = kwargs.pop("name")
+    if isinstance(target, str):
+        target = registry.get(target)
+    elif not isinstance(target, type):
+        raise TypeError("name must be a str or valid name, but got %s" % type(target))
+    return target(**kwargs)
