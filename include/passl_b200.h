@@ -110,9 +110,15 @@ int passl_b200_simce_bwd_f32(const float* A, const void* B, int b_is_bf16, const
                              void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
- * Fused InfoNCE forward on tcgen05 (bf16 operands, fp32 accumulate in TMEM, online softmax out of TMEM).
- * Same contract as passl_b200_simce_fwd_f32 with Q and Kmat in bf16; the key matrix is streamed from HBM exactly
- * once.  D multiple of 64, <= 512.
+ * Fused InfoNCE on tcgen05 (bf16 operands, fp32 accumulate in TMEM, softmax out of TMEM), ONE launch per direction.
+ * Same contract as passl_b200_simce_fwd_f32 / _bwd_f32 with Q and Kmat in bf16 (rows L2-normalised: |<q,k>| <= ~1); the
+ * key matrix is streamed from HBM exactly once per direction.  D multiple of 64, <= 512 (forward), <= 256 (backward).
+ * Replaces matmul + concat + /T + CrossEntropyLoss + topk and their autograd backward
+ * (passl_v110/modeling/architectures/moco.py:178-182, heads/contrastive_head.py:37-60, passl/models/mocov3.py:187-198).
+ * `workspace` of the forward is PERSISTENT STATE (passl_b200_infonce_tc_workspace_bytes(N, K, D) bytes): the caller
+ * zero-fills it once before its first use (and after a failed launch) and keeps one buffer per (N, stream); every launch
+ * leaves it ready for the next.  Slice partial sums are merged with float atomics (results are order-dependent in the
+ * last bit).  The backward overwrites dQ fp32 [N, D].
  * ------------------------------------------------------------------------------------------------------------- */
 long long passl_b200_infonce_tc_workspace_bytes(int N, int K, int D);
 /* developer hook: per-CTA timeline (uint64 [grid*16], %globaltimer ns) written by subsequent launches; NULL disables */
@@ -121,6 +127,9 @@ int passl_b200_infonce_tc_fwd(const void* Q, const void* Kmat, const float* P, c
                               float scale, float loss_scale, int N, int K, int D, float* lse, float* tgt,
                               float* loss_rows, float* out_scalars, void* workspace, long long workspace_bytes,
                               void* stream);
+int passl_b200_infonce_tc_bwd(const void* Q, const void* Kmat, const float* P, const long long* label, const int* excl,
+                              float scale, float loss_scale, int N, int K, int D, const float* lse, const float* tgt,
+                              const float* dloss, float* dQ, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * SimCLR NT-Xent + CO2 (passl_v110/modeling/heads/simclr_contrastive_head.py:42-102) on a similarity matrix

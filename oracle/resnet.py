@@ -13,6 +13,47 @@ import torch
 import torch.nn.functional as F
 
 
+# ---- quantisation-matched mode (q=True) -----------------------------------------------------------------------------------
+# The CUDA path keeps activations and activation gradients in bf16 between fused units (fp32 accumulation inside a unit).  With
+# q=True this oracle rounds to bf16 at exactly those points, forward AND backward, so that what is left between the two is
+# accumulation order — the comparison then isolates kernel defects from quantisation noise (which BatchNorm over small batches
+# amplifies through 50 layers).  Rounding points of the CUDA path (passl_b200/nn/layers.py, modeling/backbones/resnet.py):
+#   forward : input pixels; conv output y (statistics are taken from the rounded values); unit output z = relu(bn(y) [+ res]);
+#             max-pool / avg-pool output; fc outputs (bf16 ones)
+#   backward: dz arriving at a unit (sum of its consumers' contributions, rounded once); dy leaving the BN backward;
+#             the downsample branch's dx before the conv1 dgrad accumulates onto it
+def _round_bf16(x):
+    return x.float().bfloat16().to(x.dtype)
+
+
+class _RoundBoth(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return _round_bf16(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _round_bf16(g)
+
+
+class _RoundBwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _round_bf16(g)
+
+
+def Q(x, on=True):
+    return _RoundBoth.apply(x) if on else x
+
+
+def Qb(x, on=True):
+    return _RoundBwd.apply(x) if on else x
+
+
 def bn_train(x, gamma, beta, eps=1e-5, stats=None, use_global_stats=False, running=None):
     dims = [0] + list(range(2, x.dim()))
     if use_global_stats:
@@ -29,57 +70,70 @@ def bn_train(x, gamma, beta, eps=1e-5, stats=None, use_global_stats=False, runni
     return y
 
 
-def conv_bn(x, p, prefix, stride=1, pad=0, relu=True, residual=None, use_global_stats=False):
+def conv_bn(x, p, prefix, stride=1, pad=0, relu=True, residual=None, use_global_stats=False, q=False):
     """p[prefix+'.weight'] is [Cout, Cin, R, S] (NCHW convention)."""
-    y = F.conv2d(x, p[prefix + ".weight"], stride=stride, padding=pad)
+    y = Q(F.conv2d(x, p[prefix + ".weight"], stride=stride, padding=pad), q)
     running = (p.get(prefix + ".bn._mean"), p.get(prefix + ".bn._variance"))
     y = bn_train(y, p[prefix + ".bn.weight"], p[prefix + ".bn.bias"], use_global_stats=use_global_stats, running=running)
     if residual is not None:
         y = y + residual
-    return F.relu(y) if relu else y
+    return Q(F.relu(y) if relu else y, q)
 
 
-def bottleneck(x, p, prefix, stride, has_ds, ugs=False):
+def bottleneck(x, p, prefix, stride, has_ds, ugs=False, q=False):
     """resnetimagenet.py:133-148"""
-    out = conv_bn(x, p, prefix + ".conv1", use_global_stats=ugs)
-    out = conv_bn(out, p, prefix + ".conv2", stride=stride, pad=1, use_global_stats=ugs)
-    identity = conv_bn(x, p, prefix + ".downsample", stride=stride, relu=False, use_global_stats=ugs) if has_ds else x
-    return conv_bn(out, p, prefix + ".conv3", relu=True, residual=identity, use_global_stats=ugs)
+    out = conv_bn(x, p, prefix + ".conv1", use_global_stats=ugs, q=q)
+    out = conv_bn(out, p, prefix + ".conv2", stride=stride, pad=1, use_global_stats=ugs, q=q)
+    identity = conv_bn(Qb(x, q), p, prefix + ".downsample", stride=stride, relu=False, use_global_stats=ugs, q=q) if has_ds else x
+    return conv_bn(out, p, prefix + ".conv3", relu=True, residual=identity, use_global_stats=ugs, q=q)
 
 
-def resnet_forward(img, p, layers=(3, 4, 6, 3), stem_maxpool=True, with_pool=False, ugs=False, prefix=""):
+def resnet_forward(img, p, layers=(3, 4, 6, 3), stem_maxpool=True, with_pool=False, ugs=False, prefix="", q=False):
     """img NCHW; returns NCHW feature map (or [B, C] when with_pool).  resnetimagenet.py:232-246."""
-    x = conv_bn(img, p, prefix + "stem", stride=2, pad=3, use_global_stats=ugs)
+    if q:
+        img = _round_bf16(img)
+    x = conv_bn(img, p, prefix + "stem", stride=2, pad=3, use_global_stats=ugs, q=q)
     if stem_maxpool:
-        x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+        x = Q(F.max_pool2d(x, kernel_size=3, stride=2, padding=1), q)      # forward no-op (max commutes with rounding)
     inplanes, bi = 64, 0
     for i, (planes, n) in enumerate(zip([64, 128, 256, 512], layers)):
         for b in range(n):
             s = (1 if i == 0 else 2) if b == 0 else 1
             has_ds = b == 0 and (s != 1 or inplanes != planes * 4)
-            x = bottleneck(x, p, prefix + "blocks.%d" % bi, s, has_ds, ugs)
+            x = bottleneck(x, p, prefix + "blocks.%d" % bi, s, has_ds, ugs, q=q)
             inplanes = planes * 4
             bi += 1
     if with_pool:
-        x = x.mean(dim=(2, 3))
+        x = Q(x.mean(dim=(2, 3)), q)
     return x
 
 
-def neck_v1(feat, p, prefix="", with_avg_pool=True):
+def _neck_in(feat, with_avg_pool, q):
+    if with_avg_pool and feat.dim() == 4:
+        return Q(feat.mean(dim=(2, 3)), q)
+    return feat.reshape(feat.shape[0], -1)
+
+
+def neck_linear(feat, p, prefix="", with_avg_pool=True, q=False):
+    """LinearNeck (base_neck.py:43-64): avgpool -> fc (fp32 output; its gradient is cast to bf16 for the dgrad / wgrad GEMMs)."""
+    x = _neck_in(feat, with_avg_pool, q)
+    return Qb(F.linear(x, p[prefix + "fc.weight"], p[prefix + "fc.bias"]), q)
+
+
+def neck_v1(feat, p, prefix="", with_avg_pool=True, q=False):
     """NonLinearNeckV1 (base_neck.py:67-94): avgpool -> fc -> relu -> fc; weights here are [out, in]."""
-    x = feat.mean(dim=(2, 3)) if (with_avg_pool and feat.dim() == 4) else feat.reshape(feat.shape[0], -1)
-    x = F.relu(F.linear(x, p[prefix + "fc1.weight"], p[prefix + "fc1.bias"]))
-    return F.linear(x, p[prefix + "fc2.weight"], p[prefix + "fc2.bias"])
+    x = _neck_in(feat, with_avg_pool, q)
+    x = Q(F.relu(F.linear(x, p[prefix + "fc1.weight"], p[prefix + "fc1.bias"])), q)
+    return Qb(F.linear(x, p[prefix + "fc2.weight"], p[prefix + "fc2.bias"]), q)
 
 
-def neck_fc3(feat, p, prefix=""):
+def neck_fc3(feat, p, prefix="", with_avg_pool=False, q=False):
     """NonLinearNeckfc3 (base_neck.py:209-237) incl. the trailing l2_normalize(hidden, -1)."""
-    x = feat.reshape(feat.shape[0], -1)
+    x = _neck_in(feat, with_avg_pool, q)
     for i in (1, 2, 3):
-        x = F.linear(x, p[prefix + "fc%d.weight" % i], p[prefix + "fc%d.bias" % i])
+        x = Q(F.linear(x, p[prefix + "fc%d.weight" % i], p[prefix + "fc%d.bias" % i]), q)
         x = bn_train(x, p[prefix + "bn%d.bn.weight" % i], p[prefix + "bn%d.bn.bias" % i])
-        if i < 3:
-            x = F.relu(x)
+        x = Q(F.relu(x), q) if i < 3 else Qb(x, q)        # the last BN writes fp32; its gradient arrives in bf16
     return x / torch.sqrt((x * x).sum(-1, keepdim=True) + 1e-12)
 
 

@@ -45,6 +45,8 @@ SIGNATURES = {
     "passl_b200_infonce_tc_set_debug": (c_int, [c_void_p]),
     "passl_b200_infonce_tc_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_int,
                                           c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
+    "passl_b200_infonce_tc_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_int,
+                                          c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "passl_b200_ntxent_workspace_bytes": (c_ll, [c_int]),
     "passl_b200_ntxent_co2_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_ll, c_void_p]),
     "passl_b200_ntxent_co2_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -1,26 +1,38 @@
-// Fused InfoNCE forward on tcgen05 — the headline kernel (BASELINE.json: "fused InfoNCE HBM GB/s vs roofline").
+// Fused InfoNCE forward AND backward on tcgen05 — the headline kernel (BASELINE.json: "fused InfoNCE HBM GB/s vs roofline").
 //
 //   logits[i, j] = scale * <Q_i, K_j>  are produced tile by tile in TMEM and consumed in place by an online
-//   softmax (running row max / sum) — the [N, K] logit matrix never exists in HBM.  HBM traffic is the
-//   algorithmic minimum: the key matrix (MoCo queue) is streamed exactly once by TMA, Q is read once per CTA
-//   (L2 resident).   SURVEY.md §8(d):  bytes = (2*N*D + D*K)*2 + 4*N,  C3: 16.91 MB, 4.295 GFLOP.
+//   softmax — the [N, K] logit matrix never exists in HBM.  HBM traffic is the algorithmic minimum: the key matrix
+//   (MoCo queue) is streamed exactly once by TMA, Q is read once per CTA (L2 resident).
+//   SURVEY.md §8(d):  fwd bytes = (2*N*D + D*K)*2 + 4*N  (C3: 16.91 MB, 4.295 GFLOP);  bwd re-reads the keys once.
 //
-// Replaces: paddle.matmul(q, queue) + concat + /T + CrossEntropyLoss + topk
+// Replaces: paddle.matmul(q, queue) + concat + /T + CrossEntropyLoss + topk and their autograd backward
 //           (passl_v110/modeling/architectures/moco.py:178-182, heads/contrastive_head.py:37-60),
 //           einsum('nc,mc->nm')/T + CE (passl/models/mocov3.py:187-198), CLIP logits + CE (clip.py:331-335).
 //
+// ONE launch per direction (round 1 chained three kernels: 11 of its 21 us were outside the main loop):
+//   * target logits <q_i, k+_i> (or <q_i, K[label_i]>) are computed once per row by an owner CTA (row % grid), one warp per
+//     row with coalesced loads, and published through an epoch-stamped flag in the persistent state buffer; every CTA picks
+//     them up right before its first rank comparison;
+//   * partial sums of all key slices are merged with float atomics RELATIVE to the row's own target logit
+//     (sum_j 2^(y_j - y_tgt - 64) can neither vanish — the target is one of the terms — nor overflow in practice), so no
+//     per-slice (max, sum) pairs have to be stored and re-read;
+//   * the last CTA to take a ticket turns the sums into lse / loss / top-1 / top-5 and leaves the state zeroed.
+// Main loop (per 64-key tile, per row): row max by 3-input FMNMX (also screens the rank counter: a tile whose max does not
+// exceed the target, or a row whose count already reached 5, is not counted), lazy rescale against an INTEGER running max,
+// and the exponentials split between MUFU.EX2 and a degree-4 polynomial on the FMA pipe (Cody-Waite with the magic-number
+// rounding trick; 16 MUFU lanes/clk/SM were the round-1 bound at 0.9 us per tile).
+//
 // Work decomposition: CTA = (row group of MB*128 queries) x (contiguous slice of 64-key tiles).
-//   warp 0 lane 0 : TMA producer  (key tiles through a STAGES ring, SWIZZLE_128B)
-//   warp 1 lane 0 : MMA issuer    (tcgen05.mma M=128 N=64 K=16, A = Q resident in TMEM (written once by the softmax warps
-//                                  with tcgen05.st) so only the key tile is read from shared memory; S double-buffered)
-//   warps 2..2+4*MB : softmax warps — tcgen05.ld 64 logits / thread / tile, online max+sum in the log2 domain,
-//                     rank counter for top-1 / top-5 accuracy.
-// Partials (m, l, cnt) per (row, slice) are merged by simce_finalize_kernel (shared with the fp32 variant).
+//   warp 0 : TMA producer  (key tiles through a STAGES ring, SWIZZLE_128B)
+//   warp 1 : MMA issuer    (tcgen05.mma M=128 N=64 K=16, A = Q resident in TMEM, S double-buffered;
+//                           backward: + dQ[128 x D] += P[128 x 64] * Ktile[64 x D], P (bf16) written to TMEM by the softmax
+//                           warps over the S columns they just read, key tile re-used from shared memory as MN-major B)
+//   warps 2..2+4*MB : softmax warps (one row per thread).
 #include "common.cuh"
 #include "host_utils.h"
-#include "simce_common.cuh"
 #include "../../include/passl_b200.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace pb {
@@ -28,6 +40,9 @@ namespace pb {
 constexpr int NCE_BK = 64;          // keys per tile (= MMA N)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kRefShift = 64.f;   // slice sums are accumulated relative to 2^(target + 64): no underflow, overflow only if a
+                                    // logit exceeds the target by > 130 nats (then clamped: loss finite, > 100)
+constexpr float kMagic = 12582912.f;  // 1.5 * 2^23
 
 struct InfoNceTcParams {
   CUtensorMap q_map;  // [N, D] bf16, box {64, 128}
@@ -37,13 +52,18 @@ struct InfoNceTcParams {
   const float* P;           // [N, D] fp32 positive keys (extra column) or null
   const long long* label;   // [N] or null
   const int* excl;          // [N] or null
-  float scale;
+  float scale, loss_scale;
   int N, K, D;
   int row_groups, slices, tiles;
-  float* part_m; float* part_l; int* part_cnt;  // [N, slices]
-  float* tgt;                                   // [N]
-  const float* tgt_raw;                         // [N] raw target dot products from infonce_target_kernel (PDL producer)
-  unsigned long long* dbg;                      // optional per-CTA timeline (globaltimer ns), 16 slots per CTA
+  int tgt_mode;             // 0: owner CTA computes, epoch flags (grid <= SM count); 1: every thread computes its own row
+  int poly_ok;              // exponent range allows the FMA-pipe polynomial (2.1 * scale * log2e < 120)
+  // persistent state (zeroed once by the caller, left zeroed / epoch-advanced by every launch)
+  unsigned* epoch; unsigned* ticket; unsigned* flags; float* tgt_raw; float* acc_l; unsigned* acc_cnt;
+  // forward outputs
+  float* lse; float* tgt; float* loss_rows; float* out;
+  // backward
+  const float* lse_in; const float* tgt_in; const float* dloss; float* dq;
+  unsigned long long* dbg;  // optional per-CTA timeline (globaltimer ns), 16 slots per CTA
 };
 
 __device__ __forceinline__ unsigned long long gtime() {
@@ -53,139 +73,258 @@ __device__ __forceinline__ unsigned long long gtime() {
 }
 #define NCE_STAMP(slot) do { if (p.dbg) p.dbg[blockIdx.x * 16 + (slot)] = gtime(); } while (0)
 
-// Target logits <q_i, k+_i> (MoCo: P = positive keys, fp32) or <q_i, K[label_i]> (MoCo v3 / CLIP), one warp per row with whole-row
-// coalesced loads.  Runs as the programmatic-dependent-launch PRODUCER of the main kernel: it releases its dependents at once,
-// so the main kernel's setup (barriers, TMEM, Q staging, first key tiles) overlaps it; the main kernel waits
-// (griddepcontrol.wait) just before it needs the 1 KB of results.  Previously every CTA recomputed all its rows' targets
-// (148 x 128 KB of L2 reads, ~8 us of latency-bound prologue).
-__global__ void __launch_bounds__(256) infonce_target_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __restrict__ Kmat,
-                                                             const float* __restrict__ P, const long long* __restrict__ label,
-                                                             float* __restrict__ tgt_raw, unsigned* __restrict__ ticket, int N, int K,
-                                                             int D) {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  if (blockIdx.x == 0 && threadIdx.x == 0) *ticket = 0u;   // finalize's last-block ticket (it runs two grids later): no memset node
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= N) return;
-  float acc = 0.f;
-  long long lab = 0;
-  if (!P) {
-    lab = label[row];
-    lab = lab < 0 ? 0 : (lab >= K ? K - 1 : lab);
-  }
-  for (int d4 = lane * 4; d4 < D; d4 += 128) {
-    const uint2 qu = *reinterpret_cast<const uint2*>(Q + (size_t)row * D + d4);
-    const float2 q0 = unpack_bf16x2(qu.x), q1 = unpack_bf16x2(qu.y);
-    if (P) {
-      const float4 pa = *reinterpret_cast<const float4*>(P + (size_t)row * D + d4);
-      acc += q0.x * pa.x + q0.y * pa.y + q1.x * pa.z + q1.y * pa.w;
-    } else {
-      const uint2 ku = *reinterpret_cast<const uint2*>(Kmat + (size_t)lab * D + d4);
-      const float2 k0 = unpack_bf16x2(ku.x), k1 = unpack_bf16x2(ku.y);
-      acc += q0.x * k0.x + q0.y * k0.y + q1.x * k1.x + q1.y * k1.y;
-    }
-  }
-  acc = warp_sum(acc);
-  if (lane == 0) tgt_raw[row] = acc;
+__device__ __forceinline__ float ex2_mufu(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// 2^(a*c2 - mn) on the FMA pipe.  C = kMagic - mn with mn integer-valued, mn >= every a*c2 of the tile.
+//   r = a*c2 + C rounds to C + j, j = round(a*c2); x = a*c2 - j in [-0.5, 0.5]; 2^x by a degree-4 minimax polynomial
+//   (max rel. error 2.9e-6, oscillating); the exponent j - mn (<= 0, > -126 by the host's poly_ok check) is the low bits of r.
+__device__ __forceinline__ float ex2_poly(float a, float c2, float C) {
+  const float r = __fmaf_rn(a, c2, C);
+  const float jf = __fsub_rn(r, C);
+  const float x = __fmaf_rn(a, c2, -jf);
+  float q = __fmaf_rn(x, 0.00958278775f, 0.0559062883f);
+  q = __fmaf_rn(q, x, 0.240240991f);
+  q = __fmaf_rn(q, x, 0.693124235f);
+  q = __fmaf_rn(q, x, 1.0f);
+  return __int_as_float(__float_as_int(q) + (__float_as_int(r) << 23));
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int MB>
+// ---- shared-memory carve-up (same for forward and backward) --------------------------------------------------------------
+struct NceSmem {
+  uint8_t* q_smem; uint8_t* k_smem;
+  uint64_t *q_ready, *k_full, *k_empty, *s_full, *s_empty, *q_full, *p_full, *dq_full;
+  uint32_t* tmem_ptr;
+  int stages, q_bytes, stage_bytes;
+};
+__device__ __forceinline__ NceSmem nce_carve(uint8_t* smem_raw, int MB, int D) {
+  NceSmem s;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  s.q_bytes = MB * 128 * D * 2;
+  s.stage_bytes = NCE_BK * D * 2;
+  s.stages = (200 * 1024 - s.q_bytes) / s.stage_bytes;   // same rule as nce_plan() on the host
+  if (s.stages > 8) s.stages = 8;
+  s.q_smem = smem;                                       // staging only: rows go smem -> registers -> TMEM
+  s.k_smem = smem + s.q_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s.k_smem + s.stages * s.stage_bytes);
+  s.q_ready = bars;           // 4*MB softmax-warp arrivals: Q rows are in TMEM
+  s.k_full = bars + 1;        // 8
+  s.k_empty = s.k_full + 8;   // 8
+  s.s_full = s.k_empty + 8;   // 2
+  s.s_empty = s.s_full + 2;   // 2
+  s.q_full = s.s_empty + 2;   // 1
+  s.p_full = s.q_full + 1;    // 2 (backward)
+  s.dq_full = s.p_full + 2;   // 1 (backward)
+  s.tmem_ptr = reinterpret_cast<uint32_t*>(s.dq_full + 1);
+  return s;
+}
+
+// TMA producer (whole warp 0): Q block once, then the key tiles of [t_begin, t_end) through the ring
+__device__ __forceinline__ void nce_producer(const InfoNceTcParams& p, const NceSmem& s, int MB, int row_base, int t_begin, int t_end) {
+  const int DC = p.D / 64;
+  if (elect_one()) {
+    mbar_arrive_expect_tx(s.q_full, (uint32_t)s.q_bytes);
+    for (int b = 0; b < MB; ++b)
+      for (int c = 0; c < DC; ++c)
+        tma_load_2d(s.q_smem + (b * DC + c) * (128 * 128), &p.q_map, s.q_full, c * 64, row_base + b * 128);
+  }
+  __syncwarp();
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int t = t_begin; t < t_end; ++t) {
+    mbar_wait(&s.k_empty[stage], phase ^ 1);
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&s.k_full[stage], (uint32_t)s.stage_bytes);
+      for (int c = 0; c < DC; ++c)
+        tma_load_2d(s.k_smem + stage * s.stage_bytes + c * (NCE_BK * 128), &p.k_map, &s.k_full[stage], c * 64, t * NCE_BK);
+    }
+    __syncwarp();
+    if (++stage == s.stages) { stage = 0; phase ^= 1; }
+  }
+}
+
+// softmax-warp prologue, part 1 (before anything can block): target logits of the rows this CTA owns (tgt_mode 0)
+__device__ __forceinline__ void nce_owner_targets(const InfoNceTcParams& p, int ew, int nsw, uint32_t lane, unsigned epoch) {
+  if (p.tgt_mode != 0) return;
+  for (int row = (int)blockIdx.x + ew * (int)gridDim.x; row < p.N; row += nsw * (int)gridDim.x) {
+    float acc = 0.f;
+    long long lab = 0;
+    if (!p.P) {
+      lab = p.label[row];
+      lab = lab < 0 ? 0 : (lab >= p.K ? p.K - 1 : lab);
+    }
+    for (int d4 = lane * 4; d4 < p.D; d4 += 128) {
+      const uint2 qu = *reinterpret_cast<const uint2*>(p.Q + (size_t)row * p.D + d4);
+      const float2 q0 = unpack_bf16x2(qu.x), q1 = unpack_bf16x2(qu.y);
+      if (p.P) {
+        const float4 pa = *reinterpret_cast<const float4*>(p.P + (size_t)row * p.D + d4);
+        acc += q0.x * pa.x + q0.y * pa.y + q1.x * pa.z + q1.y * pa.w;
+      } else {
+        const uint2 ku = *reinterpret_cast<const uint2*>(p.Kmat + (size_t)lab * p.D + d4);
+        const float2 k0 = unpack_bf16x2(ku.x), k1 = unpack_bf16x2(ku.y);
+        acc += q0.x * k0.x + q0.y * k0.y + q1.x * k1.x + q1.y * k1.y;
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      p.tgt_raw[row] = acc;
+      st_release_u32(p.flags + row, epoch + 1u);
+    }
+  }
+}
+
+// part 2: Q block smem -> registers -> TMEM (A operand of every S MMA), then arrive on q_ready
+__device__ __forceinline__ void nce_stage_q(const InfoNceTcParams& p, const NceSmem& s, uint32_t tm_q, int b, uint32_t q4, uint32_t lane) {
+  const int DC = p.D / 64;
+  const uint32_t q_cols = p.D / 2;
+  const int rl = q4 * 32 + lane;                       // row inside the 128-row block
+  mbar_wait(s.q_full, 0);
+  const uint32_t tq = tm_q + ((q4 * 32u) << 16) + b * q_cols;
+  for (int ch = 0; ch < DC; ++ch) {
+    const uint8_t* base = s.q_smem + (b * DC + ch) * (128 * 128) + (rl >> 3) * 1024 + (rl & 7) * 128;
+    uint32_t w[32];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const uint4 u = *reinterpret_cast<const uint4*>(base + (((g ^ (rl & 7)) & 7) << 4));
+      w[g * 4 + 0] = u.x; w[g * 4 + 1] = u.y; w[g * 4 + 2] = u.z; w[g * 4 + 3] = u.w;
+    }
+    tmem_st_32x32(tq + ch * 32, w);
+  }
+  tmem_st_wait();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(s.q_ready);
+}
+
+// part 3: the row's raw target dot product
+__device__ __forceinline__ float nce_fetch_target(const InfoNceTcParams& p, int row, bool row_ok, unsigned epoch) {
+  if (!row_ok) return 0.f;
+  if (p.tgt_mode == 0) {
+    if (ld_acquire_u32(p.flags + row) != epoch + 1u) {
+      const long long t0 = clock64();
+      while (ld_acquire_u32(p.flags + row) != epoch + 1u) {
+        if (clock64() - t0 > 4000000000LL) {
+          printf("passl_b200: InfoNCE target flag timeout (block %d row %d)\n", blockIdx.x, row);
+          __trap();
+        }
+      }
+    }
+    return __ldcg(p.tgt_raw + row);
+  }
+  float acc = 0.f;
+  long long lab = 0;
+  if (!p.P) {
+    lab = p.label[row];
+    lab = lab < 0 ? 0 : (lab >= p.K ? p.K - 1 : lab);
+  }
+  for (int d = 0; d < p.D; d += 2) {
+    const float2 q2 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.Q + (size_t)row * p.D + d));
+    if (p.P) {
+      acc = fmaf(q2.x, p.P[(size_t)row * p.D + d], acc);
+      acc = fmaf(q2.y, p.P[(size_t)row * p.D + d + 1], acc);
+    } else {
+      const float2 k2 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.Kmat + (size_t)lab * p.D + d));
+      acc = fmaf(q2.x, k2.x, acc);
+      acc = fmaf(q2.y, k2.y, acc);
+    }
+  }
+  return acc;
+}
+
+__device__ __forceinline__ void nce_setup(const InfoNceTcParams& p, const NceSmem& s, int MB, uint32_t warp, uint32_t lane, bool bwd) {
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.q_map);
+    tma_prefetch_desc(&p.k_map);
+    mbar_init(s.q_ready, 4 * MB);
+    mbar_init(s.q_full, 1);
+    for (int i = 0; i < s.stages; ++i) {
+      mbar_init(&s.k_full[i], 1);
+      mbar_init(&s.k_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s.s_full[i], 1);
+      mbar_init(&s.s_empty[i], 4 * MB);
+      mbar_init(&s.p_full[i], 4);
+    }
+    mbar_init(s.dq_full, 1);
+    fence_barrier_init();
+  }
+  (void)bwd;
+  if (warp == 1) tmem_alloc(s.tmem_ptr, 512);
+  // programmatic dependent launch: everything above overlaps the tail of the previous kernel in the stream; nothing below
+  // (global reads of Q / keys / state, global writes) may start before that kernel has completed and flushed
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+}
+
+// =====================================================================================================================
+// forward
+// =====================================================================================================================
+template <int MB, int PN, int PD>
 __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const __grid_constant__ InfoNceTcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int DC = p.D / 64;                       // 64-wide feature chunks
-  const int q_bytes = MB * 128 * p.D * 2;
-  const int stage_bytes = NCE_BK * p.D * 2;
-  int STAGES = (200 * 1024 - q_bytes) / stage_bytes;   // same rule as nce_plan() on the host
-  if (STAGES > 8) STAGES = 8;
-  uint8_t* q_smem = smem;                              // staging only: rows go smem -> registers -> TMEM
-  uint8_t* k_smem = smem + q_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(k_smem + STAGES * stage_bytes);
-  uint64_t* q_ready = bars;           // 4*MB softmax-warp arrivals: Q rows are in TMEM
-  uint64_t* k_full = bars + 1;        // STAGES
-  uint64_t* k_empty = k_full + 8;     // STAGES
-  uint64_t* s_full = k_empty + 8;     // 2
-  uint64_t* s_empty = s_full + 2;     // 2
-  uint64_t* q_full = s_empty + 2;     // TMA: Q block staged in shared memory
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(q_full + 1);
-
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the finalize grid may be scheduled early (it waits for us)
+  __shared__ float red[3][4 * MB + 2];
+  __shared__ int s_is_last;
+  const NceSmem s = nce_carve(smem_raw, MB, p.D);
+  const int DC = p.D / 64;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const uint32_t warp = warp_id(), lane = lane_id();
   const int group = blockIdx.x / p.slices;
   const int slice = blockIdx.x - group * p.slices;
   const int row_base = group * MB * 128;
   const int t_begin = (int)((long long)slice * p.tiles / p.slices);
   const int t_end = (int)((long long)(slice + 1) * p.tiles / p.slices);
-  constexpr uint32_t TMEM_COLS = 512;
   const uint32_t q_cols = p.D / 2;                 // bf16x2 per 32-bit TMEM column
 
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.q_map);
-    tma_prefetch_desc(&p.k_map);
-    mbar_init(q_ready, 4 * MB);
-    mbar_init(q_full, 1);
-    for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 4 * MB);
-    }
-    fence_barrier_init();
-  }
   if (threadIdx.x == 64) NCE_STAMP(0);
-  if (warp == 1) tmem_alloc(tmem_ptr, TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
+  nce_setup(p, s, MB, warp, lane, false);
   if (threadIdx.x == 64) NCE_STAMP(1);
-  const uint32_t tmem_base = *tmem_ptr;
+  const unsigned epoch = __ldcg(p.epoch);
+  const uint32_t tmem_base = *s.tmem_ptr;
   const uint32_t tm_q = tmem_base;                       // Q (A operand): block b at columns [b*q_cols, (b+1)*q_cols)
   const uint32_t tm_s = tmem_base + MB * q_cols;         // S accumulators: (buf*MB + b) * 64
 
   // role loops are warp-uniform; only the TMA / tcgen05 issue is elect-predicated (keeps descriptors in uniform registers)
   if (warp == 0) {
-    {
-      // ---------------- TMA producer ----------------
-      if (elect_one()) {
-        mbar_arrive_expect_tx(q_full, (uint32_t)q_bytes);
-        for (int b = 0; b < MB; ++b)
-          for (int c = 0; c < DC; ++c)
-            tma_load_2d(q_smem + (b * DC + c) * (128 * 128), &p.q_map, q_full, c * 64, row_base + b * 128);
-      }
-      __syncwarp();
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = t_begin; t < t_end; ++t) {
-        mbar_wait(&k_empty[stage], phase ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&k_full[stage], (uint32_t)stage_bytes);
-          for (int c = 0; c < DC; ++c)
-            tma_load_2d(k_smem + stage * stage_bytes + c * (NCE_BK * 128), &p.k_map, &k_full[stage], c * 64, t * NCE_BK);
-        }
-        __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-      }
-    }
+    nce_producer(p, s, MB, row_base, t_begin, t_end);
   } else if (warp == 1) {
-    {
-      // ---------------- MMA issuer ----------------
-      constexpr uint32_t idesc = make_idesc_bf16(128, NCE_BK, false, false);
-      const uint64_t db0 = make_smem_desc_sw128(smem_u32(k_smem), 16, 1024);   // stage 0, chunk 0, k-step 0
-      mbar_wait(q_ready, 0);
+    // ---------------- MMA issuer ----------------
+    constexpr uint32_t idesc = make_idesc_bf16(128, NCE_BK, false, false);
+    const uint64_t db0 = make_smem_desc_sw128(smem_u32(s.k_smem), 16, 1024);   // stage 0, chunk 0, k-step 0
+    mbar_wait(s.q_ready, 0);
+    tc_fence_after();
+    if (lane == 0) NCE_STAMP(14);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = t_begin; t < t_end; ++t, ++it) {
+      const int buf = it & 1;
+      const uint32_t bphase = (it >> 1) & 1;
+      mbar_wait(&s.s_empty[buf], bphase ^ 1);
+      mbar_wait(&s.k_full[stage], phase);
       tc_fence_after();
-      if (lane == 0) NCE_STAMP(14);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int t = t_begin; t < t_end; ++t, ++it) {
-        const int buf = it & 1;
-        const uint32_t bphase = (it >> 1) & 1;
-        mbar_wait(&s_empty[buf], bphase ^ 1);
-        mbar_wait(&k_full[stage], phase);
-        tc_fence_after();
-        const uint64_t dbs = db0 + (uint64_t)((stage * stage_bytes) >> 4);
-        if (elect_one()) {
+      const uint64_t dbs = db0 + (uint64_t)((stage * s.stage_bytes) >> 4);
+      if (elect_one()) {
         for (int b = 0; b < MB; ++b) {
           const uint32_t d_tmem = tm_s + (buf * MB + b) * NCE_BK;
           const uint32_t a_tmem = tm_q + b * q_cols;
@@ -196,12 +335,11 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
                            (c > 0 || k > 0) ? 1u : 0u);
           }
         }
-        umma_commit(&k_empty[stage]);
-        umma_commit(&s_full[buf]);
-        }
-        __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        umma_commit(&s.k_empty[stage]);
+        umma_commit(&s.s_full[buf]);
       }
+      __syncwarp();
+      if (++stage == s.stages) { stage = 0; phase ^= 1; }
     }
   } else {
     // ---------------- softmax warps ----------------
@@ -212,50 +350,26 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
     const bool row_ok = row < p.N;
     const float c2 = p.scale * kLog2e;  // logits in the log2 domain: y = dot * c2
 
-    // Prologue: Q block arrives by TMA in shared memory; each thread copies its own row smem -> registers -> TMEM (A operand
-    // of every MMA); the target logit of the row (positive pair or labelled column) is read from the producer kernel's output.
-    float tgt2 = 0.f, tgt_raw = 0.f;
+    nce_owner_targets(p, ew, 4 * MB, lane, epoch);
+    nce_stage_q(p, s, tm_q, b, q4, lane);
+    if (threadIdx.x == 64) NCE_STAMP(3);
     long long lab = -1;
     int ex = -1;
-    {
-      const int rl = q4 * 32 + lane;                       // row inside the 128-row block
-      mbar_wait(q_full, 0);
-      if (threadIdx.x == 64) NCE_STAMP(2);
-      const uint32_t tq = tm_q + ((q4 * 32u) << 16) + b * q_cols;
-      for (int ch = 0; ch < DC; ++ch) {
-        const uint8_t* base = q_smem + (b * DC + ch) * (128 * 128) + (rl >> 3) * 1024 + (rl & 7) * 128;
-        uint32_t w[32];
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const uint4 u = *reinterpret_cast<const uint4*>(base + (((g ^ (rl & 7)) & 7) << 4));
-          w[g * 4 + 0] = u.x; w[g * 4 + 1] = u.y; w[g * 4 + 2] = u.z; w[g * 4 + 3] = u.w;
-        }
-        tmem_st_32x32(tq + ch * 32, w);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(q_ready);
-      if (threadIdx.x == 64) NCE_STAMP(3);
-      if (row_ok) {
-        if (!p.P) lab = p.label[row];
-        if (p.excl) ex = p.excl[row];
-      }
-      // targets come from infonce_target_kernel (PDL producer): block here, as late as possible, until that grid has completed
-      asm volatile("griddepcontrol.wait;" ::: "memory");
-      const float s_mine = row_ok ? __ldcg(p.tgt_raw + row) : 0.f;
-      tgt2 = s_mine * c2;
-      tgt_raw = s_mine;
-      if (threadIdx.x == 64) NCE_STAMP(4);
+    if (row_ok) {
+      if (!p.P) lab = p.label[row];
+      if (p.excl) ex = p.excl[row];
     }
+    const float tgt_raw = nce_fetch_target(p, row, row_ok, epoch);
+    const float tgt2 = tgt_raw * c2;
+    if (threadIdx.x == 64) NCE_STAMP(4);
 
-    float m = -INFINITY, l = 0.f;
+    float m = -INFINITY, l = 0.f;     // m: integer-valued running max (log2 domain)
     int cnt = 0;
     int it = 0;
     for (int t = t_begin; t < t_end; ++t, ++it) {
       const int buf = it & 1;
       const uint32_t bphase = (it >> 1) & 1;
-      mbar_wait(&s_full[buf], bphase);
+      mbar_wait(&s.s_full[buf], bphase);
       tc_fence_after();
       if (threadIdx.x == 64 && it < 8) NCE_STAMP(5 + it);
       const uint32_t taddr = tm_s + ((q4 * 32u) << 16) + (buf * MB + b) * NCE_BK;
@@ -266,42 +380,60 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
       // TMEM buffer can be refilled as soon as the values are in registers
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[buf]);
+      if (lane == 0) mbar_arrive(&s.s_empty[buf]);
 
       const int key0 = t * NCE_BK;
       const bool special = (key0 + NCE_BK > p.K) || (ex >= key0 && ex < key0 + NCE_BK) ||
                            (lab >= key0 && lab < key0 + NCE_BK);
-      if (!special) {
-        // fast path (instruction diet): work on the raw dot products — max is monotone in the positive scale, the scaling
-        // and the max subtraction fold into one FFMA in front of ex2, the rank counter uses set.gt + FADD on 4 chains.
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-        float c0 = 0.f, c1 = 0.f, c2n = 0.f, c3 = 0.f;
+      if (!__any_sync(0xffffffffu, special)) {
+        // fast path: everything on the raw dot products (max is monotone in the positive scale)
+        float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
         for (int j = 0; j < 64; j += 4) {
-          const float a0 = __uint_as_float(v[j]), a1 = __uint_as_float(v[j + 1]), a2 = __uint_as_float(v[j + 2]),
-                      a3 = __uint_as_float(v[j + 3]);
-          mx0 = fmaxf(mx0, a0); mx1 = fmaxf(mx1, a1); mx2 = fmaxf(mx2, a2); mx3 = fmaxf(mx3, a3);
-          float g0, g1, g2, g3;
-          asm("set.gt.f32.f32 %0, %1, %2;" : "=f"(g0) : "f"(a0), "f"(tgt_raw));
-          asm("set.gt.f32.f32 %0, %1, %2;" : "=f"(g1) : "f"(a1), "f"(tgt_raw));
-          asm("set.gt.f32.f32 %0, %1, %2;" : "=f"(g2) : "f"(a2), "f"(tgt_raw));
-          asm("set.gt.f32.f32 %0, %1, %2;" : "=f"(g3) : "f"(a3), "f"(tgt_raw));
-          c0 += g0; c1 += g1; c2n += g2; c3 += g3;
+          mx0 = max3(mx0, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+          mx1 = max3(mx1, __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
         }
-        cnt += (int)((c0 + c1) + (c2n + c3));
-        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c2;
-        const float mn = fmaxf(m, mx);
+        const float mx = fmaxf(mx0, mx1);
+        // rank counter, screened: only rows that can still change (count < 5) and only tiles that contain a larger logit
+        if (__any_sync(0xffffffffu, cnt < 5 && mx > tgt_raw)) {
+          float c0 = 0.f, c1 = 0.f, c2n = 0.f, c3 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 64; j += 4) {
+            float g0, g1, g2, g3;
+            asm("set.gt.f32.f32 %0, %1, %2;" : "=f"(g0) : "f"(__uint_as_float(v[j])), "f"(tgt_raw));
+            asm("set.gt.f32.f32 %0, %1, %2;" : "=f"(g1) : "f"(__uint_as_float(v[j + 1])), "f"(tgt_raw));
+            asm("set.gt.f32.f32 %0, %1, %2;" : "=f"(g2) : "f"(__uint_as_float(v[j + 2])), "f"(tgt_raw));
+            asm("set.gt.f32.f32 %0, %1, %2;" : "=f"(g3) : "f"(__uint_as_float(v[j + 3])), "f"(tgt_raw));
+            c0 += g0; c1 += g1; c2n += g2; c3 += g3;
+          }
+          cnt += (int)((c0 + c1) + (c2n + c3));
+        }
+        const float mn = fmaxf(m, ceilf(mx * c2));
+        if (mn > m) { l *= ex2_mufu(m - mn); m = mn; }
+        const float negm = -mn, C = kMagic - mn;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        if (PN > 0 && p.poly_ok) {
 #pragma unroll
-        for (int j = 0; j < 64; j += 4) {
-          s0 += exp2f(fmaf(__uint_as_float(v[j]), c2, -mn));
-          s1 += exp2f(fmaf(__uint_as_float(v[j + 1]), c2, -mn));
-          s2 += exp2f(fmaf(__uint_as_float(v[j + 2]), c2, -mn));
-          s3 += exp2f(fmaf(__uint_as_float(v[j + 3]), c2, -mn));
+          for (int j = 0; j < 64; j += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float a = __uint_as_float(v[j + u]);
+              const float e = (((j + u) % PD) < PN) ? ex2_poly(a, c2, C) : ex2_mufu(fmaf(a, c2, negm));
+              if (u == 0) s0 += e; else if (u == 1) s1 += e; else if (u == 2) s2 += e; else s3 += e;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 64; j += 4) {
+            s0 += ex2_mufu(fmaf(__uint_as_float(v[j]), c2, negm));
+            s1 += ex2_mufu(fmaf(__uint_as_float(v[j + 1]), c2, negm));
+            s2 += ex2_mufu(fmaf(__uint_as_float(v[j + 2]), c2, negm));
+            s3 += ex2_mufu(fmaf(__uint_as_float(v[j + 3]), c2, negm));
+          }
         }
-        l = l * exp2f(m - mn) + ((s0 + s1) + (s2 + s3));
-        m = mn;
+        l += (s0 + s1) + (s2 + s3);
       } else {
+        // tiles holding the K tail, an excluded column or the labelled column: masked, all on MUFU
         float y[64];
         float mx = -INFINITY;
 #pragma unroll
@@ -313,22 +445,266 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
           cnt += (ok && key != lab && y[j] > tgt2) ? 1 : 0;
         }
         if (mx > -INFINITY) {
-          const float mn = fmaxf(m, mx);
-          float s = 0.f;
+          const float mn = fmaxf(m, ceilf(mx));
+          float sum = 0.f;
 #pragma unroll
-          for (int j = 0; j < 64; ++j) s += exp2f(y[j] - mn);
-          l = l * exp2f(m - mn) + s;
+          for (int j = 0; j < 64; ++j) sum += ex2_mufu(y[j] - mn);
+          l = l * ex2_mufu(m - mn) + sum;
           m = mn;
         }
       }
     }
     if (threadIdx.x == 64) NCE_STAMP(13);
     if (row_ok) {
-      // back to the natural-log domain used by simce_finalize_kernel
-      p.part_m[(size_t)row * p.slices + slice] = m * kLn2;
-      p.part_l[(size_t)row * p.slices + slice] = l;
-      p.part_cnt[(size_t)row * p.slices + slice] = cnt;
-      if (slice == 0) p.tgt[row] = tgt2 * kLn2;
+      // slice sum relative to 2^(target + 64); merged over the slices by float atomics (order-dependent in the last bit)
+      if (m > -INFINITY) {
+        const float e = fminf(m - (tgt2 + kRefShift), 100.f);
+        atomicAdd(p.acc_l + row, l * ex2_mufu(e));
+      }
+      if (cnt > 0) atomicAdd(p.acc_cnt + row, (unsigned)(cnt < 5 ? cnt : 5));
+    }
+    __threadfence();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+  // ---------------- last CTA: sums -> lse / loss / accuracies; state back to zero ----------------
+  if (threadIdx.x == 0) {
+    const unsigned old = atomicInc(p.ticket, gridDim.x - 1);   // wraps back to 0 by itself
+    s_is_last = (old == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_is_last) return;
+  __threadfence();
+  float s_loss = 0.f, s_a1 = 0.f, s_a5 = 0.f;
+  const float c2 = p.scale * kLog2e;
+  for (int row = threadIdx.x; row < p.N; row += blockDim.x) {
+    float L = __ldcg(p.acc_l + row);
+    const unsigned cnt = __ldcg(p.acc_cnt + row);
+    p.acc_l[row] = 0.f;
+    p.acc_cnt[row] = 0u;
+    const float tgt2 = __ldcg(p.tgt_raw + row) * c2;
+    if (p.P) L += 5.421010862427522e-20f;                 // the positive pair's own column: 2^(tgt - (tgt + 64))
+    const float lse = (tgt2 + kRefShift + log2f(L)) * kLn2;
+    const float t = tgt2 * kLn2;
+    const float li = lse - t;
+    p.lse[row] = lse;
+    p.tgt[row] = t;
+    if (p.loss_rows) p.loss_rows[row] = li;
+    s_loss += li;
+    s_a1 += (cnt == 0u) ? 1.f : 0.f;
+    s_a5 += (cnt < 5u) ? 1.f : 0.f;
+  }
+  s_loss = warp_sum(s_loss); s_a1 = warp_sum(s_a1); s_a5 = warp_sum(s_a5);
+  if (lane == 0) { red[0][warp] = s_loss; red[1][warp] = s_a1; red[2][warp] = s_a5; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, bb = 0.f, c = 0.f;
+    for (int w = 0; w < 2 + 4 * MB; ++w) { a += red[0][w]; bb += red[1][w]; c += red[2][w]; }
+    p.out[0] = p.loss_scale * a / p.N;
+    p.out[1] = 100.f * bb / p.N;
+    p.out[2] = 100.f * c / p.N;
+    *p.epoch = epoch + 1u;
+  }
+}
+
+// =====================================================================================================================
+// backward (queries only: keys / queue / positive keys are no-grad in the reference, moco.py:162-180, mocov3.py:173-198)
+//   dQ_i = scale * g * ( sum_j p_ij K_j  +  (p_i,pos - 1) k+_i   |   - K[label_i] ),   p_ij = exp(scale <q_i,K_j> - lse_i),
+//   g = dloss * loss_scale / N.   P tiles are rounded to bf16 for the second MMA (fp32 accumulation in TMEM).
+// =====================================================================================================================
+template <int MB, int PN, int PD>
+__global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_bwd_kernel(const __grid_constant__ InfoNceTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const NceSmem s = nce_carve(smem_raw, MB, p.D);
+  const int DC = p.D / 64;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const uint32_t warp = warp_id(), lane = lane_id();
+  const int group = blockIdx.x / p.slices;
+  const int slice = blockIdx.x - group * p.slices;
+  const int row_base = group * MB * 128;
+  const int t_begin = (int)((long long)slice * p.tiles / p.slices);
+  const int t_end = (int)((long long)(slice + 1) * p.tiles / p.slices);
+  const uint32_t q_cols = p.D / 2;
+
+  nce_setup(p, s, MB, warp, lane, true);
+  const uint32_t tmem_base = *s.tmem_ptr;
+  const uint32_t tm_q = tmem_base;                        // Q: block b at [b*q_cols, ...)
+  const uint32_t tm_dq = tmem_base + MB * q_cols;         // dQ accumulators: block b at b*D (fp32)
+  const uint32_t tm_sp = tm_dq + MB * p.D;                // S (fp32, 64 cols) / P (bf16x2, 32 cols) per block: b*64
+
+  if (warp == 0) {
+    nce_producer(p, s, MB, row_base, t_begin, t_end);
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, NCE_BK, false, false);
+    const uint32_t idesc_pv = make_idesc_bf16(128, (uint32_t)p.D, false, true);     // B = key tile, MN-major (d contiguous)
+    const uint64_t dbk0 = make_smem_desc_sw128(smem_u32(s.k_smem), 16, 1024);               // K-major view (S = Q K^T)
+    const uint64_t dbm0 = make_smem_desc_sw128(smem_u32(s.k_smem), NCE_BK * 128, 1024);     // MN-major view (dQ += P K)
+    mbar_wait(s.q_ready, 0);
+    tc_fence_after();
+    auto issue_s = [&](int b, int stage) {
+      const uint64_t dbs = dbk0 + (uint64_t)((stage * s.stage_bytes) >> 4);
+      const uint32_t d_tmem = tm_sp + b * NCE_BK;
+      const uint32_t a_tmem = tm_q + b * q_cols;
+      for (int c = 0; c < DC; ++c) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ts(d_tmem, a_tmem + c * 32 + k * 8, dbs + (uint64_t)((c * (NCE_BK * 128) + k * 32) >> 4), idesc_s,
+                       (c > 0 || k > 0) ? 1u : 0u);
+      }
+    };
+    // first tile: S of every block
+    mbar_wait(&s.k_full[0], 0);
+    tc_fence_after();
+    if (elect_one()) {
+      for (int b = 0; b < MB; ++b) {
+        issue_s(b, 0);
+        umma_commit(&s.s_full[b]);
+      }
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = t_begin; t < t_end; ++t, ++it) {
+      int nstage = stage + 1;
+      uint32_t nphase = phase;
+      if (nstage == s.stages) { nstage = 0; nphase ^= 1; }
+      const bool has_next = (t + 1 < t_end);
+      if (has_next) mbar_wait(&s.k_full[nstage], nphase);
+      for (int b = 0; b < MB; ++b) {
+        mbar_wait(&s.p_full[b], it & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          // dQ_b += P_b (TMEM, 4 k-steps of 16 keys) * Ktile (MN-major: +2048 B per 16 key rows)
+          const uint64_t dbm = dbm0 + (uint64_t)((stage * s.stage_bytes) >> 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ts(tm_dq + b * p.D, tm_sp + b * NCE_BK + k * 8, dbm + (uint64_t)((k * 2048) >> 4), idesc_pv,
+                         (it > 0 || k > 0) ? 1u : 0u);
+          if (b == MB - 1) umma_commit(&s.k_empty[stage]);
+          if (has_next) {
+            issue_s(b, nstage);                 // in order behind the PV MMA that reads the same TMEM columns
+            umma_commit(&s.s_full[b]);
+          }
+        }
+        __syncwarp();
+      }
+      stage = nstage; phase = nphase;
+    }
+    if (elect_one()) umma_commit(s.dq_full);
+    __syncwarp();
+  } else {
+    // ---------------- softmax warps ----------------
+    const int ew = warp - 2;
+    const int b = ew >> 2;
+    const uint32_t q4 = warp & 3;
+    const int row = row_base + b * 128 + q4 * 32 + lane;
+    const bool row_ok = row < p.N;
+    const float c2 = p.scale * kLog2e;
+
+    nce_stage_q(p, s, tm_q, b, q4, lane);
+    long long lab = -1;
+    int ex = -1;
+    float L2 = 0.f;
+    if (row_ok) {
+      if (!p.P) lab = p.label[row];
+      if (p.excl) ex = p.excl[row];
+      L2 = p.lse_in[row] * kLog2e;
+    }
+    const float Lc = ceilf(L2);           // integer-valued: p' = 2^(y - Lc) <= 1, true p = p' * 2^(Lc - L2)
+    const float negL = -Lc, C = kMagic - Lc;
+    const uint32_t taddr = tm_sp + ((q4 * 32u) << 16) + b * NCE_BK;
+
+    int it = 0;
+    for (int t = t_begin; t < t_end; ++t, ++it) {
+      mbar_wait(&s.s_full[b], it & 1);
+      tc_fence_after();
+      uint32_t v[64];
+      tmem_ld_32x32(taddr, v);
+      tmem_ld_32x32(taddr + 32, v + 32);
+      tmem_ld_wait();
+      const int key0 = t * NCE_BK;
+      const bool special = (key0 + NCE_BK > p.K) || (ex >= key0 && ex < key0 + NCE_BK);
+      uint32_t w[32];
+      if (!__any_sync(0xffffffffu, special)) {
+        if (PN > 0 && p.poly_ok) {
+#pragma unroll
+          for (int j = 0; j < 64; j += 2) {
+            const float a0 = __uint_as_float(v[j]), a1 = __uint_as_float(v[j + 1]);
+            const float e0 = ((j % PD) < PN) ? ex2_poly(a0, c2, C) : ex2_mufu(fmaf(a0, c2, negL));
+            const float e1 = (((j + 1) % PD) < PN) ? ex2_poly(a1, c2, C) : ex2_mufu(fmaf(a1, c2, negL));
+            w[j >> 1] = pack_bf16x2(e0, e1);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 64; j += 2)
+            w[j >> 1] = pack_bf16x2(ex2_mufu(fmaf(__uint_as_float(v[j]), c2, negL)),
+                                    ex2_mufu(fmaf(__uint_as_float(v[j + 1]), c2, negL)));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 64; j += 2) {
+          const int k0 = key0 + j, k1 = key0 + j + 1;
+          const float e0 = (k0 < p.K && k0 != ex) ? ex2_mufu(fmaf(__uint_as_float(v[j]), c2, negL)) : 0.f;
+          const float e1 = (k1 < p.K && k1 != ex) ? ex2_mufu(fmaf(__uint_as_float(v[j + 1]), c2, negL)) : 0.f;
+          w[j >> 1] = pack_bf16x2(e0, e1);
+        }
+      }
+      tmem_st_32x32(taddr, w);          // P over the first 32 of the S columns this thread has just read
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.p_full[b]);
+    }
+
+    // ---------------- epilogue: dQ partial of this key slice -> global (coalesced vector reds) ----------------
+    mbar_wait(s.dq_full, 0);
+    tc_fence_after();
+    const float g = (p.dloss ? __ldg(p.dloss) : 1.f) * p.loss_scale / (float)p.N;
+    const float coef = p.scale * g;
+    const float rowfac = row_ok ? coef * ex2_mufu(Lc - L2) : 0.f;
+    // slice 0 also adds the term of the positive pair / the labelled column
+    float extra = 0.f;
+    if (slice == 0 && row_ok) extra = p.P ? coef * (__expf(p.tgt_in[row] - p.lse_in[row]) - 1.f) : -coef;
+    const long long lab_c = lab < 0 ? 0 : (lab >= p.K ? p.K - 1 : lab);
+    float* stg = reinterpret_cast<float*>(s.k_smem) + ew * (32 * 33);     // per-warp 32 x 32 transpose tile (ring is drained)
+    const int r_sub = lane >> 3, c_sub = (lane & 7) * 4;
+    for (int ch = 0; ch < p.D / 32; ++ch) {
+      uint32_t v[32];
+      tmem_ld_32x32(tm_dq + ((q4 * 32u) << 16) + b * p.D + ch * 32, v);
+      tmem_ld_wait();
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]) * rowfac;
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + r_sub;                       // row inside the warp's 32
+        const int grow = row_base + b * 128 + q4 * 32 + rr;
+        const float ex_r = __shfl_sync(0xffffffffu, extra, rr);
+        const long long lab_r = __shfl_sync(0xffffffffu, lab_c, rr);
+        float a0 = stg[rr * 33 + c_sub], a1 = stg[rr * 33 + c_sub + 1], a2 = stg[rr * 33 + c_sub + 2], a3 = stg[rr * 33 + c_sub + 3];
+        if (grow < p.N) {
+          const int col = ch * 32 + c_sub;
+          if (slice == 0) {
+            if (p.P) {
+              const float4 pk = *reinterpret_cast<const float4*>(p.P + (size_t)grow * p.D + col);
+              a0 = fmaf(ex_r, pk.x, a0); a1 = fmaf(ex_r, pk.y, a1); a2 = fmaf(ex_r, pk.z, a2); a3 = fmaf(ex_r, pk.w, a3);
+            } else {
+              const uint2 ku = *reinterpret_cast<const uint2*>(p.Kmat + (size_t)lab_r * p.D + col);
+              const float2 k0 = unpack_bf16x2(ku.x), k1 = unpack_bf16x2(ku.y);
+              a0 = fmaf(ex_r, k0.x, a0); a1 = fmaf(ex_r, k0.y, a1); a2 = fmaf(ex_r, k1.x, a2); a3 = fmaf(ex_r, k1.y, a3);
+            }
+          }
+          red_add_v4(p.dq + (size_t)grow * p.D + col, a0, a1, a2, a3);
+        }
+      }
     }
   }
 
@@ -336,7 +712,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -354,6 +730,50 @@ static void nce_plan(int N, int K, int D, int& MB, int& groups, int& slices, int
   smem = q_bytes + stages * stage_bytes + 512 + 1024;
 }
 
+// exponent mix: index into {MUFU only, 1/4, 1/3, 3/8 of the exponentials on the FMA pipe}; PASSL_B200_NCE_POLY overrides
+static int nce_poly_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PASSL_B200_NCE_POLY");
+    v = e ? atoi(e) : 2;
+    if (v < 0 || v > 3) v = 2;
+  }
+  return v;
+}
+
+template <typename KernelT>
+static int nce_launch(KernelT kern, const InfoNceTcParams& p, int grid, int threads, int smem, cudaStream_t st) {
+  PB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));   // + static smem <= 227 KB
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  PB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+static int nce_fill_params(InfoNceTcParams& p, const void* Q, const void* Kmat, const float* P, const long long* label,
+                           const int* excl, float scale, float loss_scale, int N, int K, int D, int& MB, int& smem) {
+  memset(&p, 0, sizeof(p));
+  nce_plan(N, K, D, MB, p.row_groups, p.slices, p.tiles, smem);
+  p.Q = reinterpret_cast<const __nv_bfloat16*>(Q);
+  p.Kmat = reinterpret_cast<const __nv_bfloat16*>(Kmat);
+  p.P = P; p.label = label; p.excl = excl; p.scale = scale; p.loss_scale = loss_scale; p.N = N; p.K = K; p.D = D;
+  p.tgt_mode = (p.row_groups * p.slices <= num_sms()) ? 0 : 1;
+  p.poly_ok = (2.1f * scale * kLog2e < 120.f) ? 1 : 0;
+  uint64_t qd[2] = {(uint64_t)D, (uint64_t)N}, qs[1] = {(uint64_t)D * 2};
+  uint32_t qbx[2] = {64, 128};
+  int rc = make_tmap_bf16(&p.q_map, Q, 2, qd, qs, qbx);
+  if (rc) return rc;
+  uint64_t kd[2] = {(uint64_t)D, (uint64_t)K};
+  uint32_t kbx[2] = {64, NCE_BK};
+  return make_tmap_bf16(&p.k_map, Kmat, 2, kd, qs, kbx);
+}
+
 }  // namespace pb
 
 using namespace pb;
@@ -362,73 +782,69 @@ static unsigned long long* g_nce_dbg = nullptr;
 // developer hook: per-CTA timeline buffer (uint64 [grid * 16]) filled by the next launches; NULL disables
 extern "C" int passl_b200_infonce_tc_set_debug(void* buf) { g_nce_dbg = reinterpret_cast<unsigned long long*>(buf); return 0; }
 
+// persistent state: [epoch, ticket, pad, pad][flags N][tgt_raw N][acc_l N][acc_cnt N]
 extern "C" long long passl_b200_infonce_tc_workspace_bytes(int N, int K, int D) {
-  int MB, groups, slices, tiles, smem;
-  nce_plan(N, K, D, MB, groups, slices, tiles, smem);
-  return (long long)N * slices * 12 + simce_finalize_scratch_bytes(N) + (long long)N * 4 + 512;
+  (void)K; (void)D;
+  return 16 + (long long)N * 16;
 }
 
-// Forward.  Q [N,D] bf16 (normalised queries), Kmat [K,D] bf16 keys, P [N,D] fp32 optional positive keys
+// Forward.  Q [N,D] bf16 (L2-normalised queries), Kmat [K,D] bf16 keys, P [N,D] fp32 optional positive keys
 // (MoCo), label int64 [N] (when P == NULL), excl int32 [N] optional.  Outputs as passl_b200_simce_fwd_f32.
+// `workspace` is PERSISTENT STATE: zero-filled by the caller before its first use (and after a failed launch), one buffer
+// per (N, stream); every launch leaves it ready for the next one.
 extern "C" int passl_b200_infonce_tc_fwd(const void* Q, const void* Kmat, const float* P, const long long* label,
                                          const int* excl, float scale, float loss_scale, int N, int K, int D, float* lse,
                                          float* tgt, float* loss_rows, float* out_scalars, void* workspace,
                                          long long workspace_bytes, void* stream) {
-  if (N <= 0 || K <= 0 || D < 64 || D % 64 || D > 512) return PB_ERR_BAD_ARG;
+  if (N <= 0 || K <= 0 || D < 64 || D % 64 || D > 512 || !(scale > 0.f)) return PB_ERR_BAD_ARG;
   if (!P && !label) return PB_ERR_BAD_ARG;
   if ((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(Kmat) | reinterpret_cast<uintptr_t>(P)) & 15) return PB_ERR_BAD_ARG;
   if (workspace_bytes < passl_b200_infonce_tc_workspace_bytes(N, K, D)) return PB_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   InfoNceTcParams p;
-  memset(&p, 0, sizeof(p));
   int MB, smem;
-  nce_plan(N, K, D, MB, p.row_groups, p.slices, p.tiles, smem);
-  p.Q = reinterpret_cast<const __nv_bfloat16*>(Q);
-  p.Kmat = reinterpret_cast<const __nv_bfloat16*>(Kmat);
-  p.P = P; p.label = label; p.excl = excl; p.scale = scale; p.N = N; p.K = K; p.D = D;
-  char* ws = reinterpret_cast<char*>(workspace);
-  p.part_m = reinterpret_cast<float*>(ws); ws += (size_t)N * p.slices * 4;
-  p.part_l = reinterpret_cast<float*>(ws); ws += (size_t)N * p.slices * 4;
-  p.part_cnt = reinterpret_cast<int*>(ws);
-  p.tgt = tgt;
+  int rc = nce_fill_params(p, Q, Kmat, P, label, excl, scale, loss_scale, N, K, D, MB, smem);
+  if (rc) return rc;
+  unsigned* w = reinterpret_cast<unsigned*>(workspace);
+  p.epoch = w; p.ticket = w + 1; p.flags = w + 4;
+  p.tgt_raw = reinterpret_cast<float*>(w + 4 + N);
+  p.acc_l = reinterpret_cast<float*>(w + 4 + 2 * (size_t)N);
+  p.acc_cnt = w + 4 + 3 * (size_t)N;
+  p.lse = lse; p.tgt = tgt; p.loss_rows = loss_rows; p.out = out_scalars;
   p.dbg = g_nce_dbg;
-  uint64_t qd[2] = {(uint64_t)D, (uint64_t)N}, qs[1] = {(uint64_t)D * 2};
-  uint32_t qbx[2] = {64, 128};
-  int rc = make_tmap_bf16(&p.q_map, Q, 2, qd, qs, qbx);
-  if (rc) return rc;
-  uint64_t kd[2] = {(uint64_t)D, (uint64_t)K};
-  uint32_t kbx[2] = {64, NCE_BK};
-  rc = make_tmap_bf16(&p.k_map, Kmat, 2, kd, qs, kbx);
-  if (rc) return rc;
-  int grid = p.row_groups * p.slices;
-  static bool attr_done = false;
-  if (!attr_done) {  // once per process: allow up to the full 227 KB dynamic smem carve-out
-    PB_CUDA_CHECK(cudaFuncSetAttribute(infonce_tc_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    PB_CUDA_CHECK(cudaFuncSetAttribute(infonce_tc_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_done = true;
+  const int grid = p.row_groups * p.slices, threads = 64 + 128 * MB;
+  const int pv = nce_poly_variant();
+#define NCE_FWD_CASE(mb, pn, pd) rc = nce_launch(infonce_tc_fwd_kernel<mb, pn, pd>, p, grid, threads, smem, st)
+  if (MB == 2) {
+    if (pv == 0) NCE_FWD_CASE(2, 0, 1); else if (pv == 1) NCE_FWD_CASE(2, 1, 4); else if (pv == 2) NCE_FWD_CASE(2, 1, 3); else NCE_FWD_CASE(2, 3, 8);
+  } else {
+    if (pv == 0) NCE_FWD_CASE(1, 0, 1); else if (pv == 1) NCE_FWD_CASE(1, 1, 4); else if (pv == 2) NCE_FWD_CASE(1, 1, 3); else NCE_FWD_CASE(1, 3, 8);
   }
-  // three launches chained by programmatic dependent launch: target (also zeroes the ticket) -> main (PDL) -> finalize (PDL)
-  float* scratch = reinterpret_cast<float*>(p.part_cnt + (size_t)N * p.slices);
-  const int fin_blk = (N + 7) / 8;
-  float* tgt_raw = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + ((simce_finalize_scratch_bytes(N) + 15) & ~15LL));
-  p.tgt_raw = tgt_raw;
-  infonce_target_kernel<<<fin_blk, 256, 0, st>>>(p.Q, p.Kmat, P, label, tgt_raw, reinterpret_cast<unsigned*>(scratch + (size_t)fin_blk * 3),
-                                                 N, K, D);
-  PB_LAUNCH_CHECK();
-  {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + 128 * MB); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    if (MB == 2) PB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, infonce_tc_fwd_kernel<2>, p));
-    else PB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, infonce_tc_fwd_kernel<1>, p));
-    PB_LAUNCH_CHECK();
-  }
-  PB_CUDA_CHECK(launch_simce_finalize(p.part_m, p.part_l, p.part_cnt, tgt, N, p.slices, P ? 1 : 0, loss_scale, lse,
-                                      loss_rows, out_scalars, scratch, st, /*pdl=*/true));
-  passl_b200_launch_counter_add(1);
-  return PB_OK;
+#undef NCE_FWD_CASE
+  return rc;
+}
+
+// Backward w.r.t. the queries.  lse / tgt: saved by the forward; dloss: device scalar (upstream grad) or NULL (= 1);
+// dQ fp32 [N, D] is overwritten (zero-filled here, then accumulated over the key slices with vector reds).  D <= 256.
+extern "C" int passl_b200_infonce_tc_bwd(const void* Q, const void* Kmat, const float* P, const long long* label,
+                                         const int* excl, float scale, float loss_scale, int N, int K, int D,
+                                         const float* lse, const float* tgt, const float* dloss, float* dQ, void* stream) {
+  if (N <= 0 || K <= 0 || D < 64 || D % 64 || D > 256 || !(scale > 0.f)) return PB_ERR_BAD_ARG;
+  if (!P && !label) return PB_ERR_BAD_ARG;
+  if ((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(Kmat) | reinterpret_cast<uintptr_t>(P) |
+       reinterpret_cast<uintptr_t>(dQ)) & 15) return PB_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  InfoNceTcParams p;
+  int MB, smem;
+  int rc = nce_fill_params(p, Q, Kmat, P, label, excl, scale, loss_scale, N, K, D, MB, smem);
+  if (rc) return rc;
+  p.lse_in = lse; p.tgt_in = tgt; p.dloss = dloss; p.dq = dQ;
+  PB_CUDA_CHECK(cudaMemsetAsync(dQ, 0, (size_t)N * D * 4, st));
+  const int grid = p.row_groups * p.slices, threads = 64 + 128 * MB;
+  const int pv = nce_poly_variant();
+  if (MB == 2) rc = pv == 0 ? nce_launch(infonce_tc_bwd_kernel<2, 0, 1>, p, grid, threads, smem, st)
+                            : nce_launch(infonce_tc_bwd_kernel<2, 1, 4>, p, grid, threads, smem, st);
+  else rc = pv == 0 ? nce_launch(infonce_tc_bwd_kernel<1, 0, 1>, p, grid, threads, smem, st)
+                    : nce_launch(infonce_tc_bwd_kernel<1, 1, 4>, p, grid, threads, smem, st);
+  return rc;
 }

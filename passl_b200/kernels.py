@@ -211,8 +211,22 @@ def simce_bwd(a, b, lse, tgt, *, pos=None, label=None, excl=None, scale=1.0, los
     return da
 
 
+_nce_state = {}
+
+
+def _infonce_state(nbytes, device, N):
+    """Persistent state of the fused InfoNCE kernel (epoch, ticket, target flags, slice accumulators): zero-filled ONCE per
+    (device, stream, N); every launch leaves it ready for the next one (include/passl_b200.h)."""
+    key = (str(device), int(torch.cuda.current_stream(device).cuda_stream), int(N))
+    buf = _nce_state.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.zeros(int(nbytes), dtype=torch.uint8, device=device)
+        _nce_state[key] = buf
+    return buf
+
+
 def infonce_tc_fwd(q_bf16, keys_bf16, *, pos=None, label=None, excl=None, scale=1.0, loss_scale=1.0, want_rows=False):
-    """tcgen05 fused InfoNCE forward: q [N,D] bf16, keys [K,D] bf16 (streamed once), pos [N,D] fp32 optional."""
+    """tcgen05 fused InfoNCE forward (one launch): q [N,D] bf16, keys [K,D] bf16 (streamed once), pos [N,D] fp32 optional."""
     _need_cuda(q_bf16, keys_bf16)
     lib = _lib.load()
     N, D = q_bf16.shape
@@ -224,12 +238,27 @@ def infonce_tc_fwd(q_bf16, keys_bf16, *, pos=None, label=None, excl=None, scale=
     tgt = torch.empty(N, dtype=torch.float32, device=dev)
     rows = torch.empty(N, dtype=torch.float32, device=dev) if want_rows else None
     out = torch.empty(3, dtype=torch.float32, device=dev)
-    ws = workspace(lib.passl_b200_infonce_tc_workspace_bytes(N, K, D), dev, "infonce_tc")
+    ws = _infonce_state(lib.passl_b200_infonce_tc_workspace_bytes(N, K, D), dev, N)
     code = lib.passl_b200_infonce_tc_fwd(_ptr(q_bf16), _ptr(keys_bf16), _ptr(pos), _ptr(label), _ptr(excl), float(scale),
                                          float(loss_scale), N, K, D, _ptr(lse), _ptr(tgt), _ptr(rows), _ptr(out), _ptr(ws),
                                          ws.numel(), _stream())
     _lib.check(code, "infonce_tc_fwd")
     return out, lse, tgt, rows
+
+
+def infonce_tc_bwd(q_bf16, keys_bf16, lse, tgt, *, pos=None, label=None, excl=None, scale=1.0, loss_scale=1.0, dloss=None):
+    """tcgen05 fused InfoNCE backward w.r.t. the queries (one launch + the zero fill of dq): returns dq fp32 [N, D]."""
+    _need_cuda(q_bf16, keys_bf16)
+    lib = _lib.load()
+    N, D = q_bf16.shape
+    K = keys_bf16.shape[0]
+    assert q_bf16.dtype == torch.bfloat16 and keys_bf16.dtype == torch.bfloat16
+    assert q_bf16.is_contiguous() and keys_bf16.is_contiguous()
+    dq = torch.empty((N, D), dtype=torch.float32, device=q_bf16.device)
+    code = lib.passl_b200_infonce_tc_bwd(_ptr(q_bf16), _ptr(keys_bf16), _ptr(pos), _ptr(label), _ptr(excl), float(scale),
+                                         float(loss_scale), N, K, D, _ptr(lse), _ptr(tgt), _ptr(dloss), _ptr(dq), _stream())
+    _lib.check(code, "infonce_tc_bwd")
+    return dq
 
 
 # ------------------------------------------------------------------------------------------------------------

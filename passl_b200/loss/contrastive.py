@@ -34,12 +34,18 @@ class _FusedInfoNCE(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dloss, _a1, _a5):
         qa = ctx.q_bwd
-        if qa.dtype != torch.float32:        # the backward kernel takes fp32 queries (bf16-rounded values)
+        dl = dloss.contiguous().float()
+        if qa.dtype == torch.bfloat16 and qa.shape[1] <= 256:
+            # tcgen05 backward: S recomputed tile by tile, P (bf16) x key tile accumulated into dQ in TMEM
+            dq = K.infonce_tc_bwd(qa, ctx.keys_bwd, ctx.lse, ctx.tgt, pos=ctx.pos, label=ctx.label, scale=ctx.scale,
+                                  loss_scale=ctx.loss_scale, dloss=dl)
+            return dq, None, None, None, None, None, None
+        if qa.dtype != torch.float32:        # the SIMT backward kernel takes fp32 queries (bf16-rounded values)
             qf = torch.empty(qa.shape, dtype=torch.float32, device=qa.device)
             K.cast_f32(qa, qf)
             qa = qf
         dq = K.simce_bwd(qa, ctx.keys_bwd, ctx.lse, ctx.tgt, pos=ctx.pos, label=ctx.label, scale=ctx.scale,
-                         loss_scale=ctx.loss_scale, dloss=dloss.contiguous().float())
+                         loss_scale=ctx.loss_scale, dloss=dl)
         return dq, None, None, None, None, None, None
 
 

@@ -1,7 +1,9 @@
 """ResNet building blocks and the full ResNet-50 / MoCo step on the GPU vs the torch-CPU oracle (oracle/resnet.py).
 
-Activations are bf16 between fused units, so tolerances are bf16-level (north_star: 1e-2 relative for bf16): outputs are
-compared by relative L2 error, weight gradients by relative L2 error + cosine similarity.
+Activations and activation gradients are bf16 between fused units.  The oracle is run in its QUANTISATION-MATCHED mode
+(oracle/resnet.py, q=True: bf16 rounding at exactly the points where the CUDA path rounds, forward and backward, fp64 in between),
+so what is compared is the kernels' arithmetic, not the chaotic amplification of rounding noise through BatchNorm.  Contract
+(BASELINE.json north_star, bf16): features / loss within 1e-2 relative, every weight gradient within 2e-2 relative.
 """
 import numpy as np
 import pytest
@@ -105,17 +107,16 @@ def test_bottleneck_fwd_bwd_vs_oracle(inpl, planes, stride, ds):
     p = O.params_from_cuda_module(blk)
     p = {"b." + k: v.requires_grad_(True) for k, v in p.items()}
     xr = _to_oracle_input(x).requires_grad_(True)
-    outr = O.bottleneck(xr, p, "b", stride, ds)
+    outr = O.bottleneck(O.Q(xr), p, "b", stride, ds, q=True)
     outr.backward(_to_oracle_input(dout))
-    assert rel(out.permute(0, 3, 1, 2), outr) < 2e-2
-    assert rel(dx.permute(0, 3, 1, 2), xr.grad) < 0.1 and cos(dx.permute(0, 3, 1, 2), xr.grad) > 0.995
+    assert rel(out.permute(0, 3, 1, 2), outr) < 1e-2, rel(out.permute(0, 3, 1, 2), outr)
+    assert rel(dx.permute(0, 3, 1, 2), xr.grad) < 2e-2, rel(dx.permute(0, 3, 1, 2), xr.grad)
     for name, prm in blk.named_parameters():
         ref = p["b." + name].grad
         got = prm.grad
         if got.dim() == 4:
             got = got.permute(0, 3, 1, 2)
-        assert cos(got, ref) > 0.995, (name, cos(got, ref))
-        assert rel(got, ref) < 0.12, (name, rel(got, ref))
+        assert rel(got, ref) < 2e-2, (name, rel(got, ref), cos(got, ref))
 
 
 def test_stem_fwd_bwd_vs_oracle():
@@ -138,32 +139,53 @@ def test_stem_fwd_bwd_vs_oracle():
     p = {"stem.weight": w.requires_grad_(True),
          "stem.bn.weight": stem.bn.weight.detach().double().cpu().requires_grad_(True),
          "stem.bn.bias": stem.bn.bias.detach().double().cpu().requires_grad_(True)}
-    x = img.cpu().bfloat16().double()          # im2col rounds the pixels to bf16
-    y = O.conv_bn(x, p, "stem", stride=2, pad=3)
-    y = F.max_pool2d(y, 3, 2, 1)
+    x = img.cpu().bfloat16().double()          # the repack rounds the pixels to bf16
+    y = O.conv_bn(x, p, "stem", stride=2, pad=3, q=True)
+    y = O.Q(F.max_pool2d(y, 3, 2, 1))
     y.backward(dout.float().cpu().double().permute(0, 3, 1, 2))
-    assert rel(out.permute(0, 3, 1, 2), y) < 1e-2
+    assert rel(out.permute(0, 3, 1, 2), y) < 1e-2, rel(out.permute(0, 3, 1, 2), y)
     gw = stem.weight.grad[:, :147].reshape(64, 7, 7, 3).permute(0, 3, 1, 2)
-    assert cos(gw, p["stem.weight"].grad) > 0.995, cos(gw, p["stem.weight"].grad)
-    assert rel(gw, p["stem.weight"].grad) < 0.1, rel(gw, p["stem.weight"].grad)
-    assert cos(stem.bn.weight.grad, p["stem.bn.weight"].grad) > 0.995
-    assert cos(stem.bn.bias.grad, p["stem.bn.bias"].grad) > 0.995
+    assert rel(gw, p["stem.weight"].grad) < 2e-2, rel(gw, p["stem.weight"].grad)
+    assert rel(stem.bn.weight.grad, p["stem.bn.weight"].grad) < 2e-2
+    assert rel(stem.bn.bias.grad, p["stem.bn.bias"].grad) < 2e-2
 
 
-def test_resnet50_small_fwd_bwd_vs_oracle():
+def _grad_report(named_params, pref, path):
+    rows, worst = [], 0.0
+    for name, prm in named_params:
+        ref = pref[name].grad
+        got = prm.grad
+        if name.endswith("stem.weight"):
+            got = got[:, :147].reshape(64, 7, 7, 3)
+        if got.dim() == 4:
+            got = got.permute(0, 3, 1, 2)
+        if ref is not None and ref.norm() > 0:
+            r = rel(got, ref)
+            worst = max(worst, r)
+            rows.append("%-36s rel %.5f cos %.6f |ref| %.3e" % (name, r, cos(got, ref), ref.norm().item()))
+    import os
+    os.makedirs("gpurun_out", exist_ok=True)
+    open(path, "w").write("\n".join(rows) + "\n")
+    return worst, rows
+
+
+@pytest.mark.parametrize("variant", ["ResNet", "ResNetsimclr"])
+def test_resnet50_fwd_bwd_vs_quantisation_matched_oracle(variant):
+    """The whole ResNet-50 (MoCo variant with the stem max-pool, SimCLR variant without it: resnetcifar.py:275,321-332) +
+    NonLinearNeckV1, forward and every parameter gradient, against the quantisation-matched oracle."""
     from oracle import resnet as O
     from passl_b200.modeling import build_backbone, build_neck
     torch.manual_seed(0)
-    net = build_backbone(dict(name="ResNet", depth=50)).cuda()
-    for blk in net.blocks:          # damp the residual branches so bf16 rounding noise is not chaotically amplified
-        torch.nn.init.constant_(blk.conv3.bn.weight, 0.25)
+    simclr = variant == "ResNetsimclr"
+    net = build_backbone(dict(name=variant, depth=50, with_pool=False)).cuda()
     neck = build_neck(dict(name="NonLinearNeckV1", in_channels=2048, hid_channels=2048, out_channels=128)).cuda()
-    img = torch.randn(16, 3, 128, 128, device="cuda")
+    B, S = (8, 64) if simclr else (16, 128)
+    img = torch.randn(B, 3, S, S, device="cuda")
     for p in list(net.parameters()) + list(neck.parameters()):
         p.grad = torch.zeros_like(p)
     feat = net(img)
     emb = neck(feat)
-    assert emb.dtype == torch.float32 and emb.shape == (16, 128)
+    assert emb.dtype == torch.float32 and emb.shape == (B, 128)
     g = torch.randn_like(emb)
     emb.backward(g)
     torch.cuda.synchronize()
@@ -172,35 +194,60 @@ def test_resnet50_small_fwd_bwd_vs_oracle():
     for d in (p, pn):
         for v in d.values():
             v.requires_grad_(True)
-    fr = O.resnet_forward(img.cpu().double(), p)
-    er = O.neck_v1(fr, pn)
+    fr = O.resnet_forward(img.cpu().double(), p, stem_maxpool=not simclr, q=True)
+    er = O.neck_v1(fr, pn, q=True)
     er.backward(g.cpu().double())
-    assert rel(feat.permute(0, 3, 1, 2), fr) < 5e-2, rel(feat.permute(0, 3, 1, 2), fr)
-    assert rel(emb, er) < 5e-2, rel(emb, er)
-    worst, allg, allr, report = 1.0, [], [], []
-    for name, prm in list(net.named_parameters()):
-        ref = p[name].grad
-        got = prm.grad
-        if name == "stem.weight":
-            got = got[:, :147].reshape(64, 7, 7, 3)
-        if got.dim() == 4:
-            got = got.permute(0, 3, 1, 2)
-        if ref.norm() > 0:
-            worst = min(worst, cos(got, ref))
-            report.append("%-32s cos %.4f rel %.4f |ref| %.3e" % (name, cos(got, ref), rel(got, ref), ref.norm().item()))
-            allg.append(got.double().flatten().cpu())
-            allr.append(ref.double().flatten().cpu())
-    import os
-    os.makedirs("gpurun_out", exist_ok=True)
-    open("gpurun_out/resnet_e2e_grad_report.txt", "w").write("\n".join(report))
-    # 50 layers of bf16 activations + batch statistics: individual early-layer gradients drift, the full gradient agrees
-    # (ReLU masks of the fp64 oracle and of the bf16 CUDA forward differ where activations are ~0, which bounds the agreement
-    #  of gradients deep in the net; per-unit backward parity is tested above with identical inputs)
-    assert cos(torch.cat(allg), torch.cat(allr)) > 0.8, cos(torch.cat(allg), torch.cat(allr))
-    assert worst > 0.5, worst
-    last = [l for l in report if l.startswith("blocks.15.conv3")]
-    assert all(float(l.split("cos")[1].split()[0]) > 0.95 for l in last), last
-    assert cos(neck.fc1.weight.grad, pn["fc1.weight"].grad) > 0.99
+    assert fr.shape[2] == (S // 16 if simclr else S // 32)
+    assert rel(feat.permute(0, 3, 1, 2), fr) < 1e-2, rel(feat.permute(0, 3, 1, 2), fr)
+    assert rel(emb, er) < 1e-2, rel(emb, er)
+    worst, rows = _grad_report(list(net.named_parameters()), p, "gpurun_out/r02_resnet50_%s_grad_report.txt" % variant)
+    worst_n, _ = _grad_report(list(neck.named_parameters()), pn, "gpurun_out/r02_neckv1_%s_grad_report.txt" % variant)
+    assert worst < 2e-2, (worst, [r for r in rows if float(r.split()[2]) > 2e-2][:8])
+    assert worst_n < 2e-2, worst_n
+
+
+@pytest.mark.parametrize("neck_name", ["NonLinearNeckfc3", "LinearNeck", "NonLinearNeckV1"])
+def test_necks_fwd_bwd_vs_quantisation_matched_oracle(neck_name):
+    """base_neck.py:43-64 (LinearNeck), :67-94 (NonLinearNeckV1), :209-237 (NonLinearNeckfc3: the neck of the benchmarked SimCLR
+    config) on a pooled [B, 2048] feature and on an un-pooled [B, 7, 7, 2048] map."""
+    from oracle import resnet as O
+    from passl_b200.modeling import build_neck
+    torch.manual_seed(1)
+    B = 64
+    fc3 = neck_name == "NonLinearNeckfc3"
+    cfg = dict(name=neck_name, in_channels=2048, out_channels=128)
+    if neck_name != "LinearNeck":
+        cfg["hid_channels"] = 2048
+    cfg["with_avg_pool"] = not fc3
+    neck = build_neck(cfg).cuda()
+    if fc3:
+        for bn in (neck.bn1, neck.bn2, neck.bn3):
+            torch.nn.init.uniform_(bn.bn.weight, 0.5, 1.5)
+            torch.nn.init.normal_(bn.bn.bias, 0, 0.2)
+        for fc in (neck.fc1, neck.fc2, neck.fc3):
+            torch.nn.init.normal_(fc.weight, 0, 0.05)        # the reference's 0.01 makes every gradient tiny; same code path
+        feat = torch.randn(B, 2048, device="cuda").relu().bfloat16()
+    else:
+        feat = torch.randn(B, 7, 7, 2048, device="cuda").relu().bfloat16()
+    feat.requires_grad_(True)
+    for p_ in neck.parameters():
+        p_.grad = torch.zeros_like(p_)
+    emb = neck(feat)
+    g = torch.randn_like(emb)
+    emb.backward(g)
+    torch.cuda.synchronize()
+    pn = O.params_from_cuda_module(neck)
+    for v in pn.values():
+        v.requires_grad_(True)
+    fr = (feat.detach().float().cpu().double() if fc3 else _to_oracle_input(feat.detach())).requires_grad_(True)
+    fn = {"NonLinearNeckfc3": O.neck_fc3, "LinearNeck": O.neck_linear, "NonLinearNeckV1": O.neck_v1}[neck_name]
+    er = fn(O.Q(fr), pn, q=True)
+    er.backward(g.cpu().double())
+    assert rel(emb, er) < 1e-2, rel(emb, er)
+    dfeat = feat.grad if fc3 else feat.grad.permute(0, 3, 1, 2)
+    assert rel(dfeat, fr.grad) < 2e-2, rel(dfeat, fr.grad)
+    worst, rows = _grad_report(list(neck.named_parameters()), pn, "gpurun_out/r02_%s_grad_report.txt" % neck_name)
+    assert worst < 2e-2, (worst, rows)
 
 
 def test_moco_train_iter_smoke_and_state():

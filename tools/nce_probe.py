@@ -1,0 +1,92 @@
+"""Fused InfoNCE forward / backward timing (CUDA graph of 8 calls over 8 different queues, L2 flushed between replays, the same
+method as bench.py's roofline_infonce) + per-CTA timeline.  Developer tool:  python tools/nce_probe.py [timeline]"""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from passl_b200 import _lib, kernels as K  # noqa: E402
+
+
+def graph_time(fn_of_queue, queues, flush, reps=20):
+    gph = torch.cuda.CUDAGraph()
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
+        fn_of_queue(queues[0])
+        with torch.cuda.graph(gph, stream=st):
+            for qq in queues:
+                fn_of_queue(qq)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        gph.replay()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e) / len(queues))
+    ts.sort()
+    return ts[len(ts) // 2] * 1e3        # us per call
+
+
+def main():
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    res = {"poly": os.environ.get("PASSL_B200_NCE_POLY", "default")}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for (N, D, Kq, T) in [(256, 128, 65536, 0.2), (16, 128, 65536, 0.2), (1024, 256, 8192, 0.2)]:
+        q = torch.nn.functional.normalize(torch.randn(N, D, device=dev), dim=1)
+        kpos = torch.nn.functional.normalize(torch.randn(N, D, device=dev), dim=1)
+        nq = max(2, (140 << 20) // (Kq * D * 2) + 1)
+        nq = min(nq, 16)
+        queues = [torch.nn.functional.normalize(torch.randn(Kq, D, device=dev), dim=1).bfloat16() for _ in range(nq)]
+        qb = q.bfloat16()
+        out, lse, tgt, _ = K.infonce_tc_fwd(qb, queues[0], pos=kpos, scale=1 / T)
+        us_f = graph_time(lambda qq: K.infonce_tc_fwd(qb, qq, pos=kpos, scale=1 / T), queues, flush)
+        us_b = graph_time(lambda qq: K.infonce_tc_bwd(qb, qq, lse, tgt, pos=kpos, scale=1 / T), queues, flush)
+        by = (2 * N * D + D * Kq) * 2 + 4 * N
+        res["N%d_D%d_K%d" % (N, D, Kq)] = dict(fwd_us=us_f, bwd_us=us_b, fwd_gbs=by / us_f / 1e3, bwd_gbs=by / us_b / 1e3,
+                                                fwd_frac_of_6569=by / us_f / 1e3 / 6569.3)
+        if N == 256:
+            qf = qb.float()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            K.simce_bwd(qf, queues[0], lse, tgt, pos=kpos, scale=1 / T)
+            s.record()
+            for i in range(4):
+                K.simce_bwd(qf, queues[i % nq], lse, tgt, pos=kpos, scale=1 / T)
+            e.record()
+            torch.cuda.synchronize()
+            res["simt_bwd_us"] = s.elapsed_time(e) / 4 * 1e3
+    print(json.dumps(res), flush=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "timeline":
+        N, D, Kq, T = 256, 128, 65536, 0.2
+        q = torch.nn.functional.normalize(torch.randn(N, D, device=dev), dim=1).bfloat16()
+        k = torch.nn.functional.normalize(torch.randn(N, D, device=dev), dim=1)
+        queue = torch.nn.functional.normalize(torch.randn(Kq, D, device=dev), dim=1).bfloat16()
+        for _ in range(3):
+            K.infonce_tc_fwd(q, queue, pos=k, scale=1 / T)
+        dbg = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+        flush.zero_()
+        torch.cuda.synchronize()
+        lib.passl_b200_infonce_tc_set_debug(dbg.data_ptr())
+        K.infonce_tc_fwd(q, queue, pos=k, scale=1 / T)
+        torch.cuda.synchronize()
+        lib.passl_b200_infonce_tc_set_debug(None)
+        t = dbg.cpu().reshape(148, 16).double()
+        t0 = t[:, 0][t[:, 0] > 0].min()
+        names = ["start", "after setup (alloc, PDL wait, sync)", "-", "Q staged in TMEM", "target fetched", "s_full t0", "t1", "t2", "t3",
+                 "t4", "t5", "t6", "t7", "loop end", "mma: q_ready"]
+        for i, n in enumerate(names):
+            col = t[:, i]
+            col = col[col > 0]
+            if len(col):
+                print("%-36s min %7.2f us  median %7.2f us  max %7.2f us" % (n, (col.min() - t0) / 1e3, (col.median() - t0) / 1e3,
+                                                                            (col.max() - t0) / 1e3))
+
+
+if __name__ == "__main__":
+    main()

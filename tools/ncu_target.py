@@ -33,6 +33,8 @@ elif what == "infonce":
     qb = q.bfloat16()
     for i in range(4):
         out, lse, tgt, _ = K.infonce_tc_fwd(qb, queue, pos=k, scale=1 / T)
+    for i in range(4):
+        dq = K.infonce_tc_bwd(qb, queue, lse, tgt, pos=k, scale=1 / T)
     torch.cuda.synchronize()
 if what == "conv":
     B = 128
