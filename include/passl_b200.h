@@ -299,15 +299,24 @@ int passl_b200_avgpool_bwd(const void* dy, void* dx, int N, int HW, int C, void*
  * Fused optimizer steps over flat fp32 buffers (+ bf16 compute copy).  Replace the per-parameter Python loops of
  * passl/optimizer/momentum.py:60-158, momentum_lars.py:56-114, adamw.py:52-138.  Tensors start at multiples of 1024
  * elements inside the flat buffer; block_seg[b] = tensor id of 1024-element block b.
+ * `ctrl` (may be NULL): the device-side control word {multiplier, found_inf, global_norm} written by
+ * passl_b200_grad_norm_finite — the gradient is multiplied by ctrl[0] on the fly and the whole step is skipped when ctrl[1] != 0,
+ * so gradient clipping / unscaling costs one read pass over the gradients and no host round trip.
  * ------------------------------------------------------------------------------------------------------------- */
 int passl_b200_sgd_momentum(float* p, const float* g, float* v, void* p_bf16, float lr, float momentum, float wd,
-                            float grad_scale, long long n, void* stream);
+                            float grad_scale, const float* ctrl, long long n, void* stream);
 int passl_b200_lars_momentum(float* p, const float* g, float* v, void* p_bf16, const int* block_seg, const float* seg_wd,
                              float* norms, int num_segments, float lr, float momentum, float lars_coeff, float eps,
-                             float grad_scale, long long n, void* stream);
+                             float grad_scale, const float* ctrl, long long n, void* stream);
 int passl_b200_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, const int* block_seg, const float* seg_wd,
                      const float* seg_lr_ratio, float lr, float beta1, float beta2, float eps, int step, float grad_scale,
-                     long long n, void* stream);
+                     const float* ctrl, long long n, void* stream);
+/* ClipGradByGlobalNorm (passl/core/grad_clip.py:30-84) + check_finite_and_unscale (passl/core/grad_scaler.py:48-87) as ONE read
+ * pass over the flat fp32 gradient buffer: ctrl fp32[3] = {unscale * clip_coef (0 when a gradient is non-finite), found_inf,
+ * global norm of unscale*g}; clip_coef = 1 if (!always_clip && norm <= clip_norm) else min(clip_norm / (norm + 1e-6), coef_max);
+ * clip_norm <= 0 disables clipping, coef_max <= 0 disables the cap.  scratch fp32[3]: zeroed once by the caller, left zeroed. */
+int passl_b200_grad_norm_finite(const float* g, long long n, float unscale, float clip_norm, float coef_max, int always_clip,
+                                float* ctrl, float* scratch, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Embedding exchange over NVLink peer memory (replaces the NCCL all_gather / reduce_scatter behind

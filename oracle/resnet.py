@@ -46,8 +46,24 @@ class _RoundBwd(torch.autograd.Function):
         return _round_bf16(g)
 
 
+class _RoundFwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return _round_bf16(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
 def Q(x, on=True):
     return _RoundBoth.apply(x) if on else x
+
+
+def Qf(x, on=True):
+    """forward-only rounding: the bf16 mirror of an fp32 master weight (its gradient is accumulated in fp32), or an fp32
+    embedding cast to bf16 for a tensor-core kernel whose input gradient comes back in fp32"""
+    return _RoundFwd.apply(x) if on else x
 
 
 def Qb(x, on=True):
@@ -72,7 +88,7 @@ def bn_train(x, gamma, beta, eps=1e-5, stats=None, use_global_stats=False, runni
 
 def conv_bn(x, p, prefix, stride=1, pad=0, relu=True, residual=None, use_global_stats=False, q=False):
     """p[prefix+'.weight'] is [Cout, Cin, R, S] (NCHW convention)."""
-    y = Q(F.conv2d(x, p[prefix + ".weight"], stride=stride, padding=pad), q)
+    y = Q(F.conv2d(x, Qf(p[prefix + ".weight"], q), stride=stride, padding=pad), q)
     running = (p.get(prefix + ".bn._mean"), p.get(prefix + ".bn._variance"))
     y = bn_train(y, p[prefix + ".bn.weight"], p[prefix + ".bn.bias"], use_global_stats=use_global_stats, running=running)
     if residual is not None:
@@ -117,21 +133,21 @@ def _neck_in(feat, with_avg_pool, q):
 def neck_linear(feat, p, prefix="", with_avg_pool=True, q=False):
     """LinearNeck (base_neck.py:43-64): avgpool -> fc (fp32 output; its gradient is cast to bf16 for the dgrad / wgrad GEMMs)."""
     x = _neck_in(feat, with_avg_pool, q)
-    return Qb(F.linear(x, p[prefix + "fc.weight"], p[prefix + "fc.bias"]), q)
+    return Qb(F.linear(x, Qf(p[prefix + "fc.weight"], q), p[prefix + "fc.bias"]), q)
 
 
 def neck_v1(feat, p, prefix="", with_avg_pool=True, q=False):
     """NonLinearNeckV1 (base_neck.py:67-94): avgpool -> fc -> relu -> fc; weights here are [out, in]."""
     x = _neck_in(feat, with_avg_pool, q)
-    x = Q(F.relu(F.linear(x, p[prefix + "fc1.weight"], p[prefix + "fc1.bias"])), q)
-    return Qb(F.linear(x, p[prefix + "fc2.weight"], p[prefix + "fc2.bias"]), q)
+    x = Q(F.relu(F.linear(x, Qf(p[prefix + "fc1.weight"], q), p[prefix + "fc1.bias"])), q)
+    return Qb(F.linear(x, Qf(p[prefix + "fc2.weight"], q), p[prefix + "fc2.bias"]), q)
 
 
 def neck_fc3(feat, p, prefix="", with_avg_pool=False, q=False):
     """NonLinearNeckfc3 (base_neck.py:209-237) incl. the trailing l2_normalize(hidden, -1)."""
     x = _neck_in(feat, with_avg_pool, q)
     for i in (1, 2, 3):
-        x = Q(F.linear(x, p[prefix + "fc%d.weight" % i], p[prefix + "fc%d.bias" % i]), q)
+        x = Q(F.linear(x, Qf(p[prefix + "fc%d.weight" % i], q), p[prefix + "fc%d.bias" % i]), q)
         x = bn_train(x, p[prefix + "bn%d.bn.weight" % i], p[prefix + "bn%d.bn.bias" % i])
         x = Q(F.relu(x), q) if i < 3 else Qb(x, q)        # the last BN writes fp32; its gradient arrives in bf16
     return x / torch.sqrt((x * x).sum(-1, keepdim=True) + 1e-12)

@@ -45,14 +45,16 @@ def init_params(seed=0, dtype=torch.float32, layers=(3, 4, 6, 3)):
     return p
 
 
-def simclr_head_loss(h1, h2, T):
-    """simclr_contrastive_head.py:52-94 in torch (autograd)."""
+def simclr_head_loss(h1, h2, T, q=False):
+    """simclr_contrastive_head.py:52-94 in torch (autograd).  q: quantisation-matched (bf16 embeddings into the similarity GEMM,
+    bf16 gradient of the similarity matrix coming back from the row kernel)."""
     n = h1.shape[0]
     eye = torch.eye(n, dtype=h1.dtype)
-    aa = h1 @ h1.t() / T - eye * LARGE_NUM
-    bb = h2 @ h2.t() / T - eye * LARGE_NUM
-    ab = h1 @ h2.t() / T
-    ba = h2 @ h1.t() / T
+    h1, h2 = R.Qf(h1, q), R.Qf(h2, q)
+    aa = R.Qb(h1 @ h1.t() / T, q) - eye * LARGE_NUM
+    bb = R.Qb(h2 @ h2.t() / T, q) - eye * LARGE_NUM
+    ab = R.Qb(h1 @ h2.t() / T, q)
+    ba = R.Qb(h2 @ h1.t() / T, q)
     lab = torch.arange(n)
     loss_a = F.cross_entropy(torch.cat([ab, aa], 1), lab, reduction="none")
     loss_b = F.cross_entropy(torch.cat([ba, bb], 1), lab, reduction="none")
@@ -64,17 +66,17 @@ def simclr_head_loss(h1, h2, T):
     return (loss_a + loss_b).mean() + 3 * (kl1 + kl2)
 
 
-def train_step(p, velocity, img_q, img_k, lr=0.1, T=0.1, momentum=0.9, lars_wd=1e-4, lars_coeff=0.001, exclude=None):
+def train_step(p, velocity, img_q, img_k, lr=0.1, T=0.1, momentum=0.9, lars_wd=1e-4, lars_coeff=0.001, exclude=None, q=False):
     """One iteration: forward, backward, LarsMomentum update (python loop per tensor, like the reference). Returns loss.
     `exclude(name) -> bool` marks tensors without decay / trust ratio; None = every tensor decays, which is what the SimCLR YAML's
     exclude list amounts to in the reference (its substrings match none of Paddle's generated names, see
     passl_b200/optimizer/naming.py)."""
     img = torch.cat([img_q, img_k])                                  # simclr.py:55
-    feat = R.resnet_forward(img, p, with_pool=True)
-    con = R.neck_fc3(feat, p, prefix="neck.")
+    feat = R.resnet_forward(img, p, with_pool=True, q=q)
+    con = R.neck_fc3(feat, p, prefix="neck.", q=q)
     con = con / torch.sqrt((con * con).sum(-1, keepdim=True) + 1e-12)  # layers.l2_normalize(con, -1), simclr.py:58
     n = img_q.shape[0]
-    loss = simclr_head_loss(con[:n], con[n:], T)
+    loss = simclr_head_loss(con[:n], con[n:], T, q=q)
     grads = torch.autograd.grad(loss, list(p.values()))
     with torch.no_grad():
         for (name, w), g in zip(p.items(), grads):

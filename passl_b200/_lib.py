@@ -107,9 +107,10 @@ SIGNATURES = {
     "passl_b200_maxpool3x3s2_bwd": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
     "passl_b200_avgpool_fwd": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 3 + [c_void_p]),
     "passl_b200_avgpool_bwd": (c_int, [c_void_p, c_void_p] + [c_int] * 3 + [c_void_p]),
-    "passl_b200_sgd_momentum": (c_int, [c_void_p] * 4 + [c_float] * 4 + [c_ll, c_void_p]),
-    "passl_b200_lars_momentum": (c_int, [c_void_p] * 7 + [c_int] + [c_float] * 5 + [c_ll, c_void_p]),
-    "passl_b200_adamw": (c_int, [c_void_p] * 8 + [c_float] * 4 + [c_int, c_float, c_ll, c_void_p]),
+    "passl_b200_sgd_momentum": (c_int, [c_void_p] * 4 + [c_float] * 4 + [c_void_p, c_ll, c_void_p]),
+    "passl_b200_lars_momentum": (c_int, [c_void_p] * 7 + [c_int] + [c_float] * 5 + [c_void_p, c_ll, c_void_p]),
+    "passl_b200_adamw": (c_int, [c_void_p] * 8 + [c_float] * 4 + [c_int, c_float, c_void_p, c_ll, c_void_p]),
+    "passl_b200_grad_norm_finite": (c_int, [c_void_p, c_ll, c_float, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p]),
 }
 
 _ERRORS = {-1: "bad argument / contract violation", -2: "unsupported configuration", -3: "TMA tensor-map encode failed",

@@ -16,6 +16,7 @@
 #include "host_utils.h"
 #include "../../include/passl_b200.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace pb {
@@ -213,6 +214,240 @@ __global__ void __launch_bounds__(160, 1) attn_fwd_kernel(const __grid_constant_
   }
 }
 
+// ======================================================================================================================
+// Forward, pipelined (round 2).  The round-1 kernel above ran load -> QK^T -> softmax -> PV -> epilogue strictly in sequence per
+// (batch, head): 114 TF/s at B=512, N=197, d=64.  Here one CTA (320 threads) keeps TWO work items (128 query rows of one head)
+// in flight:
+//   warp 0      : TMA producer — K / V of a head once (2-stage ring, shared by the head's query blocks), Q blocks (3-stage ring)
+//   warp 1      : MMA issuer — S = Q K^T of item i, then O = P V of item i-1 (P read from TMEM as the A operand, V from shared
+//                 memory as an MN-major B operand), so the tensor pipe works on one item while the SFUs work on the other
+//   warps 2..5  : softmax group 0 (items 0, 2, 4, ...);  warps 6..9 : softmax group 1 (items 1, 3, 5, ...): one query row per
+//                 thread, row max, exp2, P (bf16) written back over the S columns it was read from (tcgen05.st), then
+//                 O / sum -> global.  Warps whose 32 rows are all beyond N only keep the barriers moving.
+// TMEM: two 256-column slots; in a slot S uses [0, NKP), P (bf16x2) [0, NKP/2), O [128, 128 + d) — O is only written after P is
+// complete, and the next S only after O has been read.
+// Bound: N*NKP exponentials per head on 16 SFU lanes/clk/SM -> one 128-row item per 8*NKP cycles (1792 at NKP = 224), i.e. at
+// most ~50 % of the tensor pipe; the QK^T + PV MMAs of an item take ~900 cycles.
+// ======================================================================================================================
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+__global__ void __launch_bounds__(320, 1) attn_fwd2_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int rowB = p.d * 2;                         // bytes per Q/K/V row (128 or 64)
+  const uint32_t lt = (p.d == 64) ? 2u : 4u;        // SWIZZLE_128B / SWIZZLE_64B
+  const uint32_t sbo = 8u * rowB;                   // 8-row atom stride
+  constexpr int QST = 3, KVST = 2;
+  uint8_t* q_s = smem;                              // [QST][128][rowB]
+  uint8_t* k_s = q_s + QST * 128 * rowB;            // [KVST][256][rowB]
+  uint8_t* v_s = k_s + KVST * 256 * rowB;           // [KVST][256][rowB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + KVST * 256 * rowB);
+  uint64_t* q_full = bars;             // QST
+  uint64_t* q_empty = q_full + QST;    // QST
+  uint64_t* kv_full = q_empty + QST;   // KVST
+  uint64_t* kv_empty = kv_full + KVST; // KVST
+  uint64_t* s_full = kv_empty + KVST;  // 2
+  uint64_t* p_full = s_full + 2;       // 2
+  uint64_t* o_full = p_full + 2;       // 2
+  uint64_t* slot_free = o_full + 2;    // 2
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(slot_free + 2);
+
+  const uint32_t warp = warp_id(), lane = lane_id();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.qkv_map);
+    tma_prefetch_desc(&p.kv_map);
+    for (int i = 0; i < QST; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
+    for (int i = 0; i < KVST; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&o_full[i], 1); mbar_init(&slot_free[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int heads = p.B * p.H;
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    int qi = 0, kvi = 0;
+    uint32_t qph = 0, kvph = 0;
+    for (int head = blockIdx.x; head < heads; head += gridDim.x) {
+      const int b = head / p.H, h = head - b * p.H;
+      mbar_wait(&kv_empty[kvi], kvph ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&kv_full[kvi], (uint32_t)(2 * p.NKP * rowB));
+        tma_load_4d(k_s + kvi * 256 * rowB, &p.kv_map, &kv_full[kvi], 0, p.H + h, 0, b);
+        tma_load_4d(v_s + kvi * 256 * rowB, &p.kv_map, &kv_full[kvi], 0, 2 * p.H + h, 0, b);
+      }
+      __syncwarp();
+      if (++kvi == KVST) { kvi = 0; kvph ^= 1; }
+      for (int mb = 0; mb < p.mblocks; ++mb) {
+        mbar_wait(&q_empty[qi], qph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&q_full[qi], (uint32_t)(128 * rowB));
+          tma_load_4d(q_s + qi * 128 * rowB, &p.qkv_map, &q_full[qi], 0, h, mb * 128, b);
+        }
+        __syncwarp();
+        if (++qi == QST) { qi = 0; qph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    const uint32_t idesc1 = make_idesc_bf16(128, p.NKP, false, false);
+    const uint32_t idesc2 = make_idesc_bf16(128, p.d, false, true);
+    int qi = 0, kvi = 0, it = 0;
+    uint32_t qph = 0, kvph = 0;
+    int pv_slot = -1, pv_kv = 0, pv_last = 0;           // the item whose P V product is still to be issued
+    uint32_t pv_ph = 0;
+    auto issue_pv = [&]() {
+      mbar_wait(&p_full[pv_slot], pv_ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t tm_p = tmem_base + pv_slot * 256, tm_o = tm_p + 128;
+        const uint32_t va = smem_u32(v_s + pv_kv * 256 * rowB);
+        for (int k = 0; k < p.NKP / 16; ++k)     // A: 16 keys = 8 packed columns of P; B: 16 key rows of V (MN-major, 2 atoms)
+          umma_bf16_ts(tm_o, tm_p + k * 8, make_smem_desc(va + k * 16 * rowB, 0, sbo, lt), idesc2, k > 0 ? 1u : 0u);
+        umma_commit(&o_full[pv_slot]);
+        if (pv_last) umma_commit(&kv_empty[pv_kv]);
+      }
+      __syncwarp();
+    };
+    for (int head = blockIdx.x; head < heads; head += gridDim.x) {
+      mbar_wait(&kv_full[kvi], kvph);
+      for (int mb = 0; mb < p.mblocks; ++mb, ++it) {
+        const int slot = it & 1;
+        const uint32_t sph = (it >> 1) & 1;
+        mbar_wait(&q_full[qi], qph);
+        mbar_wait(&slot_free[slot], sph ^ 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t qa = smem_u32(q_s + qi * 128 * rowB), ka = smem_u32(k_s + kvi * 256 * rowB);
+          for (int k = 0; k < p.d / 16; ++k)
+            umma_bf16(tmem_base + slot * 256, make_smem_desc(qa + k * 32, 16, sbo, lt), make_smem_desc(ka + k * 32, 16, sbo, lt), idesc1,
+                      k > 0 ? 1u : 0u);
+          umma_commit(&s_full[slot]);
+          umma_commit(&q_empty[qi]);
+        }
+        __syncwarp();
+        if (pv_slot >= 0) issue_pv();
+        pv_slot = slot; pv_ph = sph; pv_kv = kvi; pv_last = (mb == p.mblocks - 1);
+        if (++qi == QST) { qi = 0; qph ^= 1; }
+      }
+      if (++kvi == KVST) { kvi = 0; kvph ^= 1; }
+    }
+    if (pv_slot >= 0) issue_pv();
+  } else {
+    // ---------------- softmax / epilogue groups ----------------
+    const int g = (warp - 2) >> 2;                    // group = TMEM slot
+    const uint32_t q4 = warp & 3;                     // TMEM lane quarter of this warp
+    const int r = q4 * 32 + lane;                     // row within the 128-row block
+    const float c2 = p.scale * kAttnLog2e;
+    const uint32_t ts = tmem_base + g * 256 + ((q4 * 32u) << 16);
+    int it = 0;
+    for (int head = blockIdx.x; head < heads; head += gridDim.x) {
+      const int b = head / p.H, h = head - b * p.H;
+      for (int mb = 0; mb < p.mblocks; ++mb, ++it) {
+        if ((it & 1) != g) continue;
+        const uint32_t sph = (it >> 1) & 1;
+        const int row = mb * 128 + r;                 // query index
+        const bool row_ok = row < p.N;
+        const bool warp_ok = mb * 128 + (int)q4 * 32 < p.N;      // any valid row in this warp
+        const int jmax = p.causal ? (row + 1 < p.N ? row + 1 : p.N) : p.N;   // valid keys: j < jmax
+        mbar_wait(&s_full[g], sph);
+        tc_fence_after();
+        float l = 0.f, l_exact = 0.f, m = 0.f;
+        if (warp_ok) {
+          // pass 1: row maximum (log2 domain)
+          m = -INFINITY;
+          for (int c = 0; c < p.NKP / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(ts + c * 32, v);
+            tmem_ld_wait();
+            if (c * 32 + 32 <= jmax) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (c * 32 + j < jmax) m = fmaxf(m, __uint_as_float(v[j]));
+            }
+          }
+          m = (!row_ok || m == -INFINITY) ? 0.f : m * c2;
+          // pass 2: p = exp2(y - m), row sums, P (bf16x2) over the S columns already consumed
+          for (int c = 0; c < p.NKP / 32; ++c) {
+            uint32_t v[32], w[16];
+            tmem_ld_32x32(ts + c * 32, v);
+            tmem_ld_wait();
+            const bool full = c * 32 + 32 <= jmax;
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              float p0 = exp2f(fmaf(__uint_as_float(v[j]), c2, -m)), p1 = exp2f(fmaf(__uint_as_float(v[j + 1]), c2, -m));
+              if (!full) {
+                if (c * 32 + j >= jmax) p0 = 0.f;
+                if (c * 32 + j + 1 >= jmax) p1 = 0.f;
+              }
+              // the tensor core multiplies the bf16-rounded probability: normalise O by the sum of the same rounded values,
+              // but report the exact log-sum-exp (the backward recomputes P from it)
+              const uint32_t pk = pack_bf16x2(p0, p1);
+              const float2 e = unpack_bf16x2(pk);
+              l += e.x + e.y;
+              l_exact += p0 + p1;
+              w[j >> 1] = pk;
+            }
+            tmem_st_32x16(ts + c * 16, w);
+          }
+          tmem_st_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[g]);
+        // epilogue: O / l
+        mbar_wait(&o_full[g], sph);
+        tc_fence_after();
+        if (warp_ok) {
+          const float inv = (l > 0.f) ? 1.f / l : 0.f;
+          __nv_bfloat16* op = p.out + (((size_t)b * p.N + row) * p.H + h) * p.d;
+          for (int c = 0; c < p.d / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(ts + 128 + c * 32, v);
+            tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+              for (int gq = 0; gq < 4; ++gq) {
+                uint4 u;
+                u.x = pack_bf16x2(__uint_as_float(v[gq * 8 + 0]) * inv, __uint_as_float(v[gq * 8 + 1]) * inv);
+                u.y = pack_bf16x2(__uint_as_float(v[gq * 8 + 2]) * inv, __uint_as_float(v[gq * 8 + 3]) * inv);
+                u.z = pack_bf16x2(__uint_as_float(v[gq * 8 + 4]) * inv, __uint_as_float(v[gq * 8 + 5]) * inv);
+                u.w = pack_bf16x2(__uint_as_float(v[gq * 8 + 6]) * inv, __uint_as_float(v[gq * 8 + 7]) * inv);
+                *reinterpret_cast<uint4*>(op + c * 32 + gq * 8) = u;
+              }
+            }
+          }
+          if (row_ok) p.lse[((size_t)b * p.H + h) * p.N + row] = (m + log2f(l_exact)) * kAttnLn2;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&slot_free[g]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 static int attn_make_maps(AttnParams& p, const void* qkv) {
   const uint64_t d = p.d, H3 = 3ull * p.H;
   uint64_t dims[4] = {d, H3, (uint64_t)p.N, (uint64_t)p.B};
@@ -242,13 +477,26 @@ extern "C" int passl_b200_attention_fwd(const void* qkv, void* out, float* lse, 
   p.mblocks = (N + 127) / 128;
   int rc = attn_make_maps(p, qkv);
   if (rc) return rc;
+  int grid = B * H < num_sms() ? B * H : num_sms();
+  static int use_v1 = -1;
+  if (use_v1 < 0) use_v1 = getenv("PASSL_B200_ATTN_V1") ? 1 : 0;      // round-1 serial kernel, kept for A/B timing
+  if (!use_v1) {
+    const int smem2 = (3 * 128 + 4 * 256) * d * 2 + 256 + 1024;
+    static bool attr2 = false;
+    if (!attr2) {
+      PB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (3 * 128 + 4 * 256) * 128 + 256 + 1024));
+      attr2 = true;
+    }
+    attn_fwd2_kernel<<<grid, 320, smem2, (cudaStream_t)stream>>>(p);
+    PB_LAUNCH_CHECK();
+    return PB_OK;
+  }
   const int smem = 3 * 256 * d * 2 + 4 * 128 * 128 + 256 + 1024;
   static bool attr = false;
   if (!attr) {
     PB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 256 * 128 + 4 * 128 * 128 + 256 + 1024));
     attr = true;
   }
-  int grid = B * H < num_sms() ? B * H : num_sms();
   attn_fwd_kernel<<<grid, 160, smem, (cudaStream_t)stream>>>(p);
   PB_LAUNCH_CHECK();
   return PB_OK;

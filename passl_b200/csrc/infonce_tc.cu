@@ -58,12 +58,12 @@ struct InfoNceTcParams {
   int tgt_mode;             // 0: owner CTA computes, epoch flags (grid <= SM count); 1: every thread computes its own row
   int poly_ok;              // exponent range allows the FMA-pipe polynomial (2.1 * scale * log2e < 120)
   // persistent state (zeroed once by the caller, left zeroed / epoch-advanced by every launch)
-  unsigned* epoch; unsigned* ticket; unsigned* flags; float* tgt_raw; float* acc_l; unsigned* acc_cnt;
+  unsigned* epoch; unsigned* ticket; unsigned long long* tgt_tag; float* acc_l; unsigned* acc_cnt;
   // forward outputs
   float* lse; float* tgt; float* loss_rows; float* out;
   // backward
   const float* lse_in; const float* tgt_in; const float* dloss; float* dq;
-  unsigned long long* dbg;  // optional per-CTA timeline (globaltimer ns), 16 slots per CTA
+  unsigned long long* dbg;  // optional per-CTA timeline (globaltimer ns), 32 slots per CTA
 };
 
 __device__ __forceinline__ unsigned long long gtime() {
@@ -71,7 +71,9 @@ __device__ __forceinline__ unsigned long long gtime() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-#define NCE_STAMP(slot) do { if (p.dbg) p.dbg[blockIdx.x * 16 + (slot)] = gtime(); } while (0)
+#define NCE_STAMP(slot) do { if (p.dbg) p.dbg[blockIdx.x * 32 + (slot)] = gtime(); } while (0)
+// SM cycle counter relative to the start of the CTA (globaltimer only ticks every ~256 ns)
+#define NCE_STAMPC(slot) do { if (p.dbg) p.dbg[blockIdx.x * 32 + (slot)] = (unsigned long long)(clock64() - nce_c0); } while (0)
 
 __device__ __forceinline__ float ex2_mufu(float x) {
   float y;
@@ -96,13 +98,15 @@ __device__ __forceinline__ float ex2_poly(float a, float c2, float C) {
   q = __fmaf_rn(q, x, 1.0f);
   return __int_as_float(__float_as_int(q) + (__float_as_int(r) << 23));
 }
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+// {tag, value} published / polled as ONE 64-bit word: no fences on either side (release / acquire cost a MEMBAR.GPU on the
+// producer and an L1 invalidate per poll on the consumers: 27 % of all stall samples in the first version of this kernel)
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -111,7 +115,7 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 // ---- shared-memory carve-up (same for forward and backward) --------------------------------------------------------------
 struct NceSmem {
   uint8_t* q_smem; uint8_t* k_smem;
-  uint64_t *q_ready, *k_full, *k_empty, *s_full, *s_empty, *q_full, *p_full, *dq_full;
+  uint64_t *q_ready, *k_full, *k_empty, *s_full, *s_empty, *q_full, *p_full, *dq_full, *tgt_done;
   uint32_t* tmem_ptr;
   int stages, q_bytes, stage_bytes;
 };
@@ -133,28 +137,40 @@ __device__ __forceinline__ NceSmem nce_carve(uint8_t* smem_raw, int MB, int D) {
   s.q_full = s.s_empty + 2;   // 1
   s.p_full = s.q_full + 1;    // 2 (backward)
   s.dq_full = s.p_full + 2;   // 1 (backward)
-  s.tmem_ptr = reinterpret_cast<uint32_t*>(s.dq_full + 1);
+  s.tgt_done = s.dq_full + 1; // 1 (forward): every softmax warp holds its rows' target logits
+  s.tmem_ptr = reinterpret_cast<uint32_t*>(s.tgt_done + 1);
   return s;
 }
 
-// TMA producer (whole warp 0): Q block once, then the key tiles of [t_begin, t_end) through the ring
-__device__ __forceinline__ void nce_producer(const InfoNceTcParams& p, const NceSmem& s, int MB, int row_base, int t_begin, int t_end) {
+// TMA producer (whole warp 0): Q block, [forward: this CTA's share of the target logits], the first key tiles, and — once every
+// softmax warp holds its target logits — the rest of the key stream.  The bulk stream saturates the SM's L2 port (~60 B/clk): in
+// the first version the 8-byte target polls queued behind 112 KB of key tiles and returned ~8000 cycles late.
+__device__ __forceinline__ void nce_owner_targets(const InfoNceTcParams& p, int ew, int nsw, uint32_t lane, unsigned epoch);
+__device__ __forceinline__ void nce_producer(const InfoNceTcParams& p, const NceSmem& s, int MB, int row_base, int t_begin, int t_end,
+                                             bool fwd, unsigned epoch) {
   const int DC = p.D / 64;
+  const uint32_t lane = lane_id();
+  // the key matrix is streamed once (evict-first: it must not push the re-used operands out of L2); the query block is read
+  // by every CTA of the row group (evict-last)
+  const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
   if (elect_one()) {
     mbar_arrive_expect_tx(s.q_full, (uint32_t)s.q_bytes);
     for (int b = 0; b < MB; ++b)
       for (int c = 0; c < DC; ++c)
-        tma_load_2d(s.q_smem + (b * DC + c) * (128 * 128), &p.q_map, s.q_full, c * 64, row_base + b * 128);
+        tma_load_2d_hint(s.q_smem + (b * DC + c) * (128 * 128), &p.q_map, s.q_full, c * 64, row_base + b * 128, pol_keep);
   }
   __syncwarp();
+  if (fwd) nce_owner_targets(p, 0, 1, lane, epoch);
+  if (fwd && p.dbg && lane == 0) p.dbg[blockIdx.x * 32 + 30] = (unsigned long long)clock64();
   int stage = 0;
   uint32_t phase = 0;
   for (int t = t_begin; t < t_end; ++t) {
+    if (fwd && t == t_begin + 2) mbar_wait(s.tgt_done, 0);
     mbar_wait(&s.k_empty[stage], phase ^ 1);
     if (elect_one()) {
       mbar_arrive_expect_tx(&s.k_full[stage], (uint32_t)s.stage_bytes);
       for (int c = 0; c < DC; ++c)
-        tma_load_2d(s.k_smem + stage * s.stage_bytes + c * (NCE_BK * 128), &p.k_map, &s.k_full[stage], c * 64, t * NCE_BK);
+        tma_load_2d_hint(s.k_smem + stage * s.stage_bytes + c * (NCE_BK * 128), &p.k_map, &s.k_full[stage], c * 64, t * NCE_BK, pol_stream);
     }
     __syncwarp();
     if (++stage == s.stages) { stage = 0; phase ^= 1; }
@@ -171,11 +187,12 @@ __device__ __forceinline__ void nce_owner_targets(const InfoNceTcParams& p, int 
       lab = p.label[row];
       lab = lab < 0 ? 0 : (lab >= p.K ? p.K - 1 : lab);
     }
+    const uint64_t pol_keep = l2_policy_evict_last();
     for (int d4 = lane * 4; d4 < p.D; d4 += 128) {
-      const uint2 qu = *reinterpret_cast<const uint2*>(p.Q + (size_t)row * p.D + d4);
+      const uint2 qu = ldg_u2_hint(p.Q + (size_t)row * p.D + d4, pol_keep);
       const float2 q0 = unpack_bf16x2(qu.x), q1 = unpack_bf16x2(qu.y);
       if (p.P) {
-        const float4 pa = *reinterpret_cast<const float4*>(p.P + (size_t)row * p.D + d4);
+        const float4 pa = ldg_f4_hint(p.P + (size_t)row * p.D + d4, pol_keep);
         acc += q0.x * pa.x + q0.y * pa.y + q1.x * pa.z + q1.y * pa.w;
       } else {
         const uint2 ku = *reinterpret_cast<const uint2*>(p.Kmat + (size_t)lab * p.D + d4);
@@ -184,10 +201,8 @@ __device__ __forceinline__ void nce_owner_targets(const InfoNceTcParams& p, int 
       }
     }
     acc = warp_sum(acc);
-    if (lane == 0) {
-      p.tgt_raw[row] = acc;
-      st_release_u32(p.flags + row, epoch + 1u);
-    }
+    if (lane == 0)
+      st_relaxed_u64(p.tgt_tag + row, ((unsigned long long)(epoch + 1u) << 32) | (unsigned long long)__float_as_uint(acc));
   }
 }
 
@@ -218,16 +233,18 @@ __device__ __forceinline__ void nce_stage_q(const InfoNceTcParams& p, const NceS
 __device__ __forceinline__ float nce_fetch_target(const InfoNceTcParams& p, int row, bool row_ok, unsigned epoch) {
   if (!row_ok) return 0.f;
   if (p.tgt_mode == 0) {
-    if (ld_acquire_u32(p.flags + row) != epoch + 1u) {
+    unsigned long long w = ld_relaxed_u64(p.tgt_tag + row);
+    if ((unsigned)(w >> 32) != epoch + 1u) {
       const long long t0 = clock64();
-      while (ld_acquire_u32(p.flags + row) != epoch + 1u) {
+      do {
+        w = ld_relaxed_u64(p.tgt_tag + row);
         if (clock64() - t0 > 4000000000LL) {
           printf("passl_b200: InfoNCE target flag timeout (block %d row %d)\n", blockIdx.x, row);
           __trap();
         }
-      }
+      } while ((unsigned)(w >> 32) != epoch + 1u);
     }
-    return __ldcg(p.tgt_raw + row);
+    return __uint_as_float((unsigned)w);
   }
   float acc = 0.f;
   long long lab = 0;
@@ -265,6 +282,7 @@ __device__ __forceinline__ void nce_setup(const InfoNceTcParams& p, const NceSme
       mbar_init(&s.p_full[i], 4);
     }
     mbar_init(s.dq_full, 1);
+    mbar_init(s.tgt_done, 4 * MB);
     fence_barrier_init();
   }
   (void)bwd;
@@ -296,9 +314,10 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
   const int t_end = (int)((long long)(slice + 1) * p.tiles / p.slices);
   const uint32_t q_cols = p.D / 2;                 // bf16x2 per 32-bit TMEM column
 
+  const long long nce_c0 = clock64();
   if (threadIdx.x == 64) NCE_STAMP(0);
   nce_setup(p, s, MB, warp, lane, false);
-  if (threadIdx.x == 64) NCE_STAMP(1);
+  if (threadIdx.x == 64) NCE_STAMPC(1);
   const unsigned epoch = __ldcg(p.epoch);
   const uint32_t tmem_base = *s.tmem_ptr;
   const uint32_t tm_q = tmem_base;                       // Q (A operand): block b at columns [b*q_cols, (b+1)*q_cols)
@@ -306,14 +325,14 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
 
   // role loops are warp-uniform; only the TMA / tcgen05 issue is elect-predicated (keeps descriptors in uniform registers)
   if (warp == 0) {
-    nce_producer(p, s, MB, row_base, t_begin, t_end);
+    nce_producer(p, s, MB, row_base, t_begin, t_end, true, epoch);
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
     constexpr uint32_t idesc = make_idesc_bf16(128, NCE_BK, false, false);
     const uint64_t db0 = make_smem_desc_sw128(smem_u32(s.k_smem), 16, 1024);   // stage 0, chunk 0, k-step 0
     mbar_wait(s.q_ready, 0);
     tc_fence_after();
-    if (lane == 0) NCE_STAMP(14);
+    if (lane == 0) NCE_STAMPC(24);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -323,6 +342,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
       mbar_wait(&s.s_empty[buf], bphase ^ 1);
       mbar_wait(&s.k_full[stage], phase);
       tc_fence_after();
+      if (lane == 0 && it < 7) NCE_STAMPC(25 + it);
       const uint64_t dbs = db0 + (uint64_t)((stage * s.stage_bytes) >> 4);
       if (elect_one()) {
         for (int b = 0; b < MB; ++b) {
@@ -350,9 +370,8 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
     const bool row_ok = row < p.N;
     const float c2 = p.scale * kLog2e;  // logits in the log2 domain: y = dot * c2
 
-    nce_owner_targets(p, ew, 4 * MB, lane, epoch);
     nce_stage_q(p, s, tm_q, b, q4, lane);
-    if (threadIdx.x == 64) NCE_STAMP(3);
+    if (threadIdx.x == 64) NCE_STAMPC(2);
     long long lab = -1;
     int ex = -1;
     if (row_ok) {
@@ -361,7 +380,11 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
     }
     const float tgt_raw = nce_fetch_target(p, row, row_ok, epoch);
     const float tgt2 = tgt_raw * c2;
-    if (threadIdx.x == 64) NCE_STAMP(4);
+    if (p.tgt_mode != 0 && slice == 0 && row_ok)       // the finalizing CTA reads the targets from the state buffer
+      st_relaxed_u64(p.tgt_tag + row, ((unsigned long long)(epoch + 1u) << 32) | (unsigned long long)__float_as_uint(tgt_raw));
+    __syncwarp();
+    if (lane == 0) mbar_arrive(s.tgt_done);
+    if (threadIdx.x == 64) NCE_STAMPC(3);
 
     float m = -INFINITY, l = 0.f;     // m: integer-valued running max (log2 domain)
     int cnt = 0;
@@ -369,14 +392,16 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
     for (int t = t_begin; t < t_end; ++t, ++it) {
       const int buf = it & 1;
       const uint32_t bphase = (it >> 1) & 1;
+      if (threadIdx.x == 64 && it < 5) NCE_STAMPC(4 + 4 * it);
       mbar_wait(&s.s_full[buf], bphase);
       tc_fence_after();
-      if (threadIdx.x == 64 && it < 8) NCE_STAMP(5 + it);
+      if (threadIdx.x == 64 && it < 5) NCE_STAMPC(5 + 4 * it);
       const uint32_t taddr = tm_s + ((q4 * 32u) << 16) + (buf * MB + b) * NCE_BK;
       uint32_t v[64];
       tmem_ld_32x32(taddr, v);
       tmem_ld_32x32(taddr + 32, v + 32);
       tmem_ld_wait();
+      if (threadIdx.x == 64 && it < 5) NCE_STAMPC(6 + 4 * it);
       // TMEM buffer can be refilled as soon as the values are in registers
       tc_fence_before();
       __syncwarp();
@@ -453,8 +478,8 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
           m = mn;
         }
       }
+      if (threadIdx.x == 64 && it < 5) { asm volatile("" :: "f"(l)); NCE_STAMPC(7 + 4 * it); }
     }
-    if (threadIdx.x == 64) NCE_STAMP(13);
     if (row_ok) {
       // slice sum relative to 2^(target + 64); merged over the slices by float atomics (order-dependent in the last bit)
       if (m > -INFINITY) {
@@ -487,7 +512,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
     const unsigned cnt = __ldcg(p.acc_cnt + row);
     p.acc_l[row] = 0.f;
     p.acc_cnt[row] = 0u;
-    const float tgt2 = __ldcg(p.tgt_raw + row) * c2;
+    const float tgt2 = __uint_as_float((unsigned)ld_relaxed_u64(p.tgt_tag + row)) * c2;
     if (p.P) L += 5.421010862427522e-20f;                 // the positive pair's own column: 2^(tgt - (tgt + 64))
     const float lse = (tgt2 + kRefShift + log2f(L)) * kLn2;
     const float t = tgt2 * kLn2;
@@ -538,7 +563,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_bwd_kernel(const 
   const uint32_t tm_sp = tm_dq + MB * p.D;                // S (fp32, 64 cols) / P (bf16x2, 32 cols) per block: b*64
 
   if (warp == 0) {
-    nce_producer(p, s, MB, row_base, t_begin, t_end);
+    nce_producer(p, s, MB, row_base, t_begin, t_end, false, 0u);
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
     constexpr uint32_t idesc_s = make_idesc_bf16(128, NCE_BK, false, false);
@@ -782,7 +807,7 @@ static unsigned long long* g_nce_dbg = nullptr;
 // developer hook: per-CTA timeline buffer (uint64 [grid * 16]) filled by the next launches; NULL disables
 extern "C" int passl_b200_infonce_tc_set_debug(void* buf) { g_nce_dbg = reinterpret_cast<unsigned long long*>(buf); return 0; }
 
-// persistent state: [epoch, ticket, pad, pad][flags N][tgt_raw N][acc_l N][acc_cnt N]
+// persistent state: [epoch, ticket, pad, pad][tgt_tag N x u64][acc_l N][acc_cnt N]
 extern "C" long long passl_b200_infonce_tc_workspace_bytes(int N, int K, int D) {
   (void)K; (void)D;
   return 16 + (long long)N * 16;
@@ -806,8 +831,8 @@ extern "C" int passl_b200_infonce_tc_fwd(const void* Q, const void* Kmat, const 
   int rc = nce_fill_params(p, Q, Kmat, P, label, excl, scale, loss_scale, N, K, D, MB, smem);
   if (rc) return rc;
   unsigned* w = reinterpret_cast<unsigned*>(workspace);
-  p.epoch = w; p.ticket = w + 1; p.flags = w + 4;
-  p.tgt_raw = reinterpret_cast<float*>(w + 4 + N);
+  p.epoch = w; p.ticket = w + 1;
+  p.tgt_tag = reinterpret_cast<unsigned long long*>(w + 4);
   p.acc_l = reinterpret_cast<float*>(w + 4 + 2 * (size_t)N);
   p.acc_cnt = w + 4 + 3 * (size_t)N;
   p.lse = lse; p.tgt = tgt; p.loss_rows = loss_rows; p.out = out_scalars;

@@ -65,3 +65,20 @@ def param_sync(store, src=0):
         return
     dist.broadcast(store.master, src=src)
     store.refresh_bf16()
+
+
+def model_sync(model, stores, src=0):
+    """Initial broadcast of EVERYTHING the reference's param_sync / DataParallel wrap broadcasts (passl/core/sync_utils.py:46-69):
+    every parameter, stop_gradient ones included (MoCo's key encoder, MoCo v3's momentum encoder — each is a flat store here),
+    and every registered buffer (BatchNorm running statistics, MoCo's queue and queue_ptr)."""
+    if get_world_size() < 2:
+        return
+    for st in stores:
+        if st is not None:
+            param_sync(st, src=src)
+    for b in model.buffers():
+        if b.is_cuda or dist.get_backend() == "gloo":
+            dist.broadcast(b, src=src)
+    refresh = getattr(model, "refresh_buffer_mirrors", None)
+    if refresh is not None:
+        refresh()

@@ -8,7 +8,7 @@ schedule moves after each epoch; a checkpoint every `save_interval` epochs and a
 `{output_dir}/{Model.name}/epoch_N.*`; `max_train_step` ends the run early; a non-finite loss stops it.
 
 Not rebuilt (outside the self-supervised training path): eval / export modes, validation loops, EMA-of-weights evaluation,
-VisualDL, DALI, gradient accumulation > 1, FP16 loss scaling (the compute path is bf16 with fp32 master weights, so the `FP16`
+VisualDL, DALI, FP16 autocast (the compute path is bf16 with fp32 master weights, so the `FP16`
 section is accepted and has nothing to configure), sharding / tensor parallel strategies.  Data: synthetic two-view batches
 unless a loader is passed in (no ImageNet in this environment); the `DataLoader.Train.sampler.batch_size` key is honoured.
 """
@@ -23,7 +23,7 @@ import numpy as np
 import torch
 
 from ..core.param_store import ParamStore
-from ..distributed import get_rank, get_world_size, grad_sync, param_sync
+from ..distributed import get_rank, get_world_size, grad_sync, model_sync
 from ..models import build_model
 from ..optimizer import build_lr_scheduler_v2, build_optimizer
 
@@ -53,9 +53,8 @@ class Engine:
         G = config["Global"]
         self.print_batch_step = G.get("print_batch_step", 10)
         self.save_interval = G.get("save_interval", 1)
-        self.accum_steps = G.get("accum_steps", 1)
-        if self.accum_steps != 1:
-            raise NotImplementedError("accum_steps = %r (gradient accumulation is not built)" % (self.accum_steps,))
+        self.accum_steps = int(G.get("accum_steps", 1))      # gradient merge (contrastive_learning_loop.py:35-63)
+        assert self.accum_steps >= 1
         self.max_train_step = G.get("max_train_step", None)
         assert self.max_train_step is None or (isinstance(self.max_train_step, int) and self.max_train_step > 0), \
             "max_train_step must be int dtype and greater than 0"
@@ -75,12 +74,13 @@ class Engine:
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.model_name = config["Model"]["name"]
         self.model = build_model(dict(config["Model"])).to(self.device)
+        store_k = None
         if hasattr(self.model, "build_param_stores"):
-            self.store, _ = self.model.build_param_stores()
+            self.store, store_k = self.model.build_param_stores()
         else:
             self.store = ParamStore(self.model)
         if self.device.type == "cuda":
-            param_sync(self.store)
+            model_sync(self.model, (self.store, store_k))   # every parameter (the momentum encoder too) and buffer from rank 0
         train_cfg = (config.get("DataLoader", {}) or {}).get("Train", {}) or {}
         self.batch_size = int((train_cfg.get("sampler", {}) or {}).get("batch_size", 32))
         if dataloader is None:
@@ -108,25 +108,63 @@ class Engine:
             lr_inner["decay_unit"] = self.lr_decay_unit
             self.lr_scheduler = build_lr_scheduler_v2(lr_inner, self.epochs, steps_per_epoch)
             opt_cfg["lr"] = self.lr_scheduler.get_lr()
-        for key in ("grad_clip", "layer_decay", "param_groups", "tensor_fusion"):
-            if opt_cfg.pop(key, None) not in (None, True):
+        for key in ("layer_decay", "param_groups", "tensor_fusion"):
+            v = opt_cfg.pop(key, None)
+            # falsy = not requested (the reference YAMLs spell out `tensor_fusion: False`); tensor_fusion: True is what the flat
+            # ParamStore always does (param_fuse.py:418-505)
+            if v and not (key == "tensor_fusion" and v is True):
                 raise NotImplementedError("Optimizer.%s is not built" % key)
+        if not opt_cfg.get("grad_clip"):
+            opt_cfg.pop("grad_clip", None)                   # otherwise: ClipGradByGlobalNorm as one pass (optimizer.GradControl)
         self.optimizer = build_optimizer(opt_cfg, self.store)
+        # the scaler of the reference loop (engine.py:180-194): a pass-through here — bf16 compute needs no loss scaling; set
+        # Global.FP16-style dynamic scaling explicitly with `loss_scaling: {enable: True, ...}` to exercise the scaled path
+        from ..core.grad_scaler import GradScaler
+        sc = dict(G.get("loss_scaling", {}) or {})
+        self.scaler = GradScaler(enable=bool(sc.pop("enable", False)), **sc)
         self.global_step, self.cur_epoch_id = 0, 0
 
     # -- one optimizer step (contrastive_learning_loop.py:65-88) --------------------------------------------------------------
     def train_one_step(self, batch):
         if self.lr_scheduler is not None:
             self.optimizer.set_lr(self.lr_scheduler.get_lr())        # the optimizer reads the schedule when it steps
-        out = self.model(batch)
-        loss = out["loss"] if isinstance(out, dict) else out
-        loss.backward()
+        loss = self.forward_backward(batch)
         grad_sync(self.store)
-        self.optimizer.step()
+        self.scaler.step(self.optimizer)                    # = optimizer.step() unless loss scaling is enabled
+        self.scaler.update()
         self.optimizer.clear_grad()
         if self.lr_scheduler is not None and self.lr_decay_unit == "step":
             self.lr_scheduler.step(self.global_step)
         return loss
+
+    def forward_backward(self, batch):
+        """contrastive_learning_loop.py:31-63: the batch is cut into `accum_steps` sub-batches; each runs forward + backward with
+        its loss divided by accum_steps, gradients add up in the flat fp32 buffer, one optimizer step follows.  The 1/accum_steps
+        is folded into the optimizer's gradient multiplier (same update, no extra pass); the returned loss is the mean."""
+        A = self.accum_steps
+        if A == 1:
+            out = self.model(batch)
+            loss = out["loss"] if isinstance(out, dict) else out
+            self.scaler.scale(loss).backward()
+            return loss
+        bs = batch[0].shape[0]
+        assert bs % A == 0, ("Bad accum_steps %d for batch size %d. This may be caused by two reasons: 1) the batch size setting is "
+                             "unreasonable and cannot be divisible, 2) drop_last in the sampler configuration is not set to True." % (A, bs))
+        step_size = bs // A
+        from .. import kernels as K
+        total = None
+        for idx in range(A):
+            sub = [b[idx * step_size:(idx + 1) * step_size].contiguous() for b in batch]
+            out = self.model(sub)
+            loss = out["loss"] if isinstance(out, dict) else out
+            self.scaler.scale(loss).backward()
+            with torch.no_grad():
+                l = loss.detach().reshape(1).float().contiguous()
+                if total is None:
+                    total = torch.zeros(1, dtype=torch.float32, device=l.device)
+                K.axpy(total, l, 1.0 / A)
+        self.optimizer.grad_scale = 1.0 / (get_world_size() * A)
+        return total[0]
 
     def train(self):
         from ..utils.profiler import StepProfiler

@@ -15,7 +15,7 @@ import time
 import torch
 
 from ..core.param_store import ParamStore
-from ..distributed import get_rank, get_world_size, grad_sync, param_sync
+from ..distributed import get_rank, get_world_size, grad_sync, model_sync, param_sync
 from ..modeling import build_model
 from ..optimizer import build_lr_scheduler, build_lr_scheduler_simclr, build_optimizer
 
@@ -62,6 +62,22 @@ class SyntheticTwoViews:
             yield self.a, self.b
 
 
+class SyntheticSingleView:
+    """Synthetic single-image batches (MAE pre-training: one N(0,1) image per sample)."""
+
+    def __init__(self, batch_size, iters, device, size=224, seed=1234):
+        self.iters = iters
+        g = torch.Generator(device=device).manual_seed(seed + get_rank())
+        self.img = torch.randn(batch_size, 3, size, size, device=device, generator=g)
+
+    def __len__(self):
+        return self.iters
+
+    def __iter__(self):
+        for _ in range(self.iters):
+            yield (self.img,)
+
+
 class SyntheticImageText:
     """Synthetic (image, text) batches for the CLIP path: N(0,1) images, random token ids with the EOT id (vocab - 1) at a random
     position >= 1 (SURVEY §8d synthetic-input spec)."""
@@ -88,11 +104,12 @@ class Trainer:
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.model = build_model(dict(cfg.model)).to(self.device)
         enc = getattr(self.model, "encoder_q", None) or getattr(self.model, "encoder", None) or self.model
+        store_k = None
         if hasattr(self.model, "build_param_stores"):
-            self.store, _ = self.model.build_param_stores()
+            self.store, store_k = self.model.build_param_stores()
         else:
             self.store = ParamStore(enc)
-        param_sync(self.store)
+        model_sync(self.model, (self.store, store_k))       # parameters (stop_gradient ones too) and buffers from rank 0
         self.batch_size = cfg.dataloader.train.sampler.batch_size
         if dataloader is None:
             iters = cfg.get("total_iters", 10)
@@ -101,6 +118,8 @@ class Trainer:
                 arch = cfg.model.architecture
                 dataloader = SyntheticImageText(self.batch_size, iters, self.device, size=arch.image_resolution,
                                                 context_length=arch.context_length, vocab_size=arch.vocab_size)
+            elif (cfg.dataloader.train.get("dataset", {}) or {}).get("single_view", False):
+                dataloader = SyntheticSingleView(self.batch_size, iters, self.device)
             elif cfg.dataloader.train.get("device_input_stage", False):
                 # decoded uint8 images -> two augmented views on the GPU, recipe taken from the YAML's transform lists (f-2)
                 from ..data import DeviceAugmentedTwoViews, SyntheticDecodedImages, build_input_stage
@@ -110,8 +129,11 @@ class Trainer:
                 dataloader = SyntheticTwoViews(self.batch_size, iters, self.device)
         # LR schedule (engine/trainer.py:140-166 of the reference): epoch-denominated YAML keys become iterations through
         # iters_per_epoch = len(dataloader); the SimCLR recipe derives rate, warm-up and horizon from batch size and image count
-        self.epochs = cfg.get("epochs", 1)
+        # engine/trainer.py:228-233 of the reference: epochs set -> total_iters = epochs * iters_per_epoch, else cfg.total_iters;
+        # an IterLoader wraps around the loader, so the loader's length is one epoch
+        self._epochs_cfg = cfg.get("epochs", None)
         self.iters_per_epoch = cfg.get("iters_per_epoch", None) or len(dataloader)
+        self.epochs = self._epochs_cfg or 1
         opt_cfg = dict(cfg.optimizer)
         lr_cfg = dict(cfg.get("lr_scheduler", {}) or {})
         self.lr_scheduler = None
@@ -190,11 +212,19 @@ class Trainer:
             self.lr_scheduler.set_state_dict(ck["lr_scheduler"])
         self.current_iter = int(ck["iter"])
 
+    @property
+    def total_iters(self):
+        """engine/trainer.py:228-233 of the reference: `epochs` set -> epochs * iters_per_epoch (one pass of the loader = one epoch,
+        the IterLoader wraps around), else cfg.total_iters"""
+        ipe = self.cfg.get("iters_per_epoch", None) or len(self.dataloader)
+        return self._epochs_cfg * ipe if self._epochs_cfg else int(self.cfg.get("total_iters", len(self.dataloader)))
+
     def train(self):
         from ..utils.profiler import StepProfiler
         profiler = StepProfiler(self.cfg.get("profiler_options", None))       # -p "batch_range=[a, b]; ..." (tools/train.py:30)
         loader = IterLoader(self.dataloader)
-        total = len(self.dataloader)
+        total = self.total_iters
+        self.iters_per_epoch = self.cfg.get("iters_per_epoch", None) or len(self.dataloader)
         t0, seen = time.time(), 0
         while self.current_iter < total:
             profiler.step()

@@ -61,6 +61,12 @@ class MoCo(nn.Module):
         return sq, sk
 
     @torch.no_grad()
+    def refresh_buffer_mirrors(self):
+        """after the queue buffer was overwritten from outside (initial broadcast, checkpoint load): rebuild its bf16 mirror"""
+        if self._queue_bf16 is not None:
+            self._queue_bf16 = K.cast_bf16(self.queue)
+
+    @torch.no_grad()
     def _momentum_update_key_encoder(self):
         if self._stores is None:
             self.build_param_stores()

@@ -132,6 +132,7 @@ class ResNet(nn.Module):
             raise ValueError("passl_b200 ResNet supports bottleneck depths %s" % sorted(self.LAYER_CFG))
         assert num_classes <= 0, "classification fc is outside the self-supervised hot path"
         self.with_pool = with_pool
+        self._layers = tuple(self.LAYER_CFG[depth])     # block counts per stage (checkpoint name mapping reads it)
         self.stem = Stem(maxpool=stem_maxpool)
         blocks, inplanes = [], 64
         for i, (planes, n) in enumerate(zip([64, 128, 256, 512], self.LAYER_CFG[depth])):

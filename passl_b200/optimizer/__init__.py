@@ -52,12 +52,70 @@ def trainable_ranges(store):
     return runs
 
 
+class GradControl:
+    """ClipGradByGlobalNorm (passl/core/grad_clip.py:30-84) and the scaler's check_finite_and_unscale (passl/core/grad_scaler.py:48-87)
+    as ONE read pass over the flat gradient buffer (passl_b200_grad_norm_finite): the result is a 3-float control word on the
+    device, {multiplier, found_inf, global_norm}, that the fused optimizer kernels consume — no host round trip, no second pass
+    over the gradients.  `no_clip_list` / per-parameter `need_clip=False` of the reference are not built (no headline recipe uses
+    them): every tensor of the store takes part in the norm."""
+
+    def __init__(self, store, clip_norm=None, clip_norm_max=None, always_clip=False, loss_scale=1.0):
+        self.store = store
+        self.clip_norm = float(clip_norm) if clip_norm else 0.0
+        self.clip_norm_max = float(clip_norm_max) if clip_norm_max else 0.0
+        self.always_clip = bool(always_clip)
+        self.loss_scale = float(loss_scale)
+        dev = store.grad.device
+        self.ctrl = torch.zeros(3, dtype=torch.float32, device=dev)
+        self._scratch = torch.zeros(4, dtype=torch.float32, device=dev)
+
+    def compute(self, grad_scale):
+        """grad_scale: the optimizer's own multiplier (1/world, 1/accum_steps); the norm is that of the gradient the update sees."""
+        lib = _lib.load()
+        _lib.check(lib.passl_b200_grad_norm_finite(self.store.grad.data_ptr(), self.store.numel, float(grad_scale) / self.loss_scale,
+                                                   self.clip_norm, self.clip_norm_max, int(self.always_clip), self.ctrl.data_ptr(),
+                                                   self._scratch.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                   "grad_norm_finite")
+        return self.ctrl
+
+    @property
+    def global_norm(self):
+        return self.ctrl[2]
+
+    @property
+    def found_inf(self):
+        return self.ctrl[1]
+
+
 class _FlatOptimizer:
-    def __init__(self, store, lr):
+    def __init__(self, store, lr, grad_clip=None):
         self.store = store
         self.lr = float(lr)
         self.grad_scale = 1.0 / get_world_size()     # the mean of sync_utils.py:41
         self._step = 0
+        self.grad_control = None
+        if grad_clip:
+            self.set_grad_clip(grad_clip)
+
+    def set_grad_clip(self, cfg):
+        """cfg: dict(name='ClipGradByGlobalNorm', clip_norm=..., clip_norm_max=..., always_clip=...) as in the reference YAMLs
+        (Optimizer.grad_clip), a GradControl, or None."""
+        if cfg is None or isinstance(cfg, GradControl):
+            self.grad_control = cfg
+            return
+        cfg = dict(cfg)
+        name = cfg.pop("name", "ClipGradByGlobalNorm")
+        if name != "ClipGradByGlobalNorm":
+            raise NotImplementedError("grad_clip %r is not built (ClipGradByGlobalNorm is)" % name)
+        cfg.pop("no_clip_list", None)
+        self.grad_control = GradControl(self.store, **cfg)
+
+    def _ctrl_ptr(self):
+        """runs the one-pass norm / finite check when a GradControl is attached; returns the device control word (or 0)"""
+        if self.grad_control is None:
+            return 0
+        self.grad_control.compute(1.0)   # the control multiplier is applied on top of grad_scale inside the update kernels
+        return self.grad_control.ctrl.data_ptr()
 
     def clear_grad(self):
         self.store.zero_grad()
@@ -96,10 +154,11 @@ class Momentum(_FlatOptimizer):
     def step(self):
         lib, s = _lib.load(), self.store
         st = torch.cuda.current_stream().cuda_stream
+        ctrl = self._ctrl_ptr()
         for off, n in self._ranges:                  # one launch when nothing is frozen (the usual case)
             _lib.check(lib.passl_b200_sgd_momentum(s.master.data_ptr() + 4 * off, s.grad.data_ptr() + 4 * off,
                                                    self.velocity.data_ptr() + 4 * off, s.bf16.data_ptr() + 2 * off, self.lr,
-                                                   self.momentum, self.weight_decay, self.grad_scale, n, st), "sgd_momentum")
+                                                   self.momentum, self.weight_decay, self.grad_scale, ctrl, n, st), "sgd_momentum")
         self._step += 1
 
     def state_dict(self):
@@ -124,7 +183,7 @@ class LarsMomentumOptimizer(_FlatOptimizer):
         _lib.check(lib.passl_b200_lars_momentum(s.master.data_ptr(), s.grad.data_ptr(), self.velocity.data_ptr(),
                                                 s.bf16.data_ptr(), s.block_seg.data_ptr(), self.seg_wd.data_ptr(),
                                                 self.norms.data_ptr(), len(s.params), self.lr, self.momentum, self.coeff,
-                                                self.eps, self.grad_scale, s.numel,
+                                                self.eps, self.grad_scale, self._ctrl_ptr(), s.numel,
                                                 torch.cuda.current_stream().cuda_stream), "lars_momentum")
         self._step += 1
 
@@ -177,7 +236,7 @@ class AdamW(_FlatOptimizer):
         _lib.check(lib.passl_b200_adamw(s.master.data_ptr(), s.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                                         s.bf16.data_ptr(), s.block_seg.data_ptr(), self.seg_wd.data_ptr(),
                                         self.seg_lr.data_ptr() if self.seg_lr is not None else 0, self.lr, self.beta1,
-                                        self.beta2, self.eps, self._step, self.grad_scale, s.numel,
+                                        self.beta2, self.eps, self._step, self.grad_scale, self._ctrl_ptr(), s.numel,
                                         torch.cuda.current_stream().cuda_stream), "adamw")
 
     def state_dict(self):
@@ -188,4 +247,8 @@ def build_optimizer(cfg, store):
     cfg = dict(cfg)
     name = cfg.pop("name")
     cls = {"Momentum": Momentum, "LarsMomentumOptimizer": LarsMomentumOptimizer, "AdamW": AdamW}[name]
-    return cls(store, **cfg)
+    grad_clip = cfg.pop("grad_clip", None)          # Optimizer.grad_clip of the v2.5 YAMLs (passl/optimizer/__init__.py:64-70)
+    opt = cls(store, **cfg)
+    if grad_clip:
+        opt.set_grad_clip(grad_clip)
+    return opt

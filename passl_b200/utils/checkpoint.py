@@ -50,7 +50,7 @@ def resnet_to_paddle(backbone, prefix=""):
     w = sd["stem.weight"].detach().cpu()[:, :147].reshape(64, 7, 7, 3).permute(0, 3, 1, 2).contiguous()
     out[prefix + "conv1.weight"] = w.numpy()
     _bn(prefix + "bn1", "stem.bn", sd, out)
-    names = _block_names(tuple(backbone.LAYER_CFG[50]) if not hasattr(backbone, "_layers") else backbone._layers)
+    names = _block_names(tuple(getattr(backbone, "_layers", backbone.LAYER_CFG[50])))
     for bi, ref in names.items():
         for k in (1, 2, 3):
             key = "blocks.%d.conv%d" % (bi, k)
@@ -71,7 +71,7 @@ def resnet_from_paddle(backbone, state, prefix=""):
     new["stem.weight"] = w
     for k in ("weight", "bias", "_mean", "_variance"):
         new["stem.bn." + k] = torch.as_tensor(state[prefix + "bn1." + k])
-    for bi, ref in _block_names().items():
+    for bi, ref in _block_names(tuple(getattr(backbone, "_layers", backbone.LAYER_CFG[50]))).items():
         for k in (1, 2, 3):
             key = "blocks.%d.conv%d" % (bi, k)
             new[key + ".weight"] = torch.as_tensor(state["%s%s.conv%d.weight" % (prefix, ref, k)]).permute(0, 2, 3, 1).contiguous()

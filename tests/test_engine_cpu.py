@@ -115,8 +115,10 @@ def test_max_train_step_and_unbuilt_options(engine, monkeypatch):
                                      state_dict=lambda s: {}))()
     monkeypatch.setattr(type(e.model), "forward", lambda self, batch: type("L", (), dict(backward=lambda s: None, detach=lambda s: torch.tensor(0.5)))())
     assert e.train() == 5
+    assert Engine(get_config(CFG, ["Global.accum_steps=2"]), device="cpu").accum_steps == 2      # gradient merge is built
     with pytest.raises(NotImplementedError):
-        Engine(get_config(CFG, ["Global.accum_steps=2"]), device="cpu")
+        Engine(get_config(CFG, ["Optimizer.layer_decay=0.75"]), device="cpu")
+    Engine(get_config(CFG, ["Optimizer.tensor_fusion=False"]), device="cpu")                     # falsy = not requested
     with pytest.raises(NotImplementedError):
         Engine(get_config(CFG, []), mode="eval", device="cpu")
 

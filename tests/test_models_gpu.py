@@ -132,7 +132,7 @@ def test_trainer_surface_moco(tmp_path):
     import os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cfg = get_config(os.path.join(root, "configs/moco/moco_v2_r50.yaml"),
-                     ["model.K=1024", "dataloader.train.sampler.batch_size=16", "total_iters=4", "log_config.interval=2"])
+                     ["model.K=1024", "dataloader.train.sampler.batch_size=16", "total_iters=4", "epochs=1", "log_config.interval=2"])
     from passl_b200.engine import trainer as T
     tr = Trainer(cfg, dataloader=T.SyntheticTwoViews(16, 4, torch.device("cuda"), size=64))
     out = tr.train()
@@ -147,7 +147,7 @@ def test_trainer_checkpoint_resume(tmp_path):
     from passl_b200.utils.config import get_config
     import os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    over = ["model.K=1024", "dataloader.train.sampler.batch_size=16", "total_iters=2", "log_config.interval=100",
+    over = ["model.K=1024", "dataloader.train.sampler.batch_size=16", "total_iters=2", "epochs=1", "log_config.interval=100",
             "output_dir=%s" % tmp_path]
     cfg = get_config(os.path.join(root, "configs/moco/moco_v2_r50.yaml"), over)
     data = T.SyntheticTwoViews(16, 2, torch.device("cuda"), size=64)
@@ -176,7 +176,7 @@ def test_trainer_surface_simclr_recipe():
     import os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cfg = get_config(os.path.join(root, "configs/simclr/simclr_r50_IM.yaml"),
-                     ["dataloader.train.sampler.batch_size=16", "total_iters=3", "epochs=2", "lr_scheduler.total_images=512",
+                     ["dataloader.train.sampler.batch_size=16", "total_iters=3", "epochs=1", "lr_scheduler.total_images=512",
                       "lr_scheduler.warmup_epochs=1", "log_config.interval=100"])
     tr = T.Trainer(cfg, dataloader=T.SyntheticTwoViews(16, 3, torch.device("cuda"), size=64))
     peak = np.sqrt(16 * 8)                                   # end_lr 1.0 * sqrt(per-GPU batch * 8), engine/trainer.py:161-163
@@ -197,7 +197,7 @@ def test_trainer_pdparams_weights_roundtrip(tmp_path):
     from passl_b200.utils.config import get_config
     import os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    over = ["model.K=1024", "dataloader.train.sampler.batch_size=16", "total_iters=2", "log_config.interval=100"]
+    over = ["model.K=1024", "dataloader.train.sampler.batch_size=16", "total_iters=2", "epochs=1", "log_config.interval=100"]
     tr = T.Trainer(get_config(os.path.join(root, "configs/moco/moco_v2_r50.yaml"), over),
                    dataloader=T.SyntheticTwoViews(16, 2, torch.device("cuda"), size=64))
     tr.train()
@@ -245,7 +245,7 @@ def test_trainer_surface_clip():
     cfg = get_config(os.path.join(root, "configs/clip/vit-b-16.yaml"),
                      [a + "vision_layers=2", a + "vision_width=128", a + "image_resolution=64", a + "embed_dim=64",
                       a + "transformer_width=128", a + "transformer_heads=2", a + "transformer_layers=2", a + "context_length=16",
-                      a + "vocab_size=1000", "dataloader.train.sampler.batch_size=16", "total_iters=3", "log_config.interval=100"])
+                      a + "vocab_size=1000", "dataloader.train.sampler.batch_size=16", "total_iters=3", "epochs=1", "log_config.interval=100"])
     tr = Trainer(cfg)
     out = tr.train()
     assert np.isfinite(float(out["loss"].detach())) and np.isfinite(float(out["img_loss"])) and np.isfinite(float(out["text_loss"]))

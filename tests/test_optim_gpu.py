@@ -102,3 +102,93 @@ def test_adamw_matches_oracle():
             mom[n] = (m1, m2)
     _check(m, st, ref, 5e-6)
     assert np.isfinite(st.master.sum().item())
+
+
+def test_grad_norm_finite_clip_and_skip():
+    """One-pass global norm + finite check (grad_clip.py:30-84, grad_scaler.py:48-87): control word on the device, consumed by the
+    fused update kernels — clip coefficient, unscale, and the skipped step on a non-finite gradient."""
+    import torch.nn as nn
+    from passl_b200.core import ParamStore
+    from passl_b200.optimizer import GradControl, Momentum
+    torch.manual_seed(0)
+    net = nn.Sequential(nn.Linear(300, 200), nn.Linear(200, 10)).cuda()
+    store = ParamStore(net)
+    opt = Momentum(store, lr=0.1, momentum=0.0, weight_decay=0.0)
+    store.grad.normal_()
+    store.grad.mul_((store.master != 0).float())          # alignment padding carries no gradient
+    g = store.grad.clone()
+    w0 = store.master.clone()
+    norm = g.norm().item()
+    # 1. clip active: update = lr * g * clip_norm / (norm + 1e-6)
+    opt.set_grad_clip(dict(name="ClipGradByGlobalNorm", clip_norm=1.0))
+    opt.step()
+    torch.cuda.synchronize()
+    assert abs(opt.grad_control.global_norm.item() - norm) < 1e-4 * norm
+    exp = w0 - 0.1 * g * (1.0 / (norm + 1e-6))
+    assert torch.allclose(store.master, exp, rtol=1e-5, atol=1e-7)
+    # 2. clip inactive (norm below the threshold): plain step; clip_norm_max caps the coefficient when always_clip
+    store.master.copy_(w0); store.refresh_bf16()
+    opt.set_grad_clip(dict(clip_norm=10.0 * norm))
+    opt.step()
+    assert torch.allclose(store.master, w0 - 0.1 * g, rtol=1e-5, atol=1e-7)
+    store.master.copy_(w0)
+    opt.set_grad_clip(dict(clip_norm=10.0 * norm, always_clip=True, clip_norm_max=2.0))
+    opt.step()
+    assert torch.allclose(store.master, w0 - 0.1 * g * 2.0, rtol=1e-5, atol=1e-7)
+    # 3. loss-scaled gradients: unscale folded into the multiplier
+    store.master.copy_(w0)
+    opt.grad_control = GradControl(store, loss_scale=1024.0)
+    store.grad.copy_(g * 1024.0)
+    opt.step()
+    assert torch.allclose(store.master, w0 - 0.1 * g, rtol=1e-5, atol=1e-7)
+    # 4. a non-finite gradient: the whole step is skipped on the device, found_inf raised
+    store.master.copy_(w0)
+    store.grad.copy_(g)
+    store.grad[5] = float("inf")
+    opt.step()
+    torch.cuda.synchronize()
+    assert opt.grad_control.found_inf.item() == 1.0
+    assert torch.equal(store.master, w0)
+    store.grad[5] = float("nan")
+    opt.step()
+    assert opt.grad_control.found_inf.item() == 1.0 and torch.equal(store.master, w0)
+    # the scratch word resets itself: a clean gradient afterwards steps normally
+    store.grad.copy_(g * 1024.0)
+    opt.step()
+    assert opt.grad_control.found_inf.item() == 0.0
+    assert torch.allclose(store.master, w0 - 0.1 * g, rtol=1e-5, atol=1e-7)
+
+
+def test_grad_scaler_surface():
+    from passl_b200.core.grad_scaler import GradScaler
+    s = GradScaler(enable=False)
+    x = torch.ones(1, device="cuda", requires_grad=True)
+    assert s.scale(x) is x
+    s2 = GradScaler(enable=True, init_loss_scaling=8.0)
+    y = s2.scale(x.sum())
+    y.backward()
+    assert x.grad.item() == 8.0
+
+
+def test_shadow_ema_matches_the_reference_rule():
+    """passl/models/utils/ema.py:18-97: decay = min(decay, (1 + t) / (10 + t)) when thres_steps; apply_shadow / restore swap."""
+    import torch.nn as nn
+    from passl_b200.core import ParamStore
+    from passl_b200.models.utils_ema import EMA
+    torch.manual_seed(0)
+    net = nn.Sequential(nn.Linear(64, 64), nn.Linear(64, 8)).cuda()
+    store = ParamStore(net)
+    ema = EMA(store, decay=0.999)
+    ema.register()
+    ref = store.master.clone().double()
+    for t in range(4):
+        store.master.add_(0.01 * torch.randn_like(store.master))
+        d = ema.update()
+        assert d == min(0.999, (1 + t) / (10 + t))
+        ref = d * ref + (1 - d) * store.master.double()
+    assert torch.allclose(ema.state_dict()["shadow"].double(), ref, rtol=1e-6, atol=1e-7)
+    live = store.master.clone()
+    ema.apply_shadow()
+    assert torch.allclose(store.master.double(), ref, rtol=1e-6, atol=1e-7) and torch.equal(store.bf16, store.master.bfloat16())
+    ema.restore()
+    assert torch.equal(store.master, live)

@@ -169,15 +169,114 @@ def _grad_report(named_params, pref, path):
     return worst, rows
 
 
+def _skip_negligible(rows_src, named_params, pref):
+    """Biases that feed a BatchNorm have a mathematically ZERO gradient (the BN backward output sums to zero over the batch);
+    what both sides hold there is rounding residue, 4-5 orders of magnitude below the weight gradients.  Such tensors are
+    checked for being negligible on both sides instead of for relative agreement."""
+    scale = max(pref[n].grad.norm().item() for n, _ in named_params if pref[n].grad is not None)
+    keep, neg = [], []
+    for n, prm in named_params:
+        ref = pref[n].grad
+        if ref is None:
+            continue
+        (neg if ref.norm().item() < 1e-3 * scale else keep).append((n, prm))
+    for n, prm in neg:
+        assert prm.grad.double().norm().item() < 2e-3 * scale, (n, prm.grad.norm().item(), scale)
+    return keep
+
+
+@pytest.mark.parametrize("variant", ["ResNet", "ResNetsimclr"])
+def test_resnet50_every_unit_in_the_chain_vs_quantisation_matched_oracle(variant):
+    """Default initialisation (every BatchNorm gamma = 1), B=16 at 128^2 (ResNet) / B=8 at 64^2 (ResNetsimclr, no stem max-pool:
+    resnetcifar.py:275,321-332).  The CUDA network runs its real forward and backward chain; the stem and EVERY bottleneck are
+    then checked in place: the oracle unit (quantisation-matched) receives the very tensors the CUDA unit received — its input
+    activation and the gradient arriving at its output — and must reproduce the CUDA unit's output, input gradient and all of its
+    parameter gradients to the contract (1e-2 / 2e-2).  This covers all 17 units at their true shapes and statistics (layer4 at
+    4x4 included) and does not depend on how an untrained 50-layer BatchNorm network amplifies perturbations.
+    The chained error (CUDA chain vs oracle chain from the same image) is written to gpurun_out for reference."""
+    from oracle import resnet as O
+    from passl_b200.core.streams import join
+    from passl_b200.modeling import build_backbone
+    torch.manual_seed(0)
+    simclr = variant == "ResNetsimclr"
+    net = build_backbone(dict(name=variant, depth=50, with_pool=False)).cuda()
+    B, S = (8, 64) if simclr else (16, 128)
+    img = torch.randn(B, 3, S, S, device="cuda")
+    for p_ in net.parameters():
+        p_.grad = torch.zeros_like(p_)
+    # --- CUDA chain, unit by unit (what ResNet._run_forward / _run_backward do) ---
+    x, cs = net.stem.fwd(img, training=True, save=True)
+    acts, ctxs = [x], []
+    for blk in net.blocks:
+        x, c = blk.fwd(x, training=True, save=True)
+        acts.append(x)
+        ctxs.append(c)
+    d = torch.randn_like(x)
+    douts = [None] * len(net.blocks)
+    for i in reversed(range(len(net.blocks))):
+        douts[i] = d
+        d = net.blocks[i].bwd(ctxs[i], d)
+    d_stem = d
+    net.stem.bwd(cs, d_stem)
+    join()
+    torch.cuda.synchronize()
+    p = O.params_from_cuda_module(net)
+    for v in p.values():
+        v.requires_grad_(True)
+    rows = []
+    # --- stem ---
+    y = O.conv_bn(img.cpu().bfloat16().double(), p, "stem", stride=2, pad=3, q=True)
+    if not simclr:
+        y = O.Q(F.max_pool2d(y, 3, 2, 1))
+    y.backward(_to_oracle_input(d_stem))
+    e_out = rel(acts[0].permute(0, 3, 1, 2), y)
+    gw = net.stem.weight.grad[:, :147].reshape(64, 7, 7, 3).permute(0, 3, 1, 2)
+    e_w = max(rel(gw, p["stem.weight"].grad), rel(net.stem.bn.weight.grad, p["stem.bn.weight"].grad),
+              rel(net.stem.bn.bias.grad, p["stem.bn.bias"].grad))
+    rows.append("stem              out %.5f             wgrad(max) %.5f" % (e_out, e_w))
+    assert e_out < 1e-2 and e_w < 2e-2, rows[-1]
+    # --- every bottleneck, fed with the CUDA unit's own input and output gradient ---
+    worst = [0.0, 0.0, 0.0]
+    for i, blk in enumerate(net.blocks):
+        xin = _to_oracle_input(acts[i]).requires_grad_(True)
+        has_ds = blk.downsample is not None
+        out = O.bottleneck(O.Q(xin), p, "blocks.%d" % i, blk.conv2.stride, has_ds, q=True)
+        out.backward(_to_oracle_input(douts[i]))
+        e_out = rel(acts[i + 1].permute(0, 3, 1, 2), out)
+        dx_cuda = douts[i - 1] if i > 0 else d_stem
+        e_dx = rel(dx_cuda.permute(0, 3, 1, 2), xin.grad)
+        e_w = 0.0
+        for name, prm in blk.named_parameters():
+            ref = p["blocks.%d.%s" % (i, name)].grad
+            got = prm.grad.permute(0, 3, 1, 2) if prm.grad.dim() == 4 else prm.grad
+            e_w = max(e_w, rel(got, ref))
+        rows.append("blocks.%-2d [%4d ch, %3dx%-3d] out %.5f dx %.5f wgrad(max) %.5f" % (i, acts[i + 1].shape[3], acts[i + 1].shape[1],
+                                                                                      acts[i + 1].shape[2], e_out, e_dx, e_w))
+        worst = [max(worst[0], e_out), max(worst[1], e_dx), max(worst[2], e_w)]
+    # --- chained comparison, for the record ---
+    with torch.no_grad():
+        fr = O.resnet_forward(img.cpu().double(), {k: v.detach() for k, v in p.items()}, stem_maxpool=not simclr, q=True)
+    rows.append("chained CUDA forward vs chained oracle forward (same image, default init): rel %.4f" % rel(acts[-1].permute(0, 3, 1, 2), fr))
+    import os
+    os.makedirs("gpurun_out", exist_ok=True)
+    open("gpurun_out/r02_resnet50_%s_unit_parity.txt" % variant, "w").write("\n".join(rows) + "\n")
+    assert worst[0] < 1e-2 and worst[1] < 2e-2 and worst[2] < 2e-2, (worst, rows)
+
+
 @pytest.mark.parametrize("variant", ["ResNet", "ResNetsimclr"])
 def test_resnet50_fwd_bwd_vs_quantisation_matched_oracle(variant):
-    """The whole ResNet-50 (MoCo variant with the stem max-pool, SimCLR variant without it: resnetcifar.py:275,321-332) +
-    NonLinearNeckV1, forward and every parameter gradient, against the quantisation-matched oracle."""
+    """The whole ResNet-50 + NonLinearNeckV1 as ONE chain, forward and every parameter gradient, against the quantisation-matched
+    oracle.  The last BatchNorm of every residual branch starts at gamma = 0.25: with the default gamma = 1 an untrained 50-layer
+    BatchNorm network amplifies ANY perturbation (here: the ~1e-4 of bf16 roundings that flip with the fp32 summation order)
+    by ~1.3x per layer, so end-to-end agreement says nothing about the kernels — the unit-in-chain test above covers that
+    initialisation unit by unit."""
     from oracle import resnet as O
     from passl_b200.modeling import build_backbone, build_neck
     torch.manual_seed(0)
     simclr = variant == "ResNetsimclr"
     net = build_backbone(dict(name=variant, depth=50, with_pool=False)).cuda()
+    for blk in net.blocks:
+        torch.nn.init.constant_(blk.conv3.bn.weight, 0.25)
     neck = build_neck(dict(name="NonLinearNeckV1", in_channels=2048, hid_channels=2048, out_channels=128)).cuda()
     B, S = (8, 64) if simclr else (16, 128)
     img = torch.randn(B, 3, S, S, device="cuda")
@@ -198,10 +297,12 @@ def test_resnet50_fwd_bwd_vs_quantisation_matched_oracle(variant):
     er = O.neck_v1(fr, pn, q=True)
     er.backward(g.cpu().double())
     assert fr.shape[2] == (S // 16 if simclr else S // 32)
-    assert rel(feat.permute(0, 3, 1, 2), fr) < 1e-2, rel(feat.permute(0, 3, 1, 2), fr)
-    assert rel(emb, er) < 1e-2, rel(emb, er)
+    e_feat, e_emb = rel(feat.permute(0, 3, 1, 2), fr), rel(emb, er)
     worst, rows = _grad_report(list(net.named_parameters()), p, "gpurun_out/r02_resnet50_%s_grad_report.txt" % variant)
     worst_n, _ = _grad_report(list(neck.named_parameters()), pn, "gpurun_out/r02_neckv1_%s_grad_report.txt" % variant)
+    open("gpurun_out/r02_resnet50_%s_grad_report.txt" % variant, "a").write("features rel %.5f  embedding rel %.5f\n" % (e_feat, e_emb))
+    assert e_feat < 1e-2, e_feat
+    assert e_emb < 1e-2, e_emb
     assert worst < 2e-2, (worst, [r for r in rows if float(r.split()[2]) > 2e-2][:8])
     assert worst_n < 2e-2, worst_n
 
@@ -246,7 +347,9 @@ def test_necks_fwd_bwd_vs_quantisation_matched_oracle(neck_name):
     assert rel(emb, er) < 1e-2, rel(emb, er)
     dfeat = feat.grad if fc3 else feat.grad.permute(0, 3, 1, 2)
     assert rel(dfeat, fr.grad) < 2e-2, rel(dfeat, fr.grad)
-    worst, rows = _grad_report(list(neck.named_parameters()), pn, "gpurun_out/r02_%s_grad_report.txt" % neck_name)
+    _grad_report(list(neck.named_parameters()), pn, "gpurun_out/r02_%s_grad_report.txt" % neck_name)
+    keep = _skip_negligible(None, list(neck.named_parameters()), pn)
+    worst, rows = _grad_report(keep, pn, "gpurun_out/r02_%s_grad_report_checked.txt" % neck_name)
     assert worst < 2e-2, (worst, rows)
 
 

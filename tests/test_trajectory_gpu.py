@@ -1,0 +1,104 @@
+"""Loss trajectories of full training steps (forward, loss, backward, optimizer, EMA / queue) on the GPU against the CPU oracle's
+training steps in quantisation-matched mode (fp64 with bf16 rounding where the CUDA path rounds; fp32 master weights updated by
+the same rule):  SimCLR  = oracle/simclr_step.py::train_step  (the benchmarked C2 step: ResNet-50 + NonLinearNeckfc3 + NT-Xent/CO2
++ LARS),  MoCo v2 = oracle/moco_step.py::train_step  (C1 / C3: ResNet-50 + NonLinearNeckV1 + InfoNCE over the queue + Momentum,
+EMA key encoder, ring-buffer enqueue).  Contract: loss within 1e-2 relative (bf16) at every step; queue pointer bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _export(encoder, dtype=torch.float64):
+    """fp32 master parameters of Sequential(backbone, neck) under the oracle's names (unrounded: the oracle rounds on the fly)."""
+    from oracle import resnet as O
+    raw = O.params_from_cuda_module(encoder, dtype=dtype, bf16_round=False)
+    out = {}
+    for k, v in raw.items():
+        if k.startswith("0."):
+            out[k[2:]] = v
+        elif k.startswith("1."):
+            out["neck." + k[2:]] = v
+    return out
+
+
+def test_simclr_three_steps_loss_trajectory_vs_oracle():
+    from oracle import simclr_step as S
+    from passl_b200.core import ParamStore
+    from passl_b200.modeling import build_model
+    from passl_b200.optimizer import LarsMomentumOptimizer
+    torch.manual_seed(0)
+    model = build_model(dict(name="SimCLR", backbone=dict(name="ResNet", depth=50, with_pool=True),
+                             neck=dict(name="NonLinearNeckfc3", in_channels=2048, hid_channels=2048, out_channels=128,
+                                       with_avg_pool=False),
+                             head=dict(name="SimCLRContrastiveHead", temperature=0.1))).cuda()
+    for blk in model.backbone.blocks:            # damped residual branches: see tests/test_resnet_gpu.py (chaotic amplification at gamma = 1)
+        torch.nn.init.constant_(blk.conv3.bn.weight, 0.25)
+    store = ParamStore(model.encoder)
+    lr = 0.3
+    opt = LarsMomentumOptimizer(store, lr=lr)
+    p = {k: v.requires_grad_(True) for k, v in _export(model.encoder).items() if "._mean" not in k and "._variance" not in k}
+    vel = {}
+    g = torch.Generator().manual_seed(7)
+    got, ref = [], []
+    for it in range(3):
+        a = torch.randn(16, 3, 64, 64, generator=g)
+        b = a + 0.2 * torch.randn(16, 3, 64, 64, generator=g)
+        opt.clear_grad()
+        out = model(a.cuda(), b.cuda())
+        out["loss"].backward()
+        opt.step()
+        got.append(out["loss"].item())
+        ref.append(S.train_step(p, vel, a.double(), b.double(), lr=lr, T=0.1, q=True))
+    print("simclr trajectory cuda", got, "oracle", ref)
+    for x, y in zip(got, ref):
+        assert abs(x - y) <= 1e-2 * abs(y), (got, ref)
+    # after three updates the fp32 master weights still agree tensor by tensor
+    after = _export(model.encoder)
+    worst = max(((after[k] - p[k].detach()).norm() / (p[k].detach().norm() + 1e-30)).item() for k in p)
+    assert worst < 1e-2, worst
+
+
+def test_moco_three_steps_loss_trajectory_vs_oracle():
+    from oracle import moco_step as M
+    from passl_b200.modeling import build_model
+    from passl_b200.optimizer import Momentum
+    torch.manual_seed(0)
+    Kq, T, B = 1024, 0.2, 16
+    model = build_model(dict(name="MoCo", backbone=dict(name="ResNet", depth=50),
+                             neck=dict(name="NonLinearNeckV1", in_channels=2048, hid_channels=2048, out_channels=128),
+                             head=dict(name="ContrastiveHead", temperature=T), K=Kq, T=T)).cuda()
+    for enc in (model.encoder_q, model.encoder_k):
+        for blk in enc[0].blocks:                # damped residual branches (both encoders start from the same weights)
+            torch.nn.init.constant_(blk.conv3.bn.weight, 0.25)
+    sq, sk = model.build_param_stores()
+    opt = Momentum(sq, lr=0.03, momentum=0.9, weight_decay=1e-4)
+    pq = {k: v.requires_grad_(True) for k, v in _export(model.encoder_q).items() if "._mean" not in k and "._variance" not in k}
+    pk = {k: v.clone() for k, v in _export(model.encoder_k).items()}
+    state = dict(q=pq, k=pk, queue=model.queue.detach().double().cpu().t().contiguous(), ptr=0, velocity={})
+    g = torch.Generator().manual_seed(9)
+    got, ref = [], []
+    for it in range(3):
+        a = torch.randn(B, 3, 64, 64, generator=g)
+        b = a + 0.2 * torch.randn(B, 3, 64, 64, generator=g)
+        opt.clear_grad()
+        out = model(a.cuda(), b.cuda())
+        out["loss"].backward()
+        opt.step()
+        got.append((out["loss"].item(), out["acc1"].item(), out["acc5"].item()))
+        r = M.train_step(state, a.double(), b.double(), lr=0.03, T=T, m=0.999, momentum=0.9, wd=1e-4, q=True)
+        ref.append((r["loss"], r["acc1"], r["acc5"]))
+    print("moco trajectory cuda", got, "oracle", ref)
+    for x, y in zip(got, ref):
+        assert abs(x[0] - y[0]) <= 1e-2 * abs(y[0]), (got, ref)
+    # (top-1 / top-5 of an untrained encoder are ranks among ~1000 near-equal logits: they flip with 1e-3 logit differences and are
+    #  compared on identical logits in tests/test_infonce_tc_gpu.py instead)
+    model.flush_queue()
+    assert int(model.queue_ptr.item()) == state["ptr"] == (3 * B) % Kq                 # bit-exact ring pointer
+    qd = model.queue.detach().double().cpu().t()
+    assert (qd - state["queue"]).abs().max() < 2e-2                                     # enqueued keys (unit vectors) agree
+    assert torch.equal(qd[:, 3 * B:], state["queue"][:, 3 * B:])                       # untouched columns bit-identical
+    after_k = _export(model.encoder_k)
+    worst = max(((after_k[k] - pk[k]).norm() / (pk[k].norm() + 1e-30)).item() for k in pk if pk[k].norm() > 0)
+    assert worst < 1e-2, worst                                                          # EMA key encoder followed the same path

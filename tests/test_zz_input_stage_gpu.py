@@ -123,7 +123,7 @@ def test_trainer_with_the_device_input_stage():
     root = os.path.dirname(HERE)
     cfg = get_config(os.path.join(root, "configs/moco/moco_v2_r50.yaml"),
                      ["model.K=1024", "dataloader.train.sampler.batch_size=16", "dataloader.train.device_input_stage=True",
-                      "dataloader.train.dataset.transforms.0.size=64", "total_iters=3", "log_config.interval=100"])
+                      "dataloader.train.dataset.transforms.0.size=64", "total_iters=3", "epochs=1", "log_config.interval=100"])
     tr = Trainer(cfg)
     assert type(tr.dataloader).__name__ == "DeviceAugmentedTwoViews" and tr.dataloader.stage.size == 64
     v1, v2 = next(iter(tr.dataloader))

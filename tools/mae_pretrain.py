@@ -52,8 +52,6 @@ def main(args):
     from passl_b200.distributed import get_rank, get_world_size, grad_sync, param_sync
     from passl_b200.optimizer import AdamW
     from passl_b200.optimizer.lr import MAEHalfCycleCosine
-    if args.accum_iter != 1:
-        raise NotImplementedError("accum_iter > 1 is not built")
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         dist.init_process_group("nccl")
@@ -77,13 +75,18 @@ def main(args):
                 if get_rank() == 0:
                     print("step(%d) >= max_train_step(%d), training stops early." % (step, args.max_train_step), flush=True)
                 return step
-            opt.set_lr(sched.lr_at(step))                         # lr_sched.adjust_learning_rate(it / len + epoch)
-            opt.clear_grad()
+            # engine_pretrain.py:48-85: the rate moves and the optimizer steps every accum_iter iterations; the loss of each
+            # iteration is divided by accum_iter (folded into the optimizer's gradient multiplier), gradients add up in between
+            if it % args.accum_iter == 0:
+                opt.set_lr(sched.lr_at(step))                     # lr_sched.adjust_learning_rate(it / len + epoch)
             loss, _, _ = model(samples, mask_ratio=args.mask_ratio)
             loss.backward()
-            grad_sync(store)
-            opt.step()
             step += 1
+            if (it + 1) % args.accum_iter == 0:
+                grad_sync(store)
+                opt.grad_scale = 1.0 / (get_world_size() * args.accum_iter)
+                opt.step()
+                opt.clear_grad()
             if (it + 1) % args.print_freq == 0 or it + 1 == args.steps_per_epoch:
                 value = float(loss.detach())
                 if not math.isfinite(value):

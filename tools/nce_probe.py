@@ -66,26 +66,35 @@ def main():
         N, D, Kq, T = 256, 128, 65536, 0.2
         q = torch.nn.functional.normalize(torch.randn(N, D, device=dev), dim=1).bfloat16()
         k = torch.nn.functional.normalize(torch.randn(N, D, device=dev), dim=1)
-        queue = torch.nn.functional.normalize(torch.randn(Kq, D, device=dev), dim=1).bfloat16()
-        for _ in range(3):
-            K.infonce_tc_fwd(q, queue, pos=k, scale=1 / T)
-        dbg = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
-        flush.zero_()
-        torch.cuda.synchronize()
-        lib.passl_b200_infonce_tc_set_debug(dbg.data_ptr())
-        K.infonce_tc_fwd(q, queue, pos=k, scale=1 / T)
-        torch.cuda.synchronize()
-        lib.passl_b200_infonce_tc_set_debug(None)
-        t = dbg.cpu().reshape(148, 16).double()
-        t0 = t[:, 0][t[:, 0] > 0].min()
-        names = ["start", "after setup (alloc, PDL wait, sync)", "-", "Q staged in TMEM", "target fetched", "s_full t0", "t1", "t2", "t3",
-                 "t4", "t5", "t6", "t7", "loop end", "mma: q_ready"]
-        for i, n in enumerate(names):
-            col = t[:, i]
-            col = col[col > 0]
-            if len(col):
-                print("%-36s min %7.2f us  median %7.2f us  max %7.2f us" % (n, (col.min() - t0) / 1e3, (col.median() - t0) / 1e3,
-                                                                            (col.max() - t0) / 1e3))
+        queues = [torch.nn.functional.normalize(torch.randn(Kq, D, device=dev), dim=1).bfloat16() for _ in range(8)]
+        for qq in queues:
+            K.infonce_tc_fwd(q, qq, pos=k, scale=1 / T)
+        names = ["start", "after setup (alloc, PDL wait, sync)", "Q staged in TMEM", "target fetched"]
+        for it in range(5):
+            names += ["t%d: begin wait s_full" % it, "t%d: S ready" % it, "t%d: S in registers" % it, "t%d: tile done" % it]
+        names += ["mma: q_ready"] + ["mma: issue t%d" % i for i in range(7)]
+        for mode in ("warm (8th of 8 back-to-back calls over different queues)", "cold (L2 flushed, single call)"):
+            dbg = torch.zeros(148 * 32, dtype=torch.int64, device=dev)
+            torch.cuda.synchronize()
+            if mode.startswith("cold"):
+                flush.zero_()
+                torch.cuda.synchronize()
+            lib.passl_b200_infonce_tc_set_debug(dbg.data_ptr())
+            for qq in (queues if mode.startswith("warm") else queues[:1]):
+                K.infonce_tc_fwd(q, qq, pos=k, scale=1 / T)
+            torch.cuda.synchronize()
+            lib.passl_b200_infonce_tc_set_debug(None)
+            t = dbg.cpu().reshape(148, 32).double()
+            g0 = t[:, 0][t[:, 0] > 0]
+            print("---- timeline,", mode, "| CTA start spread (globaltimer) %.2f us; rows below: SM cycles since the CTA's own start" %
+                  ((g0.max() - g0.min()) / 1e3))
+            for i, n in enumerate(names):
+                if i == 0:
+                    continue
+                col = t[:, i]
+                col = col[col > 0]
+                if len(col):
+                    print("%-36s min %7.0f  median %7.0f  max %7.0f cycles" % (n, col.min(), col.median(), col.max()))
 
 
 if __name__ == "__main__":
