@@ -56,6 +56,24 @@ class _RoundFwd(torch.autograd.Function):
         return g
 
 
+class _ReluGivenMask(torch.autograd.Function):
+    """relu(x) forward; the backward uses a GIVEN 0/1 mask instead of (x > 0).  A ReLU gradient is discontinuous: where the
+    pre-activation is within rounding noise of zero the two implementations can take different sides, and every such element
+    changes its gradient by 100 % — a forward difference of relative size e flips ~0.4 e of the masks and moves the backward
+    by ~sqrt(0.4 e) (1e-3 forward -> 2 % backward).  Parity tests of a backward pass therefore hand the CUDA path's masks to the
+    oracle; the forward comparison (and the masks themselves, through it) stays independent."""
+
+    @staticmethod
+    def forward(ctx, x, mask):
+        ctx.save_for_backward(mask)
+        return torch.relu(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (mask,) = ctx.saved_tensors
+        return g * mask, None
+
+
 def Q(x, on=True):
     return _RoundBoth.apply(x) if on else x
 
@@ -86,29 +104,32 @@ def bn_train(x, gamma, beta, eps=1e-5, stats=None, use_global_stats=False, runni
     return y
 
 
-def conv_bn(x, p, prefix, stride=1, pad=0, relu=True, residual=None, use_global_stats=False, q=False):
+def conv_bn(x, p, prefix, stride=1, pad=0, relu=True, residual=None, use_global_stats=False, q=False, relu_mask=None):
     """p[prefix+'.weight'] is [Cout, Cin, R, S] (NCHW convention)."""
     y = Q(F.conv2d(x, Qf(p[prefix + ".weight"], q), stride=stride, padding=pad), q)
     running = (p.get(prefix + ".bn._mean"), p.get(prefix + ".bn._variance"))
     y = bn_train(y, p[prefix + ".bn.weight"], p[prefix + ".bn.bias"], use_global_stats=use_global_stats, running=running)
     if residual is not None:
         y = y + residual
-    return Q(F.relu(y) if relu else y, q)
+    if relu:
+        y = F.relu(y) if relu_mask is None else _ReluGivenMask.apply(y, relu_mask.to(y.dtype))
+    return Q(y, q)
 
 
-def bottleneck(x, p, prefix, stride, has_ds, ugs=False, q=False):
-    """resnetimagenet.py:133-148"""
-    out = conv_bn(x, p, prefix + ".conv1", use_global_stats=ugs, q=q)
-    out = conv_bn(out, p, prefix + ".conv2", stride=stride, pad=1, use_global_stats=ugs, q=q)
+def bottleneck(x, p, prefix, stride, has_ds, ugs=False, q=False, masks=(None, None, None)):
+    """resnetimagenet.py:133-148.  masks: optional ReLU masks (NCHW 0/1) of the three units for the backward (_ReluGivenMask)."""
+    out = conv_bn(x, p, prefix + ".conv1", use_global_stats=ugs, q=q, relu_mask=masks[0])
+    out = conv_bn(out, p, prefix + ".conv2", stride=stride, pad=1, use_global_stats=ugs, q=q, relu_mask=masks[1])
     identity = conv_bn(Qb(x, q), p, prefix + ".downsample", stride=stride, relu=False, use_global_stats=ugs, q=q) if has_ds else x
-    return conv_bn(out, p, prefix + ".conv3", relu=True, residual=identity, use_global_stats=ugs, q=q)
+    return conv_bn(out, p, prefix + ".conv3", relu=True, residual=identity, use_global_stats=ugs, q=q, relu_mask=masks[2])
 
 
-def resnet_forward(img, p, layers=(3, 4, 6, 3), stem_maxpool=True, with_pool=False, ugs=False, prefix="", q=False):
-    """img NCHW; returns NCHW feature map (or [B, C] when with_pool).  resnetimagenet.py:232-246."""
+def resnet_forward(img, p, layers=(3, 4, 6, 3), stem_maxpool=True, with_pool=False, ugs=False, prefix="", q=False, masks=None):
+    """img NCHW; returns NCHW feature map (or [B, C] when with_pool).  resnetimagenet.py:232-246.
+    masks: optional dict(stem=mask, blocks=[(m1, m2, m3), ...]) of ReLU masks for the backward (_ReluGivenMask)."""
     if q:
         img = _round_bf16(img)
-    x = conv_bn(img, p, prefix + "stem", stride=2, pad=3, use_global_stats=ugs, q=q)
+    x = conv_bn(img, p, prefix + "stem", stride=2, pad=3, use_global_stats=ugs, q=q, relu_mask=None if masks is None else masks["stem"])
     if stem_maxpool:
         x = Q(F.max_pool2d(x, kernel_size=3, stride=2, padding=1), q)      # forward no-op (max commutes with rounding)
     inplanes, bi = 64, 0
@@ -116,7 +137,8 @@ def resnet_forward(img, p, layers=(3, 4, 6, 3), stem_maxpool=True, with_pool=Fal
         for b in range(n):
             s = (1 if i == 0 else 2) if b == 0 else 1
             has_ds = b == 0 and (s != 1 or inplanes != planes * 4)
-            x = bottleneck(x, p, prefix + "blocks.%d" % bi, s, has_ds, ugs, q=q)
+            x = bottleneck(x, p, prefix + "blocks.%d" % bi, s, has_ds, ugs, q=q,
+                           masks=(None, None, None) if masks is None else masks["blocks"][bi])
             inplanes = planes * 4
             bi += 1
     if with_pool:

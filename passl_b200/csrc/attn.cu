@@ -238,17 +238,19 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t* r)
       : "memory");
 }
 
-__global__ void __launch_bounds__(320, 1) attn_fwd2_kernel(const __grid_constant__ AttnParams p) {
+__global__ void __launch_bounds__(320, 2) attn_fwd2_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int rowB = p.d * 2;                         // bytes per Q/K/V row (128 or 64)
   const uint32_t lt = (p.d == 64) ? 2u : 4u;        // SWIZZLE_128B / SWIZZLE_64B
   const uint32_t sbo = 8u * rowB;                   // 8-row atom stride
   constexpr int QST = 3, KVST = 2;
+  const int kvB = ((p.NKP * rowB) + 1023) & ~1023;  // bytes of one K (or V) stage: NKP rows — short sequences leave room for 2 CTAs / SM
+  const uint32_t slot_cols = (p.NKP <= 64) ? 128u : 256u, o_off = slot_cols / 2;   // TMEM: 2 slots; O sits in the upper half of a slot
   uint8_t* q_s = smem;                              // [QST][128][rowB]
-  uint8_t* k_s = q_s + QST * 128 * rowB;            // [KVST][256][rowB]
-  uint8_t* v_s = k_s + KVST * 256 * rowB;           // [KVST][256][rowB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + KVST * 256 * rowB);
+  uint8_t* k_s = q_s + QST * 128 * rowB;            // [KVST][NKP][rowB]
+  uint8_t* v_s = k_s + KVST * kvB;                  // [KVST][NKP][rowB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + KVST * kvB);
   uint64_t* q_full = bars;             // QST
   uint64_t* q_empty = q_full + QST;    // QST
   uint64_t* kv_full = q_empty + QST;   // KVST
@@ -268,7 +270,7 @@ __global__ void __launch_bounds__(320, 1) attn_fwd2_kernel(const __grid_constant
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&o_full[i], 1); mbar_init(&slot_free[i], 4); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, 512);
+  if (warp == 1) tmem_alloc(tmem_ptr, 2 * slot_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -284,8 +286,8 @@ __global__ void __launch_bounds__(320, 1) attn_fwd2_kernel(const __grid_constant
       mbar_wait(&kv_empty[kvi], kvph ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&kv_full[kvi], (uint32_t)(2 * p.NKP * rowB));
-        tma_load_4d(k_s + kvi * 256 * rowB, &p.kv_map, &kv_full[kvi], 0, p.H + h, 0, b);
-        tma_load_4d(v_s + kvi * 256 * rowB, &p.kv_map, &kv_full[kvi], 0, 2 * p.H + h, 0, b);
+        tma_load_4d(k_s + kvi * kvB, &p.kv_map, &kv_full[kvi], 0, p.H + h, 0, b);
+        tma_load_4d(v_s + kvi * kvB, &p.kv_map, &kv_full[kvi], 0, 2 * p.H + h, 0, b);
       }
       __syncwarp();
       if (++kvi == KVST) { kvi = 0; kvph ^= 1; }
@@ -311,8 +313,8 @@ __global__ void __launch_bounds__(320, 1) attn_fwd2_kernel(const __grid_constant
       mbar_wait(&p_full[pv_slot], pv_ph);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t tm_p = tmem_base + pv_slot * 256, tm_o = tm_p + 128;
-        const uint32_t va = smem_u32(v_s + pv_kv * 256 * rowB);
+        const uint32_t tm_p = tmem_base + pv_slot * slot_cols, tm_o = tm_p + o_off;
+        const uint32_t va = smem_u32(v_s + pv_kv * kvB);
         for (int k = 0; k < p.NKP / 16; ++k)     // A: 16 keys = 8 packed columns of P; B: 16 key rows of V (MN-major, 2 atoms)
           umma_bf16_ts(tm_o, tm_p + k * 8, make_smem_desc(va + k * 16 * rowB, 0, sbo, lt), idesc2, k > 0 ? 1u : 0u);
         umma_commit(&o_full[pv_slot]);
@@ -329,9 +331,9 @@ __global__ void __launch_bounds__(320, 1) attn_fwd2_kernel(const __grid_constant
         mbar_wait(&slot_free[slot], sph ^ 1);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t qa = smem_u32(q_s + qi * 128 * rowB), ka = smem_u32(k_s + kvi * 256 * rowB);
+          const uint32_t qa = smem_u32(q_s + qi * 128 * rowB), ka = smem_u32(k_s + kvi * kvB);
           for (int k = 0; k < p.d / 16; ++k)
-            umma_bf16(tmem_base + slot * 256, make_smem_desc(qa + k * 32, 16, sbo, lt), make_smem_desc(ka + k * 32, 16, sbo, lt), idesc1,
+            umma_bf16(tmem_base + slot * slot_cols, make_smem_desc(qa + k * 32, 16, sbo, lt), make_smem_desc(ka + k * 32, 16, sbo, lt), idesc1,
                       k > 0 ? 1u : 0u);
           umma_commit(&s_full[slot]);
           umma_commit(&q_empty[qi]);
@@ -350,7 +352,7 @@ __global__ void __launch_bounds__(320, 1) attn_fwd2_kernel(const __grid_constant
     const uint32_t q4 = warp & 3;                     // TMEM lane quarter of this warp
     const int r = q4 * 32 + lane;                     // row within the 128-row block
     const float c2 = p.scale * kAttnLog2e;
-    const uint32_t ts = tmem_base + g * 256 + ((q4 * 32u) << 16);
+    const uint32_t ts = tmem_base + g * slot_cols + ((q4 * 32u) << 16);
     int it = 0;
     for (int head = blockIdx.x; head < heads; head += gridDim.x) {
       const int b = head / p.H, h = head - b * p.H;
@@ -363,49 +365,58 @@ __global__ void __launch_bounds__(320, 1) attn_fwd2_kernel(const __grid_constant
         const int jmax = p.causal ? (row + 1 < p.N ? row + 1 : p.N) : p.N;   // valid keys: j < jmax
         mbar_wait(&s_full[g], sph);
         tc_fence_after();
-        float l = 0.f, l_exact = 0.f, m = 0.f;
+        float l0 = 0.f, l1 = 0.f, m = 0.f;
         if (warp_ok) {
-          // pass 1: row maximum (log2 domain)
-          m = -INFINITY;
+          // pass 1: row maximum of the raw scores (3-input max: 16 instructions per 32 columns)
+          float m0 = -INFINITY, m1 = -INFINITY;
           for (int c = 0; c < p.NKP / 32; ++c) {
             uint32_t v[32];
             tmem_ld_32x32(ts + c * 32, v);
             tmem_ld_wait();
             if (c * 32 + 32 <= jmax) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+              for (int j = 0; j < 32; j += 4) {
+                asm("max.f32 %0, %0, %1, %2;" : "+f"(m0) : "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])));
+                asm("max.f32 %0, %0, %1, %2;" : "+f"(m1) : "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3])));
+              }
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (c * 32 + j < jmax) m = fmaxf(m, __uint_as_float(v[j]));
+                if (c * 32 + j < jmax) m0 = fmaxf(m0, __uint_as_float(v[j]));
             }
           }
+          m = fmaxf(m0, m1);
           m = (!row_ok || m == -INFINITY) ? 0.f : m * c2;
-          // pass 2: p = exp2(y - m), row sums, P (bf16x2) over the S columns already consumed
+          const float negm = -m;
+          // pass 2: p = exp2(y - m), row sum, P (bf16x2) over the S columns already consumed.  O is normalised by the fp32 sum of
+          // the unrounded probabilities (the bf16 rounding of P is unbiased: its effect on the sum is ~2^-9 / sqrt(N))
           for (int c = 0; c < p.NKP / 32; ++c) {
             uint32_t v[32], w[16];
             tmem_ld_32x32(ts + c * 32, v);
             tmem_ld_wait();
-            const bool full = c * 32 + 32 <= jmax;
+            if (c * 32 + 32 <= jmax) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              float p0 = exp2f(fmaf(__uint_as_float(v[j]), c2, -m)), p1 = exp2f(fmaf(__uint_as_float(v[j + 1]), c2, -m));
-              if (!full) {
-                if (c * 32 + j >= jmax) p0 = 0.f;
-                if (c * 32 + j + 1 >= jmax) p1 = 0.f;
+              for (int j = 0; j < 32; j += 2) {
+                float p0, p1;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(v[j]), c2, negm)));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(v[j + 1]), c2, negm)));
+                l0 += p0; l1 += p1;
+                w[j >> 1] = pack_bf16x2(p0, p1);
               }
-              // the tensor core multiplies the bf16-rounded probability: normalise O by the sum of the same rounded values,
-              // but report the exact log-sum-exp (the backward recomputes P from it)
-              const uint32_t pk = pack_bf16x2(p0, p1);
-              const float2 e = unpack_bf16x2(pk);
-              l += e.x + e.y;
-              l_exact += p0 + p1;
-              w[j >> 1] = pk;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                float p0 = (c * 32 + j < jmax) ? exp2f(fmaf(__uint_as_float(v[j]), c2, negm)) : 0.f;
+                float p1 = (c * 32 + j + 1 < jmax) ? exp2f(fmaf(__uint_as_float(v[j + 1]), c2, negm)) : 0.f;
+                l0 += p0; l1 += p1;
+                w[j >> 1] = pack_bf16x2(p0, p1);
+              }
             }
             tmem_st_32x16(ts + c * 16, w);
           }
           tmem_st_wait();
         }
+        const float l = l0 + l1, l_exact = l;
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[g]);
@@ -417,7 +428,7 @@ __global__ void __launch_bounds__(320, 1) attn_fwd2_kernel(const __grid_constant
           __nv_bfloat16* op = p.out + (((size_t)b * p.N + row) * p.H + h) * p.d;
           for (int c = 0; c < p.d / 32; ++c) {
             uint32_t v[32];
-            tmem_ld_32x32(ts + 128 + c * 32, v);
+            tmem_ld_32x32(ts + o_off + c * 32, v);
             tmem_ld_wait();
             if (row_ok) {
 #pragma unroll
@@ -444,7 +455,7 @@ __global__ void __launch_bounds__(320, 1) attn_fwd2_kernel(const __grid_constant
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, 2 * slot_cols);
   }
 }
 
@@ -481,12 +492,16 @@ extern "C" int passl_b200_attention_fwd(const void* qkv, void* out, float* lse, 
   static int use_v1 = -1;
   if (use_v1 < 0) use_v1 = getenv("PASSL_B200_ATTN_V1") ? 1 : 0;      // round-1 serial kernel, kept for A/B timing
   if (!use_v1) {
-    const int smem2 = (3 * 128 + 4 * 256) * d * 2 + 256 + 1024;
+    const int kvB = ((p.NKP * d * 2) + 1023) & ~1023;
+    const int smem2 = 3 * 128 * d * 2 + 4 * kvB + 256 + 1024;
     static bool attr2 = false;
     if (!attr2) {
       PB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (3 * 128 + 4 * 256) * 128 + 256 + 1024));
       attr2 = true;
     }
+    // short sequences: two CTAs per SM (shared memory and the 256-column TMEM allocation allow it) -> four items in flight per SM
+    const int per_sm = (p.NKP <= 64 && smem2 <= 100 * 1024) ? 2 : 1;
+    grid = B * H < num_sms() * per_sm ? B * H : num_sms() * per_sm;
     attn_fwd2_kernel<<<grid, 320, smem2, (cudaStream_t)stream>>>(p);
     PB_LAUNCH_CHECK();
     return PB_OK;

@@ -55,6 +55,13 @@ struct InfoNceTcParams {
   float scale, loss_scale;
   int N, K, D;
   int row_groups, slices, tiles;
+  // peer-sharded keys (fused compute + collective): the key matrix is the concatenation of `shards` per-rank buffers of
+  // `shard_rows` keys each, read IN PLACE over NVLink (one tensor map per rank's peer-mapped buffer); 0 = one local matrix
+  int shards, shard_rows;
+  unsigned peer_epoch;      // a shard is readable once my_flags[rank] >= peer_epoch (written by its owner, st.release.sys)
+  const unsigned* my_flags;
+  const __nv_bfloat16* shard_ptr[8];
+  CUtensorMap k_maps[8];
   int tgt_mode;             // 0: owner CTA computes, epoch flags (grid <= SM count); 1: every thread computes its own row
   int poly_ok;              // exponent range allows the FMA-pipe polynomial (2.1 * scale * log2e < 120)
   // persistent state (zeroed once by the caller, left zeroed / epoch-advanced by every launch)
@@ -112,11 +119,32 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// wait (whole warp, uniform) until rank q has published its key shard for this step
+__device__ __forceinline__ void nce_wait_shard(const InfoNceTcParams& p, int q) {
+  unsigned v;
+  const long long t0 = clock64();
+  do {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.my_flags + q) : "memory");
+    if ((int)(v - p.peer_epoch) < 0 && clock64() - t0 > 8000000000LL) {
+      printf("passl_b200: peer key shard %d not published (block %d)\n", q, blockIdx.x);
+      __trap();
+    }
+  } while ((int)(v - p.peer_epoch) < 0);
+  asm volatile("fence.proxy.async.global;" ::: "memory");    // the shard is read by TMA (async proxy) next
+}
+// row `lab` of the (possibly sharded) key matrix
+__device__ __forceinline__ const __nv_bfloat16* nce_key_row(const InfoNceTcParams& p, long long lab) {
+  if (p.shards == 0) return p.Kmat + (size_t)lab * p.D;
+  const int q = (int)(lab / p.shard_rows);
+  return p.shard_ptr[q] + (size_t)(lab - (long long)q * p.shard_rows) * p.D;
+}
+
 // ---- shared-memory carve-up (same for forward and backward) --------------------------------------------------------------
 struct NceSmem {
   uint8_t* q_smem; uint8_t* k_smem;
   uint64_t *q_ready, *k_full, *k_empty, *s_full, *s_empty, *q_full, *p_full, *dq_full, *tgt_done;
   uint32_t* tmem_ptr;
+  float* tgt_s;               // [MB*128] target dot products of this CTA's rows (forward, tgt_mode 0)
   int stages, q_bytes, stage_bytes;
 };
 __device__ __forceinline__ NceSmem nce_carve(uint8_t* smem_raw, int MB, int D) {
@@ -137,8 +165,9 @@ __device__ __forceinline__ NceSmem nce_carve(uint8_t* smem_raw, int MB, int D) {
   s.q_full = s.s_empty + 2;   // 1
   s.p_full = s.q_full + 1;    // 2 (backward)
   s.dq_full = s.p_full + 2;   // 1 (backward)
-  s.tgt_done = s.dq_full + 1; // 1 (forward): every softmax warp holds its rows' target logits
+  s.tgt_done = s.dq_full + 1; // 1 (forward): the producer warp has collected this CTA's target logits in tgt_s
   s.tmem_ptr = reinterpret_cast<uint32_t*>(s.tgt_done + 1);
+  s.tgt_s = reinterpret_cast<float*>(bars + 64);       // 512 B into the barrier block
   return s;
 }
 
@@ -146,8 +175,41 @@ __device__ __forceinline__ NceSmem nce_carve(uint8_t* smem_raw, int MB, int D) {
 // softmax warp holds its target logits — the rest of the key stream.  The bulk stream saturates the SM's L2 port (~60 B/clk): in
 // the first version the 8-byte target polls queued behind 112 KB of key tiles and returned ~8000 cycles late.
 __device__ __forceinline__ void nce_owner_targets(const InfoNceTcParams& p, int ew, int nsw, uint32_t lane, unsigned epoch);
+// ONE warp per CTA polls the tagged target words of the CTA's rows (8x fewer pollers on the same 2 KB than one poll per thread),
+// parks the values in shared memory and releases the softmax warps through an mbarrier
+__device__ __forceinline__ void nce_collect_targets(const InfoNceTcParams& p, const NceSmem& s, int MB, int row_base, uint32_t lane,
+                                                    unsigned epoch) {
+  const long long t0 = clock64();
+  // all polls of a round are in flight together (a sequential loop paid one L2 round trip per 32 rows: 8 x ~700 cycles)
+  constexpr int MAXG = 8;                       // up to 256 rows per CTA
+  const int groups = MB * 4;
+  unsigned long long w[MAXG];
+  unsigned pending = 0;
+#pragma unroll
+  for (int g = 0; g < MAXG; ++g) {
+    w[g] = 0ull;
+    if (g < groups && row_base + g * 32 + (int)lane < p.N) pending |= 1u << g;
+  }
+  while (__any_sync(0xffffffffu, pending != 0u)) {
+#pragma unroll
+    for (int g = 0; g < MAXG; ++g)
+      if (pending & (1u << g)) w[g] = ld_relaxed_u64(p.tgt_tag + row_base + g * 32 + lane);
+#pragma unroll
+    for (int g = 0; g < MAXG; ++g)
+      if ((pending & (1u << g)) && (unsigned)(w[g] >> 32) == epoch + 1u) pending &= ~(1u << g);
+    if (pending && clock64() - t0 > 4000000000LL) {
+      printf("passl_b200: InfoNCE target flag timeout (block %d lane %d pending %x)\n", blockIdx.x, lane, pending);
+      __trap();
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < MAXG; ++g)
+    if (g < groups) s.tgt_s[g * 32 + lane] = __uint_as_float((unsigned)w[g]);
+  __syncwarp();
+  if (lane == 0) mbar_arrive(s.tgt_done);
+}
 __device__ __forceinline__ void nce_producer(const InfoNceTcParams& p, const NceSmem& s, int MB, int row_base, int t_begin, int t_end,
-                                             bool fwd, unsigned epoch) {
+                                             bool fwd, unsigned epoch, long long c0 = 0) {
   const int DC = p.D / 64;
   const uint32_t lane = lane_id();
   // the key matrix is streamed once (evict-first: it must not push the re-used operands out of L2); the query block is read
@@ -161,20 +223,30 @@ __device__ __forceinline__ void nce_producer(const InfoNceTcParams& p, const Nce
   }
   __syncwarp();
   if (fwd) nce_owner_targets(p, 0, 1, lane, epoch);
-  if (fwd && p.dbg && lane == 0) p.dbg[blockIdx.x * 32 + 30] = (unsigned long long)clock64();
+  if (fwd && p.dbg && lane == 0) p.dbg[blockIdx.x * 32 + 30] = (unsigned long long)(clock64() - c0);
   int stage = 0;
   uint32_t phase = 0;
+  int ready_shard = -1;
   for (int t = t_begin; t < t_end; ++t) {
-    if (fwd && t == t_begin + 2) mbar_wait(s.tgt_done, 0);
+    if (fwd && p.tgt_mode == 0 && t == t_begin + 2) nce_collect_targets(p, s, MB, row_base, lane, epoch);
+    const CUtensorMap* kmap = &p.k_map;
+    int krow = t * NCE_BK;
+    if (p.shards) {          // tile t lives in rank q's buffer: wait for its flag once, then load straight over NVLink
+      const int q = krow / p.shard_rows;
+      if (q != ready_shard) { nce_wait_shard(p, q); ready_shard = q; }
+      kmap = &p.k_maps[q];
+      krow -= q * p.shard_rows;
+    }
     mbar_wait(&s.k_empty[stage], phase ^ 1);
     if (elect_one()) {
       mbar_arrive_expect_tx(&s.k_full[stage], (uint32_t)s.stage_bytes);
       for (int c = 0; c < DC; ++c)
-        tma_load_2d_hint(s.k_smem + stage * s.stage_bytes + c * (NCE_BK * 128), &p.k_map, &s.k_full[stage], c * 64, t * NCE_BK, pol_stream);
+        tma_load_2d_hint(s.k_smem + stage * s.stage_bytes + c * (NCE_BK * 128), kmap, &s.k_full[stage], c * 64, krow, pol_stream);
     }
     __syncwarp();
     if (++stage == s.stages) { stage = 0; phase ^= 1; }
   }
+  if (fwd && p.tgt_mode == 0 && t_end - t_begin <= 2) nce_collect_targets(p, s, MB, row_base, lane, epoch);
 }
 
 // softmax-warp prologue, part 1 (before anything can block): target logits of the rows this CTA owns (tgt_mode 0)
@@ -186,6 +258,7 @@ __device__ __forceinline__ void nce_owner_targets(const InfoNceTcParams& p, int 
     if (!p.P) {
       lab = p.label[row];
       lab = lab < 0 ? 0 : (lab >= p.K ? p.K - 1 : lab);
+      if (p.shards) nce_wait_shard(p, (int)(lab / p.shard_rows));
     }
     const uint64_t pol_keep = l2_policy_evict_last();
     for (int d4 = lane * 4; d4 < p.D; d4 += 128) {
@@ -195,7 +268,7 @@ __device__ __forceinline__ void nce_owner_targets(const InfoNceTcParams& p, int 
         const float4 pa = ldg_f4_hint(p.P + (size_t)row * p.D + d4, pol_keep);
         acc += q0.x * pa.x + q0.y * pa.y + q1.x * pa.z + q1.y * pa.w;
       } else {
-        const uint2 ku = *reinterpret_cast<const uint2*>(p.Kmat + (size_t)lab * p.D + d4);
+        const uint2 ku = __ldcv(reinterpret_cast<const uint2*>(nce_key_row(p, lab) + d4));
         const float2 k0 = unpack_bf16x2(ku.x), k1 = unpack_bf16x2(ku.y);
         acc += q0.x * k0.x + q0.y * k0.y + q1.x * k1.x + q1.y * k1.y;
       }
@@ -229,28 +302,16 @@ __device__ __forceinline__ void nce_stage_q(const InfoNceTcParams& p, const NceS
   if (lane == 0) mbar_arrive(s.q_ready);
 }
 
-// part 3: the row's raw target dot product
+// part 3 (tgt_mode 1, grids larger than the SM count): every thread computes the raw target dot product of its own row
 __device__ __forceinline__ float nce_fetch_target(const InfoNceTcParams& p, int row, bool row_ok, unsigned epoch) {
   if (!row_ok) return 0.f;
-  if (p.tgt_mode == 0) {
-    unsigned long long w = ld_relaxed_u64(p.tgt_tag + row);
-    if ((unsigned)(w >> 32) != epoch + 1u) {
-      const long long t0 = clock64();
-      do {
-        w = ld_relaxed_u64(p.tgt_tag + row);
-        if (clock64() - t0 > 4000000000LL) {
-          printf("passl_b200: InfoNCE target flag timeout (block %d row %d)\n", blockIdx.x, row);
-          __trap();
-        }
-      } while ((unsigned)(w >> 32) != epoch + 1u);
-    }
-    return __uint_as_float((unsigned)w);
-  }
+  (void)epoch;
   float acc = 0.f;
   long long lab = 0;
   if (!p.P) {
     lab = p.label[row];
     lab = lab < 0 ? 0 : (lab >= p.K ? p.K - 1 : lab);
+    if (p.shards) nce_wait_shard(p, (int)(lab / p.shard_rows));
   }
   for (int d = 0; d < p.D; d += 2) {
     const float2 q2 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.Q + (size_t)row * p.D + d));
@@ -258,7 +319,7 @@ __device__ __forceinline__ float nce_fetch_target(const InfoNceTcParams& p, int 
       acc = fmaf(q2.x, p.P[(size_t)row * p.D + d], acc);
       acc = fmaf(q2.y, p.P[(size_t)row * p.D + d + 1], acc);
     } else {
-      const float2 k2 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.Kmat + (size_t)lab * p.D + d));
+      const float2 k2 = unpack_bf16x2(__ldcv(reinterpret_cast<const uint32_t*>(nce_key_row(p, lab) + d)));
       acc = fmaf(q2.x, k2.x, acc);
       acc = fmaf(q2.y, k2.y, acc);
     }
@@ -282,7 +343,7 @@ __device__ __forceinline__ void nce_setup(const InfoNceTcParams& p, const NceSme
       mbar_init(&s.p_full[i], 4);
     }
     mbar_init(s.dq_full, 1);
-    mbar_init(s.tgt_done, 4 * MB);
+    mbar_init(s.tgt_done, 1);
     fence_barrier_init();
   }
   (void)bwd;
@@ -325,7 +386,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
 
   // role loops are warp-uniform; only the TMA / tcgen05 issue is elect-predicated (keeps descriptors in uniform registers)
   if (warp == 0) {
-    nce_producer(p, s, MB, row_base, t_begin, t_end, true, epoch);
+    nce_producer(p, s, MB, row_base, t_begin, t_end, true, epoch, nce_c0);
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
     constexpr uint32_t idesc = make_idesc_bf16(128, NCE_BK, false, false);
@@ -342,7 +403,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
       mbar_wait(&s.s_empty[buf], bphase ^ 1);
       mbar_wait(&s.k_full[stage], phase);
       tc_fence_after();
-      if (lane == 0 && it < 7) NCE_STAMPC(25 + it);
+      if (lane == 0 && it < 4) NCE_STAMPC(25 + it);
       const uint64_t dbs = db0 + (uint64_t)((stage * s.stage_bytes) >> 4);
       if (elect_one()) {
         for (int b = 0; b < MB; ++b) {
@@ -378,12 +439,16 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
       if (!p.P) lab = p.label[row];
       if (p.excl) ex = p.excl[row];
     }
-    const float tgt_raw = nce_fetch_target(p, row, row_ok, epoch);
+    float tgt_raw;
+    if (p.tgt_mode == 0) {
+      mbar_wait(s.tgt_done, 0);
+      tgt_raw = row_ok ? s.tgt_s[b * 128 + q4 * 32 + lane] : 0.f;
+    } else {
+      tgt_raw = nce_fetch_target(p, row, row_ok, epoch);
+      if (slice == 0 && row_ok)       // the finalizing CTA reads the targets from the state buffer
+        st_relaxed_u64(p.tgt_tag + row, ((unsigned long long)(epoch + 1u) << 32) | (unsigned long long)__float_as_uint(tgt_raw));
+    }
     const float tgt2 = tgt_raw * c2;
-    if (p.tgt_mode != 0 && slice == 0 && row_ok)       // the finalizing CTA reads the targets from the state buffer
-      st_relaxed_u64(p.tgt_tag + row, ((unsigned long long)(epoch + 1u) << 32) | (unsigned long long)__float_as_uint(tgt_raw));
-    __syncwarp();
-    if (lane == 0) mbar_arrive(s.tgt_done);
     if (threadIdx.x == 64) NCE_STAMPC(3);
 
     float m = -INFINITY, l = 0.f;     // m: integer-valued running max (log2 domain)
@@ -488,7 +553,9 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
       }
       if (cnt > 0) atomicAdd(p.acc_cnt + row, (unsigned)(cnt < 5 ? cnt : 5));
     }
+    if (threadIdx.x == 64) NCE_STAMPC(22);
     __threadfence();
+    if (threadIdx.x == 64) NCE_STAMPC(23);
   }
 
   tc_fence_before();
@@ -501,6 +568,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
   if (threadIdx.x == 0) {
     const unsigned old = atomicInc(p.ticket, gridDim.x - 1);   // wraps back to 0 by itself
     s_is_last = (old == gridDim.x - 1);
+    NCE_STAMPC(31);
   }
   __syncthreads();
   if (!s_is_last) return;
@@ -534,6 +602,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_fwd_kernel(const 
     p.out[1] = 100.f * bb / p.N;
     p.out[2] = 100.f * c / p.N;
     *p.epoch = epoch + 1u;
+    NCE_STAMPC(29);
   }
 }
 
@@ -698,6 +767,8 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_bwd_kernel(const 
     float extra = 0.f;
     if (slice == 0 && row_ok) extra = p.P ? coef * (__expf(p.tgt_in[row] - p.lse_in[row]) - 1.f) : -coef;
     const long long lab_c = lab < 0 ? 0 : (lab >= p.K ? p.K - 1 : lab);
+    if (slice == 0 && p.shards && !p.P)
+      for (int q = 0; q < p.shards; ++q) nce_wait_shard(p, q);      // the labelled rows may live in any rank's shard
     float* stg = reinterpret_cast<float*>(s.k_smem) + ew * (32 * 33);     // per-warp 32 x 32 transpose tile (ring is drained)
     const int r_sub = lane >> 3, c_sub = (lane & 7) * 4;
     for (int ch = 0; ch < p.D / 32; ++ch) {
@@ -722,7 +793,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) infonce_tc_bwd_kernel(const 
               const float4 pk = *reinterpret_cast<const float4*>(p.P + (size_t)grow * p.D + col);
               a0 = fmaf(ex_r, pk.x, a0); a1 = fmaf(ex_r, pk.y, a1); a2 = fmaf(ex_r, pk.z, a2); a3 = fmaf(ex_r, pk.w, a3);
             } else {
-              const uint2 ku = *reinterpret_cast<const uint2*>(p.Kmat + (size_t)lab_r * p.D + col);
+              const uint2 ku = __ldcv(reinterpret_cast<const uint2*>(nce_key_row(p, lab_r) + col));
               const float2 k0 = unpack_bf16x2(ku.x), k1 = unpack_bf16x2(ku.y);
               a0 = fmaf(ex_r, k0.x, a0); a1 = fmaf(ex_r, k0.y, a1); a2 = fmaf(ex_r, k1.x, a2); a3 = fmaf(ex_r, k1.y, a3);
             }
@@ -752,7 +823,7 @@ static void nce_plan(int N, int K, int D, int& MB, int& groups, int& slices, int
   int q_bytes = MB * 128 * D * 2, stage_bytes = NCE_BK * D * 2;
   int stages = (200 * 1024 - q_bytes) / stage_bytes;
   if (stages > 8) stages = 8;
-  smem = q_bytes + stages * stage_bytes + 512 + 1024;
+  smem = q_bytes + stages * stage_bytes + 512 + 1024 + 1024;   // rings + barrier block + target staging + alignment slack
 }
 
 // exponent mix: index into {MUFU only, 1/4, 1/3, 3/8 of the exponentials on the FMA pipe}; PASSL_B200_NCE_POLY overrides
@@ -781,8 +852,13 @@ static int nce_launch(KernelT kern, const InfoNceTcParams& p, int grid, int thre
   return PB_OK;
 }
 
+struct NcePeer {            // peer-sharded key matrix (NULL pointers = single local matrix)
+  const void* const* shard_ptrs; const unsigned* my_flags; int world, shard_rows; unsigned epoch;
+};
+
 static int nce_fill_params(InfoNceTcParams& p, const void* Q, const void* Kmat, const float* P, const long long* label,
-                           const int* excl, float scale, float loss_scale, int N, int K, int D, int& MB, int& smem) {
+                           const int* excl, float scale, float loss_scale, int N, int K, int D, int& MB, int& smem,
+                           const NcePeer* peer = nullptr) {
   memset(&p, 0, sizeof(p));
   nce_plan(N, K, D, MB, p.row_groups, p.slices, p.tiles, smem);
   p.Q = reinterpret_cast<const __nv_bfloat16*>(Q);
@@ -794,8 +870,22 @@ static int nce_fill_params(InfoNceTcParams& p, const void* Q, const void* Kmat, 
   uint32_t qbx[2] = {64, 128};
   int rc = make_tmap_bf16(&p.q_map, Q, 2, qd, qs, qbx);
   if (rc) return rc;
-  uint64_t kd[2] = {(uint64_t)D, (uint64_t)K};
   uint32_t kbx[2] = {64, NCE_BK};
+  if (peer) {
+    if (peer->world < 1 || peer->world > 8 || peer->shard_rows % NCE_BK || (long long)peer->world * peer->shard_rows != K)
+      return PB_ERR_BAD_ARG;
+    p.shards = peer->world; p.shard_rows = peer->shard_rows; p.peer_epoch = peer->epoch; p.my_flags = peer->my_flags;
+    uint64_t sd[2] = {(uint64_t)D, (uint64_t)peer->shard_rows};
+    for (int q = 0; q < peer->world; ++q) {
+      if (!peer->shard_ptrs[q] || (reinterpret_cast<uintptr_t>(peer->shard_ptrs[q]) & 15)) return PB_ERR_BAD_ARG;
+      p.shard_ptr[q] = reinterpret_cast<const __nv_bfloat16*>(peer->shard_ptrs[q]);
+      rc = make_tmap_bf16(&p.k_maps[q], peer->shard_ptrs[q], 2, sd, qs, kbx);
+      if (rc) return rc;
+    }
+    p.k_map = p.k_maps[0];
+    return PB_OK;
+  }
+  uint64_t kd[2] = {(uint64_t)D, (uint64_t)K};
   return make_tmap_bf16(&p.k_map, Kmat, 2, kd, qs, kbx);
 }
 
@@ -817,10 +907,9 @@ extern "C" long long passl_b200_infonce_tc_workspace_bytes(int N, int K, int D) 
 // (MoCo), label int64 [N] (when P == NULL), excl int32 [N] optional.  Outputs as passl_b200_simce_fwd_f32.
 // `workspace` is PERSISTENT STATE: zero-filled by the caller before its first use (and after a failed launch), one buffer
 // per (N, stream); every launch leaves it ready for the next one.
-extern "C" int passl_b200_infonce_tc_fwd(const void* Q, const void* Kmat, const float* P, const long long* label,
-                                         const int* excl, float scale, float loss_scale, int N, int K, int D, float* lse,
-                                         float* tgt, float* loss_rows, float* out_scalars, void* workspace,
-                                         long long workspace_bytes, void* stream) {
+static int nce_fwd_impl(const void* Q, const void* Kmat, const float* P, const long long* label, const int* excl, float scale,
+                        float loss_scale, int N, int K, int D, float* lse, float* tgt, float* loss_rows, float* out_scalars,
+                        void* workspace, long long workspace_bytes, void* stream, const NcePeer* peer) {
   if (N <= 0 || K <= 0 || D < 64 || D % 64 || D > 512 || !(scale > 0.f)) return PB_ERR_BAD_ARG;
   if (!P && !label) return PB_ERR_BAD_ARG;
   if ((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(Kmat) | reinterpret_cast<uintptr_t>(P)) & 15) return PB_ERR_BAD_ARG;
@@ -828,7 +917,7 @@ extern "C" int passl_b200_infonce_tc_fwd(const void* Q, const void* Kmat, const 
   cudaStream_t st = (cudaStream_t)stream;
   InfoNceTcParams p;
   int MB, smem;
-  int rc = nce_fill_params(p, Q, Kmat, P, label, excl, scale, loss_scale, N, K, D, MB, smem);
+  int rc = nce_fill_params(p, Q, Kmat, P, label, excl, scale, loss_scale, N, K, D, MB, smem, peer);
   if (rc) return rc;
   unsigned* w = reinterpret_cast<unsigned*>(workspace);
   p.epoch = w; p.ticket = w + 1;
@@ -849,11 +938,35 @@ extern "C" int passl_b200_infonce_tc_fwd(const void* Q, const void* Kmat, const 
   return rc;
 }
 
+extern "C" int passl_b200_infonce_tc_fwd(const void* Q, const void* Kmat, const float* P, const long long* label,
+                                         const int* excl, float scale, float loss_scale, int N, int K, int D, float* lse,
+                                         float* tgt, float* loss_rows, float* out_scalars, void* workspace,
+                                         long long workspace_bytes, void* stream) {
+  return nce_fwd_impl(Q, Kmat, P, label, excl, scale, loss_scale, N, K, D, lse, tgt, loss_rows, out_scalars, workspace,
+                      workspace_bytes, stream, nullptr);
+}
+
+// Fused compute + collective: the gathered-key InfoNCE of MoCo v3 / CLIP (mocov3.py:187-198: k_all = all_gather(k), labels
+// arange(N) + N*rank) WITHOUT the all-gather — the key matrix is the world's `world` bf16 shards [shard_rows, D], each read in
+// place from its owner's peer-mapped buffer by TMA (NVLink loads overlap the MMAs / softmax of the tiles already on chip).
+// shard_ptrs: HOST array of `world` device pointers (this process's mappings, own rank included); my_flags: this rank's flag row
+// (uint32[world]); a shard is consumed once my_flags[q] >= epoch (passl_b200_peer_publish_keys_bf16).  label mode only.
+extern "C" int passl_b200_infonce_tc_fwd_peer(const void* Q, const void* const* shard_ptrs, const void* my_flags, int world,
+                                              int shard_rows, unsigned epoch, const long long* label, const int* excl,
+                                              float scale, float loss_scale, int N, int D, float* lse, float* tgt,
+                                              float* loss_rows, float* out_scalars, void* workspace, long long workspace_bytes,
+                                              void* stream) {
+  if (!shard_ptrs || !my_flags || !label) return PB_ERR_BAD_ARG;
+  NcePeer peer{shard_ptrs, reinterpret_cast<const unsigned*>(my_flags), world, shard_rows, epoch};
+  return nce_fwd_impl(Q, shard_ptrs[0], nullptr, label, excl, scale, loss_scale, N, world * shard_rows, D, lse, tgt, loss_rows,
+                      out_scalars, workspace, workspace_bytes, stream, &peer);
+}
+
 // Backward w.r.t. the queries.  lse / tgt: saved by the forward; dloss: device scalar (upstream grad) or NULL (= 1);
 // dQ fp32 [N, D] is overwritten (zero-filled here, then accumulated over the key slices with vector reds).  D <= 256.
-extern "C" int passl_b200_infonce_tc_bwd(const void* Q, const void* Kmat, const float* P, const long long* label,
-                                         const int* excl, float scale, float loss_scale, int N, int K, int D,
-                                         const float* lse, const float* tgt, const float* dloss, float* dQ, void* stream) {
+static int nce_bwd_impl(const void* Q, const void* Kmat, const float* P, const long long* label, const int* excl, float scale,
+                        float loss_scale, int N, int K, int D, const float* lse, const float* tgt, const float* dloss, float* dQ,
+                        void* stream, const NcePeer* peer) {
   if (N <= 0 || K <= 0 || D < 64 || D % 64 || D > 256 || !(scale > 0.f)) return PB_ERR_BAD_ARG;
   if (!P && !label) return PB_ERR_BAD_ARG;
   if ((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(Kmat) | reinterpret_cast<uintptr_t>(P) |
@@ -861,7 +974,7 @@ extern "C" int passl_b200_infonce_tc_bwd(const void* Q, const void* Kmat, const 
   cudaStream_t st = (cudaStream_t)stream;
   InfoNceTcParams p;
   int MB, smem;
-  int rc = nce_fill_params(p, Q, Kmat, P, label, excl, scale, loss_scale, N, K, D, MB, smem);
+  int rc = nce_fill_params(p, Q, Kmat, P, label, excl, scale, loss_scale, N, K, D, MB, smem, peer);
   if (rc) return rc;
   p.lse_in = lse; p.tgt_in = tgt; p.dloss = dloss; p.dq = dQ;
   PB_CUDA_CHECK(cudaMemsetAsync(dQ, 0, (size_t)N * D * 4, st));
@@ -872,4 +985,20 @@ extern "C" int passl_b200_infonce_tc_bwd(const void* Q, const void* Kmat, const 
   else rc = pv == 0 ? nce_launch(infonce_tc_bwd_kernel<1, 0, 1>, p, grid, threads, smem, st)
                     : nce_launch(infonce_tc_bwd_kernel<1, 1, 4>, p, grid, threads, smem, st);
   return rc;
+}
+
+extern "C" int passl_b200_infonce_tc_bwd(const void* Q, const void* Kmat, const float* P, const long long* label,
+                                         const int* excl, float scale, float loss_scale, int N, int K, int D,
+                                         const float* lse, const float* tgt, const float* dloss, float* dQ, void* stream) {
+  return nce_bwd_impl(Q, Kmat, P, label, excl, scale, loss_scale, N, K, D, lse, tgt, dloss, dQ, stream, nullptr);
+}
+
+extern "C" int passl_b200_infonce_tc_bwd_peer(const void* Q, const void* const* shard_ptrs, const void* my_flags, int world,
+                                              int shard_rows, unsigned epoch, const long long* label, const int* excl,
+                                              float scale, float loss_scale, int N, int D, const float* lse, const float* tgt,
+                                              const float* dloss, float* dQ, void* stream) {
+  if (!shard_ptrs || !my_flags || !label) return PB_ERR_BAD_ARG;
+  NcePeer peer{shard_ptrs, reinterpret_cast<const unsigned*>(my_flags), world, shard_rows, epoch};
+  return nce_bwd_impl(Q, shard_ptrs[0], nullptr, label, excl, scale, loss_scale, N, world * shard_rows, D, lse, tgt, dloss, dQ,
+                      stream, &peer);
 }

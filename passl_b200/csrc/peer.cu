@@ -71,6 +71,27 @@ __global__ void peer_reduce_scatter_kernel(PeerPtrs pp, float4* __restrict__ out
   }
 }
 
+// this rank's keys fp32 [n*D] -> bf16 in its own slot buffer; then (system-scope fence) flag[rank] = epoch in every rank's row
+__global__ void peer_publish_keys_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n4, PeerPtrs pp,
+                                         int rank, int world, unsigned epoch, unsigned* __restrict__ done) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    uint2 u;
+    u.x = pack_bf16x2(v.x, v.y);
+    u.y = pack_bf16x2(v.z, v.w);
+    reinterpret_cast<uint2*>(dst)[i] = u;
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = (atomicInc(done, gridDim.x - 1) == gridDim.x - 1);      // wraps to 0: reusable
+  __syncthreads();
+  if (last && threadIdx.x < (unsigned)world) {
+    __threadfence_system();
+    st_release_sys(pp.flags[threadIdx.x] + rank, epoch);
+  }
+}
+
 }  // namespace pb
 
 using namespace pb;
@@ -114,6 +135,23 @@ extern "C" int passl_b200_peer_reduce_scatter_f32(const float* grad_all, const v
   long long blocks = (n4 + 255) / 256;
   if (blocks > num_sms()) blocks = num_sms();
   peer_reduce_scatter_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(pp, reinterpret_cast<float4*>(out), n4, rank, world, epoch);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+// Publish this rank's key shard for the peer-sharded InfoNCE (passl_b200_infonce_tc_fwd_peer): cast keys fp32 [n, D] to bf16 into
+// this rank's own data buffer (data_ptrs[rank]) and raise flag[rank] = epoch in every rank's flag row.  `done`: uint32 zeroed once.
+extern "C" int passl_b200_peer_publish_keys_bf16(const float* keys, int n, int D, const void* const* data_ptrs, void* const* flag_ptrs,
+                                                 int rank, int world, unsigned epoch, void* done, void* stream) {
+  if (!keys || n <= 0 || D <= 0 || ((long long)n * D) % 4 || rank < 0 || rank >= world || !done) return PB_ERR_BAD_ARG;
+  PeerPtrs pp;
+  int rc = fill_ptrs(pp, data_ptrs, flag_ptrs, world);
+  if (rc) return rc;
+  const long long n4 = (long long)n * D / 4;
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > 64) blocks = 64;
+  peer_publish_keys_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(keys, reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(pp.data[rank])),
+                                                                          n4, pp, rank, world, epoch, reinterpret_cast<unsigned*>(done));
   PB_LAUNCH_CHECK();
   return PB_OK;
 }

@@ -114,8 +114,13 @@ class _FlatOptimizer:
         """runs the one-pass norm / finite check when a GradControl is attached; returns the device control word (or 0)"""
         if self.grad_control is None:
             return 0
-        self.grad_control.compute(1.0)   # the control multiplier is applied on top of grad_scale inside the update kernels
+        # the norm is that of the gradient the update sees (mean over ranks / accumulation steps, unscaled): the control
+        # multiplier carries grad_scale itself, so the kernels are then launched with a unit host-side scale (_gscale)
+        self.grad_control.compute(self.grad_scale)
         return self.grad_control.ctrl.data_ptr()
+
+    def _gscale(self, ctrl):
+        return 1.0 if ctrl else self.grad_scale
 
     def clear_grad(self):
         self.store.zero_grad()
@@ -158,7 +163,7 @@ class Momentum(_FlatOptimizer):
         for off, n in self._ranges:                  # one launch when nothing is frozen (the usual case)
             _lib.check(lib.passl_b200_sgd_momentum(s.master.data_ptr() + 4 * off, s.grad.data_ptr() + 4 * off,
                                                    self.velocity.data_ptr() + 4 * off, s.bf16.data_ptr() + 2 * off, self.lr,
-                                                   self.momentum, self.weight_decay, self.grad_scale, ctrl, n, st), "sgd_momentum")
+                                                   self.momentum, self.weight_decay, self._gscale(ctrl), ctrl, n, st), "sgd_momentum")
         self._step += 1
 
     def state_dict(self):
@@ -180,10 +185,11 @@ class LarsMomentumOptimizer(_FlatOptimizer):
 
     def step(self):
         lib, s = _lib.load(), self.store
+        ctrl = self._ctrl_ptr()
         _lib.check(lib.passl_b200_lars_momentum(s.master.data_ptr(), s.grad.data_ptr(), self.velocity.data_ptr(),
                                                 s.bf16.data_ptr(), s.block_seg.data_ptr(), self.seg_wd.data_ptr(),
                                                 self.norms.data_ptr(), len(s.params), self.lr, self.momentum, self.coeff,
-                                                self.eps, self.grad_scale, self._ctrl_ptr(), s.numel,
+                                                self.eps, self._gscale(ctrl), ctrl, s.numel,
                                                 torch.cuda.current_stream().cuda_stream), "lars_momentum")
         self._step += 1
 
@@ -233,10 +239,11 @@ class AdamW(_FlatOptimizer):
     def step(self):
         lib, s = _lib.load(), self.store
         self._step += 1
+        ctrl = self._ctrl_ptr()
         _lib.check(lib.passl_b200_adamw(s.master.data_ptr(), s.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                                         s.bf16.data_ptr(), s.block_seg.data_ptr(), self.seg_wd.data_ptr(),
                                         self.seg_lr.data_ptr() if self.seg_lr is not None else 0, self.lr, self.beta1,
-                                        self.beta2, self.eps, self._step, self.grad_scale, self._ctrl_ptr(), s.numel,
+                                        self.beta2, self.eps, self._step, self._gscale(ctrl), ctrl, s.numel,
                                         torch.cuda.current_stream().cuda_stream), "adamw")
 
     def state_dict(self):

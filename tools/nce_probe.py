@@ -72,7 +72,9 @@ def main():
         names = ["start", "after setup (alloc, PDL wait, sync)", "Q staged in TMEM", "target fetched"]
         for it in range(5):
             names += ["t%d: begin wait s_full" % it, "t%d: S ready" % it, "t%d: S in registers" % it, "t%d: tile done" % it]
-        names += ["mma: q_ready"] + ["mma: issue t%d" % i for i in range(7)]
+        names = names[:22] + ["loop done, atomics issued", "after __threadfence"]
+        names += ["mma: q_ready"] + ["mma: issue t%d" % i for i in range(4)] + ["last CTA: finalize done", "producer: owner targets published",
+                                                                               "ticket taken"]
         for mode in ("warm (8th of 8 back-to-back calls over different queues)", "cold (L2 flushed, single call)"):
             dbg = torch.zeros(148 * 32, dtype=torch.int64, device=dev)
             torch.cuda.synchronize()
