@@ -130,6 +130,20 @@ int passl_b200_infonce_tc_fwd(const void* Q, const void* Kmat, const float* P, c
 int passl_b200_infonce_tc_bwd(const void* Q, const void* Kmat, const float* P, const long long* label, const int* excl,
                               float scale, float loss_scale, int N, int K, int D, const float* lse, const float* tgt,
                               const float* dloss, float* dQ, void* stream);
+/* Fused compute + collective: the gathered-key InfoNCE of MoCo v3 / CLIP (passl/models/mocov3.py:173-198: k_all =
+ * concat_all_gather(k); logits = q k_all^T / T; labels = arange(N) + N*rank) WITHOUT the all-gather.  The key matrix is the
+ * concatenation of `world` bf16 shards [shard_rows, D] (shard_rows % 64 == 0), each read IN PLACE from its owner's peer-mapped
+ * buffer by TMA, tile by tile, so the NVLink transfer overlaps the MMAs / softmax of the tiles already on chip.
+ * shard_ptrs: HOST array of `world` (<= 8) device pointers = this process's mappings of every rank's shard buffer (own rank
+ * included); my_flags: this rank's flag row (uint32[world]); the kernel consumes shard q once my_flags[q] >= epoch
+ * (passl_b200_peer_publish_keys_bf16 on rank q).  Label mode only; other arguments as passl_b200_infonce_tc_fwd / _bwd. */
+int passl_b200_infonce_tc_fwd_peer(const void* Q, const void* const* shard_ptrs, const void* my_flags, int world, int shard_rows,
+                                   unsigned epoch, const long long* label, const int* excl, float scale, float loss_scale, int N,
+                                   int D, float* lse, float* tgt, float* loss_rows, float* out_scalars, void* workspace,
+                                   long long workspace_bytes, void* stream);
+int passl_b200_infonce_tc_bwd_peer(const void* Q, const void* const* shard_ptrs, const void* my_flags, int world, int shard_rows,
+                                   unsigned epoch, const long long* label, const int* excl, float scale, float loss_scale, int N,
+                                   int D, const float* lse, const float* tgt, const float* dloss, float* dQ, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * SimCLR NT-Xent + CO2 (passl_v110/modeling/heads/simclr_contrastive_head.py:42-102) on a similarity matrix
@@ -333,6 +347,10 @@ int passl_b200_peer_buffer_open(const unsigned char* handle64, void** mapped);
 int passl_b200_peer_buffer_close(void* mapped);
 int passl_b200_peer_buffer_destroy(void* base);
 /* `shard` / `grad_all` (local device memory) is first copied into this rank's slot, then the kernel signals and gathers */
+/* publish this rank's key shard for passl_b200_infonce_tc_fwd_peer: keys fp32 [n, D] -> bf16 into data_ptrs[rank], then
+ * (system-scope fence) flag[rank] = epoch in every rank's flag row.  done: uint32, zeroed once by the caller. */
+int passl_b200_peer_publish_keys_bf16(const float* keys, int n, int D, const void* const* data_ptrs, void* const* flag_ptrs, int rank,
+                                      int world, unsigned epoch, void* done, void* stream);
 int passl_b200_peer_allgather(const void* shard, const void* const* data_ptrs, void* const* flag_ptrs, void* out, long long shard_bytes,
                               int rank, int world, unsigned epoch, void* stream);
 int passl_b200_peer_reduce_scatter_f32(const float* grad_all, const void* const* data_ptrs, void* const* flag_ptrs, float* out,

@@ -47,6 +47,12 @@ SIGNATURES = {
                                           c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
     "passl_b200_infonce_tc_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_int,
                                           c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "passl_b200_infonce_tc_fwd_peer": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, ctypes.c_uint, c_void_p, c_void_p, c_float,
+                                               c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
+    "passl_b200_infonce_tc_bwd_peer": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, ctypes.c_uint, c_void_p, c_void_p, c_float,
+                                               c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "passl_b200_peer_publish_keys_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, ctypes.c_uint, c_void_p,
+                                                  c_void_p]),
     "passl_b200_ntxent_workspace_bytes": (c_ll, [c_int]),
     "passl_b200_ntxent_co2_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_ll, c_void_p]),
     "passl_b200_ntxent_co2_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
