@@ -66,19 +66,47 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons DURING the timed region (every 0.2 s).  In-process NVML (nvidia_ml_py), initialised before the
+    timed region starts: spawning `nvidia-smi` inside it cost 70-120 ms of stalled launches per run (the first invocation loads
+    NVML and takes the driver lock) — visible as `value` < `e2e` in the first round-2 lines.  nvidia-smi is only the fallback."""
+
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
+        self.nvml, self.handle, self.max_mhz = None, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)           # first query outside the timed region
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
-    def run(self):
+    def _sample(self):
+        if self.nvml is not None:
+            mhz = int(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+            try:
+                mask = int(self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            except Exception:
+                mask = int(self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            return mhz, self.max_mhz, [n for n, bit in self.REASONS if mask & bit]
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                           capture_output=True, text=True, timeout=5).stdout.strip()
+        f = [x.strip() for x in o.split(",")]
+        return int(f[0]), int(f[1]), [n for (n, _), v in zip(self.REASONS, f[2:6]) if v.lower().startswith("active")]
+
+    def run(self):
         while not self.stop_flag:
             try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                   capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.samples.append([x.strip() for x in o.split(",")])
+                self.samples.append(self._sample())
             except Exception:
                 pass
             time.sleep(0.2)
@@ -86,14 +114,12 @@ class ClockSampler(threading.Thread):
     def summary(self):
         if not self.samples:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["unavailable"])
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        sm = sorted(s[0] for s in self.samples)
         reasons = set()
         for s in self.samples:
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], s[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
-                    reasons=sorted(reasons), samples=len(self.samples))
+            reasons.update(s[2])
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=self.samples[0][1], reasons=sorted(reasons), samples=len(self.samples),
+                    source="nvml" if self.nvml is not None else "nvidia-smi")
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -372,14 +398,24 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    per_step = {}
+
+    def timed(fn, steps, tag=None):
         barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         s.record()
-        for _ in range(steps):
+        for i in range(steps):
             loss = fn()
+            marks[i].record()                      # per-step device times (diagnostic only; the metric is the whole region)
         e.record()
         barrier()
+        if tag:
+            prev, out = s, []
+            for m in marks:
+                out.append(round(prev.elapsed_time(m), 3))
+                prev = m
+            per_step[tag] = out
         ms = torch.tensor([s.elapsed_time(e)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -391,7 +427,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     launches0 = lib.passl_b200_launch_count()
-    ms, loss = timed(lambda: step(dev_in), args.steps)
+    ms, loss = timed(lambda: step(dev_in), args.steps, tag="value")
     launches = lib.passl_b200_launch_count() - launches0
     sampler.stop_flag = True
     loss_val = float(loss.item())
@@ -427,7 +463,7 @@ def run_ours(args):
     prefetch(0)
     for _ in range(2):
         e2e_step()
-    ms_e2e, _ = timed(e2e_step, args.steps)
+    ms_e2e, _ = timed(e2e_step, args.steps, tag="e2e")
     e2e_value = B * world * args.steps / (ms_e2e / 1e3)
     h2d = sum(t.numel() * t.element_size() for t in host_in)
 
@@ -436,7 +472,7 @@ def run_ours(args):
             "data": "synthetic", "config": workload_config(cfg, world), "final_loss": loss_val,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches)}
+            "gpu_launches": int(launches), "ms_each_step": per_step}
 
     # ---- roofline of the tcgen05 launches: instrumented (untimed) step with CUDA events around every launch.
     #      Every rank runs the step (it contains collectives); only rank 0 reports.

@@ -27,7 +27,12 @@ class SimCLRContrastiveHead(nn.Module):
             return None
         if not self.peer_exchange:
             return all_gather
-        if self._ex is None or (self._ex.n, self._ex.d) != tuple(con.shape):
+        if self._ex is not None and (self._ex.n, self._ex.d) != tuple(con.shape):
+            # a different shard shape (e.g. a smaller last batch): the exchange buffers were sized at construction; creating a new
+            # exchange mid-step needs a collective handshake that deadlocks unless every rank changes shape at the same step —
+            # take the NCCL path for this call and keep the exchange for the regular shape
+            return all_gather
+        if self._ex is None:
             from ...distributed.peer import PeerExchange
             self._ex = PeerExchange(con.shape[0], con.shape[1], device=con.device)
         return self._ex.all_gather

@@ -15,7 +15,7 @@ import torch.nn as nn
 
 from .. import kernels as K
 from ..core.param_store import ParamStore
-from ..distributed import concat_all_gather, get_rank
+from ..distributed import concat_all_gather, get_rank, get_world_size
 from ..loss.contrastive import gathered_infonce, normalize
 from ..nn.layers import BatchNorm1D, Linear
 from .vision_transformer import VisionTransformer
@@ -139,9 +139,14 @@ class _Encoder(nn.Module):
 
 class MoCoV3Pretrain(nn.Module):
     def __init__(self, base_encoder, dim=256, mlp_dim=4096, T=1.0, base_momentum=0.99, max_steps=1000,
-                 reference_ema_quirk=False):
+                 reference_ema_quirk=False, peer_loss=None):
         super().__init__()
         self.T, self.base_momentum, self.max_steps, self.quirk = T, base_momentum, max_steps, reference_ema_quirk
+        # fused compute + collective (single node): the loss kernels read every rank's key shard in place over NVLink instead of
+        # consuming an NCCL all-gathered copy (distributed/peer.py::PeerKeyShards); PASSL_B200_PEER_LOSS=1 or peer_loss=True
+        import os
+        self.peer_loss = bool(int(os.environ.get("PASSL_B200_PEER_LOSS", "0"))) if peer_loss is None else bool(peer_loss)
+        self._shards = None
         vit_q, vit_k = base_encoder(), base_encoder()
         hidden = vit_q.embed_dim
         self.base_encoder = _Encoder(vit_q, MLPBN(3, hidden, mlp_dim, dim))
@@ -188,6 +193,16 @@ class MoCoV3Pretrain(nn.Module):
 
     def contrastive_loss(self, q, k):
         q = normalize(q)
+        if self.peer_loss and get_world_size() > 1 and q.shape[0] % 64 == 0 and q.shape[1] % 64 == 0 and q.shape[1] <= 256:
+            from ..distributed.peer import PeerKeyShards, peer_gathered_infonce
+            if self._shards is None or (self._shards.n, self._shards.d) != tuple(q.shape):
+                if self._shards is not None:
+                    self._shards.close()
+                self._shards = PeerKeyShards(q.shape[0], q.shape[1])
+            with torch.no_grad():
+                kn = normalize(k)
+            loss, _, _ = peer_gathered_infonce(q, kn, self._shards, 1.0 / self.T, 2 * self.T)
+            return loss
         with torch.no_grad():
             k = concat_all_gather(normalize(k))
         N = q.shape[0]

@@ -36,6 +36,17 @@ elif what == "infonce":
     for i in range(4):
         dq = K.infonce_tc_bwd(qb, queue, lse, tgt, pos=k, scale=1 / T)
     torch.cuda.synchronize()
+if what == "attn":
+    # ViT-B/16 encoder (N=197, d=64), MAE encoder (N=50), MAE decoder (N=197, d=32), CLIP text tower (N=77, causal): fwd + bwd each
+    from passl_b200 import kernels_vit as V
+    shapes = [(512, 197, 12, 64, False), (512, 50, 12, 64, False), (256, 197, 16, 32, False), (512, 77, 8, 64, True)]
+    for rep in range(2):                      # first round = warm-up (skipped by ncu -s 8)
+        for (B, N, H, d, causal) in shapes:
+            qkv = torch.randn(B * N, 3 * H * d, device="cuda").bfloat16()
+            out, lse = V.attention_fwd(qkv, B, N, H, d, causal=causal)
+            dout = torch.randn_like(out)
+            V.attention_bwd(qkv, dout, out, lse, B, N, H, d, causal=causal)
+    torch.cuda.synchronize()
 if what == "conv":
     B = 128
     x = torch.randn(B, 56, 56, 64, device="cuda").bfloat16()
