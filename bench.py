@@ -83,8 +83,9 @@ class ClockSampler(threading.Thread):
             phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
-            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)           # first query outside the timed region
             self.nvml = pynvml
+            for _ in range(2):                   # every query once outside the timed region (the first calls take ~20 ms each)
+                self._sample()
         except Exception:
             self.nvml = None
 
