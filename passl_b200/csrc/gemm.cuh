@@ -112,11 +112,43 @@ __device__ __forceinline__ void decode_patch(const PatchGeom& g, int idx, int& n
   w0 = iw * g.TW;
 }
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == ACT_RELU) return fmaxf(v, 0.f);
-  if (act == ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
-  if (act == ACT_QUICKGELU) return v / (1.f + __expf(-1.702f * v));
-  return v;
+// Phi(x) = 0.5 * erfc(-x / sqrt 2) for the exact (erf) GELU of the reference, and e = exp(-x^2 / 2) for its derivative.
+// erfc(z) = t * (a1 + t * (a2 + ... a5 t)) * exp(-z^2), t = 1 / (1 + 0.3275911 z), z >= 0 (Abramowitz & Stegun 7.1.26, absolute
+// error < 1.5e-7, the tail is formed without cancellation): 2 MUFU (rcp, ex2) + 10 FMA-pipe instructions.  erff() costs ~3x that
+// and, inlined 32x per chunk, pushed the epilogue out of the instruction cache (fc1 of ViT-B ran at 300 TF/s, profiles/
+// r02_vit_gemm_probe.txt).
+__device__ __forceinline__ float gelu_phi(float x, float& e) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
+  float y = fmaf(1.061405429f, t, -1.453152027f);
+  y = fmaf(y, t, 1.421413741f);
+  y = fmaf(y, t, -0.284496736f);
+  y = fmaf(y, t, 0.254829592f);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170f));
+  const float h = 0.5f * (y * t) * e;   // Phi(-|x|)
+  return x < 0.f ? h : 1.f - h;
+}
+__device__ __forceinline__ float act_gelu(float v) { float e; return v * gelu_phi(v, e); }
+__device__ __forceinline__ float act_quickgelu(float v) { return v / (1.f + __expf(-1.702f * v)); }
+// d/da of the activation at the saved pre-activation a
+__device__ __forceinline__ float gate_gelu(float a) { float e; const float ph = gelu_phi(a, e); return fmaf(a * 0.3989422804014327f, e, ph); }
+__device__ __forceinline__ float gate_quickgelu(float a) {
+  const float sg = 1.f / (1.f + __expf(-1.702f * a));
+  return sg * (1.f + 1.702f * a * (1.f - sg));
+}
+// the gate of one 8-column group of a row (aux values packed as bf16), mode fixed per call so that only the taken variant is
+// in the instruction stream that is executed
+template <int MODE>
+__device__ __forceinline__ void apply_gate8(float* f, const uint4& u) {
+  const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+  const float a[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+#pragma unroll
+  for (int ee = 0; ee < 8; ++ee) {
+    if (MODE == 1) f[ee] = a[ee] > 0.f ? f[ee] : 0.f;
+    else if (MODE == 2) f[ee] *= gate_gelu(a[ee]);
+    else f[ee] *= gate_quickgelu(a[ee]);
+  }
 }
 
 // Issue the TMA loads of one pipeline stage for one operand.
@@ -431,16 +463,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       // residual tiles are fetched one chunk ahead with row-coalesced loads (8 rows x 64 B per instruction); the first one is
       // issued before waiting for the accumulator so that its DRAM latency hides behind the MMA
       const bool use_res = staged && p.residual != nullptr && p.res_iters == 0;
-      auto load_res = [&](int c_, uint4 (&dst)[4]) {
+      const bool use_aux = staged && p.aux != nullptr;   // the gate's operand takes the same row-coalesced, one-chunk-ahead route
+      auto load_tile = [&](const __nv_bfloat16* src, int c_, uint4 (&dst)[4]) {
         const bool okc = (c_ < BN / 32) && (col0 + c_ * 32 + cch * 8 < col_lim);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           dst[i] = make_uint4(0u, 0u, 0u, 0u);
-          if (ro4[i] >= 0 && okc) dst[i] = ld_nc_v4(p.residual + ro4[i] + col_base + c_ * 32 + cch * 8);
+          if (ro4[i] >= 0 && okc) dst[i] = ld_nc_v4(src + ro4[i] + col_base + c_ * 32 + cch * 8);
         }
       };
-      uint4 rr[4];
-      if (use_res) load_res((int)half, rr);
+      uint4 rr[4], ar[4];
+      if (use_res) load_tile(p.residual, (int)half, rr);
+      if (use_aux) load_tile(p.aux, (int)half, ar);
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -456,8 +490,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         uint32_t v[32];
         tmem_ld_32x32(t_addr + c * 32, v);
         const bool col_ok = cc0 + cch * 8 < col_lim;
-        uint4 rn[4];
-        if (use_res) load_res(c + 2, rn);        // next chunk of this warp
+        uint4 rn[4], an[4];
+        if (use_res) load_tile(p.residual, c + 2, rn);        // next chunk of this warp
+        if (use_aux) load_tile(p.aux, c + 2, an);
         tmem_ld_wait();
         float f[32];
         if (unit_alpha) {
@@ -468,43 +503,89 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
         }
         if (p.bias) {
+          if (cc0 + 32 <= col_lim) {            // whole chunk inside the tensor: 8 broadcast 16-byte loads instead of 32 scalar ones
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + oc0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (cc0 + j < col_lim) f[j] += __ldg(p.bias + oc0 + j);
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 b = __ldg(bp + j4);
+              f[j4 * 4 + 0] += b.x; f[j4 * 4 + 1] += b.y; f[j4 * 4 + 2] += b.z; f[j4 * 4 + 3] += b.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (cc0 + j < col_lim) f[j] += __ldg(p.bias + oc0 + j);
+          }
         }
-        if (p.preact && row_ok) {
-          __nv_bfloat16* pp = p.preact + row_off + oc0;
+        if (p.preact) {
+          if (staged) {
+            // through the staging tile like the output: 8 rows x 64 B per store instruction
 #pragma unroll
-          for (int j8 = 0; j8 < 4; ++j8)
-            if (cc0 + j8 * 8 < col_lim) {
+            for (int j8 = 0; j8 < 4; ++j8) {
               uint4 u;
               u.x = pack_bf16x2(f[j8 * 8 + 0], f[j8 * 8 + 1]);
               u.y = pack_bf16x2(f[j8 * 8 + 2], f[j8 * 8 + 3]);
               u.z = pack_bf16x2(f[j8 * 8 + 4], f[j8 * 8 + 5]);
               u.w = pack_bf16x2(f[j8 * 8 + 6], f[j8 * 8 + 7]);
-              *reinterpret_cast<uint4*>(pp + j8 * 8) = u;
+              st_shared_v4(stg_u32 + lane * kEpiStride + j8 * 16, u);
             }
-        }
-        if (p.act != ACT_NONE) {
+            __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+            for (int i = 0; i < 4; ++i) {
+              if (ro4[i] >= 0 && col_ok)
+                *reinterpret_cast<uint4*>(p.preact + ro4[i] + oc0 + cch * 8) = ld_shared_v4(stg_u32 + (i * 8 + crow) * kEpiStride + cch * 16);
+            }
+            __syncwarp();
+          } else if (row_ok) {
+            __nv_bfloat16* pp = p.preact + row_off + oc0;
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8)
+              if (cc0 + j8 * 8 < col_lim) {
+                uint4 u;
+                u.x = pack_bf16x2(f[j8 * 8 + 0], f[j8 * 8 + 1]);
+                u.y = pack_bf16x2(f[j8 * 8 + 2], f[j8 * 8 + 3]);
+                u.z = pack_bf16x2(f[j8 * 8 + 4], f[j8 * 8 + 5]);
+                u.w = pack_bf16x2(f[j8 * 8 + 6], f[j8 * 8 + 7]);
+                *reinterpret_cast<uint4*>(pp + j8 * 8) = u;
+              }
+          }
         }
-        if (p.aux && row_ok) {
+        // the activation is selected outside the element loops: each variant is its own straight-line block
+        if (p.act == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        } else if (p.act == ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = act_gelu(f[j]);
+        } else if (p.act == ACT_QUICKGELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = act_quickgelu(f[j]);
+        }
+        if (use_aux) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) st_shared_v4(stg_u32 + (i * 8 + crow) * kEpiStride + cch * 16, ar[i]);
+          __syncwarp();
+          if (p.aux_mode == 1) {
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) apply_gate8<1>(f + j8 * 8, ld_shared_v4(stg_u32 + lane * kEpiStride + j8 * 16));
+          } else if (p.aux_mode == 2) {
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) apply_gate8<2>(f + j8 * 8, ld_shared_v4(stg_u32 + lane * kEpiStride + j8 * 16));
+          } else {
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) apply_gate8<3>(f + j8 * 8, ld_shared_v4(stg_u32 + lane * kEpiStride + j8 * 16));
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ar[i] = an[i];
+        } else if (p.aux && row_ok) {
           const __nv_bfloat16* ap = p.aux + row_off + oc0;
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
             if (cc0 + j8 * 8 < col_lim) {
-              uint4 u = *reinterpret_cast<const uint4*>(ap + j8 * 8);
-              float a[8];
-              float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
-              a[0] = a0.x; a[1] = a0.y; a[2] = a1.x; a[3] = a1.y; a[4] = a2.x; a[5] = a2.y; a[6] = a3.x; a[7] = a3.y;
-#pragma unroll
-              for (int ee = 0; ee < 8; ++ee) {
-                float& vv = f[j8 * 8 + ee];
-                if (p.aux_mode == 1) vv = a[ee] > 0.f ? vv : 0.f;
-                else if (p.aux_mode == 2) vv *= 0.5f * (1.f + erff(a[ee] * 0.70710678118654752f)) + a[ee] * 0.3989422804014327f * __expf(-0.5f * a[ee] * a[ee]);
-                else { float sg = 1.f / (1.f + __expf(-1.702f * a[ee])); vv *= sg * (1.f + 1.702f * a[ee] * (1.f - sg)); }
-              }
+              const uint4 u = *reinterpret_cast<const uint4*>(ap + j8 * 8);
+              if (p.aux_mode == 1) apply_gate8<1>(f + j8 * 8, u);
+              else if (p.aux_mode == 2) apply_gate8<2>(f + j8 * 8, u);
+              else apply_gate8<3>(f + j8 * 8, u);
             }
           }
         }
