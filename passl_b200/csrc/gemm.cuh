@@ -97,7 +97,8 @@ struct GemmSmem {
   static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int EPI_BYTES = kEpiWarps * 32 * kEpiStride;          // per-warp staging tiles of the epilogue
+  static constexpr int BIAS_BYTES = kEpiWarps * 4 * 32 * 4;              // per-warp bias slices of the current tile (4 chunks x 32 columns, fp32)
+  static constexpr int EPI_BYTES = kEpiWarps * 32 * kEpiStride + BIAS_BYTES;   // per-warp staging tiles of the epilogue + bias slices
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024;  // + alignment slack
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 };
@@ -117,22 +118,43 @@ __device__ __forceinline__ void decode_patch(const PatchGeom& g, int idx, int& n
 // error < 1.5e-7, the tail is formed without cancellation): 2 MUFU (rcp, ex2) + 10 FMA-pipe instructions.  erff() costs ~3x that
 // and, inlined 32x per chunk, pushed the epilogue out of the instruction cache (fc1 of ViT-B ran at 300 TF/s, profiles/
 // r02_vit_gemm_probe.txt).
-__device__ __forceinline__ float gelu_phi(float x, float& e) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
-  float y = fmaf(1.061405429f, t, -1.453152027f);
-  y = fmaf(y, t, 1.421413741f);
-  y = fmaf(y, t, -0.284496736f);
-  y = fmaf(y, t, 0.254829592f);
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170f));
-  const float h = 0.5f * (y * t) * e;   // Phi(-|x|)
-  return x < 0.f ? h : 1.f - h;
+// Eight elements at a time, stage by stage, so that the eight MUFU.RCP / MUFU.EX2 are in flight together (written one element
+// at a time ptxas chained rcp -> Horner -> ex2 through one register and every element paid the MUFU latency: short-scoreboard
+// stalls were half of the epilogue of fc1, profiles/r02_ncu_vitgemm_summary.txt).
+__device__ __forceinline__ void gelu_phi8(const float* x, float* ph, float* e) {
+  float t[8], y[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(t[k]) : "f"(fmaf(0.3275911f * 0.70710678118654752f, fabsf(x[k]), 1.f)));
+#pragma unroll
+  for (int k = 0; k < 8; ++k) asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[k]) : "f"(x[k] * x[k] * -0.72134752044448170f));
+#pragma unroll
+  for (int k = 0; k < 8; ++k) y[k] = fmaf(1.061405429f, t[k], -1.453152027f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) y[k] = fmaf(y[k], t[k], 1.421413741f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) y[k] = fmaf(y[k], t[k], -0.284496736f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) y[k] = fmaf(y[k], t[k], 0.254829592f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float h = 0.5f * (y[k] * t[k]) * e[k];   // Phi(-|x|)
+    ph[k] = x[k] < 0.f ? h : 1.f - h;
+  }
 }
-__device__ __forceinline__ float act_gelu(float v) { float e; return v * gelu_phi(v, e); }
+__device__ __forceinline__ void act_gelu8(float* f) {
+  float ph[8], e[8];
+  gelu_phi8(f, ph, e);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) f[k] *= ph[k];
+}
 __device__ __forceinline__ float act_quickgelu(float v) { return v / (1.f + __expf(-1.702f * v)); }
 // d/da of the activation at the saved pre-activation a
-__device__ __forceinline__ float gate_gelu(float a) { float e; const float ph = gelu_phi(a, e); return fmaf(a * 0.3989422804014327f, e, ph); }
+__device__ __forceinline__ void gate_gelu8(float* f, const float* a) {
+  float ph[8], e[8];
+  gelu_phi8(a, ph, e);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) f[k] *= fmaf(a[k] * 0.3989422804014327f, e[k], ph[k]);
+}
 __device__ __forceinline__ float gate_quickgelu(float a) {
   const float sg = 1.f / (1.f + __expf(-1.702f * a));
   return sg * (1.f + 1.702f * a * (1.f - sg));
@@ -143,10 +165,13 @@ template <int MODE>
 __device__ __forceinline__ void apply_gate8(float* f, const uint4& u) {
   const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
   const float a[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+  if (MODE == 2) {
+    gate_gelu8(f, a);
+    return;
+  }
 #pragma unroll
   for (int ee = 0; ee < 8; ++ee) {
     if (MODE == 1) f[ee] = a[ee] > 0.f ? f[ee] : 0.f;
-    else if (MODE == 2) f[ee] *= gate_gelu(a[ee]);
     else f[ee] *= gate_quickgelu(a[ee]);
   }
 }
@@ -385,6 +410,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     const uint32_t q = warp & 3;
     const uint32_t half = e >> 2;
     uint8_t* stg = epi_stage + e * (32 * kEpiStride);
+    const uint32_t bias_u32 = smem_u32(epi_stage + kEpiWarps * 32 * kEpiStride + e * (4 * 32 * 4));
     const uint32_t stg_u32 = smem_u32(stg);
     const bool staged = !p.out_fp32;
     const bool do_stats = staged && p.col_sum != nullptr && !(p.dbg & 1);
@@ -476,6 +502,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       if (use_res) load_tile(p.residual, (int)half, rr);
       if (use_aux) load_tile(p.aux, (int)half, ar);
 
+      if (p.bias) {
+        // this warp's bias slices (one per chunk) go to shared memory while the MMA is still running: the chunk loop then reads
+        // them with broadcast 16-byte loads instead of waiting on global loads between the TMEM load and the arithmetic
+#pragma unroll
+        for (int i = 0; i < NCH && i < 4; ++i) {
+          const int cb = ((int)half + 2 * i) * 32 + (int)lane;
+          float bvv = 0.f;
+          if (cb < BN && col0 + cb < col_lim) bvv = __ldg(p.bias + col_base + cb);
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_u32 + (i * 32 + lane) * 4), "f"(bvv) : "memory");
+        }
+        __syncwarp();
+      }
+      bool released = false;
+
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((q * 32u) << 16) + acc * BN;
@@ -502,18 +542,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
         }
-        if (p.bias) {
-          if (cc0 + 32 <= col_lim) {            // whole chunk inside the tensor: 8 broadcast 16-byte loads instead of 32 scalar ones
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + oc0);
+        if (!(ci + 1 < NCH && c + 2 < BN / 32 && cc0 + 64 < col_lim)) {
+          // that was this warp's last read of the accumulator: hand the TMEM buffer back before the arithmetic and the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          released = true;
+        }
+        if (p.bias) {                               // columns outside the tensor hold 0
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 b = __ldg(bp + j4);
-              f[j4 * 4 + 0] += b.x; f[j4 * 4 + 1] += b.y; f[j4 * 4 + 2] += b.z; f[j4 * 4 + 3] += b.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (cc0 + j < col_lim) f[j] += __ldg(p.bias + oc0 + j);
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const uint4 b = ld_shared_v4(bias_u32 + (ci * 32 + j4 * 4) * 4);
+            f[j4 * 4 + 0] += __uint_as_float(b.x); f[j4 * 4 + 1] += __uint_as_float(b.y);
+            f[j4 * 4 + 2] += __uint_as_float(b.z); f[j4 * 4 + 3] += __uint_as_float(b.w);
           }
         }
         if (p.preact) {
@@ -555,7 +596,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
         } else if (p.act == ACT_GELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = act_gelu(f[j]);
+          for (int j8 = 0; j8 < 4; ++j8) act_gelu8(f + j8 * 8);
         } else if (p.act == ACT_QUICKGELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = act_quickgelu(f[j]);
@@ -675,9 +716,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         }
         __syncwarp();
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (!released) {       // no chunk of this warp inside the tensor
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      }
     }
     if (do_stats && prev_nblk >= 0) flush_stats(prev_nblk);
   }

@@ -1,9 +1,12 @@
 """SASS rows of an .ncu-rep in address order with stall samples, condensed: runs of instructions are merged into regions separated
-by 'anchor' opcodes (barrier waits, TMEM loads, branches).  usage: ncu_sass.py file.ncu-rep [min_samples_to_print_row]"""
+by 'anchor' opcodes (barrier waits, TMEM loads, branches).  usage: ncu_sass.py file.ncu-rep [min_samples_to_print_row] [--launch=N]"""
 import csv, io, subprocess, sys
 rep = sys.argv[1]
+launch = [a for a in sys.argv if a.startswith("--launch=")]
+sys.argv = [a for a in sys.argv if not a.startswith("--launch=")]
+sel = ["--launch-skip", launch[0].split("=")[1], "--launch-count", "1"] if launch else []
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + sel, capture_output=True, text=True).stdout
 thr = int(sys.argv[2]) if len(sys.argv) > 2 else 8
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr = rows[1]
 ci = {h: i for i, h in enumerate(hdr)}

@@ -89,3 +89,22 @@ if what == "c3res":
     for i in range(2):
         K.gemm(x, w, out=y)
     torch.cuda.synchronize()
+if what == "vitgemm":
+    # three ViT-B GEMMs with their epilogues (T = 25600 tokens): qkv fwd (+bias), fc1 fwd (+bias+gelu+preact), fc2 dgrad (+gelu')
+    T, D, Hd = 25600, 768, 3072
+    a = torch.randn(T, D, device="cuda").bfloat16()
+    wq = torch.randn(3 * D, D, device="cuda").bfloat16() * 0.02
+    w1 = torch.randn(Hd, D, device="cuda").bfloat16() * 0.02
+    w2 = torch.randn(D, Hd, device="cuda").bfloat16() * 0.02
+    bq, b1 = torch.zeros(3 * D, device="cuda"), torch.zeros(Hd, device="cuda")
+    oq = torch.empty(T, 3 * D, device="cuda", dtype=torch.bfloat16)
+    o1 = torch.empty(T, Hd, device="cuda", dtype=torch.bfloat16)
+    u1 = torch.empty_like(o1)
+    dy = torch.randn(T, D, device="cuda").bfloat16()
+    aux = torch.randn(T, Hd, device="cuda").bfloat16()
+    dh = torch.empty_like(o1)
+    for rep in range(2):
+        K.gemm(a, wq, bias=bq, out=oq)
+        K.gemm(a, w1, bias=b1, act="gelu", preact_out=u1, out=o1)
+        K.gemm(dy, w2, b_t=True, aux=aux, aux_mode_name="gelu_grad", out=dh)
+    torch.cuda.synchronize()
