@@ -84,10 +84,12 @@ struct GemmParams {
   // deep as the operands (a register prefetch in the epilogue cannot cover the ~4 us DRAM latency of a saturated HBM)
   CUtensorMap res_map, eye_map;
   int res_iters;
+  // EPI = 1 (plain row-major bf16 outputs of the linear layers): 32 x 32 output boxes leave through TMA stores
+  CUtensorMap out_map, pre_map;
   int dbg;              // developer perf experiments (PASSL_B200_EPI_DEBUG): 1 skip stats, 2 skip global stores, 4 skip staging
 };
 
-template <int BN, int BK, bool A_MN, bool B_MN>
+template <int BN, int BK, bool A_MN, bool B_MN, int EPI = 0>
 struct GemmSmem {
   static constexpr int BM = 128;
   static constexpr int A_BYTES = BM * BK * 2;
@@ -98,9 +100,14 @@ struct GemmSmem {
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int BAR_BYTES = 256;
   static constexpr int BIAS_BYTES = kEpiWarps * 4 * 32 * 4;              // per-warp bias slices of the current tile (4 chunks x 32 columns, fp32)
-  static constexpr int EPI_BYTES = kEpiWarps * 32 * kEpiStride + BIAS_BYTES;   // per-warp staging tiles of the epilogue + bias slices
+  // EPI 0: per-warp padded staging tiles + bias slices, after the barriers.  EPI 1: per warp two dense 2 KB tiles (32 rows x
+  // 64 B, SWIZZLE_64B, the source of the TMA stores) placed right after the stages so that they stay 1024-byte aligned.
+  static constexpr int EPI_BYTES = EPI == 1 ? kEpiWarps * 4096 : kEpiWarps * 32 * kEpiStride + BIAS_BYTES;
+  static constexpr int EPI_OFF = EPI == 1 ? STAGES * STAGE_BYTES : STAGES * STAGE_BYTES + BAR_BYTES;
+  static constexpr int BAR_OFF = EPI == 1 ? STAGES * STAGE_BYTES + EPI_BYTES : STAGES * STAGE_BYTES;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024;  // + alignment slack
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static_assert(TOTAL <= 227 * 1024, "shared memory budget");
 };
 
 __device__ __forceinline__ void decode_patch(const PatchGeom& g, int idx, int& n0, int& h0, int& w0) {
@@ -169,6 +176,11 @@ __device__ __forceinline__ void apply_gate8(float* f, const uint4& u) {
     gate_gelu8(f, a);
     return;
   }
+  if (MODE == 4) {      // plain residual add
+#pragma unroll
+    for (int ee = 0; ee < 8; ++ee) f[ee] += a[ee];
+    return;
+  }
 #pragma unroll
   for (int ee = 0; ee < 8; ++ee) {
     if (MODE == 1) f[ee] = a[ee] > 0.f ? f[ee] : 0.f;
@@ -205,18 +217,18 @@ __device__ __forceinline__ void issue_operand_load(const GemmOperand& op, const 
   }
 }
 
-template <int BN, int BK, bool A_MN, bool B_MN>
+template <int BN, int BK, bool A_MN, bool B_MN, int EPI = 0>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
-  using S = GemmSmem<BN, BK, A_MN, B_MN>;
+  using S = GemmSmem<BN, BK, A_MN, B_MN, EPI>;
   constexpr int STAGES = S::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  uint8_t* epi_stage = smem + STAGES * S::STAGE_BYTES + S::BAR_BYTES;              // 8 warps x 32 rows x kEpiStride
+  uint8_t* epi_stage = smem + S::EPI_OFF;                                         // per-warp staging tiles of the epilogue
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
@@ -400,6 +412,161 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         }
       }
     }
+  } else if constexpr (EPI == 1) {
+    // ================= epilogue warps (2..9), linear layers =================
+    // Plain row-major bf16 outputs (out / pre-activation), no statistics, alpha = 1: the same split of the accumulator as below
+    // (two warps per TMEM lane quarter, alternating 32-column chunks), but each 32 x 32 box is packed into a dense swizzled
+    // 2 KB tile and leaves through one TMA store (bounds are clipped by the tensor map: no row / column predicates, no address
+    // arithmetic, one warp barrier instead of three per box), and nothing of the convolution epilogue's state (pixel decode,
+    // per-column statistics, tap decode) is live while the activation is evaluated.
+    const uint32_t e = warp - 2;
+    const uint32_t q = warp & 3;
+    const uint32_t half = e >> 2;
+    const uint32_t stg0 = smem_u32(epi_stage + e * 4096);
+    const uint32_t swz = (lane >> 1) & 3u;                     // SWIZZLE_64B: 16-byte slot ^= (row >> 1) & 3
+    const int crow = (int)(lane >> 2), cch = (int)(lane & 3);  // row-coalesced operand loads: 8 rows x 64 B per instruction
+    constexpr int NCH = (BN / 64) > 0 ? (BN / 64) : 1;
+    // at most one operand tile enters the epilogue: the gate's pre-activation (aux) or a residual that could not go through the MMA
+    const __nv_bfloat16* tsrc = p.aux ? p.aux : ((p.residual && p.res_iters == 0) ? p.residual : nullptr);
+    const int tmode = p.aux ? p.aux_mode : 4;                  // 1 ReLU mask, 2 GELU', 3 QuickGELU', 4 add
+    uint32_t nbuf = 0;
+    auto store_box = [&](const float (&f)[32], const CUtensorMap* map, int col, int row) {
+      const uint32_t buf = stg0 + (nbuf & 1u) * 2048u;
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store issued two boxes ago has read this tile
+      __syncwarp();
+#pragma unroll
+      for (int j8 = 0; j8 < 4; ++j8) {
+        uint4 u;
+        u.x = pack_bf16x2(f[j8 * 8 + 0], f[j8 * 8 + 1]);
+        u.y = pack_bf16x2(f[j8 * 8 + 2], f[j8 * 8 + 3]);
+        u.z = pack_bf16x2(f[j8 * 8 + 4], f[j8 * 8 + 5]);
+        u.w = pack_bf16x2(f[j8 * 8 + 6], f[j8 * 8 + 7]);
+        st_shared_v4(buf + lane * 64u + ((j8 ^ swz) << 4), u);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                     "r"(col), "r"(row), "r"(buf)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      ++nbuf;
+    };
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int rest = tile / p.splits;
+      const int n_blk = rest % p.n_blocks;
+      const int m_blk = rest / p.n_blocks;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int row0 = m_blk * 128 + (int)q * 32;
+      const int col0 = n_blk * BN;
+      auto load_tile = [&](int c_, uint4 (&dst)[4]) {
+        const int col = col0 + c_ * 32 + cch * 8;
+        const bool okc = (c_ < BN / 32) && (col < p.N);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int m = row0 + i * 8 + crow;
+          dst[i] = make_uint4(0u, 0u, 0u, 0u);
+          if (okc && m < p.M) dst[i] = ld_nc_v4(tsrc + (long long)m * p.ldc + col);
+        }
+      };
+      uint4 tr[4];
+      if (tsrc) load_tile((int)half, tr);
+      bool released = false;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((q * 32u) << 16) + acc * BN;
+#pragma unroll 1
+      for (int ci = 0; ci < NCH; ++ci) {
+        const int c = (int)half + 2 * ci;
+        if (c >= BN / 32) break;
+        const int cc0 = col0 + c * 32;
+        if (cc0 >= p.N) break;
+        uint32_t v[32];
+        tmem_ld_32x32(t_addr + c * 32, v);
+        // bias and the next operand tile are requested while the TMEM load is in flight
+        float4 bv[8];
+        if (p.bias) {
+          if (cc0 + 32 <= p.N) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) bv[j4] = __ldg(reinterpret_cast<const float4*>(p.bias + cc0) + j4);
+          } else {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              bv[j4] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (cc0 + j4 * 4 < p.N) bv[j4] = __ldg(reinterpret_cast<const float4*>(p.bias + cc0) + j4);   // N % 8 == 0
+            }
+          }
+        }
+        uint4 tn[4];
+        if (tsrc) load_tile(c + 2, tn);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (!(ci + 1 < NCH && c + 2 < BN / 32 && cc0 + 64 < p.N)) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          released = true;
+        }
+        if (p.bias) {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            f[j4 * 4 + 0] += bv[j4].x; f[j4 * 4 + 1] += bv[j4].y; f[j4 * 4 + 2] += bv[j4].z; f[j4 * 4 + 3] += bv[j4].w;
+          }
+        }
+        if (p.preact) store_box(f, &p.pre_map, cc0, row0);
+        if (p.act == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        } else if (p.act == ACT_GELU) {
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) act_gelu8(f + j8 * 8);
+        } else if (p.act == ACT_QUICKGELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = act_quickgelu(f[j]);
+        }
+        if (tsrc) {
+          // transpose the row-coalesced operand tile through the staging tile the next store will use
+          const uint32_t buf = stg0 + (nbuf & 1u) * 2048u;
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t r_ = (uint32_t)(i * 8 + crow);
+            st_shared_v4(buf + r_ * 64u + (((uint32_t)cch ^ ((r_ >> 1) & 3u)) << 4), tr[i]);
+          }
+          __syncwarp();
+          if (tmode == 1) {
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) apply_gate8<1>(f + j8 * 8, ld_shared_v4(buf + lane * 64u + ((j8 ^ swz) << 4)));
+          } else if (tmode == 2) {
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) apply_gate8<2>(f + j8 * 8, ld_shared_v4(buf + lane * 64u + ((j8 ^ swz) << 4)));
+          } else if (tmode == 3) {
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) apply_gate8<3>(f + j8 * 8, ld_shared_v4(buf + lane * 64u + ((j8 ^ swz) << 4)));
+          } else {
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) apply_gate8<4>(f + j8 * 8, ld_shared_v4(buf + lane * 64u + ((j8 ^ swz) << 4)));
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) tr[i] = tn[i];
+        }
+        store_box(f, &p.out_map, cc0, row0);
+      }
+      if (!released) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the staging tiles must outlive their stores
+    __syncwarp();
   } else {
     // ================= epilogue warps (2..9) =================
     // Eight warps: warp w may only touch TMEM lanes 32*(w%4).., so two warps share each lane quarter and split the 32-column

@@ -53,10 +53,10 @@ static int setup_residual_mma(GemmParams& p, const void* residual, long long ldc
   return PB_OK;
 }
 
-template <int BN, int BK, bool A_MN, bool B_MN>
+template <int BN, int BK, bool A_MN, bool B_MN, int EPI = 0>
 static int launch_gemm_t(const GemmParams& p, cudaStream_t st) {
-  using S = GemmSmem<BN, BK, A_MN, B_MN>;
-  auto kern = gemm_tcgen05_kernel<BN, BK, A_MN, B_MN>;
+  using S = GemmSmem<BN, BK, A_MN, B_MN, EPI>;
+  auto kern = gemm_tcgen05_kernel<BN, BK, A_MN, B_MN, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     PB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
@@ -77,10 +77,12 @@ static int launch_gemm_t(const GemmParams& p, cudaStream_t st) {
   return PB_OK;
 }
 
-static int launch_gemm(const GemmParams& p, int BN, int BK, bool a_mn, bool b_mn, cudaStream_t st) {
+static int launch_gemm(const GemmParams& p, int BN, int BK, bool a_mn, bool b_mn, cudaStream_t st, int epi = 0) {
 #define PB_DISPATCH(bn)                                                                 \
   if (BN == bn) {                                                                       \
     if (BK == 128) return launch_gemm_t<bn, 128, true, true>(p, st);                    \
+    if (epi == 1 && !a_mn && !b_mn) return launch_gemm_t<bn, 64, false, false, 1>(p, st); \
+    if (epi == 1 && !a_mn && b_mn) return launch_gemm_t<bn, 64, false, true, 1>(p, st);   \
     if (!a_mn && !b_mn) return launch_gemm_t<bn, 64, false, false>(p, st);              \
     if (!a_mn && b_mn) return launch_gemm_t<bn, 64, false, true>(p, st);                \
     if (a_mn && !b_mn) return launch_gemm_t<bn, 64, true, false>(p, st);                \
@@ -211,7 +213,25 @@ extern "C" int passl_b200_gemm_bf16_ex(const void* A, const void* B, void* out, 
   p.preact = reinterpret_cast<__nv_bfloat16*>(preact_out);
   r = setup_residual_mma(p, residual, ldc, (cudaStream_t)stream);
   if (r) return r;
-  return launch_gemm(p, BN, 64, a_mn_major != 0, b_mn_major != 0, (cudaStream_t)stream);
+  // linear-layer epilogue (EPI 1, TMA stores): plain row-major bf16 output, K-major A, no statistics / scaling, at most one
+  // operand tile (gate operand or a residual that does not go through the MMA)
+  static int lean = -1;
+  if (lean < 0) { const char* e = getenv("PASSL_B200_GEMM_EPI0"); lean = (e && atoi(e)) ? 0 : 1; }
+  int epi = 0;
+  const bool res_in_epilogue = residual && p.res_iters == 0;
+  if (lean && !out_fp32 && !a_mn_major && !col_sum && alpha == 1.f && splits == 1 && !(aux && res_in_epilogue) &&
+      !((reinterpret_cast<uintptr_t>(aux) | reinterpret_cast<uintptr_t>(preact_out) | reinterpret_cast<uintptr_t>(residual)) & 15)) {
+    uint64_t dims[2] = {(uint64_t)N, (uint64_t)M}, strides[1] = {(uint64_t)ldc * 2};
+    uint32_t box[2] = {32, 32};
+    r = make_tmap_bf16(&p.out_map, out, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (r) return r;
+    if (preact_out) {
+      r = make_tmap_bf16(&p.pre_map, preact_out, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (r) return r;
+    }
+    epi = 1;
+  }
+  return launch_gemm(p, BN, 64, a_mn_major != 0, b_mn_major != 0, (cudaStream_t)stream, epi);
 }
 
 extern "C" int passl_b200_gemm_stats_rows(void) { return 4 * num_sms(); }
