@@ -86,14 +86,18 @@ struct GemmParams {
   int res_iters;
   // EPI = 1 (plain row-major bf16 outputs of the linear layers): 32 x 32 output boxes leave through TMA stores
   CUtensorMap out_map, pre_map;
+  // the epilogue's operand tile (gate operand / residual) of a whole output tile, requested into L2 by the producer one tile
+  // ahead of the epilogue (box BN x 128): the epilogue's own one-chunk-ahead register prefetch then only sees L2 latency
+  CUtensorMap tile_map;
+  int tile_prefetch;
   int dbg;              // developer perf experiments (PASSL_B200_EPI_DEBUG): 1 skip stats, 2 skip global stores, 4 skip staging
 };
 
-template <int BN, int BK, bool A_MN, bool B_MN, int EPI = 0>
+template <int BN, int BK, bool A_MN, bool B_MN, int EPI = 0, int CG = 1>
 struct GemmSmem {
   static constexpr int BM = 128;
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2 / CG;   // CTA pair (CG = 2): each CTA holds BN / 2 rows of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BUDGET = 196 * 1024;
   static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
@@ -155,12 +159,27 @@ __device__ __forceinline__ void act_gelu8(float* f) {
   for (int k = 0; k < 8; ++k) f[k] *= ph[k];
 }
 __device__ __forceinline__ float act_quickgelu(float v) { return v / (1.f + __expf(-1.702f * v)); }
-// d/da of the activation at the saved pre-activation a
+// f *= d/da gelu(a) at the saved pre-activation a.  With u = |a| sqrt(log2(e) / 2), e = 2^(-u^2) = exp(-a^2 / 2) and the 3-term
+// A&S 7.1.25 form of erfc (|error| < 2.5e-5; the gate is exact to 1.1e-5, checked against erf on [-8, 8]):
+//   s = gelu'(-|a|) = Phi(-|a|) - |a| phi(a) = e * (t (a1 + t (a2 + a3 t)) / 2 - u / sqrt(pi log2 e)),   t = 1 / (1 + p u)
+//   gelu'(a) = a < 0 ? s : 1 - s            (gelu'(a) + gelu'(-a) = 1)
+// 11 FMA-pipe instructions + 2 MUFU per element; the epilogue of fc2's dgrad is issue-bound on this arithmetic.
 __device__ __forceinline__ void gate_gelu8(float* f, const float* a) {
-  float ph[8], e[8];
-  gelu_phi8(a, ph, e);
+  float t[8], e[8], u[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) f[k] *= fmaf(a[k] * 0.3989422804014327f, e[k], ph[k]);
+  for (int k = 0; k < 8; ++k) u[k] = fabsf(a[k]) * 0.8493218002880191f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(t[k]) : "f"(fmaf(0.39169196791136207f, u[k], 1.f)));
+#pragma unroll
+  for (int k = 0; k < 8; ++k) asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[k]) : "f"(-(u[k] * u[k])));
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float y = fmaf(0.5f * 0.7478556f, t[k], 0.5f * -0.0958798f);
+    y = fmaf(y, t[k], 0.5f * 0.3480242f);
+    const float w = fmaf(-0.46971863934982566f, u[k], y * t[k]);
+    const float fs = f[k] * (w * e[k]);
+    f[k] = a[k] < 0.f ? fs : f[k] - fs;
+  }
 }
 __device__ __forceinline__ float gate_quickgelu(float a) {
   const float sg = 1.f / (1.f + __expf(-1.702f * a));
@@ -191,35 +210,49 @@ __device__ __forceinline__ void apply_gate8(float* f, const uint4& u) {
 // Issue the TMA loads of one pipeline stage for one operand.
 //   row_blk : index of the 128-row (A) / BN-row (B) block, or patch index in PATCH_K mode
 //   kit     : pipeline iteration
-template <int ROWS, int BK>
+template <int CG>
+__device__ __forceinline__ void tma2(void* d, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  if constexpr (CG == 2) tma_load_2d_pair(d, m, bar, c0, c1);
+  else tma_load_2d(d, m, bar, c0, c1);
+}
+template <int CG>
+__device__ __forceinline__ void tma4(void* d, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  if constexpr (CG == 2) tma_load_4d_pair(d, m, bar, c0, c1, c2, c3);
+  else tma_load_4d(d, m, bar, c0, c1, c2, c3);
+}
+
+template <int ROWS, int BK, int CG = 1>
 __device__ __forceinline__ void issue_operand_load(const GemmOperand& op, const PatchGeom& g, uint8_t* dst,
                                                    uint64_t* bar, int row0, int patch_idx, int tap_fixed,
                                                    int kit) {
   if (op.mode == OP_MAT_K) {
-    tma_load_2d(dst, &op.maps[0], bar, kit * BK, row0);
+    tma2<CG>(dst, &op.maps[0], bar, kit * BK, row0);
   } else if (op.mode == OP_MAT_MN) {
 #pragma unroll
-    for (int j = 0; j < ROWS / 64; ++j) tma_load_2d(dst + j * (BK * 128), &op.maps[0], bar, row0 + 64 * j, kit * BK);
+    for (int j = 0; j < ROWS / 64; ++j) tma2<CG>(dst + j * (BK * 128), &op.maps[0], bar, row0 + 64 * j, kit * BK);
   } else if (op.mode == OP_PATCH_K) {
     int tap = kit / op.cchunks;
     int cc = kit - tap * op.cchunks;
     int n0, h0, w0;
     decode_patch(g, patch_idx, n0, h0, w0);
-    tma_load_4d(dst, &op.maps[op.map[tap]], bar, cc * 64, w0 + op.dw[tap], h0 + op.dh[tap], n0);
+    tma4<CG>(dst, &op.maps[op.map[tap]], bar, cc * 64, w0 + op.dw[tap], h0 + op.dh[tap], n0);
   } else {  // OP_PATCH_MN: K = pixels of patch `kit`, rows = channels starting at row0
     int n0, h0, w0;
     decode_patch(g, kit, n0, h0, w0);
     int tap = tap_fixed;
 #pragma unroll
     for (int j = 0; j < ROWS / 64; ++j)
-      tma_load_4d(dst + j * (BK * 128), &op.maps[op.map[tap]], bar, row0 + 64 * j, w0 + op.dw[tap],
-                  h0 + op.dh[tap], n0);
+      tma4<CG>(dst + j * (BK * 128), &op.maps[op.map[tap]], bar, row0 + 64 * j, w0 + op.dw[tap], h0 + op.dh[tap], n0);
   }
 }
 
-template <int BN, int BK, bool A_MN, bool B_MN, int EPI = 0>
+// CG = 2: the kernel runs as clusters of two CTAs that share one 256 x BN tile (tcgen05 cta_group::2): each CTA loads its own 128
+// rows of A and HALF of the B tile, CTA rank 0 issues MMAs of M = 256 that read both shared memories and write both TMEMs, each
+// CTA runs the epilogue of its own 128 rows.  Per MMA flop the pair pulls 2/3 of the bytes from L2 that two independent CTAs
+// would (the 128 x 256 tile of one CTA needs 96 B/clk/SM at full MMA rate, above what the L2 delivers: DESIGN.md 3.2).
+template <int BN, int BK, bool A_MN, bool B_MN, int EPI = 0, int CG = 1>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
-  using S = GemmSmem<BN, BK, A_MN, B_MN, EPI>;
+  using S = GemmSmem<BN, BK, A_MN, B_MN, EPI, CG>;
   constexpr int STAGES = S::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -232,7 +265,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
-  const int total_tiles = p.m_blocks * p.n_blocks * p.splits;
+  // tile = (row block [pair], column block, split); a CTA pair walks the same tile sequence, CTA rank r takes row block 2 * pm + r
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const int total_tiles = (CG == 2 ? (p.m_blocks + 1) / 2 : p.m_blocks) * p.n_blocks * p.splits;
+  const int tile_first = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   // PATCH_MN stages contain rows no TMA box ever writes (K padding) -> must be zero, not garbage.
   if (p.a.mode == OP_PATCH_MN || p.b.mode == OP_PATCH_MN) {
@@ -249,13 +286,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], kEpiWarps);
+      mbar_init(&tmem_empty[i], kEpiWarps * CG);   // pair: the issuing CTA waits for the epilogue warps of both CTAs
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, S::TMEM_COLS);
+  if (warp == 1) {
+    if constexpr (CG == 2) tmem_alloc_pair(tmem_ptr, S::TMEM_COLS);
+    else tmem_alloc(tmem_ptr, S::TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();     // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -282,11 +323,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       };
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
         int split = tile % p.splits;
         int rest = tile / p.splits;
         int n_blk = rest % p.n_blocks;
-        int m_blk = rest / p.n_blocks;
+        int m_blk = (rest / p.n_blocks) * CG + (int)cta_rank;
+        if (EPI == 1 && p.tile_prefetch && elect_one())
+          asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(&p.tile_map)),
+                       "r"(n_blk * BN), "r"(m_blk * 128)
+                       : "memory");
         int k_begin = (int)(((long long)split * p.k_iters) / p.splits);
         int k_end = (int)(((long long)(split + 1) * p.k_iters) / p.splits);
         int b_row0 = n_blk * BN, b_tap = 0;
@@ -294,7 +339,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           b_tap = n_blk / p.n_blocks_per_tap;
           b_row0 = (n_blk - b_tap * p.n_blocks_per_tap) * BN;
         }
-        const uint32_t tx = (uint32_t)(p.a.tx_bytes + p.b.tx_bytes);
+        if constexpr (CG == 2) b_row0 += (int)cta_rank * (BN / 2);      // this CTA's half of the B tile
+        // bytes one stage receives: in a pair both CTAs' loads are counted on the barrier of CTA 0, which alone posts the expectation
+        const uint32_t tx = (uint32_t)(p.a.tx_bytes + p.b.tx_bytes) * CG;
+        const bool post_tx = CG == 1 || cta_rank == 0;
         if (p.a.mode == OP_PATCH_K && p.b.mode == OP_MAT_K) {
           // implicit-GEMM convolution fast path: patch decoded once per tile, (tap, chunk) advanced with counters —
           // this single thread's instruction latency is on the critical path of every pipeline stage
@@ -305,9 +353,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * S::STAGE_BYTES;
             if (elect_one()) {
-              mbar_arrive_expect_tx(&full_bar[stage], tx);
-              tma_load_4d(sa, &p.a.maps[p.a.map[tap]], &full_bar[stage], cc * 64, w0 + p.a.dw[tap], h0 + p.a.dh[tap], n0);
-              tma_load_2d(sa + S::A_BYTES, &p.b.maps[0], &full_bar[stage], kit * BK, b_row0);
+              if (post_tx) mbar_arrive_expect_tx(&full_bar[stage], tx);
+              tma4<CG>(sa, &p.a.maps[p.a.map[tap]], &full_bar[stage], cc * 64, w0 + p.a.dw[tap], h0 + p.a.dh[tap], n0);
+              tma2<CG>(sa + S::A_BYTES, &p.b.maps[0], &full_bar[stage], kit * BK, b_row0);
             }
             __syncwarp();
             if (++cc == p.a.cchunks) { cc = 0; ++tap; }
@@ -318,9 +366,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * S::STAGE_BYTES;
             if (elect_one()) {
-              mbar_arrive_expect_tx(&full_bar[stage], tx);
-              tma_load_2d(sa, &p.a.maps[0], &full_bar[stage], kit * BK, m_blk * 128);
-              tma_load_2d(sa + S::A_BYTES, &p.b.maps[0], &full_bar[stage], kit * BK, b_row0);
+              if (post_tx) mbar_arrive_expect_tx(&full_bar[stage], tx);
+              tma2<CG>(sa, &p.a.maps[0], &full_bar[stage], kit * BK, m_blk * 128);
+              tma2<CG>(sa + S::A_BYTES, &p.b.maps[0], &full_bar[stage], kit * BK, b_row0);
             }
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -331,9 +379,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             uint8_t* sa = smem + stage * S::STAGE_BYTES;
             uint8_t* sb = sa + S::A_BYTES;
             if (elect_one()) {
-              mbar_arrive_expect_tx(&full_bar[stage], tx);
-              issue_operand_load<128, BK>(p.a, p.geom, sa, &full_bar[stage], m_blk * 128, m_blk, 0, kit);
-              issue_operand_load<BN, BK>(p.b, p.geom, sb, &full_bar[stage], b_row0, n_blk, b_tap, kit);
+              if (post_tx) mbar_arrive_expect_tx(&full_bar[stage], tx);
+              issue_operand_load<128, BK, CG>(p.a, p.geom, sa, &full_bar[stage], m_blk * 128, m_blk, 0, kit);
+              issue_operand_load<BN / CG, BK, CG>(p.b, p.geom, sb, &full_bar[stage], b_row0, n_blk, b_tap, kit);
             }
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -343,9 +391,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       }
     }
   } else if (warp == 1) {
-    {
-      // ================= MMA issuer =================
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN, A_MN, B_MN);
+    if (CG == 1 || cta_rank == 0) {
+      // ================= MMA issuer (CTA 0 of a pair) =================
+      constexpr uint32_t idesc = make_idesc_bf16(128 * CG, BN, A_MN, B_MN);
+      auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t accum) {
+        if constexpr (CG == 2) umma_bf16_pair(d, a, b, id, accum);
+        else umma_bf16(d, a, b, id, accum);
+      };
+      auto commit = [](uint64_t* bar) {
+        if constexpr (CG == 2) umma_commit_pair(bar);
+        else umma_commit(bar);
+      };
       // descriptor of stage 0 / k-step 0; later stages and k-steps only add to the 14-bit start-address field
       const uint32_t smem0 = smem_u32(smem);
       const uint64_t da0 = A_MN ? make_smem_desc_sw128(smem0, BK * 128, 1024) : make_smem_desc_sw128(smem0, 16, 1024);
@@ -361,7 +417,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++it) {
         int split = tile % p.splits;
         int k_begin = (int)(((long long)split * p.k_iters) / p.splits);
         int k_end = (int)(((long long)(split + 1) * p.k_iters) / p.splits);
@@ -380,13 +436,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             if (p.k_steps == KSTEPS_FULL) {
 #pragma unroll
               for (int k = 0; k < KSTEPS_FULL; ++k)
-                umma_bf16(d_tmem, da + k * kStepA, db + k * kStepB, idesc, (kit > k_begin || k > 0) ? 1u : 0u);
+                mma(d_tmem, da + k * kStepA, db + k * kStepB, idesc, (kit > k_begin || k > 0) ? 1u : 0u);
             } else {
               for (int k = 0; k < p.k_steps; ++k)
-                umma_bf16(d_tmem, da + k * kStepA, db + k * kStepB, idesc, (kit > k_begin || k > 0) ? 1u : 0u);
+                mma(d_tmem, da + k * kStepA, db + k * kStepB, idesc, (kit > k_begin || k > 0) ? 1u : 0u);
             }
-            umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
-            if (kit == k_end - 1 && p.res_iters == 0) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+            commit(&empty_bar[stage]);  // smem slot free (in both CTAs of a pair) once these MMAs retire
+            if (kit == k_end - 1 && p.res_iters == 0) commit(&tmem_full[acc]);  // accumulator complete -> epilogue
           }
           __syncwarp();
           if (++stage == STAGES) {
@@ -424,15 +480,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     const uint32_t half = e >> 2;
     const uint32_t stg0 = smem_u32(epi_stage + e * 4096);
     const uint32_t swz = (lane >> 1) & 3u;                     // SWIZZLE_64B: 16-byte slot ^= (row >> 1) & 3
-    const int crow = (int)(lane >> 2), cch = (int)(lane & 3);  // row-coalesced operand loads: 8 rows x 64 B per instruction
+    const int crow = (int)(lane >> 2), cch = (int)(lane & 3);  // row-coalesced operand copies: 8 rows x 64 B per instruction
     constexpr int NCH = (BN / 64) > 0 ? (BN / 64) : 1;
-    // at most one operand tile enters the epilogue: the gate's pre-activation (aux) or a residual that could not go through the MMA
+    // at most one operand tile enters the epilogue: the gate's pre-activation (aux) or a residual that could not go through the MMA.
+    // It is copied global -> shared with cp.async (no registers, issued one chunk ahead into the second 2 KB tile of this warp;
+    // the producer has already pulled the whole 128 x BN operand tile into L2); without an operand both tiles alternate as
+    // sources of the TMA stores.
     const __nv_bfloat16* tsrc = p.aux ? p.aux : ((p.residual && p.res_iters == 0) ? p.residual : nullptr);
     const int tmode = p.aux ? p.aux_mode : 4;                  // 1 ReLU mask, 2 GELU', 3 QuickGELU', 4 add
+    const uint32_t obuf = stg0 + 2048u;
+    const uint32_t nalt = tsrc ? 0u : 1u;                      // store tiles in rotation
     uint32_t nbuf = 0;
     auto store_box = [&](const float (&f)[32], const CUtensorMap* map, int col, int row) {
-      const uint32_t buf = stg0 + (nbuf & 1u) * 2048u;
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store issued two boxes ago has read this tile
+      const uint32_t buf = stg0 + (nbuf & nalt) * 2048u;
+      // the store that last used this tile has read it (two boxes ago when the tiles alternate)
+      if (lane == 0) {
+        if (nalt) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
       __syncwarp();
 #pragma unroll
       for (int j8 = 0; j8 < 4; ++j8) {
@@ -454,39 +519,43 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       ++nbuf;
     };
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++it) {
       const int rest = tile / p.splits;
       const int n_blk = rest % p.n_blocks;
-      const int m_blk = rest / p.n_blocks;
+      const int m_blk = (rest / p.n_blocks) * CG + (int)cta_rank;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int row0 = m_blk * 128 + (int)q * 32;
       const int col0 = n_blk * BN;
-      auto load_tile = [&](int c_, uint4 (&dst)[4]) {
+      auto copy_tile = [&](int c_) {      // chunk c_ of the operand -> obuf (zero fill outside the tensor); one cp.async group
         const int col = col0 + c_ * 32 + cch * 8;
         const bool okc = (c_ < BN / 32) && (col < p.N);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int m = row0 + i * 8 + crow;
-          dst[i] = make_uint4(0u, 0u, 0u, 0u);
-          if (okc && m < p.M) dst[i] = ld_nc_v4(tsrc + (long long)m * p.ldc + col);
+          const uint32_t r_ = (uint32_t)(i * 8 + crow);
+          const int m = row0 + (int)r_;
+          const bool ok = okc && m < p.M;
+          const __nv_bfloat16* src = ok ? tsrc + (long long)m * p.ldc + col : tsrc;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(obuf + r_ * 64u + (((uint32_t)cch ^ ((r_ >> 1) & 3u)) << 4)),
+                       "l"(src), "r"(ok ? 16 : 0)
+                       : "memory");
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
       };
-      uint4 tr[4];
-      if (tsrc) load_tile((int)half, tr);
+      if (tsrc) copy_tile((int)half);
       bool released = false;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((q * 32u) << 16) + acc * BN;
+      // the accumulator is read one chunk ahead of the arithmetic
+      uint32_t v[32];
+      if ((int)half < BN / 32 && col0 + (int)half * 32 < p.N) tmem_ld_32x32(t_addr + half * 32, v);
 #pragma unroll 1
       for (int ci = 0; ci < NCH; ++ci) {
         const int c = (int)half + 2 * ci;
         if (c >= BN / 32) break;
         const int cc0 = col0 + c * 32;
         if (cc0 >= p.N) break;
-        uint32_t v[32];
-        tmem_ld_32x32(t_addr + c * 32, v);
-        // bias and the next operand tile are requested while the TMEM load is in flight
         float4 bv[8];
         if (p.bias) {
           if (cc0 + 32 <= p.N) {
@@ -500,16 +569,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             }
           }
         }
-        uint4 tn[4];
-        if (tsrc) load_tile(c + 2, tn);
         tmem_ld_wait();
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (!(ci + 1 < NCH && c + 2 < BN / 32 && cc0 + 64 < p.N)) {
+        if (ci + 1 < NCH && c + 2 < BN / 32 && cc0 + 64 < p.N) {
+          tmem_ld_32x32(t_addr + (c + 2) * 32, v);
+        } else {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          if (lane == 0) { if constexpr (CG == 2) mbar_arrive_leader(&tmem_empty[acc]); else mbar_arrive(&tmem_empty[acc]); }
           released = true;
         }
         if (p.bias) {
@@ -530,40 +599,32 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           for (int j = 0; j < 32; ++j) f[j] = act_quickgelu(f[j]);
         }
         if (tsrc) {
-          // transpose the row-coalesced operand tile through the staging tile the next store will use
-          const uint32_t buf = stg0 + (nbuf & 1u) * 2048u;
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint32_t r_ = (uint32_t)(i * 8 + crow);
-            st_shared_v4(buf + r_ * 64u + (((uint32_t)cch ^ ((r_ >> 1) & 3u)) << 4), tr[i]);
-          }
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
           __syncwarp();
           if (tmode == 1) {
 #pragma unroll
-            for (int j8 = 0; j8 < 4; ++j8) apply_gate8<1>(f + j8 * 8, ld_shared_v4(buf + lane * 64u + ((j8 ^ swz) << 4)));
+            for (int j8 = 0; j8 < 4; ++j8) apply_gate8<1>(f + j8 * 8, ld_shared_v4(obuf + lane * 64u + ((j8 ^ swz) << 4)));
           } else if (tmode == 2) {
 #pragma unroll
-            for (int j8 = 0; j8 < 4; ++j8) apply_gate8<2>(f + j8 * 8, ld_shared_v4(buf + lane * 64u + ((j8 ^ swz) << 4)));
+            for (int j8 = 0; j8 < 4; ++j8) apply_gate8<2>(f + j8 * 8, ld_shared_v4(obuf + lane * 64u + ((j8 ^ swz) << 4)));
           } else if (tmode == 3) {
 #pragma unroll
-            for (int j8 = 0; j8 < 4; ++j8) apply_gate8<3>(f + j8 * 8, ld_shared_v4(buf + lane * 64u + ((j8 ^ swz) << 4)));
+            for (int j8 = 0; j8 < 4; ++j8) apply_gate8<3>(f + j8 * 8, ld_shared_v4(obuf + lane * 64u + ((j8 ^ swz) << 4)));
           } else {
 #pragma unroll
-            for (int j8 = 0; j8 < 4; ++j8) apply_gate8<4>(f + j8 * 8, ld_shared_v4(buf + lane * 64u + ((j8 ^ swz) << 4)));
+            for (int j8 = 0; j8 < 4; ++j8) apply_gate8<4>(f + j8 * 8, ld_shared_v4(obuf + lane * 64u + ((j8 ^ swz) << 4)));
           }
           __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 4; ++i) tr[i] = tn[i];
+          if (ci + 1 < NCH) copy_tile(c + 2);       // the tile is free again: next chunk's operand
         }
         store_box(f, &p.out_map, cc0, row0);
       }
       if (!released) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) { if constexpr (CG == 2) mbar_arrive_leader(&tmem_empty[acc]); else mbar_arrive(&tmem_empty[acc]); }
       }
+      if (tsrc) asm volatile("cp.async.wait_group 0;" ::: "memory");   // (a zero-fill group of a chunk beyond the tensor)
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the staging tiles must outlive their stores
     __syncwarp();
@@ -605,10 +666,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     };
     int prev_nblk = -1;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++it) {
       int rest = tile / p.splits;
       int n_blk = rest % p.n_blocks;
-      int m_blk = rest / p.n_blocks;
+      int m_blk = (rest / p.n_blocks) * CG + (int)cta_rank;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
 
@@ -713,7 +774,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           // that was this warp's last read of the accumulator: hand the TMEM buffer back before the arithmetic and the stores
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          if (lane == 0) { if constexpr (CG == 2) mbar_arrive_leader(&tmem_empty[acc]); else mbar_arrive(&tmem_empty[acc]); }
           released = true;
         }
         if (p.bias) {                               // columns outside the tensor hold 0
@@ -886,7 +947,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       if (!released) {       // no chunk of this warp inside the tensor
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) { if constexpr (CG == 2) mbar_arrive_leader(&tmem_empty[acc]); else mbar_arrive(&tmem_empty[acc]); }
       }
     }
     if (do_stats && prev_nblk >= 0) flush_stats(prev_nblk);
@@ -894,9 +955,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();     // neither CTA leaves while the other may still read its shared memory / signal its barriers
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_base, S::TMEM_COLS);
+    if constexpr (CG == 2) tmem_dealloc_pair(tmem_base, S::TMEM_COLS);
+    else tmem_dealloc(tmem_base, S::TMEM_COLS);
   }
 }
 

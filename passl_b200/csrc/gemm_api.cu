@@ -53,17 +53,18 @@ static int setup_residual_mma(GemmParams& p, const void* residual, long long ldc
   return PB_OK;
 }
 
-template <int BN, int BK, bool A_MN, bool B_MN, int EPI = 0>
+template <int BN, int BK, bool A_MN, bool B_MN, int EPI = 0, int CG = 1>
 static int launch_gemm_t(const GemmParams& p, cudaStream_t st) {
-  using S = GemmSmem<BN, BK, A_MN, B_MN, EPI>;
-  auto kern = gemm_tcgen05_kernel<BN, BK, A_MN, B_MN, EPI>;
+  using S = GemmSmem<BN, BK, A_MN, B_MN, EPI, CG>;
+  auto kern = gemm_tcgen05_kernel<BN, BK, A_MN, B_MN, EPI, CG>;
   static bool attr_set = false;
   if (!attr_set) {
     PB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     attr_set = true;
   }
-  int tiles = p.m_blocks * p.n_blocks * p.splits;
-  int grid = tiles < num_sms() ? tiles : num_sms();
+  int tiles = (CG == 2 ? (p.m_blocks + 1) / 2 : p.m_blocks) * p.n_blocks * p.splits;
+  int slots = num_sms() / CG;
+  int grid = (tiles < slots ? tiles : slots) * CG;
   if (grid <= 0) return PB_OK;
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("PASSL_B200_EPI_DEBUG"); dbg = e ? atoi(e) : 0; }
@@ -72,12 +73,41 @@ static int launch_gemm_t(const GemmParams& p, cudaStream_t st) {
     if (p.out_fp32 || p.n_blocks_per_tap > 0 || p.splits != 1) return PB_ERR_UNSUPPORTED;
     PB_CUDA_CHECK(cudaMemsetAsync(p.col_sum, 0, (size_t)num_sms() * 4 * 2 * p.N * sizeof(float), st));
   }
+  if (CG == 2) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = S::TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    PB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
+    return PB_OK;
+  }
   kern<<<grid, kGemmThreads, S::TOTAL, st>>>(p);
   PB_LAUNCH_CHECK();
   return PB_OK;
 }
 
-static int launch_gemm(const GemmParams& p, int BN, int BK, bool a_mn, bool b_mn, cudaStream_t st, int epi = 0) {
+// CTA pairs (cta_group::2, gemm.cuh) for the big K-major-A tiles; PASSL_B200_GEMM_PAIR=0 keeps every launch single-CTA
+static bool pair_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PASSL_B200_GEMM_PAIR"); v = (e && !atoi(e)) ? 0 : 1; }
+  return v != 0;
+}
+static bool pair_eligible(const GemmParams& p, int BN, int BK, bool a_mn) {
+  return pair_enabled() && BN == 256 && BK == 64 && !a_mn && p.res_iters == 0 && p.a.mode != OP_PATCH_MN && p.b.mode != OP_PATCH_MN &&
+         (long long)((p.m_blocks + 1) / 2) * p.n_blocks * p.splits >= num_sms() / 2;
+}
+
+static int launch_gemm(const GemmParams& p, int BN, int BK, bool a_mn, bool b_mn, cudaStream_t st, int epi = 0, int cg = 1) {
+  if (cg == 2 && BN == 256 && BK == 64 && !a_mn) {
+    if (epi == 1) return b_mn ? launch_gemm_t<256, 64, false, true, 1, 2>(p, st) : launch_gemm_t<256, 64, false, false, 1, 2>(p, st);
+    return b_mn ? launch_gemm_t<256, 64, false, true, 0, 2>(p, st) : launch_gemm_t<256, 64, false, false, 0, 2>(p, st);
+  }
 #define PB_DISPATCH(bn)                                                                 \
   if (BN == bn) {                                                                       \
     if (BK == 128) return launch_gemm_t<bn, 128, true, true>(p, st);                    \
@@ -205,14 +235,18 @@ extern "C" int passl_b200_gemm_bf16_ex(const void* A, const void* B, void* out, 
   p.splits = splits;
   int r = fill_mat_operand(p.a, A, a_mn_major != 0, M, K, lda, 128, 64);
   if (r) return r;
-  r = fill_mat_operand(p.b, B, b_mn_major != 0, N, K, ldb, BN, 64);
+  // CTA pairs: each CTA loads half of the B tile (its own box of BN / 2 rows); the residual then enters through the epilogue
+  const int cg = pair_eligible(p, BN, 64, a_mn_major != 0) ? 2 : 1;
+  r = fill_mat_operand(p.b, B, b_mn_major != 0, N, K, ldb, BN / cg, 64);
   if (r) return r;
   set_epilogue(p, out, ldc, out_fp32, atomic_add, bias, residual, act, alpha, col_sum, col_sqsum);
   p.aux = reinterpret_cast<const __nv_bfloat16*>(aux);
   p.aux_mode = aux_mode;
   p.preact = reinterpret_cast<__nv_bfloat16*>(preact_out);
-  r = setup_residual_mma(p, residual, ldc, (cudaStream_t)stream);
-  if (r) return r;
+  if (cg == 1) {
+    r = setup_residual_mma(p, residual, ldc, (cudaStream_t)stream);
+    if (r) return r;
+  }
   // linear-layer epilogue (EPI 1, TMA stores): plain row-major bf16 output, K-major A, no statistics / scaling, at most one
   // operand tile (gate operand or a residual that does not go through the MMA)
   static int lean = -1;
@@ -229,9 +263,14 @@ extern "C" int passl_b200_gemm_bf16_ex(const void* A, const void* B, void* out, 
       r = make_tmap_bf16(&p.pre_map, preact_out, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
       if (r) return r;
     }
+    const void* tsrc = aux ? aux : (res_in_epilogue ? residual : nullptr);
+    if (tsrc) {
+      uint32_t tbox[2] = {(uint32_t)(BN < N ? BN : N), 128};
+      if (tbox[0] <= 256 && make_tmap_bf16(&p.tile_map, tsrc, 2, dims, strides, tbox, CU_TENSOR_MAP_SWIZZLE_NONE) == PB_OK) p.tile_prefetch = 1;
+    }
     epi = 1;
   }
-  return launch_gemm(p, BN, 64, a_mn_major != 0, b_mn_major != 0, (cudaStream_t)stream, epi);
+  return launch_gemm(p, BN, 64, a_mn_major != 0, b_mn_major != 0, (cudaStream_t)stream, epi, cg);
 }
 
 extern "C" int passl_b200_gemm_stats_rows(void) { return 4 * num_sms(); }
