@@ -99,8 +99,12 @@ static bool pair_enabled() {
   return v != 0;
 }
 static bool pair_eligible(const GemmParams& p, int BN, int BK, bool a_mn) {
+  // k_iters: a tile with a short K loop (1x1 convolutions on 64..256 channels) is bound by its epilogue / HBM, where the pair
+  // only couples two epilogues to one MMA stream (PASSL_B200_GEMM_PAIR_MINK overrides the threshold)
+  static int mink = -1;
+  if (mink < 0) { const char* e = getenv("PASSL_B200_GEMM_PAIR_MINK"); mink = e ? atoi(e) : 8; }
   return pair_enabled() && BN == 256 && BK == 64 && !a_mn && p.res_iters == 0 && p.a.mode != OP_PATCH_MN && p.b.mode != OP_PATCH_MN &&
-         (long long)((p.m_blocks + 1) / 2) * p.n_blocks * p.splits >= num_sms() / 2;
+         p.k_iters >= mink && (long long)((p.m_blocks + 1) / 2) * p.n_blocks * p.splits >= num_sms() / 2;
 }
 
 static int launch_gemm(const GemmParams& p, int BN, int BK, bool a_mn, bool b_mn, cudaStream_t st, int epi = 0, int cg = 1) {
@@ -236,7 +240,11 @@ extern "C" int passl_b200_gemm_bf16_ex(const void* A, const void* B, void* out, 
   int r = fill_mat_operand(p.a, A, a_mn_major != 0, M, K, lda, 128, 64);
   if (r) return r;
   // CTA pairs: each CTA loads half of the B tile (its own box of BN / 2 rows); the residual then enters through the epilogue
-  const int cg = pair_eligible(p, BN, 64, a_mn_major != 0) ? 2 : 1;
+  // not for epilogue-bound launches (GELU / gate arithmetic: the pair couples two epilogues to one MMA stream, measured 5 % slower),
+  // nor when a residual could ride the MMA of a short K loop instead of the epilogue (proj of ViT-B: 999 vs 917 TF/s)
+  const bool heavy_epi = act == ACT_GELU || act == ACT_QUICKGELU || (aux && aux_mode >= 2);
+  const bool short_k_residual = residual && K < 1536;
+  const int cg = (!heavy_epi && !short_k_residual && pair_eligible(p, BN, 64, a_mn_major != 0)) ? 2 : 1;
   r = fill_mat_operand(p.b, B, b_mn_major != 0, N, K, ldb, BN / cg, 64);
   if (r) return r;
   set_epilogue(p, out, ldc, out_fp32, atomic_add, bias, residual, act, alpha, col_sum, col_sqsum);
@@ -312,11 +320,12 @@ static int conv_fwd_impl(const void* x, const void* w, void* out, int N, int H, 
   if (rc) return rc;
   p.k_iters = R * S * p.a.cchunks;
   p.k_steps = 4;
-  rc = fill_mat_operand(p.b, w, false, Cout, (long long)R * S * Cin, (long long)R * S * Cin, BN, 64);
+  const int cg = pair_eligible(p, BN, 64, false) ? 2 : 1;
+  rc = fill_mat_operand(p.b, w, false, Cout, (long long)R * S * Cin, (long long)R * S * Cin, BN / cg, 64);
   if (rc) return rc;
   set_epilogue(p, out, Cout, 0, 0, bias, residual, act, 1.f, col_sum, col_sqsum);
   p.out_pixel = 1; p.OH = Ho; p.OW = Wo; p.osh = 1; p.osw = 1; p.oh0 = 0; p.ow0 = 0;
-  return launch_gemm(p, BN, 64, false, false, (cudaStream_t)stream);
+  return launch_gemm(p, BN, 64, false, false, (cudaStream_t)stream, 0, cg);
 }
 
 extern "C" int passl_b200_conv2d_fwd_bf16(const void* x, const void* w, void* out, int N, int H, int W, int Cin,
@@ -441,11 +450,12 @@ extern "C" int passl_b200_conv2d_dgrad_bf16(const void* dy, const void* w, void*
     if (rc) return rc;
     p.k_iters = k.ntaps * p.a.cchunks;
     p.k_steps = 4;
-    rc = fill_mat_operand(p.b, wt, false, Cin, (long long)k.ntaps * Cout, (long long)k.ntaps * Cout, BN, 64);
+    const int cg = pair_eligible(p, BN, 64, false) ? 2 : 1;
+    rc = fill_mat_operand(p.b, wt, false, Cin, (long long)k.ntaps * Cout, (long long)k.ntaps * Cout, BN / cg, 64);
     if (rc) return rc;
     set_epilogue(p, dx, Cin, 0, 0, nullptr, accumulate ? dx : nullptr, ACT_NONE, 1.f, nullptr, nullptr);
     p.out_pixel = 1; p.OH = H; p.OW = W; p.osh = stride; p.osw = stride; p.oh0 = k.a; p.ow0 = k.b;
-    rc = launch_gemm(p, BN, 64, false, false, st);
+    rc = launch_gemm(p, BN, 64, false, false, st, 0, cg);
     if (rc) return rc;
     wt += (size_t)Cin * k.ntaps * Cout;
   }

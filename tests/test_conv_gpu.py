@@ -19,6 +19,11 @@ CASES = [
     (2, 56, 56, 64, 256, 1, 1, 0),
     (2, 14, 14, 1024, 256, 1, 1, 0),
     (1, 112, 112, 64, 64, 3, 1, 1),
+    # enough 256-wide tiles for the CTA-pair path (gemm.cuh CG = 2): 3x3, 3x3 stride 2 and 1x1, odd number of pixel patches
+    (19, 56, 56, 64, 256, 3, 1, 1),
+    (25, 28, 28, 256, 256, 3, 1, 1),
+    (100, 28, 28, 256, 256, 3, 2, 1),
+    (21, 56, 56, 256, 512, 1, 1, 0),
 ]
 
 

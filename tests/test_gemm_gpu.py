@@ -75,3 +75,104 @@ def test_gemm_splitk_atomic_and_colstats():
     cs, cq = part[:, 0].sum(0), part[:, 1].sum(0)
     assert torch.allclose(cs, o.sum(0), rtol=1e-3, atol=1e-1), (cs - o.sum(0)).abs().max()
     assert torch.allclose(cq, (o * o).sum(0), rtol=1e-3, atol=1.0), (cq - (o * o).sum(0)).abs().max()
+
+
+def _gelu_grad(u):
+    u = u.double()
+    return (0.5 * (1 + torch.erf(u / 2 ** 0.5)) + u * torch.exp(-u * u / 2) / (2 * torch.pi) ** 0.5).float()
+
+
+@pytest.mark.parametrize("M,N,K", [(777, 200, 136), (128, 32, 64), (1000, 2304, 768), (33, 3072, 192)])
+def test_gemm_linear_epilogue_tma_store(M, N, K):
+    """bf16 row-major outputs of the linear layers (gemm.cuh EPI 1: swizzled 32 x 32 boxes leave through TMA stores, ragged edges
+    are clipped by the tensor map): bias, GELU + saved pre-activation, gates from a saved pre-activation, residual."""
+    from passl_b200 import kernels as K_
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda").bfloat16()
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    y = a.float() @ w.float().t()
+    out = K_.gemm(a, w, bias=bias)
+    bad, msg = _err_report(out, y + bias, "bias")
+    assert out.dtype == torch.bfloat16 and not bad, msg
+    u = torch.full((M, N), 7.0, device="cuda", dtype=torch.bfloat16)
+    out = K_.gemm(a, w, bias=bias, act="gelu", preact_out=u)
+    bad, msg = _err_report(u, y + bias, "pre-activation")
+    assert not bad, msg
+    bad, msg = _err_report(out, torch.nn.functional.gelu(y + bias), "gelu")
+    assert not bad, msg
+    out = K_.gemm(a, w, bias=bias, act="quick_gelu")
+    bad, msg = _err_report(out, (y + bias) * torch.sigmoid(1.702 * (y + bias)), "quick_gelu")
+    assert not bad, msg
+    res = torch.randn(M, N, device="cuda").bfloat16()
+    out = K_.gemm(a, w, bias=bias, residual=res, act="relu")          # residual through the epilogue (an activation precedes it)
+    bad, msg = _err_report(out, torch.relu(y + bias) + res.float(), "relu + residual")
+    assert not bad, msg
+    out = K_.gemm(a, w, bias=bias, residual=res)                      # residual through the MMA when the shape allows
+    bad, msg = _err_report(out, y + bias + res.float(), "residual")
+    assert not bad, msg
+    aux = torch.randn(M, N, device="cuda").bfloat16()
+    for mode, gate in [("relu_mask", (aux.float() > 0).float()), ("gelu_grad", _gelu_grad(aux)),
+                       ("quick_gelu_grad", (lambda s: s * (1 + 1.702 * aux.float() * (1 - s)))(torch.sigmoid(1.702 * aux.float())))]:
+        out = K_.gemm(a, w, aux=aux, aux_mode_name=mode)
+        bad, msg = _err_report(out, y * gate, mode)
+        assert not bad, msg
+    # dgrad form (B given as [K, N]) with the GELU' gate, as fc2's backward issues it
+    wt = w.t().contiguous()
+    out = K_.gemm(a, wt, b_t=True, aux=aux, aux_mode_name="gelu_grad")
+    bad, msg = _err_report(out, y * _gelu_grad(aux), "gelu_grad, b_t")
+    assert not bad, msg
+
+
+def test_gelu_gate_arithmetic_is_exact_to_bf16():
+    """The A&S erfc forms in the epilogue against erf in double: the gate / activation error must vanish under bf16 rounding."""
+    from passl_b200 import kernels as K_
+    M, N, K = 256, 256, 64
+    a = torch.zeros(M, K, device="cuda", dtype=torch.bfloat16)
+    a[:, 0] = 1.0
+    w = torch.zeros(N, K, device="cuda", dtype=torch.bfloat16)
+    w[:, 0] = 1.0                                                  # a @ w.T = 1 everywhere: out = gate(aux)
+    aux = torch.linspace(-8, 8, M * N, device="cuda").view(M, N).bfloat16()
+    out = K_.gemm(a, w, aux=aux, aux_mode_name="gelu_grad").float()
+    ref = _gelu_grad(aux)
+    assert (out - ref).abs().max().item() < 6e-3                   # bf16 rounding of values in [-0.13, 1.13] is <= 3.9e-3
+    assert (out - ref.bfloat16().float()).abs().mean().item() < 2e-4
+    bias = torch.linspace(-6, 6, N, device="cuda")                 # activation of a row of pre-activations
+    a0 = torch.zeros(M, K, device="cuda", dtype=torch.bfloat16)
+    out = K_.gemm(a0, w, bias=bias, act="gelu").float()
+    ref = torch.nn.functional.gelu(bias.double()).float().expand(M, N)
+    assert bool(((out - ref).abs() <= 2 ** -8 * ref.abs() + 2e-5).all()), (out - ref).abs().max().item()
+
+
+@pytest.mark.parametrize("b_t", [False, True])
+def test_gemm_cta_pair(b_t):
+    """Shapes big enough for the CTA-pair path (cluster of 2, tcgen05 cta_group::2, gemm.cuh CG = 2): odd number of 128-row
+    blocks (the last pair has one CTA outside the tensor), fp32 and bf16 outputs, bias, column statistics, residual."""
+    from passl_b200 import kernels as K_
+    torch.manual_seed(5)
+    M, N, K = 128 * 150 + 40, 512, 512
+    a = torch.randn(M, K, device="cuda").bfloat16()
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
+    ww = w.t().contiguous() if b_t else w
+    y = a.float() @ w.float().t()
+    out = K_.gemm(a, ww, b_t=b_t, out_dtype=torch.float32)
+    bad, msg = _err_report(out, y, "pair fp32")
+    assert not bad, msg
+    bias = torch.randn(N, device="cuda")
+    out = K_.gemm(a, ww, b_t=b_t, bias=bias)
+    bad, msg = _err_report(out, y + bias, "pair bf16 + bias")
+    assert not bad, msg
+    part = K_.stats_buffer(N, "cuda")
+    out2 = K_.gemm(a, ww, b_t=b_t, col_stats=part)
+    o = out2.float()
+    cs, cq = part[:, 0].sum(0), part[:, 1].sum(0)
+    assert torch.allclose(cs, o.sum(0), rtol=1e-3, atol=0.5), (cs - o.sum(0)).abs().max()
+    assert torch.allclose(cq, (o * o).sum(0), rtol=1e-3, atol=2.0), (cq - (o * o).sum(0)).abs().max()
+    # long K loop + residual: the pair takes the residual through the epilogue's operand tile
+    K2 = 1536
+    a2 = torch.randn(M, K2, device="cuda").bfloat16()
+    w2 = (torch.randn(N, K2, device="cuda") / K2 ** 0.5).bfloat16()
+    res = torch.randn(M, N, device="cuda").bfloat16()
+    out = K_.gemm(a2, w2.t().contiguous() if b_t else w2, b_t=b_t, bias=bias, residual=res)
+    bad, msg = _err_report(out, a2.float() @ w2.float().t() + bias + res.float(), "pair + residual")
+    assert not bad, msg
