@@ -479,7 +479,7 @@ def run_ours(args):
     #      Every rank runs the step (it contains collectives); only rank 0 reports.
     if rank == 0:
         line["clocks"] = sampler.summary()
-    rec = []
+    rec, desc = [], []
     orig = {n: getattr(K, n) for n in ("gemm", "conv2d_fwd", "conv2d_dgrad", "conv2d_wgrad")}
 
     def cost_of(name, a, kw, res):
@@ -509,6 +509,9 @@ def run_ours(args):
             r = orig[name](*a, **kw)
             e.record()
             rec.append((s, e) + cost_of(name, a, kw, r))
+            desc.append("%s %s -> %s%s" % (name, " x ".join(str(tuple(t.shape)) for t in a[:2] if torch.is_tensor(t)), tuple(r.shape),
+                                          "".join(" +" + k for k in ("bias", "residual", "aux", "preact_out", "col_stats", "act", "a_t",
+                                                                      "b_t", "accumulate") if kw.get(k) is not None and kw.get(k) is not False)))
             return r
         return f
     from passl_b200.core import streams
@@ -535,6 +538,15 @@ def run_ours(args):
             t_bind += max(fl / pk_tf, by / pk_bw) * 1e3
         tc_ms = cls["tensor"][0] + cls["hbm"][0]
         tc_flops = cls["tensor"][1] + cls["hbm"][1]
+        table = os.environ.get("PASSL_B200_BENCH_LAUNCH_TABLE")
+        if table:                                   # developer aid: one line per tcgen05 launch of the instrumented step
+            with open(table, "w") as f:
+                for (s_, e_, fl, by), d in zip(rec, desc):
+                    dt = s_.elapsed_time(e_)
+                    bind = max(fl / pk_tf, by / pk_bw) * 1e3
+                    f.write("%8.1f us  %5.2f of %s roofline  %7.1f TF/s %7.0f GB/s  %s\n" % (
+                        dt * 1e3, bind / dt if dt else 0.0, "tensor" if fl / pk_tf >= by / pk_bw else "hbm   ", fl / dt / 1e9,
+                        by / dt / 1e6, d))
         traffic_db = {}
         tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
         if os.path.exists(tp):

@@ -104,11 +104,11 @@ struct GemmSmem {
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int BAR_BYTES = 256;
   static constexpr int BIAS_BYTES = kEpiWarps * 4 * 32 * 4;              // per-warp bias slices of the current tile (4 chunks x 32 columns, fp32)
-  // EPI 0: per-warp padded staging tiles + bias slices, after the barriers.  EPI 1: per warp two dense 2 KB tiles (32 rows x
+  // EPI 0: per-warp padded staging tiles + bias slices, after the barriers.  EPI 1, 2: per warp two dense 2 KB tiles (32 rows x
   // 64 B, SWIZZLE_64B, the source of the TMA stores) placed right after the stages so that they stay 1024-byte aligned.
-  static constexpr int EPI_BYTES = EPI == 1 ? kEpiWarps * 4096 : kEpiWarps * 32 * kEpiStride + BIAS_BYTES;
-  static constexpr int EPI_OFF = EPI == 1 ? STAGES * STAGE_BYTES : STAGES * STAGE_BYTES + BAR_BYTES;
-  static constexpr int BAR_OFF = EPI == 1 ? STAGES * STAGE_BYTES + EPI_BYTES : STAGES * STAGE_BYTES;
+  static constexpr int EPI_BYTES = EPI >= 1 ? kEpiWarps * 4096 : kEpiWarps * 32 * kEpiStride + BIAS_BYTES;
+  static constexpr int EPI_OFF = EPI >= 1 ? STAGES * STAGE_BYTES : STAGES * STAGE_BYTES + BAR_BYTES;
+  static constexpr int BAR_OFF = EPI >= 1 ? STAGES * STAGE_BYTES + EPI_BYTES : STAGES * STAGE_BYTES;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024;  // + alignment slack
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static_assert(TOTAL <= 227 * 1024, "shared memory budget");
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         int rest = tile / p.splits;
         int n_blk = rest % p.n_blocks;
         int m_blk = (rest / p.n_blocks) * CG + (int)cta_rank;
-        if (EPI == 1 && p.tile_prefetch && elect_one())
+        if (EPI >= 1 && p.tile_prefetch && elect_one())
           asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(&p.tile_map)),
                        "r"(n_blk * BN), "r"(m_blk * 128)
                        : "memory");
@@ -468,13 +468,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         }
       }
     }
-  } else if constexpr (EPI == 1) {
-    // ================= epilogue warps (2..9), linear layers =================
+  } else if constexpr (EPI >= 1) {
+    // ================= epilogue warps (2..9), linear layers (EPI 1) / 1x1 convolutions with BatchNorm statistics (EPI 2) =========
     // Plain row-major bf16 outputs (out / pre-activation), no statistics, alpha = 1: the same split of the accumulator as below
     // (two warps per TMEM lane quarter, alternating 32-column chunks), but each 32 x 32 box is packed into a dense swizzled
     // 2 KB tile and leaves through one TMA store (bounds are clipped by the tensor map: no row / column predicates, no address
     // arithmetic, one warp barrier instead of three per box), and nothing of the convolution epilogue's state (pixel decode,
-    // per-column statistics, tap decode) is live while the activation is evaluated.
+    // per-column statistics, tap decode) is live while the activation is evaluated.  EPI 2 is the same path for the 1x1
+    // convolutions: bias / ReLU only, plus the per-column sums of the stored bf16 values (BatchNorm batch statistics) read back
+    // from the staging tile, accumulated in registers and folded into this CTA's partial rows like the generic epilogue does.
     const uint32_t e = warp - 2;
     const uint32_t q = warp & 3;
     const uint32_t half = e >> 2;
@@ -491,8 +493,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     const uint32_t obuf = stg0 + 2048u;
     const uint32_t nalt = tsrc ? 0u : 1u;                      // store tiles in rotation
     uint32_t nbuf = 0;
-    auto store_box = [&](const float (&f)[32], const CUtensorMap* map, int col, int row) {
+    // a box is STAGED (packed into the next free 2 KB tile) and later COMMITTED (proxy fence + TMA store): the arithmetic that
+    // follows the staging (activation of the saved pre-activation, column statistics) runs between the two, so that the fence
+    // finds the shared-memory writes already performed
+    auto stage_box = [&](const float (&f)[32], int row) -> uint32_t {
       const uint32_t buf = stg0 + (nbuf & nalt) * 2048u;
+      const bool zero_row = EPI == 2 && row + (int)lane >= p.M;   // rows outside the tensor must not reach the statistics
       // the store that last used this tile has read it (two boxes ago when the tiles alternate)
       if (lane == 0) {
         if (nalt) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -506,8 +512,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         u.y = pack_bf16x2(f[j8 * 8 + 2], f[j8 * 8 + 3]);
         u.z = pack_bf16x2(f[j8 * 8 + 4], f[j8 * 8 + 5]);
         u.w = pack_bf16x2(f[j8 * 8 + 6], f[j8 * 8 + 7]);
+        if (zero_row) u = make_uint4(0u, 0u, 0u, 0u);
         st_shared_v4(buf + lane * 64u + ((j8 ^ swz) << 4), u);
       }
+      ++nbuf;
+      return buf;
+    };
+    auto commit_box = [&](uint32_t buf, const CUtensorMap* map, int col, int row) {
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
@@ -516,8 +527,29 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                      : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
-      ++nbuf;
     };
+    // EPI 2: per-warp register accumulators of the column sums (lanes 0..15 own the column pairs of each of the warp's chunks)
+    float sacc[EPI == 2 ? NCH : 1][4];
+#pragma unroll
+    for (int i = 0; i < (EPI == 2 ? NCH : 1); ++i) { sacc[i][0] = 0.f; sacc[i][1] = 0.f; sacc[i][2] = 0.f; sacc[i][3] = 0.f; }
+    auto flush_stats = [&](int nblk_) {
+      if constexpr (EPI == 2) {
+        float* part = p.col_sum + ((size_t)blockIdx.x * 4 + q) * 2 * p.N;
+        if (lane < 16) {
+#pragma unroll
+          for (int i = 0; i < NCH; ++i) {
+            const int col = nblk_ * BN + ((int)half + 2 * i) * 32 + (int)lane * 2;
+            if (col < p.N) {
+              part[col] += sacc[i][0]; part[col + 1] += sacc[i][1];
+              part[p.N + col] += sacc[i][2]; part[p.N + col + 1] += sacc[i][3];
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) { sacc[i][0] = 0.f; sacc[i][1] = 0.f; sacc[i][2] = 0.f; sacc[i][3] = 0.f; }
+      }
+    };
+    int prev_nblk = -1;
     int it = 0;
     for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++it) {
       const int rest = tile / p.splits;
@@ -527,6 +559,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       const uint32_t acc_phase = (it >> 1) & 1;
       const int row0 = m_blk * 128 + (int)q * 32;
       const int col0 = n_blk * BN;
+      if (EPI == 2 && n_blk != prev_nblk) {
+        if (prev_nblk >= 0) flush_stats(prev_nblk);
+        prev_nblk = n_blk;
+      }
       auto copy_tile = [&](int c_) {      // chunk c_ of the operand -> obuf (zero fill outside the tensor); one cp.async group
         const int col = col0 + c_ * 32 + cch * 8;
         const bool okc = (c_ < BN / 32) && (col < p.N);
@@ -587,27 +623,29 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             f[j4 * 4 + 0] += bv[j4].x; f[j4 * 4 + 1] += bv[j4].y; f[j4 * 4 + 2] += bv[j4].z; f[j4 * 4 + 3] += bv[j4].w;
           }
         }
-        if (p.preact) store_box(f, &p.pre_map, cc0, row0);
+        uint32_t pbuf = 0;
+        if (EPI == 1 && p.preact) pbuf = stage_box(f, row0);
         if (p.act == ACT_RELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-        } else if (p.act == ACT_GELU) {
+        } else if (EPI == 1 && p.act == ACT_GELU) {
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) act_gelu8(f + j8 * 8);
-        } else if (p.act == ACT_QUICKGELU) {
+        } else if (EPI == 1 && p.act == ACT_QUICKGELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = act_quickgelu(f[j]);
         }
+        if (EPI == 1 && p.preact) commit_box(pbuf, &p.pre_map, cc0, row0);
         if (tsrc) {
           asm volatile("cp.async.wait_group 0;" ::: "memory");
           __syncwarp();
           if (tmode == 1) {
 #pragma unroll
             for (int j8 = 0; j8 < 4; ++j8) apply_gate8<1>(f + j8 * 8, ld_shared_v4(obuf + lane * 64u + ((j8 ^ swz) << 4)));
-          } else if (tmode == 2) {
+          } else if (EPI == 1 && tmode == 2) {
 #pragma unroll
             for (int j8 = 0; j8 < 4; ++j8) apply_gate8<2>(f + j8 * 8, ld_shared_v4(obuf + lane * 64u + ((j8 ^ swz) << 4)));
-          } else if (tmode == 3) {
+          } else if (EPI == 1 && tmode == 3) {
 #pragma unroll
             for (int j8 = 0; j8 < 4; ++j8) apply_gate8<3>(f + j8 * 8, ld_shared_v4(obuf + lane * 64u + ((j8 ^ swz) << 4)));
           } else {
@@ -617,7 +655,36 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           __syncwarp();
           if (ci + 1 < NCH) copy_tile(c + 2);       // the tile is free again: next chunk's operand
         }
-        store_box(f, &p.out_map, cc0, row0);
+        const uint32_t sbuf = stage_box(f, row0);
+        if constexpr (EPI == 2) {
+          __syncwarp();
+          // column sums of the bf16 values just staged: lane = (row parity, column pair), 16 rows x one 32-bit word each; the
+          // two lanes of a column pair are folded with one shuffle round (the TMA store reads the tile concurrently)
+          // (row 2 rr + rpar sits at rr * 128 + rpar * 64; its 16-byte slots are permuted by rr & 3: four lane addresses, then
+          // immediate offsets only; two independent partial sums per accumulator halve the dependent chains)
+          const uint32_t wsel = lane & 15u, rpar = lane >> 4;
+          const uint32_t a0 = sbuf + rpar * 64u + (wsel & 3u) * 4u;
+          uint32_t ak[4];
+#pragma unroll
+          for (uint32_t k = 0; k < 4; ++k) ak[k] = a0 + (((wsel >> 2) ^ k) << 4);
+          float sa = 0.f, sb = 0.f, qa = 0.f, qb = 0.f, sa2 = 0.f, sb2 = 0.f, qa2 = 0.f, qb2 = 0.f;
+#pragma unroll
+          for (int rr_ = 0; rr_ < 16; rr_ += 2) {
+            const uint32_t wv = ld_shared_u32(ak[rr_ & 3] + (uint32_t)rr_ * 128u);
+            const uint32_t wv2 = ld_shared_u32(ak[(rr_ + 1) & 3] + (uint32_t)(rr_ + 1) * 128u);
+            const float x0 = __uint_as_float(wv << 16), x1 = __uint_as_float(wv & 0xffff0000u);
+            const float y0 = __uint_as_float(wv2 << 16), y1 = __uint_as_float(wv2 & 0xffff0000u);
+            sa += x0; sb += x1; sa2 += y0; sb2 += y1;
+            qa = fmaf(x0, x0, qa); qb = fmaf(x1, x1, qb); qa2 = fmaf(y0, y0, qa2); qb2 = fmaf(y1, y1, qb2);
+          }
+          sa += sa2; sb += sb2; qa += qa2; qb += qb2;
+          sa += __shfl_xor_sync(0xffffffffu, sa, 16); sb += __shfl_xor_sync(0xffffffffu, sb, 16);
+          qa += __shfl_xor_sync(0xffffffffu, qa, 16); qb += __shfl_xor_sync(0xffffffffu, qb, 16);
+#pragma unroll
+          for (int i = 0; i < NCH; ++i)
+            if (i == ci) { sacc[i][0] += sa; sacc[i][1] += sb; sacc[i][2] += qa; sacc[i][3] += qb; }
+        }
+        commit_box(sbuf, &p.out_map, cc0, row0);
       }
       if (!released) {
         tc_fence_before();
@@ -626,6 +693,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       }
       if (tsrc) asm volatile("cp.async.wait_group 0;" ::: "memory");   // (a zero-fill group of a chunk beyond the tensor)
     }
+    if (EPI == 2 && prev_nblk >= 0) flush_stats(prev_nblk);
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the staging tiles must outlive their stores
     __syncwarp();
   } else {

@@ -109,12 +109,14 @@ static bool pair_eligible(const GemmParams& p, int BN, int BK, bool a_mn) {
 
 static int launch_gemm(const GemmParams& p, int BN, int BK, bool a_mn, bool b_mn, cudaStream_t st, int epi = 0, int cg = 1) {
   if (cg == 2 && BN == 256 && BK == 64 && !a_mn) {
+    if (epi == 2 && !b_mn) return launch_gemm_t<256, 64, false, false, 2, 2>(p, st);
     if (epi == 1) return b_mn ? launch_gemm_t<256, 64, false, true, 1, 2>(p, st) : launch_gemm_t<256, 64, false, false, 1, 2>(p, st);
     return b_mn ? launch_gemm_t<256, 64, false, true, 0, 2>(p, st) : launch_gemm_t<256, 64, false, false, 0, 2>(p, st);
   }
 #define PB_DISPATCH(bn)                                                                 \
   if (BN == bn) {                                                                       \
     if (BK == 128) return launch_gemm_t<bn, 128, true, true>(p, st);                    \
+    if (epi == 2 && !a_mn && !b_mn) return launch_gemm_t<bn, 64, false, false, 2>(p, st); \
     if (epi == 1 && !a_mn && !b_mn) return launch_gemm_t<bn, 64, false, false, 1>(p, st); \
     if (epi == 1 && !a_mn && b_mn) return launch_gemm_t<bn, 64, false, true, 1>(p, st);   \
     if (!a_mn && !b_mn) return launch_gemm_t<bn, 64, false, false>(p, st);              \
@@ -261,7 +263,8 @@ extern "C" int passl_b200_gemm_bf16_ex(const void* A, const void* B, void* out, 
   if (lean < 0) { const char* e = getenv("PASSL_B200_GEMM_EPI0"); lean = (e && atoi(e)) ? 0 : 1; }
   int epi = 0;
   const bool res_in_epilogue = residual && p.res_iters == 0;
-  if (lean && !out_fp32 && !a_mn_major && !col_sum && alpha == 1.f && splits == 1 && !(aux && res_in_epilogue) &&
+  const bool stats_ok = !col_sum || (!b_mn_major && act <= ACT_RELU && !preact_out && (!aux || aux_mode == 1));   // EPI 2
+  if (lean && !out_fp32 && !a_mn_major && stats_ok && alpha == 1.f && splits == 1 && !(aux && res_in_epilogue) &&
       !((reinterpret_cast<uintptr_t>(aux) | reinterpret_cast<uintptr_t>(preact_out) | reinterpret_cast<uintptr_t>(residual)) & 15)) {
     uint64_t dims[2] = {(uint64_t)N, (uint64_t)M}, strides[1] = {(uint64_t)ldc * 2};
     uint32_t box[2] = {32, 32};
@@ -276,7 +279,7 @@ extern "C" int passl_b200_gemm_bf16_ex(const void* A, const void* B, void* out, 
       uint32_t tbox[2] = {(uint32_t)(BN < N ? BN : N), 128};
       if (tbox[0] <= 256 && make_tmap_bf16(&p.tile_map, tsrc, 2, dims, strides, tbox, CU_TENSOR_MAP_SWIZZLE_NONE) == PB_OK) p.tile_prefetch = 1;
     }
-    epi = 1;
+    epi = col_sum ? 2 : 1;
   }
   return launch_gemm(p, BN, 64, a_mn_major != 0, b_mn_major != 0, (cudaStream_t)stream, epi, cg);
 }
