@@ -108,6 +108,7 @@ static bool pair_eligible(const GemmParams& p, int BN, int BK, bool a_mn) {
 }
 
 static int launch_gemm(const GemmParams& p, int BN, int BK, bool a_mn, bool b_mn, cudaStream_t st, int epi = 0, int cg = 1) {
+  if (cg == 2 && BN == 256 && BK == 64 && a_mn && b_mn && epi == 0) return launch_gemm_t<256, 64, true, true, 0, 2>(p, st);
   if (cg == 2 && BN == 256 && BK == 64 && !a_mn) {
     if (epi == 2 && !b_mn) return launch_gemm_t<256, 64, false, false, 2, 2>(p, st);
     if (epi == 1) return b_mn ? launch_gemm_t<256, 64, false, true, 1, 2>(p, st) : launch_gemm_t<256, 64, false, false, 1, 2>(p, st);
@@ -238,6 +239,25 @@ extern "C" int passl_b200_gemm_bf16_ex(const void* A, const void* B, void* out, 
   if (splits < 1) splits = 1;
   if (splits > p.k_iters) splits = p.k_iters;
   if (splits > 1 && !(out_fp32 && atomic_add)) return PB_ERR_BAD_ARG;
+  // Weight gradients of the linear layers (both operands MN-major, fp32 split-K accumulation): 128 x 128 tiles pull 256 B/clk/SM
+  // from L2 at full MMA rate (delivered: ~50), so they ran at 0.45-0.65 of a plain GEMM.  A CTA pair on a 256 x 256 tile needs half
+  // of that per SM; the caller's split count is replaced by the one that minimises whole waves of num_sms / 2 clusters x item length.
+  bool wgrad_pair = false;
+  if (a_mn_major && b_mn_major && out_fp32 && atomic_add && splits > 1 && N % 256 == 0 && pair_enabled() && !bias && !residual && !aux) {
+    const int slots = num_sms() / 2;
+    const int ptiles = ((p.m_blocks + 1) / 2) * (N / 256);
+    // cost of a split count in K iterations: whole waves x (iterations per item + ~32 for the pipeline fill and the 128 KB of
+    // fp32 reductions each CTA issues per item)
+    int best = 0; long long best_cost = 0;
+    const int smax = p.k_iters / 16 < 64 ? p.k_iters / 16 : 64;
+    for (int sp = 1; sp <= smax; ++sp) {
+      const long long items = (long long)ptiles * sp;
+      const long long waves = (items + slots - 1) / slots;
+      const long long cost = waves * ((p.k_iters + sp - 1) / sp + 32);
+      if (best == 0 || cost < best_cost) { best_cost = cost; best = sp; }
+    }
+    if (best > 0) { BN = 256; p.n_blocks = N / 256; splits = best; wgrad_pair = true; }
+  }
   p.splits = splits;
   int r = fill_mat_operand(p.a, A, a_mn_major != 0, M, K, lda, 128, 64);
   if (r) return r;
@@ -246,7 +266,7 @@ extern "C" int passl_b200_gemm_bf16_ex(const void* A, const void* B, void* out, 
   // nor when a residual could ride the MMA of a short K loop instead of the epilogue (proj of ViT-B: 999 vs 917 TF/s)
   const bool heavy_epi = act == ACT_GELU || act == ACT_QUICKGELU || (aux && aux_mode >= 2);
   const bool short_k_residual = residual && K < 1536;
-  const int cg = (!heavy_epi && !short_k_residual && pair_eligible(p, BN, 64, a_mn_major != 0)) ? 2 : 1;
+  const int cg = (wgrad_pair || (!heavy_epi && !short_k_residual && pair_eligible(p, BN, 64, a_mn_major != 0))) ? 2 : 1;
   r = fill_mat_operand(p.b, B, b_mn_major != 0, N, K, ldb, BN / cg, 64);
   if (r) return r;
   set_epilogue(p, out, ldc, out_fp32, atomic_add, bias, residual, act, alpha, col_sum, col_sqsum);

@@ -70,17 +70,25 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* __rest
   if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
 }
 
-// CTA = 8 warps, each warp walks rows r0 + w, r0 + w + 8, ... of the CTA's row range.
+// CTA = LN_BWD_WARPS warps, each warp walks rows r0 + w, r0 + w + WARPS, ... of the CTA's row range.
 // part[blockIdx.x][0][D] = sum_rows dy (dbeta), part[blockIdx.x][1][D] = sum_rows dy * xhat (dgamma)
+// Round 2: the pass was latency-bound (2.2-3.0 TB/s, 11.5 % of the CLIP step): one row per warp at a time with ~200 registers
+// of fp32 row state kept only 37 KB per SM in flight.  Now the row stays PACKED (bf16, 4 registers per 8 elements) and is
+// unpacked twice, the next row of the warp is requested before the current one is touched, and 12 warps share an SM.
+constexpr int LN_BWD_WARPS = 12;
 template <int MAXCH>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
-                                                     const float* __restrict__ gamma, const float* __restrict__ mean,
-                                                     const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ dres,
-                                                     __nv_bfloat16* __restrict__ dx, float* __restrict__ part, long long T,
-                                                     int D, int rows_per_block) {
-  extern __shared__ float red[];  // [8 warps][2][D]
+__global__ void __launch_bounds__(LN_BWD_WARPS * 32) ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                                                   const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                                   const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ dres,
+                                                                   __nv_bfloat16* __restrict__ dx, float* __restrict__ part, long long T,
+                                                                   int D, int rows_per_block) {
+  extern __shared__ float red[];  // [D] gamma, then [WARPS][2][D] partials
+  float* gsm = red;
+  float* rsm = red + D;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunks = D >> 3;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) gsm[i] = gamma[i];
+  __syncthreads();
   float ab[MAXCH][8], ag[MAXCH][8];
 #pragma unroll
   for (int j = 0; j < MAXCH; ++j)
@@ -89,27 +97,44 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   long long r1 = r0 + rows_per_block;
   if (r1 > T) r1 = T;
-  for (long long row = r0 + warp; row < r1; row += 8) {
-    const float mu = mean[row], rs = rstd[row];
-    float xh[MAXCH][8], g[MAXCH][8];
+  uint4 px[MAXCH], pd[MAXCH], pr[MAXCH];
+  auto load_row = [&](long long row, uint4 (&ax)[MAXCH], uint4 (&ad)[MAXCH], uint4 (&ar)[MAXCH]) {
+#pragma unroll
+    for (int j = 0; j < MAXCH; ++j) {
+      const int c = lane + 32 * j;
+      if (c < chunks) {
+        ax[j] = ld_nc_v4(x + row * D + c * 8);
+        ad[j] = ld_nc_v4(dy + row * D + c * 8);
+        if (dres) ar[j] = ld_nc_v4(dres + row * D + c * 8);
+      }
+    }
+  };
+  long long row = r0 + warp;
+  float mu = 0.f, rs = 0.f;
+  if (row < r1) { load_row(row, px, pd, pr); mu = mean[row]; rs = rstd[row]; }
+  for (; row < r1; row += LN_BWD_WARPS) {
+    uint4 nx[MAXCH], nd[MAXCH], nr[MAXCH];
+    const long long nrow = row + LN_BWD_WARPS;
+    float nmu = 0.f, nrs = 0.f;
+    if (nrow < r1) { load_row(nrow, nx, nd, nr); nmu = mean[nrow]; nrs = rstd[nrow]; }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < MAXCH; ++j) {
       const int c = lane + 32 * j;
       if (c < chunks) {
         float xv[8], dv[8];
-        ln_unpack8(ld_nc_v4(x + row * D + c * 8), xv);
-        ln_unpack8(ld_nc_v4(dy + row * D + c * 8), dv);
-        const float4 g0 = *reinterpret_cast<const float4*>(gamma + c * 8), g1 = *reinterpret_cast<const float4*>(gamma + c * 8 + 4);
+        ln_unpack8(px[j], xv);
+        ln_unpack8(pd[j], dv);
+        const float4 g0 = *reinterpret_cast<const float4*>(gsm + c * 8), g1 = *reinterpret_cast<const float4*>(gsm + c * 8 + 4);
         const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          xh[j][e] = (xv[e] - mu) * rs;
-          g[j][e] = dv[e] * gg[e];
-          s1 += g[j][e];
-          s2 = fmaf(g[j][e], xh[j][e], s2);
+          const float xh = (xv[e] - mu) * rs;
+          const float g = dv[e] * gg[e];
+          s1 += g;
+          s2 = fmaf(g, xh, s2);
           ab[j][e] += dv[e];
-          ag[j][e] = fmaf(dv[e], xh[j][e], ag[j][e]);
+          ag[j][e] = fmaf(dv[e], xh, ag[j][e]);
         }
       }
     }
@@ -119,18 +144,25 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
     for (int j = 0; j < MAXCH; ++j) {
       const int c = lane + 32 * j;
       if (c < chunks) {
-        float o[8];
+        float xv[8], dv[8], o[8];
+        ln_unpack8(px[j], xv);
+        ln_unpack8(pd[j], dv);
+        const float4 g0 = *reinterpret_cast<const float4*>(gsm + c * 8), g1 = *reinterpret_cast<const float4*>(gsm + c * 8 + 4);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = rs * (g[j][e] - s1 - xh[j][e] * s2);
+        for (int e = 0; e < 8; ++e) o[e] = rs * (dv[e] * gg[e] - s1 - (xv[e] - mu) * rs * s2);
         if (dres) {   // gradient arriving through the residual connection around this LayerNorm's branch
           float rr[8];
-          ln_unpack8(ld_nc_v4(dres + row * D + c * 8), rr);
+          ln_unpack8(pr[j], rr);
 #pragma unroll
           for (int e = 0; e < 8; ++e) o[e] += rr[e];
         }
         *reinterpret_cast<uint4*>(dx + row * D + c * 8) = ln_pack8(o);
       }
     }
+#pragma unroll
+    for (int j = 0; j < MAXCH; ++j) { px[j] = nx[j]; pd[j] = nd[j]; pr[j] = nr[j]; }
+    mu = nmu; rs = nrs;
   }
   // cross-warp reduction of the parameter-gradient partials
 #pragma unroll
@@ -139,8 +171,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
     if (c < chunks) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        red[(warp * 2 + 0) * D + c * 8 + e] = ab[j][e];
-        red[(warp * 2 + 1) * D + c * 8 + e] = ag[j][e];
+        rsm[(warp * 2 + 0) * D + c * 8 + e] = ab[j][e];
+        rsm[(warp * 2 + 1) * D + c * 8 + e] = ag[j][e];
       }
     }
   }
@@ -149,15 +181,15 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
     const int which = i / D, col = i - which * D;
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += red[(w * 2 + which) * D + col];
+    for (int w = 0; w < LN_BWD_WARPS; ++w) s += rsm[(w * 2 + which) * D + col];
     part[((size_t)blockIdx.x * 2 + which) * D + col] = s;
   }
 }
 
 static void ln_bwd_cfg(long long T, int& blocks, int& rpb) {
-  long long target = (long long)num_sms() * 2;
+  long long target = (long long)num_sms();        // one 12-warp CTA per SM
   long long r = (T + target - 1) / target;
-  if (r < 8) r = 8;
+  if (r < LN_BWD_WARPS) r = LN_BWD_WARPS;
   rpb = (int)r;
   blocks = (int)((T + r - 1) / r);
 }
@@ -192,23 +224,24 @@ extern "C" int passl_b200_layernorm_bwd(const void* x, const void* dy, const flo
   if (T <= 0 || D <= 0 || D % 8 || D > 256 * LN_MAXCH) return PB_ERR_BAD_ARG;
   int blocks, rpb;
   ln_bwd_cfg(T, blocks, rpb);
-  const int smem = 8 * 2 * D * 4;
+  const int smem = (LN_BWD_WARPS * 2 + 1) * D * 4;
   static bool attr = false;
   if (!attr) {
-    PB_CUDA_CHECK(cudaFuncSetAttribute(ln_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4));
-    PB_CUDA_CHECK(cudaFuncSetAttribute(ln_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 2048 * 4));
+    PB_CUDA_CHECK(cudaFuncSetAttribute(ln_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (LN_BWD_WARPS * 2 + 1) * 512 * 4));
+    PB_CUDA_CHECK(cudaFuncSetAttribute(ln_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (LN_BWD_WARPS * 2 + 1) * 768 * 4));
+    PB_CUDA_CHECK(cudaFuncSetAttribute(ln_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (LN_BWD_WARPS * 2 + 1) * 1024 * 4));
+    PB_CUDA_CHECK(cudaFuncSetAttribute(ln_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (LN_BWD_WARPS * 2 + 1) * 2048 * 4));
     attr = true;
   }
-  if (D <= 1024)
-    ln_bwd_kernel<4><<<blocks, 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
-                                                                 reinterpret_cast<const __nv_bfloat16*>(dy), gamma, mean, rstd,
-                                                                 reinterpret_cast<const __nv_bfloat16*>(dres),
-                                                                 reinterpret_cast<__nv_bfloat16*>(dx), part, T, D, rpb);
-  else
-    ln_bwd_kernel<8><<<blocks, 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
-                                                                 reinterpret_cast<const __nv_bfloat16*>(dy), gamma, mean, rstd,
-                                                                 reinterpret_cast<const __nv_bfloat16*>(dres),
-                                                                 reinterpret_cast<__nv_bfloat16*>(dx), part, T, D, rpb);
+#define PB_LN_BWD(mc)                                                                                                            \
+  ln_bwd_kernel<mc><<<blocks, LN_BWD_WARPS * 32, smem, (cudaStream_t)stream>>>(                                                  \
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), gamma, mean, rstd,                  \
+      reinterpret_cast<const __nv_bfloat16*>(dres), reinterpret_cast<__nv_bfloat16*>(dx), part, T, D, rpb)
+  if (D <= 512) PB_LN_BWD(2);
+  else if (D <= 768) PB_LN_BWD(3);
+  else if (D <= 1024) PB_LN_BWD(4);
+  else PB_LN_BWD(8);
+#undef PB_LN_BWD
   PB_LAUNCH_CHECK();
   return PB_OK;
 }
