@@ -243,7 +243,7 @@ extern "C" int passl_b200_gemm_bf16_ex(const void* A, const void* B, void* out, 
   // from L2 at full MMA rate (delivered: ~50), so they ran at 0.45-0.65 of a plain GEMM.  A CTA pair on a 256 x 256 tile needs half
   // of that per SM; the caller's split count is replaced by the one that minimises whole waves of num_sms / 2 clusters x item length.
   bool wgrad_pair = false;
-  if (a_mn_major && b_mn_major && out_fp32 && atomic_add && splits > 1 && N % 256 == 0 && pair_enabled() && !bias && !residual && !aux) {
+  if (a_mn_major && b_mn_major && out_fp32 && atomic_add && splits > 1 && N % 256 == 0 && M >= 256 && pair_enabled() && !bias && !residual && !aux) {
     const int slots = num_sms() / 2;
     const int ptiles = ((p.m_blocks + 1) / 2) * (N / 256);
     // cost of a split count in K iterations: whole waves x (iterations per item + ~32 for the pipeline fill and the 128 KB of
