@@ -236,8 +236,9 @@ int passl_b200_layernorm_bwd(const void* x, const void* dy, const float* gamma, 
  * ------------------------------------------------------------------------------------------------------------- */
 int passl_b200_attention_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int d, float scale, int causal,
                              void* stream);
-int passl_b200_attention_bwd(const void* qkv, const void* dO, const void* O, const float* lse, void* dqkv, int B, int N,
-                             int H, int d, float scale, int causal, void* stream);
+/* delta_ws: caller-provided fp32 [B, H, N] workspace (row sums of dO * O, filled by a pre-pass on the same stream) */
+int passl_b200_attention_bwd(const void* qkv, const void* dO, const void* O, const float* lse, void* dqkv, float* delta_ws, int B,
+                             int N, int H, int d, float scale, int causal, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * MAE (passl/models/mae.py).

@@ -103,7 +103,7 @@ SIGNATURES = {
     "passl_b200_gaussian_blur_workspace_bytes": (c_ll, [c_int] * 2),
     "passl_b200_gaussian_blur_u8": (c_int, [c_void_p] * 4 + [c_ll] + [c_int] * 3 + [c_void_p]),
     "passl_b200_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
-    "passl_b200_attention_bwd": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
+    "passl_b200_attention_bwd": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "passl_b200_layernorm_fwd": (c_int, [c_void_p] * 6 + [c_ll, c_int, c_float, c_void_p]),
     "passl_b200_layernorm_bwd_blocks": (c_int, [c_ll]),
     "passl_b200_layernorm_bwd": (c_int, [c_void_p] * 8 + [c_ll, c_int, c_void_p]),

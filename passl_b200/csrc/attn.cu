@@ -531,12 +531,42 @@ struct AttnBwdParams {
   const __nv_bfloat16* dO;
   const __nv_bfloat16* O;
   const float* lse;
+  const float* delta;    // [B, H, N] fp32: sum_e dO * O per row, from attn_delta_kernel
   __nv_bfloat16* dqkv;
   int B, N, H, d, mblocks, causal;
   float scale;
 };
 
-__global__ void __launch_bounds__(160, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
+// delta[b, h, n] = sum_e dO[b, n, h, e] * O[b, n, h, e].  One warp per token: the H*d contiguous elements of dO and O are read with
+// coalesced 16-byte loads, each head's d elements sit in d / 8 neighbouring lanes (segmented shuffle reduction).  Round 2: inside
+// the backward kernel this was a per-thread strided dot product at the start of every item — 15 % of the kernel's stall samples
+// (`profiles/r02_ncu_attn_bwd_summary.txt`) with the DRAM latency fully exposed.
+__global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* __restrict__ O,
+                                                         float* __restrict__ delta, long long T, int N, int H, int d) {
+  const long long tok = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (tok >= T) return;
+  const int lane = threadIdx.x & 31;
+  const int chunks = H * d / 8, seg = d / 8;
+  const long long b = tok / N;
+  const int n = (int)(tok - b * N);
+  for (int c = lane; c < ((chunks + 31) / 32) * 32; c += 32) {
+    float sacc = 0.f;
+    if (c < chunks) {
+      const uint4 ua = ld_nc_v4(dO + tok * (long long)H * d + c * 8), uo = ld_nc_v4(O + tok * (long long)H * d + c * 8);
+      const float2 a0 = unpack_bf16x2(ua.x), a1 = unpack_bf16x2(ua.y), a2 = unpack_bf16x2(ua.z), a3 = unpack_bf16x2(ua.w);
+      const float2 o0 = unpack_bf16x2(uo.x), o1 = unpack_bf16x2(uo.y), o2 = unpack_bf16x2(uo.z), o3 = unpack_bf16x2(uo.w);
+      sacc = a0.x * o0.x + a0.y * o0.y + a1.x * o1.x + a1.y * o1.y + a2.x * o2.x + a2.y * o2.y + a3.x * o3.x + a3.y * o3.y;
+    }
+    for (int off = seg >> 1; off > 0; off >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, off);
+    if (c < chunks && (c % seg) == 0) delta[(b * H + c / seg) * N + n] = sacc;
+  }
+}
+
+// Round 2: EIGHT math warps (two per TMEM lane quarter, each takes two of the four 32-column chunks of a tile and half of the
+// dK / dV / dQ epilogue columns) + the control warp: the softmax arithmetic between the two MMA groups of a tile was half of the
+// tile time with one warp per sub-partition.
+constexpr int kAttnBwdThreads = 288;
+__global__ void __launch_bounds__(kAttnBwdThreads, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int rowB = p.d * 2;
@@ -559,16 +589,16 @@ __global__ void __launch_bounds__(160, 1) attn_bwd_kernel(const __grid_constant_
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7);
 
   const uint32_t warp = warp_id(), lane = lane_id();
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&p.qkv_map);
     tma_prefetch_desc(&p.do_map);
     mbar_init(load_full, 1);
     mbar_init(sp_full, 1);
-    mbar_init(pd_full, 4);
+    mbar_init(pd_full, 8);
     mbar_init(kv_done, 1);
-    mbar_init(kv_free, 4);
+    mbar_init(kv_free, 8);
     mbar_init(q_done, 1);
-    mbar_init(q_free, 4);
+    mbar_init(q_free, 8);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_ptr, 512);
@@ -582,9 +612,11 @@ __global__ void __launch_bounds__(160, 1) attn_bwd_kernel(const __grid_constant_
   const int nb = p.mblocks;
   uint32_t ph_load = 0, ph_sp = 0, ph_pd = 0, ph_kvd = 0, ph_kvf = 0, ph_qd = 0, ph_qf = 0;
 
-  if (warp == 4) {
+  if (warp == 8) {
     {   // warp-uniform control loop; TMA / tcgen05 issue elect-predicated
-      const uint32_t id_s = make_idesc_bf16(128, 128, false, false);
+      // Tiles are cut to the valid extent of the sequence (N = 197: the second block has 69 rows / keys, N = 50: one 64-key
+      // tile): S / dP over the valid keys rounded up to 32, dV / dK over the valid query rows rounded up to 16, dQ over the
+      // valid keys — the padded remainder is neither multiplied nor exponentiated.
       const uint32_t id_kv = make_idesc_bf16(128, p.d, true, true);
       const uint32_t id_q = make_idesc_bf16(128, p.d, false, true);
       bool first_item = true;
@@ -609,6 +641,9 @@ __global__ void __launch_bounds__(160, 1) attn_bwd_kernel(const __grid_constant_
           for (int i = 0; i < nb; ++i) {
             const uint32_t qa = smem_u32(q_s + i * 128 * rowB), doa = smem_u32(do_s + i * 128 * rowB);
             const uint32_t ka = smem_u32(k_s + j * 128 * rowB), va = smem_u32(v_s + j * 128 * rowB);
+            const int nk = p.N - j * 128 < 128 ? p.N - j * 128 : 128, nr = p.N - i * 128 < 128 ? p.N - i * 128 : 128;
+            const int nmma = ((nk + 31) / 32) * 32, rk = (nr + 15) / 16;
+            const uint32_t id_s = make_idesc_bf16(128, (uint32_t)nmma, false, false);
             if (elect_one()) {
               for (int k = 0; k < p.d / 16; ++k)
                 umma_bf16(tm_s, make_smem_desc(qa + k * 32, 16, sbo, lt), make_smem_desc(ka + k * 32, 16, sbo, lt), id_s, k > 0);
@@ -621,14 +656,14 @@ __global__ void __launch_bounds__(160, 1) attn_bwd_kernel(const __grid_constant_
             tc_fence_after();
             const uint32_t pa = smem_u32(p_s), dsa = smem_u32(ds_s);
             if (elect_one()) {
-            for (int k = 0; k < 8; ++k) {   // K = 128 query rows
+            for (int k = 0; k < rk; ++k) {   // K = the valid query rows
               // dV_j += P^T dO_i ; dK_j += dS^T Q_i      (A = P / dS viewed MN-major: M = keys, K = query rows)
               umma_bf16(tm_dv, make_smem_desc(pa + k * 2048, 128 * 128, 1024, 2), make_smem_desc(doa + k * 16 * rowB, 0, sbo, lt),
                         id_kv, (i > 0 || k > 0));
               umma_bf16(tm_dk, make_smem_desc(dsa + k * 2048, 128 * 128, 1024, 2), make_smem_desc(qa + k * 16 * rowB, 0, sbo, lt),
                         id_kv, (i > 0 || k > 0));
             }
-            for (int k = 0; k < 8; ++k)     // dQ_i += dS K_j   (A = dS K-major over keys, B = K_j MN-major)
+            for (int k = 0; k < nmma / 16; ++k)     // dQ_i += dS K_j   (A = dS K-major over the valid keys, B = K_j MN-major)
               umma_bf16(tm_dq + i * 64, make_smem_desc_sw128(dsa + (k >> 2) * (128 * 128) + (k & 3) * 32, 16, 1024),
                         make_smem_desc(ka + k * 16 * rowB, 0, sbo, lt), id_q, (j > 0 || k > 0));
             if (i == nb - 1) umma_commit(kv_done);
@@ -644,38 +679,39 @@ __global__ void __launch_bounds__(160, 1) attn_bwd_kernel(const __grid_constant_
       }
     }
   } else {
-    const uint32_t q4 = warp;
+    const uint32_t q4 = warp & 3u, hf = warp >> 2;     // TMEM lane quarter, column half
     const int r = q4 * 32 + lane;
     const float c2 = p.scale * kAttnLog2e;
     const uint32_t lane_off = (q4 * 32u) << 16;
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
-      const int b = item / p.H, h = item - b * p.H;
-      // per-row constants for both query blocks: lse (log2 domain) and delta
-      float lse2[2], delta[2];
+    float nlse[2] = {0.f, 0.f}, ndel[2] = {0.f, 0.f};
+    auto load_consts = [&](int item_) {
+      if (item_ >= items) return;
       for (int i = 0; i < nb; ++i) {
         const int row = i * 128 + r;
-        lse2[i] = 0.f; delta[i] = 0.f;
+        nlse[i] = 0.f; ndel[i] = 0.f;
         if (row < p.N) {
-          lse2[i] = p.lse[((size_t)b * p.H + h) * p.N + row] * kAttnLog2e;
-          const __nv_bfloat16* a = p.dO + (((size_t)b * p.N + row) * p.H + h) * p.d;
-          const __nv_bfloat16* o = p.O + (((size_t)b * p.N + row) * p.H + h) * p.d;
-          float s = 0.f;
-          for (int e = 0; e < p.d; e += 8) {
-            uint4 ua = *reinterpret_cast<const uint4*>(a + e), uo = *reinterpret_cast<const uint4*>(o + e);
-            float2 a0 = unpack_bf16x2(ua.x), a1 = unpack_bf16x2(ua.y), a2 = unpack_bf16x2(ua.z), a3 = unpack_bf16x2(ua.w);
-            float2 o0 = unpack_bf16x2(uo.x), o1 = unpack_bf16x2(uo.y), o2 = unpack_bf16x2(uo.z), o3 = unpack_bf16x2(uo.w);
-            s += a0.x * o0.x + a0.y * o0.y + a1.x * o1.x + a1.y * o1.y + a2.x * o2.x + a2.y * o2.y + a3.x * o3.x + a3.y * o3.y;
-          }
-          delta[i] = s;
+          nlse[i] = p.lse[(size_t)item_ * p.N + row];
+          ndel[i] = p.delta[(size_t)item_ * p.N + row];
         }
       }
+    };
+    load_consts((int)blockIdx.x);
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const int b = item / p.H, h = item - b * p.H;
+      // per-row constants for both query blocks: lse (log2 domain) and delta — requested one item ahead
+      float lse2[2], delta[2];
+      for (int i = 0; i < 2; ++i) { lse2[i] = nlse[i] * kAttnLog2e; delta[i] = ndel[i]; }
+      load_consts(item + (int)gridDim.x);
       for (int j = 0; j < nb; ++j) {
         for (int i = 0; i < nb; ++i) {
           const int row = i * 128 + r;
           const bool row_ok = row < p.N;
+          const int nk = p.N - j * 128 < 128 ? p.N - j * 128 : 128, nr = p.N - i * 128 < 128 ? p.N - i * 128 : 128;
+          const int kc = (nk + 31) / 32;                                   // 32-key chunks the MMAs produced
+          const bool warp_live = (int)q4 * 32 < ((nr + 15) / 16) * 16;     // rows the dV / dK MMAs will read
           mbar_wait(sp_full, ph_sp); ph_sp ^= 1;
           tc_fence_after();
-          for (int c = 0; c < 4; ++c) {
+          for (int c = (int)hf; c < kc && warp_live; c += 2) {
             uint32_t sv[32], dv[32];
             tmem_ld_32x32(tm_s + lane_off + c * 32, sv);
             tmem_ld_32x32(tm_dp + lane_off + c * 32, dv);
@@ -716,7 +752,7 @@ __global__ void __launch_bounds__(160, 1) attn_bwd_kernel(const __grid_constant_
           const int key = j * 128 + r;
           __nv_bfloat16* dk = p.dqkv + ((((size_t)b * p.N + key) * 3 + 1) * p.H + h) * p.d;
           __nv_bfloat16* dvp = p.dqkv + ((((size_t)b * p.N + key) * 3 + 2) * p.H + h) * p.d;
-          for (int c = 0; c < p.d / 32; ++c) {
+          for (int c = (int)hf; c < p.d / 32; c += 2) {
             uint32_t a[32], bq[32];
             tmem_ld_32x32(tm_dk + lane_off + c * 32, a);
             tmem_ld_32x32(tm_dv + lane_off + c * 32, bq);
@@ -749,7 +785,7 @@ __global__ void __launch_bounds__(160, 1) attn_bwd_kernel(const __grid_constant_
       for (int i = 0; i < nb; ++i) {
         const int row = i * 128 + r;
         __nv_bfloat16* dq = p.dqkv + ((((size_t)b * p.N + row) * 3 + 0) * p.H + h) * p.d;
-        for (int c = 0; c < p.d / 32; ++c) {
+        for (int c = (int)hf; c < p.d / 32; c += 2) {
           uint32_t a[32];
           tmem_ld_32x32(tm_dq + i * 64 + lane_off + c * 32, a);
           tmem_ld_wait();
@@ -783,13 +819,15 @@ __global__ void __launch_bounds__(160, 1) attn_bwd_kernel(const __grid_constant_
 }  // namespace pb
 
 // dO, O: bf16 [B, N, H, d]; lse fp32 [B, H, N]; dqkv: bf16 [B, N, 3, H, d] (fully overwritten)
-extern "C" int passl_b200_attention_bwd(const void* qkv, const void* dO, const void* O, const float* lse, void* dqkv, int B,
-                                        int N, int H, int d, float scale, int causal, void* stream) {
-  if (B <= 0 || N <= 0 || N > 256 || H <= 0 || (d != 64 && d != 32)) return PB_ERR_UNSUPPORTED;
+// delta_ws: fp32 [B, H, N] workspace (row sums of dO * O, written by a pre-pass on the same stream)
+extern "C" int passl_b200_attention_bwd(const void* qkv, const void* dO, const void* O, const float* lse, void* dqkv, float* delta_ws,
+                                        int B, int N, int H, int d, float scale, int causal, void* stream) {
+  if (B <= 0 || N <= 0 || N > 256 || H <= 0 || (d != 64 && d != 32) || !delta_ws) return PB_ERR_UNSUPPORTED;
   AttnBwdParams p;
   memset(&p, 0, sizeof(p));
   p.dO = reinterpret_cast<const __nv_bfloat16*>(dO); p.O = reinterpret_cast<const __nv_bfloat16*>(O);
   p.lse = lse; p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
+  p.delta = delta_ws;
   p.B = B; p.N = N; p.H = H; p.d = d; p.causal = causal; p.scale = scale;
   p.mblocks = (N + 127) / 128;
   CUtensorMapSwizzle swz = (d == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -811,8 +849,11 @@ extern "C" int passl_b200_attention_bwd(const void* qkv, const void* dO, const v
     PB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 256 * 128 + 4 * 128 * 128 + 256 + 1024));
     attr = true;
   }
+  const long long T = (long long)B * N;
+  attn_delta_kernel<<<(unsigned)((T + 7) / 8), 256, 0, (cudaStream_t)stream>>>(p.dO, p.O, delta_ws, T, N, H, d);
+  PB_LAUNCH_CHECK();
   int grid = B * H < num_sms() ? B * H : num_sms();
-  attn_bwd_kernel<<<grid, 160, smem, (cudaStream_t)stream>>>(p);
+  attn_bwd_kernel<<<grid, kAttnBwdThreads, smem, (cudaStream_t)stream>>>(p);
   PB_LAUNCH_CHECK();
   return PB_OK;
 }

@@ -51,8 +51,9 @@ def attention_bwd(qkv, dout, out, lse, B, N, H, d, scale=None, causal=False):
     lib = _lib.load()
     dqkv = torch.empty_like(qkv)
     scale = float(d) ** -0.5 if scale is None else float(scale)
-    _lib.check(lib.passl_b200_attention_bwd(_ptr(qkv), _ptr(dout.contiguous()), _ptr(out), _ptr(lse), _ptr(dqkv), B, N, H, d, scale,
-                                            int(causal), _stream()), "attention_bwd")
+    delta = torch.empty((B, H, N), dtype=torch.float32, device=qkv.device)      # workspace of the dO.O pre-pass
+    _lib.check(lib.passl_b200_attention_bwd(_ptr(qkv), _ptr(dout.contiguous()), _ptr(out), _ptr(lse), _ptr(dqkv), _ptr(delta), B, N, H, d,
+                                            scale, int(causal), _stream()), "attention_bwd")
     return dqkv
 
 
