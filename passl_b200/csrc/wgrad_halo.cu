@@ -24,9 +24,11 @@ constexpr int WH_TH = 8, WH_TW = 16;                        // pixel tile (one i
 constexpr int WH_A_BYTES = 2 * 128 * 128;                   // dy: two 64-channel atoms x 128 pixels x 128 B
 constexpr int WH_HALO_ROWS = (WH_TH + 2) * (WH_TW + 2);     // 180
 constexpr int WH_B_BYTES = 23552;                           // 180 x 128 B rounded up to a multiple of 1024
-constexpr int WH_STAGE_BYTES = WH_A_BYTES + WH_B_BYTES;     // 56320
+constexpr int WH_STAGE_BYTES = WH_A_BYTES + WH_B_BYTES;     // 56320   (one 64-channel halo atom: 3 stages)
 constexpr int WH_STAGES = 3;
-constexpr int WH_SMEM = WH_STAGES * WH_STAGE_BYTES + 256 + 1024;
+constexpr int WH_STAGE_BYTES2 = WH_A_BYTES + 2 * WH_B_BYTES;   // 79872  (two halo atoms = 128 input channels per CTA: 2 stages)
+constexpr int WH_STAGES2 = 2;
+constexpr int WH_SMEM = WH_STAGES * WH_STAGE_BYTES + 256 + 1024;   // >= WH_STAGES2 * WH_STAGE_BYTES2 + 256 + 1024
 
 struct WgradHaloParams {
   CUtensorMap dy_map, x_map;
@@ -38,12 +40,18 @@ struct WgradHaloParams {
   int R, S, pad_h, pad_w;   // filter taps (R*S <= 10) and padding: halo tile = (TH + R - 1) x (TW + S - 1) pixels
   int groups, tpg;          // tap groups per (m, ci) block and taps per group (<= 5: 5 x 64 TMEM columns)
   int halo_w, halo_rows;
+  // Round 2: cib = 2 makes a CTA own 128 input channels (two halo atoms, MMA N = 128, 3 taps x 128 TMEM columns per group).  An
+  // M = 128 x N = 64 MMA reads 6 KB of shared memory per 16 clk (A 4 KB + B 2 KB), three times what the SM delivers; at N = 128 it
+  // is 8 KB per 32 clk — the launches with Cin >= 128 were at 0.30-0.34 of the tensor roofline on that limit.
+  int cib;
 };
 
 __global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constant__ WgradHaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WH_STAGES * WH_STAGE_BYTES);
+  const int nstages = p.cib == 2 ? WH_STAGES2 : WH_STAGES;
+  const int stage_bytes = p.cib == 2 ? WH_STAGE_BYTES2 : WH_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WH_STAGES * WH_STAGE_BYTES);   // past the larger of the two rings
   uint64_t* empty_bar = full_bar + WH_STAGES;
   uint64_t* acc_full = empty_bar + WH_STAGES;
   uint64_t* acc_empty = acc_full + 1;
@@ -93,24 +101,27 @@ __global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constan
       int ih = rem / p.wb, iw = rem - ih * p.wb;
       for (int kt = k_begin; kt < k_end; ++kt) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * WH_STAGE_BYTES;
+        uint8_t* sa = smem + stage * stage_bytes;
         if (elect_one()) {
-          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(WH_A_BYTES + p.halo_rows * 128));
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(WH_A_BYTES + p.cib * p.halo_rows * 128));
           const int h0 = ih * WH_TH, w0 = iw * WH_TW;
           tma_load_4d(sa, &p.dy_map, &full_bar[stage], m_blk * 128, w0, h0, n);
           tma_load_4d(sa + 128 * 128, &p.dy_map, &full_bar[stage], m_blk * 128 + 64, w0, h0, n);
-          tma_load_4d(sa + WH_A_BYTES, &p.x_map, &full_bar[stage], ci_blk * 64, w0 - p.pad_w, h0 - p.pad_h, n);
+          for (int a = 0; a < p.cib; ++a)
+            tma_load_4d(sa + WH_A_BYTES + a * WH_B_BYTES, &p.x_map, &full_bar[stage], (ci_blk * p.cib + a) * 64, w0 - p.pad_w,
+                        h0 - p.pad_h, n);
         }
         __syncwarp();
         if (++iw == p.wb) { iw = 0; if (++ih == p.hb) { ih = 0; ++n; } }
-        if (++stage == WH_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == nstages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    constexpr uint32_t idesc = make_idesc_bf16(128, 64, true, true);
+    const uint32_t idesc = make_idesc_bf16(128, 64u * (uint32_t)p.cib, true, true);
     const uint64_t da0 = make_smem_desc_sw128(smem_u32(smem), 128 * 128, 1024);                 // LBO = next 64-channel atom
-    const uint64_t db0 = make_smem_desc_sw128(smem_u32(smem + WH_A_BYTES), 128 * 128, 1024);    // N = 64: single atom
+    const uint64_t db0 = make_smem_desc_sw128(smem_u32(smem + WH_A_BYTES), WH_B_BYTES, 1024);   // LBO = second halo atom (cib = 2)
+    const uint32_t tap_cols = 64u * (uint32_t)p.cib;
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -124,13 +135,13 @@ __global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constan
       for (int kt = k_begin; kt < k_end; ++kt) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint64_t das = da0 + (uint64_t)((stage * WH_STAGE_BYTES) >> 4);
-        const uint64_t dbs = db0 + (uint64_t)((stage * WH_STAGE_BYTES) >> 4);
+        const uint64_t das = da0 + (uint64_t)((stage * stage_bytes) >> 4);
+        const uint64_t dbs = db0 + (uint64_t)((stage * stage_bytes) >> 4);
         if (elect_one()) {
           for (int t = 0; t < ntap; ++t) {
             const int tap = tap0 + t;
             const int r = tap / p.S, s = tap - r * p.S;
-            const uint32_t d_tmem = tmem_base + t * 64;
+            const uint32_t d_tmem = tmem_base + t * tap_cols;
 #pragma unroll
             for (int h = 0; h < WH_TH; ++h) {
               const uint64_t da = das + (uint64_t)((h * 16 * 128) >> 4);
@@ -142,7 +153,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constan
           if (kt == k_end - 1) umma_commit(acc_full);
         }
         __syncwarp();
-        if (++stage == WH_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == nstages) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -161,16 +172,17 @@ __global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constan
       if (k_end > k_begin) {
         for (int t = 0; t < ntap; ++t) {
           const int tap = tap0 + t;
-          float* dst = p.dw + ((size_t)co * (p.R * p.S) + tap) * p.Cin + ci_blk * 64;
+          const int ci0 = ci_blk * 64 * p.cib;
+          float* dst = p.dw + ((size_t)co * (p.R * p.S) + tap) * p.Cin + ci0;
 #pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
+          for (int c = 0; c < 2 * p.cib; ++c) {
             uint32_t v[32];
-            tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + t * 64 + c * 32, v);
+            tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + t * 64 * p.cib + c * 32, v);
             tmem_ld_wait();
             if (row_ok) {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (ci_blk * 64 + c * 32 + j < p.Cin) red_add_f32(dst + c * 32 + j, __uint_as_float(v[j]));
+                if (ci0 + c * 32 + j < p.Cin) red_add_f32(dst + c * 32 + j, __uint_as_float(v[j]));
             }
           }
         }
@@ -199,7 +211,11 @@ int launch_wgrad_halo(const void* x, const void* dy, float* dw, int N, int H, in
   memset(&p, 0, sizeof(p));
   p.dw = dw; p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.R = R; p.S = S; p.pad_h = pad_h; p.pad_w = pad_w;
-  p.groups = (R * S + 4) / 5;
+  static int cib_env = -1;
+  if (cib_env < 0) { const char* e = getenv("PASSL_B200_WGRAD_HALO_CIB"); cib_env = e ? atoi(e) : 0; }
+  p.cib = (Cin % 128 == 0 && cib_env != 1) ? 2 : 1;
+  const int tmax = p.cib == 2 ? 3 : 5;               // taps per group: 512 TMEM columns / (64 * cib)
+  p.groups = (R * S + tmax - 1) / tmax;
   p.tpg = (R * S + p.groups - 1) / p.groups;
   p.halo_w = WH_TW + S - 1;
   p.halo_rows = (WH_TH + R - 1) * p.halo_w;
@@ -208,7 +224,7 @@ int launch_wgrad_halo(const void* x, const void* dy, float* dw, int N, int H, in
   p.wb = (W + WH_TW - 1) / WH_TW;
   p.k_total = N * p.hb * p.wb;
   p.m_blocks = (Cout + 127) / 128;
-  p.ci_blocks = Cin / 64;
+  p.ci_blocks = Cin / (64 * p.cib);
   const int base = p.m_blocks * p.ci_blocks * p.groups;
   // every work item ends with a 128 x 320 fp32 red.add epilogue: it needs a long K loop to amortise it, and the grid needs enough
   // items to fill the SMs — small batches stay on the generic kernel (measured: B=64 halo 2x slower, B=1024 halo 1.4x faster)
