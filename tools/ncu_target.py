@@ -108,3 +108,17 @@ if what == "vitgemm":
         K.gemm(a, w1, bias=b1, act="gelu", preact_out=u1, out=o1)
         K.gemm(dy, w2, b_t=True, aux=aux, aux_mode_name="gelu_grad", out=dh)
     torch.cuda.synchronize()
+if what == "conv3":
+    # 3x3 convolutions of ResNet-50 at the bench batch (1024 images): forward, dgrad, wgrad — DRAM traffic vs algorithmic bytes
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+    for (hw, C) in [(56, 64), (14, 256)]:
+        x = torch.randn(B, hw, hw, C, device="cuda").bfloat16()
+        w = torch.randn(C, 3, 3, C, device="cuda").bfloat16()
+        y = K.conv2d_fwd(x, w, stride=1, pad=1)
+        dy = torch.randn_like(y)
+        dw = torch.zeros(C, 3, 3, C, device="cuda")
+        for i in range(2):
+            K.conv2d_fwd(x, w, stride=1, pad=1, out=y)
+            K.conv2d_dgrad(dy, w, tuple(x.shape), stride=1, pad=1)
+            K.conv2d_wgrad(x, dy, (C, 3, 3, C), stride=1, pad=1, out=dw, accumulate=True)
+    torch.cuda.synchronize()
