@@ -31,6 +31,12 @@ enum ActMode : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_QUICKGELU = 3
 constexpr int kMaxTaps = 12;
 constexpr int kEpiWarps = 8;                       // epilogue warps (2 per TMEM lane quarter)
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
+// HALO variant (3x3 stride-1 convolutions): pixel tile 16 rows x 8 columns; ONE TMA box {64 ch, 10, 18} per 64-channel chunk holds
+// every pixel the nine taps touch; tap (r, s) is the K-major view that starts (r * 10 + s) pixel rows into the box, 8-pixel row
+// groups 10 pixels (1280 B) apart (descriptor semantics pinned by umma_probe.cu: shifted start, SBO = 1280, base_offset 0).
+constexpr int kHaloTH = 16, kHaloTW = 8, kHaloW = kHaloTW + 2, kHaloRows = (kHaloTH + 2) * kHaloW;   // 180 pixel rows of 128 B
+constexpr int kHaloBytes = 23 * 1024;              // 180 * 128 = 23040 rounded up to a 1024 multiple
+constexpr int kHaloStages = 2;
 constexpr int kEpiStride = 80;                     // bytes per staged row: 32 bf16 + 16 B pad (conflict-free 16 B accesses)
 
 
@@ -90,16 +96,18 @@ struct GemmParams {
   // ahead of the epilogue (box BN x 128): the epilogue's own one-chunk-ahead register prefetch then only sees L2 latency
   CUtensorMap tile_map;
   int tile_prefetch;
+  int halo_dh0, halo_dw0;   // HALO variant: smallest row / column shift over the taps = origin of the halo box relative to the tile
   int dbg;              // developer perf experiments (PASSL_B200_EPI_DEBUG): 1 skip stats, 2 skip global stores, 4 skip staging
 };
 
-template <int BN, int BK, bool A_MN, bool B_MN, int EPI = 0, int CG = 1>
+template <int BN, int BK, bool A_MN, bool B_MN, int EPI = 0, int CG = 1, bool HALO = false>
 struct GemmSmem {
   static constexpr int BM = 128;
-  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int A_BYTES = HALO ? 0 : BM * BK * 2;     // HALO: the A operand lives in its own ring of halo boxes (after the stages)
+  static constexpr int AH_BYTES = HALO ? kHaloStages * kHaloBytes : 0;
   static constexpr int B_BYTES = BN * BK * 2 / CG;   // CTA pair (CG = 2): each CTA holds BN / 2 rows of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BUDGET = 196 * 1024;
+  static constexpr int BUDGET = 196 * 1024 - AH_BYTES;
   static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int BAR_BYTES = 256;
@@ -107,9 +115,10 @@ struct GemmSmem {
   // EPI 0: per-warp padded staging tiles + bias slices, after the barriers.  EPI 1, 2: per warp two dense 2 KB tiles (32 rows x
   // 64 B, SWIZZLE_64B, the source of the TMA stores) placed right after the stages so that they stay 1024-byte aligned.
   static constexpr int EPI_BYTES = EPI >= 1 ? kEpiWarps * 4096 : kEpiWarps * 32 * kEpiStride + BIAS_BYTES;
-  static constexpr int EPI_OFF = EPI >= 1 ? STAGES * STAGE_BYTES : STAGES * STAGE_BYTES + BAR_BYTES;
-  static constexpr int BAR_OFF = EPI >= 1 ? STAGES * STAGE_BYTES + EPI_BYTES : STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024;  // + alignment slack
+  static constexpr int AH_OFF = STAGES * STAGE_BYTES;
+  static constexpr int EPI_OFF = EPI >= 1 ? AH_OFF + AH_BYTES : AH_OFF + AH_BYTES + BAR_BYTES;
+  static constexpr int BAR_OFF = EPI >= 1 ? AH_OFF + AH_BYTES + EPI_BYTES : AH_OFF + AH_BYTES;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + AH_BYTES + BAR_BYTES + EPI_BYTES + 1024;  // + alignment slack
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static_assert(TOTAL <= 227 * 1024, "shared memory budget");
 };
@@ -250,9 +259,9 @@ __device__ __forceinline__ void issue_operand_load(const GemmOperand& op, const 
 // rows of A and HALF of the B tile, CTA rank 0 issues MMAs of M = 256 that read both shared memories and write both TMEMs, each
 // CTA runs the epilogue of its own 128 rows.  Per MMA flop the pair pulls 2/3 of the bytes from L2 that two independent CTAs
 // would (the 128 x 256 tile of one CTA needs 96 B/clk/SM at full MMA rate, above what the L2 delivers: DESIGN.md 3.2).
-template <int BN, int BK, bool A_MN, bool B_MN, int EPI = 0, int CG = 1>
+template <int BN, int BK, bool A_MN, bool B_MN, int EPI = 0, int CG = 1, bool HALO = false>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
-  using S = GemmSmem<BN, BK, A_MN, B_MN, EPI, CG>;
+  using S = GemmSmem<BN, BK, A_MN, B_MN, EPI, CG, HALO>;
   constexpr int STAGES = S::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -260,7 +269,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* ah_full = tmem_empty + 2;                   // HALO: ring of A halo boxes
+  uint64_t* ah_empty = ah_full + kHaloStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(ah_empty + kHaloStages);
+  uint8_t* ah_smem = smem + S::AH_OFF;
   uint8_t* epi_stage = smem + S::EPI_OFF;                                         // per-warp staging tiles of the epilogue
 
   const uint32_t warp = warp_id();
@@ -283,6 +295,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < kHaloStages; ++i) {
+      mbar_init(&ah_full[i], 1);
+      mbar_init(&ah_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -308,6 +324,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       // ================= TMA producer =================
       int stage = 0;
       uint32_t phase = 0;
+      int ah_stage = 0;
+      uint32_t ah_phase = 0;
       auto produce_residual = [&](int m_blk, int n_blk) {
         for (int r = 0; r < p.res_iters; ++r) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -343,7 +361,33 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         // bytes one stage receives: in a pair both CTAs' loads are counted on the barrier of CTA 0, which alone posts the expectation
         const uint32_t tx = (uint32_t)(p.a.tx_bytes + p.b.tx_bytes) * CG;
         const bool post_tx = CG == 1 || cta_rank == 0;
-        if (p.a.mode == OP_PATCH_K && p.b.mode == OP_MAT_K) {
+        if constexpr (HALO) {
+          // K order: channel chunk outer, filter tap inner.  One halo box per chunk (A ring), one weight tile per (chunk, tap)
+          // (the pipeline stages hold B only).  The weights' K index is (tap * cchunks + chunk) * 64.
+          int n0, h0, w0;
+          decode_patch(p.geom, m_blk, n0, h0, w0);
+          const uint32_t ah_tx = (uint32_t)(kHaloRows * 128) * CG;
+          const uint32_t b_tx = (uint32_t)p.b.tx_bytes * CG;
+          for (int cc = 0; cc < p.a.cchunks; ++cc) {
+            mbar_wait(&ah_empty[ah_stage], ah_phase ^ 1);
+            if (elect_one()) {
+              if (post_tx) mbar_arrive_expect_tx(&ah_full[ah_stage], ah_tx);
+              tma4<CG>(ah_smem + ah_stage * kHaloBytes, &p.a.maps[0], &ah_full[ah_stage], cc * 64, w0 + p.halo_dw0, h0 + p.halo_dh0, n0);
+            }
+            __syncwarp();
+            if (++ah_stage == kHaloStages) { ah_stage = 0; ah_phase ^= 1; }
+            for (int tap = 0; tap < p.a.ntaps; ++tap) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* sa = smem + stage * S::STAGE_BYTES;
+              if (elect_one()) {
+                if (post_tx) mbar_arrive_expect_tx(&full_bar[stage], b_tx);
+                tma2<CG>(sa, &p.b.maps[0], &full_bar[stage], (tap * p.a.cchunks + cc) * BK, b_row0);
+              }
+              __syncwarp();
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        } else if (p.a.mode == OP_PATCH_K && p.b.mode == OP_MAT_K) {
           // implicit-GEMM convolution fast path: patch decoded once per tile, (tap, chunk) advanced with counters —
           // this single thread's instruction latency is on the critical path of every pipeline stage
           int n0, h0, w0;
@@ -416,6 +460,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       const uint64_t db_res0 = make_smem_desc_sw128(smem0 + S::A_BYTES, 64 * 128, 1024);
       int stage = 0;
       uint32_t phase = 0;
+      int ah_stage = 0;
+      uint32_t ah_phase = 0;
       int it = 0;
       for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++it) {
         int split = tile % p.splits;
@@ -426,6 +472,33 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
+        if constexpr (HALO) {
+          const uint64_t dah0 = make_smem_desc_sw128(smem_u32(ah_smem), 16, kHaloW * 128);
+          for (int cc = 0; cc < p.a.cchunks; ++cc) {
+            mbar_wait(&ah_full[ah_stage], ah_phase);
+            tc_fence_after();
+            for (int tap = 0; tap < p.a.ntaps; ++tap) {
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              const int shift = (p.a.dh[tap] - p.halo_dh0) * kHaloW + (p.a.dw[tap] - p.halo_dw0);     // pixel rows into the box
+              const uint64_t da = dah0 + (uint64_t)((ah_stage * kHaloBytes + shift * 128) >> 4);
+              const uint64_t db = db0 + (uint64_t)stage * kStage;
+              if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma(d_tmem, da + k * 2, db + k * kStepB, idesc, (cc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                commit(&empty_bar[stage]);
+                if (tap == p.a.ntaps - 1) {
+                  commit(&ah_empty[ah_stage]);
+                  if (cc == p.a.cchunks - 1) commit(&tmem_full[acc]);
+                }
+              }
+              __syncwarp();
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (++ah_stage == kHaloStages) { ah_stage = 0; ah_phase ^= 1; }
+          }
+          continue;
+        }
         for (int kit = k_begin; kit < k_end; ++kit) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();

@@ -53,10 +53,10 @@ static int setup_residual_mma(GemmParams& p, const void* residual, long long ldc
   return PB_OK;
 }
 
-template <int BN, int BK, bool A_MN, bool B_MN, int EPI = 0, int CG = 1>
+template <int BN, int BK, bool A_MN, bool B_MN, int EPI = 0, int CG = 1, bool HALO = false>
 static int launch_gemm_t(const GemmParams& p, cudaStream_t st) {
-  using S = GemmSmem<BN, BK, A_MN, B_MN, EPI, CG>;
-  auto kern = gemm_tcgen05_kernel<BN, BK, A_MN, B_MN, EPI, CG>;
+  using S = GemmSmem<BN, BK, A_MN, B_MN, EPI, CG, HALO>;
+  auto kern = gemm_tcgen05_kernel<BN, BK, A_MN, B_MN, EPI, CG, HALO>;
   static bool attr_set = false;
   if (!attr_set) {
     PB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
@@ -107,7 +107,15 @@ static bool pair_eligible(const GemmParams& p, int BN, int BK, bool a_mn) {
          p.k_iters >= mink && (long long)((p.m_blocks + 1) / 2) * p.n_blocks * p.splits >= num_sms() / 2;
 }
 
-static int launch_gemm(const GemmParams& p, int BN, int BK, bool a_mn, bool b_mn, cudaStream_t st, int epi = 0, int cg = 1) {
+static int launch_gemm(const GemmParams& p, int BN, int BK, bool a_mn, bool b_mn, cudaStream_t st, int epi = 0, int cg = 1,
+                       bool halo = false) {
+  if (halo) {      // 3x3 stride-1 convolutions with the halo-box A operand (gemm.cuh HALO)
+    if (BK != 64 || a_mn || b_mn || epi != 0) return PB_ERR_UNSUPPORTED;
+    if (BN == 256) return cg == 2 ? launch_gemm_t<256, 64, false, false, 0, 2, true>(p, st) : launch_gemm_t<256, 64, false, false, 0, 1, true>(p, st);
+    if (BN == 128) return launch_gemm_t<128, 64, false, false, 0, 1, true>(p, st);
+    if (BN == 64) return launch_gemm_t<64, 64, false, false, 0, 1, true>(p, st);
+    return PB_ERR_UNSUPPORTED;
+  }
   if (cg == 2 && BN == 256 && BK == 64 && a_mn && b_mn && epi == 0) return launch_gemm_t<256, 64, true, true, 0, 2>(p, st);
   if (cg == 2 && BN == 256 && BK == 64 && !a_mn) {
     if (epi == 2 && !b_mn) return launch_gemm_t<256, 64, false, false, 2, 2>(p, st);
@@ -178,6 +186,41 @@ static void pick_patch(PatchGeom& g, int Nimg, int Ho, int Wo) {
   g.wb = (Wo + g.TW - 1) / g.TW;
   g.hb = (Ho + g.TH - 1) / g.TH;
   g.nb = (Nimg + g.TN - 1) / g.TN;
+}
+
+// 3x3 (or any <= 3x3, stride 1) convolution through ONE halo box per channel chunk (gemm.cuh HALO): 16 x 8 pixel tiles of one image.
+// PASSL_B200_CONV_HALO=0 keeps the per-tap loads.
+static bool conv_halo_ok(int H, int W, int ntaps, const signed char* dh, const signed char* dw, int& dh0, int& dw0) {
+  static int en = -1;
+  if (en < 0) { const char* e = getenv("PASSL_B200_CONV_HALO"); en = (e && !atoi(e)) ? 0 : 1; }
+  if (!en || H < 12 || W < 8 || ntaps < 2) return false;
+  int hmin = 127, hmax = -127, wmin = 127, wmax = -127;
+  for (int t = 0; t < ntaps; ++t) {
+    hmin = dh[t] < hmin ? dh[t] : hmin; hmax = dh[t] > hmax ? dh[t] : hmax;
+    wmin = dw[t] < wmin ? dw[t] : wmin; wmax = dw[t] > wmax ? dw[t] : wmax;
+  }
+  if (hmax - hmin > 2 || wmax - wmin > 2) return false;
+  // the 16 x 8 tile must cover the image about as well as the row-major 128-pixel patches do (28 x 28: 77 % vs 87.5 % -> no)
+  PatchGeom g0;
+  pick_patch(g0, 1, H, W);
+  const double u_old = (double)H * W / ((double)g0.hb * g0.wb * 128.0);
+  const double u_halo = (double)H * W / ((double)((H + kHaloTH - 1) / kHaloTH) * ((W + kHaloTW - 1) / kHaloTW) * 128.0);
+  if (u_halo < 0.95 * u_old) return false;
+  dh0 = hmin; dw0 = wmin;
+  return true;
+}
+static void halo_geom(PatchGeom& g, int Nimg, int Ho, int Wo) {
+  g.Nimg = Nimg; g.Ho = Ho; g.Wo = Wo;
+  g.TN = 1; g.TH = kHaloTH; g.TW = kHaloTW;
+  g.wb = (Wo + g.TW - 1) / g.TW;
+  g.hb = (Ho + g.TH - 1) / g.TH;
+  g.nb = Nimg;
+}
+static int fill_halo_map(GemmOperand& op, const void* base, int N, int H, int W, int C) {
+  uint32_t box[4] = {64, (uint32_t)kHaloW, (uint32_t)(kHaloTH + 2), 1};
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+  uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+  return make_tmap_bf16(&op.maps[0], base, 4, dims, str, box);
 }
 
 static inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
@@ -321,7 +364,17 @@ static int conv_fwd_impl(const void* x, const void* w, void* out, int N, int H, 
     return passl_b200_gemm_bf16(x, w, out, N * H * W, Cout, Cin, 0, 0, Cin, Cin, Cout, 0, 0, bias, residual, act,
                                 1.f, 1, col_sum, col_sqsum, stream);
   }
-  pick_patch(p.geom, N, Ho, Wo);
+  for (int r = 0; r < R; ++r)
+    for (int s = 0; s < S; ++s) {
+      int t = r * S + s;
+      int th = r - pad, tw = s - pad_w;
+      p.a.dh[t] = (signed char)floordiv(th, stride);
+      p.a.dw[t] = (signed char)floordiv(tw, stride);
+      p.a.map[t] = (signed char)(stride == 1 ? 0 : posmod(th, 2) * 2 + posmod(tw, 2));
+    }
+  const bool halo = stride == 1 && Ho == H && Wo == W && !residual && conv_halo_ok(H, W, R * S, p.a.dh, p.a.dw, p.halo_dh0, p.halo_dw0);
+  if (halo) halo_geom(p.geom, N, Ho, Wo);
+  else pick_patch(p.geom, N, Ho, Wo);
   p.M = N * Ho * Wo; p.N = Cout;
   p.m_blocks = p.geom.nb * p.geom.hb * p.geom.wb;
   int BN = pick_bn(p.m_blocks, Cout);
@@ -331,15 +384,7 @@ static int conv_fwd_impl(const void* x, const void* w, void* out, int N, int H, 
   p.a.cchunks = Cin / 64;
   p.a.ntaps = R * S;
   p.a.tx_bytes = p.geom.TN * p.geom.TH * p.geom.TW * 128;
-  for (int r = 0; r < R; ++r)
-    for (int s = 0; s < S; ++s) {
-      int t = r * S + s;
-      int th = r - pad, tw = s - pad_w;
-      p.a.dh[t] = (signed char)floordiv(th, stride);
-      p.a.dw[t] = (signed char)floordiv(tw, stride);
-      p.a.map[t] = (signed char)(stride == 1 ? 0 : posmod(th, 2) * 2 + posmod(tw, 2));
-    }
-  int rc = fill_patch_maps(p.a, x, N, H, W, Cin, stride, p.geom);
+  int rc = halo ? fill_halo_map(p.a, x, N, H, W, Cin) : fill_patch_maps(p.a, x, N, H, W, Cin, stride, p.geom);
   if (rc) return rc;
   p.k_iters = R * S * p.a.cchunks;
   p.k_steps = 4;
@@ -348,7 +393,7 @@ static int conv_fwd_impl(const void* x, const void* w, void* out, int N, int H, 
   if (rc) return rc;
   set_epilogue(p, out, Cout, 0, 0, bias, residual, act, 1.f, col_sum, col_sqsum);
   p.out_pixel = 1; p.OH = Ho; p.OW = Wo; p.osh = 1; p.osw = 1; p.oh0 = 0; p.ow0 = 0;
-  return launch_gemm(p, BN, 64, false, false, (cudaStream_t)stream, 0, cg);
+  return launch_gemm(p, BN, 64, false, false, (cudaStream_t)stream, 0, cg, halo);
 }
 
 extern "C" int passl_b200_conv2d_fwd_bf16(const void* x, const void* w, void* out, int N, int H, int W, int Cin,
@@ -458,7 +503,10 @@ extern "C" int passl_b200_conv2d_dgrad_bf16(const void* dy, const void* w, void*
     GemmParams p;
     memset(&p, 0, sizeof(p));
     const int Hc = H / stride, Wc = W / stride;  // class pixel grid
-    pick_patch(p.geom, N, Hc, Wc);
+    for (int t = 0; t < k.ntaps; ++t) { p.a.dh[t] = (signed char)k.dh[t]; p.a.dw[t] = (signed char)k.dw[t]; p.a.map[t] = 0; }
+    const bool halo = stride == 1 && Ho == H && Wo == W && conv_halo_ok(Ho, Wo, k.ntaps, p.a.dh, p.a.dw, p.halo_dh0, p.halo_dw0);
+    if (halo) halo_geom(p.geom, N, Hc, Wc);
+    else pick_patch(p.geom, N, Hc, Wc);
     p.M = N * Hc * Wc; p.N = Cin;
     p.m_blocks = p.geom.nb * p.geom.hb * p.geom.wb;
     int BN = pick_bn(p.m_blocks, Cin);
@@ -468,8 +516,7 @@ extern "C" int passl_b200_conv2d_dgrad_bf16(const void* dy, const void* w, void*
     p.a.cchunks = Cout / 64;
     p.a.ntaps = k.ntaps;
     p.a.tx_bytes = p.geom.TN * p.geom.TH * p.geom.TW * 128;
-    for (int t = 0; t < k.ntaps; ++t) { p.a.dh[t] = (signed char)k.dh[t]; p.a.dw[t] = (signed char)k.dw[t]; p.a.map[t] = 0; }
-    int rc = fill_patch_maps(p.a, dy, N, Ho, Wo, Cout, 1, p.geom);
+    int rc = halo ? fill_halo_map(p.a, dy, N, Ho, Wo, Cout) : fill_patch_maps(p.a, dy, N, Ho, Wo, Cout, 1, p.geom);
     if (rc) return rc;
     p.k_iters = k.ntaps * p.a.cchunks;
     p.k_steps = 4;
@@ -478,7 +525,7 @@ extern "C" int passl_b200_conv2d_dgrad_bf16(const void* dy, const void* w, void*
     if (rc) return rc;
     set_epilogue(p, dx, Cin, 0, 0, nullptr, accumulate ? dx : nullptr, ACT_NONE, 1.f, nullptr, nullptr);
     p.out_pixel = 1; p.OH = H; p.OW = W; p.osh = stride; p.osw = stride; p.oh0 = k.a; p.ow0 = k.b;
-    rc = launch_gemm(p, BN, 64, false, false, st, 0, cg);
+    rc = launch_gemm(p, BN, 64, false, false, st, 0, cg, halo);
     if (rc) return rc;
     wt += (size_t)Cin * k.ntaps * Cout;
   }
