@@ -383,6 +383,9 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION (the default of some launchers); the contract is ONE JSON line
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     from passl_b200 import _lib, kernels as K
     lib = _lib.load()
