@@ -113,7 +113,7 @@ static int launch_gemm(const GemmParams& p, int BN, int BK, bool a_mn, bool b_mn
     if (BK != 64 || a_mn || b_mn || epi != 0) return PB_ERR_UNSUPPORTED;
     if (BN == 256) return cg == 2 ? launch_gemm_t<256, 64, false, false, 0, 2, true>(p, st) : launch_gemm_t<256, 64, false, false, 0, 1, true>(p, st);
     if (BN == 128) return launch_gemm_t<128, 64, false, false, 0, 1, true>(p, st);
-    if (BN == 64) return launch_gemm_t<64, 64, false, false, 0, 1, true>(p, st);
+    if (BN == 64) return cg == 2 ? launch_gemm_t<64, 64, false, false, 0, 2, true>(p, st) : launch_gemm_t<64, 64, false, false, 0, 1, true>(p, st);
     return PB_ERR_UNSUPPORTED;
   }
   if (cg == 2 && BN == 256 && BK == 64 && a_mn && b_mn && epi == 0) return launch_gemm_t<256, 64, true, true, 0, 2>(p, st);
@@ -388,7 +388,9 @@ static int conv_fwd_impl(const void* x, const void* w, void* out, int N, int H, 
   if (rc) return rc;
   p.k_iters = R * S * p.a.cchunks;
   p.k_steps = 4;
-  const int cg = pair_eligible(p, BN, 64, false) ? 2 : 1;
+  // 64-wide halo tiles are bound by the shared-memory reads of an M = 128 x N = 64 MMA (A 4 KB + B 2 KB per 16 clk); a CTA pair
+  // halves the B share per CTA
+  const int cg = (pair_eligible(p, BN, 64, false) || (halo && BN == 64 && pair_eligible(p, 256, 64, false))) ? 2 : 1;
   rc = fill_mat_operand(p.b, w, false, Cout, (long long)R * S * Cin, (long long)R * S * Cin, BN / cg, 64);
   if (rc) return rc;
   set_epilogue(p, out, Cout, 0, 0, bias, residual, act, 1.f, col_sum, col_sqsum);
@@ -520,7 +522,7 @@ extern "C" int passl_b200_conv2d_dgrad_bf16(const void* dy, const void* w, void*
     if (rc) return rc;
     p.k_iters = k.ntaps * p.a.cchunks;
     p.k_steps = 4;
-    const int cg = pair_eligible(p, BN, 64, false) ? 2 : 1;
+    const int cg = (pair_eligible(p, BN, 64, false) || (halo && BN == 64 && pair_eligible(p, 256, 64, false))) ? 2 : 1;
     rc = fill_mat_operand(p.b, wt, false, Cin, (long long)k.ntaps * Cout, (long long)k.ntaps * Cout, BN / cg, 64);
     if (rc) return rc;
     set_epilogue(p, dx, Cin, 0, 0, nullptr, accumulate ? dx : nullptr, ACT_NONE, 1.f, nullptr, nullptr);
