@@ -100,21 +100,25 @@ struct GemmParams {
   int dbg;              // developer perf experiments (PASSL_B200_EPI_DEBUG): 1 skip stats, 2 skip global stores, 4 skip staging
 };
 
-template <int BN, int BK, bool A_MN, bool B_MN, int EPI = 0, int CG = 1, bool HALO = false>
+// EW = number of epilogue warps: 8 (two per TMEM lane quarter), or 16 for the epilogue-bound linear launches (GELU / gate
+// arithmetic): four warps per sub-partition hide the MUFU / TMEM / shared-memory latencies that two cannot; 576 threads leave 112
+// registers per thread, so that variant reads the accumulator in place (no read-ahead) and pays for its 64 KB of staging tiles
+// with one pipeline stage.
+template <int BN, int BK, bool A_MN, bool B_MN, int EPI = 0, int CG = 1, bool HALO = false, int EW = kEpiWarps>
 struct GemmSmem {
   static constexpr int BM = 128;
   static constexpr int A_BYTES = HALO ? 0 : BM * BK * 2;     // HALO: the A operand lives in its own ring of halo boxes (after the stages)
   static constexpr int AH_BYTES = HALO ? kHaloStages * kHaloBytes : 0;
   static constexpr int B_BYTES = BN * BK * 2 / CG;   // CTA pair (CG = 2): each CTA holds BN / 2 rows of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BUDGET = 196 * 1024 - AH_BYTES;
+  static constexpr int BUDGET = 196 * 1024 - AH_BYTES - (EW > 8 ? (EW - 8) * 4096 : 0);
   static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int BIAS_BYTES = kEpiWarps * 4 * 32 * 4;              // per-warp bias slices of the current tile (4 chunks x 32 columns, fp32)
+  static constexpr int BIAS_BYTES = EW * 4 * 32 * 4;              // per-warp bias slices of the current tile (4 chunks x 32 columns, fp32)
   // EPI 0: per-warp padded staging tiles + bias slices, after the barriers.  EPI 1, 2: per warp two dense 2 KB tiles (32 rows x
   // 64 B, SWIZZLE_64B, the source of the TMA stores) placed right after the stages so that they stay 1024-byte aligned.
-  static constexpr int EPI_BYTES = EPI >= 1 ? kEpiWarps * 4096 : kEpiWarps * 32 * kEpiStride + BIAS_BYTES;
+  static constexpr int EPI_BYTES = EPI >= 1 ? EW * 4096 : EW * 32 * kEpiStride + BIAS_BYTES;
   static constexpr int AH_OFF = STAGES * STAGE_BYTES;
   static constexpr int EPI_OFF = EPI >= 1 ? AH_OFF + AH_BYTES : AH_OFF + AH_BYTES + BAR_BYTES;
   static constexpr int BAR_OFF = EPI >= 1 ? AH_OFF + AH_BYTES + EPI_BYTES : AH_OFF + AH_BYTES;
@@ -259,9 +263,10 @@ __device__ __forceinline__ void issue_operand_load(const GemmOperand& op, const 
 // rows of A and HALF of the B tile, CTA rank 0 issues MMAs of M = 256 that read both shared memories and write both TMEMs, each
 // CTA runs the epilogue of its own 128 rows.  Per MMA flop the pair pulls 2/3 of the bytes from L2 that two independent CTAs
 // would (the 128 x 256 tile of one CTA needs 96 B/clk/SM at full MMA rate, above what the L2 delivers: DESIGN.md 3.2).
-template <int BN, int BK, bool A_MN, bool B_MN, int EPI = 0, int CG = 1, bool HALO = false>
-__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
-  using S = GemmSmem<BN, BK, A_MN, B_MN, EPI, CG, HALO>;
+template <int BN, int BK, bool A_MN, bool B_MN, int EPI = 0, int CG = 1, bool HALO = false, int EW = kEpiWarps>
+__global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+  using S = GemmSmem<BN, BK, A_MN, B_MN, EPI, CG, HALO, EW>;
+  static_assert(EW == 8 || (EW == 16 && EPI == 1), "16 epilogue warps: linear-layer epilogue only");
   constexpr int STAGES = S::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -302,7 +307,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], kEpiWarps * CG);   // pair: the issuing CTA waits for the epilogue warps of both CTAs
+      mbar_init(&tmem_empty[i], EW * CG);   // pair: the issuing CTA waits for the epilogue warps of both CTAs
     }
     fence_barrier_init();
   }
@@ -556,7 +561,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     const uint32_t stg0 = smem_u32(epi_stage + e * 4096);
     const uint32_t swz = (lane >> 1) & 3u;                     // SWIZZLE_64B: 16-byte slot ^= (row >> 1) & 3
     const int crow = (int)(lane >> 2), cch = (int)(lane & 3);  // row-coalesced operand copies: 8 rows x 64 B per instruction
-    constexpr int NCH = (BN / 64) > 0 ? (BN / 64) : 1;
+    constexpr int HALVES = EW / 4;                                   // warps per TMEM lane quarter = stride of a warp's chunks
+    constexpr int NCH = (BN / 32 + HALVES - 1) / HALVES;             // 32-column chunks per epilogue warp
+    constexpr bool kReadAhead = EW <= 8;                             // 16 warps: 112 registers, the accumulator is read in place
     // at most one operand tile enters the epilogue: the gate's pre-activation (aux) or a residual that could not go through the MMA.
     // It is copied global -> shared with cp.async (no registers, issued one chunk ahead into the second 2 KB tile of this warp;
     // the producer has already pulled the whole 128 x BN operand tile into L2); without an operand both tiles alternate as
@@ -611,7 +618,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         if (lane < 16) {
 #pragma unroll
           for (int i = 0; i < NCH; ++i) {
-            const int col = nblk_ * BN + ((int)half + 2 * i) * 32 + (int)lane * 2;
+            const int col = nblk_ * BN + ((int)half + HALVES * i) * 32 + (int)lane * 2;
             if (col < p.N) {
               part[col] += sacc[i][0]; part[col + 1] += sacc[i][1];
               part[p.N + col] += sacc[i][2]; part[p.N + col + 1] += sacc[i][3];
@@ -658,15 +665,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       const uint32_t t_addr = tmem_base + ((q * 32u) << 16) + acc * BN;
       // the accumulator is read one chunk ahead of the arithmetic
       uint32_t v[32];
-      if ((int)half < BN / 32 && col0 + (int)half * 32 < p.N) tmem_ld_32x32(t_addr + half * 32, v);
+      if (kReadAhead && (int)half < BN / 32 && col0 + (int)half * 32 < p.N) tmem_ld_32x32(t_addr + half * 32, v);
 #pragma unroll 1
       for (int ci = 0; ci < NCH; ++ci) {
-        const int c = (int)half + 2 * ci;
+        const int c = (int)half + HALVES * ci;
         if (c >= BN / 32) break;
         const int cc0 = col0 + c * 32;
         if (cc0 >= p.N) break;
+        if constexpr (!kReadAhead) tmem_ld_32x32(t_addr + c * 32, v);
         float4 bv[8];
-        if (p.bias) {
+        if (kReadAhead && p.bias) {
           if (cc0 + 32 <= p.N) {
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) bv[j4] = __ldg(reinterpret_cast<const float4*>(p.bias + cc0) + j4);
@@ -682,8 +690,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (ci + 1 < NCH && c + 2 < BN / 32 && cc0 + 64 < p.N) {
-          tmem_ld_32x32(t_addr + (c + 2) * 32, v);
+        const bool more = ci + 1 < NCH && c + HALVES < BN / 32 && cc0 + 32 * HALVES < p.N;
+        if (more) {
+          if constexpr (kReadAhead) tmem_ld_32x32(t_addr + (c + HALVES) * 32, v);
         } else {
           tc_fence_before();
           __syncwarp();
@@ -691,9 +700,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           released = true;
         }
         if (p.bias) {
+          if constexpr (kReadAhead) {
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            f[j4 * 4 + 0] += bv[j4].x; f[j4 * 4 + 1] += bv[j4].y; f[j4 * 4 + 2] += bv[j4].z; f[j4 * 4 + 3] += bv[j4].w;
+            for (int j4 = 0; j4 < 8; ++j4) {
+              f[j4 * 4 + 0] += bv[j4].x; f[j4 * 4 + 1] += bv[j4].y; f[j4 * 4 + 2] += bv[j4].z; f[j4 * 4 + 3] += bv[j4].w;
+            }
+          } else {            // L1-resident broadcast loads, consumed four values at a time (N % 8 == 0)
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              if (cc0 + j4 * 4 < p.N) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cc0) + j4);
+                f[j4 * 4 + 0] += b4.x; f[j4 * 4 + 1] += b4.y; f[j4 * 4 + 2] += b4.z; f[j4 * 4 + 3] += b4.w;
+              }
+            }
           }
         }
         uint32_t pbuf = 0;
@@ -726,7 +745,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             for (int j8 = 0; j8 < 4; ++j8) apply_gate8<4>(f + j8 * 8, ld_shared_v4(obuf + lane * 64u + ((j8 ^ swz) << 4)));
           }
           __syncwarp();
-          if (ci + 1 < NCH) copy_tile(c + 2);       // the tile is free again: next chunk's operand
+          if (ci + 1 < NCH) copy_tile(c + HALVES);       // the tile is free again: next chunk's operand
         }
         const uint32_t sbuf = stage_box(f, row0);
         if constexpr (EPI == 2) {
@@ -779,7 +798,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     const uint32_t q = warp & 3;
     const uint32_t half = e >> 2;
     uint8_t* stg = epi_stage + e * (32 * kEpiStride);
-    const uint32_t bias_u32 = smem_u32(epi_stage + kEpiWarps * 32 * kEpiStride + e * (4 * 32 * 4));
+    const uint32_t bias_u32 = smem_u32(epi_stage + EW * 32 * kEpiStride + e * (4 * 32 * 4));
     const uint32_t stg_u32 = smem_u32(stg);
     const bool staged = !p.out_fp32;
     const bool do_stats = staged && p.col_sum != nullptr && !(p.dbg & 1);

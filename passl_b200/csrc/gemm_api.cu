@@ -53,10 +53,11 @@ static int setup_residual_mma(GemmParams& p, const void* residual, long long ldc
   return PB_OK;
 }
 
-template <int BN, int BK, bool A_MN, bool B_MN, int EPI = 0, int CG = 1, bool HALO = false>
+template <int BN, int BK, bool A_MN, bool B_MN, int EPI = 0, int CG = 1, bool HALO = false, int EW = kEpiWarps>
 static int launch_gemm_t(const GemmParams& p, cudaStream_t st) {
-  using S = GemmSmem<BN, BK, A_MN, B_MN, EPI, CG, HALO>;
-  auto kern = gemm_tcgen05_kernel<BN, BK, A_MN, B_MN, EPI, CG, HALO>;
+  using S = GemmSmem<BN, BK, A_MN, B_MN, EPI, CG, HALO, EW>;
+  auto kern = gemm_tcgen05_kernel<BN, BK, A_MN, B_MN, EPI, CG, HALO, EW>;
+  constexpr int kThreads = 64 + 32 * EW;
   static bool attr_set = false;
   if (!attr_set) {
     PB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
@@ -77,7 +78,7 @@ static int launch_gemm_t(const GemmParams& p, cudaStream_t st) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kGemmThreads);
+    cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = S::TOTAL;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -87,7 +88,7 @@ static int launch_gemm_t(const GemmParams& p, cudaStream_t st) {
     PB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
     return PB_OK;
   }
-  kern<<<grid, kGemmThreads, S::TOTAL, st>>>(p);
+  kern<<<grid, kThreads, S::TOTAL, st>>>(p);
   PB_LAUNCH_CHECK();
   return PB_OK;
 }
@@ -108,12 +109,14 @@ static bool pair_eligible(const GemmParams& p, int BN, int BK, bool a_mn) {
 }
 
 static int launch_gemm(const GemmParams& p, int BN, int BK, bool a_mn, bool b_mn, cudaStream_t st, int epi = 0, int cg = 1,
-                       bool halo = false) {
+                       bool halo = false, int ew = 8) {
+  if (ew == 16 && epi == 1 && cg == 1 && BN == 256 && BK == 64 && !a_mn && !halo)   // epilogue-bound linear launches (GELU / gates)
+    return b_mn ? launch_gemm_t<256, 64, false, true, 1, 1, false, 16>(p, st) : launch_gemm_t<256, 64, false, false, 1, 1, false, 16>(p, st);
   if (halo) {      // 3x3 stride-1 convolutions with the halo-box A operand (gemm.cuh HALO)
     if (BK != 64 || a_mn || b_mn || epi != 0) return PB_ERR_UNSUPPORTED;
     if (BN == 256) return cg == 2 ? launch_gemm_t<256, 64, false, false, 0, 2, true>(p, st) : launch_gemm_t<256, 64, false, false, 0, 1, true>(p, st);
     if (BN == 128) return launch_gemm_t<128, 64, false, false, 0, 1, true>(p, st);
-    if (BN == 64) return cg == 2 ? launch_gemm_t<64, 64, false, false, 0, 2, true>(p, st) : launch_gemm_t<64, 64, false, false, 0, 1, true>(p, st);
+    if (BN == 64) return launch_gemm_t<64, 64, false, false, 0, 1, true>(p, st);
     return PB_ERR_UNSUPPORTED;
   }
   if (cg == 2 && BN == 256 && BK == 64 && a_mn && b_mn && epi == 0) return launch_gemm_t<256, 64, true, true, 0, 2>(p, st);
@@ -344,7 +347,13 @@ extern "C" int passl_b200_gemm_bf16_ex(const void* A, const void* B, void* out, 
     }
     epi = col_sum ? 2 : 1;
   }
-  return launch_gemm(p, BN, 64, a_mn_major != 0, b_mn_major != 0, (cudaStream_t)stream, epi, cg);
+  static int ew16 = -1;
+  if (ew16 < 0) { const char* e = getenv("PASSL_B200_GEMM_EW16"); ew16 = (e && !atoi(e)) ? 0 : 1; }
+  // 16 epilogue warps (3 pipeline stages, accumulator read in place): fc2-dgrad with the GELU' gate 647 -> 801 TF/s at the CLIP
+  // batch, 597 -> 760 at the MAE decoder's; fc1 forward (+GELU, saved pre-activation) gains only with a short K loop (K = 512:
+  // 746 -> 783, K = 768: 940 -> 917), `profiles/r02_vit_gemm_probe_ew16.txt`
+  const bool use16 = ew16 && ((aux && aux_mode >= 2) || ((act == ACT_GELU || act == ACT_QUICKGELU) && K < 768));
+  return launch_gemm(p, BN, 64, a_mn_major != 0, b_mn_major != 0, (cudaStream_t)stream, epi, cg, false, use16 ? 16 : 8);
 }
 
 extern "C" int passl_b200_gemm_stats_rows(void) { return 4 * num_sms(); }
@@ -388,9 +397,8 @@ static int conv_fwd_impl(const void* x, const void* w, void* out, int N, int H, 
   if (rc) return rc;
   p.k_iters = R * S * p.a.cchunks;
   p.k_steps = 4;
-  // 64-wide halo tiles are bound by the shared-memory reads of an M = 128 x N = 64 MMA (A 4 KB + B 2 KB per 16 clk); a CTA pair
-  // halves the B share per CTA
-  const int cg = (pair_eligible(p, BN, 64, false) || (halo && BN == 64 && pair_eligible(p, 256, 64, false))) ? 2 : 1;
+  // (CTA pairs on the 64-wide halo tiles were measured and dropped: 64 ch at 56x56 forward 453 -> 545 us, dgrad 427 -> 501 us)
+  const int cg = pair_eligible(p, BN, 64, false) ? 2 : 1;
   rc = fill_mat_operand(p.b, w, false, Cout, (long long)R * S * Cin, (long long)R * S * Cin, BN / cg, 64);
   if (rc) return rc;
   set_epilogue(p, out, Cout, 0, 0, bias, residual, act, 1.f, col_sum, col_sqsum);
@@ -522,7 +530,7 @@ extern "C" int passl_b200_conv2d_dgrad_bf16(const void* dy, const void* w, void*
     if (rc) return rc;
     p.k_iters = k.ntaps * p.a.cchunks;
     p.k_steps = 4;
-    const int cg = (pair_eligible(p, BN, 64, false) || (halo && BN == 64 && pair_eligible(p, 256, 64, false))) ? 2 : 1;
+    const int cg = pair_eligible(p, BN, 64, false) ? 2 : 1;
     rc = fill_mat_operand(p.b, wt, false, Cin, (long long)k.ntaps * Cout, (long long)k.ntaps * Cout, BN / cg, 64);
     if (rc) return rc;
     set_epilogue(p, dx, Cin, 0, 0, nullptr, accumulate ? dx : nullptr, ACT_NONE, 1.f, nullptr, nullptr);
