@@ -110,8 +110,10 @@ static bool pair_eligible(const GemmParams& p, int BN, int BK, bool a_mn) {
 
 static int launch_gemm(const GemmParams& p, int BN, int BK, bool a_mn, bool b_mn, cudaStream_t st, int epi = 0, int cg = 1,
                        bool halo = false, int ew = 8) {
-  if (ew == 16 && epi == 1 && cg == 1 && BN == 256 && BK == 64 && !a_mn && !halo)   // epilogue-bound linear launches (GELU / gates)
+  if (ew == 16 && epi == 1 && BN == 256 && BK == 64 && !a_mn && !halo) {   // epilogue-bound linear launches (GELU / gates)
+    if (cg == 2) return b_mn ? launch_gemm_t<256, 64, false, true, 1, 2, false, 16>(p, st) : launch_gemm_t<256, 64, false, false, 1, 2, false, 16>(p, st);
     return b_mn ? launch_gemm_t<256, 64, false, true, 1, 1, false, 16>(p, st) : launch_gemm_t<256, 64, false, false, 1, 1, false, 16>(p, st);
+  }
   if (halo) {      // 3x3 stride-1 convolutions with the halo-box A operand (gemm.cuh HALO)
     if (BK != 64 || a_mn || b_mn || epi != 0) return PB_ERR_UNSUPPORTED;
     if (BN == 256) return cg == 2 ? launch_gemm_t<256, 64, false, false, 0, 2, true>(p, st) : launch_gemm_t<256, 64, false, false, 0, 1, true>(p, st);
@@ -310,7 +312,15 @@ extern "C" int passl_b200_gemm_bf16_ex(const void* A, const void* B, void* out, 
   // CTA pairs: each CTA loads half of the B tile (its own box of BN / 2 rows); the residual then enters through the epilogue
   // not for epilogue-bound launches (GELU / gate arithmetic: the pair couples two epilogues to one MMA stream, measured 5 % slower),
   // nor when a residual could ride the MMA of a short K loop instead of the epilogue (proj of ViT-B: 999 vs 917 TF/s)
-  const bool heavy_epi = act == ACT_GELU || act == ACT_QUICKGELU || (aux && aux_mode >= 2);
+  // GELU / gate launches: epilogue-bound.  With 8 epilogue warps a pair only couples two slow epilogues to one MMA stream (-5 %);
+  // with 16 warps per CTA and K >= 768 the pair wins (fc2-dgrad + GELU' 817 -> 1011 TF/s, fc1 + GELU 1017 -> 1064 at the CLIP batch;
+  // K = 512: 798 -> 753, so those stay single).  PASSL_B200_GEMM_HEAVY_PAIR=0 / PASSL_B200_GEMM_EW16=0 switch the two off.
+  static int heavy_pair = -1, ew16 = -1;
+  if (heavy_pair < 0) { const char* e = getenv("PASSL_B200_GEMM_HEAVY_PAIR"); heavy_pair = (e && !atoi(e)) ? 0 : 1; }
+  if (ew16 < 0) { const char* e = getenv("PASSL_B200_GEMM_EW16"); ew16 = (e && !atoi(e)) ? 0 : 1; }
+  const bool heavy = act == ACT_GELU || act == ACT_QUICKGELU || (aux && aux_mode >= 2);
+  const bool heavy_pair_ok = heavy && heavy_pair && ew16 && K >= 768;
+  const bool heavy_epi = heavy && !heavy_pair_ok;
   const bool short_k_residual = residual && K < 1536;
   const int cg = (wgrad_pair || (!heavy_epi && !short_k_residual && pair_eligible(p, BN, 64, a_mn_major != 0))) ? 2 : 1;
   r = fill_mat_operand(p.b, B, b_mn_major != 0, N, K, ldb, BN / cg, 64);
@@ -347,12 +357,10 @@ extern "C" int passl_b200_gemm_bf16_ex(const void* A, const void* B, void* out, 
     }
     epi = col_sum ? 2 : 1;
   }
-  static int ew16 = -1;
-  if (ew16 < 0) { const char* e = getenv("PASSL_B200_GEMM_EW16"); ew16 = (e && !atoi(e)) ? 0 : 1; }
   // 16 epilogue warps (3 pipeline stages, accumulator read in place): fc2-dgrad with the GELU' gate 647 -> 801 TF/s at the CLIP
   // batch, 597 -> 760 at the MAE decoder's; fc1 forward (+GELU, saved pre-activation) gains only with a short K loop (K = 512:
   // 746 -> 783, K = 768: 940 -> 917), `profiles/r02_vit_gemm_probe_ew16.txt`
-  const bool use16 = ew16 && ((aux && aux_mode >= 2) || ((act == ACT_GELU || act == ACT_QUICKGELU) && K < 768));
+  const bool use16 = ew16 && ((aux && aux_mode >= 2) || ((act == ACT_GELU || act == ACT_QUICKGELU) && (K < 768 || (heavy_pair_ok && cg == 2))));
   return launch_gemm(p, BN, 64, a_mn_major != 0, b_mn_major != 0, (cudaStream_t)stream, epi, cg, false, use16 ? 16 : 8);
 }
 
