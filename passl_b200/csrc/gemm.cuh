@@ -266,7 +266,7 @@ __device__ __forceinline__ void issue_operand_load(const GemmOperand& op, const 
 template <int BN, int BK, bool A_MN, bool B_MN, int EPI = 0, int CG = 1, bool HALO = false, int EW = kEpiWarps>
 __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   using S = GemmSmem<BN, BK, A_MN, B_MN, EPI, CG, HALO, EW>;
-  static_assert(EW == 8 || (EW == 16 && EPI == 1), "16 epilogue warps: linear-layer epilogue only");
+  static_assert(EW == 8 || (EW == 16 && EPI >= 1), "16 epilogue warps: linear-layer / 1x1-convolution epilogues only");
   constexpr int STAGES = S::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));

@@ -110,6 +110,8 @@ static bool pair_eligible(const GemmParams& p, int BN, int BK, bool a_mn) {
 
 static int launch_gemm(const GemmParams& p, int BN, int BK, bool a_mn, bool b_mn, cudaStream_t st, int epi = 0, int cg = 1,
                        bool halo = false, int ew = 8) {
+  if (ew == 16 && epi == 2 && cg == 1 && BN == 256 && BK == 64 && !a_mn && !b_mn && !halo)   // K-small 1x1 convolutions with statistics
+    return launch_gemm_t<256, 64, false, false, 2, 1, false, 16>(p, st);
   if (ew == 16 && epi == 1 && BN == 256 && BK == 64 && !a_mn && !halo) {   // epilogue-bound linear launches (GELU / gates)
     if (cg == 2) return b_mn ? launch_gemm_t<256, 64, false, true, 1, 2, false, 16>(p, st) : launch_gemm_t<256, 64, false, false, 1, 2, false, 16>(p, st);
     return b_mn ? launch_gemm_t<256, 64, false, true, 1, 1, false, 16>(p, st) : launch_gemm_t<256, 64, false, false, 1, 1, false, 16>(p, st);
@@ -360,7 +362,10 @@ extern "C" int passl_b200_gemm_bf16_ex(const void* A, const void* B, void* out, 
   // 16 epilogue warps (3 pipeline stages, accumulator read in place): fc2-dgrad with the GELU' gate 647 -> 801 TF/s at the CLIP
   // batch, 597 -> 760 at the MAE decoder's; fc1 forward (+GELU, saved pre-activation) gains only with a short K loop (K = 512:
   // 746 -> 783, K = 768: 940 -> 917), `profiles/r02_vit_gemm_probe_ew16.txt`
-  const bool use16 = ew16 && ((aux && aux_mode >= 2) || ((act == ACT_GELU || act == ACT_QUICKGELU) && (K < 768 || (heavy_pair_ok && cg == 2))));
+  // (also the 1x1 convolutions with BatchNorm statistics and a K loop of <= 4 iterations: one MMA group per tile, the epilogue is all
+  // there is)
+  const bool use16 = ew16 && ((aux && aux_mode >= 2) || ((act == ACT_GELU || act == ACT_QUICKGELU) && (K < 768 || (heavy_pair_ok && cg == 2))) ||
+                              (epi == 2 && cg == 1 && p.k_iters <= 4));
   return launch_gemm(p, BN, 64, a_mn_major != 0, b_mn_major != 0, (cudaStream_t)stream, epi, cg, false, use16 ? 16 : 8);
 }
 
