@@ -18,6 +18,8 @@ binding roofline; `roofline_infonce`: the fused InfoNCE kernel (MoCo C3 shape) a
 BASELINE's metric; `cpu_baseline`: the oracle port of BASELINE configs[0] (MoCo v2 bs 16) timed on this box's host cores.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -604,10 +606,27 @@ def main():
     ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints "NCCL version ..." from its C side at
+    # communicator creation): everything goes to stderr while the run is in progress, the real stdout comes back for the result line.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    buf = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(buf):
+            if args.impl == "reference":
+                run_reference(args)
+            else:
+                run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    out = [l for l in buf.getvalue().splitlines() if l.strip()]
+    for l in out[:-1]:
+        print(l, file=sys.stderr)
+    if out:
+        print(out[-1], flush=True)
 
 
 if __name__ == "__main__":
