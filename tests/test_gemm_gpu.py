@@ -176,3 +176,44 @@ def test_gemm_cta_pair(b_t):
     out = K_.gemm(a2, w2.t().contiguous() if b_t else w2, b_t=b_t, bias=bias, residual=res)
     bad, msg = _err_report(out, a2.float() @ w2.float().t() + bias + res.float(), "pair + residual")
     assert not bad, msg
+
+
+@pytest.mark.parametrize("K", [128, 256, 768])
+def test_gemm_sixteen_epilogue_warps(K):
+    """Large-M launches on 256-wide tiles that take the 16-epilogue-warp instantiations (gemm.cuh EW = 16): GELU + saved
+    pre-activation (K < 768 single CTA, K >= 768 CTA pair), the GELU' / QuickGELU' gates in both weight layouts, and the K-small
+    1x1-convolution form with BatchNorm column statistics.  M is not a multiple of 128 and the number of row blocks is odd."""
+    from passl_b200 import kernels as K_
+    torch.manual_seed(K)
+    M, N = 128 * 150 + 40, 512
+    a = torch.randn(M, K, device="cuda").bfloat16()
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    y = a.float() @ w.float().t()
+    u = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    out = K_.gemm(a, w, bias=bias, act="gelu", preact_out=u)
+    bad, msg = _err_report(u, y + bias, "pre-activation")
+    assert not bad, msg
+    bad, msg = _err_report(out, torch.nn.functional.gelu(y + bias), "gelu")
+    assert not bad, msg
+    out = K_.gemm(a, w, bias=bias, act="quick_gelu")
+    bad, msg = _err_report(out, (y + bias) * torch.sigmoid(1.702 * (y + bias)), "quick_gelu")
+    assert not bad, msg
+    aux = torch.randn(M, N, device="cuda").bfloat16()
+    sg = torch.sigmoid(1.702 * aux.float())
+    for b_t in (False, True):
+        ww = w.t().contiguous() if b_t else w
+        out = K_.gemm(a, ww, b_t=b_t, aux=aux, aux_mode_name="gelu_grad")
+        bad, msg = _err_report(out, y * _gelu_grad(aux), "gelu_grad b_t=%s" % b_t)
+        assert not bad, msg
+        out = K_.gemm(a, ww, b_t=b_t, aux=aux, aux_mode_name="quick_gelu_grad")
+        bad, msg = _err_report(out, y * (sg * (1 + 1.702 * aux.float() * (1 - sg))), "quick_gelu_grad b_t=%s" % b_t)
+        assert not bad, msg
+    part = K_.stats_buffer(N, "cuda")
+    out2 = K_.gemm(a, w, col_stats=part)                     # 1x1-convolution form: statistics of the stored bf16 values
+    bad, msg = _err_report(out2, y, "stats output")
+    assert not bad, msg
+    o = out2.float()
+    cs, cq = part[:, 0].sum(0), part[:, 1].sum(0)
+    assert torch.allclose(cs, o.sum(0), rtol=1e-3, atol=0.5), (cs - o.sum(0)).abs().max()
+    assert torch.allclose(cq, (o * o).sum(0), rtol=1e-3, atol=2.0), (cq - (o * o).sum(0)).abs().max()
