@@ -1,0 +1,18 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 200 python -m pytest tests/test_conv_gpu.py -x -q -m gpu --timeout 100 --timeout-method=thread > gpurun_out/r02_test_resident.log 2>&1; rc=$?; echo "conv tests rc=$rc"; tail -5 gpurun_out/r02_test_resident.log
+if [ $rc -ne 0 ]; then exit 0; fi
+python - <<'PY'
+import torch, sys
+sys.path.insert(0,'.')
+from passl_b200 import kernels as K
+def timeit(fn, iters=10):
+    for _ in range(3): fn()
+    torch.cuda.synchronize(); s,e=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters): fn()
+    e.record(); torch.cuda.synchronize(); return s.elapsed_time(e)/iters
+x=torch.randn(1024,56,56,64,device='cuda').bfloat16(); w=(torch.randn(64,3,3,64,device='cuda')/24).bfloat16()
+y=K.conv2d_fwd(x,w,stride=1,pad=1); dy=torch.randn_like(y)
+print("conv3x3 64ch 56x56 B=1024: fwd %.1f us, dgrad %.1f us"%(timeit(lambda: K.conv2d_fwd(x,w,stride=1,pad=1,out=y))*1e3, timeit(lambda: K.conv2d_dgrad(dy,w,tuple(x.shape),stride=1,pad=1))*1e3))
+PY
