@@ -576,9 +576,13 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tcgen05_kernel(const __g
     // a box is STAGED (packed into the next free 2 KB tile) and later COMMITTED (proxy fence + TMA store): the arithmetic that
     // follows the staging (activation of the saved pre-activation, column statistics) runs between the two, so that the fence
     // finds the shared-memory writes already performed
+    // HALO tiles (16 x 8 pixels of one image): this warp's 32 accumulator rows are the 4 x 8 pixel box at tile rows 4q .. 4q + 3, so
+    // the same dense staging tile leaves through a 4-D TMA store {32 ch, 8, 4, 1} of the NHWC output — no pixel addressing
+    int hal_n0 = 0, hal_h0 = 0, hal_w0 = 0;
+    bool hal_row_ok = true;
     auto stage_box = [&](const float (&f)[32], int row) -> uint32_t {
       const uint32_t buf = stg0 + (nbuf & nalt) * 2048u;
-      const bool zero_row = EPI == 2 && row + (int)lane >= p.M;   // rows outside the tensor must not reach the statistics
+      const bool zero_row = EPI == 2 && (HALO ? !hal_row_ok : row + (int)lane >= p.M);   // rows outside the tensor must not reach the statistics
       // the store that last used this tile has read it (two boxes ago when the tiles alternate)
       if (lane == 0) {
         if (nalt) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -602,9 +606,14 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tcgen05_kernel(const __g
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(reinterpret_cast<uint64_t>(map)),
-                     "r"(col), "r"(row), "r"(buf)
-                     : "memory");
+        if constexpr (HALO)
+          asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                       "r"(col), "r"(hal_w0), "r"(hal_h0 + (int)q * 4), "r"(hal_n0), "r"(buf)
+                       : "memory");
+        else
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                       "r"(col), "r"(row), "r"(buf)
+                       : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     };
@@ -639,6 +648,11 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tcgen05_kernel(const __g
       const uint32_t acc_phase = (it >> 1) & 1;
       const int row0 = m_blk * 128 + (int)q * 32;
       const int col0 = n_blk * BN;
+      if constexpr (HALO) {
+        decode_patch(p.geom, m_blk, hal_n0, hal_h0, hal_w0);
+        const int r_ = (int)q * 32 + (int)lane;
+        hal_row_ok = hal_n0 < p.geom.Nimg && hal_h0 + (r_ >> 3) < p.geom.Ho && hal_w0 + (r_ & 7) < p.geom.Wo;
+      }
       if (EPI == 2 && n_blk != prev_nblk) {
         if (prev_nblk >= 0) flush_stats(prev_nblk);
         prev_nblk = n_blk;

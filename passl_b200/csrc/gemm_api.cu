@@ -116,6 +116,13 @@ static int launch_gemm(const GemmParams& p, int BN, int BK, bool a_mn, bool b_mn
     if (cg == 2) return b_mn ? launch_gemm_t<256, 64, false, true, 1, 2, false, 16>(p, st) : launch_gemm_t<256, 64, false, false, 1, 2, false, 16>(p, st);
     return b_mn ? launch_gemm_t<256, 64, false, true, 1, 1, false, 16>(p, st) : launch_gemm_t<256, 64, false, false, 1, 1, false, 16>(p, st);
   }
+  if (halo && epi >= 1) {      // halo tiles whose 4 x 8 pixel boxes leave through 4-D TMA stores (no residual / gate operand)
+    if (BK != 64 || a_mn || b_mn) return PB_ERR_UNSUPPORTED;
+    if (BN == 64 && cg == 1) return epi == 2 ? launch_gemm_t<64, 64, false, false, 2, 1, true>(p, st) : launch_gemm_t<64, 64, false, false, 1, 1, true>(p, st);
+    if (BN == 256 && cg == 1) return epi == 2 ? launch_gemm_t<256, 64, false, false, 2, 1, true>(p, st) : launch_gemm_t<256, 64, false, false, 1, 1, true>(p, st);
+    if (BN == 256 && cg == 2) return epi == 2 ? launch_gemm_t<256, 64, false, false, 2, 2, true>(p, st) : launch_gemm_t<256, 64, false, false, 1, 2, true>(p, st);
+    return PB_ERR_UNSUPPORTED;
+  }
   if (halo) {      // 3x3 stride-1 convolutions with the halo-box A operand (gemm.cuh HALO)
     if (BK != 64 || a_mn || b_mn || epi != 0) return PB_ERR_UNSUPPORTED;
     if (BN == 256) return cg == 2 ? launch_gemm_t<256, 64, false, false, 0, 2, true>(p, st) : launch_gemm_t<256, 64, false, false, 0, 1, true>(p, st);
@@ -215,6 +222,20 @@ static bool conv_halo_ok(int H, int W, int ntaps, const signed char* dh, const s
   if (u_halo < 0.95 * u_old) return false;
   dh0 = hmin; dw0 = wmin;
   return true;
+}
+// HALO tiles with a TMA-store epilogue: NHWC output as a 4-D tensor map, box {32 ch, 8, 4, 1} (= one warp's 32 accumulator rows).
+// Returns the epilogue variant (1 plain, 2 with column statistics) or 0 when the pixel-addressed epilogue has to stay.
+static int halo_lean_epi(GemmParams& p, int BN, int cg, void* out, int N, int Ho, int Wo, int C, const void* residual, int act,
+                         float* col_sum) {
+  static int en = -1;
+  if (en < 0) { const char* e = getenv("PASSL_B200_CONV_HALO_TMA_STORE"); en = (e && !atoi(e)) ? 0 : 1; }
+  if (!en || residual || act > ACT_RELU || (C % 8) || (reinterpret_cast<uintptr_t>(out) & 15)) return 0;
+  if (!((BN == 64 && cg == 1) || BN == 256)) return 0;
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)N};
+  uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)Wo * C * 2, (uint64_t)Ho * Wo * C * 2};
+  uint32_t box[4] = {32, (uint32_t)kHaloTW, 4, 1};
+  if (make_tmap_bf16(&p.out_map, out, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B) != PB_OK) return 0;
+  return col_sum ? 2 : 1;
 }
 static void halo_geom(PatchGeom& g, int Nimg, int Ho, int Wo) {
   g.Nimg = Nimg; g.Ho = Ho; g.Wo = Wo;
@@ -416,7 +437,8 @@ static int conv_fwd_impl(const void* x, const void* w, void* out, int N, int H, 
   if (rc) return rc;
   set_epilogue(p, out, Cout, 0, 0, bias, residual, act, 1.f, col_sum, col_sqsum);
   p.out_pixel = 1; p.OH = Ho; p.OW = Wo; p.osh = 1; p.osw = 1; p.oh0 = 0; p.ow0 = 0;
-  return launch_gemm(p, BN, 64, false, false, (cudaStream_t)stream, 0, cg, halo);
+  const int hepi = halo ? halo_lean_epi(p, BN, cg, out, N, Ho, Wo, Cout, residual, act, col_sum) : 0;
+  return launch_gemm(p, BN, 64, false, false, (cudaStream_t)stream, hepi, cg, halo);
 }
 
 extern "C" int passl_b200_conv2d_fwd_bf16(const void* x, const void* w, void* out, int N, int H, int W, int Cin,
@@ -548,7 +570,8 @@ extern "C" int passl_b200_conv2d_dgrad_bf16(const void* dy, const void* w, void*
     if (rc) return rc;
     set_epilogue(p, dx, Cin, 0, 0, nullptr, accumulate ? dx : nullptr, ACT_NONE, 1.f, nullptr, nullptr);
     p.out_pixel = 1; p.OH = H; p.OW = W; p.osh = stride; p.osw = stride; p.oh0 = k.a; p.ow0 = k.b;
-    rc = launch_gemm(p, BN, 64, false, false, st, 0, cg, halo);
+    const int hepi = halo ? halo_lean_epi(p, BN, cg, dx, N, H, W, Cin, accumulate ? dx : nullptr, ACT_NONE, nullptr) : 0;
+    rc = launch_gemm(p, BN, 64, false, false, st, hepi, cg, halo);
     if (rc) return rc;
     wt += (size_t)Cin * k.ntaps * Cout;
   }
