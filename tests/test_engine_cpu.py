@@ -164,3 +164,20 @@ def test_profiler_options_and_step_window(tmp_path):
     with pytest.raises(SystemExit):
         q.step()
     StepProfiler(None).step()                                                             # disabled: no-op
+
+
+def test_bench_prints_exactly_one_json_line_on_stdout():
+    """bench.py's contract: ONE JSON line on stdout (library banners and progress go to stderr).  The reference arm of a config
+    without a CPU port is the cheapest path through main()."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--config", "c4"], capture_output=True,
+                       text=True, cwd=root, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and "unavailable" in d
